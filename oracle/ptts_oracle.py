@@ -1,0 +1,421 @@
+"""CPU oracle for the Pocket TTS generation hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain f32 restatement (torch CPU tensor ops, no nn.Module, no
+CUDA) of the reference's Candle CPU algorithm for one stream:
+FlowLM AR step -> LSD flow head -> streaming Mimi decode.  Only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` may import it; the product (pocket_tts_b200/) never does.
+
+Each function cites the reference lines it follows ("RS" =
+/root/reference/crates/pocket-tts/src, "PY" =
+/root/reference/python-reference/pocket_tts).  Where RS and PY differ, RS wins
+(deviations D1-D4).
+
+Parity pin: `tests/golden/make_golden.py` ran the *unmodified* PY package (the
+implementation RS is itself parity-tested against, RS tests/parity_tests.rs) on
+the same seeded weights and stored its outputs in `tests/golden/*.npz`;
+`tests/test_oracle_golden.py` checks this file against them (gelu="erf" for the
+untouched PY run, gelu="tanh" for the PY run with only D1 patched in).  The RS
+in-tree known-answer tests (variance-RMSNorm mlp.rs:394-417, mask sdpa.rs:287-345,
+text-prep tts_model.rs:1243-1290) are checked in `tests/test_oracle_kat.py`.
+The reference pins no FlowLM latent or EOS index with real weights (the
+checkpoint is gated), so with real weights parity is unpinned; with seeded
+random weights it is pinned as above.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+torch.set_grad_enabled(False)
+
+D_MODEL, N_HEADS, HEAD_DIM, N_LAYERS = 1024, 16, 64, 6
+LDIM, FLOW_DIM, FLOW_DEPTH = 32, 512, 6
+MIMI_DIM, MIMI_HEADS, MIMI_LAYERS, MIMI_CONTEXT = 512, 8, 2, 250
+FRAME_SAMPLES = 1920
+
+
+def to_torch(weights: dict[str, np.ndarray]) -> dict[str, torch.Tensor]:
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in weights.items()}
+
+
+# --------------------------------------------------------------------------- primitives
+def layer_norm(x, w, b, eps):
+    """candle_nn::LayerNorm via RS modules/mlp.rs:29-58: biased variance, eps inside sqrt."""
+    mean = x.mean(-1, keepdim=True)
+    var = ((x - mean) ** 2).mean(-1, keepdim=True)
+    y = (x - mean) / torch.sqrt(var + eps)
+    if w is not None:
+        y = y * w + b
+    return y
+
+
+def variance_rms_norm(x, alpha, eps=1e-5):
+    """RS modules/mlp.rs:18-26 (PY modules/mlp.py:20-25): x * alpha * rsqrt(var_unbiased(x) + eps);
+    no mean subtraction on x itself, Bessel-corrected variance."""
+    var = x.var(dim=-1, unbiased=True, keepdim=True)
+    return x * (alpha * torch.rsqrt(var + eps))
+
+
+def gelu(x, kind: str):
+    """D1: RS transformer.rs:85 `.gelu()` is Candle's tanh approximation; PY uses erf (mimi_transformer.py:174)."""
+    if kind == "tanh":
+        return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * x * (1.0 + 0.044715 * x * x)))
+    return F.gelu(x)
+
+
+def silu(x):
+    return x / (1.0 + torch.exp(-x))
+
+
+def elu(x):
+    """RS models/seanet.rs:36 `x.elu(1.0)`."""
+    return torch.where(x > 0, x, torch.exp(torch.clamp(x, max=0.0)) - 1.0)
+
+
+def rope(q, k, offset: int, max_period: float = 10000.0):
+    """RS modules/rope.rs:9-60.  q,k: [T, H, D]; interleaved pairs (2i, 2i+1) rotated by
+    (offset+t) * max_period^(-2i/D)."""
+    T, H, D = q.shape
+    half = D // 2
+    ds = torch.arange(half, dtype=torch.float32)
+    inv_freq = torch.exp(ds * (-math.log(max_period) * 2.0 / D))
+    ts = (torch.arange(T, dtype=torch.float32) + float(offset)).view(T, 1, 1)
+    ang = inv_freq.view(1, 1, half) * ts
+    cos, sin = torch.cos(ang), torch.sin(ang)
+
+    def rot(x):
+        x = x.reshape(T, H, half, 2)
+        xr, xi = x[..., 0], x[..., 1]
+        return torch.stack([xr * cos - xi * sin, xr * sin + xi * cos], dim=-1).reshape(T, H, D)
+
+    return rot(q), rot(k)
+
+
+def attention_mask(num_q: int, k_len: int, causal: bool, context: int | None):
+    """RS modules/sdpa.rs:129-171 generate_mask_chunk with start_q=0, total_q_len=num_q."""
+    shift = max(k_len - num_q, 0)
+    pos_q = (torch.arange(num_q) + shift).view(num_q, 1)
+    pos_k = torch.arange(k_len).view(1, k_len)
+    mask = torch.zeros(num_q, k_len)
+    if causal:
+        mask = torch.where(pos_k > pos_q, torch.tensor(float("-inf")), mask)
+    if context is not None:
+        mask = torch.where(pos_k <= pos_q - context, torch.tensor(float("-inf")), mask)
+    return mask
+
+
+def sdpa(q, k, v, context: int | None):
+    """RS modules/sdpa.rs:36-82 naive path.  q [H,Tq,D], k,v [H,Tk,D]; causal always (attention.rs:231)."""
+    scale = 1.0 / math.sqrt(q.shape[-1])
+    scores = torch.matmul(q, k.transpose(1, 2)) * scale
+    tq, tk = q.shape[1], k.shape[1]
+    skip = tq == 1 and (context is None or tk <= context)  # sdpa.rs:4-18
+    if not skip:
+        scores = scores + attention_mask(tq, tk, True, context)
+    return torch.matmul(torch.softmax(scores, dim=-1), v)
+
+
+# --------------------------------------------------------------------------- transformer
+@dataclass
+class AttnState:
+    """RS voice_state.rs:16-22 AttentionCursor + k_buf/v_buf; chronological order kept explicitly
+    (the ring of attention.rs:167-264 holds exactly the last `context` rows)."""
+    k: list = field(default_factory=list)  # per layer [H, L, D]
+    v: list = field(default_factory=list)
+    pos: int = 0
+
+    def clone(self):
+        return AttnState([t.clone() for t in self.k], [t.clone() for t in self.v], self.pos)
+
+
+def transformer_forward(W, prefix: str, x, st: AttnState, n_layers: int, n_heads: int,
+                        context: int | None, layer_scale: bool, gelu_kind: str, trace: dict | None = None):
+    """RS models/transformer.rs:66-90,136-153 + modules/attention.rs:104-283.  x: [T, d]."""
+    T, d = x.shape
+    hd = d // n_heads
+    pos = st.pos
+    if not st.k:
+        st.k = [torch.zeros(n_heads, 0, hd) for _ in range(n_layers)]
+        st.v = [torch.zeros(n_heads, 0, hd) for _ in range(n_layers)]
+    for l in range(n_layers):
+        p = f"{prefix}.layers.{l}."
+        h = layer_norm(x, W[p + "norm1.weight"], W[p + "norm1.bias"], 1e-5)
+        proj = h @ W[p + "self_attn.in_proj.weight"].T  # [T, 3d] -> (t, 3, h, d): attention.rs:132-135
+        packed = proj.view(T, 3, n_heads, hd)
+        q, k, v = packed[:, 0], packed[:, 1], packed[:, 2]
+        q, k = rope(q, k, pos)
+        q, k, v = q.transpose(0, 1), k.transpose(0, 1), v.transpose(0, 1)  # [H, T, D]
+        kc = torch.cat([st.k[l], k], dim=1)
+        vc = torch.cat([st.v[l], v], dim=1)
+        a = sdpa(q, kc, vc, context)  # [H, T, D]
+        if context is not None:  # ring eviction attention.rs:233-264: keep last `context` rows
+            kc, vc = kc[:, -context:], vc[:, -context:]
+        st.k[l], st.v[l] = kc, vc
+        a = a.transpose(0, 1).reshape(T, d)
+        if trace is not None:
+            trace[f"{prefix}.l{l}.attn"] = a.clone()
+        upd = a @ W[p + "self_attn.out_proj.weight"].T
+        if layer_scale:
+            upd = upd * W[p + "layer_scale_1.scale"]
+        x = x + upd
+        h = layer_norm(x, W[p + "norm2.weight"], W[p + "norm2.bias"], 1e-5)
+        upd = gelu(h @ W[p + "linear1.weight"].T, gelu_kind) @ W[p + "linear2.weight"].T
+        if layer_scale:
+            upd = upd * W[p + "layer_scale_2.scale"]
+        x = x + upd
+        if trace is not None:
+            trace[f"{prefix}.l{l}.out"] = x.clone()
+    st.pos = pos + T
+    return x
+
+
+# --------------------------------------------------------------------------- flow head
+def timestep_embed(W, idx: int, t: float):
+    """RS modules/mlp.rs:84-133 TimestepEmbedder (freq size 256, max_period 1e4)."""
+    p = f"flow_lm.flow_net.time_embed.{idx}.mlp."
+    half = 128
+    freqs = torch.exp(torch.arange(half, dtype=torch.float32) * (-math.log(10000.0) / half))
+    args = torch.tensor([[t]], dtype=torch.float32) * freqs
+    x = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    x = x @ W[p + "0.weight"].T + W[p + "0.bias"]
+    x = silu(x)
+    x = x @ W[p + "2.weight"].T + W[p + "2.bias"]
+    return variance_rms_norm(x, W[p + "3.alpha"], 1e-5)
+
+
+def compute_time_embeddings(W, num_steps: int):
+    """RS modules/mlp.rs:296-319: te[s] = (TE0(s/S) + TE1((s+1)/S)) / 2  -> [S, 512]."""
+    out = []
+    for i in range(num_steps):
+        s, t = i / num_steps, (i + 1) / num_steps
+        out.append((timestep_embed(W, 0, s) + timestep_embed(W, 1, t)) / 2.0)
+    return torch.cat(out, dim=0)
+
+
+def flow_head(W, h_last, x0, time_emb, trace: dict | None = None):
+    """RS flow_lm.rs:156-161 + modules/mlp.rs:275,322-383 + lsd_decode flow_lm.rs:7-22.
+    h_last [1024] (post out_norm), x0 [32] noise, time_emb [S,512] -> latent [32]."""
+    f = "flow_lm.flow_net."
+    c = h_last @ W[f + "cond_embed.weight"].T + W[f + "cond_embed.bias"]  # [512]
+    S = time_emb.shape[0]
+    cur = x0.clone()
+    for s in range(S):
+        y = silu(time_emb[s] + c)
+        x = cur @ W[f + "input_proj.weight"].T + W[f + "input_proj.bias"]
+        for i in range(FLOW_DEPTH):
+            q = f + f"res_blocks.{i}."
+            mod = y @ W[q + "adaLN_modulation.1.weight"].T + W[q + "adaLN_modulation.1.bias"]
+            shift, scale, gate = mod[:FLOW_DIM], mod[FLOW_DIM:2 * FLOW_DIM], mod[2 * FLOW_DIM:]
+            h = layer_norm(x, W[q + "in_ln.weight"], W[q + "in_ln.bias"], 1e-6)
+            h = h * (1.0 + scale) + shift
+            h = silu(h @ W[q + "mlp.0.weight"].T + W[q + "mlp.0.bias"])
+            h = h @ W[q + "mlp.2.weight"].T + W[q + "mlp.2.bias"]
+            x = x + gate * h
+        q = f + "final_layer."
+        mod = y @ W[q + "adaLN_modulation.1.weight"].T + W[q + "adaLN_modulation.1.bias"]
+        shift, scale = mod[:FLOW_DIM], mod[FLOW_DIM:]
+        h = layer_norm(x, None, None, 1e-6) * (1.0 + scale) + shift
+        vflow = h @ W[q + "linear.weight"].T + W[q + "linear.bias"]
+        cur = cur + vflow / S
+        if trace is not None:
+            trace[f"flow.step{s}.v"] = vflow.clone()
+    return cur
+
+
+def flowlm_step(W, latent_in, st: AttnState, x0, time_emb, gelu_kind="tanh", trace: dict | None = None):
+    """RS models/flow_lm.rs:98-164 with empty text_embeddings (tts_model.rs:1013).
+    Returns (next_latent [32], eos_logit float)."""
+    x = latent_in.view(1, LDIM) @ W["flow_lm.input_linear.weight"].T
+    x = transformer_forward(W, "flow_lm.transformer", x, st, N_LAYERS, N_HEADS, None, False, gelu_kind, trace)
+    h = layer_norm(x, W["flow_lm.out_norm.weight"], W["flow_lm.out_norm.bias"], 1e-5)[-1]
+    eos = float(h @ W["flow_lm.out_eos.weight"][0] + W["flow_lm.out_eos.bias"][0])
+    if trace is not None:
+        trace["flowlm.h"] = h.clone()
+    return flow_head(W, h, x0, time_emb, trace), eos
+
+
+def flowlm_prefill(W, rows, st: AttnState, gelu_kind="tanh"):
+    """RS tts_model.rs:958-964 (text) and :580-599 (voice): transformer over T rows, output discarded."""
+    transformer_forward(W, "flow_lm.transformer", rows, st, N_LAYERS, N_HEADS, None, False, gelu_kind)
+
+
+def embed_tokens(W, tokens):
+    """RS conditioners/text.rs:289-303: LUT gather."""
+    idx = torch.as_tensor(np.asarray(tokens), dtype=torch.long)
+    return W["flow_lm.conditioner.embed.weight"][idx]
+
+
+# --------------------------------------------------------------------------- Mimi decode
+@dataclass
+class MimiState:
+    attn: AttnState = field(default_factory=AttnState)
+    up_partial: torch.Tensor | None = None
+    conv_prev: dict = field(default_factory=dict)
+    convtr_partial: dict = field(default_factory=dict)
+
+
+def streaming_conv1d(W, name: str, x, st: MimiState):
+    """RS modules/conv.rs:90-136, stride 1, dilation 1, pad_mode constant.  x [Cin, T]."""
+    w, b = W[name + ".conv.weight"], W[name + ".conv.bias"]
+    k = w.shape[-1]
+    if k > 1:
+        prev = st.conv_prev.get(name)
+        if prev is None:
+            prev = torch.zeros(x.shape[0], k - 1)
+        xp = torch.cat([prev, x], dim=1)
+        st.conv_prev[name] = xp[:, -(k - 1):].clone()
+    else:
+        xp = x
+    return F.conv1d(xp.unsqueeze(0), w, b).squeeze(0)
+
+
+def streaming_convtr1d(W, name: str, x, st: MimiState, stride: int):
+    """RS modules/conv.rs:219-267: overlap-add with carried tail; bias removed from the tail."""
+    w, b = W[name + ".convtr.weight"], W[name + ".convtr.bias"]
+    k = w.shape[-1]
+    y = F.conv_transpose1d(x.unsqueeze(0), w, b, stride=stride).squeeze(0)
+    trim = k - stride
+    part = st.convtr_partial.get(name)
+    if part is not None:
+        y[:, :trim] = y[:, :trim] + part
+    st.convtr_partial[name] = (y[:, -trim:] - b.view(-1, 1)).clone()
+    return y[:, :-trim]
+
+
+def mimi_decode_step(W, latent, st: MimiState, gelu_kind="tanh", trace: dict | None = None):
+    """RS tts_model.rs:1033-1038 (de-norm, quantize) + models/mimi.rs:143-157 decode_from_latent.
+    latent [32] -> pcm [1920]."""
+    z = latent * W["flow_lm.emb_std"] + W["flow_lm.emb_mean"]
+    quant = W["mimi.quantizer.output_proj.weight"][:, :, 0] @ z  # [512]  mimi.rs:32-36
+    # ConvTrUpsample1d: depthwise k=32 s=16, no bias (conv.rs:314-346 -> :219-267)
+    wup = W["mimi.upsample.convtr.convtr.weight"][:, 0, :]  # [512, 32]
+    y = quant.view(-1, 1) * wup
+    if st.up_partial is not None:
+        y[:, :16] = y[:, :16] + st.up_partial
+    st.up_partial = y[:, 16:].clone()
+    emb = y[:, :16]  # [512, 16]
+    if trace is not None:
+        trace["mimi.quantized"] = quant.clone()
+        trace["mimi.after_upsample"] = emb.clone()
+    # ProjectedTransformer: [C,T] -> [T,C], no in/out projection since 512 == 512 (transformer.rs:227-251)
+    x = transformer_forward(W, "mimi.decoder_transformer.transformer", emb.T.contiguous(), st.attn,
+                            MIMI_LAYERS, MIMI_HEADS, MIMI_CONTEXT, True, gelu_kind, trace)
+    x = x.T.contiguous()  # [512, 16]
+    if trace is not None:
+        trace["mimi.after_decoder_transformer"] = x.clone()
+    # SEANetDecoder (seanet.rs:309-402)
+    d = "mimi.decoder.model."
+    x = streaming_conv1d(W, d + "0", x, st)
+    for idx, stride in ((2, 6), (5, 5), (8, 4)):
+        x = streaming_convtr1d(W, d + str(idx), elu(x), st, stride)
+        if trace is not None:
+            trace[f"seanet.convtr{idx}"] = x.clone()
+        r = d + f"{idx + 1}.block."
+        v = streaming_conv1d(W, r + "1", elu(x), st)
+        v = streaming_conv1d(W, r + "3", elu(v), st)
+        x = x + v  # seanet.rs:82-88
+        if trace is not None:
+            trace[f"seanet.res{idx + 1}"] = x.clone()
+    x = streaming_conv1d(W, d + "11", elu(x), st)
+    return x.reshape(-1)
+
+
+# --------------------------------------------------------------------------- host control (A17)
+def strip_pause_markers(text: str) -> str:
+    """RS pause.rs:34-37 EXPLICIT_PAUSE_REGEX (case-sensitive): `[pause:Xms|Xs]` -> single space."""
+    import re
+    return re.sub(r"\[pause:(\d+(?:\.\d+)?)(ms|s)\]", " ", text)
+
+
+def prepare_text_prompt(text: str) -> str:
+    """RS tts_model.rs:1194-1227."""
+    text = strip_pause_markers(text).strip()
+    if not text:
+        return "."
+    text = text.replace("\n", " ").replace("\r", " ").replace("  ", " ")
+    word_count = len(text.split())
+    if not text[0].isupper():
+        text = text[0].upper() + text[1:]
+    if text[-1].isalnum():
+        text += "."
+    if word_count < 5:
+        text = " " * 8 + text
+    return text
+
+
+def estimate_frames_after_eos(text: str) -> int:
+    """RS tts_model.rs:1230-1237."""
+    return 5 if len(text.split()) <= 4 else 3
+
+
+def max_gen_len(prepared_text: str) -> int:
+    """D3: RS tts_model.rs:968 `(words + 2) * 13`."""
+    return (len(prepared_text.split()) + 2) * 13
+
+
+def voice_state_from_prompt(W, audio_prompt, gelu_kind="tanh") -> AttnState:
+    """RS tts_model.rs:490-501,580-599: FlowLM prefill over the [T,1024] conditioning rows."""
+    st = AttnState()
+    flowlm_prefill(W, torch.as_tensor(audio_prompt).float(), st, gelu_kind)
+    return st
+
+
+def generate_segment(W, voice: AttnState, tokens, noise, max_len: int, frames_after_eos: int,
+                     eos_threshold: float, lsd_steps: int = 1, gelu_kind="tanh", decode_audio=True,
+                     teacher_latents=None):
+    """RS tts_model.rs:935-1071 generate_stream_segment with injected noise [max_len, 32]
+    (already scaled by sqrt(temp); the reference draws it at flow_lm.rs:148-153).
+    D2: the frame at step == eos_step + frames_after_eos is emitted, then the stream stops.
+    Returns dict(latents [F,32], eos_logits [F], pcm [F,1920], eos_step, frames)."""
+    st = voice.clone()
+    flowlm_prefill(W, embed_tokens(W, tokens), st, gelu_kind)
+    time_emb = compute_time_embeddings(W, lsd_steps)
+    mimi = MimiState()
+    cur = W["flow_lm.bos_emb"].clone()  # D4
+    noise = torch.as_tensor(noise).float()
+    lat, logits, pcm = [], [], []
+    eos_step = None
+    for step in range(max_len):
+        nxt, logit = flowlm_step(W, cur, st, noise[step], time_emb, gelu_kind)
+        lat.append(nxt)
+        logits.append(logit)
+        if decode_audio:
+            pcm.append(mimi_decode_step(W, nxt, mimi, gelu_kind))
+        if logit > eos_threshold and eos_step is None:
+            eos_step = step
+        cur = nxt if teacher_latents is None else torch.as_tensor(teacher_latents[step]).float()
+        if eos_step is not None and step >= eos_step + frames_after_eos:
+            break
+    return dict(
+        latents=torch.stack(lat).numpy(),
+        eos_logits=np.asarray(logits, dtype=np.float32),
+        pcm=torch.stack(pcm).numpy() if pcm else np.zeros((0, FRAME_SAMPLES), np.float32),
+        eos_step=-1 if eos_step is None else eos_step,
+        frames=len(lat),
+    )
+
+
+# --------------------------------------------------------------------------- int8 numerics (row Q)
+def quantize_per_tensor(w: np.ndarray, num_levels: int = 256):
+    """RS quantize.rs:65-94: scale = absmax/127, q = clamp(round(w/scale), -127, 127).
+    Candle's `round` is round-half-away-from-zero.  Returns (q int8, scale f32)."""
+    w = np.asarray(w, dtype=np.float32)
+    half = np.float32(num_levels // 2)
+    amax = np.float32(np.abs(w).max()) if w.size else np.float32(0)
+    scale = np.float32(amax / (half - 1)) if amax > 0 else np.float32(1.0)
+    r = w / scale
+    q = np.sign(r) * np.floor(np.abs(r) + np.float32(0.5))
+    q = np.clip(q, -(half - 1), half - 1)
+    return q.astype(np.int8), scale
+
+
+def should_quantize(name: str, numel: int) -> bool:
+    """RS quantize.rs:27-41,117-154: skip < 1024 elements and names containing embed/lut/out_proj/eos_head."""
+    if numel < 1024:
+        return False
+    return not any(s in name for s in ("embed", "lut", "out_proj", "eos_head"))
