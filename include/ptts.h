@@ -1,0 +1,159 @@
+/*
+ * ptts.h — C ABI of libptts_cuda.so, the B200 (sm_100a) engine for the Pocket TTS
+ * generation hot path: FlowLM autoregressive decode step, LSD flow head, streaming
+ * Mimi decoder.
+ *
+ * The reference (ykevinc/pocket-tts) has no FFI; its seam is the public Rust API of
+ * `TTSModel` (crates/pocket-tts/src/lib.rs:15-18).  Every entry point below names the
+ * reference function it replaces.  A Rust `pocket-tts-cuda` crate binds exactly these
+ * symbols; tests and bench.py bind them through ctypes.
+ *
+ * Conventions: all functions return 0 on success and a negative ptts_status otherwise;
+ * ptts_last_error() returns a NUL-terminated message for the calling thread's last
+ * failure.  Handles are opaque.  The library never frees caller memory; the caller
+ * frees library objects only through the *_destroy / *_close calls.  One engine owns
+ * one CUDA device and one stream set; an engine is not re-entrant (the Rust facade
+ * wraps it in a Mutex, harnesses use one thread per GPU).  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with PTTS_ERR_CUDA.
+ */
+#ifndef PTTS_H
+#define PTTS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTTS_ABI_VERSION 1
+
+typedef enum {
+  PTTS_OK = 0,
+  PTTS_ERR_INVALID = -1,   /* bad argument / unknown tensor / wrong shape */
+  PTTS_ERR_CUDA = -2,      /* CUDA runtime or driver error, or no device */
+  PTTS_ERR_CAPACITY = -3,  /* no free slot / KV capacity exceeded */
+  PTTS_ERR_STATE = -4      /* call not valid in the current state */
+} ptts_status;
+
+typedef enum { PTTS_F32 = 0, PTTS_BF16 = 1, PTTS_F16 = 2 } ptts_dtype;
+
+/* How GEMM weights are held in HBM.  PTTS_W_F16: 16-bit float operands, f32 accumulate
+ * (checkpoint values are bf16-representable, tts_model.py:143-145, and convert exactly).
+ * PTTS_W_INT8: per-tensor symmetric int8 with the reference's scheme and skip list
+ * (crates/pocket-tts/src/quantize.rs:27-41,65-94), dequantised in registers. */
+typedef enum { PTTS_W_F16 = 0, PTTS_W_INT8 = 1 } ptts_weight_mode;
+
+/* One named tensor in host memory, safetensors key + PyTorch layout
+ * (keys as built at crates/pocket-tts/src/tts_model.rs:296-409). */
+typedef struct {
+  const char* name;
+  ptts_dtype dtype;
+  int32_t ndim;
+  int64_t shape[4];
+  const void* data;
+} ptts_tensor_desc;
+
+typedef struct {
+  int32_t device;          /* CUDA ordinal */
+  int32_t max_slots;       /* concurrent streams held resident */
+  int32_t max_batch;       /* streams advanced per ptts_step call (<= max_slots) */
+  int32_t kv_capacity;     /* FlowLM KV rows per slot (text + generated frames) */
+  int32_t weight_mode;     /* ptts_weight_mode */
+  int32_t use_cuda_graph;  /* capture the decode step per batch bucket */
+  int32_t debug_gemm;      /* 0 = tcgen05 path; 1 = SIMT cross-check kernel (tests only) */
+  int32_t reserved[9];
+} ptts_engine_cfg;
+
+typedef struct ptts_engine ptts_engine;
+typedef struct ptts_voice ptts_voice;
+
+/* Per-stream generation parameters: the public fields of TTSModel the reference lets
+ * callers mutate (tts_model.rs:22-49) plus the per-segment values its host code derives
+ * (tts_model.rs:968-969). */
+typedef struct {
+  int32_t max_gen_len;       /* (words(prepared)+2)*13, tts_model.rs:968 */
+  int32_t frames_after_eos;  /* estimate_frames_after_eos, tts_model.rs:1230-1237 */
+  float eos_threshold;       /* config.rs:123, default -4.0 */
+  float temp;                /* config.rs:120, default 0.7; used only when noise == NULL */
+  uint64_t seed;             /* device Philox stream when noise == NULL */
+  const float* noise;        /* optional [max_gen_len, 32] injected x_0 per frame, already
+                                scaled by sqrt(temp) (reference draws it at flow_lm.rs:148-153) */
+} ptts_stream_params;
+
+const char* ptts_last_error(void);
+int32_t ptts_abi_version(void);
+
+/* Replaces TTSModel::load / load_with_params (tts_model.rs:59-86) after the host side has
+ * read the safetensors file: uploads and repacks every tensor into kernel layouts. */
+int32_t ptts_engine_create(const ptts_engine_cfg* cfg, const ptts_tensor_desc* weights, int32_t n_weights,
+                           ptts_engine** out);
+void ptts_engine_destroy(ptts_engine* e);
+
+/* Sets lsd_decode_steps (TTSModel field, tts_model.rs:28) and recomputes the hoisted time
+ * embeddings (SimpleMLPAdaLN::compute_time_embeddings, modules/mlp.rs:296-319). */
+int32_t ptts_engine_set_lsd_steps(ptts_engine* e, int32_t lsd_steps);
+
+/* Replaces TTSModel::get_voice_state_from_prompt_tensor (tts_model.rs:490-501, which runs
+ * run_flow_lm_prompt :580-599): FlowLM prefill over audio_prompt [T,1024] f32 (host);
+ * the resulting KV snapshot is immutable and shared by every stream opened with it. */
+int32_t ptts_voice_from_prompt(ptts_engine* e, const float* audio_prompt, int32_t n_rows, ptts_voice** out);
+void ptts_voice_destroy(ptts_engine* e, ptts_voice* v);
+int32_t ptts_voice_len(const ptts_voice* v);
+
+/* Replaces the head of TTSModel::generate_stream_segment (tts_model.rs:935-1004) for n
+ * streams at once: clone voice state, embed tokens (conditioners/text.rs:289-303), text
+ * prefill (tts_model.rs:958-964).  tokens are concatenated, token_offsets has n+1 entries.
+ * voices and params have n entries.  Writes n slot ids. */
+int32_t ptts_streams_open(ptts_engine* e, int32_t n, ptts_voice* const* voices, const int32_t* tokens,
+                          const int32_t* token_offsets, const ptts_stream_params* params, int32_t* slots_out);
+
+/* Replaces one iteration of the frame loop (tts_model.rs:1006-1070) for n slots:
+ * FlowLMModel::forward (flow_lm.rs:98-164) -> latent de-norm + Quantizer (tts_model.rs:1033-1038)
+ * -> MimiModel::decode_from_latent (mimi.rs:143-157) -> EOS bookkeeping (tts_model.rs:1055-1063).
+ * pcm_out [n,1920] f32 host (pinned or pageable) or NULL; finished[n] is 1 when the frame just
+ * produced is the stream's last (the frame itself is valid and emitted, D2 in SURVEY 8c).
+ * latent_out [n,32] and eos_logit_out [n] are optional parity taps. */
+int32_t ptts_step(ptts_engine* e, const int32_t* slots, int32_t n, float* pcm_out, uint8_t* finished,
+                  float* latent_out, float* eos_logit_out);
+
+/* Same step with every buffer resident on the device (no host copies, no sync): used to time the
+ * kernels alone.  pcm_dev may be NULL to keep the PCM in the engine's own buffer. */
+int32_t ptts_step_device(ptts_engine* e, const int32_t* slots, int32_t n);
+int32_t ptts_sync(ptts_engine* e);
+
+/* Teacher forcing for parity tests: overrides the latent fed back into FlowLM at the next
+ * step of `slot` (the reference feeds next_latent back at tts_model.rs:1065). */
+int32_t ptts_stream_set_feedback(ptts_engine* e, int32_t slot, const float* latent32);
+int32_t ptts_stream_close(ptts_engine* e, int32_t slot);
+int32_t ptts_stream_frames(ptts_engine* e, int32_t slot, int32_t* frames_out, int32_t* eos_step_out);
+
+/* Parity taps: copy a named intermediate of the last step for batch row `row`
+ * (e.g. "flowlm.h", "mimi.after_upsample", "mimi.after_decoder_transformer", "seanet.convtr2").
+ * Returns the number of floats written or a negative status. */
+int64_t ptts_debug_read(ptts_engine* e, const char* name, int32_t row, float* out, int64_t cap);
+
+/* Device-time accounting for bench.py: kernel launches issued by the engine since the last reset,
+ * and CUDA-event time (ms) of the stages of the most recent ptts_step_timed call. */
+int64_t ptts_launch_count(ptts_engine* e, int32_t reset);
+int32_t ptts_step_timed(ptts_engine* e, const int32_t* slots, int32_t n, float* stage_ms /*[8]*/);
+void* ptts_cuda_stream(ptts_engine* e);
+
+/* Isolated kernel entry points (tests/test_kernels_gpu.py): D[r,f] = sum_k A[r,k] * W[f,k] on
+ * host f32 buffers, run through the production GEMM (operands converted to f16).  mode 0 lets the
+ * engine choose the tiling, 1 forces activation-as-M, 2 forces weight-as-M (swap-AB);
+ * split_k > 1 exercises the atomic split-K epilogue. */
+int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const float* bias, float* d, int32_t rows,
+                       int32_t feats, int32_t k, int32_t mode, int32_t split_k, int32_t act, int32_t use_simt);
+/* Implicit-GEMM streaming convs on host buffers, channels-last x [n, t, cin], state [n, k-1 (or 1), cin]. */
+int32_t ptts_test_conv1d(int32_t device, const float* x, const float* prev, const float* w /*[cout,cin,k]*/,
+                         const float* bias, float* y /*[n,t,cout]*/, int32_t n, int32_t t, int32_t cin, int32_t cout,
+                         int32_t k);
+int32_t ptts_test_convtr1d(int32_t device, const float* x, const float* prev_row, const float* w /*[cin,cout,2s]*/,
+                           const float* bias, float* y /*[n,t*s,cout]*/, int32_t n, int32_t t, int32_t cin,
+                           int32_t cout, int32_t stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTTS_H */

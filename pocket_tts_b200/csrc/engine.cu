@@ -1,0 +1,1133 @@
+// libptts_cuda.so: engine + C ABI (include/ptts.h).
+//
+// Host-side mirror of the reference's L3/L4 for the generation hot path
+// (crates/pocket-tts/src/tts_model.rs:935-1071, models/flow_lm.rs, models/mimi.rs, models/seanet.rs)
+// re-designed for one B200: all per-stream state lives in HBM in a slot arena, every call advances a
+// whole batch of independent streams, and the only host<->device traffic per step is the PCM frame and
+// the finished flags.
+#include <algorithm>
+#include <cmath>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm.cuh"
+#include "host_util.h"
+#include "kernels.cuh"
+
+namespace ptts {
+
+static thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------------------------------------
+// model constants (crates/pocket-tts/config/b6369a24.yaml)
+static constexpr int D_MODEL = 1024, N_HEADS = 16, N_LAYERS = 6, D_FFN = 4096;
+static constexpr int FLOW_DIM = 512, FLOW_DEPTH = 6, MOD_LD = FLOW_DEPTH * 3 * FLOW_DIM + 2 * FLOW_DIM;  // 10240
+static constexpr int MIMI_DIM = 512, MIMI_HEADS = 8, MIMI_LAYERS = 2, MIMI_FFN = 2048, MIMI_T = 16;
+static constexpr int N_BINS = 4000;
+
+struct Weight16 {   // GEMM operand [Fpad][K] f16, K-major
+  DevBuf<__half> w;
+  int F = 0, Fpad = 0, K = 0;
+};
+
+struct ActView {    // f16 activations [cap][Tpad][C], channels-last
+  const __half* ptr;
+  int C, Tpad, cap;
+};
+
+struct HostTensor {
+  const ptts_tensor_desc* d;
+  std::vector<float> f32;  // converted copy
+  std::vector<int64_t> shape;
+  size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; }
+};
+
+static float bf16_to_f32(uint16_t v) { uint32_t u = (uint32_t)v << 16; float f; std::memcpy(&f, &u, 4); return f; }
+
+// ------------------------------------------------------------------------------------------------
+struct Voice {
+  DevBuf<__half> kv;  // [layer][k|v][head][len][64]
+  int len = 0;
+};
+
+struct SlotHost {
+  bool in_use = false;
+  bool finished = false;
+  int frames = 0;
+  int eos_step = -1;
+  int own_len = 0;
+  int max_gen_len = 0;
+  Voice* voice = nullptr;
+  DevBuf<float> noise;
+};
+
+struct Engine {
+  ptts_engine_cfg cfg{};
+  cudaStream_t stream = nullptr;
+  TmapCache tmaps;
+  long long launches = 0;
+  int lsd_steps = 1;
+  int NB = 0, NS = 0, KVCAP = 0, PR = 0;  // max batch, slots, own kv rows, prefill rows
+
+  // ---- weights
+  std::unordered_map<std::string, HostTensor> host;
+  Weight16 w_input, w_inproj[N_LAYERS], w_outproj[N_LAYERS], w_lin1[N_LAYERS], w_lin2[N_LAYERS];
+  DevBuf<float> ln1_w[N_LAYERS], ln1_b[N_LAYERS], ln2_w[N_LAYERS], ln2_b[N_LAYERS];
+  DevBuf<float> outnorm_w, outnorm_b, eos_w, eos_b, bos, emb_std, emb_mean, lut;
+  Weight16 w_cond, w_finproj, w_ada, w_mlp0[FLOW_DEPTH], w_mlp2[FLOW_DEPTH], w_final;
+  DevBuf<float> b_cond, b_finproj, b_ada, b_mlp0[FLOW_DEPTH], b_mlp2[FLOW_DEPTH], b_final, inln_w[FLOW_DEPTH], inln_b[FLOW_DEPTH];
+  DevBuf<float> time_emb;  // [S,512]
+  DevBuf<float> wq, wup;
+  Weight16 m_inproj[MIMI_LAYERS], m_outproj[MIMI_LAYERS], m_lin1[MIMI_LAYERS], m_lin2[MIMI_LAYERS];
+  DevBuf<float> m_ln1_w[MIMI_LAYERS], m_ln1_b[MIMI_LAYERS], m_ln2_w[MIMI_LAYERS], m_ln2_b[MIMI_LAYERS], m_ls1[MIMI_LAYERS], m_ls2[MIMI_LAYERS];
+  Weight16 s_conv0, s_ct2, s_r3a, s_r3b, s_ct5, s_r6a, s_r6b, s_ct8, s_r9a, s_r9b;
+  DevBuf<float> sb_conv0, sb_ct2, sb_r3a, sb_r3b, sb_ct5, sb_r6a, sb_r6b, sb_ct8, sb_r9a, sb_r9b, s_final_w, s_final_b;
+
+  // ---- per-slot state
+  DevBuf<__half> kv;            // [NS][layer][2][H][KVCAP][64]
+  DevBuf<SeqDesc> seqs;         // NS + 1 (last = scratch sequence used while building a voice)
+  DevBuf<int> own_len;          // NS + 1
+  DevBuf<StreamCtl> ctl;        // NS
+  DevBuf<float> feedback;       // [NS,32]
+  DevBuf<float> up_partial;     // [NS,16,512]
+  DevBuf<__half> mimi_ring;     // [NS][2][2][8][272][64]
+  DevBuf<__half> st_tr, st_a0, st_e2, st_a3, st_e5, st_a6, st_e8, st_a9;  // conv left-context rows per slot
+  std::vector<SlotHost> slots;
+  std::vector<std::unique_ptr<Voice>> voices;
+
+  // ---- decode scratch (compact by batch row)
+  DevBuf<int> row_seq;
+  std::vector<int> row_seq_host;
+  DevBuf<float> x32, qkv32, eos_logit, c32, mod32, fx32, z32, h32dbg, quant_dbg;
+  DevBuf<__half> h16, attn16, ffn16, lat16, y16, fh16, fg16, z16;
+  DevBuf<float> mx32, mqkv32;
+  DevBuf<__half> mh16, mattn16, mffn16;
+  DevBuf<__half> tr16, a0, e2, h3, a3, e5, h6, a6, e8, h9, a9;
+  DevBuf<float> x2, x5, x8, pcm;
+  DevBuf<unsigned char> finished_dev;
+  DevBuf<float> latent_out, logit_out;
+  ConvSegs segs{};
+  // ---- prefill scratch
+  DevBuf<float> px32, pqkv32, pqrot;
+  DevBuf<__half> ph16, pattn16, pffn16;
+  DevBuf<int> prow_seq, prow_pos, ptokens;
+  // ---- pinned staging
+  float* pin_pcm = nullptr; unsigned char* pin_fin = nullptr; float* pin_lat = nullptr; float* pin_logit = nullptr;
+  cudaEvent_t ev[10]{};
+
+  ~Engine();
+  void init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw);
+  void load_weights(const ptts_tensor_desc* w, int nw);
+  const HostTensor& T(const std::string& name, std::initializer_list<int64_t> shape);
+  void vec(DevBuf<float>& dst, const std::string& name, int64_t n);
+  void linear(Weight16& dst, const std::string& name, int F, int K, int Kpad = 0);
+  void compute_time_embeddings(int steps);
+
+  void gemm(const ActView& a, int n_streams, int T, int taps, int R, int G, const Weight16& w, int F, GemmEpi epi,
+            bool allow_split = false);
+  void gemm_rows(const __half* a, int rows, int K, const Weight16& w, int F, GemmEpi epi, bool allow_split = false) {
+    gemm(ActView{a, K, std::max(rows, 1), 1}, 1, rows, 1, 0, 1, w, F, epi, allow_split);
+  }
+  template <int C>
+  void ln(const float* x, int rows, const float* w, const float* b, float eps, const float* shift, const float* scale,
+          int mod_ld, __half* out, int out_ld);
+  void flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* attn, __half* ffn, bool prefill, float* qrot,
+                     const int* rseq, const int* rpos);
+  void upload_rows(const int* slot_ids, int n);
+  void step_kernels(int n, float* stage_ms);
+  void prefill(int rows);
+};
+
+Engine::~Engine() {
+  if (pin_pcm) cudaFreeHost(pin_pcm);
+  if (pin_fin) cudaFreeHost(pin_fin);
+  if (pin_lat) cudaFreeHost(pin_lat);
+  if (pin_logit) cudaFreeHost(pin_logit);
+  for (auto& e : ev) if (e) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+const HostTensor& Engine::T(const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = host.find(name);
+  PTTS_REQUIRE(it != host.end(), PTTS_ERR_INVALID, "missing tensor '%s'", name.c_str());
+  std::vector<int64_t> want(shape);
+  PTTS_REQUIRE(it->second.shape == want, PTTS_ERR_INVALID, "tensor '%s' has the wrong shape", name.c_str());
+  return it->second;
+}
+
+void Engine::vec(DevBuf<float>& dst, const std::string& name, int64_t n) {
+  const HostTensor& t = T(name, {n});
+  dst.alloc(n);
+  PTTS_CUDA(cudaMemcpy(dst.p, t.f32.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+static void upload_f16(Weight16& dst, const std::vector<float>& rows, int F, int K) {
+  dst.F = F;
+  dst.K = K;
+  dst.Fpad = round_up(F, 128);
+  std::vector<__half> h((size_t)dst.Fpad * K, __float2half(0.f));
+  double worst = 0;
+  for (size_t i = 0; i < (size_t)F * K; ++i) {
+    h[i] = __float2half_rn(rows[i]);
+    const float back = __half2float(h[i]);
+    const double err = std::fabs((double)back - rows[i]);
+    if (err > worst) worst = err;
+  }
+  // bf16-representable weights convert exactly unless |w| < 2^-17 or > 65504; report, never hide
+  if (worst > 1e-6) fprintf(stderr, "ptts: f16 weight conversion max abs error %.3g\n", worst);
+  dst.w.alloc(h.size());
+  PTTS_CUDA(cudaMemcpy(dst.w.p, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice));
+}
+
+void Engine::linear(Weight16& dst, const std::string& name, int F, int K, int Kpad) {
+  const HostTensor& t = T(name, {F, K});
+  if (Kpad <= K) return upload_f16(dst, t.f32, F, K);
+  std::vector<float> p((size_t)F * Kpad, 0.f);
+  for (int f = 0; f < F; ++f) std::memcpy(&p[(size_t)f * Kpad], &t.f32[(size_t)f * K], K * sizeof(float));
+  upload_f16(dst, p, F, Kpad);
+}
+
+// Conv1d weight [cout, cin, k] -> [cout_pad][tap*cin_pad + c]  (tap-major K so the K loop walks taps)
+static void conv_weight(Weight16& dst, DevBuf<float>& bias_dst, const HostTensor& w, const HostTensor& b, int cout, int cin,
+                        int k, int cout_pad, int cin_pad) {
+  std::vector<float> g((size_t)cout_pad * k * cin_pad, 0.f), bb(cout_pad, 0.f);
+  for (int o = 0; o < cout; ++o) {
+    bb[o] = b.f32[o];
+    for (int c = 0; c < cin; ++c)
+      for (int j = 0; j < k; ++j) g[((size_t)o * k + j) * cin_pad + c] = w.f32[((size_t)o * cin + c) * k + j];
+  }
+  upload_f16(dst, g, cout_pad, k * cin_pad);
+  bias_dst.alloc(cout_pad);
+  PTTS_CUDA(cudaMemcpy(bias_dst.p, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// ConvTranspose1d weight [cin, cout, 2s] -> [rho*cout + o][tap*cin + c]; tap 0 multiplies x[t-1] (kernel index
+// rho+s), tap 1 multiplies x[t] (kernel index rho): y[t*s+rho] = x[t] W[:,:,rho] + x[t-1] W[:,:,rho+s].
+static void convtr_weight(Weight16& dst, DevBuf<float>& bias_dst, const HostTensor& w, const HostTensor& b, int cin, int cout,
+                          int s) {
+  const int k = 2 * s;
+  std::vector<float> g((size_t)s * cout * 2 * cin, 0.f), bb((size_t)s * cout);
+  for (int rho = 0; rho < s; ++rho)
+    for (int o = 0; o < cout; ++o) {
+      bb[(size_t)rho * cout + o] = b.f32[o];
+      float* row = &g[((size_t)rho * cout + o) * 2 * cin];
+      for (int c = 0; c < cin; ++c) {
+        row[c] = w.f32[((size_t)c * cout + o) * k + rho + s];
+        row[cin + c] = w.f32[((size_t)c * cout + o) * k + rho];
+      }
+    }
+  upload_f16(dst, g, s * cout, 2 * cin);
+  bias_dst.alloc(bb.size());
+  PTTS_CUDA(cudaMemcpy(bias_dst.p, bb.data(), bb.size() * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void Engine::load_weights(const ptts_tensor_desc* w, int nw) {
+  for (int i = 0; i < nw; ++i) {
+    HostTensor t;
+    t.d = &w[i];
+    PTTS_REQUIRE(w[i].ndim >= 1 && w[i].ndim <= 4 && w[i].data && w[i].name, PTTS_ERR_INVALID, "bad tensor descriptor %d", i);
+    t.shape.assign(w[i].shape, w[i].shape + w[i].ndim);
+    const size_t n = t.numel();
+    t.f32.resize(n);
+    if (w[i].dtype == PTTS_F32) std::memcpy(t.f32.data(), w[i].data, n * 4);
+    else if (w[i].dtype == PTTS_BF16) { const uint16_t* s = (const uint16_t*)w[i].data; for (size_t j = 0; j < n; ++j) t.f32[j] = bf16_to_f32(s[j]); }
+    else if (w[i].dtype == PTTS_F16) { const __half* s = (const __half*)w[i].data; for (size_t j = 0; j < n; ++j) t.f32[j] = __half2float(s[j]); }
+    else PTTS_REQUIRE(false, PTTS_ERR_INVALID, "tensor '%s': unknown dtype", w[i].name);
+    host.emplace(w[i].name, std::move(t));
+  }
+  linear(w_input, "flow_lm.input_linear.weight", D_MODEL, LDIM, 64);
+  for (int l = 0; l < N_LAYERS; ++l) {
+    const std::string p = "flow_lm.transformer.layers." + std::to_string(l) + ".";
+    linear(w_inproj[l], p + "self_attn.in_proj.weight", 3 * D_MODEL, D_MODEL);
+    linear(w_outproj[l], p + "self_attn.out_proj.weight", D_MODEL, D_MODEL);
+    linear(w_lin1[l], p + "linear1.weight", D_FFN, D_MODEL);
+    linear(w_lin2[l], p + "linear2.weight", D_MODEL, D_FFN);
+    vec(ln1_w[l], p + "norm1.weight", D_MODEL); vec(ln1_b[l], p + "norm1.bias", D_MODEL);
+    vec(ln2_w[l], p + "norm2.weight", D_MODEL); vec(ln2_b[l], p + "norm2.bias", D_MODEL);
+  }
+  vec(outnorm_w, "flow_lm.out_norm.weight", D_MODEL); vec(outnorm_b, "flow_lm.out_norm.bias", D_MODEL);
+  { const HostTensor& t = T("flow_lm.out_eos.weight", {1, D_MODEL}); eos_w.alloc(D_MODEL);
+    PTTS_CUDA(cudaMemcpy(eos_w.p, t.f32.data(), D_MODEL * 4, cudaMemcpyHostToDevice)); }
+  vec(eos_b, "flow_lm.out_eos.bias", 1);
+  vec(bos, "flow_lm.bos_emb", LDIM); vec(emb_std, "flow_lm.emb_std", LDIM); vec(emb_mean, "flow_lm.emb_mean", LDIM);
+  { const HostTensor& t = T("flow_lm.conditioner.embed.weight", {N_BINS + 1, D_MODEL}); lut.alloc(t.f32.size());
+    PTTS_CUDA(cudaMemcpy(lut.p, t.f32.data(), t.f32.size() * 4, cudaMemcpyHostToDevice)); }
+  const std::string f = "flow_lm.flow_net.";
+  linear(w_cond, f + "cond_embed.weight", FLOW_DIM, D_MODEL); vec(b_cond, f + "cond_embed.bias", FLOW_DIM);
+  linear(w_finproj, f + "input_proj.weight", FLOW_DIM, LDIM, 64); vec(b_finproj, f + "input_proj.bias", FLOW_DIM);
+  {  // all adaLN modulation Linears share the operand silu(c + te): one [10240, 512] GEMM per LSD step
+    std::vector<float> wa((size_t)MOD_LD * FLOW_DIM), ba(MOD_LD);
+    for (int i = 0; i < FLOW_DEPTH; ++i) {
+      const std::string q = f + "res_blocks." + std::to_string(i) + ".";
+      const HostTensor& tw = T(q + "adaLN_modulation.1.weight", {3 * FLOW_DIM, FLOW_DIM});
+      const HostTensor& tb = T(q + "adaLN_modulation.1.bias", {3 * FLOW_DIM});
+      std::memcpy(&wa[(size_t)i * 3 * FLOW_DIM * FLOW_DIM], tw.f32.data(), tw.f32.size() * 4);
+      std::memcpy(&ba[(size_t)i * 3 * FLOW_DIM], tb.f32.data(), tb.f32.size() * 4);
+      linear(w_mlp0[i], q + "mlp.0.weight", FLOW_DIM, FLOW_DIM); vec(b_mlp0[i], q + "mlp.0.bias", FLOW_DIM);
+      linear(w_mlp2[i], q + "mlp.2.weight", FLOW_DIM, FLOW_DIM); vec(b_mlp2[i], q + "mlp.2.bias", FLOW_DIM);
+      vec(inln_w[i], q + "in_ln.weight", FLOW_DIM); vec(inln_b[i], q + "in_ln.bias", FLOW_DIM);
+    }
+    const HostTensor& tw = T(f + "final_layer.adaLN_modulation.1.weight", {2 * FLOW_DIM, FLOW_DIM});
+    const HostTensor& tb = T(f + "final_layer.adaLN_modulation.1.bias", {2 * FLOW_DIM});
+    std::memcpy(&wa[(size_t)FLOW_DEPTH * 3 * FLOW_DIM * FLOW_DIM], tw.f32.data(), tw.f32.size() * 4);
+    std::memcpy(&ba[(size_t)FLOW_DEPTH * 3 * FLOW_DIM], tb.f32.data(), tb.f32.size() * 4);
+    upload_f16(w_ada, wa, MOD_LD, FLOW_DIM);
+    b_ada.alloc(MOD_LD);
+    PTTS_CUDA(cudaMemcpy(b_ada.p, ba.data(), ba.size() * 4, cudaMemcpyHostToDevice));
+  }
+  linear(w_final, f + "final_layer.linear.weight", LDIM, FLOW_DIM); vec(b_final, f + "final_layer.linear.bias", LDIM);
+  { const HostTensor& t = T("mimi.quantizer.output_proj.weight", {MIMI_DIM, LDIM, 1}); wq.alloc(t.f32.size());
+    PTTS_CUDA(cudaMemcpy(wq.p, t.f32.data(), t.f32.size() * 4, cudaMemcpyHostToDevice)); }
+  { const HostTensor& t = T("mimi.upsample.convtr.convtr.weight", {MIMI_DIM, 1, 32}); wup.alloc(t.f32.size());
+    PTTS_CUDA(cudaMemcpy(wup.p, t.f32.data(), t.f32.size() * 4, cudaMemcpyHostToDevice)); }
+  for (int l = 0; l < MIMI_LAYERS; ++l) {
+    const std::string p = "mimi.decoder_transformer.transformer.layers." + std::to_string(l) + ".";
+    linear(m_inproj[l], p + "self_attn.in_proj.weight", 3 * MIMI_DIM, MIMI_DIM);
+    linear(m_outproj[l], p + "self_attn.out_proj.weight", MIMI_DIM, MIMI_DIM);
+    linear(m_lin1[l], p + "linear1.weight", MIMI_FFN, MIMI_DIM);
+    linear(m_lin2[l], p + "linear2.weight", MIMI_DIM, MIMI_FFN);
+    vec(m_ln1_w[l], p + "norm1.weight", MIMI_DIM); vec(m_ln1_b[l], p + "norm1.bias", MIMI_DIM);
+    vec(m_ln2_w[l], p + "norm2.weight", MIMI_DIM); vec(m_ln2_b[l], p + "norm2.bias", MIMI_DIM);
+    vec(m_ls1[l], p + "layer_scale_1.scale", MIMI_DIM); vec(m_ls2[l], p + "layer_scale_2.scale", MIMI_DIM);
+  }
+  const std::string d = "mimi.decoder.model.";
+  auto cw = [&](Weight16& dst, DevBuf<float>& bd, const std::string& n, int cout, int cin, int k, int cout_pad, int cin_pad) {
+    conv_weight(dst, bd, T(d + n + ".conv.weight", {cout, cin, k}), T(d + n + ".conv.bias", {cout}), cout, cin, k, cout_pad, cin_pad);
+  };
+  auto ctw = [&](Weight16& dst, DevBuf<float>& bd, const std::string& n, int cin, int cout, int s) {
+    convtr_weight(dst, bd, T(d + n + ".convtr.weight", {cin, cout, 2 * s}), T(d + n + ".convtr.bias", {cout}), cin, cout, s);
+  };
+  cw(s_conv0, sb_conv0, "0", 512, 512, 7, 512, 512);
+  ctw(s_ct2, sb_ct2, "2", 512, 256, 6);
+  cw(s_r3a, sb_r3a, "3.block.1", 128, 256, 3, 128, 256);
+  cw(s_r3b, sb_r3b, "3.block.3", 256, 128, 1, 256, 128);
+  ctw(s_ct5, sb_ct5, "5", 256, 128, 5);
+  cw(s_r6a, sb_r6a, "6.block.1", 64, 128, 3, 64, 128);
+  cw(s_r6b, sb_r6b, "6.block.3", 128, 64, 1, 128, 64);
+  ctw(s_ct8, sb_ct8, "8", 128, 64, 4);
+  // hidden width 32 is padded to 64 channels (zero weights, zero bias -> ELU(0) = 0) so K stays a multiple of 64
+  cw(s_r9a, sb_r9a, "9.block.1", 32, 64, 3, 64, 64);
+  cw(s_r9b, sb_r9b, "9.block.3", 64, 32, 1, 64, 64);
+  {
+    const HostTensor& tw = T(d + "11.conv.weight", {1, 64, 3});
+    std::vector<float> g(192);
+    for (int c = 0; c < 64; ++c) for (int j = 0; j < 3; ++j) g[j * 64 + c] = tw.f32[c * 3 + j];
+    s_final_w.alloc(192);
+    PTTS_CUDA(cudaMemcpy(s_final_w.p, g.data(), 192 * 4, cudaMemcpyHostToDevice));
+    vec(s_final_b, d + "11.conv.bias", 1);
+  }
+}
+
+// TimestepEmbedder + combine on the host in f32 (reference modules/mlp.rs:84-133,296-319); hoisted out of the
+// frame loop exactly like tts_model.rs:994-1001.
+void Engine::compute_time_embeddings(int steps) {
+  std::vector<float> te((size_t)steps * FLOW_DIM, 0.f);
+  for (int idx = 0; idx < 2; ++idx) {
+    const std::string p = "flow_lm.flow_net.time_embed." + std::to_string(idx) + ".mlp.";
+    const HostTensor& w0 = T(p + "0.weight", {FLOW_DIM, 256});
+    const HostTensor& b0 = T(p + "0.bias", {FLOW_DIM});
+    const HostTensor& w2 = T(p + "2.weight", {FLOW_DIM, FLOW_DIM});
+    const HostTensor& b2 = T(p + "2.bias", {FLOW_DIM});
+    const HostTensor& al = T(p + "3.alpha", {FLOW_DIM});
+    for (int s = 0; s < steps; ++s) {
+      const float tval = idx == 0 ? (float)((double)s / steps) : (float)((double)(s + 1) / steps);
+      float emb[256], h1[FLOW_DIM], h2[FLOW_DIM];
+      for (int i = 0; i < 128; ++i) {
+        const float fr = std::exp((float)i * (-std::log(10000.f) / 128.f));
+        emb[i] = std::cos(tval * fr);
+        emb[128 + i] = std::sin(tval * fr);
+      }
+      for (int o = 0; o < FLOW_DIM; ++o) {
+        float a = b0.f32[o];
+        for (int i = 0; i < 256; ++i) a += w0.f32[(size_t)o * 256 + i] * emb[i];
+        h1[o] = a / (1.f + std::exp(-a));
+      }
+      double mean = 0;
+      for (int o = 0; o < FLOW_DIM; ++o) {
+        float a = b2.f32[o];
+        for (int i = 0; i < FLOW_DIM; ++i) a += w2.f32[(size_t)o * FLOW_DIM + i] * h1[i];
+        h2[o] = a;
+        mean += a;
+      }
+      mean /= FLOW_DIM;
+      double var = 0;
+      for (int o = 0; o < FLOW_DIM; ++o) var += (h2[o] - mean) * (h2[o] - mean);
+      var /= (FLOW_DIM - 1);  // unbiased: the reference's "RMSNorm" is x * alpha * rsqrt(var(x) + eps), mlp.rs:18-26
+      const float r = 1.f / std::sqrt((float)var + 1e-5f);
+      for (int o = 0; o < FLOW_DIM; ++o) te[(size_t)s * FLOW_DIM + o] += 0.5f * h2[o] * al.f32[o] * r;
+    }
+  }
+  time_emb.alloc(te.size());
+  PTTS_CUDA(cudaMemcpy(time_emb.p, te.data(), te.size() * 4, cudaMemcpyHostToDevice));
+  lsd_steps = steps;
+}
+
+// ------------------------------------------------------------------------------------------------ init
+void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
+  cfg = c;
+  int ndev = 0;
+  PTTS_CUDA(cudaGetDeviceCount(&ndev));
+  PTTS_REQUIRE(c.device >= 0 && c.device < ndev, PTTS_ERR_CUDA, "CUDA device %d not present (%d devices)", c.device, ndev);
+  PTTS_CUDA(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  PTTS_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  PTTS_REQUIRE(prop.major == 10, PTTS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", c.device,
+               prop.major, prop.minor);
+  PTTS_REQUIRE(c.weight_mode == PTTS_W_F16, PTTS_ERR_INVALID, "weight_mode %d not built yet", c.weight_mode);
+  NS = c.max_slots > 0 ? c.max_slots : 64;
+  NB = c.max_batch > 0 ? std::min(c.max_batch, NS) : NS;
+  KVCAP = c.kv_capacity > 0 ? c.kv_capacity : 1024;
+  PR = 4096;
+  PTTS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  for (auto& e : ev) PTTS_CUDA(cudaEventCreate(&e));
+  PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  {
+    float inv[HD / 2];
+    const float cst = -std::log(10000.f) * 2.f / (float)HD;  // f32 like modules/rope.rs:12-14
+    for (int i = 0; i < HD / 2; ++i) inv[i] = std::exp((float)i * cst);
+    PTTS_CUDA(cudaMemcpyToSymbol(c_inv_freq, inv, sizeof inv));
+  }
+  load_weights(w, nw);
+  compute_time_embeddings(1);
+
+  kv.alloc((size_t)NS * N_LAYERS * 2 * N_HEADS * KVCAP * HD);
+  seqs.alloc(NS + 1); own_len.alloc(NS + 1); ctl.alloc(NS); feedback.alloc((size_t)NS * LDIM);
+  up_partial.alloc((size_t)NS * 16 * 512);
+  mimi_ring.alloc((size_t)NS * MIMI_LAYERS * 2 * MIMI_HEADS * MIMI_RING * HD);
+  st_tr.alloc((size_t)NS * 6 * 512); st_a0.alloc((size_t)NS * 512); st_e2.alloc((size_t)NS * 2 * 256);
+  st_a3.alloc((size_t)NS * 256); st_e5.alloc((size_t)NS * 2 * 128); st_a6.alloc((size_t)NS * 128);
+  st_e8.alloc((size_t)NS * 2 * 64); st_a9.alloc((size_t)NS * 2 * 64);
+  slots.resize(NS);
+
+  row_seq.alloc(NB); x32.alloc((size_t)NB * D_MODEL); qkv32.alloc((size_t)NB * 3 * D_MODEL); eos_logit.alloc(NB);
+  h16.alloc((size_t)NB * D_MODEL); attn16.alloc((size_t)NB * D_MODEL); ffn16.alloc((size_t)NB * D_FFN);
+  h32dbg.alloc((size_t)NB * D_MODEL); quant_dbg.alloc((size_t)NB * 512);
+  lat16.alloc((size_t)NB * 64); c32.alloc((size_t)NB * FLOW_DIM); mod32.alloc((size_t)NB * MOD_LD);
+  fx32.alloc((size_t)NB * FLOW_DIM); y16.alloc((size_t)NB * FLOW_DIM); fh16.alloc((size_t)NB * FLOW_DIM);
+  fg16.alloc((size_t)NB * FLOW_DIM); z32.alloc((size_t)NB * LDIM); z16.alloc((size_t)NB * 64);
+  const size_t MR = (size_t)NB * MIMI_T;
+  mx32.alloc(MR * MIMI_DIM); mqkv32.alloc(MR * 3 * MIMI_DIM); mh16.alloc(MR * MIMI_DIM); mattn16.alloc(MR * MIMI_DIM);
+  mffn16.alloc(MR * MIMI_FFN);
+  tr16.alloc((size_t)NB * 22 * 512); a0.alloc((size_t)NB * 17 * 512);
+  x2.alloc((size_t)NB * 96 * 256); e2.alloc((size_t)NB * 98 * 256); h3.alloc((size_t)NB * 96 * 128);
+  a3.alloc((size_t)NB * 97 * 256); x5.alloc((size_t)NB * 480 * 128); e5.alloc((size_t)NB * 482 * 128);
+  h6.alloc((size_t)NB * 480 * 64); a6.alloc((size_t)NB * 481 * 128); x8.alloc((size_t)NB * 1920 * 64);
+  e8.alloc((size_t)NB * 1922 * 64); h9.alloc((size_t)NB * 1920 * 64); a9.alloc((size_t)NB * 1922 * 64);
+  pcm.alloc((size_t)NB * FRAME); finished_dev.alloc(NB); latent_out.alloc((size_t)NB * LDIM); logit_out.alloc(NB);
+  segs.s[0] = ConvSeg{tr16.p, st_tr.p, 6, 16, 512, 0};
+  segs.s[1] = ConvSeg{a0.p, st_a0.p, 1, 16, 512, 0};
+  segs.s[2] = ConvSeg{e2.p, st_e2.p, 2, 96, 256, 0};
+  segs.s[3] = ConvSeg{a3.p, st_a3.p, 1, 96, 256, 0};
+  segs.s[4] = ConvSeg{e5.p, st_e5.p, 2, 480, 128, 0};
+  segs.s[5] = ConvSeg{a6.p, st_a6.p, 1, 480, 128, 0};
+  segs.s[6] = ConvSeg{e8.p, st_e8.p, 2, 1920, 64, 0};
+  segs.s[7] = ConvSeg{a9.p, st_a9.p, 2, 1920, 64, 0};
+
+  px32.alloc((size_t)PR * D_MODEL); pqkv32.alloc((size_t)PR * 3 * D_MODEL); pqrot.alloc((size_t)PR * D_MODEL);
+  ph16.alloc((size_t)PR * D_MODEL); pattn16.alloc((size_t)PR * D_MODEL); pffn16.alloc((size_t)PR * D_FFN);
+  prow_seq.alloc(PR); prow_pos.alloc(PR); ptokens.alloc(PR);
+  PTTS_CUDA(cudaMallocHost(&pin_pcm, (size_t)NB * FRAME * 4));
+  PTTS_CUDA(cudaMallocHost(&pin_fin, NB));
+  PTTS_CUDA(cudaMallocHost(&pin_lat, (size_t)NB * LDIM * 4));
+  PTTS_CUDA(cudaMallocHost(&pin_logit, (size_t)NB * 4));
+  for (auto it = host.begin(); it != host.end();)  // only the time-embedding MLPs are needed again (set_lsd_steps)
+    it = (it->first.find("time_embed") == std::string::npos) ? host.erase(it) : std::next(it);
+  PTTS_CUDA(cudaDeviceSynchronize());
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G, const Weight16& w, int F, GemmEpi epi,
+                  bool allow_split) {
+  const long long rows = (long long)n_streams * T;
+  if (rows <= 0) return;
+  PTTS_REQUIRE(a.C % 64 == 0 && w.K == taps * a.C, PTTS_ERR_INVALID, "gemm: K mismatch (C %d taps %d, weight K %d)", a.C, taps, w.K);
+  PTTS_REQUIRE(F <= w.Fpad, PTTS_ERR_INVALID, "gemm: F %d beyond weight rows %d", F, w.Fpad);
+  GemmParams p{};
+  p.F = F; p.K = w.K; p.taps = taps; p.cblocks = a.C / 64;
+  p.epi = epi;
+  p.act = a.ptr; p.act_stream_stride = (long long)a.Tpad * a.C; p.act_ld = a.C; p.w = w.w.p;
+  const int total_kb = p.taps * p.cblocks;
+  const bool plain = (taps == 1 && n_streams == 1);
+  int force = cfg.reserved[0];  // test hook: 1 = never swap, 2 = always swap when legal
+  bool swap = plain && rows <= 256 && force != 1;
+  if (plain && !swap) { R = 128; G = 1; }
+  dim3 grid;
+  if (swap) {
+    p.swap = 1;
+    p.BN = std::max(16, round_up((int)rows, 16));
+    p.n_streams = 1; p.T = (int)rows; p.R = p.BN; p.G = 1;
+    grid = dim3(w.Fpad / 128, 1, 1);
+  } else {
+    p.swap = 0;
+    PTTS_REQUIRE(R > 0 && G > 0 && R * G <= 128, PTTS_ERR_INVALID, "gemm: bad tile geometry R %d G %d", R, G);
+    p.n_streams = n_streams; p.T = T; p.R = R; p.G = G;
+    const int act_tiles = ((T + R - 1) / R) * ((n_streams + G - 1) / G);
+    const int fcap = round_up(F, 16);
+    int bn = std::min(256, fcap);
+    while (bn > 64 && (long long)act_tiles * ((F + bn - 1) / bn) < 148) bn >>= 1;
+    bn = std::min(round_up(bn, 16), fcap);
+    p.BN = bn;
+    grid = dim3(act_tiles, (F + bn - 1) / bn, 1);
+  }
+  int splits = 1;
+  if (allow_split && epi.atomic) {
+    const int tiles = grid.x * grid.y;
+    splits = std::max(1, std::min(148 / std::max(tiles, 1), total_kb / 2));
+  }
+  p.kb_per_split = (total_kb + splits - 1) / splits;
+  splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  if (splits == 1) p.epi.atomic = 0;  // single CTA per tile: plain read-modify-write through epi.res
+  grid.z = splits;
+  const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
+  p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));
+  p.tmem_cols = pow2_at_least(p.BN);
+  const size_t smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
+
+  if (cfg.debug_gemm) {
+    const long long n = rows * F;
+    gemm_simt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+  } else {
+    const CUtensorMap& ma = swap ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
+                                 : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
+    const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
+    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ma, mw, p);
+  }
+  ++launches;
+  PTTS_CUDA(cudaGetLastError());
+}
+
+template <int C>
+void Engine::ln(const float* x, int rows, const float* w, const float* b, float eps, const float* shift, const float* scale,
+                int mod_ld, __half* out, int out_ld) {
+  if (rows <= 0) return;
+  ln_rows_kernel<C><<<(rows + 3) / 4, 128, 0, stream>>>(x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
+  ++launches;
+}
+
+static GemmEpi epi_none() {
+  GemmEpi e{};
+  e.alpha = 1.f;
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------ FlowLM transformer
+// Reference models/transformer.rs:66-90 per layer.  Residual stream x stays f32 in HBM; out_proj and linear2
+// accumulate straight into it (split-K, red.add) so no epilogue buffer exists.
+void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* attn, __half* ffn, bool is_prefill,
+                           float* qrot, const int* rseq, const int* rpos) {
+  for (int l = 0; l < N_LAYERS; ++l) {
+    ln<D_MODEL>(x, rows, ln1_w[l].p, ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
+    GemmEpi e = epi_none();
+    e.out32 = qkv; e.out32_map = plain_map(3 * D_MODEL);
+    gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
+    if (is_prefill) {
+      flowlm_rope_append_kernel<<<dim3(rows, N_HEADS), 32, 0, stream>>>(qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot);
+      ++launches;
+      if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
+      const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
+      flowlm_attn_prefill_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qrot, rseq, rpos, seqs.p, l, N_HEADS, attn);
+      ++launches;
+    } else {
+      const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
+      flowlm_attn_decode_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn);
+      ++launches;
+    }
+    // x += attn W_o^T: split-K CTAs add their partial sums with red.add (epi.atomic); when the dispatcher
+    // keeps one CTA per tile it clears `atomic` and the same epilogue reads the residual through epi.res.
+    e = epi_none();
+    e.out32 = x; e.out32_map = plain_map(D_MODEL); e.atomic = 1; e.res = x; e.res_map = plain_map(D_MODEL);
+    gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
+    ln<D_MODEL>(x, rows, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
+    e = epi_none();
+    e.act = ACT_GELU; e.out16 = ffn; e.out16_map = plain_map(D_FFN);
+    gemm_rows(h, rows, D_MODEL, w_lin1[l], D_FFN, e);
+    e = epi_none();
+    e.out32 = x; e.out32_map = plain_map(D_MODEL); e.atomic = 1; e.res = x; e.res_map = plain_map(D_MODEL);
+    gemm_rows(ffn, rows, D_FFN, w_lin2[l], D_MODEL, e, true);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ one decode step
+void Engine::upload_rows(const int* slot_ids, int n) {
+  if ((int)row_seq_host.size() == n && std::equal(slot_ids, slot_ids + n, row_seq_host.begin())) return;
+  row_seq_host.assign(slot_ids, slot_ids + n);
+  PTTS_CUDA(cudaMemcpyAsync(row_seq.p, row_seq_host.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
+}
+
+static RowMap stream_map(int T, int ld, long long stream_stride, long long base) { return RowMap{T, ld, stream_stride, base}; }
+
+void Engine::step_kernels(int n, float* stage_ms) {
+  auto mark = [&](int i) { if (stage_ms) PTTS_CUDA(cudaEventRecord(ev[i], stream)); };
+  mark(0);
+  // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
+  step_begin_kernel<<<n, 64, 0, stream>>>(row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p);
+  ++launches;
+  GemmEpi e = epi_none();
+  e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
+  gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
+  flowlm_layers(n, x32.p, h16.p, qkv32.p, attn16.p, ffn16.p, false, nullptr, row_seq.p, nullptr);
+  ln_eos_kernel<<<(n + 3) / 4, 128, 0, stream>>>(x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,
+                                                 eos_logit.p);
+  ++launches;
+  mark(1);
+  // ---- LSD flow head (reference flow_lm.rs:7-22,156-161; modules/mlp.rs:275,322-383)
+  e = epi_none();
+  e.bias = b_cond.p; e.out32 = c32.p; e.out32_map = plain_map(FLOW_DIM);
+  gemm_rows(h16.p, n, D_MODEL, w_cond, FLOW_DIM, e);
+  for (int s = 0; s < lsd_steps; ++s) {
+    silu_add_kernel<<<(n * FLOW_DIM + 255) / 256, 256, 0, stream>>>(c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p);
+    ++launches;
+    e = epi_none();
+    e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
+    gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
+    e = epi_none();
+    e.bias = b_finproj.p; e.out32 = fx32.p; e.out32_map = plain_map(FLOW_DIM);
+    gemm_rows(z16.p, n, 64, w_finproj, FLOW_DIM, e);
+    for (int i = 0; i < FLOW_DEPTH; ++i) {
+      const float* shift = mod32.p + (size_t)i * 3 * FLOW_DIM;
+      ln<FLOW_DIM>(fx32.p, n, inln_w[i].p, inln_b[i].p, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
+      e = epi_none();
+      e.bias = b_mlp0[i].p; e.act = ACT_SILU; e.out16 = fg16.p; e.out16_map = plain_map(FLOW_DIM);
+      gemm_rows(fh16.p, n, FLOW_DIM, w_mlp0[i], FLOW_DIM, e);
+      e = epi_none();
+      e.bias = b_mlp2[i].p; e.gate = shift + 2 * FLOW_DIM; e.gate_map = plain_map(MOD_LD);
+      e.res = fx32.p; e.res_map = plain_map(FLOW_DIM); e.out32 = fx32.p; e.out32_map = plain_map(FLOW_DIM);
+      gemm_rows(fg16.p, n, FLOW_DIM, w_mlp2[i], FLOW_DIM, e);
+    }
+    const float* shift = mod32.p + (size_t)FLOW_DEPTH * 3 * FLOW_DIM;
+    ln<FLOW_DIM>(fx32.p, n, nullptr, nullptr, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
+    e = epi_none();  // z += (W h + b) / S   (Euler step, flow_lm.rs:15-19)
+    e.bias = b_final.p; e.alpha = 1.f / (float)lsd_steps; e.res = z32.p; e.res_map = plain_map(LDIM);
+    e.out32 = z32.p; e.out32_map = plain_map(LDIM); e.out16 = z16.p; e.out16_map = plain_map(64);
+    gemm_rows(fh16.p, n, FLOW_DIM, w_final, LDIM, e);
+  }
+  mark(2);
+  // ---- Mimi: de-norm + quantizer + upsample, decoder transformer (reference mimi.rs:143-157, transformer.rs:227-251)
+  const int MR = n * MIMI_T;
+  mimi_frontend_kernel<<<n, 512, 0, stream>>>(z32.p, row_seq.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
+                                             quant_dbg.p);
+  ++launches;
+  for (int l = 0; l < MIMI_LAYERS; ++l) {
+    ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[l].p, m_ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
+    e = epi_none();
+    e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
+    gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
+    mimi_attn_kernel<<<dim3(n, MIMI_HEADS), 128, 0, stream>>>(mqkv32.p, row_seq.p, ctl.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p);
+    ++launches;
+    e = epi_none();
+    e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
+    e.atomic = 1;
+    gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);
+    ln<MIMI_DIM>(mx32.p, MR, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
+    e = epi_none();
+    e.act = ACT_GELU; e.out16 = mffn16.p; e.out16_map = plain_map(MIMI_FFN);
+    gemm_rows(mh16.p, MR, MIMI_DIM, m_lin1[l], MIMI_FFN, e);
+    e = epi_none();
+    e.fscale = m_ls2[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
+    const bool last = (l == MIMI_LAYERS - 1);
+    if (last) {  // also emit the f16 operand of SEANet's first conv behind its 6 left-context rows
+      e.out16 = tr16.p; e.out16_map = stream_map(16, 512, 22 * 512, 6 * 512);
+    } else {
+      e.atomic = 1;
+    }
+    gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
+  }
+  mark(3);
+  // ---- SEANet decoder (reference seanet.rs:309-402) as implicit GEMMs; ELU fused into the producer's epilogue
+  conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 0);
+  ++launches;
+  e = epi_none(); e.bias = sb_conv0.p; e.out16 = a0.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 512, 17 * 512, 512);
+  gemm(ActView{tr16.p, 512, 22, NB}, n, 16, 7, 16, 8, s_conv0, 512, e);
+  e = epi_none(); e.bias = sb_ct2.p; e.out32 = x2.p; e.out32_map = stream_map(16, 1536, 96 * 256, 0);
+  e.out16 = e2.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 1536, 98 * 256, 2 * 256);
+  gemm(ActView{a0.p, 512, 17, NB}, n, 16, 2, 16, 8, s_ct2, 1536, e);
+  e = epi_none(); e.bias = sb_r3a.p; e.out16 = h3.p; e.act16 = ACT_ELU; e.out16_map = plain_map(128);
+  gemm(ActView{e2.p, 256, 98, NB}, n, 96, 3, 96, 1, s_r3a, 128, e);
+  e = epi_none(); e.bias = sb_r3b.p; e.res = x2.p; e.res_map = plain_map(256);
+  e.out16 = a3.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 256, 97 * 256, 256);
+  gemm_rows(h3.p, n * 96, 128, s_r3b, 256, e);
+  e = epi_none(); e.bias = sb_ct5.p; e.out32 = x5.p; e.out32_map = stream_map(96, 640, 480 * 128, 0);
+  e.out16 = e5.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 640, 482 * 128, 2 * 128);
+  gemm(ActView{a3.p, 256, 97, NB}, n, 96, 2, 96, 1, s_ct5, 640, e);
+  e = epi_none(); e.bias = sb_r6a.p; e.out16 = h6.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
+  gemm(ActView{e5.p, 128, 482, NB}, n, 480, 3, 120, 1, s_r6a, 64, e);
+  e = epi_none(); e.bias = sb_r6b.p; e.res = x5.p; e.res_map = plain_map(128);
+  e.out16 = a6.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 128, 481 * 128, 128);
+  gemm_rows(h6.p, n * 480, 64, s_r6b, 128, e);
+  e = epi_none(); e.bias = sb_ct8.p; e.out32 = x8.p; e.out32_map = stream_map(480, 256, 1920 * 64, 0);
+  e.out16 = e8.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 256, 1922 * 64, 2 * 64);
+  gemm(ActView{a6.p, 128, 481, NB}, n, 480, 2, 120, 1, s_ct8, 256, e);
+  e = epi_none(); e.bias = sb_r9a.p; e.out16 = h9.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
+  gemm(ActView{e8.p, 64, 1922, NB}, n, 1920, 3, 128, 1, s_r9a, 64, e);
+  e = epi_none(); e.bias = sb_r9b.p; e.res = x8.p; e.res_map = plain_map(64);
+  e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(1920, 64, 1922 * 64, 128);
+  gemm_rows(h9.p, n * 1920, 64, s_r9b, 64, e);
+  seanet_final_conv_kernel<<<dim3((FRAME + 255) / 256, n), 256, 0, stream>>>(a9.p, s_final_w.p, s_final_b.p, n, pcm.p);
+  ++launches;
+  conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 1);
+  ++launches;
+  mark(4);
+  // ---- EOS bookkeeping, AR feedback, cursors (reference tts_model.rs:1055-1069)
+  step_end_kernel<<<n, 32, 0, stream>>>(row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
+                                        latent_out.p, logit_out.p);
+  ++launches;
+  mark(5);
+  PTTS_CUDA(cudaGetLastError());
+  if (stage_ms) {
+    PTTS_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < 5; ++i) PTTS_CUDA(cudaEventElapsedTime(stage_ms + i, ev[i], ev[i + 1]));
+    PTTS_CUDA(cudaEventElapsedTime(stage_ms + 5, ev[0], ev[5]));
+    stage_ms[6] = stage_ms[7] = 0.f;
+  }
+}
+
+void Engine::prefill(int rows) {
+  flowlm_layers(rows, px32.p, ph16.p, pqkv32.p, pattn16.p, pffn16.p, true, pqrot.p, prow_seq.p, prow_pos.p);
+}
+
+static std::mutex g_mu;  // engine handles are not re-entrant; this only serialises create/destroy bookkeeping
+
+}  // namespace ptts
+
+// ================================================================================================ C ABI
+using namespace ptts;
+
+struct ptts_engine { Engine e; };
+struct ptts_voice { Voice v; };
+
+#define PTTS_TRY try {
+#define PTTS_CATCH                                            \
+  }                                                           \
+  catch (const ptts::Error& ex) {                             \
+    g_last_error = ex.what();                                 \
+    return ex.code;                                           \
+  }                                                           \
+  catch (const std::exception& ex) {                          \
+    g_last_error = ex.what();                                 \
+    return PTTS_ERR_INVALID;                                  \
+  }
+
+extern "C" {
+
+const char* ptts_last_error(void) { return g_last_error.c_str(); }
+int32_t ptts_abi_version(void) { return PTTS_ABI_VERSION; }
+
+int32_t ptts_engine_create(const ptts_engine_cfg* cfg, const ptts_tensor_desc* weights, int32_t n_weights, ptts_engine** out) {
+  PTTS_TRY
+  PTTS_REQUIRE(cfg && weights && out && n_weights > 0, PTTS_ERR_INVALID, "ptts_engine_create: null argument");
+  std::unique_ptr<ptts_engine> h(new ptts_engine);
+  h->e.init(*cfg, weights, n_weights);
+  *out = h.release();
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+void ptts_engine_destroy(ptts_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->e.cfg.device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+int32_t ptts_engine_set_lsd_steps(ptts_engine* h, int32_t lsd_steps) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && lsd_steps >= 1 && lsd_steps <= 64, PTTS_ERR_INVALID, "lsd_steps must be in [1,64]");
+  PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+  PTTS_CUDA(cudaStreamSynchronize(h->e.stream));
+  h->e.compute_time_embeddings(lsd_steps);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_voice_from_prompt(ptts_engine* h, const float* audio_prompt, int32_t n_rows, ptts_voice** out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && audio_prompt && out, PTTS_ERR_INVALID, "ptts_voice_from_prompt: null argument");
+  Engine& e = h->e;
+  PTTS_REQUIRE(n_rows >= 1 && n_rows <= 1024, PTTS_ERR_CAPACITY, "voice prompt of %d rows (supported: 1..1024)", n_rows);
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  std::unique_ptr<ptts_voice> v(new ptts_voice);
+  v->v.len = n_rows;
+  v->v.kv.alloc((size_t)N_LAYERS * 2 * N_HEADS * n_rows * HD);
+  SeqDesc sd{v->v.kv.p, nullptr, n_rows, 0, 0, 0};
+  PTTS_CUDA(cudaMemcpyAsync(e.seqs.p + e.NS, &sd, sizeof sd, cudaMemcpyHostToDevice, e.stream));
+  std::vector<int> rs(n_rows, e.NS), rp(n_rows);
+  for (int i = 0; i < n_rows; ++i) rp[i] = i;
+  PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, rs.data(), n_rows * 4, cudaMemcpyHostToDevice, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.prow_pos.p, rp.data(), n_rows * 4, cudaMemcpyHostToDevice, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.px32.p, audio_prompt, (size_t)n_rows * D_MODEL * 4, cudaMemcpyHostToDevice, e.stream));
+  e.prefill(n_rows);
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  *out = v.release();
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+void ptts_voice_destroy(ptts_engine* h, ptts_voice* v) {
+  if (!v) return;
+  if (h) { cudaSetDevice(h->e.cfg.device); cudaStreamSynchronize(h->e.stream); }
+  delete v;
+}
+
+int32_t ptts_voice_len(const ptts_voice* v) { return v ? v->v.len : -1; }
+
+int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, const int32_t* tokens,
+                          const int32_t* token_offsets, const ptts_stream_params* params, int32_t* slots_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && voices && tokens && token_offsets && params && slots_out && n >= 1, PTTS_ERR_INVALID,
+               "ptts_streams_open: null argument");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  // validate everything before touching state
+  std::vector<int> free_slots;
+  for (int s = 0; s < e.NS && (int)free_slots.size() < n; ++s) if (!e.slots[s].in_use) free_slots.push_back(s);
+  PTTS_REQUIRE((int)free_slots.size() == n, PTTS_ERR_CAPACITY, "%d streams requested, %zu slots free", n, free_slots.size());
+  for (int i = 0; i < n; ++i) {
+    const int nt = token_offsets[i + 1] - token_offsets[i];
+    PTTS_REQUIRE(voices[i], PTTS_ERR_INVALID, "stream %d: null voice", i);
+    PTTS_REQUIRE(nt >= 0 && nt <= e.PR, PTTS_ERR_INVALID, "stream %d: %d tokens", i, nt);
+    PTTS_REQUIRE(params[i].max_gen_len >= 1, PTTS_ERR_INVALID, "stream %d: max_gen_len %d", i, params[i].max_gen_len);
+    PTTS_REQUIRE(nt + params[i].max_gen_len <= e.KVCAP, PTTS_ERR_CAPACITY, "stream %d: %d tokens + %d frames exceed kv_capacity %d",
+                 i, nt, params[i].max_gen_len, e.KVCAP);
+    for (int j = token_offsets[i]; j < token_offsets[i + 1]; ++j)
+      PTTS_REQUIRE(tokens[j] >= 0 && tokens[j] <= N_BINS, PTTS_ERR_INVALID, "stream %d: token id %d out of range", i, tokens[j]);
+  }
+  const size_t per_slot_kv = (size_t)N_LAYERS * 2 * N_HEADS * e.KVCAP * HD;
+  std::vector<SeqDesc> sds(n);
+  std::vector<StreamCtl> ctls(n);
+  std::vector<int> lens(n);
+  for (int i = 0; i < n; ++i) {
+    const int s = free_slots[i];
+    SlotHost& sh = e.slots[s];
+    const int nt = token_offsets[i + 1] - token_offsets[i];
+    sh = SlotHost{};
+    sh.in_use = true; sh.voice = &voices[i]->v; sh.own_len = nt; sh.max_gen_len = params[i].max_gen_len;
+    const float* noise_dev = nullptr;
+    if (params[i].noise) {
+      sh.noise.alloc((size_t)params[i].max_gen_len * LDIM);
+      PTTS_CUDA(cudaMemcpyAsync(sh.noise.p, params[i].noise, sh.noise.n * 4, cudaMemcpyHostToDevice, e.stream));
+      noise_dev = sh.noise.p;
+    }
+    sds[i] = SeqDesc{e.kv.p + (size_t)s * per_slot_kv, sh.voice->kv.p, e.KVCAP, sh.voice->len, sh.voice->len, 0};
+    ctls[i] = StreamCtl{params[i].max_gen_len, params[i].frames_after_eos, params[i].eos_threshold, params[i].temp,
+                        (unsigned long long)params[i].seed, noise_dev, 0, -1, 0, 0};
+    lens[i] = nt;
+    PTTS_CUDA(cudaMemcpyAsync(e.seqs.p + s, &sds[i], sizeof(SeqDesc), cudaMemcpyHostToDevice, e.stream));
+    PTTS_CUDA(cudaMemcpyAsync(e.ctl.p + s, &ctls[i], sizeof(StreamCtl), cudaMemcpyHostToDevice, e.stream));
+    PTTS_CUDA(cudaMemcpyAsync(e.own_len.p + s, &lens[i], sizeof(int), cudaMemcpyHostToDevice, e.stream));
+    PTTS_CUDA(cudaMemcpyAsync(e.feedback.p + (size_t)s * LDIM, e.bos.p, LDIM * 4, cudaMemcpyDeviceToDevice, e.stream));
+    slots_out[i] = s;
+  }
+  // zero the streaming state of the new slots (slot list staged through the prefill row buffer)
+  PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, free_slots.data(), n * 4, cudaMemcpyHostToDevice, e.stream));
+  for (int off = 0; off < n; off += 32768) {
+    const int cnt = std::min(32768, n - off);
+    slot_reset_kernel<<<dim3(cnt, 9), 128, 0, e.stream>>>(e.segs, e.up_partial.p, e.prow_seq.p + off);
+  }
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  // text prefill in groups of at most PR rows (reference tts_model.rs:944-964)
+  int i0 = 0;
+  while (i0 < n) {
+    int i1 = i0, rows = 0;
+    while (i1 < n && rows + (token_offsets[i1 + 1] - token_offsets[i1]) <= e.PR) { rows += token_offsets[i1 + 1] - token_offsets[i1]; ++i1; }
+    if (rows > 0) {
+      std::vector<int> rs(rows), rp(rows);
+      int r = 0;
+      for (int i = i0; i < i1; ++i)
+        for (int j = 0; j < token_offsets[i + 1] - token_offsets[i]; ++j, ++r) { rs[r] = free_slots[i]; rp[r] = voices[i]->v.len + j; }
+      PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, rs.data(), rows * 4, cudaMemcpyHostToDevice, e.stream));
+      PTTS_CUDA(cudaMemcpyAsync(e.prow_pos.p, rp.data(), rows * 4, cudaMemcpyHostToDevice, e.stream));
+      PTTS_CUDA(cudaMemcpyAsync(e.ptokens.p, tokens + token_offsets[i0], rows * 4, cudaMemcpyHostToDevice, e.stream));
+      embed_rows_kernel<<<rows, 256, 0, e.stream>>>(e.ptokens.p, rows, e.lut.p, e.px32.p);
+      ++e.launches;
+      e.prefill(rows);
+      PTTS_CUDA(cudaStreamSynchronize(e.stream));
+    }
+    i0 = i1;
+  }
+  e.row_seq_host.clear();
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+static void check_slots(Engine& e, const int32_t* slot_ids, int n) {
+  PTTS_REQUIRE(slot_ids && n >= 1 && n <= e.NB, PTTS_ERR_INVALID, "step: n = %d (max_batch %d)", n, e.NB);
+  for (int i = 0; i < n; ++i) {
+    const int s = slot_ids[i];
+    PTTS_REQUIRE(s >= 0 && s < e.NS && e.slots[s].in_use, PTTS_ERR_STATE, "step: slot %d is not open", s);
+    PTTS_REQUIRE(!e.slots[s].finished, PTTS_ERR_STATE, "step: slot %d already finished", s);
+    PTTS_REQUIRE(e.slots[s].own_len < e.KVCAP, PTTS_ERR_CAPACITY, "step: slot %d KV full", s);
+  }
+}
+
+int32_t ptts_step(ptts_engine* h, const int32_t* slot_ids, int32_t n, float* pcm_out, uint8_t* finished, float* latent_out,
+                  float* eos_logit_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  check_slots(e, slot_ids, n);
+  e.upload_rows(slot_ids, n);
+  e.step_kernels(n, nullptr);
+  if (pcm_out) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm, e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.pin_fin, e.finished_dev.p, n, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.pin_lat, e.latent_out.p, (size_t)n * LDIM * 4, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.pin_logit, e.logit_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  if (pcm_out) std::memcpy(pcm_out, e.pin_pcm, (size_t)n * FRAME * 4);
+  if (latent_out) std::memcpy(latent_out, e.pin_lat, (size_t)n * LDIM * 4);
+  if (eos_logit_out) std::memcpy(eos_logit_out, e.pin_logit, (size_t)n * 4);
+  for (int i = 0; i < n; ++i) {
+    SlotHost& sh = e.slots[slot_ids[i]];
+    sh.frames += 1; sh.own_len += 1;
+    sh.finished = e.pin_fin[i] != 0;
+    if (finished) finished[i] = e.pin_fin[i];
+  }
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_step_device(ptts_engine* h, const int32_t* slot_ids, int32_t n) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  check_slots(e, slot_ids, n);
+  e.upload_rows(slot_ids, n);
+  e.step_kernels(n, nullptr);
+  for (int i = 0; i < n; ++i) {
+    SlotHost& sh = e.slots[slot_ids[i]];
+    sh.frames += 1; sh.own_len += 1;
+    if (sh.frames >= sh.max_gen_len) sh.finished = true;  // EOS-based finish needs the flags: use ptts_step for that
+  }
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_step_timed(ptts_engine* h, const int32_t* slot_ids, int32_t n, float* stage_ms) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && stage_ms, PTTS_ERR_INVALID, "null argument");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  check_slots(e, slot_ids, n);
+  e.upload_rows(slot_ids, n);
+  e.step_kernels(n, stage_ms);
+  for (int i = 0; i < n; ++i) {
+    SlotHost& sh = e.slots[slot_ids[i]];
+    sh.frames += 1; sh.own_len += 1;
+    if (sh.frames >= sh.max_gen_len) sh.finished = true;
+  }
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_sync(ptts_engine* h) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+  PTTS_CUDA(cudaStreamSynchronize(h->e.stream));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_stream_set_feedback(ptts_engine* h, int32_t slot, const float* latent32) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && latent32, PTTS_ERR_INVALID, "null argument");
+  Engine& e = h->e;
+  PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  PTTS_CUDA(cudaMemcpyAsync(e.feedback.p + (size_t)slot * LDIM, latent32, LDIM * 4, cudaMemcpyHostToDevice, e.stream));
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_stream_close(ptts_engine* h, int32_t slot) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  Engine& e = h->e;
+  PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  e.slots[slot] = SlotHost{};
+  e.row_seq_host.clear();
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_stream_frames(ptts_engine* h, int32_t slot, int32_t* frames_out, int32_t* eos_step_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  Engine& e = h->e;
+  PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  StreamCtl c;
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  PTTS_CUDA(cudaMemcpy(&c, e.ctl.p + slot, sizeof c, cudaMemcpyDeviceToHost));
+  if (frames_out) *frames_out = c.frame;
+  if (eos_step_out) *eos_step_out = c.eos_step;
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int64_t ptts_debug_read(ptts_engine* h, const char* name, int32_t row, float* out, int64_t cap) {
+  try {
+    PTTS_REQUIRE(h && name && out, PTTS_ERR_INVALID, "null argument");
+    Engine& e = h->e;
+    PTTS_REQUIRE(row >= 0 && row < e.NB, PTTS_ERR_INVALID, "row %d out of range", row);
+    PTTS_CUDA(cudaSetDevice(e.cfg.device));
+    PTTS_CUDA(cudaStreamSynchronize(e.stream));
+    const std::string n(name);
+    const float* src = nullptr;
+    int64_t cnt = 0;
+    if (n == "flowlm.x") { src = e.x32.p + (size_t)row * D_MODEL; cnt = D_MODEL; }
+    else if (n == "flowlm.h") { src = e.h32dbg.p + (size_t)row * D_MODEL; cnt = D_MODEL; }
+    else if (n == "flowlm.qkv") { src = e.qkv32.p + (size_t)row * 3 * D_MODEL; cnt = 3 * D_MODEL; }
+    else if (n == "flow.c") { src = e.c32.p + (size_t)row * FLOW_DIM; cnt = FLOW_DIM; }
+    else if (n == "flow.x") { src = e.fx32.p + (size_t)row * FLOW_DIM; cnt = FLOW_DIM; }
+    else if (n == "mimi.quantized") { src = e.quant_dbg.p + (size_t)row * 512; cnt = 512; }
+    else if (n == "mimi.after_decoder_transformer") { src = e.mx32.p + (size_t)row * 16 * 512; cnt = 16 * 512; }
+    else if (n == "seanet.convtr2") { src = e.x2.p + (size_t)row * 96 * 256; cnt = 96 * 256; }
+    else if (n == "seanet.convtr5") { src = e.x5.p + (size_t)row * 480 * 128; cnt = 480 * 128; }
+    else if (n == "seanet.convtr8") { src = e.x8.p + (size_t)row * 1920 * 64; cnt = 1920 * 64; }
+    else if (n == "pcm") { src = e.pcm.p + (size_t)row * FRAME; cnt = FRAME; }
+    else PTTS_REQUIRE(false, PTTS_ERR_INVALID, "unknown tap '%s'", name);
+    PTTS_REQUIRE(cnt <= cap, PTTS_ERR_INVALID, "tap '%s' needs %lld floats, buffer holds %lld", name, (long long)cnt, (long long)cap);
+    PTTS_CUDA(cudaMemcpy(out, src, cnt * 4, cudaMemcpyDeviceToHost));
+    return cnt;
+  } catch (const ptts::Error& ex) {
+    g_last_error = ex.what();
+    return ex.code;
+  }
+}
+
+int64_t ptts_launch_count(ptts_engine* h, int32_t reset) {
+  if (!h) return -1;
+  const long long v = h->e.launches;
+  if (reset) h->e.launches = 0;
+  return v;
+}
+
+void* ptts_cuda_stream(ptts_engine* h) { return h ? (void*)h->e.stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ isolated kernel tests
+struct TestCtx {
+  Engine e;
+  explicit TestCtx(int device, int use_simt) {
+    int ndev = 0;
+    PTTS_CUDA(cudaGetDeviceCount(&ndev));
+    PTTS_REQUIRE(device >= 0 && device < ndev, PTTS_ERR_CUDA, "CUDA device %d not present", device);
+    PTTS_CUDA(cudaSetDevice(device));
+    e.cfg.device = device;
+    e.cfg.debug_gemm = use_simt;
+    PTTS_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+    PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+};
+
+static void to_f16_dev(DevBuf<__half>& dst, const float* src, size_t n) {
+  std::vector<__half> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = __float2half_rn(src[i]);
+  dst.alloc(n);
+  PTTS_CUDA(cudaMemcpy(dst.p, h.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+}
+
+int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const float* bias, float* d, int32_t rows,
+                       int32_t feats, int32_t k, int32_t mode, int32_t split_k, int32_t act, int32_t use_simt) {
+  PTTS_TRY
+  PTTS_REQUIRE(a && w && d && rows > 0 && feats > 0 && k > 0 && k % 64 == 0, PTTS_ERR_INVALID, "bad test_gemm arguments");
+  TestCtx t(device, use_simt);
+  Engine& e = t.e;
+  e.cfg.reserved[0] = mode;
+  DevBuf<__half> a16;
+  to_f16_dev(a16, a, (size_t)rows * k);
+  Weight16 w16;
+  upload_f16(w16, std::vector<float>(w, w + (size_t)feats * k), feats, k);
+  DevBuf<float> out, bd;
+  out.alloc((size_t)rows * feats);
+  if (bias) { bd.alloc(feats); PTTS_CUDA(cudaMemcpy(bd.p, bias, feats * 4, cudaMemcpyHostToDevice)); }
+  GemmEpi ep = epi_none();
+  ep.bias = bias ? bd.p : nullptr; ep.act = act; ep.out32 = out.p; ep.out32_map = plain_map(feats);
+  if (split_k > 1) { ep.atomic = 1; ep.res = out.p; ep.res_map = plain_map(feats); }
+  e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  PTTS_CUDA(cudaMemcpy(d, out.p, (size_t)rows * feats * 4, cudaMemcpyDeviceToHost));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+static void pick_tile(int T, int* R, int* G) {
+  if (T <= 128) { *R = T; *G = std::max(1, 128 / T); }
+  else if (T % 128 == 0) { *R = 128; *G = 1; }
+  else if (T % 120 == 0) { *R = 120; *G = 1; }
+  else { *R = 128; *G = 1; }
+}
+
+int32_t ptts_test_conv1d(int32_t device, const float* x, const float* prev, const float* w, const float* bias, float* y,
+                         int32_t n, int32_t t, int32_t cin, int32_t cout, int32_t k) {
+  PTTS_TRY
+  PTTS_REQUIRE(x && w && bias && y && n > 0 && t > 0 && cin % 64 == 0 && k >= 1, PTTS_ERR_INVALID, "bad test_conv1d arguments");
+  TestCtx tc(device, 0);
+  Engine& e = tc.e;
+  const int pad = k - 1, tp = pad + t;
+  std::vector<float> xp((size_t)n * tp * cin, 0.f);
+  for (int b = 0; b < n; ++b) {
+    if (prev && pad) std::memcpy(&xp[(size_t)b * tp * cin], prev + (size_t)b * pad * cin, (size_t)pad * cin * 4);
+    std::memcpy(&xp[((size_t)b * tp + pad) * cin], x + (size_t)b * t * cin, (size_t)t * cin * 4);
+  }
+  DevBuf<__half> x16;
+  to_f16_dev(x16, xp.data(), xp.size());
+  HostTensor hw, hb;
+  hw.f32.assign(w, w + (size_t)cout * cin * k);
+  hb.f32.assign(bias, bias + cout);
+  Weight16 wg; DevBuf<float> bg;
+  conv_weight(wg, bg, hw, hb, cout, cin, k, cout, cin);
+  DevBuf<float> out;
+  out.alloc((size_t)n * t * cout);
+  GemmEpi ep = epi_none();
+  ep.bias = bg.p; ep.out32 = out.p; ep.out32_map = plain_map(cout);
+  int R, G;
+  pick_tile(t, &R, &G);
+  e.gemm(ActView{x16.p, cin, tp, n}, n, t, k, R, G, wg, cout, ep);
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  PTTS_CUDA(cudaMemcpy(y, out.p, out.n * 4, cudaMemcpyDeviceToHost));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_test_convtr1d(int32_t device, const float* x, const float* prev_row, const float* w, const float* bias, float* y,
+                           int32_t n, int32_t t, int32_t cin, int32_t cout, int32_t stride) {
+  PTTS_TRY
+  PTTS_REQUIRE(x && w && bias && y && n > 0 && t > 0 && cin % 64 == 0 && stride >= 1, PTTS_ERR_INVALID, "bad test_convtr1d arguments");
+  TestCtx tc(device, 0);
+  Engine& e = tc.e;
+  const int tp = 1 + t;
+  std::vector<float> xp((size_t)n * tp * cin, 0.f);
+  for (int b = 0; b < n; ++b) {
+    if (prev_row) std::memcpy(&xp[(size_t)b * tp * cin], prev_row + (size_t)b * cin, (size_t)cin * 4);
+    std::memcpy(&xp[((size_t)b * tp + 1) * cin], x + (size_t)b * t * cin, (size_t)t * cin * 4);
+  }
+  DevBuf<__half> x16;
+  to_f16_dev(x16, xp.data(), xp.size());
+  HostTensor hw, hb;
+  hw.f32.assign(w, w + (size_t)cin * cout * 2 * stride);
+  hb.f32.assign(bias, bias + cout);
+  Weight16 wg; DevBuf<float> bg;
+  convtr_weight(wg, bg, hw, hb, cin, cout, stride);
+  DevBuf<float> out;
+  out.alloc((size_t)n * t * stride * cout);
+  GemmEpi ep = epi_none();
+  ep.bias = bg.p; ep.out32 = out.p;
+  ep.out32_map = RowMap{t, stride * cout, (long long)t * stride * cout, 0};
+  int R, G;
+  pick_tile(t, &R, &G);
+  e.gemm(ActView{x16.p, cin, tp, n}, n, t, 2, R, G, wg, stride * cout, ep);
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  PTTS_CUDA(cudaMemcpy(y, out.p, out.n * 4, cudaMemcpyDeviceToHost));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+}  // extern "C"

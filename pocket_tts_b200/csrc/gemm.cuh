@@ -1,0 +1,266 @@
+// One GEMM engine for every matrix product on the hot path.
+//
+//   D[r, f] = sum_k  A[r, k] * W[f, k]          (f16 operands, f32 accumulate in TMEM)
+//
+// A is an activation tensor kept channels-last as [stream][row][C]; a logical A row (stream b,
+// row t) is the window of `taps` consecutive stored rows t..t+taps-1, so K = taps*C.  With
+// taps = 1 this is a Linear layer; with taps = k it is the reference's causal StreamingConv1d
+// (modules/conv.rs:90-136: [previous | x] then a valid conv) as an implicit GEMM whose left
+// context rows simply sit in front of the body rows; with taps = 2 it is StreamingConvTranspose1d
+// with k = 2*stride (modules/conv.rs:219-267): y[t*s+rho] = x[t] W[:,:,rho] + x[t-1] W[:,:,rho+s],
+// i.e. N = s*Cout and the carried state is the previous input row instead of the partial sums.
+// No im2col buffer exists: the K loop walks (tap, 64-channel block) and offsets the TMA row
+// coordinate by the tap.
+//
+// Two operand placements share the kernel:
+//   swap = 0  activations on the 128-row MMA-M side, BN features on MMA-N   (rows >= 128: Mimi, SEANet)
+//   swap = 1  weights on the MMA-M side (128 features per tile), up to 256 activation rows on
+//             MMA-N, so a small decode batch wastes no MMA rows          (FlowLM decode, flow head)
+// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + tcgen05.mma issuer, warps 2-5 epilogue.
+#pragma once
+#include "ptx.cuh"
+
+namespace ptts {
+
+// Address of logical element (r, f) in an output / residual tensor:
+//   off = (r / T) * stream_stride + base + (r % T) * ld + f
+// which covers plain [rows, F] (T = INT_MAX) and the padded per-stream conv buffers.
+struct RowMap {
+  int T;
+  int ld;
+  long long stream_stride;
+  long long base;
+  __host__ __device__ long long off(int r, int f) const {
+    int b = r / T;
+    int t = r - b * T;
+    return static_cast<long long>(b) * stream_stride + base + static_cast<long long>(t) * ld + f;
+  }
+};
+inline RowMap plain_map(int ld) { return RowMap{0x7fffffff, ld, 0, 0}; }
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2, ACT_ELU = 3 };
+
+struct GemmEpi {
+  const float* bias;    // [F] or null
+  const float* fscale;  // [F] per-feature multiplier (LayerScale, modules/mlp.rs:71-73) or null
+  const float* gate;    // per-(r,f) multiplier (flow head gate, modules/mlp.rs:174-176) or null
+  RowMap gate_map;
+  const float* res;     // f32 residual input or null
+  RowMap res_map;
+  float* out32;         // f32 output or null
+  RowMap out32_map;
+  __half* out16;        // f16 output (next GEMM's operand) or null
+  RowMap out16_map;
+  int act;              // applied to acc + bias
+  int act16;            // applied to the f16 copy only (ELU in front of the next SEANet conv)
+  float alpha;          // multiplies after the activation
+  int atomic;           // split-K: out32 += v with red.global.add (epilogue must be linear)
+};
+
+struct GemmParams {
+  int swap;
+  int F, K;
+  int n_streams, T, R, G;   // activation rows = n_streams*T; one tile = G streams x R rows
+  int taps, cblocks;        // K blocks = taps * cblocks, cblocks = C/64
+  int BN;                   // MMA N
+  int kb_per_split;
+  int stages;
+  int tmem_cols;
+  GemmEpi epi;
+  // raw view, used by the SIMT cross-check kernel only
+  const __half* act;
+  long long act_stream_stride;
+  int act_ld;
+  const __half* w;
+};
+
+static constexpr int GEMM_BM = 128;
+static constexpr int GEMM_BK = 64;
+static constexpr int GEMM_THREADS = 192;
+
+__device__ __forceinline__ void epi_apply(const GemmEpi& e, float acc, int r, int f) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + f);
+  if (e.act == ACT_GELU) v = gelu_tanh(v);
+  else if (e.act == ACT_SILU) v = silu(v);
+  else if (e.act == ACT_ELU) v = elu1(v);
+  v *= e.alpha;
+  if (e.fscale) v *= __ldg(e.fscale + f);
+  if (e.gate) v *= e.gate[e.gate_map.off(r, f)];
+  if (e.atomic) {
+    atomicAdd(e.out32 + e.out32_map.off(r, f), v);
+    return;
+  }
+  if (e.res) v += e.res[e.res_map.off(r, f)];
+  if (e.out32) e.out32[e.out32_map.off(r, f)] = v;
+  if (e.out16) {
+    float h = (e.act16 == ACT_ELU) ? elu1(v) : v;
+    e.out16[e.out16_map.off(r, f)] = __float2half_rn(h);
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w,
+               const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (M tile 16 KB | N tile BN*128 B)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_tile_bytes = p.BN * GEMM_BK * 2;
+  const int m_tile_bytes = GEMM_BM * GEMM_BK * 2;
+  const int stage_bytes = m_tile_bytes + n_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int tiles_t = (p.T + p.R - 1) / p.R;
+  int act_tile, f0;
+  if (p.swap) {
+    f0 = blockIdx.x * GEMM_BM;
+    act_tile = blockIdx.y;
+  } else {
+    act_tile = blockIdx.x;
+    f0 = blockIdx.y * p.BN;
+  }
+  const int tb = act_tile / tiles_t;
+  const int b0 = tb * p.G;
+  const int t0 = (act_tile - tb * tiles_t) * p.R;
+  const int total_kb = p.taps * p.cblocks;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_act);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      const uint32_t act_bytes = p.swap ? n_tile_bytes : (GEMM_BK * p.R * p.G * 2);
+      const uint32_t w_bytes = p.swap ? m_tile_bytes : n_tile_bytes;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        const int kb = kb0 + i;
+        const int tap = kb / p.cblocks;
+        const int c0 = (kb - tap * p.cblocks) * GEMM_BK;
+        uint8_t* m_tile = smem + s * stage_bytes;
+        uint8_t* n_tile = m_tile + m_tile_bytes;
+        mbar_arrive_expect_tx(full_bar + s, act_bytes + w_bytes);
+        tma_load_3d(p.swap ? n_tile : m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
+        tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = make_idesc_f16_m128(p.BN);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % p.stages;
+      const uint32_t ph = (i / p.stages) & 1;
+      mbar_wait(full_bar + s, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t m_addr = smem_u32(smem + s * stage_bytes);
+        const uint64_t da = make_sw128_kmajor_desc(m_addr);
+        const uint64_t db = make_sw128_kmajor_desc(m_addr + m_tile_bytes);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // +32 B along K inside the 128-B swizzle row = +2 in the 16-byte address field
+          umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
+        }
+        umma_commit(empty_bar + s);  // frees this smem stage once the MMAs above have read it
+        if (i == nkb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
+    const int i = quad * 32 + lane;
+    const GemmEpi& e = p.epi;
+    int r_fixed = -1, f_fixed = -1;
+    if (p.swap) {
+      f_fixed = f0 + i;
+      if (f_fixed >= p.F) f_fixed = -1;
+    } else {
+      const int g = i / p.R;
+      const int tt = i - g * p.R;
+      const int b = b0 + g, t = t0 + tt;
+      if (g < p.G && b < p.n_streams && t < p.T) r_fixed = b * p.T + t;
+    }
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (p.swap) {
+        if (f_fixed >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int r = t0 + c + j;
+            if (r < p.T) epi_apply(e, __uint_as_float(v[j]), r, f_fixed);
+          }
+        }
+      } else {
+        if (r_fixed >= 0) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int f = f0 + c + j;
+            if (f < p.F) epi_apply(e, __uint_as_float(v[j]), r_fixed, f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// SIMT cross-check of the same contract (tests only; selected by ptts_engine_cfg.debug_gemm or
+// ptts_test_gemm(use_simt=1)).  One thread per output element.
+__global__ void gemm_simt_kernel(const GemmParams p) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long rows = static_cast<long long>(p.n_streams) * p.T;
+  if (idx >= rows * p.F) return;
+  const int r = static_cast<int>(idx / p.F);
+  const int f = static_cast<int>(idx - static_cast<long long>(r) * p.F);
+  const int b = r / p.T, t = r - b * p.T;
+  const int C = p.cblocks * GEMM_BK;
+  const __half* a = p.act + b * p.act_stream_stride + static_cast<long long>(t) * p.act_ld;
+  const __half* w = p.w + static_cast<long long>(f) * p.K;
+  float acc = 0.f;
+  for (int j = 0; j < p.taps; ++j)
+    for (int c = 0; c < C; ++c) acc += __half2float(a[j * p.act_ld + c]) * __half2float(w[j * C + c]);
+  GemmEpi e = p.epi;
+  e.atomic = 0;
+  if (p.epi.atomic) {  // emulate "+=" of the split-K epilogue
+    e.res = p.epi.out32;
+    e.res_map = p.epi.out32_map;
+  }
+  epi_apply(e, acc, r, f);
+}
+
+}  // namespace ptts

@@ -1,0 +1,550 @@
+// HBM-bound kernels of the hot path (everything that is not a matrix product): norms, RoPE +
+// KV-cache attention, the Mimi front end, the last SEANet conv, per-stream state movement and
+// the EOS bookkeeping.  128-bit loads where rows are contiguous, warp-shuffle reductions,
+// f32 math throughout; f16 only as storage for GEMM operands and KV rows.
+#pragma once
+#include "ptx.cuh"
+
+namespace ptts {
+
+static constexpr int HD = 64;           // head dim of both transformers
+static constexpr int LDIM = 32;         // latent dim
+static constexpr int MIMI_RING = 272;   // >= context(250) + 16 new rows - 1, see mimi_attn_kernel
+static constexpr int MIMI_CTX = 250;    // config/b6369a24.yaml:49
+static constexpr int FRAME = 1920;
+
+__constant__ float c_inv_freq[HD / 2];  // max_period^(-2i/64), reference modules/rope.rs:9-16
+
+struct StreamCtl {       // per slot, device resident
+  int max_gen_len;
+  int frames_after_eos;
+  float eos_threshold;
+  float temp;
+  unsigned long long seed;
+  const float* noise;    // device [max_gen_len, 32] or null
+  int frame;             // frames generated so far == index of the step being run
+  int eos_step;          // -1 until the first logit above threshold
+  int finished;
+  int pad;
+};
+
+// One resident sequence: its own KV rows plus an immutable shared prefix (the voice).
+// Layout of either buffer: [layer][k|v][head][cap][64] f16.
+struct SeqDesc {
+  __half* own;
+  const __half* prefix;
+  int own_cap;
+  int prefix_len;
+  int prefix_cap;
+  int pad;
+};
+
+__device__ __forceinline__ const __half* kv_row(const SeqDesc& s, int layer, int kv, int head, int n_heads, int i) {
+  if (i < s.prefix_len)
+    return s.prefix + ((static_cast<long long>(layer * 2 + kv) * n_heads + head) * s.prefix_cap + i) * HD;
+  return s.own + ((static_cast<long long>(layer * 2 + kv) * n_heads + head) * s.own_cap + (i - s.prefix_len)) * HD;
+}
+
+// ---------------------------------------------------------------- LayerNorm family
+// One warp per row.  out16 = LN(x) [* w + b] [* (1 + scale) + shift]   (reference modules/mlp.rs:29-58,135-137;
+// biased variance, eps inside the sqrt).  shift/scale rows live in the flow head's modulation buffer.
+template <int C>
+__global__ void ln_rows_kernel(const float* __restrict__ x, int rows, const float* __restrict__ w,
+                               const float* __restrict__ b, float eps, const float* __restrict__ shift,
+                               const float* __restrict__ scale, int mod_ld, __half* __restrict__ out16, int out_ld) {
+  constexpr int PER = C / 32;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  float v[PER];
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    float4 t = xr[i * 32 + lane];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float y = (v[4 * i + j] - mean) * rstd;
+      if (w) y = y * __ldg(w + c + j) + __ldg(b + c + j);
+      if (scale) y = y * (1.f + scale[static_cast<long long>(row) * mod_ld + c + j]) +
+                     shift[static_cast<long long>(row) * mod_ld + c + j];
+      o[j] = y;
+    }
+    __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(out16 + static_cast<long long>(row) * out_ld + c) = pk;
+  }
+}
+
+// out_norm + EOS head (reference models/flow_lm.rs:132-145): h16 = LN(x) for the flow head's cond_embed,
+// logit = <LN(x), w_eos> + b_eos in f32 (not from the f16 copy: the threshold compare must not see rounding).
+__global__ void ln_eos_kernel(const float* __restrict__ x, int rows, const float* __restrict__ w,
+                              const float* __restrict__ b, const float* __restrict__ w_eos, const float* __restrict__ b_eos,
+                              __half* __restrict__ h16, float* __restrict__ h32, float* __restrict__ eos_logit) {
+  constexpr int C = 1024, PER = 32;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  float v[PER];
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    float4 t = xr[i * 32 + lane];
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / C) + 1e-5f);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y = (v[4 * i + j] - mean) * rstd * __ldg(w + c + j) + __ldg(b + c + j);
+      dot += y * __ldg(w_eos + c + j);
+      h16[static_cast<long long>(row) * C + c + j] = __float2half_rn(y);
+      if (h32) h32[static_cast<long long>(row) * C + c + j] = y;
+    }
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) eos_logit[row] = dot + b_eos[0];
+}
+
+// ---------------------------------------------------------------- embedding gather (conditioners/text.rs:289-303)
+__global__ void embed_rows_kernel(const int* __restrict__ tokens, int rows, const float* __restrict__ lut,
+                                  float* __restrict__ x) {
+  const int row = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(lut + static_cast<long long>(tokens[row]) * 1024);
+  float4* dst = reinterpret_cast<float4*>(x + static_cast<long long>(row) * 1024);
+  dst[threadIdx.x] = src[threadIdx.x];  // 256 threads x 16 B
+}
+
+// ---------------------------------------------------------------- RoPE helper (modules/rope.rs:18-60)
+// pair i of a head: (x[2i], x[2i+1]) rotated by pos * inv_freq[i]
+__device__ __forceinline__ void rope_pair(float xr, float xi, int pos, int i, float& o_r, float& o_i) {
+  float s, c;
+  sincosf(static_cast<float>(pos) * c_inv_freq[i], &s, &c);
+  o_r = xr * c - xi * s;
+  o_i = xr * s + xi * c;
+}
+
+// softmax(q K^T / 8) V over keys [k_begin, k_end) of one (sequence, layer, head); q in smem (f32, already
+// rotated); scores in smem.  Reference modules/sdpa.rs:36-82 (naive path), causal handled by the caller's range.
+// Block = 128 threads.  out: 64 floats in smem (red[0..63]).
+__device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int head, int n_heads, const float* q_s,
+                                             float* score_s, float* red_s, int n_keys) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // pass 1: one key per thread, full 64-dim dot from a 128-byte row (8 x 16 B loads)
+  float lmax = -INFINITY;
+  for (int i = tid; i < n_keys; i += 128) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, head, n_heads, i));
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u = kr[c];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __half22float2(h[j]);
+        acc += f.x * q_s[c * 8 + 2 * j] + f.y * q_s[c * 8 + 2 * j + 1];
+      }
+    }
+    acc *= 0.125f;  // 1/sqrt(64)
+    score_s[i] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) red_s[warp] = lmax;
+  __syncthreads();
+  const float gmax = fmaxf(fmaxf(red_s[0], red_s[1]), fmaxf(red_s[2], red_s[3]));
+  __syncthreads();
+  float lsum = 0.f;
+  for (int i = tid; i < n_keys; i += 128) {
+    const float p = expf(score_s[i] - gmax);
+    score_s[i] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) red_s[warp] = lsum;
+  __syncthreads();
+  const float inv = 1.f / (red_s[0] + red_s[1] + red_s[2] + red_s[3]);
+  __syncthreads();
+  // pass 2: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1 (one coalesced 128-B row per warp)
+  float a0 = 0.f, a1 = 0.f;
+  for (int i = warp; i < n_keys; i += 4) {
+    const __half2 hv = reinterpret_cast<const __half2*>(kv_row(sd, layer, 1, head, n_heads, i))[lane];
+    const float2 f = __half22float2(hv);
+    const float p = score_s[i];
+    a0 += p * f.x;
+    a1 += p * f.y;
+  }
+  red_s[warp * 64 + 2 * lane] = a0;
+  red_s[warp * 64 + 2 * lane + 1] = a1;
+  __syncthreads();
+  if (tid < 64) red_s[256 + tid] = (red_s[tid] + red_s[64 + tid] + red_s[128 + tid] + red_s[192 + tid]) * inv;
+  __syncthreads();
+}
+
+// FlowLM decode attention, one new row per stream (reference modules/attention.rs:104-231 with t = 1):
+// RoPE(q,k) at the absolute position, append K,V at the cursor, causal SDPA over prefix + own rows, all fused.
+// grid (n, heads), block 128, dyn smem = (max_keys + 64 + 320) floats.
+__global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
+                                          const SeqDesc* __restrict__ seqs, const int* __restrict__ own_len, int layer,
+                                          int n_heads, __half* __restrict__ out16) {
+  extern __shared__ float sm[];
+  float* q_s = sm;          // 64
+  float* red_s = sm + 64;   // 320
+  float* score_s = sm + 384;
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int d_model = n_heads * HD;
+  const int seq = row_seq[b];
+  const SeqDesc sd = seqs[seq];
+  const int lo = own_len[seq];
+  const int pos = sd.prefix_len + lo;
+  const float* row = qkv + static_cast<long long>(b) * 3 * d_model;
+  if (tid < 32) {
+    float qr, qi, kr, ki;
+    rope_pair(row[h * HD + 2 * tid], row[h * HD + 2 * tid + 1], pos, tid, qr, qi);
+    rope_pair(row[d_model + h * HD + 2 * tid], row[d_model + h * HD + 2 * tid + 1], pos, tid, kr, ki);
+    q_s[2 * tid] = qr;
+    q_s[2 * tid + 1] = qi;
+    __half* kd = const_cast<__half*>(kv_row(sd, layer, 0, h, n_heads, pos));
+    __half* vd = const_cast<__half*>(kv_row(sd, layer, 1, h, n_heads, pos));
+    reinterpret_cast<__half2*>(kd)[tid] = __floats2half2_rn(kr, ki);
+    reinterpret_cast<__half2*>(vd)[tid] =
+        __floats2half2_rn(row[2 * d_model + h * HD + 2 * tid], row[2 * d_model + h * HD + 2 * tid + 1]);
+  }
+  __syncthreads();
+  attend_block(sd, layer, h, n_heads, q_s, score_s, red_s, pos + 1);
+  if (tid < 64) out16[static_cast<long long>(b) * d_model + h * HD + tid] = __float2half_rn(red_s[256 + tid]);
+}
+
+// Prefill, step 1: RoPE + KV append for every new row (rows of several sequences at once); rotated q kept in f32.
+// grid (rows, heads), block 32.
+__global__ void flowlm_rope_append_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
+                                          const int* __restrict__ row_pos, const SeqDesc* __restrict__ seqs, int layer,
+                                          int n_heads, float* __restrict__ q_rot) {
+  const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int d_model = n_heads * HD;
+  const SeqDesc sd = seqs[row_seq[r]];
+  const int pos = row_pos[r];
+  const float* row = qkv + static_cast<long long>(r) * 3 * d_model;
+  float qr, qi, kr, ki;
+  rope_pair(row[h * HD + 2 * tid], row[h * HD + 2 * tid + 1], pos, tid, qr, qi);
+  rope_pair(row[d_model + h * HD + 2 * tid], row[d_model + h * HD + 2 * tid + 1], pos, tid, kr, ki);
+  q_rot[static_cast<long long>(r) * d_model + h * HD + 2 * tid] = qr;
+  q_rot[static_cast<long long>(r) * d_model + h * HD + 2 * tid + 1] = qi;
+  __half* kd = const_cast<__half*>(kv_row(sd, layer, 0, h, n_heads, pos));
+  __half* vd = const_cast<__half*>(kv_row(sd, layer, 1, h, n_heads, pos));
+  reinterpret_cast<__half2*>(kd)[tid] = __floats2half2_rn(kr, ki);
+  reinterpret_cast<__half2*>(vd)[tid] =
+      __floats2half2_rn(row[2 * d_model + h * HD + 2 * tid], row[2 * d_model + h * HD + 2 * tid + 1]);
+}
+
+// Prefill, step 2: causal attention of each new row over keys [0, pos] (reference sdpa.rs:36-82 with the
+// causal mask of :129-171; shift = Lk - Lq makes row i see keys <= its absolute position).
+__global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, const int* __restrict__ row_seq,
+                                           const int* __restrict__ row_pos, const SeqDesc* __restrict__ seqs, int layer,
+                                           int n_heads, __half* __restrict__ out16) {
+  extern __shared__ float sm[];
+  float* q_s = sm;
+  float* red_s = sm + 64;
+  float* score_s = sm + 384;
+  const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int d_model = n_heads * HD;
+  const SeqDesc sd = seqs[row_seq[r]];
+  const int pos = row_pos[r];
+  if (tid < 64) q_s[tid] = q_rot[static_cast<long long>(r) * d_model + h * HD + tid];
+  __syncthreads();
+  attend_block(sd, layer, h, n_heads, q_s, score_s, red_s, pos + 1);
+  if (tid < 64) out16[static_cast<long long>(r) * d_model + h * HD + tid] = __float2half_rn(red_s[256 + tid]);
+}
+
+// ---------------------------------------------------------------- Mimi front end
+// latent de-norm (tts_model.rs:1033-1035) -> Quantizer 1x1 conv 32->512 (mimi.rs:32-36) -> depthwise
+// ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid n, block 512 (one channel each).
+__global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __restrict__ row_seq,
+                                     const float* __restrict__ emb_std, const float* __restrict__ emb_mean,
+                                     const float* __restrict__ wq /*[512,32]*/, const float* __restrict__ wup /*[512,32]*/,
+                                     float* __restrict__ partial /*[slots,16,512]*/, float* __restrict__ x /*[n*16,512]*/,
+                                     float* __restrict__ dbg_quant) {
+  __shared__ float zd[LDIM];
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c < LDIM) zd[c] = z[b * LDIM + c] * emb_std[c] + emb_mean[c];
+  __syncthreads();
+  float qv = 0.f;
+#pragma unroll
+  for (int k = 0; k < LDIM; ++k) qv += wq[c * LDIM + k] * zd[k];
+  if (dbg_quant) dbg_quant[b * 512 + c] = qv;
+  float* part = partial + static_cast<long long>(row_seq[b]) * 16 * 512;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float head = qv * wup[c * 32 + j] + part[j * 512 + c];
+    part[j * 512 + c] = qv * wup[c * 32 + 16 + j];
+    x[(static_cast<long long>(b) * 16 + j) * 512 + c] = head;
+  }
+}
+
+// Mimi decoder-transformer attention: 16 new rows per stream, sliding window of 250 positions
+// (reference attention.rs:167-264 ring + sdpa.rs:129-171 mask: query at position p sees keys in (p-250, p]).
+// K,V live in a per-slot ring indexed by position % 272; 272 >= 250 + 15 so the 16 rows written first never
+// overwrite a key that a query of this step still needs.  grid (n, 8 heads), block 128.
+__global__ void mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
+                                 const StreamCtl* __restrict__ ctl, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/,
+                                 int layer, int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
+  constexpr int NH = 8, DM = 512, T = 16, SW = MIMI_RING + 8;
+  __shared__ float q_s[T][HD];
+  __shared__ float p_s[T][SW];
+  __shared__ float inv_s[T];
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = row_seq[b];
+  const int p0 = ctl[slot].frame * T;  // absolute position of the first new row
+  __half* kring = ring + ((static_cast<long long>(slot) * n_layers + layer) * 2 * NH + h) * MIMI_RING * HD;
+  __half* vring = kring + static_cast<long long>(NH) * MIMI_RING * HD;
+  // RoPE + ring write: 16 rows x 32 pairs = 512 items over 128 threads
+  for (int it = tid; it < T * 32; it += 128) {
+    const int t = it >> 5, i = it & 31;
+    const float* row = qkv + (static_cast<long long>(b) * T + t) * 3 * DM;
+    float qr, qi, kr, ki;
+    rope_pair(row[h * HD + 2 * i], row[h * HD + 2 * i + 1], p0 + t, i, qr, qi);
+    rope_pair(row[DM + h * HD + 2 * i], row[DM + h * HD + 2 * i + 1], p0 + t, i, kr, ki);
+    q_s[t][2 * i] = qr;
+    q_s[t][2 * i + 1] = qi;
+    const int ri = (p0 + t) % MIMI_RING;
+    reinterpret_cast<__half2*>(kring + ri * HD)[i] = __floats2half2_rn(kr, ki);
+    reinterpret_cast<__half2*>(vring + ri * HD)[i] =
+        __floats2half2_rn(row[2 * DM + h * HD + 2 * i], row[2 * DM + h * HD + 2 * i + 1]);
+  }
+  __syncthreads();
+  // keys: positions [kmin, p0+15]; window of the first query starts at p0-249
+  const int kmin = max(0, p0 - (MIMI_CTX - 1));
+  const int nk = p0 + T - kmin;  // <= 265
+  for (int j = tid; j < nk; j += 128) {
+    const int kp = kmin + j;
+    const uint4* kr = reinterpret_cast<const uint4*>(kring + (kp % MIMI_RING) * HD);
+    float kf[HD];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u = kr[c];
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(hh[e]);
+        kf[c * 8 + 2 * e] = f.x;
+        kf[c * 8 + 2 * e + 1] = f.y;
+      }
+    }
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+      const int qp = p0 + t;
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc += kf[d] * q_s[t][d];
+      const bool ok = (kp <= qp) && (kp > qp - MIMI_CTX);
+      p_s[t][j] = ok ? acc * 0.125f : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // softmax per query row: warp w owns rows 4w..4w+3
+  for (int t = warp * 4; t < warp * 4 + 4; ++t) {
+    float m = -INFINITY;
+    for (int j = lane; j < nk; j += 32) m = fmaxf(m, p_s[t][j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      const float p = expf(p_s[t][j] - m);
+      p_s[t][j] = p;
+      s += p;
+    }
+    s = warp_sum(s);
+    if (lane == 0) inv_s[t] = 1.f / s;
+  }
+  __syncthreads();
+  // P V: warp w owns rows 4w..4w+3, lane owns dims 2*lane, 2*lane+1
+  float acc[4][2] = {};
+  for (int j = 0; j < nk; ++j) {
+    const int kp = kmin + j;
+    const float2 f = __half22float2(reinterpret_cast<const __half2*>(vring + (kp % MIMI_RING) * HD)[lane]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float p = p_s[warp * 4 + u][j];
+      acc[u][0] += p * f.x;
+      acc[u][1] += p * f.y;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int t = warp * 4 + u;
+    reinterpret_cast<__half2*>(out16 + (static_cast<long long>(b) * T + t) * DM + h * HD)[lane] =
+        __floats2half2_rn(acc[u][0] * inv_s[t], acc[u][1] * inv_s[t]);
+  }
+}
+
+// ---------------------------------------------------------------- flow head glue
+// y16[r, :] = silu(c[r, :] + te[:])   (reference modules/mlp.rs:328-330)
+__global__ void silu_add_kernel(const float* __restrict__ c, const float* __restrict__ te, int rows, int C,
+                                __half* __restrict__ y16) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * C) return;
+  const int col = static_cast<int>(i % C);
+  y16[i] = __float2half_rn(silu(c[i] + te[col]));
+}
+
+// ---------------------------------------------------------------- step begin / end
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+// Counter-based N(0,1): hash(seed, frame, lane) -> two uniforms -> Box-Muller.  Only used when the caller
+// injects no noise (throughput runs); parity runs inject the oracle's noise.
+__device__ __forceinline__ float counter_normal(unsigned long long seed, int frame, int k) {
+  uint32_t a = mix32(static_cast<uint32_t>(seed) ^ mix32(static_cast<uint32_t>(frame) * 0x9E3779B9U + k));
+  uint32_t b = mix32(static_cast<uint32_t>(seed >> 32) ^ mix32(a + 0x85EBCA6BU));
+  const float u1 = (static_cast<float>(a >> 8) + 1.f) * (1.f / 16777217.f);
+  const float u2 = static_cast<float>(b >> 8) * (1.f / 16777216.f);
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+// Gathers the AR feedback latent (BOS at frame 0, reference tts_model.rs:971,1065) as the f16 operand of
+// input_linear (K padded 32 -> 64) and the flow head's starting point x_0 (flow_lm.rs:148-153).
+__global__ void step_begin_kernel(const int* __restrict__ row_seq, const StreamCtl* __restrict__ ctl,
+                                  const float* __restrict__ feedback /*[slots,32]*/, __half* __restrict__ lat16 /*[n,64]*/,
+                                  float* __restrict__ z32 /*[n,32]*/, __half* __restrict__ z16 /*[n,64]*/) {
+  const int b = blockIdx.x, k = threadIdx.x;  // 64 threads
+  const int slot = row_seq[b];
+  const StreamCtl c = ctl[slot];
+  float lat = 0.f, z = 0.f;
+  if (k < LDIM) {
+    lat = feedback[slot * LDIM + k];
+    if (c.noise) z = c.noise[static_cast<long long>(c.frame) * LDIM + k];
+    else if (c.temp > 0.f) z = sqrtf(c.temp) * counter_normal(c.seed, c.frame, k);
+    z32[b * LDIM + k] = z;
+  }
+  lat16[b * 64 + k] = __float2half_rn(lat);
+  z16[b * 64 + k] = __float2half_rn(z);
+}
+
+// EOS bookkeeping of the frame loop (reference tts_model.rs:1055-1069, D2: the frame at
+// eos_step + frames_after_eos is still emitted) + AR feedback + cursor advance.
+__global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCtl* __restrict__ ctl,
+                                int* __restrict__ own_len, const float* __restrict__ eos_logit,
+                                const float* __restrict__ z32, float* __restrict__ feedback,
+                                unsigned char* __restrict__ finished_out, float* __restrict__ latent_out,
+                                float* __restrict__ logit_out) {
+  const int b = blockIdx.x, k = threadIdx.x;  // 32 threads
+  if (b >= n) return;
+  const int slot = row_seq[b];
+  const float zk = z32[b * LDIM + k];
+  feedback[slot * LDIM + k] = zk;
+  latent_out[b * LDIM + k] = zk;
+  if (k == 0) {
+    StreamCtl c = ctl[slot];
+    const int step = c.frame;
+    const float logit = eos_logit[b];
+    if (logit > c.eos_threshold && c.eos_step < 0) c.eos_step = step;
+    int fin = 0;
+    if (c.eos_step >= 0 && step >= c.eos_step + c.frames_after_eos) fin = 1;
+    if (step + 1 >= c.max_gen_len) fin = 1;
+    c.finished = fin;
+    c.frame = step + 1;
+    ctl[slot] = c;
+    own_len[slot] += 1;
+    finished_out[b] = static_cast<unsigned char>(fin);
+    logit_out[b] = logit;
+  }
+}
+
+// ---------------------------------------------------------------- SEANet tail and streaming state
+// Last layer: ELU (already applied by the producer) -> Conv1d 64->1 k3 (reference seanet.rs:379-392).
+// One thread per output sample; the 3x64 window of sample t is 384 contiguous bytes.
+__global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+1920][64]*/, const float* __restrict__ w /*[3][64]*/,
+                                         const float* __restrict__ bias, int n, float* __restrict__ pcm /*[n,1920]*/) {
+  __shared__ float w_s[192];
+  if (threadIdx.x < 192) w_s[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= FRAME) return;
+  const uint4* src = reinterpret_cast<const uint4*>(a + (static_cast<long long>(b) * (FRAME + 2) + t) * 64);
+  float acc = bias[0];
+#pragma unroll
+  for (int c = 0; c < 24; ++c) {
+    uint4 u = src[c];
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(h[j]);
+      acc += f.x * w_s[c * 8 + 2 * j] + f.y * w_s[c * 8 + 2 * j + 1];
+    }
+  }
+  pcm[static_cast<long long>(b) * FRAME + t] = acc;
+}
+
+// Left-context rows of every streaming conv (reference `previous`, conv.rs:125-128; and the previous input row
+// that replaces ConvTranspose1d's `partial`, conv.rs:246-262) move between the per-slot state and the head of
+// the compact per-batch-row activation buffers.
+struct ConvSeg {
+  __half* buf;      // [max_batch][pad + T][C]
+  __half* state;    // [slots][pad][C]
+  int pad, T, C, unused;
+};
+struct ConvSegs { ConvSeg s[8]; };
+
+__global__ void conv_state_move_kernel(const ConvSegs segs, const int* __restrict__ row_seq, int save) {
+  const ConvSeg g = segs.s[blockIdx.y];
+  const int b = blockIdx.x;
+  const int slot = row_seq[b];
+  const int n16 = g.pad * g.C / 8;  // 16-byte packets
+  uint4* st = reinterpret_cast<uint4*>(g.state + static_cast<long long>(slot) * g.pad * g.C);
+  uint4* hd = reinterpret_cast<uint4*>(g.buf + static_cast<long long>(b) * (g.pad + g.T) * g.C);
+  uint4* tl = reinterpret_cast<uint4*>(g.buf + (static_cast<long long>(b) * (g.pad + g.T) + g.T) * g.C);
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) {
+    if (save) st[i] = tl[i];
+    else hd[i] = st[i];
+  }
+}
+
+// Stream open: zero the per-slot streaming state (reference init_state zeros: conv.rs:71-88,205-217).
+__global__ void slot_reset_kernel(const ConvSegs segs, float* __restrict__ partial, const int* __restrict__ slot_list) {
+  const int slot = slot_list[blockIdx.x];
+  if (blockIdx.y < 8) {
+    const ConvSeg g = segs.s[blockIdx.y];
+    uint4* st = reinterpret_cast<uint4*>(g.state + static_cast<long long>(slot) * g.pad * g.C);
+    for (int i = threadIdx.x; i < g.pad * g.C / 8; i += blockDim.x) st[i] = make_uint4(0, 0, 0, 0);
+  } else {
+    float4* p = reinterpret_cast<float4*>(partial + static_cast<long long>(slot) * 16 * 512);
+    for (int i = threadIdx.x; i < 16 * 512 / 4; i += blockDim.x) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, float v, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
+}  // namespace ptts

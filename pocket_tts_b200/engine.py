@@ -1,0 +1,187 @@
+"""Python view of the C-ABI engine (numpy in / numpy out).  Used by tests and bench.py; a Rust or
+C++ host binds the same symbols."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineCfg, StreamParams, TensorDesc, check
+
+FRAME = 1920
+LDIM = 32
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class StreamSpec:
+    tokens: np.ndarray
+    max_gen_len: int
+    frames_after_eos: int = 3
+    eos_threshold: float = -4.0
+    temp: float = 0.7
+    seed: int = 0
+    noise: np.ndarray | None = None  # [max_gen_len, 32], already scaled by sqrt(temp)
+
+
+class Voice:
+    def __init__(self, engine: "Engine", handle):
+        self._engine, self._h = engine, handle
+
+    def __len__(self):
+        return int(_lib.lib().ptts_voice_len(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lib().ptts_voice_destroy(self._engine._h, self._h)
+            self._h = None
+
+
+class Engine:
+    def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
+                 kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0):
+        L = _lib.lib()
+        self._keep = []
+        descs = (TensorDesc * len(weights))()
+        for i, (name, arr) in enumerate(weights.items()):
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            self._keep.append(a)
+            descs[i].name = name.encode()
+            descs[i].dtype = 0
+            descs[i].ndim = a.ndim
+            for j, s in enumerate(a.shape):
+                descs[i].shape[j] = s
+            descs[i].data = a.ctypes.data
+        cfg = EngineCfg()
+        cfg.device, cfg.max_slots = device, max_slots
+        cfg.max_batch = max_batch or max_slots
+        cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, 0, 0, debug_gemm
+        cfg.reserved[0] = gemm_mode
+        h = C.c_void_p()
+        check(L.ptts_engine_create(C.byref(cfg), descs, len(weights), C.byref(h)))
+        self._h = h
+        self._keep = []
+        self.max_batch = cfg.max_batch
+
+    def close(self):
+        if self._h:
+            _lib.lib().ptts_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_lsd_steps(self, n: int):
+        check(_lib.lib().ptts_engine_set_lsd_steps(self._h, n))
+
+    def voice_from_prompt(self, audio_prompt: np.ndarray) -> Voice:
+        a = np.ascontiguousarray(audio_prompt, dtype=np.float32).reshape(-1, 1024)
+        h = C.c_void_p()
+        check(_lib.lib().ptts_voice_from_prompt(self._h, _ptr(a), a.shape[0], C.byref(h)))
+        return Voice(self, h)
+
+    def open_streams(self, voices: list[Voice], specs: list[StreamSpec]) -> np.ndarray:
+        n = len(specs)
+        toks = np.concatenate([np.asarray(s.tokens, dtype=np.int32) for s in specs]) if n else np.zeros(0, np.int32)
+        toks = np.ascontiguousarray(toks, dtype=np.int32)
+        offs = np.zeros(n + 1, np.int32)
+        offs[1:] = np.cumsum([len(s.tokens) for s in specs])
+        params = (StreamParams * n)()
+        keep = []
+        for i, s in enumerate(specs):
+            params[i].max_gen_len, params[i].frames_after_eos = s.max_gen_len, s.frames_after_eos
+            params[i].eos_threshold, params[i].temp, params[i].seed = s.eos_threshold, s.temp, s.seed
+            if s.noise is not None:
+                nz = np.ascontiguousarray(s.noise, dtype=np.float32)
+                assert nz.shape == (s.max_gen_len, LDIM), nz.shape
+                keep.append(nz)
+                params[i].noise = nz.ctypes.data
+        vh = (C.c_void_p * n)(*[v._h for v in voices])
+        slots = np.zeros(n, np.int32)
+        check(_lib.lib().ptts_streams_open(self._h, n, vh, _ptr(toks), _ptr(offs), params, _ptr(slots)))
+        return slots
+
+    def step(self, slots: np.ndarray, want_pcm: bool = True):
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        n = len(slots)
+        pcm = np.empty((n, FRAME), np.float32) if want_pcm else None
+        fin = np.zeros(n, np.uint8)
+        lat = np.empty((n, LDIM), np.float32)
+        logit = np.empty(n, np.float32)
+        check(_lib.lib().ptts_step(self._h, _ptr(slots), n, _ptr(pcm), _ptr(fin), _ptr(lat), _ptr(logit)))
+        return pcm, fin.astype(bool), lat, logit
+
+    def step_device(self, slots: np.ndarray):
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        check(_lib.lib().ptts_step_device(self._h, _ptr(slots), len(slots)))
+
+    def step_timed(self, slots: np.ndarray) -> np.ndarray:
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        ms = np.zeros(8, np.float32)
+        check(_lib.lib().ptts_step_timed(self._h, _ptr(slots), len(slots), _ptr(ms)))
+        return ms
+
+    def sync(self):
+        check(_lib.lib().ptts_sync(self._h))
+
+    def set_feedback(self, slot: int, latent: np.ndarray):
+        a = np.ascontiguousarray(latent, dtype=np.float32).reshape(LDIM)
+        check(_lib.lib().ptts_stream_set_feedback(self._h, int(slot), _ptr(a)))
+
+    def close_stream(self, slot: int):
+        check(_lib.lib().ptts_stream_close(self._h, int(slot)))
+
+    def stream_frames(self, slot: int) -> tuple[int, int]:
+        f, e = C.c_int32(), C.c_int32()
+        check(_lib.lib().ptts_stream_frames(self._h, int(slot), C.byref(f), C.byref(e)))
+        return f.value, e.value
+
+    def debug_read(self, name: str, row: int, cap: int = 1920 * 64) -> np.ndarray:
+        out = np.empty(cap, np.float32)
+        n = _lib.lib().ptts_debug_read(self._h, name.encode(), row, _ptr(out), cap)
+        check(int(n))
+        return out[:n].copy()
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(_lib.lib().ptts_launch_count(self._h, int(reset)))
+
+
+def test_gemm(a, w, bias=None, mode=0, split_k=1, act=0, use_simt=0, device=0):
+    a = np.ascontiguousarray(a, np.float32); w = np.ascontiguousarray(w, np.float32)
+    b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+    d = np.zeros((a.shape[0], w.shape[0]), np.float32)
+    check(_lib.lib().ptts_test_gemm(device, _ptr(a), _ptr(w), _ptr(b), _ptr(d), a.shape[0], w.shape[0], a.shape[1], mode,
+                                    split_k, act, use_simt))
+    return d
+
+
+def test_conv1d(x, prev, w, bias, device=0):
+    """x [n,t,cin], prev [n,k-1,cin] or None, w [cout,cin,k] -> y [n,t,cout]"""
+    x = np.ascontiguousarray(x, np.float32); w = np.ascontiguousarray(w, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    p = None if prev is None else np.ascontiguousarray(prev, np.float32)
+    n, t, cin = x.shape
+    cout, _, k = w.shape
+    y = np.zeros((n, t, cout), np.float32)
+    check(_lib.lib().ptts_test_conv1d(device, _ptr(x), _ptr(p), _ptr(w), _ptr(bias), _ptr(y), n, t, cin, cout, k))
+    return y
+
+
+def test_convtr1d(x, prev_row, w, bias, stride, device=0):
+    """x [n,t,cin], prev_row [n,cin] or None, w [cin,cout,2*stride] -> y [n,t*stride,cout]"""
+    x = np.ascontiguousarray(x, np.float32); w = np.ascontiguousarray(w, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    p = None if prev_row is None else np.ascontiguousarray(prev_row, np.float32)
+    n, t, cin = x.shape
+    cout = w.shape[1]
+    y = np.zeros((n, t * stride, cout), np.float32)
+    check(_lib.lib().ptts_test_convtr1d(device, _ptr(x), _ptr(p), _ptr(w), _ptr(bias), _ptr(y), n, t, cin, cout, stride))
+    return y

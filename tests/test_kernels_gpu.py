@@ -1,0 +1,90 @@
+"""Isolated kernels through the C ABI vs plain torch f32 references (operands rounded to f16 on both
+sides, so the only difference is accumulation order)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def f16r(a):
+    return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+def ref_gemm(a, w, bias=None, act=0):
+    d = torch.from_numpy(f16r(a)).double() @ torch.from_numpy(f16r(w)).double().T
+    if bias is not None:
+        d = d + torch.from_numpy(np.asarray(bias, np.float32)).double()
+    if act == 1:
+        d = F.gelu(d, approximate="tanh")
+    elif act == 2:
+        d = F.silu(d)
+    return d.float().numpy()
+
+
+GEMM_CASES = [
+    # rows, feats, k, mode (0 auto, 1 act-as-M, 2 weight-as-M), split_k, act
+    (64, 3072, 1024, 0, 1, 0),      # FlowLM in_proj at B=64 (swap-AB)
+    (1, 1024, 1024, 0, 1, 0),       # B=1
+    (64, 1024, 4096, 0, 8, 0),      # linear2 with atomic split-K
+    (64, 4096, 1024, 0, 1, 1),      # linear1 + tanh-GELU
+    (200, 512, 512, 0, 1, 2),       # flow head width, SiLU, ragged rows
+    (1024, 1536, 512, 0, 1, 0),     # Mimi in_proj at B=64 (activation-as-M)
+    (300, 640, 512, 1, 1, 0),       # ragged rows and features, activation-as-M
+    (1000, 72, 64, 1, 1, 0),        # tiny K, odd feature count
+    (64, 32, 512, 0, 1, 0),         # flow final linear (32 features)
+]
+
+
+@pytest.mark.parametrize("rows,feats,k,mode,split,act", GEMM_CASES)
+@pytest.mark.parametrize("simt", [0, 1])
+def test_gemm(rows, feats, k, mode, split, act, simt):
+    from pocket_tts_b200.engine import test_gemm as run
+    rng = np.random.default_rng(rows * 7 + feats)
+    a = rng.standard_normal((rows, k), dtype=np.float32)
+    w = rng.standard_normal((feats, k), dtype=np.float32) / np.sqrt(k)
+    bias = rng.standard_normal(feats, dtype=np.float32)
+    got = run(a, w, bias, mode=mode, split_k=split, act=act, use_simt=simt)
+    want = ref_gemm(a, w, bias, act)
+    err = np.abs(got - want).max()
+    assert err < 2e-3, f"max abs err {err}"
+
+
+CONV_CASES = [(3, 16, 512, 512, 7), (2, 96, 256, 128, 3), (2, 480, 128, 64, 3), (1, 1920, 64, 64, 3), (9, 16, 512, 64, 7)]
+
+
+@pytest.mark.parametrize("n,t,cin,cout,k", CONV_CASES)
+def test_streaming_conv1d(n, t, cin, cout, k):
+    from pocket_tts_b200.engine import test_conv1d as run
+    rng = np.random.default_rng(t + k)
+    x = rng.standard_normal((n, t, cin), dtype=np.float32)
+    prev = rng.standard_normal((n, k - 1, cin), dtype=np.float32)
+    w = rng.standard_normal((cout, cin, k), dtype=np.float32) / np.sqrt(cin * k)
+    b = rng.standard_normal(cout, dtype=np.float32)
+    got = run(x, prev, w, b)
+    xp = torch.from_numpy(f16r(np.concatenate([prev, x], axis=1))).permute(0, 2, 1)
+    want = F.conv1d(xp.double(), torch.from_numpy(f16r(w)).double(), torch.from_numpy(b).double()).permute(0, 2, 1).float().numpy()
+    err = np.abs(got - want).max()
+    assert err < 2e-3, f"max abs err {err}"
+
+
+CONVTR_CASES = [(3, 16, 512, 256, 6), (2, 96, 256, 128, 5), (2, 480, 128, 64, 4), (9, 16, 512, 256, 6)]
+
+
+@pytest.mark.parametrize("n,t,cin,cout,s", CONVTR_CASES)
+def test_streaming_convtr1d(n, t, cin, cout, s):
+    """y over [prev_row | x] must equal the reference's overlap-add with carried `partial`
+    (modules/conv.rs:219-267): partial = tail of convtr(prev_row) minus bias."""
+    from pocket_tts_b200.engine import test_convtr1d as run
+    rng = np.random.default_rng(t + s)
+    x = rng.standard_normal((n, t, cin), dtype=np.float32)
+    prev = rng.standard_normal((n, cin), dtype=np.float32)
+    w = rng.standard_normal((cin, cout, 2 * s), dtype=np.float32) / np.sqrt(2 * cin)
+    b = rng.standard_normal(cout, dtype=np.float32)
+    got = run(x, prev, w, b, s)
+    xin = torch.from_numpy(f16r(np.concatenate([prev[:, None], x], axis=1))).permute(0, 2, 1).double()
+    full = F.conv_transpose1d(xin, torch.from_numpy(f16r(w)).double(), torch.from_numpy(b).double(), stride=s)
+    want = full[:, :, s:s + t * s].permute(0, 2, 1).float().numpy()  # drop prev_row's own first s samples and the new tail
+    err = np.abs(got - want).max()
+    assert err < 2e-3, f"max abs err {err}"
