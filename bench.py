@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the Pocket TTS generation hot path on B200 (contract: see the task brief).
+
+Metric (BASELINE.json): audio-seconds generated per wall-second.
+Workload at every N: BASELINE.json configs[1] per GPU -- 64 concurrent ~10 s utterances
+(40 text tokens, 87-row voice prompt, 125 frames each, LSD 1, temp 0.7, EOS disabled so every stream
+runs its 125 frames), random-init b6369a24 weights, synthetic tokens.  Requests are sharded by GPU with
+no data-path collective (weak scaling: 64 streams per GPU).
+
+One "step" = one whole batch job: open 64 streams (embedding + text prefill) and run 125 decode steps
+(FlowLM step -> LSD flow head -> Mimi decode) for all of them.
+  value : device-resident run (ptts_step_device: PCM stays in HBM, no host sync inside the job)
+  e2e   : the same job through the public host call ptts_step with HOST buffers: token upload at open,
+          PCM + finished flags + latents copied back and the stream synchronised every frame.
+  --impl reference : the reference's CPU path (oracle port of the Candle implementation; the Rust crate
+          cannot be built here) on the box's host cores, one single-thread stream per core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FRAME_SEC = 0.08
+STREAMS, FRAMES, TOKENS, VOICE_ROWS = 64, 125, 40, 87
+METRIC = "audio-sec generated per wall-sec"
+UNIT = "audio_s/s"
+CONFIG = {"workload": "configs[1]: b6369a24 f16-operand batch 64 concurrent 10 s utterances (125 frames, 40 tokens, "
+                      "87-row voice), generate_stream, per GPU",
+          "streams_per_gpu": STREAMS, "frames_per_stream": FRAMES, "tokens_per_stream": TOKENS,
+          "voice_rows": VOICE_ROWS, "lsd_decode_steps": 1, "temp": 0.7, "parallelism": "request-sharded, no collective",
+          "l2": "no flush: per-step working set (190 MB weights + ~470 MB KV) exceeds the 126 MB L2"}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tf=float(d["bf16_tflops_sustained"]), src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def _cpu_worker(args):
+    """One reference stream on one core: the oracle (CPU restatement of the Candle path), f32, 1 thread."""
+    idx, frames, tokens_n = args
+    import torch
+    torch.set_num_threads(1)
+    from oracle import ptts_oracle as O
+    from pocket_tts_b200 import synth
+    W = O.to_torch(synth.make_weights(1234))
+    voice = O.voice_state_from_prompt(W, synth.make_voice_prompt(VOICE_ROWS, seed=7))
+    tok = synth.make_tokens(tokens_n, seed=1000 + idx)
+    noise = synth.make_noise(frames, seed=2000 + idx)
+    t0 = time.perf_counter()
+    O.generate_segment(W, voice, tok, noise, frames, 0, float("inf"))  # text prefill + frames
+    return time.perf_counter() - t0
+
+
+class CpuPool:
+    def __init__(self, procs):
+        import multiprocessing as mp
+        self.procs = procs
+        self.pool = mp.get_context("spawn").Pool(procs)
+
+    def run(self, frames):
+        t0 = time.perf_counter()
+        inner = self.pool.map(_cpu_worker, [(i, frames, TOKENS) for i in range(self.procs)])
+        wall = time.perf_counter() - t0
+        return wall, inner
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_sample(procs, frames, repeats=1):
+    """Returns audio-s per wall-s of `procs` single-thread streams generating `frames` frames each.
+    Wall time is the slowest worker's generate time (weight synthesis excluded)."""
+    pool = CpuPool(procs)
+    vals = []
+    try:
+        for _ in range(repeats):
+            _, inner = pool.run(frames)
+            vals.append(procs * frames * FRAME_SEC / max(inner))
+    finally:
+        pool.close()
+    return vals
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    frames = FRAMES  # bounded sample: the full 125-frame utterance, but only one stream per core instead of 64
+    pool = CpuPool(procs)
+    try:
+        for _ in range(args.warmup):
+            pool.run(2)
+        times = []
+        for _ in range(args.steps):
+            _, inner = pool.run(frames)
+            times.append(max(inner))
+    finally:
+        pool.close()
+    ms = 1000 * statistics.mean(times)
+    value = procs * frames * FRAME_SEC / (ms / 1000)
+    sample = f"{procs} single-thread oracle streams x {frames} frames (+40-token prefill) per step, f32"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from pocket_tts_b200 import synth
+    from pocket_tts_b200.engine import Engine, StreamSpec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE {world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wnp = synth.make_weights(1234)
+    eng = Engine(wnp, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3)
+    del wnp
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
+    base = rank * STREAMS  # request ids of this shard
+    specs = [StreamSpec(synth.make_tokens(TOKENS, seed=1000 + base + i), FRAMES, 3, 1e30, temp=0.7, seed=base + i)
+             for i in range(STREAMS)]
+    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
+
+    def job(host: bool, profile=None):
+        slots = eng.open_streams([voice] * STREAMS, specs)
+        for f in range(FRAMES):
+            if host:
+                pcm, fin, _, _ = eng.step(slots)
+            elif profile is not None and f in profile:
+                eng.profile(True); eng.step_device(slots); eng.profile(False)
+            else:
+                eng.step_device(slots)
+        eng.sync()
+        if host:
+            assert fin.all() and np.isfinite(pcm).all()
+        for s in slots:
+            eng.close_stream(int(s))
+
+    def timed(host: bool, steps: int, warmup: int):
+        for _ in range(warmup):
+            job(host)
+        barrier()
+        eng.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            job(host)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = eng.launch_count()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, launches
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, launches = timed(False, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(True, max(1, min(args.steps, 3)), 1)
+
+    audio_per_job = world * STREAMS * FRAMES * FRAME_SEC
+    line = {"metric": METRIC, "value": audio_per_job / (ms_dev / 1000), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 accumulate/residual", "data": "synthetic", "config": CONFIG, "clocks": clocks,
+            "e2e": {"value": audio_per_job / (ms_e2e / 1000), "unit": UNIT,
+                    "h2d_bytes_per_step": STREAMS * (TOKENS * 4 + 4 + 24) + FRAMES * STREAMS * 4,
+                    "d2h_bytes_per_step": FRAMES * STREAMS * (1920 * 4 + 1 + 32 * 4 + 4), "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "realtime_factor_per_gpu": STREAMS * FRAMES * FRAME_SEC / (ms_dev / 1000)}
+
+    if rank == 0:
+        # roofline pass: per-launch CUDA events on the engine's stream for 3 mid-utterance decode steps
+        job(False, profile={60, 61, 62})
+        rep = eng.profile_report()
+        pk = peaks()
+        tot = sum(v["ms"] for v in rep.values())
+        classes = []
+        for tag, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"]):
+            t_s = v["ms"] / 1000
+            gbs, tfs = v["bytes"] / t_s / 1e9, v["flops"] / t_s / 1e12
+            bound = "hbm" if v["bytes"] / (pk["hbm"] * 1e9) >= v["flops"] / (pk["tf"] * 1e12) else "tensor"
+            classes.append({"kernel": tag, "launches_per_step": v["launches"] / 3, "us_per_launch": 1000 * v["ms"] / v["launches"],
+                            "share": v["ms"] / tot, "bound": bound, "GB/s": gbs, "TFLOP/s": tfs,
+                            "frac": gbs / pk["hbm"] if bound == "hbm" else tfs / pk["tf"]})
+        top = classes[0]
+        v = rep[top["kernel"]]
+        line["roofline"] = {"kernel": top["kernel"], "bound": top["bound"],
+                            "achieved": top["GB/s"] if top["bound"] == "hbm" else top["TFLOP/s"],
+                            "peak": pk["hbm"] if top["bound"] == "hbm" else pk["tf"],
+                            "unit": "GB/s" if top["bound"] == "hbm" else "TFLOP/s", "frac": top["frac"], "traffic": None,
+                            "peak_source": pk["src"], "us_per_launch": top["us_per_launch"], "share_of_step": top["share"],
+                            "algorithmic_bytes_per_launch": v["bytes"] / v["launches"], "algorithmic_flops_per_launch": v["flops"] / v["launches"]}
+        line["kernel_classes"] = classes[:12]
+        line["step_device_us_sum_of_kernels"] = 1000 * tot / 3
+        # time to first audio: open -> first 1920-sample frame on the host, single stream (configs[0] shape)
+        ttfa = []
+        one = [StreamSpec(synth.make_tokens(12, seed=5), 52, 5, 1e30, temp=0.7, seed=1)]
+        for _ in range(12):
+            t0 = time.perf_counter()
+            s = eng.open_streams([voice], one)
+            eng.step(s)
+            ttfa.append(1000 * (time.perf_counter() - t0))
+            eng.close_stream(int(s[0]))
+        t0 = time.perf_counter()
+        s = eng.open_streams([voice] * STREAMS, specs)
+        eng.step(s)
+        t64 = 1000 * (time.perf_counter() - t0)
+        for x in s:
+            eng.close_stream(int(x))
+        line["ttfa_ms"] = {"p50_single_stream": statistics.median(ttfa[2:]), "batch64_first_frames": t64}
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            procs = max(1, min(cores, 32))
+            vals = cpu_sample(procs, FRAMES)
+            line["cpu_baseline"] = {"value": vals[0], "unit": UNIT, "cores": procs, "kind": "port",
+                                    "sample": f"{procs} single-thread oracle streams x {FRAMES} frames (+40-token prefill), f32, "
+                                              f"host has {cores} cores"}
+        print(json.dumps(line), flush=True)
+    voice.close()
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

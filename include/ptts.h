@@ -138,6 +138,11 @@ int64_t ptts_debug_read(ptts_engine* e, const char* name, int32_t row, float* ou
 int64_t ptts_launch_count(ptts_engine* e, int32_t reset);
 int32_t ptts_step_timed(ptts_engine* e, const int32_t* slots, int32_t n, float* stage_ms /*[8]*/);
 void* ptts_cuda_stream(ptts_engine* e);
+/* Per-launch CUDA-event profile for bench.py's roofline line.  While enabled every kernel launch is
+ * bracketed by events on the engine's stream; the report has one text line per kernel class:
+ * "<class> <launches> <total_ms> <algorithmic_bytes> <algorithmic_flops>".  Returns the string length. */
+int32_t ptts_profile_enable(ptts_engine* e, int32_t on);
+int64_t ptts_profile_report(ptts_engine* e, char* buf, int64_t cap);
 
 /* Isolated kernel entry points (tests/test_kernels_gpu.py): D[r,f] = sum_k A[r,k] * W[f,k] on
  * host f32 buffers, run through the production GEMM (operands converted to f16).  mode 0 lets the

@@ -68,6 +68,18 @@ struct Engine {
   TmapCache tmaps;
   long long launches = 0;
   int lsd_steps = 1;
+  // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
+  struct ProfRec { const char* tag; cudaEvent_t a, b; double bytes, flops; };
+  bool profiling = false;
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  const char* cur_tag = nullptr;
+  double step_kv_bytes = 0;  // FlowLM KV bytes one layer's decode attention reads in the current step
+  void tag(const char* t) { cur_tag = t; }
+  const char* take_tag(const char* dflt) { const char* t = cur_tag ? cur_tag : dflt; cur_tag = nullptr; return t; }
+  void prof_begin(const char* t, double bytes, double flops);
+  void prof_end();
+  std::string prof_report();
   int NB = 0, NS = 0, KVCAP = 0, PR = 0;  // max batch, slots, own kv rows, prefill rows
 
   // ---- weights
@@ -145,7 +157,47 @@ Engine::~Engine() {
   if (pin_lat) cudaFreeHost(pin_lat);
   if (pin_logit) cudaFreeHost(pin_logit);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
+  for (auto& e : prof_pool) cudaEventDestroy(e);
+  for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (stream) cudaStreamDestroy(stream);
+}
+
+void Engine::prof_begin(const char* t, double bytes, double flops) {
+  if (!profiling) return;
+  cudaEvent_t ev2[2];
+  for (auto& x : ev2) {
+    if (prof_pool.empty()) { cudaEvent_t n; PTTS_CUDA(cudaEventCreate(&n)); prof_pool.push_back(n); }
+    x = prof_pool.back();
+    prof_pool.pop_back();
+  }
+  PTTS_CUDA(cudaEventRecord(ev2[0], stream));
+  prof_recs.push_back(ProfRec{t, ev2[0], ev2[1], bytes, flops});
+}
+void Engine::prof_end() {
+  if (!profiling) return;
+  PTTS_CUDA(cudaEventRecord(prof_recs.back().b, stream));
+}
+struct ProfScope {
+  Engine& e;
+  ProfScope(Engine& en, const char* t, double bytes = 0, double flops = 0) : e(en) { e.prof_begin(t, bytes, flops); ++e.launches; }
+  ~ProfScope() { e.prof_end(); }
+};
+// one line per kernel class: "tag launches total_ms bytes flops" (bytes/flops are the algorithmic totals)
+std::string Engine::prof_report() {
+  PTTS_CUDA(cudaStreamSynchronize(stream));
+  struct Agg { int n = 0; double ms = 0, bytes = 0, flops = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : prof_recs) {
+    float ms = 0;
+    PTTS_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    Agg& g = agg[r.tag];
+    g.n++; g.ms += ms; g.bytes += r.bytes; g.flops += r.flops;
+    prof_pool.push_back(r.a); prof_pool.push_back(r.b);
+  }
+  prof_recs.clear();
+  std::string out;
+  for (auto& kv : agg) out += fmt("%s %d %.6f %.0f %.0f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------ weights
@@ -485,6 +537,11 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   p.tmem_cols = pow2_at_least(p.BN);
   const size_t smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
 
+  // algorithmic traffic: weights once, the distinct activation rows once, every epilogue tensor once
+  const double act_rows = (double)n_streams * (T + taps - 1);
+  double bytes = (double)F * w.K * 2 + act_rows * a.C * 2;
+  bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + ((epi.res || epi.atomic) ? 4 : 0) + (epi.gate ? 4 : 0));
+  ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K);
   if (cfg.debug_gemm) {
     const long long n = rows * F;
     gemm_simt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
@@ -494,7 +551,6 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
     gemm_tc_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ma, mw, p);
   }
-  ++launches;
   PTTS_CUDA(cudaGetLastError());
 }
 
@@ -502,8 +558,8 @@ template <int C>
 void Engine::ln(const float* x, int rows, const float* w, const float* b, float eps, const float* shift, const float* scale,
                 int mod_ld, __half* out, int out_ld) {
   if (rows <= 0) return;
+  ProfScope ps(*this, take_tag("layernorm"), (double)rows * C * (4 + 2 + (scale ? 8 : 0)), 0);
   ln_rows_kernel<C><<<(rows + 3) / 4, 128, 0, stream>>>(x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
-  ++launches;
 }
 
 static GemmEpi epi_none() {
@@ -518,40 +574,45 @@ static GemmEpi epi_none() {
 void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* attn, __half* ffn, bool is_prefill,
                            float* qrot, const int* rseq, const int* rpos) {
   for (int l = 0; l < N_LAYERS; ++l) {
-    ln<D_MODEL>(x, rows, ln1_w[l].p, ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
+    tag("flowlm.layernorm"); ln<D_MODEL>(x, rows, ln1_w[l].p, ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     GemmEpi e = epi_none();
     e.out32 = qkv; e.out32_map = plain_map(3 * D_MODEL);
-    gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
+    tag(is_prefill ? "prefill.in_proj" : "flowlm.in_proj"); gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
     if (is_prefill) {
-      flowlm_rope_append_kernel<<<dim3(rows, N_HEADS), 32, 0, stream>>>(qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot);
-      ++launches;
+      { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
+        flowlm_rope_append_kernel<<<dim3(rows, N_HEADS), 32, 0, stream>>>(qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
       if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
       const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
-      flowlm_attn_prefill_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qrot, rseq, rpos, seqs.p, l, N_HEADS, attn);
-      ++launches;
+      { ProfScope ps(*this, "prefill.attn");
+        flowlm_attn_prefill_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
       const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
-      flowlm_attn_decode_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn);
-      ++launches;
+      { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0);
+        flowlm_attn_decode_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
     }
     // x += attn W_o^T: split-K CTAs add their partial sums with red.add (epi.atomic); when the dispatcher
     // keeps one CTA per tile it clears `atomic` and the same epilogue reads the residual through epi.res.
     e = epi_none();
     e.out32 = x; e.out32_map = plain_map(D_MODEL); e.atomic = 1; e.res = x; e.res_map = plain_map(D_MODEL);
-    gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
-    ln<D_MODEL>(x, rows, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
+    tag(is_prefill ? "prefill.out_proj" : "flowlm.out_proj"); gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
+    tag("flowlm.layernorm"); ln<D_MODEL>(x, rows, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = ffn; e.out16_map = plain_map(D_FFN);
-    gemm_rows(h, rows, D_MODEL, w_lin1[l], D_FFN, e);
+    tag(is_prefill ? "prefill.linear1" : "flowlm.linear1"); gemm_rows(h, rows, D_MODEL, w_lin1[l], D_FFN, e);
     e = epi_none();
     e.out32 = x; e.out32_map = plain_map(D_MODEL); e.atomic = 1; e.res = x; e.res_map = plain_map(D_MODEL);
-    gemm_rows(ffn, rows, D_FFN, w_lin2[l], D_MODEL, e, true);
+    tag(is_prefill ? "prefill.linear2" : "flowlm.linear2"); gemm_rows(ffn, rows, D_FFN, w_lin2[l], D_MODEL, e, true);
   }
 }
 
 
 // ------------------------------------------------------------------------------------------------ one decode step
 void Engine::upload_rows(const int* slot_ids, int n) {
+  step_kv_bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    const SlotHost& sh = slots[slot_ids[i]];
+    step_kv_bytes += (double)((sh.voice ? sh.voice->len : 0) + sh.own_len + 1) * N_HEADS * HD * 2 * 2;
+  }
   if ((int)row_seq_host.size() == n && std::equal(slot_ids, slot_ids + n, row_seq_host.begin())) return;
   row_seq_host.assign(slot_ids, slot_ids + n);
   PTTS_CUDA(cudaMemcpyAsync(row_seq.p, row_seq_host.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -563,68 +624,68 @@ void Engine::step_kernels(int n, float* stage_ms) {
   auto mark = [&](int i) { if (stage_ms) PTTS_CUDA(cudaEventRecord(ev[i], stream)); };
   mark(0);
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
-  step_begin_kernel<<<n, 64, 0, stream>>>(row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p);
-  ++launches;
+  { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
+    step_begin_kernel<<<n, 64, 0, stream>>>(row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p); }
   GemmEpi e = epi_none();
   e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
-  gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
+  tag("flowlm.input_linear"); gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
   flowlm_layers(n, x32.p, h16.p, qkv32.p, attn16.p, ffn16.p, false, nullptr, row_seq.p, nullptr);
-  ln_eos_kernel<<<(n + 3) / 4, 128, 0, stream>>>(x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,
-                                                 eos_logit.p);
-  ++launches;
+  { ProfScope ps(*this, "flowlm.out_norm_eos", (double)n * D_MODEL * (4 + 2 + 4), 0);
+    ln_eos_kernel<<<(n + 3) / 4, 128, 0, stream>>>(x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,
+                                                   eos_logit.p); }
   mark(1);
   // ---- LSD flow head (reference flow_lm.rs:7-22,156-161; modules/mlp.rs:275,322-383)
   e = epi_none();
   e.bias = b_cond.p; e.out32 = c32.p; e.out32_map = plain_map(FLOW_DIM);
-  gemm_rows(h16.p, n, D_MODEL, w_cond, FLOW_DIM, e);
+  tag("flow.cond_embed"); gemm_rows(h16.p, n, D_MODEL, w_cond, FLOW_DIM, e);
   for (int s = 0; s < lsd_steps; ++s) {
-    silu_add_kernel<<<(n * FLOW_DIM + 255) / 256, 256, 0, stream>>>(c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p);
-    ++launches;
+    { ProfScope ps(*this, "flow.silu_add", (double)n * FLOW_DIM * 6, 0);
+      silu_add_kernel<<<(n * FLOW_DIM + 255) / 256, 256, 0, stream>>>(c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p); }
     e = epi_none();
     e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
-    gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
+    tag("flow.adaln"); gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
     e = epi_none();
     e.bias = b_finproj.p; e.out32 = fx32.p; e.out32_map = plain_map(FLOW_DIM);
-    gemm_rows(z16.p, n, 64, w_finproj, FLOW_DIM, e);
+    tag("flow.input_proj"); gemm_rows(z16.p, n, 64, w_finproj, FLOW_DIM, e);
     for (int i = 0; i < FLOW_DEPTH; ++i) {
       const float* shift = mod32.p + (size_t)i * 3 * FLOW_DIM;
-      ln<FLOW_DIM>(fx32.p, n, inln_w[i].p, inln_b[i].p, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
+      tag("flow.ln_modulate"); ln<FLOW_DIM>(fx32.p, n, inln_w[i].p, inln_b[i].p, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
       e = epi_none();
       e.bias = b_mlp0[i].p; e.act = ACT_SILU; e.out16 = fg16.p; e.out16_map = plain_map(FLOW_DIM);
-      gemm_rows(fh16.p, n, FLOW_DIM, w_mlp0[i], FLOW_DIM, e);
+      tag("flow.mlp0"); gemm_rows(fh16.p, n, FLOW_DIM, w_mlp0[i], FLOW_DIM, e);
       e = epi_none();
       e.bias = b_mlp2[i].p; e.gate = shift + 2 * FLOW_DIM; e.gate_map = plain_map(MOD_LD);
       e.res = fx32.p; e.res_map = plain_map(FLOW_DIM); e.out32 = fx32.p; e.out32_map = plain_map(FLOW_DIM);
-      gemm_rows(fg16.p, n, FLOW_DIM, w_mlp2[i], FLOW_DIM, e);
+      tag("flow.mlp2"); gemm_rows(fg16.p, n, FLOW_DIM, w_mlp2[i], FLOW_DIM, e);
     }
     const float* shift = mod32.p + (size_t)FLOW_DEPTH * 3 * FLOW_DIM;
-    ln<FLOW_DIM>(fx32.p, n, nullptr, nullptr, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
+    tag("flow.ln_modulate"); ln<FLOW_DIM>(fx32.p, n, nullptr, nullptr, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
     e = epi_none();  // z += (W h + b) / S   (Euler step, flow_lm.rs:15-19)
     e.bias = b_final.p; e.alpha = 1.f / (float)lsd_steps; e.res = z32.p; e.res_map = plain_map(LDIM);
     e.out32 = z32.p; e.out32_map = plain_map(LDIM); e.out16 = z16.p; e.out16_map = plain_map(64);
-    gemm_rows(fh16.p, n, FLOW_DIM, w_final, LDIM, e);
+    tag("flow.final"); gemm_rows(fh16.p, n, FLOW_DIM, w_final, LDIM, e);
   }
   mark(2);
   // ---- Mimi: de-norm + quantizer + upsample, decoder transformer (reference mimi.rs:143-157, transformer.rs:227-251)
   const int MR = n * MIMI_T;
-  mimi_frontend_kernel<<<n, 512, 0, stream>>>(z32.p, row_seq.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
-                                             quant_dbg.p);
-  ++launches;
+  { ProfScope ps(*this, "mimi.frontend", (double)n * 16 * 512 * 12, 0);
+    mimi_frontend_kernel<<<n, 512, 0, stream>>>(z32.p, row_seq.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
+                                               quant_dbg.p); }
   for (int l = 0; l < MIMI_LAYERS; ++l) {
-    ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[l].p, m_ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
+    tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[l].p, m_ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     e = epi_none();
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
-    gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
-    mimi_attn_kernel<<<dim3(n, MIMI_HEADS), 128, 0, stream>>>(mqkv32.p, row_seq.p, ctl.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p);
-    ++launches;
+    tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
+    { ProfScope ps(*this, "mimi.attn", (double)n * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0);
+      mimi_attn_kernel<<<dim3(n, MIMI_HEADS), 128, 0, stream>>>(mqkv32.p, row_seq.p, ctl.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
     e.atomic = 1;
-    gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);
-    ln<MIMI_DIM>(mx32.p, MR, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
+    tag("mimi.out_proj"); gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);
+    tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = mffn16.p; e.out16_map = plain_map(MIMI_FFN);
-    gemm_rows(mh16.p, MR, MIMI_DIM, m_lin1[l], MIMI_FFN, e);
+    tag("mimi.linear1"); gemm_rows(mh16.p, MR, MIMI_DIM, m_lin1[l], MIMI_FFN, e);
     e = epi_none();
     e.fscale = m_ls2[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
     const bool last = (l == MIMI_LAYERS - 1);
@@ -633,47 +694,47 @@ void Engine::step_kernels(int n, float* stage_ms) {
     } else {
       e.atomic = 1;
     }
-    gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
+    tag("mimi.linear2"); gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
   }
   mark(3);
   // ---- SEANet decoder (reference seanet.rs:309-402) as implicit GEMMs; ELU fused into the producer's epilogue
-  conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 0);
-  ++launches;
+  { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
+    conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 0); }
   e = epi_none(); e.bias = sb_conv0.p; e.out16 = a0.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 512, 17 * 512, 512);
-  gemm(ActView{tr16.p, 512, 22, NB}, n, 16, 7, 16, 8, s_conv0, 512, e);
+  tag("seanet.conv0"); gemm(ActView{tr16.p, 512, 22, NB}, n, 16, 7, 16, 8, s_conv0, 512, e);
   e = epi_none(); e.bias = sb_ct2.p; e.out32 = x2.p; e.out32_map = stream_map(16, 1536, 96 * 256, 0);
   e.out16 = e2.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 1536, 98 * 256, 2 * 256);
-  gemm(ActView{a0.p, 512, 17, NB}, n, 16, 2, 16, 8, s_ct2, 1536, e);
+  tag("seanet.convtr2"); gemm(ActView{a0.p, 512, 17, NB}, n, 16, 2, 16, 8, s_ct2, 1536, e);
   e = epi_none(); e.bias = sb_r3a.p; e.out16 = h3.p; e.act16 = ACT_ELU; e.out16_map = plain_map(128);
-  gemm(ActView{e2.p, 256, 98, NB}, n, 96, 3, 96, 1, s_r3a, 128, e);
+  tag("seanet.res3a"); gemm(ActView{e2.p, 256, 98, NB}, n, 96, 3, 96, 1, s_r3a, 128, e);
   e = epi_none(); e.bias = sb_r3b.p; e.res = x2.p; e.res_map = plain_map(256);
   e.out16 = a3.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 256, 97 * 256, 256);
-  gemm_rows(h3.p, n * 96, 128, s_r3b, 256, e);
+  tag("seanet.res3b"); gemm_rows(h3.p, n * 96, 128, s_r3b, 256, e);
   e = epi_none(); e.bias = sb_ct5.p; e.out32 = x5.p; e.out32_map = stream_map(96, 640, 480 * 128, 0);
   e.out16 = e5.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 640, 482 * 128, 2 * 128);
-  gemm(ActView{a3.p, 256, 97, NB}, n, 96, 2, 96, 1, s_ct5, 640, e);
+  tag("seanet.convtr5"); gemm(ActView{a3.p, 256, 97, NB}, n, 96, 2, 96, 1, s_ct5, 640, e);
   e = epi_none(); e.bias = sb_r6a.p; e.out16 = h6.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
-  gemm(ActView{e5.p, 128, 482, NB}, n, 480, 3, 120, 1, s_r6a, 64, e);
+  tag("seanet.res6a"); gemm(ActView{e5.p, 128, 482, NB}, n, 480, 3, 120, 1, s_r6a, 64, e);
   e = epi_none(); e.bias = sb_r6b.p; e.res = x5.p; e.res_map = plain_map(128);
   e.out16 = a6.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 128, 481 * 128, 128);
-  gemm_rows(h6.p, n * 480, 64, s_r6b, 128, e);
+  tag("seanet.res6b"); gemm_rows(h6.p, n * 480, 64, s_r6b, 128, e);
   e = epi_none(); e.bias = sb_ct8.p; e.out32 = x8.p; e.out32_map = stream_map(480, 256, 1920 * 64, 0);
   e.out16 = e8.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 256, 1922 * 64, 2 * 64);
-  gemm(ActView{a6.p, 128, 481, NB}, n, 480, 2, 120, 1, s_ct8, 256, e);
+  tag("seanet.convtr8"); gemm(ActView{a6.p, 128, 481, NB}, n, 480, 2, 120, 1, s_ct8, 256, e);
   e = epi_none(); e.bias = sb_r9a.p; e.out16 = h9.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
-  gemm(ActView{e8.p, 64, 1922, NB}, n, 1920, 3, 128, 1, s_r9a, 64, e);
+  tag("seanet.res9a"); gemm(ActView{e8.p, 64, 1922, NB}, n, 1920, 3, 128, 1, s_r9a, 64, e);
   e = epi_none(); e.bias = sb_r9b.p; e.res = x8.p; e.res_map = plain_map(64);
   e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(1920, 64, 1922 * 64, 128);
-  gemm_rows(h9.p, n * 1920, 64, s_r9b, 64, e);
-  seanet_final_conv_kernel<<<dim3((FRAME + 255) / 256, n), 256, 0, stream>>>(a9.p, s_final_w.p, s_final_b.p, n, pcm.p);
-  ++launches;
-  conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 1);
-  ++launches;
+  tag("seanet.res9b"); gemm_rows(h9.p, n * 1920, 64, s_r9b, 64, e);
+  { ProfScope ps(*this, "seanet.final_conv", (double)n * (1922.0 * 128 + 1920 * 4), 2.0 * n * 1920 * 192);
+    seanet_final_conv_kernel<<<dim3((FRAME + 255) / 256, n), 256, 0, stream>>>(a9.p, s_final_w.p, s_final_b.p, n, pcm.p); }
+  { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
+    conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 1); }
   mark(4);
   // ---- EOS bookkeeping, AR feedback, cursors (reference tts_model.rs:1055-1069)
-  step_end_kernel<<<n, 32, 0, stream>>>(row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
-                                        latent_out.p, logit_out.p);
-  ++launches;
+  { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
+    step_end_kernel<<<n, 32, 0, stream>>>(row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
+                                          latent_out.p, logit_out.p); }
   mark(5);
   PTTS_CUDA(cudaGetLastError());
   if (stage_ms) {
@@ -840,8 +901,8 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
       PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, rs.data(), rows * 4, cudaMemcpyHostToDevice, e.stream));
       PTTS_CUDA(cudaMemcpyAsync(e.prow_pos.p, rp.data(), rows * 4, cudaMemcpyHostToDevice, e.stream));
       PTTS_CUDA(cudaMemcpyAsync(e.ptokens.p, tokens + token_offsets[i0], rows * 4, cudaMemcpyHostToDevice, e.stream));
-      embed_rows_kernel<<<rows, 256, 0, e.stream>>>(e.ptokens.p, rows, e.lut.p, e.px32.p);
-      ++e.launches;
+      { ProfScope ps(e, "prefill.embed", (double)rows * 1024 * 8, 0);
+        embed_rows_kernel<<<rows, 256, 0, e.stream>>>(e.ptokens.p, rows, e.lut.p, e.px32.p); }
       e.prefill(rows);
       PTTS_CUDA(cudaStreamSynchronize(e.stream));
     }
@@ -1011,6 +1072,30 @@ int64_t ptts_launch_count(ptts_engine* h, int32_t reset) {
 }
 
 void* ptts_cuda_stream(ptts_engine* h) { return h ? (void*)h->e.stream : nullptr; }
+
+int32_t ptts_profile_enable(ptts_engine* h, int32_t on) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+  PTTS_CUDA(cudaStreamSynchronize(h->e.stream));
+  h->e.profiling = on != 0;
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int64_t ptts_profile_report(ptts_engine* h, char* buf, int64_t cap) {
+  try {
+    PTTS_REQUIRE(h && buf && cap > 0, PTTS_ERR_INVALID, "null argument");
+    PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+    const std::string r = h->e.prof_report();
+    PTTS_REQUIRE((int64_t)r.size() + 1 <= cap, PTTS_ERR_INVALID, "profile report needs %zu bytes", r.size() + 1);
+    std::memcpy(buf, r.c_str(), r.size() + 1);
+    return (int64_t)r.size();
+  } catch (const ptts::Error& ex) {
+    g_last_error = ex.what();
+    return ex.code;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ isolated kernel tests
 struct TestCtx {

@@ -150,6 +150,23 @@ class Engine:
         check(int(n))
         return out[:n].copy()
 
+    def profile(self, on: bool):
+        check(_lib.lib().ptts_profile_enable(self._h, int(on)))
+
+    def profile_report(self) -> dict[str, dict]:
+        buf = C.create_string_buffer(1 << 16)
+        n = _lib.lib().ptts_profile_report(self._h, buf, len(buf))
+        check(int(n))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, cnt, ms, by, fl = line.split()
+            out[tag] = dict(launches=int(cnt), ms=float(ms), bytes=float(by), flops=float(fl))
+        return out
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(_lib.lib().ptts_cuda_stream(self._h) or 0)
+
     def launch_count(self, reset: bool = False) -> int:
         return int(_lib.lib().ptts_launch_count(self._h, int(reset)))
 

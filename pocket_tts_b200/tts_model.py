@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference's `TTSModel` surface for the generation path
+(crates/pocket-tts/src/tts_model.rs), on top of the C-ABI engine.
+
+Same names, argument meaning and error behaviour as the Rust API the `pocket-tts-cuda` crate keeps
+(INTEGRATION.md): `load` / `load_with_params`, `get_voice_state_from_prompt_file|tensor`,
+`generate`, `generate_stream`, plus the public fields `temp`, `lsd_decode_steps`, `eos_threshold`.
+Host text preparation follows tts_model.rs:968-969,1194-1237.  Tokenisation itself is outside the
+hot path: pass `tokenizer=` (any callable str -> list[int], e.g. a
+sentencepiece.SentencePieceProcessor(...).encode) or call the `*_tokens` methods with ids.
+"""
+from __future__ import annotations
+
+import json
+import re
+import struct
+from pathlib import Path
+from typing import Callable, Iterator
+
+import numpy as np
+
+from .engine import FRAME, LDIM, Engine, StreamSpec, Voice
+
+SAMPLE_RATE = 24000
+# defaults: crates/pocket-tts/src/config.rs:118-124
+DEFAULT_TEMPERATURE = 0.7
+DEFAULT_LSD_DECODE_STEPS = 1
+DEFAULT_EOS_THRESHOLD = -4.0
+DEFAULT_VARIANT = "b6369a24"
+
+_PAUSE_RE = re.compile(r"\[pause:(\d+(?:\.\d+)?)(ms|s)\]")  # pause.rs:34-37
+
+
+def strip_pause_markers(text: str) -> str:
+    return _PAUSE_RE.sub(" ", text)
+
+
+def prepare_text_prompt(text: str) -> str:
+    """tts_model.rs:1194-1227"""
+    text = strip_pause_markers(text).strip()
+    if not text:
+        return "."
+    text = text.replace("\n", " ").replace("\r", " ").replace("  ", " ")
+    word_count = len(text.split())
+    if not text[0].isupper():
+        text = text[0].upper() + text[1:]
+    if text[-1].isalnum():
+        text += "."
+    if word_count < 5:
+        text = " " * 8 + text
+    return text
+
+
+def estimate_frames_after_eos(text: str) -> int:
+    """tts_model.rs:1230-1237"""
+    return 5 if len(text.split()) <= 4 else 3
+
+
+def estimate_generation_steps(text: str) -> int:
+    """tts_model.rs:968,1127-1130: (words(prepared) + 2) * 13"""
+    return (len(prepare_text_prompt(text).split()) + 2) * 13
+
+
+def silence_samples(duration_ms: int, sample_rate: int = SAMPLE_RATE) -> int:
+    """pause.rs:183-185"""
+    return (int(duration_ms) * int(sample_rate)) // 1000
+
+
+def parse_pauses(text: str) -> list[tuple[str, int]]:
+    """Explicit `[pause:Xms|Xs]` segmentation of generate_stream_long (tts_model.rs:1074-1127):
+    returns [(text_segment, pause_ms_after)], pause 0 for the last segment."""
+    out, last = [], 0
+    for m in _PAUSE_RE.finditer(text):
+        val, unit = float(m.group(1)), m.group(2)
+        ms = int(val) if unit == "ms" else int(val * 1000.0)
+        out.append((text[last:m.start()], ms))
+        last = m.end()
+    out.append((text[last:], 0))
+    return out
+
+
+def read_safetensors(path: str | Path) -> dict[str, np.ndarray]:
+    """Minimal safetensors reader (F32 / BF16 / F16), enough for the checkpoint and `audio_prompt` voice files
+    (tts_model.rs:467-487)."""
+    data = Path(path).read_bytes()
+    (hlen,) = struct.unpack("<Q", data[:8])
+    header = json.loads(data[8:8 + hlen])
+    base = 8 + hlen
+    out = {}
+    for name, meta in header.items():
+        if name == "__metadata__":
+            continue
+        b, e = meta["data_offsets"]
+        raw = np.frombuffer(data, dtype=np.uint8, count=e - b, offset=base + b)
+        dt = meta["dtype"]
+        if dt == "F32":
+            arr = raw.view(np.float32)
+        elif dt == "F16":
+            arr = raw.view(np.float16).astype(np.float32)
+        elif dt == "BF16":
+            arr = (raw.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+        else:
+            raise ValueError(f"{name}: unsupported safetensors dtype {dt}")
+        out[name] = arr.reshape(meta["shape"]).copy()
+    return out
+
+
+class TTSModel:
+    def __init__(self, weights: dict[str, np.ndarray], temp: float = DEFAULT_TEMPERATURE,
+                 lsd_decode_steps: int = DEFAULT_LSD_DECODE_STEPS, eos_threshold: float = DEFAULT_EOS_THRESHOLD,
+                 device: int = 0, max_slots: int = 64, kv_capacity: int = 1024,
+                 tokenizer: Callable[[str], list[int]] | None = None):
+        self.temp, self.lsd_decode_steps, self.eos_threshold = temp, lsd_decode_steps, eos_threshold
+        self.noise_clamp = None  # reference field (tts_model.rs:34); rejection sampling is not on the device path
+        self.sample_rate, self.dim, self.ldim = SAMPLE_RATE, 1024, LDIM
+        self.tokenizer = tokenizer
+        self.engine = Engine(weights, device=device, max_slots=max_slots, kv_capacity=kv_capacity)
+        self._lsd_on_device = 1
+
+    # ---- loading (tts_model.rs:59-86)
+    @classmethod
+    def load(cls, weights_path: str | Path, **kw) -> "TTSModel":
+        return cls.load_with_params(weights_path, DEFAULT_TEMPERATURE, DEFAULT_LSD_DECODE_STEPS, DEFAULT_EOS_THRESHOLD, **kw)
+
+    @classmethod
+    def load_with_params(cls, weights_path: str | Path, temp: float, lsd_decode_steps: int, eos_threshold: float, **kw) -> "TTSModel":
+        return cls(read_safetensors(weights_path), temp, lsd_decode_steps, eos_threshold, **kw)
+
+    # ---- voice state (tts_model.rs:467-501)
+    def get_voice_state_from_prompt_file(self, path: str | Path) -> Voice:
+        t = read_safetensors(path)
+        if "audio_prompt" not in t:
+            raise KeyError("'audio_prompt' not found in safetensors file")
+        return self.get_voice_state_from_prompt_tensor(t["audio_prompt"])
+
+    def get_voice_state_from_prompt_tensor(self, prompt: np.ndarray) -> Voice:
+        return self.engine.voice_from_prompt(np.asarray(prompt, np.float32).reshape(-1, self.dim))
+
+    # ---- generation (tts_model.rs:687-703, 894-1071)
+    def _sync_params(self):
+        if self._lsd_on_device != self.lsd_decode_steps:
+            self.engine.set_lsd_steps(self.lsd_decode_steps)
+            self._lsd_on_device = self.lsd_decode_steps
+
+    def _tokens(self, prepared: str) -> np.ndarray:
+        if self.tokenizer is None:
+            raise RuntimeError("no tokenizer attached: pass tokenizer= or use generate_stream_tokens")
+        return np.asarray(self.tokenizer(prepared), np.int32)
+
+    def generate_stream_tokens(self, tokens, voice: Voice, max_gen_len: int, frames_after_eos: int, noise=None,
+                               seed: int = 0) -> Iterator[np.ndarray]:
+        """One segment (generate_stream_segment, tts_model.rs:935-1071): yields f32 [1,1,1920] per frame."""
+        self._sync_params()
+        spec = StreamSpec(np.asarray(tokens, np.int32), max_gen_len, frames_after_eos, self.eos_threshold, self.temp, seed, noise)
+        (slot,) = self.engine.open_streams([voice], [spec])
+        try:
+            while True:
+                pcm, fin, _, _ = self.engine.step(np.array([slot], np.int32))
+                yield pcm.reshape(1, 1, FRAME)
+                if fin[0]:
+                    break
+        finally:
+            self.engine.close_stream(int(slot))
+
+    def generate_stream(self, text: str, voice: Voice, seed: int = 0) -> Iterator[np.ndarray]:
+        prepared = prepare_text_prompt(text)
+        yield from self.generate_stream_tokens(self._tokens(prepared), voice, (len(prepared.split()) + 2) * 13,
+                                               estimate_frames_after_eos(text), seed=seed)
+
+    def generate(self, text: str, voice: Voice, seed: int = 0) -> np.ndarray:
+        chunks = list(self.generate_stream(text, voice, seed))
+        if not chunks:
+            raise RuntimeError("No audio generated")  # tts_model.rs:695-697
+        return np.concatenate(chunks, axis=2)[0]
+
+    def generate_stream_long(self, text: str, voice: Voice, seed: int = 0) -> Iterator[np.ndarray]:
+        """tts_model.rs:1074-1127 for explicit pause markers: text segments interleaved with host zeros."""
+        for seg, pause_ms in parse_pauses(text):
+            if seg.strip():
+                yield from self.generate_stream(seg, voice, seed)
+            if pause_ms > 0:
+                yield np.zeros((1, 1, silence_samples(pause_ms, self.sample_rate)), np.float32)
+
+    def close(self):
+        self.engine.close()
+
+
+def shard_requests(n_requests: int, world_size: int, rank: int) -> range:
+    """Request sharding across the GPUs of one box: contiguous, disjoint, covering; streams are
+    independent so no data-path collective exists."""
+    base, rem = divmod(n_requests, world_size)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))

@@ -1,0 +1,57 @@
+"""The C-ABI library loads, exports every symbol include/ptts.h declares, and refuses to compute
+without a CUDA device (no CPU fallback)."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from pocket_tts_b200 import build
+    build.build()
+    from pocket_tts_b200 import _lib
+    return _lib
+
+
+def header_symbols():
+    text = (ROOT / "include" / "ptts.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptts_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_exports_match_header(built_lib):
+    L = built_lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in ptts.h but not exported"
+    assert sorted(built_lib.SYMBOLS) == syms
+    assert L.ptts_abi_version() == 1
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """tcgen05.mma / TMA / TMEM loads must be in the shipped SASS (B200_PROFILING.md evidence table)."""
+    import subprocess
+    sass = subprocess.run(["cuobjdump", "-sass", str(built_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass  # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(built_lib):
+    from pocket_tts_b200.engine import test_gemm
+    with pytest.raises(built_lib.PttsError) as ei:
+        test_gemm(np.zeros((4, 64), np.float32), np.zeros((8, 64), np.float32))
+    assert ei.value.code == -2  # PTTS_ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    for p in (ROOT / "pocket_tts_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p

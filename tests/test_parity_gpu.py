@@ -1,0 +1,230 @@
+"""Parity of the CUDA engine (through the C ABI) against the CPU oracle and against the golden
+vectors produced by the unmodified reference PyTorch package.
+
+Tolerances are the ones BASELINE.json's north_star states for 16-bit operands:
+  per-frame FlowLM latents  max-abs <= 1e-2   (teacher-forced: the reference latent is fed back, so the
+                                               comparison is per frame and not a chaotic AR divergence)
+  Mimi PCM                  SNR >= 40 dB
+  EOS frame index / frame counts bit-exact
+"""
+import numpy as np
+import pytest
+import torch
+
+from pocket_tts_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+LAT_TOL = 1e-2
+SNR_MIN = 40.0
+
+
+def snr(ref, x):
+    return 10 * np.log10((ref ** 2).sum() / max(((ref - x) ** 2).sum(), 1e-30))
+
+
+_cache = {}
+
+
+def engine_for(seed, ls, **kw):
+    from pocket_tts_b200.engine import Engine
+    key = (int(seed), float(ls), tuple(sorted(kw.items())))
+    if key not in _cache:
+        for e in _cache.values():
+            e[0].close()
+        _cache.clear()
+        w = synth.make_weights(key[0], layer_scale=key[1])
+        _cache[key] = (Engine(w, max_slots=kw.get("max_slots", 8), kv_capacity=kw.get("kv_capacity", 512)), w)
+    return _cache[key]
+
+
+def run_engine(eng, voice, g, kind="tanh", teacher=True, frames=None):
+    from pocket_tts_b200.engine import StreamSpec
+    frames = frames or g[f"{kind}_latents"].shape[0]
+    slots = eng.open_streams([voice], [StreamSpec(g["tokens"], frames, 0, 1e30, noise=g["noise"][:frames])])
+    lat, pcm, logit = [], [], []
+    for f in range(frames):
+        if teacher and f > 0:
+            eng.set_feedback(int(slots[0]), g[f"{kind}_latents"][f - 1])
+        p, fin, l, lg = eng.step(slots)
+        lat.append(l[0]); pcm.append(p[0]); logit.append(lg[0])
+        assert bool(fin[0]) == (f == frames - 1)
+    eng.close_stream(int(slots[0]))
+    return np.stack(lat), np.stack(pcm), np.array(logit)
+
+
+@pytest.mark.parametrize("case", ["cfg1_lsd1", "cfg3_lsd4", "stress_ls05"])
+def test_golden_teacher_forced(golden_dir, case):
+    g = np.load(golden_dir / f"{case}.npz")
+    eng, _ = engine_for(g["weight_seed"], g["layer_scale"])
+    eng.set_lsd_steps(int(g["lsd_steps"]))
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(int(g["voice_rows"]), seed=7))
+    lat, pcm, logit = run_engine(eng, voice, g)
+    voice.close()
+    eng.set_lsd_steps(1)
+    err = np.abs(lat - g["tanh_latents"]).max()
+    assert err <= LAT_TOL, f"latent max-abs {err}"
+    # first frame uses no fed-back latent at all; later PCM frames depend on the engine's own Mimi state
+    s = snr(g["tanh_pcm"], pcm)
+    assert s >= SNR_MIN, f"PCM SNR {s} dB"
+    assert np.abs(logit - g["tanh_eos_logits"]).max() < 2e-2
+
+
+def test_golden_free_running_prefix(golden_dir):
+    """Free-running AR (engine feeds its own latents back) stays inside the tolerance over the golden window."""
+    g = np.load(golden_dir / "cfg1_lsd1.npz")
+    eng, _ = engine_for(g["weight_seed"], g["layer_scale"])
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(int(g["voice_rows"]), seed=7))
+    lat, pcm, _ = run_engine(eng, voice, g, teacher=False, frames=6)
+    voice.close()
+    assert np.abs(lat - g["tanh_latents"][:6]).max() <= LAT_TOL
+    assert snr(g["tanh_pcm"][:6], pcm) >= SNR_MIN
+
+
+def test_eos_frame_index_bit_exact(golden_dir):
+    """EOS bookkeeping (tts_model.rs:1055-1069): with a threshold placed in the widest gap of the reference's
+    own logit trace, the engine must stop on exactly the reference's frame."""
+    from pocket_tts_b200.engine import StreamSpec
+    g = np.load(golden_dir / "stress_ls05.npz")
+    eng, _ = engine_for(g["weight_seed"], g["layer_scale"])
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(int(g["voice_rows"]), seed=7))
+    logits = g["tanh_eos_logits"]
+    srt = np.sort(logits)
+    gaps = np.diff(srt)
+    # thresholds in the three widest gaps -> different eos steps; margin is half the gap
+    for gi in np.argsort(gaps)[-3:]:
+        thr = float((srt[gi] + srt[gi + 1]) / 2)
+        margin = float(gaps[gi] / 2)
+        assert margin > 0.02, margin
+        for fae in (3, 5):
+            above = np.nonzero(logits > thr)[0]
+            eos_step = int(above[0]) if len(above) else -1
+            want = min(len(logits), eos_step + fae + 1) if eos_step >= 0 else len(logits)
+            slots = eng.open_streams([voice], [StreamSpec(g["tokens"], len(logits), fae, thr, noise=g["noise"])])
+            n = 0
+            while True:
+                if n > 0:
+                    eng.set_feedback(int(slots[0]), g["tanh_latents"][n - 1])
+                _, fin, _, _ = eng.step(slots)
+                n += 1
+                if fin[0]:
+                    break
+            frames, es = eng.stream_frames(int(slots[0]))
+            eng.close_stream(int(slots[0]))
+            assert (n, frames, es) == (want, want, eos_step), (thr, fae, n, frames, es, want, eos_step)
+    voice.close()
+
+
+def test_ragged_batch_matches_oracle():
+    """B independent streams = B independent batch-1 reference runs: different token counts,
+    noise and lifetimes in one batch, slots recycled, each stream compared with its own oracle run."""
+    from oracle import ptts_oracle as O
+    from pocket_tts_b200.engine import StreamSpec
+    eng, wnp = engine_for(1234, 0.01)
+    W = O.to_torch(wnp)
+    prompt = synth.make_voice_prompt(33, seed=21)
+    voice = eng.voice_from_prompt(prompt)
+    ov = O.voice_state_from_prompt(W, prompt)
+    specs, refs = [], []
+    for i, (ntok, frames) in enumerate([(5, 3), (17, 5), (1, 2), (9, 4), (30, 3)]):
+        tok = synth.make_tokens(ntok, seed=100 + i)
+        noise = synth.make_noise(frames, seed=200 + i)
+        specs.append(StreamSpec(tok, frames, 0, 1e30, noise=noise))
+        refs.append(O.generate_segment(W, ov, tok, noise, frames, 0, float("inf")))
+    slots = eng.open_streams([voice] * len(specs), specs)
+    active = list(range(len(specs)))
+    got_lat = [[] for _ in specs]
+    got_pcm = [[] for _ in specs]
+    step = 0
+    while active:
+        for i in active:  # teacher forcing per stream
+            if step > 0:
+                eng.set_feedback(int(slots[i]), refs[i]["latents"][step - 1])
+        pcm, fin, lat, _ = eng.step(slots[active])
+        nxt = []
+        for j, i in enumerate(active):
+            got_lat[i].append(lat[j]); got_pcm[i].append(pcm[j])
+            if fin[j]:
+                eng.close_stream(int(slots[i]))
+            else:
+                nxt.append(i)
+        active = nxt
+        step += 1
+    for i, r in enumerate(refs):
+        assert len(got_lat[i]) == r["frames"]
+        assert np.abs(np.stack(got_lat[i]) - r["latents"]).max() <= LAT_TOL
+        assert snr(r["pcm"], np.stack(got_pcm[i])) >= SNR_MIN
+    # recycled slot must start from clean streaming state
+    tok = synth.make_tokens(5, seed=100)
+    noise = synth.make_noise(3, seed=200)
+    s2 = eng.open_streams([voice], [StreamSpec(tok, 3, 0, 1e30, noise=noise)])
+    out = []
+    for f in range(3):
+        if f:
+            eng.set_feedback(int(s2[0]), refs[0]["latents"][f - 1])
+        pcm, _, _, _ = eng.step(s2)
+        out.append(pcm[0])
+    eng.close_stream(int(s2[0]))
+    assert snr(refs[0]["pcm"], np.stack(out)) >= SNR_MIN
+    voice.close()
+
+
+def test_temp_zero_is_deterministic_and_device_noise_runs():
+    """temp = 0 -> x_0 = 0 exactly (flow_lm.rs:39-48 with std 0), the reference's own determinism test
+    (tests/streaming_tests.rs:21-70); temp > 0 without injected noise uses the device generator."""
+    from pocket_tts_b200.engine import StreamSpec
+    eng, _ = engine_for(1234, 0.01)
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(20, seed=3))
+    tok = synth.make_tokens(8, seed=1)
+    outs = []
+    for _ in range(2):
+        s = eng.open_streams([voice], [StreamSpec(tok, 3, 0, 1e30, temp=0.0)])
+        outs.append(np.stack([eng.step(s)[0][0] for _ in range(3)]))
+        eng.close_stream(int(s[0]))
+    np.testing.assert_allclose(outs[0], outs[1], atol=1e-4)  # split-K atomics reorder f32 adds only
+    s = eng.open_streams([voice, voice], [StreamSpec(tok, 2, 0, 1e30, temp=0.7, seed=1), StreamSpec(tok, 2, 0, 1e30, temp=0.7, seed=2)])
+    pcm, _, lat, _ = eng.step(s)
+    assert np.isfinite(pcm).all() and np.abs(lat[0] - lat[1]).max() > 1e-3
+    for x in s:
+        eng.close_stream(int(x))
+    voice.close()
+
+
+def test_api_errors():
+    from pocket_tts_b200._lib import PttsError
+    from pocket_tts_b200.engine import StreamSpec
+    eng, _ = engine_for(1234, 0.01)
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(4, seed=3))
+    with pytest.raises(PttsError) as ei:  # KV capacity
+        eng.open_streams([voice], [StreamSpec(synth.make_tokens(10, 1), 100000)])
+    assert ei.value.code == -3
+    with pytest.raises(PttsError):        # bad token id
+        eng.open_streams([voice], [StreamSpec(np.array([4001], np.int32), 4)])
+    s = eng.open_streams([voice], [StreamSpec(synth.make_tokens(3, 1), 1, temp=0.0)])
+    _, fin, _, _ = eng.step(s)
+    assert fin[0]
+    with pytest.raises(PttsError) as ei:  # stepping a finished stream
+        eng.step(s)
+    assert ei.value.code == -4
+    eng.close_stream(int(s[0]))
+    with pytest.raises(PttsError):
+        eng.close_stream(int(s[0]))
+    voice.close()
+
+
+def test_host_mirror_generate_stream_tokens():
+    """TTSModel facade: yields [1,1,1920] frames until the engine reports the last one (tts_model.rs:894-1071)."""
+    from pocket_tts_b200.tts_model import TTSModel
+    for e in _cache.values():
+        e[0].close()
+    _cache.clear()
+    m = TTSModel(synth.make_weights(1234), temp=0.0, max_slots=2, kv_capacity=256)
+    voice = m.get_voice_state_from_prompt_tensor(synth.make_voice_prompt(10, seed=1)[None])
+    m.eos_threshold = 1e30
+    frames = list(m.generate_stream_tokens(synth.make_tokens(6, 2), voice, max_gen_len=4, frames_after_eos=3))
+    assert len(frames) == 4 and frames[0].shape == (1, 1, 1920)
+    m.eos_threshold = -1e30  # EOS at step 0 -> 0 + 3 + 1 frames (D2)
+    frames = list(m.generate_stream_tokens(synth.make_tokens(6, 2), voice, max_gen_len=20, frames_after_eos=3))
+    assert len(frames) == 4
+    voice.close()
+    m.close()
