@@ -148,6 +148,9 @@ struct Engine {
                      const int* rseq, const int* rpos);
   void upload_rows(const int* slot_ids, int n);
   void step_kernels(int n, float* stage_ms);
+  void run_step(int n);
+  struct StepGraph { cudaGraphExec_t exec; long long kernels; };
+  std::map<std::pair<int, int>, StepGraph> graphs;  // (batch rows, lsd steps) -> captured decode step
   void prefill(int rows);
 };
 
@@ -158,6 +161,7 @@ Engine::~Engine() {
   if (pin_logit) cudaFreeHost(pin_logit);
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   for (auto& e : prof_pool) cudaEventDestroy(e);
+  for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
   for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (stream) cudaStreamDestroy(stream);
 }
@@ -535,6 +539,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
   p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));
   p.tmem_cols = pow2_at_least(p.BN);
+  // the epilogue re-uses the stage buffers for its [128][BN+1] f32 tile
+  while ((size_t)p.stages * stage_bytes < (size_t)GEMM_BM * (p.BN + 1) * 4) ++p.stages;
   const size_t smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
 
   // algorithmic traffic: weights once, the distinct activation rows once, every epilogue tensor once
@@ -745,6 +751,35 @@ void Engine::step_kernels(int n, float* stage_ms) {
   }
 }
 
+// The decode step is ~100 dependent launches of a few microseconds each: replaying it as a CUDA graph removes
+// the per-launch host cost.  Every pointer in the step is a fixed engine buffer and the batch composition is
+// data (row_seq), so one graph per (rows, lsd_steps) serves every step of every batch of that size.
+void Engine::run_step(int n) {
+  if (!cfg.use_cuda_graph || profiling) return step_kernels(n, nullptr);
+  const auto key = std::make_pair(n, lsd_steps);
+  auto it = graphs.find(key);
+  if (it == graphs.end()) {
+    const long long before = launches;
+    cudaGraph_t g = nullptr;
+    PTTS_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      step_kernels(n, nullptr);
+    } catch (...) {
+      cudaStreamEndCapture(stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    PTTS_CUDA(cudaStreamEndCapture(stream, &g));
+    StepGraph sg{nullptr, launches - before};
+    launches = before;
+    PTTS_CUDA(cudaGraphInstantiate(&sg.exec, g, 0));
+    PTTS_CUDA(cudaGraphDestroy(g));
+    it = graphs.emplace(key, sg).first;
+  }
+  PTTS_CUDA(cudaGraphLaunch(it->second.exec, stream));
+  launches += it->second.kernels;
+}
+
 void Engine::prefill(int rows) {
   flowlm_layers(rows, px32.p, ph16.p, pqkv32.p, pattn16.p, pffn16.p, true, pqrot.p, prow_seq.p, prow_pos.p);
 }
@@ -931,7 +966,7 @@ int32_t ptts_step(ptts_engine* h, const int32_t* slot_ids, int32_t n, float* pcm
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
   check_slots(e, slot_ids, n);
   e.upload_rows(slot_ids, n);
-  e.step_kernels(n, nullptr);
+  e.run_step(n);
   if (pcm_out) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm, e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaMemcpyAsync(e.pin_fin, e.finished_dev.p, n, cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaMemcpyAsync(e.pin_lat, e.latent_out.p, (size_t)n * LDIM * 4, cudaMemcpyDeviceToHost, e.stream));
@@ -957,7 +992,7 @@ int32_t ptts_step_device(ptts_engine* h, const int32_t* slot_ids, int32_t n) {
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
   check_slots(e, slot_ids, n);
   e.upload_rows(slot_ids, n);
-  e.step_kernels(n, nullptr);
+  e.run_step(n);
   for (int i = 0; i < n; ++i) {
     SlotHost& sh = e.slots[slot_ids[i]];
     sh.frames += 1; sh.own_len += 1;

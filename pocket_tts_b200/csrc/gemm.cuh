@@ -78,25 +78,44 @@ static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;
 static constexpr int GEMM_THREADS = 192;
 
-__device__ __forceinline__ void epi_apply(const GemmEpi& e, float acc, int r, int f) {
+// Row part of a RowMap offset (everything except "+ f"); one integer division per row, none when the
+// map is a plain [rows, F] matrix.
+__device__ __forceinline__ long long row_off(const RowMap& m, int r) {
+  if (r < m.T) return m.base + static_cast<long long>(r) * m.ld;
+  const int b = r / m.T;
+  return static_cast<long long>(b) * m.stream_stride + m.base + static_cast<long long>(r - b * m.T) * m.ld;
+}
+
+struct EpiRow {  // per-row bases of every epilogue tensor
+  long long gate, res, o32, o16;
+};
+__device__ __forceinline__ EpiRow epi_row(const GemmEpi& e, int r) {
+  EpiRow o;
+  o.gate = e.gate ? row_off(e.gate_map, r) : 0;
+  o.res = e.res ? row_off(e.res_map, r) : 0;
+  o.o32 = e.out32 ? row_off(e.out32_map, r) : 0;
+  o.o16 = e.out16 ? row_off(e.out16_map, r) : 0;
+  return o;
+}
+
+// One output element.  Kept out of line: the kernel has exactly two call sites and the body (tanh/exp
+// paths included) stays a few hundred instructions, so the whole kernel fits the instruction cache.
+__device__ __noinline__ void epi_apply(const GemmEpi& e, const EpiRow& ro, float acc, int f, bool first_split) {
   float v = acc;
-  if (e.bias) v += __ldg(e.bias + f);
+  if (e.bias && first_split) v += __ldg(e.bias + f);  // split-K: the bias is added by split 0 only
   if (e.act == ACT_GELU) v = gelu_tanh(v);
   else if (e.act == ACT_SILU) v = silu(v);
   else if (e.act == ACT_ELU) v = elu1(v);
   v *= e.alpha;
   if (e.fscale) v *= __ldg(e.fscale + f);
-  if (e.gate) v *= e.gate[e.gate_map.off(r, f)];
+  if (e.gate) v *= e.gate[ro.gate + f];
   if (e.atomic) {
-    atomicAdd(e.out32 + e.out32_map.off(r, f), v);
+    atomicAdd(e.out32 + ro.o32 + f, v);
     return;
   }
-  if (e.res) v += e.res[e.res_map.off(r, f)];
-  if (e.out32) e.out32[e.out32_map.off(r, f)] = v;
-  if (e.out16) {
-    float h = (e.act16 == ACT_ELU) ? elu1(v) : v;
-    e.out16[e.out16_map.off(r, f)] = __float2half_rn(h);
-  }
+  if (e.res) v += e.res[ro.res + f];
+  if (e.out32) e.out32[ro.o32 + f] = v;
+  if (e.out16) e.out16[ro.o16 + f] = __float2half_rn((e.act16 == ACT_ELU) ? elu1(v) : v);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -195,41 +214,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       __syncwarp();
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> smem (raw f32 tile) -> coalesced global =====
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
     const int i = quad * 32 + lane;
     const GemmEpi& e = p.epi;
-    int r_fixed = -1, f_fixed = -1;
-    if (p.swap) {
-      f_fixed = f0 + i;
-      if (f_fixed >= p.F) f_fixed = -1;
-    } else {
-      const int g = i / p.R;
-      const int tt = i - g * p.R;
-      const int b = b0 + g, t = t0 + tt;
-      if (g < p.G && b < p.n_streams && t < p.T) r_fixed = b * p.T + t;
-    }
+    // The pipeline stages are dead once tmem_full has arrived (every MMA has consumed its operands), so the
+    // accumulator tile [128][BN+1] f32 is staged there; the odd row pitch keeps both passes conflict-free.
+    float* stile = reinterpret_cast<float*>(smem);
+    const int LD = p.BN + 1;
     for (int c = 0; c < p.BN; c += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
       tmem_ld_wait();
-      if (p.swap) {
-        if (f_fixed >= 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int r = t0 + c + j;
-            if (r < p.T) epi_apply(e, __uint_as_float(v[j]), r, f_fixed);
-          }
+      for (int j = 0; j < 16; ++j) stile[i * LD + c + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    const bool first_split = blockIdx.z == 0;
+    const int ew = warp - 2;
+    if (p.swap) {
+      // tile rows = features, tile columns = activation rows: a warp takes one activation row at a time and its
+      // lanes walk 32 consecutive features -> 128-byte global transactions
+      for (int j = ew; j < p.BN; j += 4) {
+        const int r = t0 + j;
+        if (r >= p.T) break;
+        const EpiRow ro = epi_row(e, r);
+        for (int ii = lane; ii < GEMM_BM; ii += 32) {
+          const int f = f0 + ii;
+          if (f < p.F) epi_apply(e, ro, stile[ii * LD + j], f, first_split);
         }
-      } else {
-        if (r_fixed >= 0) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int f = f0 + c + j;
-            if (f < p.F) epi_apply(e, __uint_as_float(v[j]), r_fixed, f);
-          }
+      }
+    } else {
+      for (int ii = ew; ii < GEMM_BM; ii += 4) {
+        const int g = ii / p.R;
+        const int tt = ii - g * p.R;
+        const int b = b0 + g, t = t0 + tt;
+        if (g >= p.G || b >= p.n_streams || t >= p.T) continue;
+        const EpiRow ro = epi_row(e, b * p.T + t);
+        for (int j = lane; j < p.BN; j += 32) {
+          const int f = f0 + j;
+          if (f < p.F) epi_apply(e, ro, stile[ii * LD + j], f, first_split);
         }
       }
     }
@@ -260,7 +286,7 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
     e.res = p.epi.out32;
     e.res_map = p.epi.out32_map;
   }
-  epi_apply(e, acc, r, f);
+  epi_apply(e, epi_row(e, r), acc, f, true);
 }
 
 }  // namespace ptts

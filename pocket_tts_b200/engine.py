@@ -44,7 +44,7 @@ class Voice:
 
 class Engine:
     def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
-                 kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0):
+                 kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True):
         L = _lib.lib()
         self._keep = []
         descs = (TensorDesc * len(weights))()
@@ -60,7 +60,7 @@ class Engine:
         cfg = EngineCfg()
         cfg.device, cfg.max_slots = device, max_slots
         cfg.max_batch = max_batch or max_slots
-        cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, 0, 0, debug_gemm
+        cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, 0, int(cuda_graph), debug_gemm
         cfg.reserved[0] = gemm_mode
         h = C.c_void_p()
         check(L.ptts_engine_create(C.byref(cfg), descs, len(weights), C.byref(h)))
