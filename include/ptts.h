@@ -150,6 +150,9 @@ int64_t ptts_profile_report(ptts_engine* e, char* buf, int64_t cap);
  * split_k > 1 exercises the atomic split-K epilogue. */
 int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const float* bias, float* d, int32_t rows,
                        int32_t feats, int32_t k, int32_t mode, int32_t split_k, int32_t act, int32_t use_simt);
+/* Bring-up probe: back-to-back launches of one GEMM with per-CTA %globaltimer stamps (10 per CTA, ns). */
+int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_t k, int32_t mode, int32_t split_k,
+                             int32_t iters, float* us_per_launch, int64_t* stamps, int32_t max_ctas, int32_t* n_ctas);
 /* Implicit-GEMM streaming convs on host buffers, channels-last x [n, t, cin], state [n, k-1 (or 1), cin]. */
 int32_t ptts_test_conv1d(int32_t device, const float* x, const float* prev, const float* w /*[cout,cin,k]*/,
                          const float* bias, float* y /*[n,t,cout]*/, int32_t n, int32_t t, int32_t cin, int32_t cout,

@@ -74,6 +74,7 @@ struct Engine {
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
   const char* cur_tag = nullptr;
+  unsigned long long* gemm_trace = nullptr;  // bring-up: passed to the next GEMM launches
   double step_kv_bytes = 0;  // FlowLM KV bytes one layer's decode attention reads in the current step
   void tag(const char* t) { cur_tag = t; }
   const char* take_tag(const char* dflt) { const char* t = cur_tag ? cur_tag : dflt; cur_tag = nullptr; return t; }
@@ -503,6 +504,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   GemmParams p{};
   p.F = F; p.K = w.K; p.taps = taps; p.cblocks = a.C / 64;
   p.epi = epi;
+  p.trace = gemm_trace;
   p.act = a.ptr; p.act_stream_stride = (long long)a.Tpad * a.C; p.act_ld = a.C; p.w = w.w.p;
   const int total_kb = p.taps * p.cblocks;
   const bool plain = (taps == 1 && n_streams == 1);
@@ -539,6 +541,11 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
   p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));
   p.tmem_cols = pow2_at_least(p.BN);
+  auto map_ok = [](const void* ptr, const RowMap& m) {
+    return !ptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && m.ld % 4 == 0 && m.base % 4 == 0 && m.stream_stride % 4 == 0);
+  };
+  p.vec4 = (F % 4 == 0) && map_ok(epi.gate, epi.gate_map) && map_ok(epi.res, epi.res_map) && map_ok(epi.out32, epi.out32_map) &&
+           map_ok(epi.out16, epi.out16_map) && map_ok(epi.bias, plain_map(4)) && map_ok(epi.fscale, plain_map(4));
   // the epilogue re-uses the stage buffers for its [128][BN+1] f32 tile
   while ((size_t)p.stages * stage_bytes < (size_t)GEMM_BM * (p.BN + 1) * 4) ++p.stages;
   const size_t smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
@@ -1174,6 +1181,46 @@ int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const flo
   e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
   PTTS_CUDA(cudaStreamSynchronize(e.stream));
   PTTS_CUDA(cudaMemcpy(d, out.p, (size_t)rows * feats * 4, cudaMemcpyDeviceToHost));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+// Bring-up probe: `iters` back-to-back launches of one GEMM; returns the CUDA-event time per launch and, for the
+// last launch, the %globaltimer stamps of up to `max_ctas` CTAs relative to the first CTA's entry (ns):
+// [entry, setup done, first TMA issued, producer done, first tile landed, MMAs issued, accumulator ready,
+//  tile staged, epilogue done, TMEM freed].
+int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_t k, int32_t mode, int32_t split_k,
+                             int32_t iters, float* us_per_launch, int64_t* stamps, int32_t max_ctas, int32_t* n_ctas) {
+  PTTS_TRY
+  TestCtx t(device, 0);
+  Engine& e = t.e;
+  e.cfg.reserved[0] = mode;
+  DevBuf<__half> a16; a16.alloc((size_t)rows * k);
+  Weight16 w16; w16.F = feats; w16.K = k; w16.Fpad = round_up(feats, 128); w16.w.alloc((size_t)w16.Fpad * k);
+  DevBuf<float> out; out.alloc((size_t)rows * feats);
+  DevBuf<unsigned long long> tr; tr.alloc(16 * 65536);
+  GemmEpi ep = epi_none();
+  ep.out32 = out.p; ep.out32_map = plain_map(feats);
+  if (split_k > 1) { ep.atomic = 1; ep.res = out.p; ep.res_map = plain_map(feats); }
+  e.gemm_trace = tr.p;
+  for (int i = 0; i < 3; ++i) e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
+  cudaEvent_t a, b;
+  PTTS_CUDA(cudaEventCreate(&a)); PTTS_CUDA(cudaEventCreate(&b));
+  PTTS_CUDA(cudaEventRecord(a, e.stream));
+  for (int i = 0; i < iters; ++i) e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
+  PTTS_CUDA(cudaEventRecord(b, e.stream));
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  float ms = 0;
+  PTTS_CUDA(cudaEventElapsedTime(&ms, a, b));
+  *us_per_launch = 1000.f * ms / iters;
+  std::vector<unsigned long long> h(16 * (size_t)max_ctas);
+  PTTS_CUDA(cudaMemcpy(h.data(), tr.p, h.size() * 8, cudaMemcpyDeviceToHost));
+  unsigned long long t0 = ~0ull;
+  int n = 0;
+  for (int c = 0; c < max_ctas; ++c) if (h[c * 16] != 0) { t0 = std::min(t0, h[c * 16]); n = c + 1; }
+  for (int c = 0; c < n; ++c) for (int j = 0; j < 10; ++j) stamps[c * 10 + j] = h[c * 16 + j] ? (int64_t)(h[c * 16 + j] - t0) : -1;
+  *n_ctas = n;
+  cudaEventDestroy(a); cudaEventDestroy(b);
   return PTTS_OK;
   PTTS_CATCH
 }

@@ -66,56 +66,136 @@ struct GemmParams {
   int kb_per_split;
   int stages;
   int tmem_cols;
+  int vec4;                 // every epilogue tensor is 16-byte addressable in groups of 4 features
   GemmEpi epi;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
   long long act_stream_stride;
   int act_ld;
   const __half* w;
+  unsigned long long* trace;  // optional [grid][16] %globaltimer stamps (bring-up only)
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PTTS_TRACE(slot)                                                                                           \
+  do {                                                                                                             \
+    if (p.trace && lane == 0)                                                                                      \
+      p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime();            \
+  } while (0)
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;
 static constexpr int GEMM_THREADS = 192;
 
-// Row part of a RowMap offset (everything except "+ f"); one integer division per row, none when the
-// map is a plain [rows, F] matrix.
+// Row part of a RowMap offset (everything except "+ f"); no integer division when the map is a plain
+// [rows, F] matrix.
 __device__ __forceinline__ long long row_off(const RowMap& m, int r) {
   if (r < m.T) return m.base + static_cast<long long>(r) * m.ld;
   const int b = r / m.T;
   return static_cast<long long>(b) * m.stream_stride + m.base + static_cast<long long>(r - b * m.T) * m.ld;
 }
 
-struct EpiRow {  // per-row bases of every epilogue tensor
-  long long gate, res, o32, o16;
-};
-__device__ __forceinline__ EpiRow epi_row(const GemmEpi& e, int r) {
-  EpiRow o;
-  o.gate = e.gate ? row_off(e.gate_map, r) : 0;
-  o.res = e.res ? row_off(e.res_map, r) : 0;
-  o.o32 = e.out32 ? row_off(e.out32_map, r) : 0;
-  o.o16 = e.out16 ? row_off(e.out16_map, r) : 0;
-  return o;
+__device__ __forceinline__ float epi_act(int act, float v) {
+  if (act == ACT_GELU) return gelu_tanh(v);
+  if (act == ACT_SILU) return silu(v);
+  if (act == ACT_ELU) return elu1(v);
+  return v;
 }
 
-// One output element.  Kept out of line: the kernel has exactly two call sites and the body (tanh/exp
-// paths included) stays a few hundred instructions, so the whole kernel fits the instruction cache.
-__device__ __noinline__ void epi_apply(const GemmEpi& e, const EpiRow& ro, float acc, int f, bool first_split) {
-  float v = acc;
-  if (e.bias && first_split) v += __ldg(e.bias + f);  // split-K: the bias is added by split 0 only
-  if (e.act == ACT_GELU) v = gelu_tanh(v);
-  else if (e.act == ACT_SILU) v = silu(v);
-  else if (e.act == ACT_ELU) v = elu1(v);
-  v *= e.alpha;
-  if (e.fscale) v *= __ldg(e.fscale + f);
-  if (e.gate) v *= e.gate[ro.gate + f];
-  if (e.atomic) {
-    atomicAdd(e.out32 + ro.o32 + f, v);
-    return;
+// Second half of the epilogue: the f32 accumulator tile sits in shared memory ([128][LD], LD odd); all threads
+// of the CTA walk it in output order, V consecutive features per thread, so every global access of a warp is
+// one contiguous 128-byte (V=1) or 512-byte (V=4) run.  Every epilogue field is hoisted into registers first;
+// the flag tests inside the loop are warp-uniform.
+template <int V>
+__device__ __forceinline__ void epi_store_tile(const GemmParams& p, const float* __restrict__ stile, int LD, int f0,
+                                               int t0, int b0, int tid, int nthreads, bool first_split) {
+  const float* __restrict__ bias = first_split ? p.epi.bias : nullptr;
+  const float* __restrict__ fscale = p.epi.fscale;
+  const float* gate = p.epi.gate;
+  const float* res = p.epi.res;
+  float* out32 = p.epi.out32;
+  __half* out16 = p.epi.out16;
+  const RowMap gate_map = p.epi.gate_map, res_map = p.epi.res_map, o32_map = p.epi.out32_map, o16_map = p.epi.out16_map;
+  const int act = p.epi.act, act16 = p.epi.act16, atomic = p.epi.atomic;
+  const float alpha = p.epi.alpha;
+  const int swap = p.swap, F = p.F, T = p.T, R = p.R, G = p.G, n_streams = p.n_streams;
+  const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
+  const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
+  const int units = tile_rows * fv;
+  for (int u = tid; u < units; u += nthreads) {
+    const int row = u / fv;
+    const int q = u - row * fv;
+    const int f = f0 + q * V;
+    if (f >= F) continue;
+    int r;
+    if (swap) {
+      r = t0 + row;
+      if (r >= T) continue;
+    } else {
+      const int g = row / R;
+      const int tt = row - g * R;
+      const int b = b0 + g, t = t0 + tt;
+      if (g >= G || b >= n_streams || t >= T) continue;
+      r = b * T + t;
+    }
+    float v[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) v[c] = swap ? stile[(q * V + c) * LD + row] : stile[row * LD + q * V + c];
+    // issue every global read of this unit before the math
+    float gv[V], rv[V], bv[V], sv[V];
+    if (V == 4) {
+      if (gate) { const float4 t4 = *reinterpret_cast<const float4*>(gate + row_off(gate_map, r) + f); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
+      if (res && !atomic) { const float4 t4 = *reinterpret_cast<const float4*>(res + row_off(res_map, r) + f); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
+      if (bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
+      if (fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
+    } else {
+      if (gate) gv[0] = gate[row_off(gate_map, r) + f];
+      if (res && !atomic) rv[0] = res[row_off(res_map, r) + f];
+      if (bias) bv[0] = __ldg(bias + f);
+      if (fscale) sv[0] = __ldg(fscale + f);
+    }
+#pragma unroll
+    for (int c = 0; c < V; ++c) {
+      float x = v[c];
+      if (bias) x += bv[c];
+      x = epi_act(act, x) * alpha;
+      if (fscale) x *= sv[c];
+      if (gate) x *= gv[c];
+      if (res && !atomic) x += rv[c];
+      v[c] = x;
+    }
+    if (atomic) {
+      float* dst = out32 + row_off(o32_map, r) + f;
+#pragma unroll
+      for (int c = 0; c < V; ++c) atomicAdd(dst + c, v[c]);
+      continue;
+    }
+    if (out32) {
+      float* dst = out32 + row_off(o32_map, r) + f;
+      if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      else dst[0] = v[0];
+    }
+    if (out16) {
+      __half* dst = out16 + row_off(o16_map, r) + f;
+      if (act16 == ACT_ELU) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) v[c] = elu1(v[c]);
+      }
+      if (V == 4) {
+        const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(dst) = pk;
+      } else {
+        dst[0] = __float2half_rn(v[0]);
+      }
+    }
   }
-  if (e.res) v += e.res[ro.res + f];
-  if (e.out32) e.out32[ro.o32 + f] = v;
-  if (e.out16) e.out16[ro.o16 + f] = __float2half_rn((e.act16 == ACT_ELU) ? elu1(v) : v);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -134,6 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 0) PTTS_TRACE(0);
 
   // tile coordinates
   const int tiles_t = (p.T + p.R - 1) / p.R;
@@ -171,6 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) PTTS_TRACE(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -189,7 +271,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         mbar_arrive_expect_tx(full_bar + s, act_bytes + w_bytes);
         tma_load_3d(p.swap ? n_tile : m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
         tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
+        if (i == 0) PTTS_TRACE(2);
       }
+      PTTS_TRACE(3);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -199,6 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       const uint32_t ph = (i / p.stages) & 1;
       mbar_wait(full_bar + s, ph);
       tc_fence_after();
+      if (i == 0) PTTS_TRACE(4);
       if (elect_one()) {
         const uint32_t m_addr = smem_u32(smem + s * stage_bytes);
         const uint64_t da = make_sw128_kmajor_desc(m_addr);
@@ -213,13 +298,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       }
       __syncwarp();
     }
+    PTTS_TRACE(5);
   } else {
-    // ===== epilogue: TMEM -> registers -> smem (raw f32 tile) -> coalesced global =====
+    // ===== epilogue, first half: TMEM -> registers -> smem (raw f32 tile) =====
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (warp == 2) PTTS_TRACE(6);
     const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
     const int i = quad * 32 + lane;
-    const GemmEpi& e = p.epi;
     // The pipeline stages are dead once tmem_full has arrived (every MMA has consumed its operands), so the
     // accumulator tile [128][BN+1] f32 is staged there; the odd row pitch keeps both passes conflict-free.
     float* stile = reinterpret_cast<float*>(smem);
@@ -231,38 +317,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
 #pragma unroll
       for (int j = 0; j < 16; ++j) stile[i * LD + c + j] = __uint_as_float(v[j]);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-    const bool first_split = blockIdx.z == 0;
-    const int ew = warp - 2;
-    if (p.swap) {
-      // tile rows = features, tile columns = activation rows: a warp takes one activation row at a time and its
-      // lanes walk 32 consecutive features -> 128-byte global transactions
-      for (int j = ew; j < p.BN; j += 4) {
-        const int r = t0 + j;
-        if (r >= p.T) break;
-        const EpiRow ro = epi_row(e, r);
-        for (int ii = lane; ii < GEMM_BM; ii += 32) {
-          const int f = f0 + ii;
-          if (f < p.F) epi_apply(e, ro, stile[ii * LD + j], f, first_split);
-        }
-      }
-    } else {
-      for (int ii = ew; ii < GEMM_BM; ii += 4) {
-        const int g = ii / p.R;
-        const int tt = ii - g * p.R;
-        const int b = b0 + g, t = t0 + tt;
-        if (g >= p.G || b >= p.n_streams || t >= p.T) continue;
-        const EpiRow ro = epi_row(e, b * p.T + t);
-        for (int j = lane; j < p.BN; j += 32) {
-          const int f = f0 + j;
-          if (f < p.F) epi_apply(e, ro, stile[ii * LD + j], f, first_split);
-        }
-      }
-    }
+    if (warp == 2) PTTS_TRACE(7);
   }
+  // ===== epilogue, second half: every warp of the CTA (producer and MMA warps are idle by now) =====
   tc_fence_before();
   __syncthreads();
+  {
+    const float* stile = reinterpret_cast<const float*>(smem);
+    if (p.vec4) epi_store_tile<4>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, blockIdx.z == 0);
+    else epi_store_tile<1>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, blockIdx.z == 0);
+  }
+  if (warp == 2) PTTS_TRACE(8);
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 1) PTTS_TRACE(9);
 }
 
 // SIMT cross-check of the same contract (tests only; selected by ptts_engine_cfg.debug_gemm or
@@ -286,7 +353,14 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
     e.res = p.epi.out32;
     e.res_map = p.epi.out32_map;
   }
-  epi_apply(e, epi_row(e, r), acc, f, true);
+  float v = acc;
+  if (e.bias) v += e.bias[f];
+  v = epi_act(e.act, v) * e.alpha;
+  if (e.fscale) v *= e.fscale[f];
+  if (e.gate) v *= e.gate[row_off(e.gate_map, r) + f];
+  if (e.res) v += e.res[row_off(e.res_map, r) + f];
+  if (e.out32) e.out32[row_off(e.out32_map, r) + f] = v;
+  if (e.out16) e.out16[row_off(e.out16_map, r) + f] = __float2half_rn(e.act16 == ACT_ELU ? elu1(v) : v);
 }
 
 }  // namespace ptts
