@@ -74,7 +74,10 @@ struct Engine {
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
   const char* cur_tag = nullptr;
-  unsigned long long* gemm_trace = nullptr;  // bring-up: passed to the next GEMM launches
+  unsigned long long* gemm_trace = nullptr;
+  DevBuf<float> gemm_ws;      // split-K partial tiles
+  DevBuf<int> gemm_counters;  // split-K arrival counters (self-resetting)
+  void ensure_gemm_ws() { if (!gemm_ws.p) { gemm_ws.alloc((size_t)16 << 20); gemm_counters.alloc(4096); } }  // bring-up: passed to the next GEMM launches
   double step_kv_bytes = 0;  // FlowLM KV bytes one layer's decode attention reads in the current step
   void tag(const char* t) { cur_tag = t; }
   const char* take_tag(const char* dflt) { const char* t = cur_tag ? cur_tag : dflt; cur_tag = nullptr; return t; }
@@ -529,14 +532,24 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     p.BN = bn;
     grid = dim3(act_tiles, (F + bn - 1) / bn, 1);
   }
+  // Split-K whenever the output tiles alone cannot fill the chip (decode batches: 64 rows x F features is only
+  // F/128 tiles).  The reduction is ordered, so results are bit-reproducible run to run.
+  (void)allow_split;
   int splits = 1;
-  if (allow_split && epi.atomic) {
+  {
     const int tiles = grid.x * grid.y;
-    splits = std::max(1, std::min(148 / std::max(tiles, 1), total_kb / 2));
+    ensure_gemm_ws();
+    const size_t tile_bytes = (size_t)GEMM_BM * p.BN * 4;
+    if (tiles < 96 && tiles <= (int)gemm_counters.n && total_kb >= 4) {
+      splits = std::max(1, std::min(148 / tiles, total_kb / 2));
+      while (splits > 1 && (size_t)splits * tiles * tile_bytes > gemm_ws.n * sizeof(float)) --splits;
+    }
   }
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-  if (splits == 1) p.epi.atomic = 0;  // single CTA per tile: plain read-modify-write through epi.res
+  p.epi.atomic = 0;
+  p.ws = gemm_ws.p;
+  p.counters = gemm_counters.p;
   grid.z = splits;
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
   p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));

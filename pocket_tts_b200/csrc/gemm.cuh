@@ -54,7 +54,7 @@ struct GemmEpi {
   int act;              // applied to acc + bias
   int act16;            // applied to the f16 copy only (ELU in front of the next SEANet conv)
   float alpha;          // multiplies after the activation
-  int atomic;           // split-K: out32 += v with red.global.add (epilogue must be linear)
+  int atomic;           // unused by the engine (kept for the probe): out32 += v with red.global.add
 };
 
 struct GemmParams {
@@ -73,6 +73,8 @@ struct GemmParams {
   long long act_stream_stride;
   int act_ld;
   const __half* w;
+  float* ws;                // split-K workspace [split][tile][128*BN] f32
+  int* counters;            // split-K arrival counters, one per output tile, self-resetting
   unsigned long long* trace;  // optional [grid][16] %globaltimer stamps (bring-up only)
 };
 
@@ -89,7 +91,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;
-static constexpr int GEMM_THREADS = 192;
+static constexpr int GEMM_THREADS = 384;  // warp 0 TMA, warp 1 MMA, warps 2-5 TMEM readers, all 12 warps store the tile
 
 // Row part of a RowMap offset (everything except "+ f"); no integer division when the map is a plain
 // [rows, F] matrix.
@@ -119,22 +121,18 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, const float*
   const float* res = p.epi.res;
   float* out32 = p.epi.out32;
   __half* out16 = p.epi.out16;
-  const RowMap gate_map = p.epi.gate_map, res_map = p.epi.res_map, o32_map = p.epi.out32_map, o16_map = p.epi.out16_map;
   const int act = p.epi.act, act16 = p.epi.act16, atomic = p.epi.atomic;
   const float alpha = p.epi.alpha;
   const int swap = p.swap, F = p.F, T = p.T, R = p.R, G = p.G, n_streams = p.n_streams;
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
-  const int units = tile_rows * fv;
-  for (int u = tid; u < units; u += nthreads) {
-    const int row = u / fv;
-    const int q = u - row * fv;
-    const int f = f0 + q * V;
-    if (f >= F) continue;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  // one activation row per warp at a time: row validity and the four row offsets are warp-uniform
+  for (int row = warp; row < tile_rows; row += nwarps) {
     int r;
     if (swap) {
       r = t0 + row;
-      if (r >= T) continue;
+      if (r >= T) break;
     } else {
       const int g = row / R;
       const int tt = row - g * R;
@@ -142,57 +140,61 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, const float*
       if (g >= G || b >= n_streams || t >= T) continue;
       r = b * T + t;
     }
-    float v[V];
+    const float* gate_r = gate ? gate + row_off(p.epi.gate_map, r) : nullptr;
+    const float* res_r = (res && !atomic) ? res + row_off(p.epi.res_map, r) : nullptr;
+    float* o32_r = out32 ? out32 + row_off(p.epi.out32_map, r) : nullptr;
+    __half* o16_r = out16 ? out16 + row_off(p.epi.out16_map, r) : nullptr;
+    for (int q = lane; q < fv; q += 32) {
+      const int f = f0 + q * V;
+      if (f >= F) break;
+      float v[V];
 #pragma unroll
-    for (int c = 0; c < V; ++c) v[c] = swap ? stile[(q * V + c) * LD + row] : stile[row * LD + q * V + c];
-    // issue every global read of this unit before the math
-    float gv[V], rv[V], bv[V], sv[V];
-    if (V == 4) {
-      if (gate) { const float4 t4 = *reinterpret_cast<const float4*>(gate + row_off(gate_map, r) + f); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
-      if (res && !atomic) { const float4 t4 = *reinterpret_cast<const float4*>(res + row_off(res_map, r) + f); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
-      if (bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
-      if (fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
-    } else {
-      if (gate) gv[0] = gate[row_off(gate_map, r) + f];
-      if (res && !atomic) rv[0] = res[row_off(res_map, r) + f];
-      if (bias) bv[0] = __ldg(bias + f);
-      if (fscale) sv[0] = __ldg(fscale + f);
-    }
-#pragma unroll
-    for (int c = 0; c < V; ++c) {
-      float x = v[c];
-      if (bias) x += bv[c];
-      x = epi_act(act, x) * alpha;
-      if (fscale) x *= sv[c];
-      if (gate) x *= gv[c];
-      if (res && !atomic) x += rv[c];
-      v[c] = x;
-    }
-    if (atomic) {
-      float* dst = out32 + row_off(o32_map, r) + f;
-#pragma unroll
-      for (int c = 0; c < V; ++c) atomicAdd(dst + c, v[c]);
-      continue;
-    }
-    if (out32) {
-      float* dst = out32 + row_off(o32_map, r) + f;
-      if (V == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      else dst[0] = v[0];
-    }
-    if (out16) {
-      __half* dst = out16 + row_off(o16_map, r) + f;
-      if (act16 == ACT_ELU) {
-#pragma unroll
-        for (int c = 0; c < V; ++c) v[c] = elu1(v[c]);
-      }
+      for (int c = 0; c < V; ++c) v[c] = swap ? stile[(q * V + c) * LD + row] : stile[row * LD + q * V + c];
+      float gv[V], rv[V], bv[V], sv[V];
       if (V == 4) {
-        const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(dst) = pk;
+        if (gate_r) { const float4 t4 = *reinterpret_cast<const float4*>(gate_r + f); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
+        if (res_r) { const float4 t4 = *reinterpret_cast<const float4*>(res_r + f); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
+        if (bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
+        if (fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
       } else {
-        dst[0] = __float2half_rn(v[0]);
+        if (gate_r) gv[0] = gate_r[f];
+        if (res_r) rv[0] = res_r[f];
+        if (bias) bv[0] = __ldg(bias + f);
+        if (fscale) sv[0] = __ldg(fscale + f);
+      }
+#pragma unroll
+      for (int c = 0; c < V; ++c) {
+        float x = v[c];
+        if (bias) x += bv[c];
+        x = epi_act(act, x) * alpha;
+        if (fscale) x *= sv[c];
+        if (gate_r) x *= gv[c];
+        if (res_r) x += rv[c];
+        v[c] = x;
+      }
+      if (atomic) {
+#pragma unroll
+        for (int c = 0; c < V; ++c) atomicAdd(o32_r + f + c, v[c]);
+        continue;
+      }
+      if (o32_r) {
+        if (V == 4) *reinterpret_cast<float4*>(o32_r + f) = make_float4(v[0], v[1], v[2], v[3]);
+        else o32_r[f] = v[0];
+      }
+      if (o16_r) {
+        if (act16 == ACT_ELU) {
+#pragma unroll
+          for (int c = 0; c < V; ++c) v[c] = elu1(v[c]);
+        }
+        if (V == 4) {
+          const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(o16_r + f) = pk;
+        } else {
+          o16_r[f] = __float2half_rn(v[0]);
+        }
       }
     }
   }
@@ -299,7 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       __syncwarp();
     }
     PTTS_TRACE(5);
-  } else {
+  } else if (warp < 6) {
     // ===== epilogue, first half: TMEM -> registers -> smem (raw f32 tile) =====
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -322,10 +324,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   // ===== epilogue, second half: every warp of the CTA (producer and MMA warps are idle by now) =====
   tc_fence_before();
   __syncthreads();
-  {
+  bool do_epilogue = true;
+  if (gridDim.z > 1) {
+    // Deterministic split-K: every split parks its raw tile in the workspace; the CTA that arrives last sums the
+    // splits in index order (so the result does not depend on arrival order) and alone runs the epilogue.
+    __shared__ int s_last;
+    float* stile_w = reinterpret_cast<float*>(smem);
+    const int LD = p.BN + 1;
+    const int tile_elems = GEMM_BM * p.BN;
+    const int n_tiles = gridDim.x * gridDim.y;
+    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+    float* mine = p.ws + (static_cast<size_t>(blockIdx.z) * n_tiles + tile_id) * tile_elems;
+    for (int e = threadIdx.x; e < tile_elems; e += GEMM_THREADS) {
+      const int row = e / p.BN;
+      __stcg(mine + e, stile_w[row * LD + (e - row * p.BN)]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.counters + tile_id, 1) == static_cast<int>(gridDim.z) - 1);
+    __syncthreads();
+    do_epilogue = s_last != 0;
+    if (do_epilogue) {
+      __threadfence();
+      const float* base = p.ws + static_cast<size_t>(tile_id) * tile_elems;
+      const size_t zstride = static_cast<size_t>(n_tiles) * tile_elems;
+      for (int e = threadIdx.x; e < tile_elems; e += GEMM_THREADS) {
+        float acc = 0.f;
+        for (int z = 0; z < static_cast<int>(gridDim.z); ++z) acc += __ldcg(base + z * zstride + e);
+        const int row = e / p.BN;
+        stile_w[row * LD + (e - row * p.BN)] = acc;
+      }
+      if (threadIdx.x == 0) p.counters[tile_id] = 0;
+      __syncthreads();
+    }
+  }
+  if (do_epilogue) {
     const float* stile = reinterpret_cast<const float*>(smem);
-    if (p.vec4) epi_store_tile<4>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, blockIdx.z == 0);
-    else epi_store_tile<1>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, blockIdx.z == 0);
+    if (p.vec4) epi_store_tile<4>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, true);
+    else epi_store_tile<1>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, true);
   }
   if (warp == 2) PTTS_TRACE(8);
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
