@@ -328,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   if (gridDim.z > 1) {
     // Deterministic split-K: every split parks its raw tile in the workspace; the CTA that arrives last sums the
     // splits in index order (so the result does not depend on arrival order) and alone runs the epilogue.
-    __shared__ int s_last;
+    volatile int* s_last_p = reinterpret_cast<volatile int*>(tmem_slot + 1);  // spare word after the barriers
     float* stile_w = reinterpret_cast<float*>(smem);
     const int LD = p.BN + 1;
     const int tile_elems = GEMM_BM * p.BN;
@@ -341,9 +341,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(p.counters + tile_id, 1) == static_cast<int>(gridDim.z) - 1);
+    if (threadIdx.x == 0) *s_last_p = (atomicAdd(p.counters + tile_id, 1) == static_cast<int>(gridDim.z) - 1);
     __syncthreads();
-    do_epilogue = s_last != 0;
+    do_epilogue = *s_last_p != 0;
     if (do_epilogue) {
       __threadfence();
       const float* base = p.ws + static_cast<size_t>(tile_id) * tile_elems;
