@@ -548,6 +548,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.epi.atomic = 0;
+  p.epi_mask = epi_mask_of(p.epi);
   p.ws = gemm_ws.p;
   p.counters = gemm_counters.p;
   grid.z = splits;

@@ -67,6 +67,7 @@ struct GemmParams {
   int stages;
   int tmem_cols;
   int vec4;                 // every epilogue tensor is 16-byte addressable in groups of 4 features
+  int epi_mask;             // epi_mask_of(epi): selects the compiled store loop
   GemmEpi epi;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
@@ -112,22 +113,56 @@ __device__ __forceinline__ float epi_act(int act, float v) {
 // of the CTA walk it in output order, V consecutive features per thread, so every global access of a warp is
 // one contiguous 128-byte (V=1) or 512-byte (V=4) run.  Every epilogue field is hoisted into registers first;
 // the flag tests inside the loop are warp-uniform.
-template <int V>
-__device__ __forceinline__ void epi_store_tile(const GemmParams& p, const float* __restrict__ stile, int LD, int f0,
-                                               int t0, int b0, int tid, int nthreads, bool first_split) {
-  const float* __restrict__ bias = first_split ? p.epi.bias : nullptr;
-  const float* __restrict__ fscale = p.epi.fscale;
-  const float* gate = p.epi.gate;
-  const float* res = p.epi.res;
-  float* out32 = p.epi.out32;
-  __half* out16 = p.epi.out16;
-  const int act = p.epi.act, act16 = p.epi.act16, atomic = p.epi.atomic;
-  const float alpha = p.epi.alpha;
+// Epilogue shape as a bit mask.  The kernel switches once (warp-uniformly) to a copy of the store loop compiled
+// for exactly that shape, so the loop carries no predicated-off instructions for features it does not use;
+// EPI_GENERIC keeps every test at run time and serves shapes outside the list.
+enum {
+  EPI_BIAS = 1, EPI_FSCALE = 2, EPI_GATE = 4, EPI_RES = 8, EPI_OUT32 = 16, EPI_OUT16 = 32, EPI_ELU16 = 64,
+  EPI_ACT_SHIFT = 7 /* 2 bits */, EPI_ALPHA = 512, EPI_GENERIC = -1
+};
+__host__ __device__ inline int epi_mask_of(const GemmEpi& e) {
+  return (e.bias ? EPI_BIAS : 0) | (e.fscale ? EPI_FSCALE : 0) | (e.gate ? EPI_GATE : 0) | (e.res ? EPI_RES : 0) |
+         (e.out32 ? EPI_OUT32 : 0) | (e.out16 ? EPI_OUT16 : 0) | ((e.out16 && e.act16 == ACT_ELU) ? EPI_ELU16 : 0) |
+         (e.act << EPI_ACT_SHIFT) | (e.alpha != 1.f ? EPI_ALPHA : 0);
+}
+// every shape the engine issues (engine.cu: FlowLM, flow head, Mimi transformer, SEANet)
+#define PTTS_EPI_SHAPES(X)                                                                  \
+  X(EPI_OUT32)                                                                              \
+  X(EPI_BIAS | EPI_OUT32)                                                                   \
+  X(EPI_RES | EPI_OUT32)                                                                    \
+  X((ACT_GELU << EPI_ACT_SHIFT) | EPI_OUT16)                                                \
+  X(EPI_BIAS | (ACT_SILU << EPI_ACT_SHIFT) | EPI_OUT16)                                     \
+  X(EPI_BIAS | EPI_GATE | EPI_RES | EPI_OUT32)                                              \
+  X(EPI_BIAS | EPI_ALPHA | EPI_RES | EPI_OUT32 | EPI_OUT16)                                 \
+  X(EPI_FSCALE | EPI_RES | EPI_OUT32)                                                       \
+  X(EPI_FSCALE | EPI_RES | EPI_OUT32 | EPI_OUT16)                                           \
+  X(EPI_BIAS | EPI_OUT16 | EPI_ELU16)                                                       \
+  X(EPI_BIAS | EPI_OUT32 | EPI_OUT16 | EPI_ELU16)                                           \
+  X(EPI_BIAS | EPI_RES | EPI_OUT16 | EPI_ELU16)
+
+// Second half of the epilogue: the f32 accumulator tile sits in shared memory ([128][LD], LD odd); every warp of
+// the CTA takes one activation row at a time and its lanes walk V consecutive features each, so a warp's global
+// accesses are contiguous 128-byte (V=1) or 512-byte (V=4) runs.
+template <int V, int M>
+__device__ __noinline__ void epi_store_tile(const GemmParams& p, const float* __restrict__ stile, int LD, int f0, int t0,
+                                            int b0, int tid, int nthreads) {
+  constexpr bool GEN = (M == EPI_GENERIC);
+  const GemmEpi& e = p.epi;
+  const bool has_bias = GEN ? e.bias != nullptr : (M & EPI_BIAS) != 0;
+  const bool has_fscale = GEN ? e.fscale != nullptr : (M & EPI_FSCALE) != 0;
+  const bool has_gate = GEN ? e.gate != nullptr : (M & EPI_GATE) != 0;
+  const bool has_res = GEN ? e.res != nullptr : (M & EPI_RES) != 0;
+  const bool has_o32 = GEN ? e.out32 != nullptr : (M & EPI_OUT32) != 0;
+  const bool has_o16 = GEN ? e.out16 != nullptr : (M & EPI_OUT16) != 0;
+  const bool elu16 = GEN ? e.act16 == ACT_ELU : (M & EPI_ELU16) != 0;
+  const int act = GEN ? e.act : ((M >> EPI_ACT_SHIFT) & 3);
+  const float alpha = (GEN || (M & EPI_ALPHA)) ? e.alpha : 1.f;
+  const float* __restrict__ bias = e.bias;
+  const float* __restrict__ fscale = e.fscale;
   const int swap = p.swap, F = p.F, T = p.T, R = p.R, G = p.G, n_streams = p.n_streams;
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  // one activation row per warp at a time: row validity and the four row offsets are warp-uniform
   for (int row = warp; row < tile_rows; row += nwarps) {
     int r;
     if (swap) {
@@ -140,49 +175,43 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, const float*
       if (g >= G || b >= n_streams || t >= T) continue;
       r = b * T + t;
     }
-    const float* gate_r = gate ? gate + row_off(p.epi.gate_map, r) : nullptr;
-    const float* res_r = (res && !atomic) ? res + row_off(p.epi.res_map, r) : nullptr;
-    float* o32_r = out32 ? out32 + row_off(p.epi.out32_map, r) : nullptr;
-    __half* o16_r = out16 ? out16 + row_off(p.epi.out16_map, r) : nullptr;
+    const float* gate_r = has_gate ? e.gate + row_off(e.gate_map, r) : nullptr;
+    const float* res_r = has_res ? e.res + row_off(e.res_map, r) : nullptr;
+    float* o32_r = has_o32 ? e.out32 + row_off(e.out32_map, r) : nullptr;
+    __half* o16_r = has_o16 ? e.out16 + row_off(e.out16_map, r) : nullptr;
     for (int q = lane; q < fv; q += 32) {
       const int f = f0 + q * V;
       if (f >= F) break;
-      float v[V];
+      float v[V], gv[V], rv[V], bv[V], sv[V];
 #pragma unroll
       for (int c = 0; c < V; ++c) v[c] = swap ? stile[(q * V + c) * LD + row] : stile[row * LD + q * V + c];
-      float gv[V], rv[V], bv[V], sv[V];
       if (V == 4) {
-        if (gate_r) { const float4 t4 = *reinterpret_cast<const float4*>(gate_r + f); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
-        if (res_r) { const float4 t4 = *reinterpret_cast<const float4*>(res_r + f); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
-        if (bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
-        if (fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
+        if (has_gate) { const float4 t4 = *reinterpret_cast<const float4*>(gate_r + f); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
+        if (has_res) { const float4 t4 = *reinterpret_cast<const float4*>(res_r + f); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
+        if (has_bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
+        if (has_fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
       } else {
-        if (gate_r) gv[0] = gate_r[f];
-        if (res_r) rv[0] = res_r[f];
-        if (bias) bv[0] = __ldg(bias + f);
-        if (fscale) sv[0] = __ldg(fscale + f);
+        if (has_gate) gv[0] = gate_r[f];
+        if (has_res) rv[0] = res_r[f];
+        if (has_bias) bv[0] = __ldg(bias + f);
+        if (has_fscale) sv[0] = __ldg(fscale + f);
       }
 #pragma unroll
       for (int c = 0; c < V; ++c) {
         float x = v[c];
-        if (bias) x += bv[c];
+        if (has_bias) x += bv[c];
         x = epi_act(act, x) * alpha;
-        if (fscale) x *= sv[c];
-        if (gate_r) x *= gv[c];
-        if (res_r) x += rv[c];
+        if (has_fscale) x *= sv[c];
+        if (has_gate) x *= gv[c];
+        if (has_res) x += rv[c];
         v[c] = x;
       }
-      if (atomic) {
-#pragma unroll
-        for (int c = 0; c < V; ++c) atomicAdd(o32_r + f + c, v[c]);
-        continue;
-      }
-      if (o32_r) {
+      if (has_o32) {
         if (V == 4) *reinterpret_cast<float4*>(o32_r + f) = make_float4(v[0], v[1], v[2], v[3]);
         else o32_r[f] = v[0];
       }
-      if (o16_r) {
-        if (act16 == ACT_ELU) {
+      if (has_o16) {
+        if (elu16) {
 #pragma unroll
           for (int c = 0; c < V; ++c) v[c] = elu1(v[c]);
         }
@@ -335,9 +364,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     const int n_tiles = gridDim.x * gridDim.y;
     const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
     float* mine = p.ws + (static_cast<size_t>(blockIdx.z) * n_tiles + tile_id) * tile_elems;
-    for (int e = threadIdx.x; e < tile_elems; e += GEMM_THREADS) {
+    for (int e = threadIdx.x * 4; e < tile_elems; e += GEMM_THREADS * 4) {  // BN % 16 == 0: 4 columns share a row
       const int row = e / p.BN;
-      __stcg(mine + e, stile_w[row * LD + (e - row * p.BN)]);
+      const float* src = stile_w + row * LD + (e - row * p.BN);
+      __stcg(reinterpret_cast<float4*>(mine + e), make_float4(src[0], src[1], src[2], src[3]));
     }
     __threadfence();
     __syncthreads();
@@ -348,11 +378,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       __threadfence();
       const float* base = p.ws + static_cast<size_t>(tile_id) * tile_elems;
       const size_t zstride = static_cast<size_t>(n_tiles) * tile_elems;
-      for (int e = threadIdx.x; e < tile_elems; e += GEMM_THREADS) {
-        float acc = 0.f;
-        for (int z = 0; z < static_cast<int>(gridDim.z); ++z) acc += __ldcg(base + z * zstride + e);
+      const int nz = gridDim.z;
+      for (int e = threadIdx.x * 4; e < tile_elems; e += GEMM_THREADS * 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z0 = 0; z0 < nz; z0 += 8) {  // loads of a batch are issued together, sums stay in split order
+          float4 t[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (z0 + k < nz) t[k] = __ldcg(reinterpret_cast<const float4*>(base + (z0 + k) * zstride + e));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (z0 + k < nz) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
+        }
         const int row = e / p.BN;
-        stile_w[row * LD + (e - row * p.BN)] = acc;
+        float* dst = stile_w + row * LD + (e - row * p.BN);
+        dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
       }
       if (threadIdx.x == 0) p.counters[tile_id] = 0;
       __syncthreads();
@@ -360,8 +400,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   }
   if (do_epilogue) {
     const float* stile = reinterpret_cast<const float*>(smem);
-    if (p.vec4) epi_store_tile<4>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, true);
-    else epi_store_tile<1>(p, stile, p.BN + 1, f0, t0, b0, threadIdx.x, GEMM_THREADS, true);
+    const int LD = p.BN + 1;
+    if (!p.vec4) {
+      epi_store_tile<1, EPI_GENERIC>(p, stile, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS);
+    } else {
+      switch (p.epi_mask) {
+#define PTTS_EPI_CASE(MASK) \
+  case (MASK): epi_store_tile<4, (MASK)>(p, stile, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS); break;
+        PTTS_EPI_SHAPES(PTTS_EPI_CASE)
+#undef PTTS_EPI_CASE
+        default: epi_store_tile<4, EPI_GENERIC>(p, stile, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS); break;
+      }
+    }
   }
   if (warp == 2) PTTS_TRACE(8);
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
