@@ -19,6 +19,29 @@ namespace ptts {
 
 static thread_local std::string g_last_error;
 
+// Every kernel goes through here: programmatic dependent launch (the kernel's prologue overlaps its
+// predecessor's tail; see pdl_wait in ptx.cuh) and, for split-K GEMMs, a thread-block cluster along z.
+template <typename... KArgs, typename... Args>
+static void launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_z,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  if (pdl) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_z > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = 1; attrs[na].val.clusterDim.y = 1; attrs[na].val.clusterDim.z = cluster_z;
+    ++na;
+  }
+  cfg.attrs = attrs; cfg.numAttrs = na;
+  PTTS_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 // ------------------------------------------------------------------------------------------------
 // model constants (crates/pocket-tts/config/b6369a24.yaml)
 static constexpr int D_MODEL = 1024, N_HEADS = 16, N_LAYERS = 6, D_FFN = 4096;
@@ -67,6 +90,7 @@ struct Engine {
   cudaStream_t stream = nullptr;
   TmapCache tmaps;
   long long launches = 0;
+  bool use_pdl = true;
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
   struct ProfRec { const char* tag; cudaEvent_t a, b; double bytes, flops; };
@@ -75,9 +99,7 @@ struct Engine {
   std::vector<cudaEvent_t> prof_pool;
   const char* cur_tag = nullptr;
   unsigned long long* gemm_trace = nullptr;
-  DevBuf<float> gemm_ws;      // split-K partial tiles
-  DevBuf<int> gemm_counters;  // split-K arrival counters (self-resetting)
-  void ensure_gemm_ws() { if (!gemm_ws.p) { gemm_ws.alloc((size_t)16 << 20); gemm_counters.alloc(4096); } }  // bring-up: passed to the next GEMM launches
+  // bring-up: passed to the next GEMM launches
   double step_kv_bytes = 0;  // FlowLM KV bytes one layer's decode attention reads in the current step
   void tag(const char* t) { cur_tag = t; }
   const char* take_tag(const char* dflt) { const char* t = cur_tag ? cur_tag : dflt; cur_tag = nullptr; return t; }
@@ -533,24 +555,17 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     grid = dim3(act_tiles, (F + bn - 1) / bn, 1);
   }
   // Split-K whenever the output tiles alone cannot fill the chip (decode batches: 64 rows x F features is only
-  // F/128 tiles).  The reduction is ordered, so results are bit-reproducible run to run.
+  // F/128 tiles): a cluster of `splits` CTAs along z shares one output tile (gemm.cuh), at most 8 (portable size).
   (void)allow_split;
   int splits = 1;
   {
     const int tiles = grid.x * grid.y;
-    ensure_gemm_ws();
-    const size_t tile_bytes = (size_t)GEMM_BM * p.BN * 4;
-    if (tiles < 96 && tiles <= (int)gemm_counters.n && total_kb >= 4) {
-      splits = std::max(1, std::min(148 / tiles, total_kb / 2));
-      while (splits > 1 && (size_t)splits * tiles * tile_bytes > gemm_ws.n * sizeof(float)) --splits;
-    }
+    if (tiles < 96 && total_kb >= 4) splits = std::max(1, std::min(std::min(148 / tiles, total_kb / 2), GEMM_MAX_SPLIT));
+    if (cfg.reserved[2] > 0) splits = std::min(cfg.reserved[2], std::min(total_kb, GEMM_MAX_SPLIT));  // test hook
   }
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-  p.epi.atomic = 0;
   p.epi_mask = epi_mask_of(p.epi);
-  p.ws = gemm_ws.p;
-  p.counters = gemm_counters.p;
   grid.z = splits;
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
   p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));
@@ -561,22 +576,23 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   p.vec4 = (F % 4 == 0) && map_ok(epi.gate, epi.gate_map) && map_ok(epi.res, epi.res_map) && map_ok(epi.out32, epi.out32_map) &&
            map_ok(epi.out16, epi.out16_map) && map_ok(epi.bias, plain_map(4)) && map_ok(epi.fscale, plain_map(4));
   // the epilogue re-uses the stage buffers for its [128][BN+1] f32 tile
-  while ((size_t)p.stages * stage_bytes < (size_t)GEMM_BM * (p.BN + 1) * 4) ++p.stages;
+  const size_t tile_bytes = swap ? (size_t)p.BN * (GEMM_BM + 4) * 4 : (size_t)GEMM_BM * (p.BN + 4) * 4;
+  while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;
   const size_t smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
 
   // algorithmic traffic: weights once, the distinct activation rows once, every epilogue tensor once
   const double act_rows = (double)n_streams * (T + taps - 1);
   double bytes = (double)F * w.K * 2 + act_rows * a.C * 2;
-  bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + ((epi.res || epi.atomic) ? 4 : 0) + (epi.gate ? 4 : 0));
+  bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + (epi.res ? 4 : 0) + (epi.gate ? 4 : 0));
   ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K);
   if (cfg.debug_gemm) {
     const long long n = rows * F;
-    gemm_simt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+    launch_k(use_pdl, gemm_simt_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, 1, p);
   } else {
     const CUtensorMap& ma = swap ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
                                  : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
     const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
-    gemm_tc_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ma, mw, p);
+    launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, stream, (int)grid.z, ma, mw, p);
   }
   PTTS_CUDA(cudaGetLastError());
 }
@@ -586,7 +602,7 @@ void Engine::ln(const float* x, int rows, const float* w, const float* b, float 
                 int mod_ld, __half* out, int out_ld) {
   if (rows <= 0) return;
   ProfScope ps(*this, take_tag("layernorm"), (double)rows * C * (4 + 2 + (scale ? 8 : 0)), 0);
-  ln_rows_kernel<C><<<(rows + 3) / 4, 128, 0, stream>>>(x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
+  launch_k(use_pdl, ln_rows_kernel<C>, (rows + 3) / 4, 128, 0, stream, 1, x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
 }
 
 static GemmEpi epi_none() {
@@ -607,27 +623,26 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
     tag(is_prefill ? "prefill.in_proj" : "flowlm.in_proj"); gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
     if (is_prefill) {
       { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
-        flowlm_rope_append_kernel<<<dim3(rows, N_HEADS), 32, 0, stream>>>(qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
+        launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, N_HEADS), 32, 0, stream, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
       if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
       const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
       { ProfScope ps(*this, "prefill.attn");
-        flowlm_attn_prefill_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), 128, sm, stream, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
       const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
       { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0);
-        flowlm_attn_decode_kernel<<<dim3(rows, N_HEADS), 128, sm, stream>>>(qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), 128, sm, stream, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
     }
-    // x += attn W_o^T: split-K CTAs add their partial sums with red.add (epi.atomic); when the dispatcher
-    // keeps one CTA per tile it clears `atomic` and the same epilogue reads the residual through epi.res.
+    // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue
     e = epi_none();
-    e.out32 = x; e.out32_map = plain_map(D_MODEL); e.atomic = 1; e.res = x; e.res_map = plain_map(D_MODEL);
+    e.out32 = x; e.out32_map = plain_map(D_MODEL); e.res = x; e.res_map = plain_map(D_MODEL);
     tag(is_prefill ? "prefill.out_proj" : "flowlm.out_proj"); gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
     tag("flowlm.layernorm"); ln<D_MODEL>(x, rows, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = ffn; e.out16_map = plain_map(D_FFN);
     tag(is_prefill ? "prefill.linear1" : "flowlm.linear1"); gemm_rows(h, rows, D_MODEL, w_lin1[l], D_FFN, e);
     e = epi_none();
-    e.out32 = x; e.out32_map = plain_map(D_MODEL); e.atomic = 1; e.res = x; e.res_map = plain_map(D_MODEL);
+    e.out32 = x; e.out32_map = plain_map(D_MODEL); e.res = x; e.res_map = plain_map(D_MODEL);
     tag(is_prefill ? "prefill.linear2" : "flowlm.linear2"); gemm_rows(ffn, rows, D_FFN, w_lin2[l], D_MODEL, e, true);
   }
 }
@@ -652,13 +667,13 @@ void Engine::step_kernels(int n, float* stage_ms) {
   mark(0);
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
   { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
-    step_begin_kernel<<<n, 64, 0, stream>>>(row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p); }
+    launch_k(use_pdl, step_begin_kernel, n, 64, 0, stream, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p); }
   GemmEpi e = epi_none();
   e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
   tag("flowlm.input_linear"); gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
   flowlm_layers(n, x32.p, h16.p, qkv32.p, attn16.p, ffn16.p, false, nullptr, row_seq.p, nullptr);
   { ProfScope ps(*this, "flowlm.out_norm_eos", (double)n * D_MODEL * (4 + 2 + 4), 0);
-    ln_eos_kernel<<<(n + 3) / 4, 128, 0, stream>>>(x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,
+    launch_k(use_pdl, ln_eos_kernel, (n + 3) / 4, 128, 0, stream, 1, x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,
                                                    eos_logit.p); }
   mark(1);
   // ---- LSD flow head (reference flow_lm.rs:7-22,156-161; modules/mlp.rs:275,322-383)
@@ -667,7 +682,7 @@ void Engine::step_kernels(int n, float* stage_ms) {
   tag("flow.cond_embed"); gemm_rows(h16.p, n, D_MODEL, w_cond, FLOW_DIM, e);
   for (int s = 0; s < lsd_steps; ++s) {
     { ProfScope ps(*this, "flow.silu_add", (double)n * FLOW_DIM * 6, 0);
-      silu_add_kernel<<<(n * FLOW_DIM + 255) / 256, 256, 0, stream>>>(c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p); }
+      launch_k(use_pdl, silu_add_kernel, (n * FLOW_DIM + 255) / 256, 256, 0, stream, 1, c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p); }
     e = epi_none();
     e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
     tag("flow.adaln"); gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
@@ -696,7 +711,7 @@ void Engine::step_kernels(int n, float* stage_ms) {
   // ---- Mimi: de-norm + quantizer + upsample, decoder transformer (reference mimi.rs:143-157, transformer.rs:227-251)
   const int MR = n * MIMI_T;
   { ProfScope ps(*this, "mimi.frontend", (double)n * 16 * 512 * 12, 0);
-    mimi_frontend_kernel<<<n, 512, 0, stream>>>(z32.p, row_seq.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
+    launch_k(use_pdl, mimi_frontend_kernel, n, 512, 0, stream, 1, z32.p, row_seq.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
                                                quant_dbg.p); }
   for (int l = 0; l < MIMI_LAYERS; ++l) {
     tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[l].p, m_ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
@@ -704,10 +719,9 @@ void Engine::step_kernels(int n, float* stage_ms) {
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
     tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
     { ProfScope ps(*this, "mimi.attn", (double)n * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0);
-      mimi_attn_kernel<<<dim3(n, MIMI_HEADS), 128, 0, stream>>>(mqkv32.p, row_seq.p, ctl.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
+      launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), 128, 0, stream, 1, mqkv32.p, row_seq.p, ctl.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
-    e.atomic = 1;
     tag("mimi.out_proj"); gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);
     tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     e = epi_none();
@@ -718,15 +732,13 @@ void Engine::step_kernels(int n, float* stage_ms) {
     const bool last = (l == MIMI_LAYERS - 1);
     if (last) {  // also emit the f16 operand of SEANet's first conv behind its 6 left-context rows
       e.out16 = tr16.p; e.out16_map = stream_map(16, 512, 22 * 512, 6 * 512);
-    } else {
-      e.atomic = 1;
     }
     tag("mimi.linear2"); gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
   }
   mark(3);
   // ---- SEANet decoder (reference seanet.rs:309-402) as implicit GEMMs; ELU fused into the producer's epilogue
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
-    conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 0); }
+    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, stream, 1, segs, row_seq.p, 0); }
   e = epi_none(); e.bias = sb_conv0.p; e.out16 = a0.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 512, 17 * 512, 512);
   tag("seanet.conv0"); gemm(ActView{tr16.p, 512, 22, NB}, n, 16, 7, 16, 8, s_conv0, 512, e);
   e = epi_none(); e.bias = sb_ct2.p; e.out32 = x2.p; e.out32_map = stream_map(16, 1536, 96 * 256, 0);
@@ -754,13 +766,13 @@ void Engine::step_kernels(int n, float* stage_ms) {
   e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(1920, 64, 1922 * 64, 128);
   tag("seanet.res9b"); gemm_rows(h9.p, n * 1920, 64, s_r9b, 64, e);
   { ProfScope ps(*this, "seanet.final_conv", (double)n * (1922.0 * 128 + 1920 * 4), 2.0 * n * 1920 * 192);
-    seanet_final_conv_kernel<<<dim3((FRAME + 255) / 256, n), 256, 0, stream>>>(a9.p, s_final_w.p, s_final_b.p, n, pcm.p); }
+    launch_k(use_pdl, seanet_final_conv_kernel, dim3((FRAME + 255) / 256, n), 256, 0, stream, 1, a9.p, s_final_w.p, s_final_b.p, n, pcm.p); }
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
-    conv_state_move_kernel<<<dim3(n, 8), 128, 0, stream>>>(segs, row_seq.p, 1); }
+    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, stream, 1, segs, row_seq.p, 1); }
   mark(4);
   // ---- EOS bookkeeping, AR feedback, cursors (reference tts_model.rs:1055-1069)
   { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
-    step_end_kernel<<<n, 32, 0, stream>>>(row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
+    launch_k(use_pdl, step_end_kernel, n, 32, 0, stream, 1, row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
                                           latent_out.p, logit_out.p); }
   mark(5);
   PTTS_CUDA(cudaGetLastError());
@@ -941,7 +953,7 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
   PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, free_slots.data(), n * 4, cudaMemcpyHostToDevice, e.stream));
   for (int off = 0; off < n; off += 32768) {
     const int cnt = std::min(32768, n - off);
-    slot_reset_kernel<<<dim3(cnt, 9), 128, 0, e.stream>>>(e.segs, e.up_partial.p, e.prow_seq.p + off);
+    launch_k(e.use_pdl, slot_reset_kernel, dim3(cnt, 9), 128, 0, e.stream, 1, e.segs, e.up_partial.p, e.prow_seq.p + off);
   }
   PTTS_CUDA(cudaStreamSynchronize(e.stream));
   // text prefill in groups of at most PR rows (reference tts_model.rs:944-964)
@@ -958,7 +970,7 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
       PTTS_CUDA(cudaMemcpyAsync(e.prow_pos.p, rp.data(), rows * 4, cudaMemcpyHostToDevice, e.stream));
       PTTS_CUDA(cudaMemcpyAsync(e.ptokens.p, tokens + token_offsets[i0], rows * 4, cudaMemcpyHostToDevice, e.stream));
       { ProfScope ps(e, "prefill.embed", (double)rows * 1024 * 8, 0);
-        embed_rows_kernel<<<rows, 256, 0, e.stream>>>(e.ptokens.p, rows, e.lut.p, e.px32.p); }
+        launch_k(e.use_pdl, embed_rows_kernel, rows, 256, 0, e.stream, 1, e.ptokens.p, rows, e.lut.p, e.px32.p); }
       e.prefill(rows);
       PTTS_CUDA(cudaStreamSynchronize(e.stream));
     }
@@ -1191,7 +1203,7 @@ int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const flo
   if (bias) { bd.alloc(feats); PTTS_CUDA(cudaMemcpy(bd.p, bias, feats * 4, cudaMemcpyHostToDevice)); }
   GemmEpi ep = epi_none();
   ep.bias = bias ? bd.p : nullptr; ep.act = act; ep.out32 = out.p; ep.out32_map = plain_map(feats);
-  if (split_k > 1) { ep.atomic = 1; ep.res = out.p; ep.res_map = plain_map(feats); }
+  e.cfg.reserved[2] = split_k;
   e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
   PTTS_CUDA(cudaStreamSynchronize(e.stream));
   PTTS_CUDA(cudaMemcpy(d, out.p, (size_t)rows * feats * 4, cudaMemcpyDeviceToHost));
@@ -1215,7 +1227,7 @@ int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_
   DevBuf<unsigned long long> tr; tr.alloc(16 * 65536);
   GemmEpi ep = epi_none();
   ep.out32 = out.p; ep.out32_map = plain_map(feats);
-  if (split_k > 1) { ep.atomic = 1; ep.res = out.p; ep.res_map = plain_map(feats); }
+  e.cfg.reserved[2] = split_k;
   e.gemm_trace = tr.p;
   for (int i = 0; i < 3; ++i) e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
   cudaEvent_t a, b;

@@ -16,7 +16,16 @@
 //   swap = 0  activations on the 128-row MMA-M side, BN features on MMA-N   (rows >= 128: Mimi, SEANet)
 //   swap = 1  weights on the MMA-M side (128 features per tile), up to 256 activation rows on
 //             MMA-N, so a small decode batch wastes no MMA rows          (FlowLM decode, flow head)
-// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + tcgen05.mma issuer, warps 2-5 epilogue.
+//
+// Split-K (decode batches give only F/128 output tiles) runs as a thread-block cluster along z: every CTA of
+// the cluster accumulates its K slice in TMEM, stages the partial tile in its own shared memory, and after a
+// cluster barrier each CTA sums one interleaved set of rows over all peers through distributed shared memory
+// in rank order (bit-reproducible) and stores only those rows.  No workspace, no atomics, and the epilogue
+// work is spread over the whole cluster.
+//
+// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + tcgen05.mma issuer, warps 2-5 TMEM -> smem staging,
+// then all 12 warps store the tile.  Launched with programmatic dependent launch: everything before
+// griddepcontrol.wait (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail.
 #pragma once
 #include "ptx.cuh"
 
@@ -30,11 +39,6 @@ struct RowMap {
   int ld;
   long long stream_stride;
   long long base;
-  __host__ __device__ long long off(int r, int f) const {
-    int b = r / T;
-    int t = r - b * T;
-    return static_cast<long long>(b) * stream_stride + base + static_cast<long long>(t) * ld + f;
-  }
 };
 inline RowMap plain_map(int ld) { return RowMap{0x7fffffff, ld, 0, 0}; }
 
@@ -54,7 +58,7 @@ struct GemmEpi {
   int act;              // applied to acc + bias
   int act16;            // applied to the f16 copy only (ELU in front of the next SEANet conv)
   float alpha;          // multiplies after the activation
-  int atomic;           // unused by the engine (kept for the probe): out32 += v with red.global.add
+  int reserved;
 };
 
 struct GemmParams {
@@ -74,8 +78,6 @@ struct GemmParams {
   long long act_stream_stride;
   int act_ld;
   const __half* w;
-  float* ws;                // split-K workspace [split][tile][128*BN] f32
-  int* counters;            // split-K arrival counters, one per output tile, self-resetting
   unsigned long long* trace;  // optional [grid][16] %globaltimer stamps (bring-up only)
 };
 
@@ -92,7 +94,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;
-static constexpr int GEMM_THREADS = 384;  // warp 0 TMA, warp 1 MMA, warps 2-5 TMEM readers, all 12 warps store the tile
+static constexpr int GEMM_THREADS = 384;
+static constexpr int GEMM_MAX_SPLIT = 8;  // portable cluster size
 
 // Row part of a RowMap offset (everything except "+ f"); no integer division when the map is a plain
 // [rows, F] matrix.
@@ -109,10 +112,6 @@ __device__ __forceinline__ float epi_act(int act, float v) {
   return v;
 }
 
-// Second half of the epilogue: the f32 accumulator tile sits in shared memory ([128][LD], LD odd); all threads
-// of the CTA walk it in output order, V consecutive features per thread, so every global access of a warp is
-// one contiguous 128-byte (V=1) or 512-byte (V=4) run.  Every epilogue field is hoisted into registers first;
-// the flag tests inside the loop are warp-uniform.
 // Epilogue shape as a bit mask.  The kernel switches once (warp-uniformly) to a copy of the store loop compiled
 // for exactly that shape, so the loop carries no predicated-off instructions for features it does not use;
 // EPI_GENERIC keeps every test at run time and serves shapes outside the list.
@@ -140,12 +139,32 @@ __host__ __device__ inline int epi_mask_of(const GemmEpi& e) {
   X(EPI_BIAS | EPI_OUT32 | EPI_OUT16 | EPI_ELU16)                                           \
   X(EPI_BIAS | EPI_RES | EPI_OUT16 | EPI_ELU16)
 
-// Second half of the epilogue: the f32 accumulator tile sits in shared memory ([128][LD], LD odd); every warp of
-// the CTA takes one activation row at a time and its lanes walk V consecutive features each, so a warp's global
-// accesses are contiguous 128-byte (V=1) or 512-byte (V=4) runs.
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
+  return v;
+}
+__device__ __forceinline__ float ld_dsmem_f1(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t cta_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Second half of the epilogue.  The f32 accumulator tile sits in shared memory as [activation row][feature]
+// (pitch LD floats) in every CTA of the split-K cluster; CTA `rank` of `nsplit` owns rows rank*nwarps + warp,
+// stepping by nsplit*nwarps, sums them over the peers in rank order, applies the epilogue and writes V
+// consecutive features per lane, so each warp access is one contiguous 128-byte (V=1) or 512-byte (V=4) run.
 template <int V, int M>
-__device__ __noinline__ void epi_store_tile(const GemmParams& p, const float* __restrict__ stile, int LD, int f0, int t0,
-                                            int b0, int tid, int nthreads) {
+__device__ __noinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0,
+                                            int tid, int nthreads, int rank, int nsplit) {
   constexpr bool GEN = (M == EPI_GENERIC);
   const GemmEpi& e = p.epi;
   const bool has_bias = GEN ? e.bias != nullptr : (M & EPI_BIAS) != 0;
@@ -163,7 +182,10 @@ __device__ __noinline__ void epi_store_tile(const GemmParams& p, const float* __
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  for (int row = warp; row < tile_rows; row += nwarps) {
+  uint32_t peer[GEMM_MAX_SPLIT];
+#pragma unroll
+  for (int k = 0; k < GEMM_MAX_SPLIT; ++k) peer[k] = (nsplit > 1 && k < nsplit) ? map_to_rank(stile_addr, k) : stile_addr;
+  for (int row = rank * nwarps + warp; row < tile_rows; row += nwarps * nsplit) {
     int r;
     if (swap) {
       r = t0 + row;
@@ -182,15 +204,31 @@ __device__ __noinline__ void epi_store_tile(const GemmParams& p, const float* __
     for (int q = lane; q < fv; q += 32) {
       const int f = f0 + q * V;
       if (f >= F) break;
+      const uint32_t toff = static_cast<uint32_t>(row * LD + q * V) * 4u;
       float v[V], gv[V], rv[V], bv[V], sv[V];
-#pragma unroll
-      for (int c = 0; c < V; ++c) v[c] = swap ? stile[(q * V + c) * LD + row] : stile[row * LD + q * V + c];
       if (V == 4) {
+        float4 a4;
+        if (nsplit == 1) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(stile_addr + toff));
+        } else {
+          float4 t[GEMM_MAX_SPLIT];
+#pragma unroll
+          for (int k = 0; k < GEMM_MAX_SPLIT; ++k)
+            if (k < nsplit) t[k] = ld_dsmem_f4(peer[k] + toff);
+          a4 = t[0];
+#pragma unroll
+          for (int k = 1; k < GEMM_MAX_SPLIT; ++k)
+            if (k < nsplit) { a4.x += t[k].x; a4.y += t[k].y; a4.z += t[k].z; a4.w += t[k].w; }
+        }
+        v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w;
         if (has_gate) { const float4 t4 = *reinterpret_cast<const float4*>(gate_r + f); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
         if (has_res) { const float4 t4 = *reinterpret_cast<const float4*>(res_r + f); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
         if (has_bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
         if (has_fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
       } else {
+        float a = 0.f;
+        for (int k = 0; k < nsplit; ++k) a += ld_dsmem_f1(peer[k] + toff);
+        v[0] = a;
         if (has_gate) gv[0] = gate_r[f];
         if (has_res) rv[0] = res_r[f];
         if (has_bias) bv[0] = __ldg(bias + f);
@@ -245,6 +283,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (warp == 0) PTTS_TRACE(0);
 
   // tile coordinates
@@ -261,9 +300,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   const int b0 = tb * p.G;
   const int t0 = (act_tile - tb * tiles_t) * p.R;
   const int total_kb = p.taps * p.cblocks;
-  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int nsplit = gridDim.z;      // the cluster spans z: rank == blockIdx.z
+  const int rank = blockIdx.z;
+  const int kb0 = rank * p.kb_per_split;
   const int kb1 = min(total_kb, kb0 + p.kb_per_split);
-  const int nkb = kb1 - kb0;
+  const int nkb = kb1 - kb0;         // >= 1 by construction of the split
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_act);
@@ -284,6 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) PTTS_TRACE(1);
+  pdl_wait();  // nothing above reads or writes memory another kernel produces
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -331,89 +373,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     }
     PTTS_TRACE(5);
   } else if (warp < 6) {
-    // ===== epilogue, first half: TMEM -> registers -> smem (raw f32 tile) =====
+    // ===== epilogue, first half: TMEM -> registers -> smem tile [activation row][feature] (raw f32) =====
+    // The pipeline stages are dead once tmem_full has arrived (every MMA has consumed its operands), so the tile
+    // is staged over them.  Pitch = features + 4 floats: 16-byte aligned rows, conflict-free in both passes.
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (warp == 2) PTTS_TRACE(6);
     const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
     const int i = quad * 32 + lane;
-    // The pipeline stages are dead once tmem_full has arrived (every MMA has consumed its operands), so the
-    // accumulator tile [128][BN+1] f32 is staged there; the odd row pitch keeps both passes conflict-free.
     float* stile = reinterpret_cast<float*>(smem);
-    const int LD = p.BN + 1;
+    const int LD = (p.swap ? GEMM_BM : p.BN) + 4;
     for (int c = 0; c < p.BN; c += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c, v);
       tmem_ld_wait();
+      if (p.swap) {
+        // TMEM lane = feature, column = activation row: lanes write consecutive floats of row c+j
 #pragma unroll
-      for (int j = 0; j < 16; ++j) stile[i * LD + c + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) stile[(c + j) * LD + i] = __uint_as_float(v[j]);
+      } else {
+        // TMEM lane = activation row, columns = features: four 16-byte stores into row i
+        float4* dst = reinterpret_cast<float4*>(stile + i * LD + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
     }
     if (warp == 2) PTTS_TRACE(7);
   }
-  // ===== epilogue, second half: every warp of the CTA (producer and MMA warps are idle by now) =====
+  // ===== epilogue, second half: every warp of every CTA of the split-K cluster =====
   tc_fence_before();
   __syncthreads();
-  bool do_epilogue = true;
-  if (gridDim.z > 1) {
-    // Deterministic split-K: every split parks its raw tile in the workspace; the CTA that arrives last sums the
-    // splits in index order (so the result does not depend on arrival order) and alone runs the epilogue.
-    volatile int* s_last_p = reinterpret_cast<volatile int*>(tmem_slot + 1);  // spare word after the barriers
-    float* stile_w = reinterpret_cast<float*>(smem);
-    const int LD = p.BN + 1;
-    const int tile_elems = GEMM_BM * p.BN;
-    const int n_tiles = gridDim.x * gridDim.y;
-    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-    float* mine = p.ws + (static_cast<size_t>(blockIdx.z) * n_tiles + tile_id) * tile_elems;
-    for (int e = threadIdx.x * 4; e < tile_elems; e += GEMM_THREADS * 4) {  // BN % 16 == 0: 4 columns share a row
-      const int row = e / p.BN;
-      const float* src = stile_w + row * LD + (e - row * p.BN);
-      __stcg(reinterpret_cast<float4*>(mine + e), make_float4(src[0], src[1], src[2], src[3]));
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) *s_last_p = (atomicAdd(p.counters + tile_id, 1) == static_cast<int>(gridDim.z) - 1);
-    __syncthreads();
-    do_epilogue = *s_last_p != 0;
-    if (do_epilogue) {
-      __threadfence();
-      const float* base = p.ws + static_cast<size_t>(tile_id) * tile_elems;
-      const size_t zstride = static_cast<size_t>(n_tiles) * tile_elems;
-      const int nz = gridDim.z;
-      for (int e = threadIdx.x * 4; e < tile_elems; e += GEMM_THREADS * 4) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int z0 = 0; z0 < nz; z0 += 8) {  // loads of a batch are issued together, sums stay in split order
-          float4 t[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (z0 + k < nz) t[k] = __ldcg(reinterpret_cast<const float4*>(base + (z0 + k) * zstride + e));
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (z0 + k < nz) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
-        }
-        const int row = e / p.BN;
-        float* dst = stile_w + row * LD + (e - row * p.BN);
-        dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
-      }
-      if (threadIdx.x == 0) p.counters[tile_id] = 0;
-      __syncthreads();
-    }
-  }
-  if (do_epilogue) {
-    const float* stile = reinterpret_cast<const float*>(smem);
-    const int LD = p.BN + 1;
+  if (nsplit > 1) cluster_sync_all();  // all partial tiles are staged and visible cluster-wide
+  {
+    const uint32_t stile_addr = smem_u32(smem);
+    const int LD = (p.swap ? GEMM_BM : p.BN) + 4;
     if (!p.vec4) {
-      epi_store_tile<1, EPI_GENERIC>(p, stile, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS);
+      epi_store_tile<1, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
     } else {
       switch (p.epi_mask) {
 #define PTTS_EPI_CASE(MASK) \
-  case (MASK): epi_store_tile<4, (MASK)>(p, stile, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS); break;
+  case (MASK): epi_store_tile<4, (MASK)>(p, stile_addr, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit); break;
         PTTS_EPI_SHAPES(PTTS_EPI_CASE)
 #undef PTTS_EPI_CASE
-        default: epi_store_tile<4, EPI_GENERIC>(p, stile, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS); break;
+        default: epi_store_tile<4, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit); break;
       }
     }
   }
   if (warp == 2) PTTS_TRACE(8);
+  if (nsplit > 1) cluster_sync_all();  // peers may still be reading this CTA's tile
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
   if (warp == 1) PTTS_TRACE(9);
 }
@@ -421,6 +430,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
 // SIMT cross-check of the same contract (tests only; selected by ptts_engine_cfg.debug_gemm or
 // ptts_test_gemm(use_simt=1)).  One thread per output element.
 __global__ void gemm_simt_kernel(const GemmParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long rows = static_cast<long long>(p.n_streams) * p.T;
   if (idx >= rows * p.F) return;
@@ -433,12 +444,7 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
   float acc = 0.f;
   for (int j = 0; j < p.taps; ++j)
     for (int c = 0; c < C; ++c) acc += __half2float(a[j * p.act_ld + c]) * __half2float(w[j * C + c]);
-  GemmEpi e = p.epi;
-  e.atomic = 0;
-  if (p.epi.atomic) {  // emulate "+=" of the split-K epilogue
-    e.res = p.epi.out32;
-    e.res_map = p.epi.out32_map;
-  }
+  const GemmEpi& e = p.epi;
   float v = acc;
   if (e.bias) v += e.bias[f];
   v = epi_act(e.act, v) * e.alpha;

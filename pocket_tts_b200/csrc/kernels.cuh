@@ -52,6 +52,8 @@ template <int C>
 __global__ void ln_rows_kernel(const float* __restrict__ x, int rows, const float* __restrict__ w,
                                const float* __restrict__ b, float eps, const float* __restrict__ shift,
                                const float* __restrict__ scale, int mod_ld, __half* __restrict__ out16, int out_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int PER = C / 32;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -96,6 +98,8 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, int rows, const floa
 __global__ void ln_eos_kernel(const float* __restrict__ x, int rows, const float* __restrict__ w,
                               const float* __restrict__ b, const float* __restrict__ w_eos, const float* __restrict__ b_eos,
                               __half* __restrict__ h16, float* __restrict__ h32, float* __restrict__ eos_logit) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int C = 1024, PER = 32;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -134,6 +138,8 @@ __global__ void ln_eos_kernel(const float* __restrict__ x, int rows, const float
 // ---------------------------------------------------------------- embedding gather (conditioners/text.rs:289-303)
 __global__ void embed_rows_kernel(const int* __restrict__ tokens, int rows, const float* __restrict__ lut,
                                   float* __restrict__ x) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const float4* src = reinterpret_cast<const float4*>(lut + static_cast<long long>(tokens[row]) * 1024);
   float4* dst = reinterpret_cast<float4*>(x + static_cast<long long>(row) * 1024);
@@ -212,6 +218,8 @@ __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int h
 __global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
                                           const SeqDesc* __restrict__ seqs, const int* __restrict__ own_len, int layer,
                                           int n_heads, __half* __restrict__ out16) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* q_s = sm;          // 64
   float* red_s = sm + 64;   // 320
@@ -245,6 +253,8 @@ __global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const i
 __global__ void flowlm_rope_append_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
                                           const int* __restrict__ row_pos, const SeqDesc* __restrict__ seqs, int layer,
                                           int n_heads, float* __restrict__ q_rot) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int d_model = n_heads * HD;
   const SeqDesc sd = seqs[row_seq[r]];
@@ -267,6 +277,8 @@ __global__ void flowlm_rope_append_kernel(const float* __restrict__ qkv, const i
 __global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, const int* __restrict__ row_seq,
                                            const int* __restrict__ row_pos, const SeqDesc* __restrict__ seqs, int layer,
                                            int n_heads, __half* __restrict__ out16) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* q_s = sm;
   float* red_s = sm + 64;
@@ -289,6 +301,8 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __r
                                      const float* __restrict__ wq /*[512,32]*/, const float* __restrict__ wup /*[512,32]*/,
                                      float* __restrict__ partial /*[slots,16,512]*/, float* __restrict__ x /*[n*16,512]*/,
                                      float* __restrict__ dbg_quant) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float zd[LDIM];
   const int b = blockIdx.x, c = threadIdx.x;
   if (c < LDIM) zd[c] = z[b * LDIM + c] * emb_std[c] + emb_mean[c];
@@ -313,6 +327,8 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __r
 __global__ void mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
                                  const StreamCtl* __restrict__ ctl, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/,
                                  int layer, int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int NH = 8, DM = 512, T = 16, SW = MIMI_RING + 8;
   __shared__ float q_s[T][HD];
   __shared__ float p_s[T][SW];
@@ -405,6 +421,8 @@ __global__ void mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/,
 // y16[r, :] = silu(c[r, :] + te[:])   (reference modules/mlp.rs:328-330)
 __global__ void silu_add_kernel(const float* __restrict__ c, const float* __restrict__ te, int rows, int C,
                                 __half* __restrict__ y16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(rows) * C) return;
   const int col = static_cast<int>(i % C);
@@ -431,6 +449,8 @@ __device__ __forceinline__ float counter_normal(unsigned long long seed, int fra
 __global__ void step_begin_kernel(const int* __restrict__ row_seq, const StreamCtl* __restrict__ ctl,
                                   const float* __restrict__ feedback /*[slots,32]*/, __half* __restrict__ lat16 /*[n,64]*/,
                                   float* __restrict__ z32 /*[n,32]*/, __half* __restrict__ z16 /*[n,64]*/) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, k = threadIdx.x;  // 64 threads
   const int slot = row_seq[b];
   const StreamCtl c = ctl[slot];
@@ -452,6 +472,8 @@ __global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCt
                                 const float* __restrict__ z32, float* __restrict__ feedback,
                                 unsigned char* __restrict__ finished_out, float* __restrict__ latent_out,
                                 float* __restrict__ logit_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, k = threadIdx.x;  // 32 threads
   if (b >= n) return;
   const int slot = row_seq[b];
@@ -480,6 +502,8 @@ __global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCt
 // One thread per output sample; the 3x64 window of sample t is 384 contiguous bytes.
 __global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+1920][64]*/, const float* __restrict__ w /*[3][64]*/,
                                          const float* __restrict__ bias, int n, float* __restrict__ pcm /*[n,1920]*/) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float w_s[192];
   if (threadIdx.x < 192) w_s[threadIdx.x] = w[threadIdx.x];
   __syncthreads();
@@ -512,6 +536,8 @@ struct ConvSeg {
 struct ConvSegs { ConvSeg s[8]; };
 
 __global__ void conv_state_move_kernel(const ConvSegs segs, const int* __restrict__ row_seq, int save) {
+  pdl_launch_dependents();
+  pdl_wait();
   const ConvSeg g = segs.s[blockIdx.y];
   const int b = blockIdx.x;
   const int slot = row_seq[b];
@@ -527,6 +553,8 @@ __global__ void conv_state_move_kernel(const ConvSegs segs, const int* __restric
 
 // Stream open: zero the per-slot streaming state (reference init_state zeros: conv.rs:71-88,205-217).
 __global__ void slot_reset_kernel(const ConvSegs segs, float* __restrict__ partial, const int* __restrict__ slot_list) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int slot = slot_list[blockIdx.x];
   if (blockIdx.y < 8) {
     const ConvSeg g = segs.s[blockIdx.y];
@@ -539,10 +567,14 @@ __global__ void slot_reset_kernel(const ConvSegs segs, float* __restrict__ parti
 }
 
 __global__ void fill_f32_kernel(float* p, float v, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) p[i] = v;
 }
 __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) dst[i] = __float2half_rn(src[i]);
 }

@@ -125,6 +125,12 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_f16_m128(uint32_t n) {
          ((128u >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the engine is launched with programmaticStreamSerialization: it may start while its predecessor
+// drains, must not touch memory the predecessor produces before pdl_wait(), and lets its successor start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

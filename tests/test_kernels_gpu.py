@@ -27,7 +27,7 @@ GEMM_CASES = [
     # rows, feats, k, mode (0 auto, 1 act-as-M, 2 weight-as-M), split_k, act
     (64, 3072, 1024, 0, 1, 0),      # FlowLM in_proj at B=64 (swap-AB)
     (1, 1024, 1024, 0, 1, 0),       # B=1
-    (64, 1024, 4096, 0, 8, 0),      # linear2 with atomic split-K
+    (64, 1024, 4096, 0, 8, 0),      # linear2 with cluster split-K
     (64, 4096, 1024, 0, 1, 1),      # linear1 + tanh-GELU
     (200, 512, 512, 0, 1, 2),       # flow head width, SiLU, ragged rows
     (1024, 1536, 512, 0, 1, 0),     # Mimi in_proj at B=64 (activation-as-M)
