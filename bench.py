@@ -10,8 +10,9 @@ no data-path collective (weak scaling: 64 streams per GPU).
 One "step" = one whole batch job: open 64 streams (embedding + text prefill) and run 125 decode steps
 (FlowLM step -> LSD flow head -> Mimi decode) for all of them.
   value : device-resident run (ptts_step_device: PCM stays in HBM, no host sync inside the job)
-  e2e   : the same job through the public host call ptts_step with HOST buffers: token upload at open,
-          PCM + finished flags + latents copied back and the stream synchronised every frame.
+  e2e   : the same job through the public host calls (ptts_streams_open, ptts_step_begin/flags/pcm) with HOST
+          buffers: token upload at open; PCM + finished flags + latents copied back every frame, the flags awaited
+          before the next frame is issued.
   --impl reference : the reference's CPU path (oracle port of the Candle implementation; the Rust crate
           cannot be built here) on the box's host cores, one single-thread stream per core.
 """
@@ -198,13 +199,22 @@ def run_gpu(args):
 
     def job(host: bool, profile=None):
         slots = eng.open_streams([voice] * STREAMS, specs)
+        prev = None
         for f in range(FRAMES):
             if host:
-                pcm, fin, _, _ = eng.step(slots)
+                # public pipelined call: flags of frame f are needed to form the next batch, PCM of frame f-1 is
+                # fetched while frame f's language-model half runs
+                t = eng.step_begin(slots)
+                fin, _, _ = eng.step_flags(t)
+                if prev is not None:
+                    pcm = eng.step_pcm(prev)
+                prev = t
             elif profile is not None and f in profile:
                 eng.profile(True); eng.step_device(slots); eng.profile(False)
             else:
                 eng.step_device(slots)
+        if host:
+            pcm = eng.step_pcm(prev)
         eng.sync()
         if host:
             assert fin.all() and np.isfinite(pcm).all()

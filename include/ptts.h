@@ -117,6 +117,17 @@ int32_t ptts_streams_open(ptts_engine* e, int32_t n, ptts_voice* const* voices, 
 int32_t ptts_step(ptts_engine* e, const int32_t* slots, int32_t n, float* pcm_out, uint8_t* finished,
                   float* latent_out, float* eos_logit_out);
 
+/* The same step split so the host can overlap frames: the codec half of frame n (Mimi transformer + SEANet, which
+ * feeds nothing back) runs on its own CUDA stream while the language-model half of frame n+1 runs.
+ *   ticket = ptts_step_begin(e, slots, n, want_pcm)        enqueue only, returns a ticket >= 0
+ *   ptts_step_flags(e, ticket, finished, latent, logit)    waits for the language-model half (needed to choose the
+ *                                                          next batch); must precede the next ptts_step_begin
+ *   ptts_step_pcm(e, ticket, pcm_out)                      waits for the codec half; may follow the next begin
+ * At most two steps are in flight.  ptts_step == begin + flags + pcm. */
+int64_t ptts_step_begin(ptts_engine* e, const int32_t* slots, int32_t n, int32_t want_pcm);
+int32_t ptts_step_flags(ptts_engine* e, int64_t ticket, uint8_t* finished, float* latent_out, float* eos_logit_out);
+int32_t ptts_step_pcm(ptts_engine* e, int64_t ticket, float* pcm_out);
+
 /* Same step with every buffer resident on the device (no host copies, no sync): used to time the
  * kernels alone.  pcm_dev may be NULL to keep the PCM in the engine's own buffer. */
 int32_t ptts_step_device(ptts_engine* e, const int32_t* slots, int32_t n);

@@ -11,7 +11,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libptts_cuda.so"
 SYMBOLS = [
     "ptts_last_error", "ptts_abi_version", "ptts_engine_create", "ptts_engine_destroy",
     "ptts_engine_set_lsd_steps", "ptts_voice_from_prompt", "ptts_voice_destroy", "ptts_voice_len",
-    "ptts_streams_open", "ptts_step", "ptts_step_device", "ptts_sync", "ptts_stream_set_feedback",
+    "ptts_streams_open", "ptts_step", "ptts_step_begin", "ptts_step_flags", "ptts_step_pcm", "ptts_step_device", "ptts_sync", "ptts_stream_set_feedback",
     "ptts_stream_close", "ptts_stream_frames", "ptts_debug_read", "ptts_launch_count", "ptts_step_timed",
     "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report", "ptts_test_gemm", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
 ]
@@ -57,6 +57,10 @@ def lib() -> C.CDLL:
     L.ptts_voice_len.argtypes = [vp]
     L.ptts_streams_open.argtypes = [vp, i32, C.POINTER(vp), vp, vp, C.POINTER(StreamParams), vp]
     L.ptts_step.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.ptts_step_begin.argtypes = [vp, vp, i32, i32]
+    L.ptts_step_begin.restype = i64
+    L.ptts_step_flags.argtypes = [vp, i64, vp, vp, vp]
+    L.ptts_step_pcm.argtypes = [vp, i64, vp]
     L.ptts_step_device.argtypes = [vp, vp, i32]
     L.ptts_sync.argtypes = [vp]
     L.ptts_stream_set_feedback.argtypes = [vp, i32, vp]

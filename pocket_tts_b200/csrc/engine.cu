@@ -87,7 +87,10 @@ struct SlotHost {
 
 struct Engine {
   ptts_engine_cfg cfg{};
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;    // A: language-model path, prefill, host copies of the step flags
+  cudaStream_t stream_b = nullptr;  // B: codec path (Mimi transformer + SEANet)
+  cudaStream_t ls = nullptr;        // stream the launch helpers currently target
+  cudaEvent_t ev_a_done = nullptr, ev_front_done = nullptr, ev_b_done = nullptr;
   TmapCache tmaps;
   long long launches = 0;
   bool use_pdl = true;
@@ -140,6 +143,7 @@ struct Engine {
   DevBuf<float> x32, qkv32, eos_logit, c32, mod32, fx32, z32, h32dbg, quant_dbg;
   DevBuf<__half> h16, attn16, ffn16, lat16, y16, fh16, fg16, z16;
   DevBuf<float> mx32, mqkv32;
+  DevBuf<int> mimi_pos;  // per batch row: absolute position of the frame's first Mimi token (snapshot by front)
   DevBuf<__half> mh16, mattn16, mffn16;
   DevBuf<__half> tr16, a0, e2, h3, a3, e5, h6, a6, e8, h9, a9;
   DevBuf<float> x2, x5, x8, pcm;
@@ -151,7 +155,13 @@ struct Engine {
   DevBuf<__half> ph16, pattn16, pffn16;
   DevBuf<int> prow_seq, prow_pos, ptokens;
   // ---- pinned staging
-  float* pin_pcm = nullptr; unsigned char* pin_fin = nullptr; float* pin_lat = nullptr; float* pin_logit = nullptr;
+  float* pin_pcm[2] = {nullptr, nullptr}; unsigned char* pin_fin[2] = {nullptr, nullptr};
+  float* pin_lat[2] = {nullptr, nullptr}; float* pin_logit[2] = {nullptr, nullptr};
+  cudaEvent_t ev_flags[2] = {nullptr, nullptr}, ev_pcm[2] = {nullptr, nullptr};
+  struct Ticket { long long id = -1; int n = 0; bool flags_done = true, pcm_done = true, want_pcm = false; std::vector<int> slot_ids; };
+  Ticket tickets[2];
+  long long next_ticket = 0;
+  void sync_all() { PTTS_CUDA(cudaStreamSynchronize(stream)); PTTS_CUDA(cudaStreamSynchronize(stream_b)); }
   cudaEvent_t ev[10]{};
 
   ~Engine();
@@ -174,20 +184,32 @@ struct Engine {
                      const int* rseq, const int* rpos);
   void upload_rows(const int* slot_ids, int n);
   void step_kernels(int n, float* stage_ms);
+  void step_part_a(int n, bool marks);
+  void step_front(int n);
+  void step_part_b(int n, bool marks);
+  cudaGraphExec_t capture(cudaStream_t st, int n, int part, long long* kernels);
   void run_step(int n);
-  struct StepGraph { cudaGraphExec_t exec; long long kernels; };
+  struct StepGraph { cudaGraphExec_t a, b; long long kernels_a, kernels_b; };
   std::map<std::pair<int, int>, StepGraph> graphs;  // (batch rows, lsd steps) -> captured decode step
   void prefill(int rows);
 };
 
 Engine::~Engine() {
-  if (pin_pcm) cudaFreeHost(pin_pcm);
-  if (pin_fin) cudaFreeHost(pin_fin);
-  if (pin_lat) cudaFreeHost(pin_lat);
-  if (pin_logit) cudaFreeHost(pin_logit);
+  for (int i = 0; i < 2; ++i) {
+    if (pin_pcm[i]) cudaFreeHost(pin_pcm[i]);
+    if (pin_fin[i]) cudaFreeHost(pin_fin[i]);
+    if (pin_lat[i]) cudaFreeHost(pin_lat[i]);
+    if (pin_logit[i]) cudaFreeHost(pin_logit[i]);
+    if (ev_flags[i]) cudaEventDestroy(ev_flags[i]);
+    if (ev_pcm[i]) cudaEventDestroy(ev_pcm[i]);
+  }
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   for (auto& e : prof_pool) cudaEventDestroy(e);
-  for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+  for (auto& g : graphs) { cudaGraphExecDestroy(g.second.a); cudaGraphExecDestroy(g.second.b); }
+  if (ev_a_done) cudaEventDestroy(ev_a_done);
+  if (ev_front_done) cudaEventDestroy(ev_front_done);
+  if (ev_b_done) cudaEventDestroy(ev_b_done);
+  if (stream_b) cudaStreamDestroy(stream_b);
   for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (stream) cudaStreamDestroy(stream);
 }
@@ -200,12 +222,12 @@ void Engine::prof_begin(const char* t, double bytes, double flops) {
     x = prof_pool.back();
     prof_pool.pop_back();
   }
-  PTTS_CUDA(cudaEventRecord(ev2[0], stream));
+  PTTS_CUDA(cudaEventRecord(ev2[0], ls));
   prof_recs.push_back(ProfRec{t, ev2[0], ev2[1], bytes, flops});
 }
 void Engine::prof_end() {
   if (!profiling) return;
-  PTTS_CUDA(cudaEventRecord(prof_recs.back().b, stream));
+  PTTS_CUDA(cudaEventRecord(prof_recs.back().b, ls));
 }
 struct ProfScope {
   Engine& e;
@@ -463,6 +485,11 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   KVCAP = c.kv_capacity > 0 ? c.kv_capacity : 1024;
   PR = 4096;
   PTTS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  PTTS_CUDA(cudaStreamCreateWithFlags(&stream_b, cudaStreamNonBlocking));
+  ls = stream;
+  PTTS_CUDA(cudaEventCreateWithFlags(&ev_a_done, cudaEventDisableTiming));
+  PTTS_CUDA(cudaEventCreateWithFlags(&ev_front_done, cudaEventDisableTiming));
+  PTTS_CUDA(cudaEventCreateWithFlags(&ev_b_done, cudaEventDisableTiming));
   for (auto& e : ev) PTTS_CUDA(cudaEventCreate(&e));
   PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   {
@@ -489,6 +516,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   lat16.alloc((size_t)NB * 64); c32.alloc((size_t)NB * FLOW_DIM); mod32.alloc((size_t)NB * MOD_LD);
   fx32.alloc((size_t)NB * FLOW_DIM); y16.alloc((size_t)NB * FLOW_DIM); fh16.alloc((size_t)NB * FLOW_DIM);
   fg16.alloc((size_t)NB * FLOW_DIM); z32.alloc((size_t)NB * LDIM); z16.alloc((size_t)NB * 64);
+  mimi_pos.alloc(NB);
   const size_t MR = (size_t)NB * MIMI_T;
   mx32.alloc(MR * MIMI_DIM); mqkv32.alloc(MR * 3 * MIMI_DIM); mh16.alloc(MR * MIMI_DIM); mattn16.alloc(MR * MIMI_DIM);
   mffn16.alloc(MR * MIMI_FFN);
@@ -510,10 +538,14 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   px32.alloc((size_t)PR * D_MODEL); pqkv32.alloc((size_t)PR * 3 * D_MODEL); pqrot.alloc((size_t)PR * D_MODEL);
   ph16.alloc((size_t)PR * D_MODEL); pattn16.alloc((size_t)PR * D_MODEL); pffn16.alloc((size_t)PR * D_FFN);
   prow_seq.alloc(PR); prow_pos.alloc(PR); ptokens.alloc(PR);
-  PTTS_CUDA(cudaMallocHost(&pin_pcm, (size_t)NB * FRAME * 4));
-  PTTS_CUDA(cudaMallocHost(&pin_fin, NB));
-  PTTS_CUDA(cudaMallocHost(&pin_lat, (size_t)NB * LDIM * 4));
-  PTTS_CUDA(cudaMallocHost(&pin_logit, (size_t)NB * 4));
+  for (int i = 0; i < 2; ++i) {
+    PTTS_CUDA(cudaMallocHost(&pin_pcm[i], (size_t)NB * FRAME * 4));
+    PTTS_CUDA(cudaMallocHost(&pin_fin[i], NB));
+    PTTS_CUDA(cudaMallocHost(&pin_lat[i], (size_t)NB * LDIM * 4));
+    PTTS_CUDA(cudaMallocHost(&pin_logit[i], (size_t)NB * 4));
+    PTTS_CUDA(cudaEventCreateWithFlags(&ev_flags[i], cudaEventDisableTiming));
+    PTTS_CUDA(cudaEventCreateWithFlags(&ev_pcm[i], cudaEventDisableTiming));
+  }
   for (auto it = host.begin(); it != host.end();)  // only the time-embedding MLPs are needed again (set_lsd_steps)
     it = (it->first.find("time_embed") == std::string::npos) ? host.erase(it) : std::next(it);
   PTTS_CUDA(cudaDeviceSynchronize());
@@ -587,12 +619,12 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K);
   if (cfg.debug_gemm) {
     const long long n = rows * F;
-    launch_k(use_pdl, gemm_simt_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, 1, p);
+    launch_k(use_pdl, gemm_simt_kernel, (unsigned)((n + 255) / 256), 256, 0, ls, 1, p);
   } else {
     const CUtensorMap& ma = swap ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
                                  : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
     const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
-    launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, stream, (int)grid.z, ma, mw, p);
+    launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);
   }
   PTTS_CUDA(cudaGetLastError());
 }
@@ -602,7 +634,7 @@ void Engine::ln(const float* x, int rows, const float* w, const float* b, float 
                 int mod_ld, __half* out, int out_ld) {
   if (rows <= 0) return;
   ProfScope ps(*this, take_tag("layernorm"), (double)rows * C * (4 + 2 + (scale ? 8 : 0)), 0);
-  launch_k(use_pdl, ln_rows_kernel<C>, (rows + 3) / 4, 128, 0, stream, 1, x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
+  launch_k(use_pdl, ln_rows_kernel<C>, (rows + 3) / 4, 128, 0, ls, 1, x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
 }
 
 static GemmEpi epi_none() {
@@ -623,15 +655,15 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
     tag(is_prefill ? "prefill.in_proj" : "flowlm.in_proj"); gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
     if (is_prefill) {
       { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
-        launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, N_HEADS), 32, 0, stream, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
+        launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, N_HEADS), 32, 0, ls, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
       if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
       const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
       { ProfScope ps(*this, "prefill.attn");
-        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), 128, sm, stream, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), 128, sm, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
       const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
       { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0);
-        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), 128, sm, stream, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), 128, sm, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
     }
     // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue
     e = epi_none();
@@ -656,33 +688,38 @@ void Engine::upload_rows(const int* slot_ids, int n) {
     step_kv_bytes += (double)((sh.voice ? sh.voice->len : 0) + sh.own_len + 1) * N_HEADS * HD * 2 * 2;
   }
   if ((int)row_seq_host.size() == n && std::equal(slot_ids, slot_ids + n, row_seq_host.begin())) return;
+  PTTS_CUDA(cudaStreamSynchronize(stream_b));  // the codec stream may still be reading the previous batch map
   row_seq_host.assign(slot_ids, slot_ids + n);
   PTTS_CUDA(cudaMemcpyAsync(row_seq.p, row_seq_host.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
 }
 
 static RowMap stream_map(int T, int ld, long long stream_stride, long long base) { return RowMap{T, ld, stream_stride, base}; }
 
-void Engine::step_kernels(int n, float* stage_ms) {
-  auto mark = [&](int i) { if (stage_ms) PTTS_CUDA(cudaEventRecord(ev[i], stream)); };
-  mark(0);
+// One decode step is three launch sequences:
+//   A      step_begin, FlowLM transformer step, out_norm + EOS, LSD flow head, step_end      (the AR critical path)
+//   front  latent de-norm + quantizer + upsample; snapshots the frame position for Mimi's attention
+//   B      Mimi decoder transformer, SEANet decoder                                          (feeds nothing back)
+// Frame n+1's A depends only on frame n's A, so run_step() puts A on one stream and front+B on another: the codec
+// of frame n overlaps the language model of frame n+1.
+void Engine::step_part_a(int n, bool marks) {
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
   { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
-    launch_k(use_pdl, step_begin_kernel, n, 64, 0, stream, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p); }
+    launch_k(use_pdl, step_begin_kernel, n, 64, 0, ls, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p); }
   GemmEpi e = epi_none();
   e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
   tag("flowlm.input_linear"); gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
   flowlm_layers(n, x32.p, h16.p, qkv32.p, attn16.p, ffn16.p, false, nullptr, row_seq.p, nullptr);
   { ProfScope ps(*this, "flowlm.out_norm_eos", (double)n * D_MODEL * (4 + 2 + 4), 0);
-    launch_k(use_pdl, ln_eos_kernel, (n + 3) / 4, 128, 0, stream, 1, x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,
+    launch_k(use_pdl, ln_eos_kernel, (n + 3) / 4, 128, 0, ls, 1, x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,
                                                    eos_logit.p); }
-  mark(1);
+  if (marks) PTTS_CUDA(cudaEventRecord(ev[1], ls));
   // ---- LSD flow head (reference flow_lm.rs:7-22,156-161; modules/mlp.rs:275,322-383)
   e = epi_none();
   e.bias = b_cond.p; e.out32 = c32.p; e.out32_map = plain_map(FLOW_DIM);
   tag("flow.cond_embed"); gemm_rows(h16.p, n, D_MODEL, w_cond, FLOW_DIM, e);
   for (int s = 0; s < lsd_steps; ++s) {
     { ProfScope ps(*this, "flow.silu_add", (double)n * FLOW_DIM * 6, 0);
-      launch_k(use_pdl, silu_add_kernel, (n * FLOW_DIM + 255) / 256, 256, 0, stream, 1, c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p); }
+      launch_k(use_pdl, silu_add_kernel, (n * FLOW_DIM + 255) / 256, 256, 0, ls, 1, c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p); }
     e = epi_none();
     e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
     tag("flow.adaln"); gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
@@ -707,19 +744,30 @@ void Engine::step_kernels(int n, float* stage_ms) {
     e.out32 = z32.p; e.out32_map = plain_map(LDIM); e.out16 = z16.p; e.out16_map = plain_map(64);
     tag("flow.final"); gemm_rows(fh16.p, n, FLOW_DIM, w_final, LDIM, e);
   }
-  mark(2);
+  // ---- EOS bookkeeping, AR feedback, cursors (reference tts_model.rs:1055-1069)
+  { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
+    launch_k(use_pdl, step_end_kernel, n, 32, 0, ls, 1, row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
+                                          latent_out.p, logit_out.p); }
+}
+
+void Engine::step_front(int n) {
   // ---- Mimi: de-norm + quantizer + upsample, decoder transformer (reference mimi.rs:143-157, transformer.rs:227-251)
   const int MR = n * MIMI_T;
   { ProfScope ps(*this, "mimi.frontend", (double)n * 16 * 512 * 12, 0);
-    launch_k(use_pdl, mimi_frontend_kernel, n, 512, 0, stream, 1, z32.p, row_seq.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
-                                               quant_dbg.p); }
+    launch_k(use_pdl, mimi_frontend_kernel, n, 512, 0, ls, 1, z32.p, row_seq.p, ctl.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
+                                               quant_dbg.p, mimi_pos.p); }
+}
+
+void Engine::step_part_b(int n, bool marks) {
+  const int MR = n * MIMI_T;
+  GemmEpi e = epi_none();
   for (int l = 0; l < MIMI_LAYERS; ++l) {
     tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[l].p, m_ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     e = epi_none();
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
     tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
     { ProfScope ps(*this, "mimi.attn", (double)n * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0);
-      launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), 128, 0, stream, 1, mqkv32.p, row_seq.p, ctl.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
+      launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), 128, 0, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
     tag("mimi.out_proj"); gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);
@@ -735,10 +783,10 @@ void Engine::step_kernels(int n, float* stage_ms) {
     }
     tag("mimi.linear2"); gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
   }
-  mark(3);
+  if (marks) PTTS_CUDA(cudaEventRecord(ev[3], ls));
   // ---- SEANet decoder (reference seanet.rs:309-402) as implicit GEMMs; ELU fused into the producer's epilogue
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
-    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, stream, 1, segs, row_seq.p, 0); }
+    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, segs, row_seq.p, 0); }
   e = epi_none(); e.bias = sb_conv0.p; e.out16 = a0.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 512, 17 * 512, 512);
   tag("seanet.conv0"); gemm(ActView{tr16.p, 512, 22, NB}, n, 16, 7, 16, 8, s_conv0, 512, e);
   e = epi_none(); e.bias = sb_ct2.p; e.out32 = x2.p; e.out32_map = stream_map(16, 1536, 96 * 256, 0);
@@ -766,51 +814,90 @@ void Engine::step_kernels(int n, float* stage_ms) {
   e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(1920, 64, 1922 * 64, 128);
   tag("seanet.res9b"); gemm_rows(h9.p, n * 1920, 64, s_r9b, 64, e);
   { ProfScope ps(*this, "seanet.final_conv", (double)n * (1922.0 * 128 + 1920 * 4), 2.0 * n * 1920 * 192);
-    launch_k(use_pdl, seanet_final_conv_kernel, dim3((FRAME + 255) / 256, n), 256, 0, stream, 1, a9.p, s_final_w.p, s_final_b.p, n, pcm.p); }
+    launch_k(use_pdl, seanet_final_conv_kernel, dim3((FRAME + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, pcm.p); }
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
-    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, stream, 1, segs, row_seq.p, 1); }
-  mark(4);
-  // ---- EOS bookkeeping, AR feedback, cursors (reference tts_model.rs:1055-1069)
-  { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
-    launch_k(use_pdl, step_end_kernel, n, 32, 0, stream, 1, row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
-                                          latent_out.p, logit_out.p); }
-  mark(5);
+    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, segs, row_seq.p, 1); }
+}
+
+// Sequential form on one stream (stage timing, per-launch profiling).
+void Engine::step_kernels(int n, float* stage_ms) {
+  ls = stream;
+  const bool marks = stage_ms != nullptr;
+  if (marks) PTTS_CUDA(cudaEventRecord(ev[0], ls));
+  step_part_a(n, marks);
+  if (marks) PTTS_CUDA(cudaEventRecord(ev[2], ls));
+  step_front(n);
+  step_part_b(n, marks);
+  if (marks) PTTS_CUDA(cudaEventRecord(ev[4], ls));
   PTTS_CUDA(cudaGetLastError());
   if (stage_ms) {
     PTTS_CUDA(cudaStreamSynchronize(stream));
-    for (int i = 0; i < 5; ++i) PTTS_CUDA(cudaEventElapsedTime(stage_ms + i, ev[i], ev[i + 1]));
-    PTTS_CUDA(cudaEventElapsedTime(stage_ms + 5, ev[0], ev[5]));
+    for (int i = 0; i < 4; ++i) PTTS_CUDA(cudaEventElapsedTime(stage_ms + i, ev[i], ev[i + 1]));
+    stage_ms[4] = 0.f;
+    PTTS_CUDA(cudaEventElapsedTime(stage_ms + 5, ev[0], ev[4]));
     stage_ms[6] = stage_ms[7] = 0.f;
   }
 }
 
-// The decode step is ~100 dependent launches of a few microseconds each: replaying it as a CUDA graph removes
-// the per-launch host cost.  Every pointer in the step is a fixed engine buffer and the batch composition is
-// data (row_seq), so one graph per (rows, lsd_steps) serves every step of every batch of that size.
-void Engine::run_step(int n) {
-  if (!cfg.use_cuda_graph || profiling) return step_kernels(n, nullptr);
-  const auto key = std::make_pair(n, lsd_steps);
-  auto it = graphs.find(key);
-  if (it == graphs.end()) {
-    const long long before = launches;
-    cudaGraph_t g = nullptr;
-    PTTS_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    try {
-      step_kernels(n, nullptr);
-    } catch (...) {
-      cudaStreamEndCapture(stream, &g);
-      if (g) cudaGraphDestroy(g);
-      throw;
-    }
-    PTTS_CUDA(cudaStreamEndCapture(stream, &g));
-    StepGraph sg{nullptr, launches - before};
-    launches = before;
-    PTTS_CUDA(cudaGraphInstantiate(&sg.exec, g, 0));
-    PTTS_CUDA(cudaGraphDestroy(g));
-    it = graphs.emplace(key, sg).first;
+cudaGraphExec_t Engine::capture(cudaStream_t st, int n, int part, long long* kernels) {
+  const long long before = launches;
+  cudaGraph_t g = nullptr;
+  ls = st;
+  PTTS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  try {
+    if (part == 0) step_part_a(n, false);
+    else step_part_b(n, false);
+  } catch (...) {
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
   }
-  PTTS_CUDA(cudaGraphLaunch(it->second.exec, stream));
-  launches += it->second.kernels;
+  PTTS_CUDA(cudaStreamEndCapture(st, &g));
+  *kernels = launches - before;
+  launches = before;
+  cudaGraphExec_t exec = nullptr;
+  PTTS_CUDA(cudaGraphInstantiate(&exec, g, 0));
+  PTTS_CUDA(cudaGraphDestroy(g));
+  return exec;
+}
+
+// Enqueue one step: A on `stream`, front + B on `stream_b`, each of A and B replayed as a CUDA graph (the step is
+// ~100 dependent launches of a few microseconds; every pointer is a fixed engine buffer and the batch composition is
+// data, so one pair of graphs per (rows, lsd_steps) serves every step of that size).
+void Engine::run_step(int n) {
+  if (profiling) return step_kernels(n, nullptr);
+  // A(n) may not overwrite z32 / advance the frame counters before front(n-1) has consumed them
+  PTTS_CUDA(cudaStreamWaitEvent(stream, ev_front_done, 0));
+  if (cfg.use_cuda_graph) {
+    const auto key = std::make_pair(n, lsd_steps);
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      StepGraph sg{};
+      sg.a = capture(stream, n, 0, &sg.kernels_a);
+      sg.b = capture(stream_b, n, 1, &sg.kernels_b);
+      it = graphs.emplace(key, sg).first;
+    }
+    PTTS_CUDA(cudaGraphLaunch(it->second.a, stream));
+    PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
+    PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_a_done, 0));
+    ls = stream_b;
+    step_front(n);
+    PTTS_CUDA(cudaEventRecord(ev_front_done, stream_b));
+    PTTS_CUDA(cudaGraphLaunch(it->second.b, stream_b));
+    launches += it->second.kernels_a + it->second.kernels_b;
+  } else {
+    ls = stream;
+    step_part_a(n, false);
+    PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
+    PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_a_done, 0));
+    ls = stream_b;
+    step_front(n);
+    PTTS_CUDA(cudaEventRecord(ev_front_done, stream_b));
+    step_part_b(n, false);
+  }
+  PTTS_CUDA(cudaEventRecord(ev_b_done, stream_b));
+  ls = stream;
+  PTTS_CUDA(cudaGetLastError());
 }
 
 void Engine::prefill(int rows) {
@@ -896,7 +983,7 @@ int32_t ptts_voice_from_prompt(ptts_engine* h, const float* audio_prompt, int32_
 
 void ptts_voice_destroy(ptts_engine* h, ptts_voice* v) {
   if (!v) return;
-  if (h) { cudaSetDevice(h->e.cfg.device); cudaStreamSynchronize(h->e.stream); }
+  if (h) { cudaSetDevice(h->e.cfg.device); cudaStreamSynchronize(h->e.stream); cudaStreamSynchronize(h->e.stream_b); }
   delete v;
 }
 
@@ -909,6 +996,7 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
                "ptts_streams_open: null argument");
   Engine& e = h->e;
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  PTTS_CUDA(cudaStreamSynchronize(e.stream_b));  // a recycled slot's codec state may still be in use
   // validate everything before touching state
   std::vector<int> free_slots;
   for (int s = 0; s < e.NS && (int)free_slots.size() < n; ++s) if (!e.slots[s].in_use) free_slots.push_back(s);
@@ -991,29 +1079,95 @@ static void check_slots(Engine& e, const int32_t* slot_ids, int n) {
   }
 }
 
+// ---- pipelined step: begin (enqueue) / flags (language-model results) / pcm (codec result)
+static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, bool want_pcm) {
+  check_slots(e, slot_ids, n);
+  const long long id = e.next_ticket;
+  Engine::Ticket& t = e.tickets[id & 1];
+  PTTS_REQUIRE(t.flags_done && t.pcm_done, PTTS_ERR_STATE, "step %lld still has unfetched results (two steps may be in flight)", t.id);
+  const Engine::Ticket& prev = e.tickets[(id + 1) & 1];
+  PTTS_REQUIRE(prev.flags_done, PTTS_ERR_STATE, "fetch the flags of step %lld before beginning the next step", prev.id);
+  e.upload_rows(slot_ids, n);
+  e.run_step(n);
+  const int par = (int)(id & 1);
+  PTTS_CUDA(cudaMemcpyAsync(e.pin_fin[par], e.finished_dev.p, n, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.pin_lat[par], e.latent_out.p, (size_t)n * LDIM * 4, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.pin_logit[par], e.logit_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaEventRecord(e.ev_flags[par], e.stream));
+  if (want_pcm) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm[par], e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream_b));
+  PTTS_CUDA(cudaEventRecord(e.ev_pcm[par], e.stream_b));
+  t.id = id; t.n = n; t.flags_done = false; t.pcm_done = false; t.want_pcm = want_pcm;
+  t.slot_ids.assign(slot_ids, slot_ids + n);
+  e.next_ticket = id + 1;
+  return id;
+}
+
+static void step_flags_impl(Engine& e, long long id, uint8_t* finished, float* latent_out, float* eos_logit_out) {
+  Engine::Ticket& t = e.tickets[id & 1];
+  PTTS_REQUIRE(t.id == id && !t.flags_done, PTTS_ERR_STATE, "ticket %lld is not pending", id);
+  const int par = (int)(id & 1);
+  PTTS_CUDA(cudaEventSynchronize(e.ev_flags[par]));
+  if (latent_out) std::memcpy(latent_out, e.pin_lat[par], (size_t)t.n * LDIM * 4);
+  if (eos_logit_out) std::memcpy(eos_logit_out, e.pin_logit[par], (size_t)t.n * 4);
+  for (int i = 0; i < t.n; ++i) {
+    SlotHost& sh = e.slots[t.slot_ids[i]];
+    sh.frames += 1; sh.own_len += 1;
+    sh.finished = e.pin_fin[par][i] != 0;
+    if (finished) finished[i] = e.pin_fin[par][i];
+  }
+  t.flags_done = true;
+}
+
+static void step_pcm_impl(Engine& e, long long id, float* pcm_out) {
+  Engine::Ticket& t = e.tickets[id & 1];
+  PTTS_REQUIRE(t.id == id && !t.pcm_done, PTTS_ERR_STATE, "ticket %lld has no pending PCM", id);
+  const int par = (int)(id & 1);
+  PTTS_CUDA(cudaEventSynchronize(e.ev_pcm[par]));
+  if (pcm_out) {
+    PTTS_REQUIRE(t.want_pcm, PTTS_ERR_STATE, "step %lld was begun without PCM read-back", id);
+    std::memcpy(pcm_out, e.pin_pcm[par], (size_t)t.n * FRAME * 4);
+  }
+  t.pcm_done = true;
+}
+
+int64_t ptts_step_begin(ptts_engine* h, const int32_t* slot_ids, int32_t n, int32_t want_pcm) {
+  try {
+    PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+    PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+    return step_begin_impl(h->e, slot_ids, n, want_pcm != 0);
+  } catch (const ptts::Error& ex) {
+    g_last_error = ex.what();
+    return ex.code;
+  }
+}
+
+int32_t ptts_step_flags(ptts_engine* h, int64_t ticket, uint8_t* finished, float* latent_out, float* eos_logit_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+  step_flags_impl(h->e, ticket, finished, latent_out, eos_logit_out);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_step_pcm(ptts_engine* h, int64_t ticket, float* pcm_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+  step_pcm_impl(h->e, ticket, pcm_out);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
 int32_t ptts_step(ptts_engine* h, const int32_t* slot_ids, int32_t n, float* pcm_out, uint8_t* finished, float* latent_out,
                   float* eos_logit_out) {
   PTTS_TRY
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
   Engine& e = h->e;
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
-  check_slots(e, slot_ids, n);
-  e.upload_rows(slot_ids, n);
-  e.run_step(n);
-  if (pcm_out) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm, e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream));
-  PTTS_CUDA(cudaMemcpyAsync(e.pin_fin, e.finished_dev.p, n, cudaMemcpyDeviceToHost, e.stream));
-  PTTS_CUDA(cudaMemcpyAsync(e.pin_lat, e.latent_out.p, (size_t)n * LDIM * 4, cudaMemcpyDeviceToHost, e.stream));
-  PTTS_CUDA(cudaMemcpyAsync(e.pin_logit, e.logit_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e.stream));
-  PTTS_CUDA(cudaStreamSynchronize(e.stream));
-  if (pcm_out) std::memcpy(pcm_out, e.pin_pcm, (size_t)n * FRAME * 4);
-  if (latent_out) std::memcpy(latent_out, e.pin_lat, (size_t)n * LDIM * 4);
-  if (eos_logit_out) std::memcpy(eos_logit_out, e.pin_logit, (size_t)n * 4);
-  for (int i = 0; i < n; ++i) {
-    SlotHost& sh = e.slots[slot_ids[i]];
-    sh.frames += 1; sh.own_len += 1;
-    sh.finished = e.pin_fin[i] != 0;
-    if (finished) finished[i] = e.pin_fin[i];
-  }
+  const long long id = step_begin_impl(e, slot_ids, n, pcm_out != nullptr);
+  step_flags_impl(e, id, finished, latent_out, eos_logit_out);
+  step_pcm_impl(e, id, pcm_out);
   return PTTS_OK;
   PTTS_CATCH
 }
@@ -1042,6 +1196,7 @@ int32_t ptts_step_timed(ptts_engine* h, const int32_t* slot_ids, int32_t n, floa
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
   check_slots(e, slot_ids, n);
   e.upload_rows(slot_ids, n);
+  e.sync_all();
   e.step_kernels(n, stage_ms);
   for (int i = 0; i < n; ++i) {
     SlotHost& sh = e.slots[slot_ids[i]];
@@ -1056,7 +1211,7 @@ int32_t ptts_sync(ptts_engine* h) {
   PTTS_TRY
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
   PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
-  PTTS_CUDA(cudaStreamSynchronize(h->e.stream));
+  h->e.sync_all();
   return PTTS_OK;
   PTTS_CATCH
 }
@@ -1079,7 +1234,7 @@ int32_t ptts_stream_close(ptts_engine* h, int32_t slot) {
   Engine& e = h->e;
   PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
-  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  e.sync_all();
   e.slots[slot] = SlotHost{};
   e.row_seq_host.clear();
   return PTTS_OK;
@@ -1107,7 +1262,7 @@ int64_t ptts_debug_read(ptts_engine* h, const char* name, int32_t row, float* ou
     Engine& e = h->e;
     PTTS_REQUIRE(row >= 0 && row < e.NB, PTTS_ERR_INVALID, "row %d out of range", row);
     PTTS_CUDA(cudaSetDevice(e.cfg.device));
-    PTTS_CUDA(cudaStreamSynchronize(e.stream));
+    e.sync_all();
     const std::string n(name);
     const float* src = nullptr;
     int64_t cnt = 0;
@@ -1145,7 +1300,7 @@ int32_t ptts_profile_enable(ptts_engine* h, int32_t on) {
   PTTS_TRY
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
   PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
-  PTTS_CUDA(cudaStreamSynchronize(h->e.stream));
+  h->e.sync_all();
   h->e.profiling = on != 0;
   return PTTS_OK;
   PTTS_CATCH
@@ -1176,6 +1331,7 @@ struct TestCtx {
     e.cfg.device = device;
     e.cfg.debug_gemm = use_simt;
     PTTS_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+    e.ls = e.stream;
     PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
 };

@@ -297,15 +297,17 @@ __global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, cons
 // latent de-norm (tts_model.rs:1033-1035) -> Quantizer 1x1 conv 32->512 (mimi.rs:32-36) -> depthwise
 // ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid n, block 512 (one channel each).
 __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __restrict__ row_seq,
-                                     const float* __restrict__ emb_std, const float* __restrict__ emb_mean,
+                                     const StreamCtl* __restrict__ ctl, const float* __restrict__ emb_std, const float* __restrict__ emb_mean,
                                      const float* __restrict__ wq /*[512,32]*/, const float* __restrict__ wup /*[512,32]*/,
                                      float* __restrict__ partial /*[slots,16,512]*/, float* __restrict__ x /*[n*16,512]*/,
-                                     float* __restrict__ dbg_quant) {
+                                     float* __restrict__ dbg_quant, int* __restrict__ mimi_pos) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float zd[LDIM];
   const int b = blockIdx.x, c = threadIdx.x;
   if (c < LDIM) zd[c] = z[b * LDIM + c] * emb_std[c] + emb_mean[c];
+  // runs after step_end of the same frame: the frame counter has already advanced by one
+  if (c == 0) mimi_pos[b] = (ctl[row_seq[b]].frame - 1) * 16;
   __syncthreads();
   float qv = 0.f;
 #pragma unroll
@@ -325,7 +327,7 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __r
 // K,V live in a per-slot ring indexed by position % 272; 272 >= 250 + 15 so the 16 rows written first never
 // overwrite a key that a query of this step still needs.  grid (n, 8 heads), block 128.
 __global__ void mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
-                                 const StreamCtl* __restrict__ ctl, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/,
+                                 const int* __restrict__ mimi_pos, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/,
                                  int layer, int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
   pdl_launch_dependents();
   pdl_wait();
@@ -335,7 +337,7 @@ __global__ void mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/,
   __shared__ float inv_s[T];
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = row_seq[b];
-  const int p0 = ctl[slot].frame * T;  // absolute position of the first new row
+  const int p0 = mimi_pos[b];  // absolute position of the first new row
   __half* kring = ring + ((static_cast<long long>(slot) * n_layers + layer) * 2 * NH + h) * MIMI_RING * HD;
   __half* vring = kring + static_cast<long long>(NH) * MIMI_RING * HD;
   // RoPE + ring write: 16 rows x 32 pairs = 512 items over 128 threads

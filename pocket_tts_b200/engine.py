@@ -119,6 +119,29 @@ class Engine:
         check(_lib.lib().ptts_step(self._h, _ptr(slots), n, _ptr(pcm), _ptr(fin), _ptr(lat), _ptr(logit)))
         return pcm, fin.astype(bool), lat, logit
 
+    # ---- pipelined form: begin -> flags -> (next begin) -> pcm
+    def step_begin(self, slots: np.ndarray, want_pcm: bool = True) -> int:
+        slots = np.ascontiguousarray(slots, dtype=np.int32)
+        t = int(_lib.lib().ptts_step_begin(self._h, _ptr(slots), len(slots), int(want_pcm)))
+        check(t)
+        self._pending_n = getattr(self, "_pending_n", {})
+        self._pending_n[t] = len(slots)
+        return t
+
+    def step_flags(self, ticket: int):
+        n = self._pending_n[ticket]
+        fin = np.zeros(n, np.uint8)
+        lat = np.empty((n, LDIM), np.float32)
+        logit = np.empty(n, np.float32)
+        check(_lib.lib().ptts_step_flags(self._h, ticket, _ptr(fin), _ptr(lat), _ptr(logit)))
+        return fin.astype(bool), lat, logit
+
+    def step_pcm(self, ticket: int, want: bool = True):
+        n = self._pending_n.pop(ticket)
+        pcm = np.empty((n, FRAME), np.float32) if want else None
+        check(_lib.lib().ptts_step_pcm(self._h, ticket, _ptr(pcm)))
+        return pcm
+
     def step_device(self, slots: np.ndarray):
         slots = np.ascontiguousarray(slots, dtype=np.int32)
         check(_lib.lib().ptts_step_device(self._h, _ptr(slots), len(slots)))

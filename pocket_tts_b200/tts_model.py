@@ -152,13 +152,22 @@ class TTSModel:
         self._sync_params()
         spec = StreamSpec(np.asarray(tokens, np.int32), max_gen_len, frames_after_eos, self.eos_threshold, self.temp, seed, noise)
         (slot,) = self.engine.open_streams([voice], [spec])
+        ids = np.array([slot], np.int32)
         try:
+            # frame n's codec half overlaps frame n+1's language-model half (ptts_step_begin/flags/pcm)
+            ticket = self.engine.step_begin(ids)
+            fin, _, _ = self.engine.step_flags(ticket)
             while True:
-                pcm, fin, _, _ = self.engine.step(np.array([slot], np.int32))
-                yield pcm.reshape(1, 1, FRAME)
-                if fin[0]:
+                nxt = None
+                if not fin[0]:
+                    nxt = self.engine.step_begin(ids)
+                    fin_next, _, _ = self.engine.step_flags(nxt)
+                yield self.engine.step_pcm(ticket).reshape(1, 1, FRAME)
+                if nxt is None:
                     break
+                ticket, fin = nxt, fin_next
         finally:
+            self.engine.sync()
             self.engine.close_stream(int(slot))
 
     def generate_stream(self, text: str, voice: Voice, seed: int = 0) -> Iterator[np.ndarray]:

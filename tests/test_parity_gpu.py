@@ -190,6 +190,35 @@ def test_temp_zero_is_deterministic_and_device_noise_runs():
     voice.close()
 
 
+def test_pipelined_step_matches_synchronous_step():
+    """begin/flags/pcm with two frames in flight (codec of frame n overlapping the LM of frame n+1) must give
+    bit-identical frames to the synchronous ptts_step."""
+    from pocket_tts_b200.engine import StreamSpec
+    eng, _ = engine_for(1234, 0.01)
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(30, seed=3))
+    specs = [StreamSpec(synth.make_tokens(7 + i, seed=i), 6, 0, 1e30, temp=0.7, seed=i) for i in range(3)]
+    s = eng.open_streams([voice] * 3, specs)
+    ref = [eng.step(s) for _ in range(6)]
+    for x in s:
+        eng.close_stream(int(x))
+    s = eng.open_streams([voice] * 3, specs)
+    got, prev = [], None
+    for f in range(6):
+        t = eng.step_begin(s)
+        fin, lat, logit = eng.step_flags(t)
+        np.testing.assert_array_equal(lat, ref[f][2])
+        assert (fin == ref[f][1]).all()
+        if prev is not None:
+            got.append(eng.step_pcm(prev))
+        prev = t
+    got.append(eng.step_pcm(prev))
+    for f in range(6):
+        np.testing.assert_array_equal(got[f], ref[f][0])
+    for x in s:
+        eng.close_stream(int(x))
+    voice.close()
+
+
 def test_api_errors():
     from pocket_tts_b200._lib import PttsError
     from pocket_tts_b200.engine import StreamSpec
