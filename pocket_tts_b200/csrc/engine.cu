@@ -382,10 +382,14 @@ void Engine::load_weights(const ptts_tensor_desc* w, int nw) {
     PTTS_CUDA(cudaMemcpy(b_ada.p, ba.data(), ba.size() * 4, cudaMemcpyHostToDevice));
   }
   linear(w_final, f + "final_layer.linear.weight", LDIM, FLOW_DIM); vec(b_final, f + "final_layer.linear.bias", LDIM);
-  { const HostTensor& t = T("mimi.quantizer.output_proj.weight", {MIMI_DIM, LDIM, 1}); wq.alloc(t.f32.size());
-    PTTS_CUDA(cudaMemcpy(wq.p, t.f32.data(), t.f32.size() * 4, cudaMemcpyHostToDevice)); }
-  { const HostTensor& t = T("mimi.upsample.convtr.convtr.weight", {MIMI_DIM, 1, 32}); wup.alloc(t.f32.size());
-    PTTS_CUDA(cudaMemcpy(wup.p, t.f32.data(), t.f32.size() * 4, cudaMemcpyHostToDevice)); }
+  auto upload_transposed_512x32 = [&](DevBuf<float>& dst, const HostTensor& t) {  // [512][32] -> [32][512]
+    std::vector<float> tr(32 * 512);
+    for (int c = 0; c < 512; ++c) for (int k = 0; k < 32; ++k) tr[k * 512 + c] = t.f32[c * 32 + k];
+    dst.alloc(tr.size());
+    PTTS_CUDA(cudaMemcpy(dst.p, tr.data(), tr.size() * 4, cudaMemcpyHostToDevice));
+  };
+  upload_transposed_512x32(wq, T("mimi.quantizer.output_proj.weight", {MIMI_DIM, LDIM, 1}));
+  upload_transposed_512x32(wup, T("mimi.upsample.convtr.convtr.weight", {MIMI_DIM, 1, 32}));
   for (int l = 0; l < MIMI_LAYERS; ++l) {
     const std::string p = "mimi.decoder_transformer.transformer.layers." + std::to_string(l) + ".";
     linear(m_inproj[l], p + "self_attn.in_proj.weight", 3 * MIMI_DIM, MIMI_DIM);
@@ -492,6 +496,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_b_done, cudaEventDisableTiming));
   for (auto& e : ev) PTTS_CUDA(cudaEventCreate(&e));
   PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  PTTS_CUDA(cudaFuncSetAttribute(mimi_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATTN_SMEM));
   {
     float inv[HD / 2];
     const float cst = -std::log(10000.f) * 2.f / (float)HD;  // f32 like modules/rope.rs:12-14
@@ -657,13 +662,13 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
       { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
         launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, N_HEADS), 32, 0, ls, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
       if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
-      const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
+      const size_t sm = (size_t)(640 + 1024 + KVCAP) * sizeof(float);
       { ProfScope ps(*this, "prefill.attn");
-        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), 128, sm, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
-      const size_t sm = (size_t)(384 + 1024 + KVCAP) * sizeof(float);
+      const size_t sm = (size_t)(640 + 1024 + KVCAP) * sizeof(float);
       { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0);
-        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), 128, sm, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
     }
     // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue
     e = epi_none();
@@ -754,7 +759,7 @@ void Engine::step_front(int n) {
   // ---- Mimi: de-norm + quantizer + upsample, decoder transformer (reference mimi.rs:143-157, transformer.rs:227-251)
   const int MR = n * MIMI_T;
   { ProfScope ps(*this, "mimi.frontend", (double)n * 16 * 512 * 12, 0);
-    launch_k(use_pdl, mimi_frontend_kernel, n, 512, 0, ls, 1, z32.p, row_seq.p, ctl.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
+    launch_k(use_pdl, mimi_frontend_kernel, dim3(n, 4), 128, 0, ls, 1, z32.p, row_seq.p, ctl.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
                                                quant_dbg.p, mimi_pos.p); }
 }
 
@@ -767,7 +772,7 @@ void Engine::step_part_b(int n, bool marks) {
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
     tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
     { ProfScope ps(*this, "mimi.attn", (double)n * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0);
-      launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), 128, 0, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
+      launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), MATTN_THREADS, MATTN_SMEM, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
     tag("mimi.out_proj"); gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);

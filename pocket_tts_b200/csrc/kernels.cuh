@@ -155,26 +155,29 @@ __device__ __forceinline__ void rope_pair(float xr, float xi, int pos, int i, fl
   o_i = xr * s + xi * c;
 }
 
-// softmax(q K^T / 8) V over keys [k_begin, k_end) of one (sequence, layer, head); q in smem (f32, already
-// rotated); scores in smem.  Reference modules/sdpa.rs:36-82 (naive path), causal handled by the caller's range.
-// Block = 128 threads.  out: 64 floats in smem (red[0..63]).
+// softmax(q K^T / 8) V over keys [0, n_keys) of one (sequence, layer, head); q in smem (f32, already rotated);
+// scores in smem.  Reference modules/sdpa.rs:36-82 (naive path), causality is the caller's key range.
+// Block = ATTN_THREADS (8 warps).  Result: 64 floats at red_s[0..63].
+//   pass 1  one key per thread: its 128-byte row arrives as 8 independent 16-byte loads, dot with q in f32
+//   pass 2  a warp takes 4 keys per iteration (8 lanes x 16 bytes cover one V row), 8 f32 accumulators per lane
+static constexpr int ATTN_THREADS = 256;
 __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int head, int n_heads, const float* q_s,
                                              float* score_s, float* red_s, int n_keys) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // pass 1: one key per thread, full 64-dim dot from a 128-byte row (8 x 16 B loads)
   float lmax = -INFINITY;
-  for (int i = tid; i < n_keys; i += 128) {
+  for (int i = tid; i < n_keys; i += ATTN_THREADS) {
     const uint4* kr = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, head, n_heads, i));
+    uint4 u[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[c] = kr[c];
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      uint4 u = kr[c];
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __half22float2(h[j]);
-        acc += f.x * q_s[c * 8 + 2 * j] + f.y * q_s[c * 8 + 2 * j + 1];
-      }
+      const __half2* h = reinterpret_cast<const __half2*>(&u[c]);
+      const float4 qa = *reinterpret_cast<const float4*>(q_s + c * 8);
+      const float4 qb = *reinterpret_cast<const float4*>(q_s + c * 8 + 4);
+      const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+      acc += f0.x * qa.x + f0.y * qa.y + f1.x * qa.z + f1.y * qa.w + f2.x * qb.x + f2.y * qb.y + f3.x * qb.z + f3.y * qb.w;
     }
     acc *= 0.125f;  // 1/sqrt(64)
     score_s[i] = acc;
@@ -183,10 +186,12 @@ __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int h
   lmax = warp_max(lmax);
   if (lane == 0) red_s[warp] = lmax;
   __syncthreads();
-  const float gmax = fmaxf(fmaxf(red_s[0], red_s[1]), fmaxf(red_s[2], red_s[3]));
+  float gmax = red_s[0];
+#pragma unroll
+  for (int w = 1; w < ATTN_THREADS / 32; ++w) gmax = fmaxf(gmax, red_s[w]);
   __syncthreads();
   float lsum = 0.f;
-  for (int i = tid; i < n_keys; i += 128) {
+  for (int i = tid; i < n_keys; i += ATTN_THREADS) {
     const float p = expf(score_s[i] - gmax);
     score_s[i] = p;
     lsum += p;
@@ -194,27 +199,50 @@ __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int h
   lsum = warp_sum(lsum);
   if (lane == 0) red_s[warp] = lsum;
   __syncthreads();
-  const float inv = 1.f / (red_s[0] + red_s[1] + red_s[2] + red_s[3]);
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < ATTN_THREADS / 32; ++w) tot += red_s[w];
+  const float inv = 1.f / tot;
   __syncthreads();
-  // pass 2: warp w takes keys w, w+4, ...; lane owns dims 2*lane, 2*lane+1 (one coalesced 128-B row per warp)
-  float a0 = 0.f, a1 = 0.f;
-  for (int i = warp; i < n_keys; i += 4) {
-    const __half2 hv = reinterpret_cast<const __half2*>(kv_row(sd, layer, 1, head, n_heads, i))[lane];
-    const float2 f = __half22float2(hv);
-    const float p = score_s[i];
-    a0 += p * f.x;
-    a1 += p * f.y;
+  // pass 2
+  const int sub = lane >> 3, part = lane & 7;  // key within the group of 4, 16-byte slice of the row
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i0 = warp * 4; i0 < n_keys; i0 += ATTN_THREADS / 32 * 4) {
+    const int i = i0 + sub;
+    if (i < n_keys) {
+      const uint4 u = reinterpret_cast<const uint4*>(kv_row(sd, layer, 1, head, n_heads, i))[part];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+      const float p = score_s[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        a[2 * j] += p * f.x;
+        a[2 * j + 1] += p * f.y;
+      }
+    }
   }
-  red_s[warp * 64 + 2 * lane] = a0;
-  red_s[warp * 64 + 2 * lane + 1] = a1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {  // fold the 4 key sub-groups of the warp (fixed order)
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 8);
+    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 16);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red_s[64 + warp * 64 + part * 8 + j] = a[j];
+  }
   __syncthreads();
-  if (tid < 64) red_s[256 + tid] = (red_s[tid] + red_s[64 + tid] + red_s[128 + tid] + red_s[192 + tid]) * inv;
+  if (tid < 64) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < ATTN_THREADS / 32; ++w) o += red_s[64 + w * 64 + tid];
+    red_s[tid] = o * inv;
+  }
   __syncthreads();
 }
 
 // FlowLM decode attention, one new row per stream (reference modules/attention.rs:104-231 with t = 1):
 // RoPE(q,k) at the absolute position, append K,V at the cursor, causal SDPA over prefix + own rows, all fused.
-// grid (n, heads), block 128, dyn smem = (max_keys + 64 + 320) floats.
+// grid (n, heads), block ATTN_THREADS, dyn smem = (640 + max_keys) floats.
 __global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
                                           const SeqDesc* __restrict__ seqs, const int* __restrict__ own_len, int layer,
                                           int n_heads, __half* __restrict__ out16) {
@@ -222,8 +250,8 @@ __global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const i
   pdl_wait();
   extern __shared__ float sm[];
   float* q_s = sm;          // 64
-  float* red_s = sm + 64;   // 320
-  float* score_s = sm + 384;
+  float* red_s = sm + 64;   // 576
+  float* score_s = sm + 640;
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int d_model = n_heads * HD;
   const int seq = row_seq[b];
@@ -245,7 +273,7 @@ __global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const i
   }
   __syncthreads();
   attend_block(sd, layer, h, n_heads, q_s, score_s, red_s, pos + 1);
-  if (tid < 64) out16[static_cast<long long>(b) * d_model + h * HD + tid] = __float2half_rn(red_s[256 + tid]);
+  if (tid < 64) out16[static_cast<long long>(b) * d_model + h * HD + tid] = __float2half_rn(red_s[tid]);
 }
 
 // Prefill, step 1: RoPE + KV append for every new row (rows of several sequences at once); rotated q kept in f32.
@@ -282,7 +310,7 @@ __global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, cons
   extern __shared__ float sm[];
   float* q_s = sm;
   float* red_s = sm + 64;
-  float* score_s = sm + 384;
+  float* score_s = sm + 640;
   const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int d_model = n_heads * HD;
   const SeqDesc sd = seqs[row_seq[r]];
@@ -290,132 +318,180 @@ __global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, cons
   if (tid < 64) q_s[tid] = q_rot[static_cast<long long>(r) * d_model + h * HD + tid];
   __syncthreads();
   attend_block(sd, layer, h, n_heads, q_s, score_s, red_s, pos + 1);
-  if (tid < 64) out16[static_cast<long long>(r) * d_model + h * HD + tid] = __float2half_rn(red_s[256 + tid]);
+  if (tid < 64) out16[static_cast<long long>(r) * d_model + h * HD + tid] = __float2half_rn(red_s[tid]);
 }
 
 // ---------------------------------------------------------------- Mimi front end
 // latent de-norm (tts_model.rs:1033-1035) -> Quantizer 1x1 conv 32->512 (mimi.rs:32-36) -> depthwise
-// ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid n, block 512 (one channel each).
+// ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid (n, 4), block 128: one channel per
+// thread, weights pre-transposed to [k][512] so every access of a warp is contiguous; the 16 partial-sum reads are
+// issued before any store to the same buffer.
 __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __restrict__ row_seq,
-                                     const StreamCtl* __restrict__ ctl, const float* __restrict__ emb_std, const float* __restrict__ emb_mean,
-                                     const float* __restrict__ wq /*[512,32]*/, const float* __restrict__ wup /*[512,32]*/,
-                                     float* __restrict__ partial /*[slots,16,512]*/, float* __restrict__ x /*[n*16,512]*/,
-                                     float* __restrict__ dbg_quant, int* __restrict__ mimi_pos) {
+                                     const StreamCtl* __restrict__ ctl, const float* __restrict__ emb_std,
+                                     const float* __restrict__ emb_mean, const float* __restrict__ wq_t /*[32,512]*/,
+                                     const float* __restrict__ wup_t /*[32,512]*/, float* __restrict__ partial /*[slots,16,512]*/,
+                                     float* __restrict__ x /*[n*16,512]*/, float* __restrict__ dbg_quant,
+                                     int* __restrict__ mimi_pos) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float zd[LDIM];
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c < LDIM) zd[c] = z[b * LDIM + c] * emb_std[c] + emb_mean[c];
+  const int b = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  const int slot = row_seq[b];
+  if (threadIdx.x < LDIM) zd[threadIdx.x] = z[b * LDIM + threadIdx.x] * emb_std[threadIdx.x] + emb_mean[threadIdx.x];
   // runs after step_end of the same frame: the frame counter has already advanced by one
-  if (c == 0) mimi_pos[b] = (ctl[row_seq[b]].frame - 1) * 16;
+  if (c == 0) mimi_pos[b] = (ctl[slot].frame - 1) * 16;
   __syncthreads();
   float qv = 0.f;
 #pragma unroll
-  for (int k = 0; k < LDIM; ++k) qv += wq[c * LDIM + k] * zd[k];
+  for (int k = 0; k < LDIM; ++k) qv += __ldg(wq_t + k * 512 + c) * zd[k];
   if (dbg_quant) dbg_quant[b * 512 + c] = qv;
-  float* part = partial + static_cast<long long>(row_seq[b]) * 16 * 512;
+  float* part = partial + static_cast<long long>(slot) * 16 * 512;
+  float old[16], w0[16], w1[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    const float head = qv * wup[c * 32 + j] + part[j * 512 + c];
-    part[j * 512 + c] = qv * wup[c * 32 + 16 + j];
-    x[(static_cast<long long>(b) * 16 + j) * 512 + c] = head;
+    old[j] = part[j * 512 + c];
+    w0[j] = __ldg(wup_t + j * 512 + c);
+    w1[j] = __ldg(wup_t + (16 + j) * 512 + c);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    x[(static_cast<long long>(b) * 16 + j) * 512 + c] = qv * w0[j] + old[j];
+    part[j * 512 + c] = qv * w1[j];
   }
 }
 
 // Mimi decoder-transformer attention: 16 new rows per stream, sliding window of 250 positions
 // (reference attention.rs:167-264 ring + sdpa.rs:129-171 mask: query at position p sees keys in (p-250, p]).
 // K,V live in a per-slot ring indexed by position % 272; 272 >= 250 + 15 so the 16 rows written first never
-// overwrite a key that a query of this step still needs.  grid (n, 8 heads), block 128.
-__global__ void mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
-                                 const int* __restrict__ mimi_pos, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/,
-                                 int layer, int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
+// overwrite a key that a query of this step still needs.  grid (n, 8 heads), block 256, dynamic smem.
+//   scores  one key per thread (row in registers via 8 x 16-byte loads) against the 16 queries in smem
+//   P V     a warp takes keys w, w+8, ...; each lane owns 2 of the 64 dims for all 16 queries; the 8 warps'
+//           partial sums are folded in warp order (bit-reproducible)
+static constexpr int MATTN_THREADS = 256;
+static constexpr int MATTN_SW = MIMI_RING + 8;
+static constexpr int MATTN_SMEM = (16 * HD + 16 * MATTN_SW + 16 + 8 * 16 * HD) * 4;
+__global__ void __launch_bounds__(MATTN_THREADS)
+mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
+                 const int* __restrict__ mimi_pos, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/, int layer,
+                 int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int NH = 8, DM = 512, T = 16, SW = MIMI_RING + 8;
-  __shared__ float q_s[T][HD];
-  __shared__ float p_s[T][SW];
-  __shared__ float inv_s[T];
+  constexpr int NH = 8, DM = 512, T = 16, SW = MATTN_SW, NW = MATTN_THREADS / 32;
+  extern __shared__ float msm[];
+  float (*q_s)[HD] = reinterpret_cast<float (*)[HD]>(msm);                       // [16][64]
+  float (*p_s)[SW] = reinterpret_cast<float (*)[SW]>(msm + T * HD);              // [16][280]
+  float* inv_s = msm + T * HD + T * SW;                                          // [16]
+  float* red_s = inv_s + 16;                                                     // [8][16][64]
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = row_seq[b];
   const int p0 = mimi_pos[b];  // absolute position of the first new row
   __half* kring = ring + ((static_cast<long long>(slot) * n_layers + layer) * 2 * NH + h) * MIMI_RING * HD;
   __half* vring = kring + static_cast<long long>(NH) * MIMI_RING * HD;
-  // RoPE + ring write: 16 rows x 32 pairs = 512 items over 128 threads
-  for (int it = tid; it < T * 32; it += 128) {
+  // RoPE + ring write: 16 rows x 32 pairs = 512 items
+  for (int it = tid; it < T * 32; it += MATTN_THREADS) {
     const int t = it >> 5, i = it & 31;
     const float* row = qkv + (static_cast<long long>(b) * T + t) * 3 * DM;
+    const float2 qx = *reinterpret_cast<const float2*>(row + h * HD + 2 * i);
+    const float2 kx = *reinterpret_cast<const float2*>(row + DM + h * HD + 2 * i);
+    const float2 vx = *reinterpret_cast<const float2*>(row + 2 * DM + h * HD + 2 * i);
     float qr, qi, kr, ki;
-    rope_pair(row[h * HD + 2 * i], row[h * HD + 2 * i + 1], p0 + t, i, qr, qi);
-    rope_pair(row[DM + h * HD + 2 * i], row[DM + h * HD + 2 * i + 1], p0 + t, i, kr, ki);
+    rope_pair(qx.x, qx.y, p0 + t, i, qr, qi);
+    rope_pair(kx.x, kx.y, p0 + t, i, kr, ki);
     q_s[t][2 * i] = qr;
     q_s[t][2 * i + 1] = qi;
     const int ri = (p0 + t) % MIMI_RING;
     reinterpret_cast<__half2*>(kring + ri * HD)[i] = __floats2half2_rn(kr, ki);
-    reinterpret_cast<__half2*>(vring + ri * HD)[i] =
-        __floats2half2_rn(row[2 * DM + h * HD + 2 * i], row[2 * DM + h * HD + 2 * i + 1]);
+    reinterpret_cast<__half2*>(vring + ri * HD)[i] = __floats2half2_rn(vx.x, vx.y);
   }
   __syncthreads();
-  // keys: positions [kmin, p0+15]; window of the first query starts at p0-249
+  // keys: positions [kmin, p0+15]; the window of the first query starts at p0-249
   const int kmin = max(0, p0 - (MIMI_CTX - 1));
   const int nk = p0 + T - kmin;  // <= 265
-  for (int j = tid; j < nk; j += 128) {
+  for (int j = tid; j < nk; j += MATTN_THREADS) {
     const int kp = kmin + j;
     const uint4* kr = reinterpret_cast<const uint4*>(kring + (kp % MIMI_RING) * HD);
+    uint4 u[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[c] = kr[c];
     float kf[HD];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      uint4 u = kr[c];
-      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+      const __half2* hh = reinterpret_cast<const __half2*>(&u[c]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float2 f = __half22float2(hh[e]);
+        const float2 f = __half22float2(hh[e]);
         kf[c * 8 + 2 * e] = f.x;
         kf[c * 8 + 2 * e + 1] = f.y;
       }
     }
-#pragma unroll 4
+#pragma unroll 2
     for (int t = 0; t < T; ++t) {
       const int qp = p0 + t;
       float acc = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc += kf[d] * q_s[t][d];
+      for (int d = 0; d < HD; d += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&q_s[t][d]);
+        acc += kf[d] * q4.x + kf[d + 1] * q4.y + kf[d + 2] * q4.z + kf[d + 3] * q4.w;
+      }
       const bool ok = (kp <= qp) && (kp > qp - MIMI_CTX);
       p_s[t][j] = ok ? acc * 0.125f : -INFINITY;
     }
   }
   __syncthreads();
-  // softmax per query row: warp w owns rows 4w..4w+3
-  for (int t = warp * 4; t < warp * 4 + 4; ++t) {
+  // softmax per query row: warp w owns rows 2w, 2w+1
+  for (int t = warp * 2; t < warp * 2 + 2; ++t) {
     float m = -INFINITY;
     for (int j = lane; j < nk; j += 32) m = fmaxf(m, p_s[t][j]);
     m = warp_max(m);
-    float s = 0.f;
+    float sacc = 0.f;
     for (int j = lane; j < nk; j += 32) {
       const float p = expf(p_s[t][j] - m);
       p_s[t][j] = p;
-      s += p;
+      sacc += p;
     }
-    s = warp_sum(s);
-    if (lane == 0) inv_s[t] = 1.f / s;
+    sacc = warp_sum(sacc);
+    if (lane == 0) inv_s[t] = 1.f / sacc;
   }
   __syncthreads();
-  // P V: warp w owns rows 4w..4w+3, lane owns dims 2*lane, 2*lane+1
-  float acc[4][2] = {};
-  for (int j = 0; j < nk; ++j) {
-    const int kp = kmin + j;
-    const float2 f = __half22float2(reinterpret_cast<const __half2*>(vring + (kp % MIMI_RING) * HD)[lane]);
+  // P V
+  float acc[T][2];
+#pragma unroll
+  for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = 0.f;
+  for (int j0 = warp; j0 < nk; j0 += NW * 4) {
+    float2 f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // four independent loads in flight
+      const int j = j0 + u * NW;
+      f[u] = (j < nk) ? __half22float2(reinterpret_cast<const __half2*>(vring + ((kmin + j) % MIMI_RING) * HD)[lane])
+                      : make_float2(0.f, 0.f);
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float p = p_s[warp * 4 + u][j];
-      acc[u][0] += p * f.x;
-      acc[u][1] += p * f.y;
+      const int j = j0 + u * NW;
+      if (j < nk) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const float p = p_s[t][j];
+          acc[t][0] += p * f[u].x;
+          acc[t][1] += p * f[u].y;
+        }
+      }
     }
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int t = warp * 4 + u;
-    reinterpret_cast<__half2*>(out16 + (static_cast<long long>(b) * T + t) * DM + h * HD)[lane] =
-        __floats2half2_rn(acc[u][0] * inv_s[t], acc[u][1] * inv_s[t]);
+  for (int t = 0; t < T; ++t) *reinterpret_cast<float2*>(red_s + (warp * T + t) * HD + 2 * lane) = make_float2(acc[t][0], acc[t][1]);
+  __syncthreads();
+  for (int o = tid; o < T * 32; o += MATTN_THREADS) {
+    const int t = o >> 5, i = o & 31;
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float2 v = *reinterpret_cast<const float2*>(red_s + (w * T + t) * HD + 2 * i);
+      sx += v.x;
+      sy += v.y;
+    }
+    reinterpret_cast<__half2*>(out16 + (static_cast<long long>(b) * T + t) * DM + h * HD)[i] =
+        __floats2half2_rn(sx * inv_s[t], sy * inv_s[t]);
   }
 }
 
