@@ -496,6 +496,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_b_done, cudaEventDisableTiming));
   for (auto& e : ev) PTTS_CUDA(cudaEventCreate(&e));
   PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   PTTS_CUDA(cudaFuncSetAttribute(mimi_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATTN_SMEM));
   {
     float inv[HD / 2];
@@ -574,6 +575,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   bool swap = plain && rows <= 256 && force != 1;
   if (plain && !swap) { R = 128; G = 1; }
   dim3 grid;
+  bool persistent = false;
   if (swap) {
     p.swap = 1;
     p.BN = std::max(16, round_up((int)rows, 16));
@@ -584,12 +586,21 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     PTTS_REQUIRE(R > 0 && G > 0 && R * G <= 128, PTTS_ERR_INVALID, "gemm: bad tile geometry R %d G %d", R, G);
     p.n_streams = n_streams; p.T = T; p.R = R; p.G = G;
     const int act_tiles = ((T + R - 1) / R) * ((n_streams + G - 1) / G);
+    p.n_act_tiles = act_tiles;
     const int fcap = round_up(F, 16);
-    int bn = std::min(256, fcap);
-    while (bn > 64 && (long long)act_tiles * ((F + bn - 1) / bn) < 148) bn >>= 1;
-    bn = std::min(round_up(bn, 16), fcap);
+    int bn;
+    if (act_tiles >= 148 && cfg.reserved[3] != 1) {
+      // enough activation tiles to give every SM several: persistent kernel, accumulator double-buffered in TMEM
+      bn = std::min(128, fcap);
+      persistent = true;
+    } else {
+      bn = std::min(256, fcap);
+      while (bn > 64 && (long long)act_tiles * ((F + bn - 1) / bn) < 148) bn >>= 1;
+      bn = std::min(round_up(bn, 16), fcap);
+    }
     p.BN = bn;
     grid = dim3(act_tiles, (F + bn - 1) / bn, 1);
+    if (persistent) grid.x = std::min(act_tiles, std::max(1, 148 / (int)grid.y));
   }
   // Split-K whenever the output tiles alone cannot fill the chip (decode batches: 64 rows x F features is only
   // F/128 tiles): a cluster of `splits` CTAs along z shares one output tile (gemm.cuh), at most 8 (portable size).
@@ -597,25 +608,33 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   int splits = 1;
   {
     const int tiles = grid.x * grid.y;
-    if (tiles < 96 && total_kb >= 4) splits = std::max(1, std::min(std::min(148 / tiles, total_kb / 2), GEMM_MAX_SPLIT));
-    if (cfg.reserved[2] > 0) splits = std::min(cfg.reserved[2], std::min(total_kb, GEMM_MAX_SPLIT));  // test hook
+    if (!persistent && tiles < 96 && total_kb >= 4) splits = std::max(1, std::min(std::min(148 / tiles, total_kb / 2), GEMM_MAX_SPLIT));
+    if (cfg.reserved[2] > 0 && !persistent) splits = std::min(cfg.reserved[2], std::min(total_kb, GEMM_MAX_SPLIT));  // test hook
   }
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.epi_mask = epi_mask_of(p.epi);
   grid.z = splits;
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
-  p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));
-  p.tmem_cols = pow2_at_least(p.BN);
+  const size_t tile_bytes = swap ? (size_t)p.BN * (GEMM_BM + 4) * 4 : (size_t)GEMM_BM * (p.BN + 4) * 4;
+  size_t smem;
+  if (persistent) {
+    // stages | staging tile | barriers; the pipeline may run a whole tile ahead of the epilogue
+    p.stages = std::max(2, std::min(8, (int)((200 * 1024 - tile_bytes) / stage_bytes)));
+    p.tmem_cols = pow2_at_least(2 * p.BN);
+    smem = (size_t)p.stages * stage_bytes + tile_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
+  } else {
+    p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));
+    p.tmem_cols = pow2_at_least(p.BN);
+    // the epilogue re-uses the stage buffers for its staged f32 tile
+    while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;
+    smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
+  }
   auto map_ok = [](const void* ptr, const RowMap& m) {
     return !ptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && m.ld % 4 == 0 && m.base % 4 == 0 && m.stream_stride % 4 == 0);
   };
   p.vec4 = (F % 4 == 0) && map_ok(epi.gate, epi.gate_map) && map_ok(epi.res, epi.res_map) && map_ok(epi.out32, epi.out32_map) &&
            map_ok(epi.out16, epi.out16_map) && map_ok(epi.bias, plain_map(4)) && map_ok(epi.fscale, plain_map(4));
-  // the epilogue re-uses the stage buffers for its [128][BN+1] f32 tile
-  const size_t tile_bytes = swap ? (size_t)p.BN * (GEMM_BM + 4) * 4 : (size_t)GEMM_BM * (p.BN + 4) * 4;
-  while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;
-  const size_t smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
 
   // algorithmic traffic: weights once, the distinct activation rows once, every epilogue tensor once
   const double act_rows = (double)n_streams * (T + taps - 1);
@@ -629,7 +648,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     const CUtensorMap& ma = swap ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
                                  : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
     const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
-    launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);
+    if (persistent) launch_k(use_pdl, gemm_tc_persistent_kernel, grid, GEMM_THREADS, smem, ls, 1, ma, mw, p);
+    else launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);
   }
   PTTS_CUDA(cudaGetLastError());
 }
@@ -662,11 +682,11 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
       { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
         launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, N_HEADS), 32, 0, ls, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
       if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
-      const size_t sm = (size_t)(640 + 1024 + KVCAP) * sizeof(float);
+      const size_t sm = 0;
       { ProfScope ps(*this, "prefill.attn");
         launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
-      const size_t sm = (size_t)(640 + 1024 + KVCAP) * sizeof(float);
+      const size_t sm = 0;
       { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0);
         launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
     }
@@ -1338,6 +1358,7 @@ struct TestCtx {
     PTTS_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
     e.ls = e.stream;
     PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
 };
 

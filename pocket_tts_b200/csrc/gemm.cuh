@@ -72,6 +72,7 @@ struct GemmParams {
   int tmem_cols;
   int vec4;                 // every epilogue tensor is 16-byte addressable in groups of 4 features
   int epi_mask;             // epi_mask_of(epi): selects the compiled store loop
+  int n_act_tiles;          // activation tiles in total (persistent kernel walks them with stride gridDim.x)
   GemmEpi epi;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
@@ -267,6 +268,21 @@ __device__ __noinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_
   }
 }
 
+__device__ __forceinline__ void epi_dispatch(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0, int tid,
+                                             int nthreads, int rank, int nsplit) {
+  if (!p.vec4) {
+    epi_store_tile<1, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit);
+    return;
+  }
+  switch (p.epi_mask) {
+#define PTTS_EPI_CASE(MASK) \
+  case (MASK): epi_store_tile<4, (MASK)>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit); break;
+    PTTS_EPI_SHAPES(PTTS_EPI_CASE)
+#undef PTTS_EPI_CASE
+    default: epi_store_tile<4, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit); break;
+  }
+}
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w,
                const GemmParams p) {
@@ -406,25 +422,141 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (nsplit > 1) cluster_sync_all();  // all partial tiles are staged and visible cluster-wide
-  {
-    const uint32_t stile_addr = smem_u32(smem);
-    const int LD = (p.swap ? GEMM_BM : p.BN) + 4;
-    if (!p.vec4) {
-      epi_store_tile<1, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
-    } else {
-      switch (p.epi_mask) {
-#define PTTS_EPI_CASE(MASK) \
-  case (MASK): epi_store_tile<4, (MASK)>(p, stile_addr, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit); break;
-        PTTS_EPI_SHAPES(PTTS_EPI_CASE)
-#undef PTTS_EPI_CASE
-        default: epi_store_tile<4, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit); break;
-      }
-    }
-  }
+  epi_dispatch(p, smem_u32(smem), (p.swap ? GEMM_BM : p.BN) + 4, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
   if (warp == 2) PTTS_TRACE(8);
   if (nsplit > 1) cluster_sync_all();  // peers may still be reading this CTA's tile
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
   if (warp == 1) PTTS_TRACE(9);
+}
+
+
+// Persistent form for streaming GEMMs with hundreds of activation tiles and few features (the wide end of SEANet:
+// 1920 rows per stream, 64 channels).  One CTA per SM walks activation tiles with stride gridDim.x; the TMA/MMA
+// pipeline runs ahead across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of
+// tile j (10 warps: 4 TMEM readers stage the tile in shared memory, all 10 store it) overlaps the MMAs of tile j+1,
+// and barrier setup / TMEM allocation are paid once per SM instead of once per tile.  Activations on MMA-M only.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w,
+                          const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_tile_bytes = p.BN * GEMM_BK * 2;
+  const int m_tile_bytes = GEMM_BM * GEMM_BK * 2;
+  const int stage_bytes = m_tile_bytes + n_tile_bytes;
+  const int LD = p.BN + 4;
+  float* stile = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stile) + GEMM_BM * LD * 4);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int tiles_t = (p.T + p.R - 1) / p.R;
+  const int f0 = blockIdx.y * p.BN;
+  const int nkb = p.taps * p.cblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_act);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + a, 1);
+      mbar_init(tempty_bar + a, 4);  // one arrival per TMEM-reader warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t bytes = GEMM_BK * p.R * p.G * 2 + n_tile_bytes;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x) {
+        const int tb = tile / tiles_t;
+        const int b0 = tb * p.G, t0 = (tile - tb * tiles_t) * p.R;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(empty_bar + s, ((it / p.stages) & 1) ^ 1);
+          const int tap = kb / p.cblocks;
+          const int c0 = (kb - tap * p.cblocks) * GEMM_BK;
+          uint8_t* m_tile = smem + s * stage_bytes;
+          mbar_arrive_expect_tx(full_bar + s, bytes);
+          tma_load_3d(m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
+          tma_load_3d(m_tile + m_tile_bytes, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_f16_m128(p.BN);
+    int it = 0, j = 0;
+    for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x, ++j) {
+      const int as = j & 1;
+      mbar_wait(tempty_bar + as, ((j >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % p.stages;
+        mbar_wait(full_bar + s, (it / p.stages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t m_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t da = make_sw128_kmajor_desc(m_addr);
+          const uint64_t db = make_sw128_kmajor_desc(m_addr + m_tile_bytes);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(tmem_base + as * p.BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty_bar + s);
+          if (kb == nkb - 1) umma_commit(tfull_bar + as);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int etid = threadIdx.x - 64;  // 0..319
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x, ++j) {
+      const int as = j & 1;
+      const int tb = tile / tiles_t;
+      const int b0 = tb * p.G, t0 = (tile - tb * tiles_t) * p.R;
+      if (warp < 6) {
+        mbar_wait(tfull_bar + as, (j >> 1) & 1);
+        tc_fence_after();
+        const int quad = warp & 3;
+        const int i = quad * 32 + lane;
+        for (int c = 0; c < p.BN; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * p.BN + c, v);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(stile + i * LD + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + as);  // TMEM buffer free: the MMAs of tile j+2 may start
+      }
+      asm volatile("bar.sync 1, 320;" ::: "memory");  // tile staged
+      epi_dispatch(p, smem_u32(stile), LD, f0, t0, b0, etid, GEMM_THREADS - 64, 0, 1);
+      asm volatile("bar.sync 1, 320;" ::: "memory");  // staging buffer free
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // SIMT cross-check of the same contract (tests only; selected by ptts_engine_cfg.debug_gemm or

@@ -155,103 +155,106 @@ __device__ __forceinline__ void rope_pair(float xr, float xi, int pos, int i, fl
   o_i = xr * s + xi * c;
 }
 
-// softmax(q K^T / 8) V over keys [0, n_keys) of one (sequence, layer, head); q in smem (f32, already rotated);
-// scores in smem.  Reference modules/sdpa.rs:36-82 (naive path), causality is the caller's key range.
-// Block = ATTN_THREADS (8 warps).  Result: 64 floats at red_s[0..63].
-//   pass 1  one key per thread: its 128-byte row arrives as 8 independent 16-byte loads, dot with q in f32
-//   pass 2  a warp takes 4 keys per iteration (8 lanes x 16 bytes cover one V row), 8 f32 accumulators per lane
-static constexpr int ATTN_THREADS = 256;
+// softmax(q K^T / 8) V over keys [0, n_keys) of one (sequence, layer, head), single pass with a running maximum
+// (the naive reference path, modules/sdpa.rs:36-82, up to f32 rounding; causality is the caller's key range).
+// Block = ATTN_THREADS (4 warps).  Eight lanes share one key: each loads 16 bytes of the K row and 16 bytes of the
+// V row, the partial dots are folded with three shuffles, so a warp streams 4 keys x 256 bytes per iteration with
+// both rows in flight and ~40 registers per thread (many CTAs per SM keep the memory pipe full).
+// q in smem (f32, already rotated).  Result: 64 floats at red_s[0..63].  red_s needs 64 + 4*66 floats.
+static constexpr int ATTN_THREADS = 128;
 __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int head, int n_heads, const float* q_s,
-                                             float* score_s, float* red_s, int n_keys) {
+                                             float* red_s, int n_keys) {
+  constexpr int NW = ATTN_THREADS / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float lmax = -INFINITY;
-  for (int i = tid; i < n_keys; i += ATTN_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, head, n_heads, i));
-    uint4 u[8];
+  const int sub = lane >> 3, part = lane & 7;
+  float q[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) u[c] = kr[c];
-    float acc = 0.f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const __half2* h = reinterpret_cast<const __half2*>(&u[c]);
-      const float4 qa = *reinterpret_cast<const float4*>(q_s + c * 8);
-      const float4 qb = *reinterpret_cast<const float4*>(q_s + c * 8 + 4);
-      const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
-      acc += f0.x * qa.x + f0.y * qa.y + f1.x * qa.z + f1.y * qa.w + f2.x * qb.x + f2.y * qb.y + f3.x * qb.z + f3.y * qb.w;
-    }
-    acc *= 0.125f;  // 1/sqrt(64)
-    score_s[i] = acc;
-    lmax = fmaxf(lmax, acc);
-  }
-  lmax = warp_max(lmax);
-  if (lane == 0) red_s[warp] = lmax;
-  __syncthreads();
-  float gmax = red_s[0];
-#pragma unroll
-  for (int w = 1; w < ATTN_THREADS / 32; ++w) gmax = fmaxf(gmax, red_s[w]);
-  __syncthreads();
-  float lsum = 0.f;
-  for (int i = tid; i < n_keys; i += ATTN_THREADS) {
-    const float p = expf(score_s[i] - gmax);
-    score_s[i] = p;
-    lsum += p;
-  }
-  lsum = warp_sum(lsum);
-  if (lane == 0) red_s[warp] = lsum;
-  __syncthreads();
-  float tot = 0.f;
-#pragma unroll
-  for (int w = 0; w < ATTN_THREADS / 32; ++w) tot += red_s[w];
-  const float inv = 1.f / tot;
-  __syncthreads();
-  // pass 2
-  const int sub = lane >> 3, part = lane & 7;  // key within the group of 4, 16-byte slice of the row
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i0 = warp * 4; i0 < n_keys; i0 += ATTN_THREADS / 32 * 4) {
+  for (int j = 0; j < 8; ++j) q[j] = q_s[part * 8 + j] * 0.125f;  // 1/sqrt(64) folded into q
+  float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i0 = warp * 4; i0 < n_keys; i0 += NW * 4) {
     const int i = i0 + sub;
-    if (i < n_keys) {
-      const uint4 u = reinterpret_cast<const uint4*>(kv_row(sd, layer, 1, head, n_heads, i))[part];
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-      const float p = score_s[i];
+    const bool valid = i < n_keys;
+    uint4 ku = make_uint4(0, 0, 0, 0), vu = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      ku = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, head, n_heads, i))[part];
+      vu = reinterpret_cast<const uint4*>(kv_row(sd, layer, 1, head, n_heads, i))[part];
+    }
+    const __half2* kh = reinterpret_cast<const __half2*>(&ku);
+    float sc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(kh[j]);
+      sc += f.x * q[2 * j] + f.y * q[2 * j + 1];
+    }
+    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+    if (valid) {
+      const float m_new = fmaxf(m, sc);
+      const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
+      const float p = expf(sc - m_new);
+      l = l * corr + p;
+      const __half2* vh = reinterpret_cast<const __half2*>(&vu);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        a[2 * j] += p * f.x;
-        a[2 * j + 1] += p * f.y;
+        const float2 f = __half22float2(vh[j]);
+        acc[2 * j] = acc[2 * j] * corr + p * f.x;
+        acc[2 * j + 1] = acc[2 * j + 1] * corr + p * f.y;
       }
+      m = m_new;
     }
   }
+  // fold the 4 key sub-groups of the warp, then the 4 warps, always in the same order
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {  // fold the 4 key sub-groups of the warp (fixed order)
-    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 8);
-    a[j] += __shfl_xor_sync(0xffffffffu, a[j], 16);
+  for (int x = 8; x <= 16; x <<= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m, x);
+    const float l_o = __shfl_xor_sync(0xffffffffu, l, x);
+    const float m_new = fmaxf(m, m_o);
+    const float ca = (m == -INFINITY) ? 0.f : expf(m - m_new);
+    const float cb = (m_o == -INFINITY) ? 0.f : expf(m_o - m_new);
+    l = l * ca + l_o * cb;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a_o = __shfl_xor_sync(0xffffffffu, acc[j], x);
+      acc[j] = acc[j] * ca + a_o * cb;
+    }
+    m = m_new;
   }
+  float* wsm = red_s + 64 + warp * 66;
   if (sub == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red_s[64 + warp * 64 + part * 8 + j] = a[j];
+    for (int j = 0; j < 8; ++j) wsm[part * 8 + j] = acc[j];
+    if (part == 0) { wsm[64] = m; wsm[65] = l; }
   }
   __syncthreads();
   if (tid < 64) {
-    float o = 0.f;
+    float gm = -INFINITY;
 #pragma unroll
-    for (int w = 0; w < ATTN_THREADS / 32; ++w) o += red_s[64 + w * 64 + tid];
-    red_s[tid] = o * inv;
+    for (int w = 0; w < NW; ++w) gm = fmaxf(gm, red_s[64 + w * 66 + 64]);
+    float o = 0.f, lt = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float mw = red_s[64 + w * 66 + 64];
+      const float c = (mw == -INFINITY) ? 0.f : expf(mw - gm);
+      o += red_s[64 + w * 66 + tid] * c;
+      lt += red_s[64 + w * 66 + 65] * c;
+    }
+    red_s[tid] = o / lt;
   }
   __syncthreads();
 }
 
 // FlowLM decode attention, one new row per stream (reference modules/attention.rs:104-231 with t = 1):
 // RoPE(q,k) at the absolute position, append K,V at the cursor, causal SDPA over prefix + own rows, all fused.
-// grid (n, heads), block ATTN_THREADS, dyn smem = (640 + max_keys) floats.
+// grid (n, heads), block ATTN_THREADS.
 __global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
                                           const SeqDesc* __restrict__ seqs, const int* __restrict__ own_len, int layer,
                                           int n_heads, __half* __restrict__ out16) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];
-  float* q_s = sm;          // 64
-  float* red_s = sm + 64;   // 576
-  float* score_s = sm + 640;
+  __shared__ float sm[64 + 64 + 4 * 66];
+  float* q_s = sm;
+  float* red_s = sm + 64;
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int d_model = n_heads * HD;
   const int seq = row_seq[b];
@@ -272,7 +275,7 @@ __global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const i
         __floats2half2_rn(row[2 * d_model + h * HD + 2 * tid], row[2 * d_model + h * HD + 2 * tid + 1]);
   }
   __syncthreads();
-  attend_block(sd, layer, h, n_heads, q_s, score_s, red_s, pos + 1);
+  attend_block(sd, layer, h, n_heads, q_s, red_s, pos + 1);
   if (tid < 64) out16[static_cast<long long>(b) * d_model + h * HD + tid] = __float2half_rn(red_s[tid]);
 }
 
@@ -307,17 +310,16 @@ __global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, cons
                                            int n_heads, __half* __restrict__ out16) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sm[];
+  __shared__ float sm[64 + 64 + 4 * 66];
   float* q_s = sm;
   float* red_s = sm + 64;
-  float* score_s = sm + 640;
   const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int d_model = n_heads * HD;
   const SeqDesc sd = seqs[row_seq[r]];
   const int pos = row_pos[r];
   if (tid < 64) q_s[tid] = q_rot[static_cast<long long>(r) * d_model + h * HD + tid];
   __syncthreads();
-  attend_block(sd, layer, h, n_heads, q_s, score_s, red_s, pos + 1);
+  attend_block(sd, layer, h, n_heads, q_s, red_s, pos + 1);
   if (tid < 64) out16[static_cast<long long>(r) * d_model + h * HD + tid] = __float2half_rn(red_s[tid]);
 }
 

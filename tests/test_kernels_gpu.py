@@ -34,6 +34,8 @@ GEMM_CASES = [
     (300, 640, 512, 1, 1, 0),       # ragged rows and features, activation-as-M
     (1000, 72, 64, 1, 1, 0),        # tiny K, odd feature count
     (64, 32, 512, 0, 1, 0),         # flow final linear (32 features)
+    (30720, 256, 256, 1, 1, 0),     # SEANet convtr8 shape: persistent kernel, two feature tiles
+    (20000, 64, 64, 1, 1, 2),       # SEANet res9b shape: persistent kernel, ragged last tile, single K block
 ]
 
 
@@ -51,7 +53,8 @@ def test_gemm(rows, feats, k, mode, split, act, simt):
     assert err < 2e-3, f"max abs err {err}"
 
 
-CONV_CASES = [(3, 16, 512, 512, 7), (2, 96, 256, 128, 3), (2, 480, 128, 64, 3), (1, 1920, 64, 64, 3), (9, 16, 512, 64, 7)]
+CONV_CASES = [(3, 16, 512, 512, 7), (2, 96, 256, 128, 3), (2, 480, 128, 64, 3), (1, 1920, 64, 64, 3), (9, 16, 512, 64, 7),
+              (12, 1920, 64, 64, 3), (40, 480, 128, 64, 3)]  # the last two run the persistent kernel
 
 
 @pytest.mark.parametrize("n,t,cin,cout,k", CONV_CASES)
@@ -69,7 +72,7 @@ def test_streaming_conv1d(n, t, cin, cout, k):
     assert err < 2e-3, f"max abs err {err}"
 
 
-CONVTR_CASES = [(3, 16, 512, 256, 6), (2, 96, 256, 128, 5), (2, 480, 128, 64, 4), (9, 16, 512, 256, 6)]
+CONVTR_CASES = [(3, 16, 512, 256, 6), (2, 96, 256, 128, 5), (2, 480, 128, 64, 4), (9, 16, 512, 256, 6), (40, 480, 128, 64, 4)]
 
 
 @pytest.mark.parametrize("n,t,cin,cout,s", CONVTR_CASES)
