@@ -106,6 +106,15 @@ __device__ __forceinline__ long long row_off(const RowMap& m, int r) {
   return static_cast<long long>(b) * m.stream_stride + m.base + static_cast<long long>(r - b * m.T) * m.ld;
 }
 
+// Same offset when the row's (stream, row-in-stream) pair is already known: no division for a map that follows
+// the GEMM's own stream structure.
+__device__ __forceinline__ long long row_off_bt(const RowMap& m, int r, int b, int t, int T) {
+  if (m.T == T) return static_cast<long long>(b) * m.stream_stride + m.base + static_cast<long long>(t) * m.ld;
+  return row_off(m, r);
+}
+// ELU for a value that is about to be rounded to f16: exp(x) - 1 with the fast exponential (absolute error ~1e-7).
+__device__ __forceinline__ float elu1_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+
 __device__ __forceinline__ float epi_act(int act, float v) {
   if (act == ACT_GELU) return gelu_tanh(v);
   if (act == ACT_SILU) return silu(v);
@@ -186,23 +195,29 @@ __device__ __noinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_
   uint32_t peer[GEMM_MAX_SPLIT];
 #pragma unroll
   for (int k = 0; k < GEMM_MAX_SPLIT; ++k) peer[k] = (nsplit > 1 && k < nsplit) ? map_to_rank(stile_addr, k) : stile_addr;
-  for (int row = rank * nwarps + warp; row < tile_rows; row += nwarps * nsplit) {
-    int r;
+  // a narrow tile (fv < 32 feature groups) puts several rows in one warp iteration so no lane idles
+  const int lanes_per_row = fv < 32 ? fv : 32;          // fv is a multiple of 4 and <= 64
+  const int rows_per_iter = 32 / lanes_per_row;
+  const int my_sub = lane / lanes_per_row, my_q0 = lane - my_sub * lanes_per_row;
+  for (int row0 = (rank * nwarps + warp) * rows_per_iter; row0 < tile_rows; row0 += nwarps * nsplit * rows_per_iter) {
+    const int row = row0 + my_sub;
+    if (row >= tile_rows || my_sub >= rows_per_iter) continue;
+    int r, b, t;
     if (swap) {
-      r = t0 + row;
-      if (r >= T) break;
+      r = t0 + row; b = 0; t = r;
+      if (r >= T) continue;
     } else {
-      const int g = row / R;
-      const int tt = row - g * R;
-      const int b = b0 + g, t = t0 + tt;
-      if (g >= G || b >= n_streams || t >= T) continue;
+      int g = 0, tt = row;
+      if (G > 1) { g = row / R; tt = row - g * R; }
+      b = b0 + g; t = t0 + tt;
+      if (g >= G || tt >= R || b >= n_streams || t >= T) continue;
       r = b * T + t;
     }
-    const float* gate_r = has_gate ? e.gate + row_off(e.gate_map, r) : nullptr;
-    const float* res_r = has_res ? e.res + row_off(e.res_map, r) : nullptr;
-    float* o32_r = has_o32 ? e.out32 + row_off(e.out32_map, r) : nullptr;
-    __half* o16_r = has_o16 ? e.out16 + row_off(e.out16_map, r) : nullptr;
-    for (int q = lane; q < fv; q += 32) {
+    const float* gate_r = has_gate ? e.gate + row_off_bt(e.gate_map, r, b, t, T) : nullptr;
+    const float* res_r = has_res ? e.res + row_off_bt(e.res_map, r, b, t, T) : nullptr;
+    float* o32_r = has_o32 ? e.out32 + row_off_bt(e.out32_map, r, b, t, T) : nullptr;
+    __half* o16_r = has_o16 ? e.out16 + row_off_bt(e.out16_map, r, b, t, T) : nullptr;
+    for (int q = my_q0; q < fv; q += lanes_per_row) {
       const int f = f0 + q * V;
       if (f >= F) break;
       const uint32_t toff = static_cast<uint32_t>(row * LD + q * V) * 4u;
@@ -252,7 +267,7 @@ __device__ __noinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_
       if (has_o16) {
         if (elu16) {
 #pragma unroll
-          for (int c = 0; c < V; ++c) v[c] = elu1(v[c]);
+          for (int c = 0; c < V; ++c) v[c] = elu1_fast(v[c]);
         }
         if (V == 4) {
           const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
