@@ -594,8 +594,9 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
       bn = std::min(128, fcap);
       persistent = true;
     } else {
+      // largest tile that still leaves at least ~half the SMs busy: one wave of fat tiles beats two of thin ones
       bn = std::min(256, fcap);
-      while (bn > 64 && (long long)act_tiles * ((F + bn - 1) / bn) < 148) bn >>= 1;
+      while (bn > 64 && (long long)act_tiles * ((F + bn - 1) / bn) < 74) bn >>= 1;
       bn = std::min(round_up(bn, 16), fcap);
     }
     p.BN = bn;
@@ -608,7 +609,11 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   int splits = 1;
   {
     const int tiles = grid.x * grid.y;
-    if (!persistent && tiles < 96 && total_kb >= 4) splits = std::max(1, std::min(std::min(148 / tiles, total_kb / 2), GEMM_MAX_SPLIT));
+    // power-of-two cluster sizes only (they pack into a GPC), and the whole grid must fit one wave with slack for
+    // cluster placement: 24 tiles x 4 (96 CTAs) beats 24 x 6 (144 CTAs, measured 8.5 vs 15 us)
+    if (!persistent && total_kb >= 4) {
+      while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= 132 && splits * 2 <= total_kb / 2) splits *= 2;
+    }
     if (cfg.reserved[2] > 0 && !persistent) splits = std::min(cfg.reserved[2], std::min(total_kb, GEMM_MAX_SPLIT));  // test hook
   }
   p.kb_per_split = (total_kb + splits - 1) / splits;
