@@ -620,16 +620,18 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.epi_mask = epi_mask_of(p.epi);
   grid.z = splits;
+  // ~104 KB per CTA: two GEMM CTAs (possibly of different kernels / streams) share an SM and hide each other's latency
+  const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : 104) * 1024LL;
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
   const size_t tile_bytes = swap ? (size_t)p.BN * (GEMM_BM + 4) * 4 : (size_t)GEMM_BM * (p.BN + 4) * 4;
   size_t smem;
   if (persistent) {
     // stages | staging tile | barriers; the pipeline may run a whole tile ahead of the epilogue
-    p.stages = std::max(2, std::min(8, (int)((200 * 1024 - tile_bytes) / stage_bytes)));
+    p.stages = std::max(2, std::min(8, (int)((kSmemBudget - (long long)tile_bytes) / stage_bytes)));
     p.tmem_cols = pow2_at_least(2 * p.BN);
     smem = (size_t)p.stages * stage_bytes + tile_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
   } else {
-    p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (200 * 1024) / stage_bytes));
+    p.stages = std::max(2, std::min(std::min(8, p.kb_per_split + 1), (int)(kSmemBudget / stage_bytes)));
     p.tmem_cols = pow2_at_least(p.BN);
     // the epilogue re-uses the stage buffers for its staged f32 tile
     while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;

@@ -24,7 +24,7 @@
 // work is spread over the whole cluster.
 //
 // Warp roles: warp 0 TMA producer, warp 1 TMEM owner + tcgen05.mma issuer, warps 2-5 TMEM -> smem staging,
-// then all 12 warps store the tile.  Launched with programmatic dependent launch: everything before
+// then all 8 warps store the tile.  Launched with programmatic dependent launch: everything before
 // griddepcontrol.wait (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail.
 #pragma once
 #include "ptx.cuh"
@@ -95,7 +95,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;
-static constexpr int GEMM_THREADS = 384;
+static constexpr int GEMM_THREADS = 256;  // 8 warps; two CTAs fit one SM (registers, ~100 KB smem each) so kernels of the two step streams interleave
 static constexpr int GEMM_MAX_SPLIT = 8;  // portable cluster size
 
 // Row part of a RowMap offset (everything except "+ f"); no integer division when the map is a plain
@@ -298,7 +298,7 @@ __device__ __forceinline__ void epi_dispatch(const GemmParams& p, uint32_t stile
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w,
                const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -448,9 +448,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
 // Persistent form for streaming GEMMs with hundreds of activation tiles and few features (the wide end of SEANet:
 // 1920 rows per stream, 64 channels).  One CTA per SM walks activation tiles with stride gridDim.x; the TMA/MMA
 // pipeline runs ahead across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of
-// tile j (10 warps: 4 TMEM readers stage the tile in shared memory, all 10 store it) overlaps the MMAs of tile j+1,
+// tile j (6 warps: 4 TMEM readers stage the tile in shared memory, all 6 store it) overlaps the MMAs of tile j+1,
 // and barrier setup / TMEM allocation are paid once per SM instead of once per tile.  Activations on MMA-M only.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w,
                           const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -539,7 +539,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
       }
     }
   } else {
-    const int etid = threadIdx.x - 64;  // 0..319
+    const int etid = threadIdx.x - 64;
     int j = 0;
     for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x, ++j) {
       const int as = j & 1;
@@ -564,9 +564,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + as);  // TMEM buffer free: the MMAs of tile j+2 may start
       }
-      asm volatile("bar.sync 1, 320;" ::: "memory");  // tile staged
+      asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // tile staged
       epi_dispatch(p, smem_u32(stile), LD, f0, t0, b0, etid, GEMM_THREADS - 64, 0, 1);
-      asm volatile("bar.sync 1, 320;" ::: "memory");  // staging buffer free
+      asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // staging buffer free
     }
   }
   tc_fence_before();
