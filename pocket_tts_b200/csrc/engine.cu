@@ -620,8 +620,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.epi_mask = epi_mask_of(p.epi);
   grid.z = splits;
-  // ~104 KB per CTA: two GEMM CTAs (possibly of different kernels / streams) share an SM and hide each other's latency
-  const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : 104) * 1024LL;
+  const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : 200) * 1024LL;  // one CTA per SM
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
   const size_t tile_bytes = swap ? (size_t)p.BN * (GEMM_BM + 4) * 4 : (size_t)GEMM_BM * (p.BN + 4) * 4;
   size_t smem;
