@@ -154,6 +154,8 @@ void* ptts_cuda_stream(ptts_engine* e);
  * "<class> <launches> <total_ms> <algorithmic_bytes> <algorithmic_flops>".  Returns the string length. */
 int32_t ptts_profile_enable(ptts_engine* e, int32_t on);
 int64_t ptts_profile_report(ptts_engine* e, char* buf, int64_t cap);
+/* Event time (ms) of an empty kernel bracketed the same way: the fixed cost inside every per-launch figure. */
+int32_t ptts_profile_overhead(ptts_engine* e, float* ms_out);
 
 /* Isolated kernel entry points (tests/test_kernels_gpu.py): D[r,f] = sum_k A[r,k] * W[f,k] on
  * host f32 buffers, run through the production GEMM (operands converted to f16).  mode 0 lets the

@@ -59,6 +59,7 @@ struct GemmEpi {
   int act16;            // applied to the f16 copy only (ELU in front of the next SEANet conv)
   float alpha;          // multiplies after the activation
   int reserved;
+  const float* wscale;  // [F] int8 mode: weight-code scale applied to the accumulator first, else null
 };
 
 struct GemmParams {
@@ -127,12 +128,12 @@ __device__ __forceinline__ float epi_act(int act, float v) {
 // EPI_GENERIC keeps every test at run time and serves shapes outside the list.
 enum {
   EPI_BIAS = 1, EPI_FSCALE = 2, EPI_GATE = 4, EPI_RES = 8, EPI_OUT32 = 16, EPI_OUT16 = 32, EPI_ELU16 = 64,
-  EPI_ACT_SHIFT = 7 /* 2 bits */, EPI_ALPHA = 512, EPI_GENERIC = -1
+  EPI_ACT_SHIFT = 7 /* 2 bits */, EPI_ALPHA = 512, EPI_WSCALE = 1024 /* generic loop only */, EPI_GENERIC = -1
 };
 __host__ __device__ inline int epi_mask_of(const GemmEpi& e) {
   return (e.bias ? EPI_BIAS : 0) | (e.fscale ? EPI_FSCALE : 0) | (e.gate ? EPI_GATE : 0) | (e.res ? EPI_RES : 0) |
          (e.out32 ? EPI_OUT32 : 0) | (e.out16 ? EPI_OUT16 : 0) | ((e.out16 && e.act16 == ACT_ELU) ? EPI_ELU16 : 0) |
-         (e.act << EPI_ACT_SHIFT) | (e.alpha != 1.f ? EPI_ALPHA : 0);
+         (e.act << EPI_ACT_SHIFT) | (e.alpha != 1.f ? EPI_ALPHA : 0) | (e.wscale ? EPI_WSCALE : 0);
 }
 // every shape the engine issues (engine.cu: FlowLM, flow head, Mimi transformer, SEANet)
 #define PTTS_EPI_SHAPES(X)                                                                  \
@@ -188,6 +189,7 @@ __device__ __noinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_
   const float alpha = (GEN || (M & EPI_ALPHA)) ? e.alpha : 1.f;
   const float* __restrict__ bias = e.bias;
   const float* __restrict__ fscale = e.fscale;
+  const float* __restrict__ wscale = GEN ? e.wscale : nullptr;
   const int swap = p.swap, F = p.F, T = p.T, R = p.R, G = p.G, n_streams = p.n_streams;
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
@@ -253,6 +255,7 @@ __device__ __noinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_
 #pragma unroll
       for (int c = 0; c < V; ++c) {
         float x = v[c];
+        if (GEN && wscale) x *= __ldg(wscale + f + c);
         if (has_bias) x += bv[c];
         x = epi_act(act, x) * alpha;
         if (has_fscale) x *= sv[c];
@@ -593,6 +596,7 @@ __global__ void gemm_simt_kernel(const GemmParams p) {
     for (int c = 0; c < C; ++c) acc += __half2float(a[j * p.act_ld + c]) * __half2float(w[j * C + c]);
   const GemmEpi& e = p.epi;
   float v = acc;
+  if (e.wscale) v *= e.wscale[f];
   if (e.bias) v += e.bias[f];
   v = epi_act(e.act, v) * e.alpha;
   if (e.fscale) v *= e.fscale[f];

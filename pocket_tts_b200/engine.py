@@ -44,7 +44,7 @@ class Voice:
 
 class Engine:
     def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
-                 kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True):
+                 kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True, int8_weights: bool = False):
         L = _lib.lib()
         self._keep = []
         descs = (TensorDesc * len(weights))()
@@ -60,7 +60,7 @@ class Engine:
         cfg = EngineCfg()
         cfg.device, cfg.max_slots = device, max_slots
         cfg.max_batch = max_batch or max_slots
-        cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, 0, int(cuda_graph), debug_gemm
+        cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, int(int8_weights), int(cuda_graph), debug_gemm
         cfg.reserved[0] = gemm_mode
         h = C.c_void_p()
         check(L.ptts_engine_create(C.byref(cfg), descs, len(weights), C.byref(h)))
@@ -185,6 +185,11 @@ class Engine:
             tag, cnt, ms, by, fl = line.split()
             out[tag] = dict(launches=int(cnt), ms=float(ms), bytes=float(by), flops=float(fl))
         return out
+
+    def profile_overhead_us(self) -> float:
+        v = C.c_float()
+        check(_lib.lib().ptts_profile_overhead(self._h, C.byref(v)))
+        return 1000.0 * v.value
 
     @property
     def cuda_stream(self) -> int:

@@ -257,3 +257,49 @@ def test_host_mirror_generate_stream_tokens():
     assert len(frames) == 4
     voice.close()
     m.close()
+
+
+def test_int8_weight_mode_matches_reference_quantisation():
+    """BASELINE configs[3]: per-tensor symmetric int8 with the reference's scheme and skip list
+    (crates/pocket-tts/src/quantize.rs:27-41,65-94,117-154).  The oracle runs f32 math on the fake-quantised
+    tensors exactly like the reference's QuantizedTensor; the engine holds the integer codes as the GEMM operand and
+    applies the scale in the epilogue."""
+    from oracle import ptts_oracle as O
+    from pocket_tts_b200.engine import Engine, StreamSpec
+    for e in _cache.values():
+        e[0].close()
+    _cache.clear()
+    wnp = synth.make_weights(1234)
+    wq = {}
+    n_quant = 0
+    for name, w in wnp.items():
+        if O.should_quantize(name, w.size):
+            q, scale = O.quantize_per_tensor(w)
+            wq[name] = (q.astype(np.float32) * scale).reshape(w.shape)
+            n_quant += 1
+        else:
+            wq[name] = w
+    assert n_quant > 60
+    assert not np.array_equal(wq["flow_lm.transformer.layers.0.linear1.weight"], wnp["flow_lm.transformer.layers.0.linear1.weight"])
+    np.testing.assert_array_equal(wq["flow_lm.transformer.layers.0.self_attn.out_proj.weight"],
+                                  wnp["flow_lm.transformer.layers.0.self_attn.out_proj.weight"])  # skip list
+    W = O.to_torch(wq)
+    prompt = synth.make_voice_prompt(24, seed=9)
+    tok = synth.make_tokens(9, seed=4)
+    frames = 4
+    noise = synth.make_noise(frames, seed=6)
+    ref = O.generate_segment(W, O.voice_state_from_prompt(W, prompt), tok, noise, frames, 0, float("inf"))
+    eng = Engine(wnp, max_slots=2, kv_capacity=128, int8_weights=True)  # the engine quantises the raw weights itself
+    voice = eng.voice_from_prompt(prompt)
+    s = eng.open_streams([voice], [StreamSpec(tok, frames, 0, 1e30, noise=noise)])
+    lat, pcm = [], []
+    for f in range(frames):
+        if f:
+            eng.set_feedback(int(s[0]), ref["latents"][f - 1])
+        p, _, l, _ = eng.step(s)
+        lat.append(l[0]); pcm.append(p[0])
+    eng.close_stream(int(s[0]))
+    voice.close()
+    eng.close()
+    assert np.abs(np.stack(lat) - ref["latents"]).max() <= LAT_TOL
+    assert snr(ref["pcm"], np.stack(pcm)) >= SNR_MIN
