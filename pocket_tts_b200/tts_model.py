@@ -199,3 +199,73 @@ def shard_requests(n_requests: int, world_size: int, rank: int) -> range:
     base, rem = divmod(n_requests, world_size)
     start = rank * base + min(rank, rem)
     return range(start, start + base + (1 if rank < rem else 0))
+
+
+class BatchScheduler:
+    """Continuous batching of many long-form requests on one engine (BASELINE configs[4]: concurrent 60 s requests
+    with `[pause:Xms]`).  A request is an ordered list of segments, ("text", StreamSpec) or ("pause", ms); the chunks
+    of one request run one after the other (ordered emission, each restarting from the voice state exactly like
+    generate_stream's flat_map, tts_model.rs:899-910) while different requests fill the batch.  Whenever streams
+    finish, the next chunks of their requests are opened together (one batched text prefill) and join the next step;
+    pauses are host zeros (tts_model.rs:1115-1124).  Frames are fetched one step behind the launch
+    (ptts_step_begin / flags / pcm), so the codec of frame n overlaps the language model of frame n+1."""
+
+    def __init__(self, engine: Engine, voice: Voice, max_batch: int | None = None):
+        self.engine, self.voice = engine, voice
+        self.max_batch = max_batch or engine.max_batch
+
+    def run(self, requests: list[list[tuple]]) -> list[np.ndarray]:
+        eng = self.engine
+        out: list[list[np.ndarray]] = [[] for _ in requests]
+        cursor = [0] * len(requests)          # next segment of each request
+        waiting = list(range(len(requests)))  # requests with no stream in flight
+        active: dict[int, int] = {}           # slot -> request
+        pending = None                        # (ticket, [requests in row order]) whose PCM is still on the device
+
+        def admit():
+            specs, owners = [], []
+            still = []
+            for r in waiting:
+                # host-side pauses are consumed immediately; the first text segment claims a slot
+                while cursor[r] < len(requests[r]) and requests[r][cursor[r]][0] == "pause":
+                    out[r].append(np.zeros(silence_samples(requests[r][cursor[r]][1]), np.float32))
+                    cursor[r] += 1
+                if cursor[r] >= len(requests[r]):
+                    continue
+                if len(active) + len(specs) < self.max_batch:
+                    specs.append(requests[r][cursor[r]][1])
+                    owners.append(r)
+                    cursor[r] += 1
+                else:
+                    still.append(r)
+            waiting[:] = still
+            if specs:
+                for slot, r in zip(eng.open_streams([self.voice] * len(specs), specs), owners):
+                    active[int(slot)] = r
+
+        def collect(p):
+            ticket, owners = p
+            pcm = eng.step_pcm(ticket)
+            for row, r in enumerate(owners):
+                out[r].append(pcm[row])
+
+        admit()
+        while active:
+            slots = np.fromiter(active.keys(), np.int32, len(active))
+            owners = [active[int(s)] for s in slots]
+            ticket = eng.step_begin(slots)
+            fin, _, _ = eng.step_flags(ticket)
+            if pending is not None:
+                collect(pending)
+            pending = (ticket, owners)
+            done = [int(s) for s, f in zip(slots, fin) if f]
+            if done:
+                collect(pending)  # a finished slot is closed below: drain the step that still reads it
+                pending = None
+                for s in done:
+                    eng.close_stream(s)
+                    waiting.append(active.pop(s))
+                admit()
+        if pending is not None:
+            collect(pending)
+        return [np.concatenate(o) if o else np.zeros(0, np.float32) for o in out]

@@ -303,3 +303,48 @@ def test_int8_weight_mode_matches_reference_quantisation():
     eng.close()
     assert np.abs(np.stack(lat) - ref["latents"]).max() <= LAT_TOL
     assert snr(ref["pcm"], np.stack(pcm)) >= SNR_MIN
+
+
+def test_continuous_batching_long_form():
+    """configs[4] in miniature: requests made of several chunks and pauses share a small batch; chunks of a request
+    are emitted in order, pauses add exactly ms*24 zero samples (pause.rs:183-185), and every chunk equals the same
+    chunk generated alone."""
+    from pocket_tts_b200.engine import StreamSpec
+    from pocket_tts_b200.tts_model import BatchScheduler
+    eng, _ = engine_for(1234, 0.01)
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(16, seed=5))
+
+    def chunk(seed, frames):
+        return StreamSpec(synth.make_tokens(5 + seed % 7, seed=seed), frames, 0, 1e30, temp=0.0)
+
+    requests = [
+        [("text", chunk(1, 3)), ("pause", 300), ("text", chunk(2, 2))],
+        [("text", chunk(3, 5))],
+        [("pause", 100), ("text", chunk(4, 2)), ("text", chunk(5, 4)), ("pause", 50)],
+        [("text", chunk(6, 1)), ("text", chunk(7, 1)), ("text", chunk(8, 3))],
+        [("text", chunk(9, 4)), ("pause", 1000)],
+    ]
+    got = BatchScheduler(eng, voice, max_batch=3).run(requests)
+
+    def alone(spec):
+        s = eng.open_streams([voice], [spec])
+        frames = []
+        while True:
+            pcm, fin, _, _ = eng.step(s)
+            frames.append(pcm[0])
+            if fin[0]:
+                break
+        eng.close_stream(int(s[0]))
+        return np.concatenate(frames)
+
+    for req, pcm in zip(requests, got):
+        want = []
+        for kind, arg in req:
+            want.append(np.zeros(arg * 24, np.float32) if kind == "pause" else alone(arg))
+        want = np.concatenate(want)
+        assert pcm.shape == want.shape
+        # identical streams in a different batch: only the GEMM tiling (hence f32 summation order) may differ
+        assert snr(want, pcm) >= 60.0 or np.abs(want).max() == 0
+        zero_mask = want == 0
+        assert (pcm[zero_mask] == 0).all()
+    voice.close()
