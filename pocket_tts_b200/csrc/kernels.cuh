@@ -364,44 +364,32 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __r
 
 // Mimi decoder-transformer attention: 16 new rows per stream, sliding window of 250 positions
 // (reference attention.rs:167-264 ring + sdpa.rs:129-171 mask: query at position p sees keys in (p-250, p]).
-// K,V live in a per-slot ring indexed by position % 272 (272 >= 250 + 15, so the 16 rows of a frame never evict a
-// key one of its queries still needs).  grid (n, 8 heads), block 256, ~100 KB dynamic smem (two CTAs per SM).
-//   stage   RoPE the 16 new rows (q -> smem, k/v -> ring and smem); copy the <= 249 older K/V rows of the window
-//           into smem with independent 16-byte loads (row pitch 144 B: conflict-free 16-byte smem accesses)
-//   compute each warp owns two queries end to end -- scores (one key per lane), softmax, P.V (8 lanes per key row,
-//           4 keys per iteration) -- so nothing but the staging needs a block barrier and no cross-warp reduction
-//           exists (results are bit-reproducible).
+// K,V live in a per-slot ring indexed by position % 272; 272 >= 250 + 15 so the 16 rows written first never
+// overwrite a key that a query of this step still needs.  grid (n, 8 heads), block 256, dynamic smem.
+//   scores  one key per thread (row in registers via 8 x 16-byte loads) against the 16 queries in smem
+//   P V     a warp takes keys w, w+8, ...; each lane owns 2 of the 64 dims for all 16 queries; the 8 warps'
+//           partial sums are folded in warp order (bit-reproducible)
 static constexpr int MATTN_THREADS = 256;
-static constexpr int MATTN_KP = 72;                     // halves per staged row (64 + 8 pad)
-static constexpr int MATTN_SW = MIMI_RING + 8;          // score row pitch (floats)
-static constexpr int MATTN_SMEM = 2 * MIMI_RING * MATTN_KP * 2 + 16 * HD * 4 + 16 * MATTN_SW * 4;
-__global__ void __launch_bounds__(MATTN_THREADS, 2)
+static constexpr int MATTN_SW = MIMI_RING + 8;
+static constexpr int MATTN_SMEM = (16 * HD + 16 * MATTN_SW + 16 + 8 * 16 * HD) * 4;
+__global__ void __launch_bounds__(MATTN_THREADS)
 mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
                  const int* __restrict__ mimi_pos, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/, int layer,
                  int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int NH = 8, DM = 512, T = 16, KP = MATTN_KP, SW = MATTN_SW;
-  extern __shared__ __align__(16) unsigned char msm_raw[];
-  __half* k_s = reinterpret_cast<__half*>(msm_raw);                    // [272][72]
-  __half* v_s = k_s + MIMI_RING * KP;                                  // [272][72]
-  float (*q_s)[HD] = reinterpret_cast<float (*)[HD]>(v_s + MIMI_RING * KP);  // [16][64]
-  float (*p_s)[SW] = reinterpret_cast<float (*)[SW]>(&q_s[T][0]);      // [16][280]
+  constexpr int NH = 8, DM = 512, T = 16, SW = MATTN_SW, NW = MATTN_THREADS / 32;
+  extern __shared__ float msm[];
+  float (*q_s)[HD] = reinterpret_cast<float (*)[HD]>(msm);                       // [16][64]
+  float (*p_s)[SW] = reinterpret_cast<float (*)[SW]>(msm + T * HD);              // [16][280]
+  float* inv_s = msm + T * HD + T * SW;                                          // [16]
+  float* red_s = inv_s + 16;                                                     // [8][16][64]
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = row_seq[b];
   const int p0 = mimi_pos[b];  // absolute position of the first new row
   __half* kring = ring + ((static_cast<long long>(slot) * n_layers + layer) * 2 * NH + h) * MIMI_RING * HD;
   __half* vring = kring + static_cast<long long>(NH) * MIMI_RING * HD;
-  const int kmin = max(0, p0 - (MIMI_CTX - 1));  // the window of the first query starts at p0-249
-  const int nold = p0 - kmin;                    // older keys needed, <= 249
-  const int nk = nold + T;                       // <= 265
-  // older rows: 8 chunks of 16 B per row, K and V
-  for (int idx = tid; idx < nold * 16; idx += MATTN_THREADS) {
-    const int j = idx >> 4, c = idx & 7, isv = (idx >> 3) & 1;
-    const uint4 u = reinterpret_cast<const uint4*>((isv ? vring : kring) + ((kmin + j) % MIMI_RING) * HD)[c];
-    *reinterpret_cast<uint4*>((isv ? v_s : k_s) + j * KP + c * 8) = u;
-  }
-  // new rows: RoPE, ring write, smem copy (16 rows x 32 pairs)
+  // RoPE + ring write: 16 rows x 32 pairs = 512 items
   for (int it = tid; it < T * 32; it += MATTN_THREADS) {
     const int t = it >> 5, i = it & 31;
     const float* row = qkv + (static_cast<long long>(b) * T + t) * 3 * DM;
@@ -411,40 +399,49 @@ mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __re
     float qr, qi, kr, ki;
     rope_pair(qx.x, qx.y, p0 + t, i, qr, qi);
     rope_pair(kx.x, kx.y, p0 + t, i, kr, ki);
-    q_s[t][2 * i] = qr * 0.125f;  // 1/sqrt(64) folded into q
-    q_s[t][2 * i + 1] = qi * 0.125f;
-    const __half2 kh = __floats2half2_rn(kr, ki), vh = __floats2half2_rn(vx.x, vx.y);
+    q_s[t][2 * i] = qr;
+    q_s[t][2 * i + 1] = qi;
     const int ri = (p0 + t) % MIMI_RING;
-    reinterpret_cast<__half2*>(kring + ri * HD)[i] = kh;
-    reinterpret_cast<__half2*>(vring + ri * HD)[i] = vh;
-    reinterpret_cast<__half2*>(k_s + (nold + t) * KP)[i] = kh;
-    reinterpret_cast<__half2*>(v_s + (nold + t) * KP)[i] = vh;
+    reinterpret_cast<__half2*>(kring + ri * HD)[i] = __floats2half2_rn(kr, ki);
+    reinterpret_cast<__half2*>(vring + ri * HD)[i] = __floats2half2_rn(vx.x, vx.y);
   }
   __syncthreads();
-  // ---- this warp's two queries
-  const int t0 = warp * 2, t1 = t0 + 1;
-  for (int j = lane; j < nk; j += 32) {
-    const uint4* kr = reinterpret_cast<const uint4*>(k_s + j * KP);
-    float a0 = 0.f, a1 = 0.f;
+  // keys: positions [kmin, p0+15]; the window of the first query starts at p0-249
+  const int kmin = max(0, p0 - (MIMI_CTX - 1));
+  const int nk = p0 + T - kmin;  // <= 265
+  for (int j = tid; j < nk; j += MATTN_THREADS) {
+    const int kp = kmin + j;
+    const uint4* kr = reinterpret_cast<const uint4*>(kring + (kp % MIMI_RING) * HD);
+    uint4 u[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[c] = kr[c];
+    float kf[HD];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint4 u = kr[c];
-      const __half2* hh = reinterpret_cast<const __half2*>(&u);
-      const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]), f2 = __half22float2(hh[2]), f3 = __half22float2(hh[3]);
-      const float4 qa = *reinterpret_cast<const float4*>(&q_s[t0][c * 8]), qb = *reinterpret_cast<const float4*>(&q_s[t0][c * 8 + 4]);
-      const float4 ra = *reinterpret_cast<const float4*>(&q_s[t1][c * 8]), rb = *reinterpret_cast<const float4*>(&q_s[t1][c * 8 + 4]);
-      a0 += f0.x * qa.x + f0.y * qa.y + f1.x * qa.z + f1.y * qa.w + f2.x * qb.x + f2.y * qb.y + f3.x * qb.z + f3.y * qb.w;
-      a1 += f0.x * ra.x + f0.y * ra.y + f1.x * ra.z + f1.y * ra.w + f2.x * rb.x + f2.y * rb.y + f3.x * rb.z + f3.y * rb.w;
-    }
-    const int kp = kmin + j;
-    p_s[t0][j] = (kp <= p0 + t0 && kp > p0 + t0 - MIMI_CTX) ? a0 : -INFINITY;
-    p_s[t1][j] = (kp <= p0 + t1 && kp > p0 + t1 - MIMI_CTX) ? a1 : -INFINITY;
-  }
-  __syncwarp();
-  float inv0 = 0.f, inv1 = 0.f;
+      const __half2* hh = reinterpret_cast<const __half2*>(&u[c]);
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int t = t0 + u;
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(hh[e]);
+        kf[c * 8 + 2 * e] = f.x;
+        kf[c * 8 + 2 * e + 1] = f.y;
+      }
+    }
+#pragma unroll 2
+    for (int t = 0; t < T; ++t) {
+      const int qp = p0 + t;
+      float acc = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; d += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&q_s[t][d]);
+        acc += kf[d] * q4.x + kf[d + 1] * q4.y + kf[d + 2] * q4.z + kf[d + 3] * q4.w;
+      }
+      const bool ok = (kp <= qp) && (kp > qp - MIMI_CTX);
+      p_s[t][j] = ok ? acc * 0.125f : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // softmax per query row: warp w owns rows 2w, 2w+1
+  for (int t = warp * 2; t < warp * 2 + 2; ++t) {
     float m = -INFINITY;
     for (int j = lane; j < nk; j += 32) m = fmaxf(m, p_s[t][j]);
     m = warp_max(m);
@@ -454,41 +451,49 @@ mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __re
       p_s[t][j] = p;
       sacc += p;
     }
-    const float iv = 1.f / warp_sum(sacc);
-    if (u == 0) inv0 = iv; else inv1 = iv;
+    sacc = warp_sum(sacc);
+    if (lane == 0) inv_s[t] = 1.f / sacc;
   }
-  __syncwarp();
-  const int sub = lane >> 3, part = lane & 7;
-  float o0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, o1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j0 = 0; j0 < nk; j0 += 4) {
-    const int j = j0 + sub;
-    if (j < nk) {
-      const uint4 u = *reinterpret_cast<const uint4*>(v_s + j * KP + part * 8);
-      const __half2* hh = reinterpret_cast<const __half2*>(&u);
-      const float pa = p_s[t0][j], pb = p_s[t1][j];
+  __syncthreads();
+  // P V
+  float acc[T][2];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(hh[e]);
-        o0[2 * e] += pa * f.x; o0[2 * e + 1] += pa * f.y;
-        o1[2 * e] += pb * f.x; o1[2 * e + 1] += pb * f.y;
+  for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = 0.f;
+  for (int j0 = warp; j0 < nk; j0 += NW * 4) {
+    float2 f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // four independent loads in flight
+      const int j = j0 + u * NW;
+      f[u] = (j < nk) ? __half22float2(reinterpret_cast<const __half2*>(vring + ((kmin + j) % MIMI_RING) * HD)[lane])
+                      : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * NW;
+      if (j < nk) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const float p = p_s[t][j];
+          acc[t][0] += p * f[u].x;
+          acc[t][1] += p * f[u].y;
+        }
       }
     }
   }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {  // fold the four key sub-groups (fixed order)
-    o0[e] += __shfl_xor_sync(0xffffffffu, o0[e], 8);
-    o0[e] += __shfl_xor_sync(0xffffffffu, o0[e], 16);
-    o1[e] += __shfl_xor_sync(0xffffffffu, o1[e], 8);
-    o1[e] += __shfl_xor_sync(0xffffffffu, o1[e], 16);
-  }
-  if (sub < 2) {  // sub 0 writes query t0, sub 1 writes t1: 8 lanes x 16 bytes = one 128-byte row slice each
-    const float sc = sub == 0 ? inv0 : inv1;
-    __half2 hv[4];
+  for (int t = 0; t < T; ++t) *reinterpret_cast<float2*>(red_s + (warp * T + t) * HD + 2 * lane) = make_float2(acc[t][0], acc[t][1]);
+  __syncthreads();
+  for (int o = tid; o < T * 32; o += MATTN_THREADS) {
+    const int t = o >> 5, i = o & 31;
+    float sx = 0.f, sy = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e)
-      hv[e] = __floats2half2_rn((sub == 0 ? o0[2 * e] : o1[2 * e]) * sc, (sub == 0 ? o0[2 * e + 1] : o1[2 * e + 1]) * sc);
-    *reinterpret_cast<uint4*>(out16 + (static_cast<long long>(b) * T + t0 + sub) * DM + h * HD + part * 8) =
-        *reinterpret_cast<const uint4*>(hv);
+    for (int w = 0; w < NW; ++w) {
+      const float2 v = *reinterpret_cast<const float2*>(red_s + (w * T + t) * HD + 2 * i);
+      sx += v.x;
+      sy += v.y;
+    }
+    reinterpret_cast<__half2*>(out16 + (static_cast<long long>(b) * T + t) * DM + h * HD)[i] =
+        __floats2half2_rn(sx * inv_s[t], sy * inv_s[t]);
   }
 }
 
