@@ -98,7 +98,7 @@ struct Engine {
   bool use_pdl = true;
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
-  struct ProfRec { const char* tag; cudaEvent_t a, b; double bytes, flops; };
+  struct ProfRec { const char* tag; const char* fn; cudaEvent_t a, b; double bytes, flops; };
   bool profiling = false;
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
@@ -108,7 +108,7 @@ struct Engine {
   double step_kv_bytes = 0;  // FlowLM KV bytes one layer's decode attention reads in the current step
   void tag(const char* t) { cur_tag = t; }
   const char* take_tag(const char* dflt) { const char* t = cur_tag ? cur_tag : dflt; cur_tag = nullptr; return t; }
-  void prof_begin(const char* t, double bytes, double flops);
+  void prof_begin(const char* t, double bytes, double flops, const char* fn);
   void prof_end();
   std::string prof_report();
   int NB = 0, NS = 0, KVCAP = 0, PR = 0;  // max batch, slots, own kv rows, prefill rows
@@ -216,7 +216,7 @@ Engine::~Engine() {
   if (stream) cudaStreamDestroy(stream);
 }
 
-void Engine::prof_begin(const char* t, double bytes, double flops) {
+void Engine::prof_begin(const char* t, double bytes, double flops, const char* fn) {
   if (!profiling) return;
   cudaEvent_t ev2[2];
   for (auto& x : ev2) {
@@ -225,7 +225,7 @@ void Engine::prof_begin(const char* t, double bytes, double flops) {
     prof_pool.pop_back();
   }
   PTTS_CUDA(cudaEventRecord(ev2[0], ls));
-  prof_recs.push_back(ProfRec{t, ev2[0], ev2[1], bytes, flops});
+  prof_recs.push_back(ProfRec{t, fn ? fn : t, ev2[0], ev2[1], bytes, flops});
 }
 void Engine::prof_end() {
   if (!profiling) return;
@@ -233,24 +233,28 @@ void Engine::prof_end() {
 }
 struct ProfScope {
   Engine& e;
-  ProfScope(Engine& en, const char* t, double bytes = 0, double flops = 0) : e(en) { e.prof_begin(t, bytes, flops); ++e.launches; }
+  ProfScope(Engine& en, const char* t, double bytes = 0, double flops = 0, const char* fn = nullptr) : e(en) {
+    e.prof_begin(t, bytes, flops, fn);
+    ++e.launches;
+  }
   ~ProfScope() { e.prof_end(); }
 };
-// one line per kernel class: "tag launches total_ms bytes flops" (bytes/flops are the algorithmic totals)
+// one line per kernel class: "tag kernel_function launches total_ms bytes flops" (bytes/flops are the algorithmic totals)
 std::string Engine::prof_report() {
   PTTS_CUDA(cudaStreamSynchronize(stream));
-  struct Agg { int n = 0; double ms = 0, bytes = 0, flops = 0; };
+  struct Agg { int n = 0; double ms = 0, bytes = 0, flops = 0; const char* fn = ""; };
   std::map<std::string, Agg> agg;
   for (auto& r : prof_recs) {
     float ms = 0;
     PTTS_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
     Agg& g = agg[r.tag];
-    g.n++; g.ms += ms; g.bytes += r.bytes; g.flops += r.flops;
+    g.n++; g.ms += ms; g.bytes += r.bytes; g.flops += r.flops; g.fn = r.fn;
     prof_pool.push_back(r.a); prof_pool.push_back(r.b);
   }
   prof_recs.clear();
   std::string out;
-  for (auto& kv : agg) out += fmt("%s %d %.6f %.0f %.0f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
+  for (auto& kv : agg)
+    out += fmt("%s %s %d %.6f %.0f %.0f\n", kv.first.c_str(), kv.second.fn, kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
   return out;
 }
 
@@ -689,7 +693,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   const double act_rows = (double)n_streams * (T + taps - 1);
   double bytes = (double)F * w.K * 2 + act_rows * a.C * 2;
   bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + (epi.res ? 4 : 0) + (epi.gate ? 4 : 0));
-  ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K);
+  ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K,
+               cfg.debug_gemm ? "gemm_simt_kernel" : (persistent ? "gemm_tc_persistent_kernel" : "gemm_tc_kernel"));
   if (cfg.debug_gemm) {
     const long long n = rows * F;
     launch_k(use_pdl, gemm_simt_kernel, (unsigned)((n + 255) / 256), 256, 0, ls, 1, p);
@@ -707,7 +712,7 @@ template <int C>
 void Engine::ln(const float* x, int rows, const float* w, const float* b, float eps, const float* shift, const float* scale,
                 int mod_ld, __half* out, int out_ld) {
   if (rows <= 0) return;
-  ProfScope ps(*this, take_tag("layernorm"), (double)rows * C * (4 + 2 + (scale ? 8 : 0)), 0);
+  ProfScope ps(*this, take_tag("layernorm"), (double)rows * C * (4 + 2 + (scale ? 8 : 0)), 0, "ln_rows_kernel");
   launch_k(use_pdl, ln_rows_kernel<C>, (rows + 3) / 4, 128, 0, ls, 1, x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
 }
 
@@ -736,7 +741,7 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
         launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
       const size_t sm = 0;
-      { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0);
+      { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0, "flowlm_attn_decode_kernel");
         launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
     }
     // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue
@@ -840,7 +845,7 @@ void Engine::step_part_b(int n, bool marks) {
     e = epi_none();
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
     tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
-    { ProfScope ps(*this, "mimi.attn", (double)n * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0);
+    { ProfScope ps(*this, "mimi.attn", (double)n * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0, "mimi_attn_kernel");
       launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), MATTN_THREADS, MATTN_SMEM, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);

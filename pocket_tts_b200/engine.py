@@ -182,8 +182,8 @@ class Engine:
         check(int(n))
         out = {}
         for line in buf.value.decode().splitlines():
-            tag, cnt, ms, by, fl = line.split()
-            out[tag] = dict(launches=int(cnt), ms=float(ms), bytes=float(by), flops=float(fl))
+            tag, fn, cnt, ms, by, fl = line.split()
+            out[tag] = dict(fn=fn, launches=int(cnt), ms=float(ms), bytes=float(by), flops=float(fl))
         return out
 
     def profile_overhead_us(self) -> float:
