@@ -104,6 +104,16 @@ struct Engine {
   std::vector<cudaEvent_t> prof_pool;
   const char* cur_tag = nullptr;
   unsigned long long* gemm_trace = nullptr;
+  // LayerNorm requested behind the next GEMM (fused into it when its grid is small enough, else a separate launch)
+  struct LnSpec { bool set = false; const float* x; int rows, C; const float* w; const float* b; float eps; const float* shift;
+                  const float* scale; int mod_ld; __half* out; int out_ld; const char* tag; };
+  LnSpec next_ln;
+  DevBuf<int> ln_counters;  // [4]: arrive/depart for stream A, for stream B
+  bool fuse_ln = true;
+  void ln_after_next_gemm(const char* tag, const float* x, int rows, int C, const float* w, const float* b, float eps,
+                          const float* shift, const float* scale, int mod_ld, __half* out, int out_ld) {
+    next_ln = LnSpec{true, x, rows, C, w, b, eps, shift, scale, mod_ld, out, out_ld, tag};
+  }
   // bring-up: passed to the next GEMM launches
   double step_kv_bytes = 0;  // FlowLM KV bytes one layer's decode attention reads in the current step
   void tag(const char* t) { cur_tag = t; }
@@ -604,6 +614,14 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
 }
 
 // ------------------------------------------------------------------------------------------------ GEMM dispatch
+template <int C>
+void Engine::ln(const float* x, int rows, const float* w, const float* b, float eps, const float* shift, const float* scale,
+                int mod_ld, __half* out, int out_ld) {
+  if (rows <= 0) return;
+  ProfScope ps(*this, take_tag("layernorm"), (double)rows * C * (4 + 2 + (scale ? 8 : 0)), 0, "ln_rows_kernel");
+  launch_k(use_pdl, ln_rows_kernel<C>, (rows + 3) / 4, 128, 0, ls, 1, x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
+}
+
 void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G, const Weight16& w, int F, GemmEpi epi,
                   bool allow_split) {
   const long long rows = (long long)n_streams * T;
@@ -654,18 +672,30 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   // F/128 tiles): a cluster of `splits` CTAs along z shares one output tile (gemm.cuh), at most 8 (portable size).
   (void)allow_split;
   int splits = 1;
-  {
-    const int tiles = grid.x * grid.y;
-    // power-of-two cluster sizes only (they pack into a GPC), and the whole grid must fit one wave with slack for
-    // cluster placement: 24 tiles x 4 (96 CTAs) beats 24 x 6 (144 CTAs, measured 8.5 vs 15 us)
-    if (!persistent && total_kb >= 4) {
-      while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= 132 && splits * 2 <= total_kb / 2) splits *= 2;
-    }
-    if (cfg.reserved[2] > 0 && !persistent) splits = std::min(cfg.reserved[2], std::min(total_kb, GEMM_MAX_SPLIT));  // test hook
+  const int tiles = grid.x * grid.y;
+  // power-of-two cluster sizes only (they pack into a GPC), and the whole grid must fit one wave with slack for
+  // cluster placement: 24 tiles x 4 (96 CTAs) beats 24 x 6 (144 CTAs, measured 8.5 vs 15 us)
+  if (!persistent && total_kb >= 4) {
+    while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= 132 && splits * 2 <= total_kb / 2) splits *= 2;
   }
+  // A fused LayerNorm needs every CTA resident while it spins on the grid barrier, and both step streams may run such
+  // a GEMM at once: keep each at <= 64 CTAs (2 x 64 < 148 SMs) or fall back to a separate LayerNorm launch.
+  const LnSpec lnreq = next_ln;
+  next_ln.set = false;
+  bool ln_fused = false;
+  if (lnreq.set && fuse_ln && !persistent && !cfg.debug_gemm && !profiling) {
+    while (splits > 1 && tiles * splits > 64) splits /= 2;
+    ln_fused = tiles * splits <= 64;
+  }
+  if (cfg.reserved[2] > 0 && !persistent) splits = std::min(cfg.reserved[2], std::min(total_kb, GEMM_MAX_SPLIT));  // test hook
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.epi_mask = epi_mask_of(p.epi);
+  if (ln_fused) {
+    if (!ln_counters.p) ln_counters.alloc(4);
+    p.ln = LnFuse{lnreq.x, lnreq.w, lnreq.b, lnreq.shift, lnreq.scale, lnreq.out, ln_counters.p + (ls == stream_b ? 2 : 0),
+                  lnreq.rows, lnreq.C, lnreq.mod_ld, lnreq.out_ld, lnreq.eps, 1};
+  }
   grid.z = splits;
   const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : 200) * 1024LL;  // one CTA per SM
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
@@ -693,27 +723,26 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   const double act_rows = (double)n_streams * (T + taps - 1);
   double bytes = (double)F * w.K * 2 + act_rows * a.C * 2;
   bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + (epi.res ? 4 : 0) + (epi.gate ? 4 : 0));
-  ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K,
-               cfg.debug_gemm ? "gemm_simt_kernel" : (persistent ? "gemm_tc_persistent_kernel" : "gemm_tc_kernel"));
-  if (cfg.debug_gemm) {
-    const long long n = rows * F;
-    launch_k(use_pdl, gemm_simt_kernel, (unsigned)((n + 255) / 256), 256, 0, ls, 1, p);
-  } else {
-    const CUtensorMap& ma = swap ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
-                                 : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
-    const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
-    if (persistent) launch_k(use_pdl, gemm_tc_persistent_kernel, grid, GEMM_THREADS, smem, ls, 1, ma, mw, p);
-    else launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);
+  {
+    ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K,
+                 cfg.debug_gemm ? "gemm_simt_kernel" : (persistent ? "gemm_tc_persistent_kernel" : "gemm_tc_kernel"));
+    if (cfg.debug_gemm) {
+      const long long n = rows * F;
+      launch_k(use_pdl, gemm_simt_kernel, (unsigned)((n + 255) / 256), 256, 0, ls, 1, p);
+    } else {
+      const CUtensorMap& ma = swap ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
+                                   : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
+      const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
+      if (persistent) launch_k(use_pdl, gemm_tc_persistent_kernel, grid, GEMM_THREADS, smem, ls, 1, ma, mw, p);
+      else launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);
+    }
+    PTTS_CUDA(cudaGetLastError());
   }
-  PTTS_CUDA(cudaGetLastError());
-}
-
-template <int C>
-void Engine::ln(const float* x, int rows, const float* w, const float* b, float eps, const float* shift, const float* scale,
-                int mod_ld, __half* out, int out_ld) {
-  if (rows <= 0) return;
-  ProfScope ps(*this, take_tag("layernorm"), (double)rows * C * (4 + 2 + (scale ? 8 : 0)), 0, "ln_rows_kernel");
-  launch_k(use_pdl, ln_rows_kernel<C>, (rows + 3) / 4, 128, 0, ls, 1, x, rows, w, b, eps, shift, scale, mod_ld, out, out_ld);
+  if (lnreq.set && !ln_fused) {  // grid too large to fuse (prefill, profiling pass): the norm is its own launch
+    tag(lnreq.tag);
+    if (lnreq.C == 1024) ln<1024>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);
+    else ln<512>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);
+  }
 }
 
 static GemmEpi epi_none() {
@@ -725,10 +754,11 @@ static GemmEpi epi_none() {
 // ------------------------------------------------------------------------------------------------ FlowLM transformer
 // Reference models/transformer.rs:66-90 per layer.  Residual stream x stays f32 in HBM; out_proj and linear2
 // accumulate straight into it (split-K, red.add) so no epilogue buffer exists.
+// The LayerNorm in front of each GEMM rides behind the GEMM that produces its input (ln_after_next_gemm): the caller
+// provides h = LN1_0(x) on entry.
 void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* attn, __half* ffn, bool is_prefill,
                            float* qrot, const int* rseq, const int* rpos) {
   for (int l = 0; l < N_LAYERS; ++l) {
-    tag("flowlm.layernorm"); ln<D_MODEL>(x, rows, ln1_w[l].p, ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     GemmEpi e = epi_none();
     e.out32 = qkv; e.out32_map = plain_map(3 * D_MODEL);
     tag(is_prefill ? "prefill.in_proj" : "flowlm.in_proj"); gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
@@ -736,24 +766,24 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
       { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
         launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, N_HEADS), 32, 0, ls, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
       if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
-      const size_t sm = 0;
       { ProfScope ps(*this, "prefill.attn");
-        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
-      const size_t sm = 0;
       { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0, "flowlm_attn_decode_kernel");
-        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, sm, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
     }
-    // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue
+    // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue; h = LN2(x)
     e = epi_none();
     e.out32 = x; e.out32_map = plain_map(D_MODEL); e.res = x; e.res_map = plain_map(D_MODEL);
+    ln_after_next_gemm("flowlm.layernorm", x, rows, D_MODEL, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     tag(is_prefill ? "prefill.out_proj" : "flowlm.out_proj"); gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
-    tag("flowlm.layernorm"); ln<D_MODEL>(x, rows, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = ffn; e.out16_map = plain_map(D_FFN);
     tag(is_prefill ? "prefill.linear1" : "flowlm.linear1"); gemm_rows(h, rows, D_MODEL, w_lin1[l], D_FFN, e);
     e = epi_none();
     e.out32 = x; e.out32_map = plain_map(D_MODEL); e.res = x; e.res_map = plain_map(D_MODEL);
+    if (l + 1 < N_LAYERS)
+      ln_after_next_gemm("flowlm.layernorm", x, rows, D_MODEL, ln1_w[l + 1].p, ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     tag(is_prefill ? "prefill.linear2" : "flowlm.linear2"); gemm_rows(ffn, rows, D_FFN, w_lin2[l], D_MODEL, e, true);
   }
 }
@@ -786,6 +816,7 @@ void Engine::step_part_a(int n, bool marks) {
     launch_k(use_pdl, step_begin_kernel, n, 64, 0, ls, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p); }
   GemmEpi e = epi_none();
   e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
+  ln_after_next_gemm("flowlm.layernorm", x32.p, n, D_MODEL, ln1_w[0].p, ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, h16.p, D_MODEL);
   tag("flowlm.input_linear"); gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
   flowlm_layers(n, x32.p, h16.p, qkv32.p, attn16.p, ffn16.p, false, nullptr, row_seq.p, nullptr);
   { ProfScope ps(*this, "flowlm.out_norm_eos", (double)n * D_MODEL * (4 + 2 + 4), 0);
@@ -804,20 +835,24 @@ void Engine::step_part_a(int n, bool marks) {
     tag("flow.adaln"); gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
     e = epi_none();
     e.bias = b_finproj.p; e.out32 = fx32.p; e.out32_map = plain_map(FLOW_DIM);
+    // fh = LN(x) * (1 + scale) + shift of each block rides behind the GEMM that produces x (modules/mlp.rs:168-171)
+    ln_after_next_gemm("flow.ln_modulate", fx32.p, n, FLOW_DIM, inln_w[0].p, inln_b[0].p, 1e-6f, mod32.p, mod32.p + FLOW_DIM, MOD_LD,
+                       fh16.p, FLOW_DIM);
     tag("flow.input_proj"); gemm_rows(z16.p, n, 64, w_finproj, FLOW_DIM, e);
     for (int i = 0; i < FLOW_DEPTH; ++i) {
       const float* shift = mod32.p + (size_t)i * 3 * FLOW_DIM;
-      tag("flow.ln_modulate"); ln<FLOW_DIM>(fx32.p, n, inln_w[i].p, inln_b[i].p, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
       e = epi_none();
       e.bias = b_mlp0[i].p; e.act = ACT_SILU; e.out16 = fg16.p; e.out16_map = plain_map(FLOW_DIM);
       tag("flow.mlp0"); gemm_rows(fh16.p, n, FLOW_DIM, w_mlp0[i], FLOW_DIM, e);
       e = epi_none();
       e.bias = b_mlp2[i].p; e.gate = shift + 2 * FLOW_DIM; e.gate_map = plain_map(MOD_LD);
       e.res = fx32.p; e.res_map = plain_map(FLOW_DIM); e.out32 = fx32.p; e.out32_map = plain_map(FLOW_DIM);
+      const float* nshift = mod32.p + (size_t)(i + 1) * 3 * FLOW_DIM;  // next block, or the final layer (no affine)
+      const bool fin = (i + 1 == FLOW_DEPTH);
+      ln_after_next_gemm("flow.ln_modulate", fx32.p, n, FLOW_DIM, fin ? nullptr : inln_w[i + 1].p, fin ? nullptr : inln_b[i + 1].p,
+                         1e-6f, nshift, nshift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
       tag("flow.mlp2"); gemm_rows(fg16.p, n, FLOW_DIM, w_mlp2[i], FLOW_DIM, e);
     }
-    const float* shift = mod32.p + (size_t)FLOW_DEPTH * 3 * FLOW_DIM;
-    tag("flow.ln_modulate"); ln<FLOW_DIM>(fx32.p, n, nullptr, nullptr, 1e-6f, shift, shift + FLOW_DIM, MOD_LD, fh16.p, FLOW_DIM);
     e = epi_none();  // z += (W h + b) / S   (Euler step, flow_lm.rs:15-19)
     e.bias = b_final.p; e.alpha = 1.f / (float)lsd_steps; e.res = z32.p; e.res_map = plain_map(LDIM);
     e.out32 = z32.p; e.out32_map = plain_map(LDIM); e.out16 = z16.p; e.out16_map = plain_map(64);
@@ -840,8 +875,8 @@ void Engine::step_front(int n) {
 void Engine::step_part_b(int n, bool marks) {
   const int MR = n * MIMI_T;
   GemmEpi e = epi_none();
+  tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[0].p, m_ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
   for (int l = 0; l < MIMI_LAYERS; ++l) {
-    tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[l].p, m_ln1_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     e = epi_none();
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
     tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
@@ -849,8 +884,8 @@ void Engine::step_part_b(int n, bool marks) {
       launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), MATTN_THREADS, MATTN_SMEM, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
+    ln_after_next_gemm("mimi.layernorm", mx32.p, MR, MIMI_DIM, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     tag("mimi.out_proj"); gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);
-    tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = mffn16.p; e.out16_map = plain_map(MIMI_FFN);
     tag("mimi.linear1"); gemm_rows(mh16.p, MR, MIMI_DIM, m_lin1[l], MIMI_FFN, e);
@@ -860,6 +895,8 @@ void Engine::step_part_b(int n, bool marks) {
     if (last) {  // also emit the f16 operand of SEANet's first conv behind its 6 left-context rows
       e.out16 = tr16.p; e.out16_map = stream_map(16, 512, 22 * 512, 6 * 512);
     }
+    if (!last)
+      ln_after_next_gemm("mimi.layernorm", mx32.p, MR, MIMI_DIM, m_ln1_w[l + 1].p, m_ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
     tag("mimi.linear2"); gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
   }
   if (marks) PTTS_CUDA(cudaEventRecord(ev[3], ls));
@@ -980,6 +1017,8 @@ void Engine::run_step(int n) {
 }
 
 void Engine::prefill(int rows) {
+  ls = stream;
+  tag("flowlm.layernorm"); ln<D_MODEL>(px32.p, rows, ln1_w[0].p, ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, ph16.p, D_MODEL);
   flowlm_layers(rows, px32.p, ph16.p, pqkv32.p, pattn16.p, pffn16.p, true, pqrot.p, prow_seq.p, prow_pos.p);
 }
 
