@@ -353,8 +353,7 @@ __device__ __forceinline__ void fused_layernorm(const LnFuse& ln, int tid, int n
     atomicAdd(ln.counters, 1);
     unsigned spins = 0;
     while (*reinterpret_cast<volatile int*>(ln.counters) < n_ctas) {
-      __nanosleep(64);
-      if (++spins > (1u << 22)) {
+      if (++spins > (1u << 24)) {
         printf("ptts: fused-LN grid barrier timed out (%d of %d CTAs)\n", *reinterpret_cast<volatile int*>(ln.counters), n_ctas);
         __trap();
       }
