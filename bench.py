@@ -185,6 +185,7 @@ def run_gpu(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE {world}"
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -240,8 +241,11 @@ def run_gpu(args):
         launches = eng.launch_count()
         if world > 1:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # the job takes as long as its slowest GPU
             ms = float(t.item())
+            c = torch.tensor([launches], device="cuda", dtype=torch.int64)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            launches = int(c.item())
         return ms / steps, launches
 
     sampler = ClockSampler(local)
