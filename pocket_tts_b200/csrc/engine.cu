@@ -97,6 +97,8 @@ struct Engine {
   TmapCache tmaps;
   long long launches = 0;
   bool use_pdl = true;
+  int diag_skip = 0;
+  int persistent_ctas = 148;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
   struct ProfRec { const char* tag; const char* fn; cudaEvent_t a, b; double bytes, flops; };
@@ -545,8 +547,16 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   NB = c.max_batch > 0 ? std::min(c.max_batch, NS) : NS;
   KVCAP = c.kv_capacity > 0 ? c.kv_capacity : 1024;
   PR = 4096;
-  PTTS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  PTTS_CUDA(cudaStreamCreateWithFlags(&stream_b, cudaStreamNonBlocking));
+  {
+    // the language-model stream carries the AR critical path: give its CTAs first pick of free SMs; the codec
+    // stream fills what is left
+    int lo = 0, hi = 0;
+    PTTS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const bool prio = !(std::getenv("PTTS_PRIO") && std::atoi(std::getenv("PTTS_PRIO")) == 0);
+    PTTS_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio ? hi : lo));
+    PTTS_CUDA(cudaStreamCreateWithPriority(&stream_b, cudaStreamNonBlocking, lo));
+    if (const char* v = std::getenv("PTTS_B_SMS")) persistent_ctas = std::max(8, std::atoi(v));
+  }
   ls = stream;
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_a_done, cudaEventDisableTiming));
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_front_done, cudaEventDisableTiming));
@@ -563,6 +573,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   }
   if (const char* v = std::getenv("PTTS_FUSE_LN")) fuse_ln = std::atoi(v) != 0;   // tuning knobs, see DESIGN.md
   if (const char* v = std::getenv("PTTS_PDL")) use_pdl = std::atoi(v) != 0;
+  if (const char* v = std::getenv("PTTS_DIAG_SKIP")) diag_skip = std::atoi(v);  // 1: time path A alone, 2: path B alone
   load_weights(w, nw);
   compute_time_embeddings(1);
 
@@ -669,7 +680,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     }
     p.BN = bn;
     grid = dim3(act_tiles, (F + bn - 1) / bn, 1);
-    if (persistent) grid.x = std::min(act_tiles, std::max(1, 148 / (int)grid.y));
+    if (persistent) grid.x = std::min(act_tiles, std::max(1, persistent_ctas / (int)grid.y));
   }
   // Split-K whenever the output tiles alone cannot fill the chip (decode batches: 64 rows x F features is only
   // F/128 tiles): a cluster of `splits` CTAs along z shares one output tile (gemm.cuh), at most 8 (portable size).
@@ -996,13 +1007,13 @@ void Engine::run_step(int n) {
       sg.b = capture(stream_b, n, 1, &sg.kernels_b);
       it = graphs.emplace(key, sg).first;
     }
-    PTTS_CUDA(cudaGraphLaunch(it->second.a, stream));
+    if (diag_skip != 2) PTTS_CUDA(cudaGraphLaunch(it->second.a, stream));
     PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
     PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_a_done, 0));
     ls = stream_b;
-    step_front(n);
+    if (diag_skip != 1) step_front(n);
     PTTS_CUDA(cudaEventRecord(ev_front_done, stream_b));
-    PTTS_CUDA(cudaGraphLaunch(it->second.b, stream_b));
+    if (diag_skip != 1) PTTS_CUDA(cudaGraphLaunch(it->second.b, stream_b));
     launches += it->second.kernels_a + it->second.kernels_b;
   } else {
     ls = stream;
