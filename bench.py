@@ -349,7 +349,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=STREAMS,
+                    help="concurrent streams per GPU (default 64 = BASELINE configs[1]; 256/512 explore configs[3]/[4] shapes)")
     args = ap.parse_args()
+    if args.streams != STREAMS:
+        globals()["STREAMS"] = args.streams
+        CONFIG["streams_per_gpu"] = args.streams
+        CONFIG["workload"] = CONFIG["workload"].replace("batch 64", f"batch {args.streams} (non-headline size)")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -348,3 +348,42 @@ def test_continuous_batching_long_form():
         zero_mask = want == 0
         assert (pcm[zero_mask] == 0).all()
     voice.close()
+
+
+@pytest.mark.parametrize("n_streams", [130, 300])
+def test_large_ragged_batches_match_oracle(n_streams):
+    """Batch sizes beyond one MMA-N tile (130: two feature-side tiles with a ragged tail; 300: the FlowLM GEMMs move
+    to the activation-as-M tiling): a few probe streams inside the batch must still equal their own oracle runs."""
+    from oracle import ptts_oracle as O
+    from pocket_tts_b200.engine import Engine, StreamSpec
+    for e in _cache.values():
+        e[0].close()
+    _cache.clear()
+    wnp = synth.make_weights(1234)
+    W = O.to_torch(wnp)
+    eng = Engine(wnp, max_slots=n_streams, kv_capacity=64)
+    prompt = synth.make_voice_prompt(12, seed=2)
+    voice = eng.voice_from_prompt(prompt)
+    ov = O.voice_state_from_prompt(W, prompt)
+    frames = 2
+    specs = [StreamSpec(synth.make_tokens(3 + i % 5, seed=i), frames, 0, 1e30, noise=synth.make_noise(frames, seed=1000 + i))
+             for i in range(n_streams)]
+    probes = [0, n_streams // 2, n_streams - 1]
+    refs = {i: O.generate_segment(W, ov, specs[i].tokens, specs[i].noise, frames, 0, float("inf")) for i in probes}
+    slots = eng.open_streams([voice] * n_streams, specs)
+    lat, pcm = [], []
+    for f in range(frames):
+        if f:
+            for i in probes:
+                eng.set_feedback(int(slots[i]), refs[i]["latents"][f - 1])
+        p, fin, l, _ = eng.step(slots)
+        lat.append(l); pcm.append(p)
+    assert fin.all()
+    for i in probes:
+        got_lat = np.stack([lat[f][i] for f in range(frames)])
+        got_pcm = np.stack([pcm[f][i] for f in range(frames)])
+        assert np.abs(got_lat[0] - refs[i]["latents"][0]).max() <= LAT_TOL
+        assert np.abs(got_lat - refs[i]["latents"]).max() <= LAT_TOL
+        assert snr(refs[i]["pcm"], got_pcm) >= SNR_MIN
+    voice.close()
+    eng.close()
