@@ -1546,8 +1546,17 @@ int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_
   Weight16 w16; w16.F = feats; w16.K = k; w16.Fpad = round_up(feats, 128); w16.w.alloc((size_t)w16.Fpad * k);
   DevBuf<float> out; out.alloc((size_t)rows * feats);
   DevBuf<unsigned long long> tr; tr.alloc(16 * 65536);
+  DevBuf<__half> out16; out16.alloc((size_t)rows * feats);
+  DevBuf<float> resb; resb.alloc((size_t)rows * feats);
   GemmEpi ep = epi_none();
   ep.out32 = out.p; ep.out32_map = plain_map(feats);
+  if (mode >= 10) {  // SEANet-style epilogues: 10 = bias-free f32 + f16(ELU) dual output, 11 = residual in, f16(ELU) out
+    if (mode == 11) { ep.out32 = nullptr; ep.res = resb.p; ep.res_map = plain_map(feats); }
+    ep.out16 = out16.p; ep.out16_map = plain_map(feats); ep.act16 = ACT_ELU;
+    ep.bias = resb.p;  // any f32 vector of >= feats elements
+    mode = 1;
+  }
+  e.cfg.reserved[0] = mode;
   e.cfg.reserved[2] = split_k;
   e.gemm_trace = tr.p;
   for (int i = 0; i < 3; ++i) e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
@@ -1564,8 +1573,10 @@ int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_
   PTTS_CUDA(cudaMemcpy(h.data(), tr.p, h.size() * 8, cudaMemcpyDeviceToHost));
   unsigned long long t0 = ~0ull;
   int n = 0;
-  for (int c = 0; c < max_ctas; ++c) if (h[c * 16] != 0) { t0 = std::min(t0, h[c * 16]); n = c + 1; }
-  for (int c = 0; c < n; ++c) for (int j = 0; j < 10; ++j) stamps[c * 10 + j] = h[c * 16 + j] ? (int64_t)(h[c * 16 + j] - t0) : -1;
+  for (int c = 0; c < max_ctas; ++c) if (h[c * 16] != 0 && h[c * 16 + 12] == 0) { t0 = std::min(t0, h[c * 16]); n = c + 1; }
+  // persistent kernels stamp slot 12 first (entry of the epilogue warps)
+  if (t0 == ~0ull) { for (int c = 0; c < max_ctas; ++c) if (h[c * 16 + 12] != 0) { t0 = std::min(t0, h[c * 16 + 12]); n = c + 1; } }
+  for (int c = 0; c < n; ++c) for (int j = 0; j < 16; ++j) stamps[c * 16 + j] = h[c * 16 + j] ? (int64_t)(h[c * 16 + j] - t0) : -1;
   *n_ctas = n;
   cudaEventDestroy(a); cudaEventDestroy(b);
   return PTTS_OK;

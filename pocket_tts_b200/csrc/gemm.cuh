@@ -190,8 +190,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 // (pitch LD floats) in every CTA of the split-K cluster; CTA `rank` of `nsplit` owns rows rank*nwarps + warp,
 // stepping by nsplit*nwarps, sums them over the peers in rank order, applies the epilogue and writes V
 // consecutive features per lane, so each warp access is one contiguous 128-byte (V=1) or 512-byte (V=4) run.
+// Must inline into the kernel: `p` then stays in the constant bank.  Out of line, the by-reference parameter block
+// lives in local memory, and with a 200 KB shared-memory carve-out the remaining L1 cannot hold 384 threads' copies,
+// so every field access became an L2 round trip (measured: 6-11 us per 128-row tile instead of ~1 us).
 template <int V, int M>
-__device__ __noinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0,
+__device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0,
                                             int tid, int nthreads, int rank, int nsplit) {
   constexpr bool GEN = (M == EPI_GENERIC);
   const GemmEpi& e = p.epi;
@@ -636,9 +639,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
       const int as = j & 1;
       const int tb = tile / tiles_t;
       const int b0 = tb * p.G, t0 = (tile - tb * tiles_t) * p.R;
+      if (warp == 2 && j == 0) PTTS_TRACE(12);
       if (warp < 6) {
         mbar_wait(tfull_bar + as, (j >> 1) & 1);
         tc_fence_after();
+        if (warp == 2 && j < 3) PTTS_TRACE(j * 4 + 0);
         const int quad = warp & 3;
         const int i = quad * 32 + lane;
         for (int c = 0; c < p.BN; c += 16) {
@@ -654,12 +659,16 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar + as);  // TMEM buffer free: the MMAs of tile j+2 may start
+        if (warp == 2 && j < 3) PTTS_TRACE(j * 4 + 1);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // tile staged
+      if (warp == 2 && j < 3) PTTS_TRACE(j * 4 + 2);
       epi_dispatch(p, smem_u32(stile), LD, f0, t0, b0, etid, GEMM_THREADS - 64, 0, 1);
+      if (warp == 2 && j < 3) PTTS_TRACE(j * 4 + 3);
       asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // staging buffer free
     }
   }
+  if (warp == 2) PTTS_TRACE(13);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
