@@ -214,6 +214,70 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  // ---- fast path: one CTA per tile (no split-K) and every row of the tile in one stream, so each tensor's row
+  // offset is affine in the tile row; with <= 32 feature groups per row a lane keeps the same features for every
+  // row it visits, so bias / LayerScale are loaded once.  This is the path of the persistent SEANet kernels.
+  if (V == 4 && nsplit == 1 && (swap || G == 1) && fv <= 32) {
+    auto affine = [&](const RowMap& m, long long& off0) {  // offset of tile row 0; rows advance by m.ld
+      if (m.T == T && !swap) { off0 = static_cast<long long>(b0) * m.stream_stride + m.base + static_cast<long long>(t0) * m.ld; return true; }
+      if (m.T == 0x7fffffff) { off0 = m.base + static_cast<long long>(swap ? t0 : b0 * T + t0) * m.ld; return true; }
+      return false;
+    };
+    long long g0 = 0, r0 = 0, a0 = 0, h0 = 0;
+    const bool ok = (!has_gate || affine(e.gate_map, g0)) && (!has_res || affine(e.res_map, r0)) &&
+                    (!has_o32 || affine(e.out32_map, a0)) && (!has_o16 || affine(e.out16_map, h0));
+    if (ok) {
+      int nrows = min(tile_rows, T - t0);
+      if (!swap) nrows = min(nrows, R);
+      const int lanes_per_row = fv;  // 4..32, divides 32 when a power of two; otherwise the spare lanes idle
+      const int rows_per_iter = 32 / lanes_per_row;
+      const int my_sub = lane / lanes_per_row, q = lane - my_sub * lanes_per_row;
+      const int f = f0 + q * 4;
+      if (my_sub < rows_per_iter && f < F) {
+        float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f};
+        if (has_bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
+        if (has_fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
+        const int ld_g = e.gate_map.ld, ld_r = e.res_map.ld, ld_a = e.out32_map.ld, ld_h = e.out16_map.ld;
+        const float* gate_p = has_gate ? e.gate + g0 + f : nullptr;
+        const float* res_p = has_res ? e.res + r0 + f : nullptr;
+        float* o32_p = has_o32 ? e.out32 + a0 + f : nullptr;
+        __half* o16_p = has_o16 ? e.out16 + h0 + f : nullptr;
+        const int step = nwarps * rows_per_iter;
+        for (int row = warp * rows_per_iter + my_sub; row < nrows; row += step) {
+          float4 a4;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
+                       : "r"(stile_addr + static_cast<uint32_t>(row * LD + q * 4) * 4u));
+          float v[4] = {a4.x, a4.y, a4.z, a4.w};
+          float gv[4], rv[4];
+          if (has_gate) { const float4 t4 = *reinterpret_cast<const float4*>(gate_p + static_cast<long long>(row) * ld_g); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
+          if (has_res) { const float4 t4 = *reinterpret_cast<const float4*>(res_p + static_cast<long long>(row) * ld_r); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float x = v[c];
+            if (has_bias) x += bv[c];
+            x = epi_act(act, x) * alpha;
+            if (has_fscale) x *= sv[c];
+            if (has_gate) x *= gv[c];
+            if (has_res) x += rv[c];
+            v[c] = x;
+          }
+          if (has_o32) *reinterpret_cast<float4*>(o32_p + static_cast<long long>(row) * ld_a) = make_float4(v[0], v[1], v[2], v[3]);
+          if (has_o16) {
+            if (elu16) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) v[c] = elu1_fast(v[c]);
+            }
+            const __half2 h0v = __floats2half2_rn(v[0], v[1]), h1v = __floats2half2_rn(v[2], v[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&h0v);
+            pk.y = *reinterpret_cast<const uint32_t*>(&h1v);
+            *reinterpret_cast<uint2*>(o16_p + static_cast<long long>(row) * ld_h) = pk;
+          }
+        }
+      }
+      return;
+    }
+  }
   uint32_t peer[GEMM_MAX_SPLIT];
 #pragma unroll
   for (int k = 0; k < GEMM_MAX_SPLIT; ++k) peer[k] = (nsplit > 1 && k < nsplit) ? map_to_rank(stile_addr, k) : stile_addr;
