@@ -234,7 +234,8 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
       const int my_sub = lane / lanes_per_row, q = lane - my_sub * lanes_per_row;
       const int f = f0 + q * 4;
       if (my_sub < rows_per_iter && f < F) {
-        float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f};
+        float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f}, wv[4] = {1.f, 1.f, 1.f, 1.f};
+        if (GEN && wscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(wscale + f)); wv[0] = t4.x; wv[1] = t4.y; wv[2] = t4.z; wv[3] = t4.w; }
         if (has_bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
         if (has_fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
         const int ld_g = e.gate_map.ld, ld_r = e.res_map.ld, ld_a = e.out32_map.ld, ld_h = e.out16_map.ld;
@@ -254,6 +255,7 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float x = v[c];
+            if (GEN && wscale) x *= wv[c];
             if (has_bias) x += bv[c];
             x = epi_act(act, x) * alpha;
             if (has_fscale) x *= sv[c];
