@@ -214,10 +214,10 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  // ---- fast path: one CTA per tile (no split-K) and every row of the tile in one stream, so each tensor's row
+  // ---- fast path: every row of the tile in one stream, so each tensor's row
   // offset is affine in the tile row; with <= 32 feature groups per row a lane keeps the same features for every
   // row it visits, so bias / LayerScale are loaded once.  This is the path of the persistent SEANet kernels.
-  if (V == 4 && nsplit == 1 && (swap || G == 1) && fv <= 32) {
+  if (V == 4 && (swap || G == 1) && fv <= 32) {
     auto affine = [&](const RowMap& m, long long& off0) {  // offset of tile row 0; rows advance by m.ld
       if (m.T == T && !swap) { off0 = static_cast<long long>(b0) * m.stream_stride + m.base + static_cast<long long>(t0) * m.ld; return true; }
       if (m.T == 0x7fffffff) { off0 = m.base + static_cast<long long>(swap ? t0 : b0 * T + t0) * m.ld; return true; }
@@ -243,11 +243,25 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
         const float* res_p = has_res ? e.res + r0 + f : nullptr;
         float* o32_p = has_o32 ? e.out32 + a0 + f : nullptr;
         __half* o16_p = has_o16 ? e.out16 + h0 + f : nullptr;
-        const int step = nwarps * rows_per_iter;
-        for (int row = warp * rows_per_iter + my_sub; row < nrows; row += step) {
+        uint32_t peer[GEMM_MAX_SPLIT];
+#pragma unroll
+        for (int k = 0; k < GEMM_MAX_SPLIT; ++k) peer[k] = (nsplit > 1 && k < nsplit) ? map_to_rank(stile_addr, k) : stile_addr;
+        const int step = nwarps * nsplit * rows_per_iter;
+        for (int row = (rank * nwarps + warp) * rows_per_iter + my_sub; row < nrows; row += step) {
+          const uint32_t toff = static_cast<uint32_t>(row * LD + q * 4) * 4u;
           float4 a4;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w)
-                       : "r"(stile_addr + static_cast<uint32_t>(row * LD + q * 4) * 4u));
+          if (nsplit == 1) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(stile_addr + toff));
+          } else {  // split-K: sum the cluster's partial tiles in rank order (bit-reproducible)
+            float4 t[GEMM_MAX_SPLIT];
+#pragma unroll
+            for (int k = 0; k < GEMM_MAX_SPLIT; ++k)
+              if (k < nsplit) t[k] = ld_dsmem_f4(peer[k] + toff);
+            a4 = t[0];
+#pragma unroll
+            for (int k = 1; k < GEMM_MAX_SPLIT; ++k)
+              if (k < nsplit) { a4.x += t[k].x; a4.y += t[k].y; a4.z += t[k].z; a4.w += t[k].w; }
+          }
           float v[4] = {a4.x, a4.y, a4.z, a4.w};
           float gv[4], rv[4];
           if (has_gate) { const float4 t4 = *reinterpret_cast<const float4*>(gate_p + static_cast<long long>(row) * ld_g); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
