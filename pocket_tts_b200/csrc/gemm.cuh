@@ -529,25 +529,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) PTTS_TRACE(1);
-  pdl_wait();  // nothing above reads or writes memory another kernel produces
 
   if (warp == 0) {
     // ===== TMA producer =====
+    // Weights are constants, so their tiles for the first stages are requested BEFORE griddepcontrol.wait: the HBM
+    // fetch of this GEMM's weights overlaps the tail of the kernel it depends on, and only the (L2-resident)
+    // activation tiles remain on the critical path once the dependency resolves.
     if (elect_one()) {
       const uint32_t act_bytes = p.swap ? n_tile_bytes : (GEMM_BK * p.R * p.G * 2);
       const uint32_t w_bytes = p.swap ? m_tile_bytes : n_tile_bytes;
+      const int npre = min(nkb, p.stages);
+      for (int i = 0; i < npre; ++i) {
+        uint8_t* m_tile = smem + i * stage_bytes;
+        mbar_arrive_expect_tx(full_bar + i, act_bytes + w_bytes);
+        tma_load_3d(p.swap ? m_tile : m_tile + m_tile_bytes, &map_w, full_bar + i, (kb0 + i) * GEMM_BK, f0, 0);
+      }
+      pdl_wait();
       for (int i = 0; i < nkb; ++i) {
         const int s = i % p.stages;
-        const uint32_t ph = (i / p.stages) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
         const int kb = kb0 + i;
         const int tap = kb / p.cblocks;
         const int c0 = (kb - tap * p.cblocks) * GEMM_BK;
         uint8_t* m_tile = smem + s * stage_bytes;
         uint8_t* n_tile = m_tile + m_tile_bytes;
-        mbar_arrive_expect_tx(full_bar + s, act_bytes + w_bytes);
+        if (i >= npre) {
+          const uint32_t ph = (i / p.stages) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_arrive_expect_tx(full_bar + s, act_bytes + w_bytes);
+          tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
+        }
         tma_load_3d(p.swap ? n_tile : m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
-        tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
         if (i == 0) PTTS_TRACE(2);
       }
       PTTS_TRACE(3);
@@ -610,6 +621,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (nsplit > 1) cluster_sync_all();  // all partial tiles are staged and visible cluster-wide
+  pdl_wait();  // residual / gate / output tensors belong to earlier kernels until they have completed
   epi_dispatch(p, smem_u32(smem), (p.swap ? GEMM_BM : p.BN) + 4, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
   if (warp == 2) PTTS_TRACE(8);
   if (nsplit > 1) cluster_sync_all();  // peers may still be reading this CTA's tile
@@ -668,24 +680,33 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
       const uint32_t bytes = GEMM_BK * p.R * p.G * 2 + n_tile_bytes;
+      // the weight tiles of the first stages do not depend on the previous kernel: request them before the wait
+      const int total_it = ((p.n_act_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)) * nkb;
+      const int npre = min(total_it, p.stages);
+      for (int i = 0; i < npre; ++i) {
+        mbar_arrive_expect_tx(full_bar + i, bytes);
+        tma_load_3d(smem + i * stage_bytes + m_tile_bytes, &map_w, full_bar + i, (i % nkb) * GEMM_BK, f0, 0);
+      }
+      pdl_wait();
       int it = 0;
       for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x) {
         const int tb = tile / tiles_t;
         const int b0 = tb * p.G, t0 = (tile - tb * tiles_t) * p.R;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % p.stages;
-          mbar_wait(empty_bar + s, ((it / p.stages) & 1) ^ 1);
           const int tap = kb / p.cblocks;
           const int c0 = (kb - tap * p.cblocks) * GEMM_BK;
           uint8_t* m_tile = smem + s * stage_bytes;
-          mbar_arrive_expect_tx(full_bar + s, bytes);
+          if (it >= npre) {
+            mbar_wait(empty_bar + s, ((it / p.stages) & 1) ^ 1);
+            mbar_arrive_expect_tx(full_bar + s, bytes);
+            tma_load_3d(m_tile + m_tile_bytes, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
+          }
           tma_load_3d(m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
-          tma_load_3d(m_tile + m_tile_bytes, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
         }
       }
     }
@@ -714,6 +735,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
     }
   } else {
     const int etid = threadIdx.x - 64;
+    pdl_wait();  // epilogue tensors (residual, outputs) belong to earlier kernels until they have completed
     int j = 0;
     for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x, ++j) {
       const int as = j & 1;
