@@ -372,7 +372,7 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __r
 static constexpr int MATTN_THREADS = 256;
 static constexpr int MATTN_SW = MIMI_RING + 8;
 static constexpr int MATTN_SMEM = (16 * HD + 16 * MATTN_SW + 16 + 8 * 16 * HD) * 4;
-__global__ void __launch_bounds__(MATTN_THREADS)
+__global__ void __launch_bounds__(MATTN_THREADS, 3)
 mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
                  const int* __restrict__ mimi_pos, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/, int layer,
                  int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
