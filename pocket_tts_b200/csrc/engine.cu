@@ -107,12 +107,10 @@ struct Engine {
   std::vector<cudaEvent_t> prof_pool;
   const char* cur_tag = nullptr;
   unsigned long long* gemm_trace = nullptr;
-  // LayerNorm requested behind the next GEMM (fused into it when its grid is small enough, else a separate launch)
+  // LayerNorm requested behind the next GEMM (its own launch; a grid-barrier fusion measured -3% and was removed)
   struct LnSpec { bool set = false; const float* x; int rows, C; const float* w; const float* b; float eps; const float* shift;
                   const float* scale; int mod_ld; __half* out; int out_ld; const char* tag; };
   LnSpec next_ln;
-  DevBuf<int> ln_counters;  // [4]: arrive/depart for stream A, for stream B
-  bool fuse_ln = false;  // measured on B200: 22 fewer launches but -3% throughput (barrier + 1 row per CTA); PTTS_FUSE_LN=1 enables
   void ln_after_next_gemm(const char* tag, const float* x, int rows, int C, const float* w, const float* b, float eps,
                           const float* shift, const float* scale, int mod_ld, __half* out, int out_ld) {
     next_ln = LnSpec{true, x, rows, C, w, b, eps, shift, scale, mod_ld, out, out_ld, tag};
@@ -571,7 +569,6 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     for (int i = 0; i < HD / 2; ++i) inv[i] = std::exp((float)i * cst);
     PTTS_CUDA(cudaMemcpyToSymbol(c_inv_freq, inv, sizeof inv));
   }
-  if (const char* v = std::getenv("PTTS_FUSE_LN")) fuse_ln = std::atoi(v) != 0;   // tuning knobs, see DESIGN.md
   if (const char* v = std::getenv("PTTS_PDL")) use_pdl = std::atoi(v) != 0;
   if (const char* v = std::getenv("PTTS_DIAG_SKIP")) diag_skip = std::atoi(v);  // 1: time path A alone, 2: path B alone
   load_weights(w, nw);
@@ -692,24 +689,12 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   if (!persistent && total_kb >= 4) {
     while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= 132 && splits * 2 <= total_kb / 2) splits *= 2;
   }
-  // A fused LayerNorm needs every CTA resident while it spins on the grid barrier, and both step streams may run such
-  // a GEMM at once: keep each at <= 64 CTAs (2 x 64 < 148 SMs) or fall back to a separate LayerNorm launch.
   const LnSpec lnreq = next_ln;
   next_ln.set = false;
-  bool ln_fused = false;
-  if (lnreq.set && fuse_ln && !persistent && !cfg.debug_gemm && !profiling) {
-    while (splits > 1 && tiles * splits > 64) splits /= 2;
-    ln_fused = tiles * splits <= 64;
-  }
   if (cfg.reserved[2] > 0 && !persistent) splits = std::min(cfg.reserved[2], std::min(total_kb, GEMM_MAX_SPLIT));  // test hook
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.epi_mask = epi_mask_of(p.epi);
-  if (ln_fused) {
-    if (!ln_counters.p) ln_counters.alloc(4);
-    p.ln = LnFuse{lnreq.x, lnreq.w, lnreq.b, lnreq.shift, lnreq.scale, lnreq.out, ln_counters.p + (ls == stream_b ? 2 : 0),
-                  lnreq.rows, lnreq.C, lnreq.mod_ld, lnreq.out_ld, lnreq.eps, 1};
-  }
   grid.z = splits;
   const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : 200) * 1024LL;  // one CTA per SM
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
@@ -752,7 +737,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     }
     PTTS_CUDA(cudaGetLastError());
   }
-  if (lnreq.set && !ln_fused) {  // grid too large to fuse (prefill, profiling pass): the norm is its own launch
+  if (lnreq.set) {
     tag(lnreq.tag);
     if (lnreq.C == 1024) ln<1024>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);
     else ln<512>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);

@@ -62,22 +62,6 @@ struct GemmEpi {
   const float* wscale;  // [F] int8 mode: weight-code scale applied to the accumulator first, else null
 };
 
-// LayerNorm of the f32 tensor this GEMM just finished writing (its out32), fused behind a grid-wide barrier so the
-// norm in front of the next GEMM costs no launch: out[r,:] = LN(x[r,:]) [*w+b] [*(1+scale[r,:])+shift[r,:]] as f16
-// (reference modules/mlp.rs:29-58,135-137).  Every CTA of the grid is resident (host guarantees <= 64 CTAs).
-struct LnFuse {
-  const float* x;
-  const float* w;
-  const float* b;
-  const float* shift;
-  const float* scale;
-  __half* out;
-  int* counters;   // [2] arrive / depart, zero between launches
-  int rows, C, mod_ld, out_ld;
-  float eps;
-  int enabled;
-};
-
 struct GemmParams {
   int swap;
   int F, K;
@@ -91,7 +75,6 @@ struct GemmParams {
   int epi_mask;             // epi_mask_of(epi): selects the compiled store loop
   int n_act_tiles;          // activation tiles in total (persistent kernel walks them with stride gridDim.x)
   GemmEpi epi;
-  LnFuse ln;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
   long long act_stream_stride;
@@ -386,76 +369,6 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
   }
 }
 
-// One row by one warp, two passes over registers (mean, then centred sum of squares), L2 loads: the row was written
-// by other SMs of this very launch.
-template <int C>
-__device__ __forceinline__ void ln_row_warp(const LnFuse& ln, int row, int lane) {
-  constexpr int PER = C / 32;
-  const float4* xr = reinterpret_cast<const float4*>(ln.x + static_cast<long long>(row) * C);
-  float v[PER];
-#pragma unroll
-  for (int i = 0; i < PER / 4; ++i) {
-    const float4 t = __ldcg(xr + i * 32 + lane);
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.f / C);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; q += d * d; }
-  const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / C) + ln.eps);
-#pragma unroll
-  for (int i = 0; i < PER / 4; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    float o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float y = (v[4 * i + j] - mean) * rstd;
-      if (ln.w) y = y * __ldg(ln.w + c + j) + __ldg(ln.b + c + j);
-      if (ln.scale) y = y * (1.f + __ldcg(ln.scale + static_cast<long long>(row) * ln.mod_ld + c + j)) +
-                        __ldcg(ln.shift + static_cast<long long>(row) * ln.mod_ld + c + j);
-      o[j] = y;
-    }
-    const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<const uint32_t*>(&h0);
-    pk.y = *reinterpret_cast<const uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(ln.out + static_cast<long long>(row) * ln.out_ld + c) = pk;
-  }
-}
-
-// Grid-wide barrier (all CTAs resident) followed by the fused LayerNorm; rows are dealt to (CTA, warp) pairs.
-__device__ __forceinline__ void fused_layernorm(const LnFuse& ln, int tid, int nthreads) {
-  const int n_ctas = gridDim.x * gridDim.y * gridDim.z;
-  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    atomicAdd(ln.counters, 1);
-    unsigned spins = 0;
-    while (*reinterpret_cast<volatile int*>(ln.counters) < n_ctas) {
-      if (++spins > (1u << 24)) {
-        printf("ptts: fused-LN grid barrier timed out (%d of %d CTAs)\n", *reinterpret_cast<volatile int*>(ln.counters), n_ctas);
-        __trap();
-      }
-    }
-    __threadfence();
-    if (atomicAdd(ln.counters + 1, 1) == n_ctas - 1) {  // last one out re-arms the barrier for the next launch
-      ln.counters[0] = 0;
-      ln.counters[1] = 0;
-      __threadfence();
-    }
-  }
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  for (int row = cta + warp * n_ctas; row < ln.rows; row += n_ctas * nwarps) {
-    if (ln.C == 1024) ln_row_warp<1024>(ln, row, lane);
-    else ln_row_warp<512>(ln, row, lane);
-  }
-}
-
 __device__ __forceinline__ void epi_dispatch(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0, int tid,
                                              int nthreads, int rank, int nsplit) {
   if (!p.vec4) {
@@ -626,7 +539,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   if (warp == 2) PTTS_TRACE(8);
   if (nsplit > 1) cluster_sync_all();  // peers may still be reading this CTA's tile
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
-  if (p.ln.enabled) fused_layernorm(p.ln, threadIdx.x, GEMM_THREADS);
   if (warp == 1) PTTS_TRACE(9);
 }
 

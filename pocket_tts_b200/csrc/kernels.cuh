@@ -364,32 +364,56 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __r
 
 // Mimi decoder-transformer attention: 16 new rows per stream, sliding window of 250 positions
 // (reference attention.rs:167-264 ring + sdpa.rs:129-171 mask: query at position p sees keys in (p-250, p]).
-// K,V live in a per-slot ring indexed by position % 272; 272 >= 250 + 15 so the 16 rows written first never
-// overwrite a key that a query of this step still needs.  grid (n, 8 heads), block 256, dynamic smem.
-//   scores  one key per thread (row in registers via 8 x 16-byte loads) against the 16 queries in smem
-//   P V     a warp takes keys w, w+8, ...; each lane owns 2 of the 64 dims for all 16 queries; the 8 warps'
-//           partial sums are folded in warp order (bit-reproducible)
-static constexpr int MATTN_THREADS = 256;
-static constexpr int MATTN_SW = MIMI_RING + 8;
-static constexpr int MATTN_SMEM = (16 * HD + 16 * MATTN_SW + 16 + 8 * 16 * HD) * 4;
+// Per slot, layer and head the ring holds K as [272][64] and V transposed as [64][272], both f16, indexed by
+// position % 272.  272 = 17 blocks of 16 and every frame's 16 rows fill exactly one block, so the block written first
+// is the one whose keys fell out of every window of this frame.
+// grid (n, 8 heads), block 192: the 16 queries are exactly one m16n8k16 tile.  Warp w takes ring blocks w, w+6, w+12
+// (16 keys each) and runs S = Q K^T and O = P V on mma.sync with every operand fragment loaded straight from HBM in
+// 16/32-byte pieces: both products sum over an index whose order is free, so the K rows are read with the head dim
+// permuted (lane c of a quad owns dims 16c..16c+15 for all four k-steps) and the S columns are assigned to keys so
+// that a lane ends up with four consecutive keys (4c..4c+3), which is one 8-byte load per dim of the transposed V.
+// The six warps' partial (max, sum, O) are merged in warp order (bit-reproducible).
+static constexpr int MATTN_THREADS = 192;
+static constexpr int MATTN_WARPS = MATTN_THREADS / 32;
+static constexpr int MATTN_BLOCKS = MIMI_RING / 16;  // 17
+static constexpr int MATTN_QP = HD + 8;              // q16 pitch (halves)
+static constexpr int MATTN_VP = 24;                  // new-V transpose pitch (halves), 16-byte aligned rows
+static constexpr int MATTN_OP = HD + 4;              // partial-O pitch (floats)
+static constexpr int MATTN_SMEM = 16 * MATTN_QP * 2 + HD * MATTN_VP * 2 + MATTN_WARPS * 16 * (MATTN_OP + 2) * 4;
+
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                             uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 __global__ void __launch_bounds__(MATTN_THREADS, 3)
 mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
-                 const int* __restrict__ mimi_pos, __half* __restrict__ ring /*[slots][layer][2][8][272][64]*/, int layer,
-                 int n_layers, __half* __restrict__ out16 /*[n*16, 512]*/) {
+                 const int* __restrict__ mimi_pos, __half* ring /*[slots][layer][k|v][8][272*64]*/, int layer, int n_layers,
+                 __half* __restrict__ out16 /*[n*16, 512]*/) {
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int NH = 8, DM = 512, T = 16, SW = MATTN_SW, NW = MATTN_THREADS / 32;
-  extern __shared__ float msm[];
-  float (*q_s)[HD] = reinterpret_cast<float (*)[HD]>(msm);                       // [16][64]
-  float (*p_s)[SW] = reinterpret_cast<float (*)[SW]>(msm + T * HD);              // [16][280]
-  float* inv_s = msm + T * HD + T * SW;                                          // [16]
-  float* red_s = inv_s + 16;                                                     // [8][16][64]
+  constexpr int NH = 8, DM = 512, T = 16, NW = MATTN_WARPS;
+  constexpr float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) and log2(e): softmax in base 2
+  extern __shared__ __align__(16) unsigned char msm_raw[];
+  __half* q16 = reinterpret_cast<__half*>(msm_raw);                      // [16][72]
+  __half* vt_s = q16 + 16 * MATTN_QP;                                    // [64][24]
+  float* o_s = reinterpret_cast<float*>(vt_s + HD * MATTN_VP);           // [6][16][68]
+  float* m_s = o_s + NW * 16 * MATTN_OP;                                 // [6][16]
+  float* l_s = m_s + NW * 16;                                            // [6][16]
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
   const int slot = row_seq[b];
-  const int p0 = mimi_pos[b];  // absolute position of the first new row
+  const int p0 = mimi_pos[b];  // absolute position of the first new row (multiple of 16)
   __half* kring = ring + ((static_cast<long long>(slot) * n_layers + layer) * 2 * NH + h) * MIMI_RING * HD;
-  __half* vring = kring + static_cast<long long>(NH) * MIMI_RING * HD;
-  // RoPE + ring write: 16 rows x 32 pairs = 512 items
+  __half* vring = kring + static_cast<long long>(NH) * MIMI_RING * HD;  // [64][272]
+  const int blk0 = (p0 >> 4) % MATTN_BLOCKS;                              // ring block of the new rows
+  // RoPE, K ring rows, q (f16) and the new V rows transposed through smem: 16 rows x 32 pairs
   for (int it = tid; it < T * 32; it += MATTN_THREADS) {
     const int t = it >> 5, i = it & 31;
     const float* row = qkv + (static_cast<long long>(b) * T + t) * 3 * DM;
@@ -399,101 +423,141 @@ mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __re
     float qr, qi, kr, ki;
     rope_pair(qx.x, qx.y, p0 + t, i, qr, qi);
     rope_pair(kx.x, kx.y, p0 + t, i, kr, ki);
-    q_s[t][2 * i] = qr;
-    q_s[t][2 * i + 1] = qi;
-    const int ri = (p0 + t) % MIMI_RING;
-    reinterpret_cast<__half2*>(kring + ri * HD)[i] = __floats2half2_rn(kr, ki);
-    reinterpret_cast<__half2*>(vring + ri * HD)[i] = __floats2half2_rn(vx.x, vx.y);
+    reinterpret_cast<__half2*>(q16 + t * MATTN_QP)[i] = __floats2half2_rn(qr, qi);
+    reinterpret_cast<__half2*>(kring + (blk0 * 16 + t) * HD)[i] = __floats2half2_rn(kr, ki);
+    vt_s[(2 * i) * MATTN_VP + t] = __float2half_rn(vx.x);
+    vt_s[(2 * i + 1) * MATTN_VP + t] = __float2half_rn(vx.y);
   }
   __syncthreads();
-  // keys: positions [kmin, p0+15]; the window of the first query starts at p0-249
-  const int kmin = max(0, p0 - (MIMI_CTX - 1));
-  const int nk = p0 + T - kmin;  // <= 265
-  for (int j = tid; j < nk; j += MATTN_THREADS) {
-    const int kp = kmin + j;
-    const uint4* kr = reinterpret_cast<const uint4*>(kring + (kp % MIMI_RING) * HD);
-    uint4 u[8];
+  if (tid < 2 * HD) {
+    const int d = tid >> 1, hf = tid & 1;
+    *reinterpret_cast<uint4*>(vring + d * MIMI_RING + blk0 * 16 + 8 * hf) = *reinterpret_cast<const uint4*>(vt_s + d * MATTN_VP + 8 * hf);
+  }
+  // q fragments: rows g and g+8, dims 16c..16c+15 (the permuted k index, see above)
+  uint32_t qa[8], qb[8];
+  {
+    const uint4 a0 = *reinterpret_cast<const uint4*>(q16 + g * MATTN_QP + 16 * c);
+    const uint4 a1 = *reinterpret_cast<const uint4*>(q16 + g * MATTN_QP + 16 * c + 8);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(q16 + (g + 8) * MATTN_QP + 16 * c);
+    const uint4 b1 = *reinterpret_cast<const uint4*>(q16 + (g + 8) * MATTN_QP + 16 * c + 8);
+    qa[0] = a0.x; qa[1] = a0.y; qa[2] = a0.z; qa[3] = a0.w; qa[4] = a1.x; qa[5] = a1.y; qa[6] = a1.z; qa[7] = a1.w;
+    qb[0] = b0.x; qb[1] = b0.y; qb[2] = b0.z; qb[3] = b0.w; qb[4] = b1.x; qb[5] = b1.y; qb[6] = b1.z; qb[7] = b1.w;
+  }
+  __syncthreads();  // the new K / V rows are visible to the whole CTA
+  // this warp's ring blocks and the position of their first key; a block that was never written has posb < 0
+  int blk[3], posb[3];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) u[c] = kr[c];
-    float kf[HD];
+  for (int u = 0; u < 3; ++u) {
+    blk[u] = warp + u * NW;
+    posb[u] = (blk[u] < MATTN_BLOCKS) ? p0 - 16 * ((blk0 - blk[u] + MATTN_BLOCKS) % MATTN_BLOCKS) : -1;
+  }
+  // K fragments of all three blocks in flight at once: n-tile t of a block, column g  <->  key 4*(g/2) + 2t + (g%2)
+  uint4 kf[3][2][2];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const __half2* hh = reinterpret_cast<const __half2*>(&u[c]);
+  for (int u = 0; u < 3; ++u)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      if (posb[u] >= 0) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kring + (blk[u] * 16 + 4 * (g >> 1) + 2 * t + (g & 1)) * HD + 16 * c);
+        kf[u][t][0] = kr[0];
+        kf[u][t][1] = kr[1];
+      } else {
+        kf[u][t][0] = kf[u][t][1] = make_uint4(0, 0, 0, 0);
+      }
+    }
+  float sacc[3][2][4];
+#pragma unroll
+  for (int u = 0; u < 3; ++u)
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      sacc[u][t][0] = sacc[u][t][1] = sacc[u][t][2] = sacc[u][t][3] = 0.f;
+      const uint32_t kk[8] = {kf[u][t][0].x, kf[u][t][0].y, kf[u][t][0].z, kf[u][t][0].w,
+                              kf[u][t][1].x, kf[u][t][1].y, kf[u][t][1].z, kf[u][t][1].w};
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) mma_m16n8k16(sacc[u][t], qa[2 * s4], qb[2 * s4], qa[2 * s4 + 1], qb[2 * s4 + 1], kk[2 * s4], kk[2 * s4 + 1]);
+    }
+  // V fragments (issued before the softmax arithmetic): dim nt*8+g, keys 4c..4c+3 of the block
+  uint2 vf[3][8];
+#pragma unroll
+  for (int u = 0; u < 3; ++u)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+      vf[u][nt] = (posb[u] >= 0) ? *reinterpret_cast<const uint2*>(vring + (nt * 8 + g) * MIMI_RING + blk[u] * 16 + 4 * c) : make_uint2(0, 0);
+  // mask, row maxima and sums over this warp's 48 keys; rows g (index 0) and g+8 (index 1)
+  float mrow[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int u = 0; u < 3; ++u)
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(hh[e]);
-        kf[c * 8 + 2 * e] = f.x;
-        kf[c * 8 + 2 * e + 1] = f.y;
+        const int kp = posb[u] + 4 * c + 2 * t + (e & 1);
+        const int qp = p0 + g + 8 * (e >> 1);
+        const bool ok = (posb[u] >= 0) && (kp <= qp) && (kp > qp - MIMI_CTX);
+        const float sv = ok ? sacc[u][t][e] * kScale : -INFINITY;
+        sacc[u][t][e] = sv;
+        mrow[e >> 1] = fmaxf(mrow[e >> 1], sv);
       }
-    }
-#pragma unroll 2
-    for (int t = 0; t < T; ++t) {
-      const int qp = p0 + t;
-      float acc = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; d += 4) {
-        const float4 q4 = *reinterpret_cast<const float4*>(&q_s[t][d]);
-        acc += kf[d] * q4.x + kf[d + 1] * q4.y + kf[d + 2] * q4.z + kf[d + 3] * q4.w;
-      }
-      const bool ok = (kp <= qp) && (kp > qp - MIMI_CTX);
-      p_s[t][j] = ok ? acc * 0.125f : -INFINITY;
-    }
+  for (int r = 0; r < 2; ++r) {
+    mrow[r] = fmaxf(mrow[r], __shfl_xor_sync(0xffffffffu, mrow[r], 1));
+    mrow[r] = fmaxf(mrow[r], __shfl_xor_sync(0xffffffffu, mrow[r], 2));
   }
-  __syncthreads();
-  // softmax per query row: warp w owns rows 2w, 2w+1
-  for (int t = warp * 2; t < warp * 2 + 2; ++t) {
-    float m = -INFINITY;
-    for (int j = lane; j < nk; j += 32) m = fmaxf(m, p_s[t][j]);
-    m = warp_max(m);
-    float sacc = 0.f;
-    for (int j = lane; j < nk; j += 32) {
-      const float p = expf(p_s[t][j] - m);
-      p_s[t][j] = p;
-      sacc += p;
-    }
-    sacc = warp_sum(sacc);
-    if (lane == 0) inv_s[t] = 1.f / sacc;
-  }
-  __syncthreads();
-  // P V
-  float acc[T][2];
+  const float muse[2] = {mrow[0] == -INFINITY ? 0.f : mrow[0], mrow[1] == -INFINITY ? 0.f : mrow[1]};
+  float lrow[2] = {0.f, 0.f};
+  float oacc[8][4];
 #pragma unroll
-  for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = 0.f;
-  for (int j0 = warp; j0 < nk; j0 += NW * 4) {
-    float2 f[4];
+  for (int nt = 0; nt < 8; ++nt) oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {  // four independent loads in flight
-      const int j = j0 + u * NW;
-      f[u] = (j < nk) ? __half22float2(reinterpret_cast<const __half2*>(vring + ((kmin + j) % MIMI_RING) * HD)[lane])
-                      : make_float2(0.f, 0.f);
-    }
+  for (int u = 0; u < 3; ++u) {
+    float pv[2][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * NW;
-      if (j < nk) {
+    for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          const float p = p_s[t][j];
-          acc[t][0] += p * f[u].x;
-          acc[t][1] += p * f[u].y;
-        }
+      for (int e = 0; e < 4; ++e) {
+        pv[t][e] = exp2f(sacc[u][t][e] - muse[e >> 1]);
+        lrow[e >> 1] += pv[t][e];
       }
-    }
+    const uint32_t a0 = pack_half2(pv[0][0], pv[0][1]), a1 = pack_half2(pv[0][2], pv[0][3]);
+    const uint32_t a2 = pack_half2(pv[1][0], pv[1][1]), a3 = pack_half2(pv[1][2], pv[1][3]);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) mma_m16n8k16(oacc[nt], a0, a1, a2, a3, vf[u][nt].x, vf[u][nt].y);
   }
 #pragma unroll
-  for (int t = 0; t < T; ++t) *reinterpret_cast<float2*>(red_s + (warp * T + t) * HD + 2 * lane) = make_float2(acc[t][0], acc[t][1]);
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+  if (c == 0) {
+    m_s[warp * 16 + g] = mrow[0];
+    m_s[warp * 16 + g + 8] = mrow[1];
+    l_s[warp * 16 + g] = lrow[0];
+    l_s[warp * 16 + g + 8] = lrow[1];
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    *reinterpret_cast<float2*>(o_s + (warp * 16 + g) * MATTN_OP + nt * 8 + 2 * c) = make_float2(oacc[nt][0], oacc[nt][1]);
+    *reinterpret_cast<float2*>(o_s + (warp * 16 + g + 8) * MATTN_OP + nt * 8 + 2 * c) = make_float2(oacc[nt][2], oacc[nt][3]);
+  }
   __syncthreads();
+  // merge the six partials in warp order; every query sees at least its own key, so the sum is positive
   for (int o = tid; o < T * 32; o += MATTN_THREADS) {
     const int t = o >> 5, i = o & 31;
-    float sx = 0.f, sy = 0.f;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mx = fmaxf(mx, m_s[w * 16 + t]);
+    float sx = 0.f, sy = 0.f, den = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-      const float2 v = *reinterpret_cast<const float2*>(red_s + (w * T + t) * HD + 2 * i);
-      sx += v.x;
-      sy += v.y;
+      const float mw = m_s[w * 16 + t];
+      const float f = (mw == -INFINITY) ? 0.f : exp2f(mw - mx);
+      const float2 v = *reinterpret_cast<const float2*>(o_s + (w * 16 + t) * MATTN_OP + 2 * i);
+      sx += f * v.x;
+      sy += f * v.y;
+      den += f * l_s[w * 16 + t];
     }
-    reinterpret_cast<__half2*>(out16 + (static_cast<long long>(b) * T + t) * DM + h * HD)[i] =
-        __floats2half2_rn(sx * inv_s[t], sy * inv_s[t]);
+    const float inv = 1.f / den;
+    reinterpret_cast<__half2*>(out16 + (static_cast<long long>(b) * T + t) * DM + h * HD)[i] = __floats2half2_rn(sx * inv, sy * inv);
   }
 }
 
