@@ -12,6 +12,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "flow_head.cuh"
 #include "gemm.cuh"
 #include "host_util.h"
 #include "kernels.cuh"
@@ -98,7 +99,11 @@ struct Engine {
   long long launches = 0;
   bool use_pdl = true;
   int diag_skip = 0;
-  int persistent_ctas = 148;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
+  bool diag_times = false;      // PTTS_DIAG_TIMES=1: event stamps around both paths of the last step, printed by sync
+  cudaEvent_t ev_t[4] = {};
+  int trig_a = 1, trig_b = 1;   // GemmParams::pdl_trigger per step stream (PTTS_TRIG_A / PTTS_TRIG_B)
+  int split_cta_cap = 64;   // a split-K GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
+  int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
   struct ProfRec { const char* tag; const char* fn; cudaEvent_t a, b; double bytes, flops; };
@@ -130,6 +135,10 @@ struct Engine {
   DevBuf<float> ln1_w[N_LAYERS], ln1_b[N_LAYERS], ln2_w[N_LAYERS], ln2_b[N_LAYERS];
   DevBuf<float> outnorm_w, outnorm_b, eos_w, eos_b, bos, emb_std, emb_mean, lut;
   Weight16 w_cond, w_finproj, w_ada, w_mlp0[FLOW_DEPTH], w_mlp2[FLOW_DEPTH], w_final;
+  DevBuf<__half> w_flowpack;   // mlp.0 / mlp.2 of the six blocks and the final Linear, one [6272][512] operand (flow_head.cuh)
+  bool fused_flow = true;      // ptts_engine_cfg.reserved[5] = 1 or debug_gemm: the per-layer launches instead
+  void flow_head_fused(int n);
+  DevBuf<unsigned long long> fh_trace;  // PTTS_FH_TRACE=1: stage stamps of the fused flow head, printed by sync
   DevBuf<float> b_cond, b_finproj, b_ada, b_mlp0[FLOW_DEPTH], b_mlp2[FLOW_DEPTH], b_final, inln_w[FLOW_DEPTH], inln_b[FLOW_DEPTH];
   DevBuf<float> time_emb;  // [S,512]
   DevBuf<float> wq, wup;
@@ -439,6 +448,16 @@ void Engine::load_weights(const ptts_tensor_desc* w, int nw) {
     PTTS_CUDA(cudaMemcpy(b_ada.p, ba.data(), ba.size() * 4, cudaMemcpyHostToDevice));
   }
   linear(w_final, f + "final_layer.linear.weight", LDIM, FLOW_DIM); vec(b_final, f + "final_layer.linear.bias", LDIM);
+  {
+    static_assert(FH_DIM == FLOW_DIM && FH_DEPTH == FLOW_DEPTH && FH_MOD_LD == MOD_LD, "flow_head.cuh constants");
+    w_flowpack.alloc((size_t)FH_PACK_ROWS * FLOW_DIM);
+    const size_t blk = (size_t)FLOW_DIM * FLOW_DIM;
+    for (int i = 0; i < FLOW_DEPTH; ++i) {
+      PTTS_CUDA(cudaMemcpy(w_flowpack.p + (2 * i) * blk, w_mlp0[i].w.p, blk * sizeof(__half), cudaMemcpyDeviceToDevice));
+      PTTS_CUDA(cudaMemcpy(w_flowpack.p + (2 * i + 1) * blk, w_mlp2[i].w.p, blk * sizeof(__half), cudaMemcpyDeviceToDevice));
+    }
+    PTTS_CUDA(cudaMemcpy(w_flowpack.p + 2 * FLOW_DEPTH * blk, w_final.w.p, (size_t)w_final.Fpad * FLOW_DIM * sizeof(__half), cudaMemcpyDeviceToDevice));
+  }
   auto upload_transposed_512x32 = [&](DevBuf<float>& dst, const HostTensor& t) {  // [512][32] -> [32][512]
     std::vector<float> tr(32 * 512);
     for (int c = 0; c < 512; ++c) for (int k = 0; k < 32; ++k) tr[k * 512 + c] = t.f32[c * 32 + k];
@@ -554,6 +573,9 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     PTTS_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio ? hi : lo));
     PTTS_CUDA(cudaStreamCreateWithPriority(&stream_b, cudaStreamNonBlocking, lo));
     if (const char* v = std::getenv("PTTS_B_SMS")) persistent_ctas = std::max(8, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_MAX_CTAS")) split_cta_cap = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_TRIG_A")) trig_a = std::atoi(v);
+    if (const char* v = std::getenv("PTTS_TRIG_B")) trig_b = std::atoi(v);
   }
   ls = stream;
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_a_done, cudaEventDisableTiming));
@@ -563,6 +585,9 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   PTTS_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   PTTS_CUDA(cudaFuncSetAttribute(mimi_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MATTN_SMEM));
+  PTTS_CUDA(cudaFuncSetAttribute(flow_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FH_SMEM));
+  fused_flow = !cfg.debug_gemm && cfg.reserved[5] == 0;
+  if (std::getenv("PTTS_FH_TRACE")) fh_trace.alloc(FH_LAYERS * 8);
   {
     float inv[HD / 2];
     const float cst = -std::log(10000.f) * 2.f / (float)HD;  // f32 like modules/rope.rs:12-14
@@ -570,6 +595,8 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     PTTS_CUDA(cudaMemcpyToSymbol(c_inv_freq, inv, sizeof inv));
   }
   if (const char* v = std::getenv("PTTS_PDL")) use_pdl = std::atoi(v) != 0;
+  if (const char* v = std::getenv("PTTS_DIAG_TIMES")) diag_times = std::atoi(v) != 0;
+  if (diag_times) for (auto& e4 : ev_t) PTTS_CUDA(cudaEventCreate(&e4));
   if (const char* v = std::getenv("PTTS_DIAG_SKIP")) diag_skip = std::atoi(v);  // 1: time path A alone, 2: path B alone
   load_weights(w, nw);
   compute_time_embeddings(1);
@@ -586,9 +613,12 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   row_seq.alloc(NB); x32.alloc((size_t)NB * D_MODEL); qkv32.alloc((size_t)NB * 3 * D_MODEL); eos_logit.alloc(NB);
   h16.alloc((size_t)NB * D_MODEL); attn16.alloc((size_t)NB * D_MODEL); ffn16.alloc((size_t)NB * D_FFN);
   h32dbg.alloc((size_t)NB * D_MODEL); quant_dbg.alloc((size_t)NB * 512);
-  lat16.alloc((size_t)NB * 64); c32.alloc((size_t)NB * FLOW_DIM); mod32.alloc((size_t)NB * MOD_LD);
-  fx32.alloc((size_t)NB * FLOW_DIM); y16.alloc((size_t)NB * FLOW_DIM); fh16.alloc((size_t)NB * FLOW_DIM);
-  fg16.alloc((size_t)NB * FLOW_DIM); z32.alloc((size_t)NB * LDIM); z16.alloc((size_t)NB * 64);
+  // the fused flow head works on whole 64-row chunks: its row-indexed buffers are padded so that rows past the
+  // batch are readable and writable (never consumed), which keeps every access at a compile-time offset
+  const size_t NBP = (size_t)round_up(NB, FH_ROWS);
+  lat16.alloc((size_t)NB * 64); c32.alloc((size_t)NB * FLOW_DIM); mod32.alloc(NBP * MOD_LD);
+  fx32.alloc(NBP * FLOW_DIM); y16.alloc((size_t)NB * FLOW_DIM); fh16.alloc(NBP * FLOW_DIM);
+  fg16.alloc(NBP * FLOW_DIM); z32.alloc(NBP * LDIM); z16.alloc(NBP * 64);
   mimi_pos.alloc(NB);
   const size_t MR = (size_t)NB * MIMI_T;
   mx32.alloc(MR * MIMI_DIM); mqkv32.alloc(MR * 3 * MIMI_DIM); mh16.alloc(MR * MIMI_DIM); mattn16.alloc(MR * MIMI_DIM);
@@ -687,7 +717,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   // power-of-two cluster sizes only (they pack into a GPC), and the whole grid must fit one wave with slack for
   // cluster placement: 24 tiles x 4 (96 CTAs) beats 24 x 6 (144 CTAs, measured 8.5 vs 15 us)
   if (!persistent && total_kb >= 4) {
-    while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= 132 && splits * 2 <= total_kb / 2) splits *= 2;
+    while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= split_cta_cap && splits * 2 <= total_kb / 2) splits *= 2;
   }
   const LnSpec lnreq = next_ln;
   next_ln.set = false;
@@ -695,6 +725,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   p.kb_per_split = (total_kb + splits - 1) / splits;
   splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.epi_mask = epi_mask_of(p.epi);
+  p.pdl_trigger = (ls == stream_b) ? trig_b : trig_a;
   grid.z = splits;
   const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : 200) * 1024LL;  // one CTA per SM
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
@@ -809,6 +840,36 @@ static RowMap stream_map(int T, int ld, long long stream_stride, long long base)
 //   B      Mimi decoder transformer, SEANet decoder                                          (feeds nothing back)
 // Frame n+1's A depends only on frame n's A, so run_step() puts A on one stream and front+B on another: the codec
 // of frame n overlaps the language model of frame n+1.
+// input_proj + six AdaLN residual blocks + final layer of one LSD step as a single cluster kernel (flow_head.cuh)
+void Engine::flow_head_fused(int n) {
+  FlowHeadParams fp{};
+  fp.b_in = b_finproj.p; fp.b_final = b_final.p;
+  fp.ws_in = w_finproj.wscale.p; fp.ws_final = w_final.wscale.p;
+  for (int i = 0; i < FLOW_DEPTH; ++i) {
+    fp.b0[i] = b_mlp0[i].p; fp.b2[i] = b_mlp2[i].p;
+    fp.ln_w[i] = inln_w[i].p; fp.ln_b[i] = inln_b[i].p;
+    fp.ws0[i] = w_mlp0[i].wscale.p; fp.ws2[i] = w_mlp2[i].wscale.p;
+  }
+  fp.mod = mod32.p; fp.z32 = z32.p; fp.z16 = z16.p; fp.h16 = fh16.p; fp.g16 = fg16.p; fp.x_dbg = fx32.p;
+  fp.n = n; fp.alpha = 1.f / (float)lsd_steps;
+  fp.trace = fh_trace.p;
+  const CUtensorMap& m_win = tmaps.get(w_finproj.w.p, 64, w_finproj.Fpad, 1, 64, (long long)w_finproj.Fpad * 64, 128, 1);
+  const CUtensorMap& m_wp = tmaps.get(w_flowpack.p, FLOW_DIM, FH_PACK_ROWS, 1, FLOW_DIM, (long long)FH_PACK_ROWS * FLOW_DIM, 128, 1);
+  const long long NBP = round_up(NB, FH_ROWS);
+  // operand maps: (64 k, rows, k-blocks) with the k-block as the slowest box dimension, so one box is the whole
+  // [k-block][row][64] operand of a layer
+  const CUtensorMap& m_z = tmaps.get(z16.p, 64, NBP, 1, 64, 64, FH_ROWS, 1);
+  const CUtensorMap& m_h = tmaps.get(fh16.p, 64, NBP, 8, FLOW_DIM, 64, FH_ROWS, 8);
+  const CUtensorMap& m_g = tmaps.get(fg16.p, 64, NBP, 8, FLOW_DIM, 64, FH_ROWS, 8);
+  const int chunks = (n + FH_ROWS - 1) / FH_ROWS;
+  // weights once per cluster, modulation rows three times a block, the operand all-gather twice a block
+  const double bytes = (double)chunks * ((double)FH_PACK_ROWS * FLOW_DIM * 2 + 512.0 * 64 * 2) + (double)n * (MOD_LD * 4.0 + 26.0 * FLOW_DIM * 2 + 64 * 2 + 32 * 8);
+  const double flops = 2.0 * n * (12.0 * FLOW_DIM * FLOW_DIM + 64.0 * FLOW_DIM + 32.0 * FLOW_DIM);
+  ProfScope ps(*this, "flow.head_fused", bytes, flops, "flow_head_kernel");
+  launch_k(use_pdl, flow_head_kernel, dim3(chunks, 1, FH_CLUSTER), FH_THREADS, FH_SMEM, ls, FH_CLUSTER, m_win, m_wp, m_z, m_h, m_g, fp);
+  PTTS_CUDA(cudaGetLastError());
+}
+
 void Engine::step_part_a(int n, bool marks) {
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
   { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
@@ -832,6 +893,10 @@ void Engine::step_part_a(int n, bool marks) {
     e = epi_none();
     e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
     tag("flow.adaln"); gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
+    if (fused_flow) {
+      flow_head_fused(n);
+      continue;
+    }
     e = epi_none();
     e.bias = b_finproj.p; e.out32 = fx32.p; e.out32_map = plain_map(FLOW_DIM);
     // fh = LN(x) * (1 + scale) + shift of each block rides behind the GEMM that produces x (modules/mlp.rs:168-171)
@@ -992,13 +1057,17 @@ void Engine::run_step(int n) {
       sg.b = capture(stream_b, n, 1, &sg.kernels_b);
       it = graphs.emplace(key, sg).first;
     }
+    if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[0], stream));
     if (diag_skip != 2) PTTS_CUDA(cudaGraphLaunch(it->second.a, stream));
+    if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[1], stream));
     PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
     PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_a_done, 0));
     ls = stream_b;
+    if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[2], stream_b));
     if (diag_skip != 1) step_front(n);
     PTTS_CUDA(cudaEventRecord(ev_front_done, stream_b));
     if (diag_skip != 1) PTTS_CUDA(cudaGraphLaunch(it->second.b, stream_b));
+    if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[3], stream_b));
     launches += it->second.kernels_a + it->second.kernels_b;
   } else {
     ls = stream;
@@ -1329,6 +1398,24 @@ int32_t ptts_sync(ptts_engine* h) {
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
   PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
   h->e.sync_all();
+  if (h->e.fh_trace.p) {
+    unsigned long long st[FH_LAYERS * 8];
+    if (cudaMemcpy(st, h->e.fh_trace.p, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess && st[0]) {
+      std::fprintf(stderr, "ptts flow head trace (ns since layer-0 entry): layer: start | act TMA issued, first k-block landed, last landed | acc_ready math_done barrier\n");
+      for (int L = 0; L < FH_LAYERS; ++L)
+        std::fprintf(stderr, "  L%02d: %6lld | %6lld %6lld %6lld | %6lld %6lld %6lld\n", L, (long long)(st[L * 8] - st[0]), (long long)(st[L * 8 + 4] - st[0]),
+                     (long long)(st[L * 8 + 5] - st[0]), (long long)(st[L * 8 + 6] - st[0]), (long long)(st[L * 8 + 1] - st[0]),
+                     (long long)(st[L * 8 + 2] - st[0]), (long long)(st[L * 8 + 3] - st[0]));
+    }
+  }
+  if (h->e.diag_times) {
+    float a = 0, b = 0, ab = 0, ae = 0;
+    if (cudaEventElapsedTime(&a, h->e.ev_t[0], h->e.ev_t[1]) == cudaSuccess && cudaEventElapsedTime(&b, h->e.ev_t[2], h->e.ev_t[3]) == cudaSuccess &&
+        cudaEventElapsedTime(&ab, h->e.ev_t[0], h->e.ev_t[2]) == cudaSuccess && cudaEventElapsedTime(&ae, h->e.ev_t[0], h->e.ev_t[3]) == cudaSuccess)
+      std::fprintf(stderr, "ptts diag: last step  A %.1f us | B %.1f us | A start -> B start %.1f us | A start -> B end %.1f us\n", a * 1e3f, b * 1e3f,
+                   ab * 1e3f, ae * 1e3f);
+    (void)cudaGetLastError();
+  }
   return PTTS_OK;
   PTTS_CATCH
 }

@@ -74,6 +74,7 @@ struct GemmParams {
   int vec4;                 // every epilogue tensor is 16-byte addressable in groups of 4 features
   int epi_mask;             // epi_mask_of(epi): selects the compiled store loop
   int n_act_tiles;          // activation tiles in total (persistent kernel walks them with stride gridDim.x)
+  int pdl_trigger;          // where the CTA lets the next kernel launch: 0 entry, 1 all loads issued, 2 accumulator ready
   GemmEpi epi;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
@@ -400,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
+  if (p.pdl_trigger == 0) pdl_launch_dependents();
   if (warp == 0) PTTS_TRACE(0);
 
   // tile coordinates
@@ -474,6 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         tma_load_3d(p.swap ? n_tile : m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
         if (i == 0) PTTS_TRACE(2);
       }
+      if (p.pdl_trigger == 1) pdl_launch_dependents();
       PTTS_TRACE(3);
     }
   } else if (warp == 1) {
@@ -506,6 +508,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     // is staged over them.  Pitch = features + 4 floats: 16-byte aligned rows, conflict-free in both passes.
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (p.pdl_trigger == 2 && warp == 2 && lane == 0) pdl_launch_dependents();
     if (warp == 2) PTTS_TRACE(6);
     const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4)..+31
     const int i = quad * 32 + lane;
@@ -566,7 +569,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  pdl_launch_dependents();
+  if (p.pdl_trigger == 0) pdl_launch_dependents();
   const int tiles_t = (p.T + p.R - 1) / p.R;
   const int f0 = blockIdx.y * p.BN;
   const int nkb = p.taps * p.cblocks;
@@ -621,6 +624,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
           tma_load_3d(m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
         }
       }
+      if (p.pdl_trigger != 0) pdl_launch_dependents();
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_f16_m128(p.BN);

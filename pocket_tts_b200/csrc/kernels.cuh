@@ -158,8 +158,8 @@ __device__ __forceinline__ void rope_pair(float xr, float xi, int pos, int i, fl
 // softmax(q K^T / 8) V over keys [0, n_keys) of one (sequence, layer, head), single pass with a running maximum
 // (the naive reference path, modules/sdpa.rs:36-82, up to f32 rounding; causality is the caller's key range).
 // Block = ATTN_THREADS (4 warps).  Eight lanes share one key: each loads 16 bytes of the K row and 16 bytes of the
-// V row, the partial dots are folded with three shuffles, so a warp streams 4 keys x 256 bytes per iteration with
-// both rows in flight and ~40 registers per thread (many CTAs per SM keep the memory pipe full).
+// V row, the partial dots are folded with three shuffles; a lane group has 4 keys (8 loads) in flight before the
+// first use, so a warp streams 16 keys x 256 bytes per iteration (one loop trip per memory round trip was the limit).
 // q in smem (f32, already rotated).  Result: 64 floats at red_s[0..63].  red_s needs 64 + 4*66 floats.
 static constexpr int ATTN_THREADS = 128;
 __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int head, int n_heads, const float* q_s,
@@ -171,35 +171,56 @@ __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int h
 #pragma unroll
   for (int j = 0; j < 8; ++j) q[j] = q_s[part * 8 + j] * 0.125f;  // 1/sqrt(64) folded into q
   float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i0 = warp * 4; i0 < n_keys; i0 += NW * 4) {
-    const int i = i0 + sub;
-    const bool valid = i < n_keys;
-    uint4 ku = make_uint4(0, 0, 0, 0), vu = make_uint4(0, 0, 0, 0);
-    if (valid) {
-      ku = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, head, n_heads, i))[part];
-      vu = reinterpret_cast<const uint4*>(kv_row(sd, layer, 1, head, n_heads, i))[part];
-    }
-    const __half2* kh = reinterpret_cast<const __half2*>(&ku);
-    float sc = 0.f;
+  constexpr int U = 4;  // keys per lane group in flight: 8 x 16-byte loads before the first use
+  for (int i0 = warp * 4 * U; i0 < n_keys; i0 += NW * 4 * U) {
+    uint4 ku[U], vu[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(kh[j]);
-      sc += f.x * q[2 * j] + f.y * q[2 * j + 1];
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * 4 + sub;
+      ku[u] = vu[u] = make_uint4(0, 0, 0, 0);
+      if (i < n_keys) {
+        ku[u] = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, head, n_heads, i))[part];
+        vu[u] = reinterpret_cast<const uint4*>(kv_row(sd, layer, 1, head, n_heads, i))[part];
+      }
     }
-    sc += __shfl_xor_sync(0xffffffffu, sc, 1);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 2);
-    sc += __shfl_xor_sync(0xffffffffu, sc, 4);
-    if (valid) {
-      const float m_new = fmaxf(m, sc);
-      const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first key
-      const float p = expf(sc - m_new);
-      l = l * corr + p;
-      const __half2* vh = reinterpret_cast<const __half2*>(&vu);
+    float sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const __half2* kh = reinterpret_cast<const __half2*>(&ku[u]);
+      sc[u] = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(vh[j]);
-        acc[2 * j] = acc[2 * j] * corr + p * f.x;
-        acc[2 * j + 1] = acc[2 * j + 1] * corr + p * f.y;
+        const float2 f = __half22float2(kh[j]);
+        sc[u] += f.x * q[2 * j] + f.y * q[2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int x = 1; x <= 4; x <<= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], x);
+    // one rescale for the group of U keys (keys past the end score -inf and weigh 0)
+    float m_new = m;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * 4 + sub >= n_keys) sc[u] = -INFINITY;
+      m_new = fmaxf(m_new, sc[u]);
+    }
+    if (m_new != -INFINITY) {
+      const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first group
+      l *= corr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= corr;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float p = expf(sc[u] - m_new);
+        l += p;
+        const __half2* vh = reinterpret_cast<const __half2*>(&vu[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(vh[j]);
+          acc[2 * j] += p * f.x;
+          acc[2 * j + 1] += p * f.y;
+        }
       }
       m = m_new;
     }
@@ -247,7 +268,7 @@ __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int h
 // FlowLM decode attention, one new row per stream (reference modules/attention.rs:104-231 with t = 1):
 // RoPE(q,k) at the absolute position, append K,V at the cursor, causal SDPA over prefix + own rows, all fused.
 // grid (n, heads), block ATTN_THREADS.
-__global__ void flowlm_attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
+__global__ void __launch_bounds__(ATTN_THREADS, 7) flowlm_attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
                                           const SeqDesc* __restrict__ seqs, const int* __restrict__ own_len, int layer,
                                           int n_heads, __half* __restrict__ out16) {
   pdl_launch_dependents();
