@@ -854,7 +854,8 @@ void Engine::flow_head_fused(int n) {
   fp.n = n; fp.alpha = 1.f / (float)lsd_steps;
   fp.trace = fh_trace.p;
   const CUtensorMap& m_win = tmaps.get(w_finproj.w.p, 64, w_finproj.Fpad, 1, 64, (long long)w_finproj.Fpad * 64, 128, 1);
-  const CUtensorMap& m_wp = tmaps.get(w_flowpack.p, FLOW_DIM, FH_PACK_ROWS, 1, FLOW_DIM, (long long)FH_PACK_ROWS * FLOW_DIM, 128, 1);
+  // weights: (64 k, rows, k-blocks); one box = four k-block tiles [k-block][128 features][64]
+  const CUtensorMap& m_wp = tmaps.get(w_flowpack.p, 64, FH_PACK_ROWS, 8, FLOW_DIM, 64, 128, 4);
   const long long NBP = round_up(NB, FH_ROWS);
   // operand maps: (64 k, rows, k-blocks) with the k-block as the slowest box dimension, so one box is the whole
   // [k-block][row][64] operand of a layer

@@ -4,7 +4,7 @@
 // paid a ~2 us grid hand-off plus pipeline fill for ~0.5 MB of work; here a cluster of four CTAs keeps the chain on
 // chip:
 //   * CTA `rank` owns features [128 rank, 128 rank + 128) of every layer.  Weights are the MMA-M operand (swap-AB,
-//     64 activation rows = MMA-N), streamed by TMA through an 8-slot ring that runs a whole layer ahead.
+//     64 activation rows = MMA-N), the next layer's 128 KB land (two TMA boxes) while this layer's epilogue runs.
 //   * the residual stream x never leaves registers: thread = feature, 64 rows per thread (the TMEM accumulator
 //     layout), so bias / gate / residual are register arithmetic straight after tcgen05.ld.
 //   * LayerNorm needs row statistics over all 512 features: a 62-shuffle transpose-reduce per warp, 16 partials
@@ -19,7 +19,7 @@ namespace ptts {
 
 static constexpr int FH_DIM = 512, FH_DEPTH = 6, FH_ROWS = 64, FH_CLUSTER = 4, FH_FEATS = 128;
 static constexpr int FH_LDIM = 32;                  // latent dim (the final Linear's features)
-static constexpr int FH_STAGES = 8;                 // weight ring slots (16 KB each): one whole layer ahead
+static constexpr int FH_STAGES = 8;                 // weight k-block tiles resident (16 KB each): one whole layer, in two halves
 static constexpr int FH_THREADS = 320;              // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 static constexpr int FH_EROWS = FH_ROWS / 2;        // rows per epilogue thread
 static constexpr int FH_LAYERS = 2 + 2 * FH_DEPTH;  // input_proj, (mlp.0, mlp.2) x 6, final
@@ -27,7 +27,7 @@ static constexpr int FH_MOD_LD = FH_DEPTH * 3 * FH_DIM + 2 * FH_DIM;
 static constexpr int FH_PACK_ROWS = 2 * FH_DEPTH * FH_DIM + 128;  // packed weights: 12 x [512][512] then final [128][512]
 static constexpr int FH_ACT_BYTES = 8 * FH_ROWS * 128;            // 8 k-blocks of [64 rows][64 k] f16
 static constexpr int FH_W_BYTES = FH_FEATS * 128;                 // one k-block of [128 features][64 k] f16
-static constexpr int FH_SMEM = FH_ACT_BYTES + FH_STAGES * FH_W_BYTES + 8 * (2 * FH_STAGES + 2) + 16 +
+static constexpr int FH_SMEM = FH_ACT_BYTES + FH_STAGES * FH_W_BYTES + 8 * 6 + 16 +
                                (2 * 16 * FH_ROWS + 2 * FH_ROWS) * 4 + 1024;
 
 struct FlowHeadParams {
@@ -88,8 +88,8 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
   uint8_t* act_s = smem;                                  // 8 x 8 KB
   uint8_t* w_s = smem + FH_ACT_BYTES;                     // ring
   uint64_t* full_w = reinterpret_cast<uint64_t*>(w_s + FH_STAGES * FH_W_BYTES);
-  uint64_t* empty_w = full_w + FH_STAGES;
-  uint64_t* full_act = empty_w + FH_STAGES;
+  uint64_t* empty_w = full_w + 2;
+  uint64_t* full_act = empty_w + 2;
   uint64_t* tmem_full = full_act + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* stat_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][16][64]
@@ -106,9 +106,9 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
     tma_prefetch_desc(&map_z);
     tma_prefetch_desc(&map_h);
     tma_prefetch_desc(&map_g);
-    for (int s = 0; s < FH_STAGES; ++s) {
-      mbar_init(full_w + s, 1);
-      mbar_init(empty_w + s, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(full_w + h, 1);
+      mbar_init(empty_w + h, 1);
     }
     mbar_init(full_act, 1);
     mbar_init(tmem_full, 1);
@@ -129,25 +129,21 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
   auto has_ln = [](int L) { return L == 0 || (L < FH_LAYERS - 1 && (L & 1) == 0); };
   const int n_layers_mine = (rank == 0) ? FH_LAYERS : FH_LAYERS - 1;
 
+  // Weights of a layer sit in two 64 KB halves (k-blocks 0-3 | 4-7), one TMA box and one full/empty barrier pair each, so
+  // the MMA warp waits twice and commits twice per layer instead of once per k-block (each wait + fence + commit round
+  // costs ~600 cycles of single-thread latency, which at eight rounds per layer was twice the MMA time itself).
+  // Half 0 is used by every layer (its load number for layer L is L), half 1 by layers >= 1 (load number L - 1).
   if (warp == 0) {
-    // ===== TMA producer: weight ring (runs up to a layer ahead) and the activation operand =====
-    int w_it = 0;             // weight k-blocks issued so far
-    int wl = 0, wkb = 0;      // next weight k-block to issue: layer, k-block
-    // k-block number `it` may be requested once block it-8 (the slot's previous tenant) is certain to be consumed,
-    // i.e. once the activations of that block's layer have been requested: callers pass the matching limit.
-    auto first_block = [](int L) { return L <= 0 ? 0 : 1 + 8 * (L - 1); };
-    auto issue_weights = [&](int limit_it) {  // lane 0 only
-      while (wl < n_layers_mine && w_it < limit_it) {
-        const int s = w_it % FH_STAGES;
-        if (w_it >= FH_STAGES) mbar_wait(empty_w + s, ((w_it / FH_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(full_w + s, FH_W_BYTES);
-        if (wl == 0) tma_load_3d(w_s + s * FH_W_BYTES, &map_win, full_w + s, 0, rank * FH_FEATS, 0);
-        else tma_load_3d(w_s + s * FH_W_BYTES, &map_wpack, full_w + s, wkb * 64, (wl - 1) * FH_DIM + rank * FH_FEATS, 0);
-        ++w_it;
-        if (++wkb == kblocks(wl)) { wkb = 0; ++wl; }
-      }
+    // ===== TMA producer: next layer's weights as soon as this layer's MMAs have read theirs, and the activation operand =====
+    auto load_w = [&](int L, int h) {  // lane 0 only
+      mbar_arrive_expect_tx(full_w + h, (L == 0 ? 1 : 4) * FH_W_BYTES);
+      if (L == 0) tma_load_3d(w_s, &map_win, full_w, 0, rank * FH_FEATS, 0);
+      else tma_load_3d(w_s + h * 4 * FH_W_BYTES, &map_wpack, full_w + h, 0, (L - 1) * FH_DIM + rank * FH_FEATS, 4 * h);
     };
-    if (lane == 0) issue_weights(FH_STAGES);  // constants: requested before the dependency on the previous kernel resolves
+    if (lane == 0) {  // constants: requested before the dependency on the previous kernel resolves
+      load_w(0, 0);
+      load_w(1, 1);
+    }
     pdl_wait();
     for (int L = 0; L < FH_LAYERS; ++L) {
       if (lane == 0 && L < n_layers_mine) {
@@ -157,8 +153,14 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
         mbar_arrive_expect_tx(full_act, kblocks(L) * FH_ROWS * 128);
         tma_load_3d(act_s, am, full_act, 0, row0, 0);
         if (p.trace && rank == 0 && blockIdx.x == 0) p.trace[L * 8 + 4] = gtime();
-        issue_weights(first_block(L + 1));              // the rest of this layer
-        issue_weights(first_block(L + 1) + FH_STAGES);  // and a ring's worth ahead, in flight during this layer's epilogue
+        if (L + 1 < n_layers_mine) {
+          mbar_wait(empty_w, L & 1);  // half 0: commit number L
+          load_w(L + 1, 0);
+          if (L >= 1) {
+            mbar_wait(empty_w + 1, (L - 1) & 1);  // half 1: commit number L - 1
+            load_w(L + 1, 1);
+          }
+        }
         if (L == FH_LAYERS - 2) pdl_launch_dependents();
       }
       __syncwarp();
@@ -169,26 +171,40 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = make_idesc_f16_m128(FH_ROWS);
-    int w_it = 0;
-    uint32_t act_par = 0;
+    const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(w_s));
+    const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(act_s));
     for (int L = 0; L < FH_LAYERS; ++L) {
       if (L < n_layers_mine) {
-        for (int kb = 0; kb < kblocks(L); ++kb, ++w_it) {
-          const int s = w_it % FH_STAGES;
-          mbar_wait(full_w + s, (w_it / FH_STAGES) & 1);
-          if (kb == 0) { mbar_wait(full_act, act_par & 1); act_par ^= 1u; }
-          tc_fence_after();
-          if (p.trace && rank == 0 && blockIdx.x == 0 && lane == 0 && (kb == 0 || kb == kblocks(L) - 1)) p.trace[L * 8 + (kb == 0 ? 5 : 6)] = gtime();
-          if (elect_one()) {
-            const uint64_t da = make_sw128_kmajor_desc(smem_u32(w_s + s * FH_W_BYTES));
-            const uint64_t db = make_sw128_kmajor_desc(smem_u32(act_s + kb * FH_ROWS * 128));
+        mbar_wait(full_w, L & 1);
+        mbar_wait(full_act, L & 1);
+        tc_fence_after();
+        if (p.trace && rank == 0 && blockIdx.x == 0 && lane == 0) p.trace[L * 8 + 5] = gtime();
+        if (elect_one()) {
+          const int nk0 = (L == 0) ? 1 : 4;
+          for (int kb = 0; kb < nk0; ++kb) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(empty_w + s);
-            if (kb == kblocks(L) - 1) umma_commit(tmem_full);
+            for (int k = 0; k < 4; ++k)  // k-block tiles are 16 KB (weights) / 8 KB (rows) apart: +1024 / +512 in the address field
+              umma_f16(tmem_base, da0 + kb * (FH_W_BYTES >> 4) + 2 * k, db0 + kb * (FH_ROWS * 128 >> 4) + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_w);
+          if (L == 0) umma_commit(tmem_full);
+        }
+        __syncwarp();
+        if (L >= 1) {
+          mbar_wait(full_w + 1, (L - 1) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int kb = 4; kb < 8; ++kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base, da0 + kb * (FH_W_BYTES >> 4) + 2 * k, db0 + kb * (FH_ROWS * 128 >> 4) + 2 * k, idesc, 1);
+            }
+            umma_commit(empty_w + 1);
+            umma_commit(tmem_full);
           }
           __syncwarp();
         }
+        if (p.trace && rank == 0 && blockIdx.x == 0 && lane == 0) p.trace[L * 8 + 6] = gtime();
       }
       if (L == FH_LAYERS - 1) break;
       if (has_ln(L)) { cluster_sync_all(); cluster_sync_all(); }

@@ -169,6 +169,12 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t cta_smem_addr, uint32_t
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only rendezvous (no memory ordering): the release form drains every outstanding global store of the CTA
+// (MEMBAR.ALL.GPU, ~0.8 us right after an epilogue), which a barrier that merely keeps shared memory alive for the
+// peers' reads does not need.
+__device__ __forceinline__ void cluster_sync_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
 
 // Second half of the epilogue.  The f32 accumulator tile sits in shared memory as [activation row][feature]
 // (pitch LD floats) in every CTA of the split-K cluster; CTA `rank` of `nsplit` owns rows rank*nwarps + warp,
@@ -231,47 +237,65 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 #pragma unroll
         for (int k = 0; k < GEMM_MAX_SPLIT; ++k) peer[k] = (nsplit > 1 && k < nsplit) ? map_to_rank(stile_addr, k) : stile_addr;
         const int step = nwarps * nsplit * rows_per_iter;
-        for (int row = (rank * nwarps + warp) * rows_per_iter + my_sub; row < nrows; row += step) {
-          const uint32_t toff = static_cast<uint32_t>(row * LD + q * 4) * 4u;
-          float4 a4;
-          if (nsplit == 1) {
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(stile_addr + toff));
-          } else {  // split-K: sum the cluster's partial tiles in rank order (bit-reproducible)
-            float4 t[GEMM_MAX_SPLIT];
+        // Rows are taken two at a time: the residual / gate rows of both are requested before the first store (four at a
+        // time measured no faster and spilled in the persistent kernel).
+        // One row per trip made every trip a full memory round trip (the compiler may not move a load above the
+        // previous row's store to a possibly aliasing tensor), ~0.35 us x 7-11 trips per 128-row tile.
+        constexpr int U = GEN ? 1 : 2;  // the catch-all shape keeps every optional tensor live: no room to prefetch
+        for (int row_b = (rank * nwarps + warp) * rows_per_iter + my_sub; row_b < nrows; row_b += step * U) {
+          float4 g4[U], r4[U];
 #pragma unroll
-            for (int k = 0; k < GEMM_MAX_SPLIT; ++k)
-              if (k < nsplit) t[k] = ld_dsmem_f4(peer[k] + toff);
-            a4 = t[0];
-#pragma unroll
-            for (int k = 1; k < GEMM_MAX_SPLIT; ++k)
-              if (k < nsplit) { a4.x += t[k].x; a4.y += t[k].y; a4.z += t[k].z; a4.w += t[k].w; }
-          }
-          float v[4] = {a4.x, a4.y, a4.z, a4.w};
-          float gv[4], rv[4];
-          if (has_gate) { const float4 t4 = *reinterpret_cast<const float4*>(gate_p + static_cast<long long>(row) * ld_g); gv[0] = t4.x; gv[1] = t4.y; gv[2] = t4.z; gv[3] = t4.w; }
-          if (has_res) { const float4 t4 = *reinterpret_cast<const float4*>(res_p + static_cast<long long>(row) * ld_r); rv[0] = t4.x; rv[1] = t4.y; rv[2] = t4.z; rv[3] = t4.w; }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            float x = v[c];
-            if (GEN && wscale) x *= wv[c];
-            if (has_bias) x += bv[c];
-            x = epi_act(act, x) * alpha;
-            if (has_fscale) x *= sv[c];
-            if (has_gate) x *= gv[c];
-            if (has_res) x += rv[c];
-            v[c] = x;
-          }
-          if (has_o32) *reinterpret_cast<float4*>(o32_p + static_cast<long long>(row) * ld_a) = make_float4(v[0], v[1], v[2], v[3]);
-          if (has_o16) {
-            if (elu16) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) v[c] = elu1_fast(v[c]);
+          for (int u = 0; u < U; ++u) {
+            const int row = row_b + u * step;
+            if (row < nrows) {
+              if (has_gate) g4[u] = *reinterpret_cast<const float4*>(gate_p + static_cast<long long>(row) * ld_g);
+              if (has_res) r4[u] = *reinterpret_cast<const float4*>(res_p + static_cast<long long>(row) * ld_r);
             }
-            const __half2 h0v = __floats2half2_rn(v[0], v[1]), h1v = __floats2half2_rn(v[2], v[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&h0v);
-            pk.y = *reinterpret_cast<const uint32_t*>(&h1v);
-            *reinterpret_cast<uint2*>(o16_p + static_cast<long long>(row) * ld_h) = pk;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int row = row_b + u * step;
+            if (row >= nrows) break;
+            const uint32_t toff = static_cast<uint32_t>(row * LD + q * 4) * 4u;
+            float4 a4;
+            if (nsplit == 1) {
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(stile_addr + toff));
+            } else {  // split-K: sum the cluster's partial tiles in rank order (bit-reproducible)
+              float4 t[GEMM_MAX_SPLIT];
+#pragma unroll
+              for (int k = 0; k < GEMM_MAX_SPLIT; ++k)
+                if (k < nsplit) t[k] = ld_dsmem_f4(peer[k] + toff);
+              a4 = t[0];
+#pragma unroll
+              for (int k = 1; k < GEMM_MAX_SPLIT; ++k)
+                if (k < nsplit) { a4.x += t[k].x; a4.y += t[k].y; a4.z += t[k].z; a4.w += t[k].w; }
+            }
+            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+            const float rv[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float x = v[c];
+              if (GEN && wscale) x *= wv[c];
+              if (has_bias) x += bv[c];
+              x = epi_act(act, x) * alpha;
+              if (has_fscale) x *= sv[c];
+              if (has_gate) x *= gv[c];
+              if (has_res) x += rv[c];
+              v[c] = x;
+            }
+            if (has_o32) *reinterpret_cast<float4*>(o32_p + static_cast<long long>(row) * ld_a) = make_float4(v[0], v[1], v[2], v[3]);
+            if (has_o16) {
+              if (elu16) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = elu1_fast(v[c]);
+              }
+              const __half2 h0v = __floats2half2_rn(v[0], v[1]), h1v = __floats2half2_rn(v[2], v[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&h0v);
+              pk.y = *reinterpret_cast<const uint32_t*>(&h1v);
+              *reinterpret_cast<uint2*>(o16_p + static_cast<long long>(row) * ld_h) = pk;
+            }
           }
         }
       }
@@ -479,18 +503,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       PTTS_TRACE(3);
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: one elected thread runs the whole loop =====
+    // Per k-block: one barrier wait, four MMAs, one commit.  (Electing a lane, fencing and re-converging the warp in
+    // every iteration cost ~600 cycles of single-thread latency per k-block, more than the MMAs themselves.)
     const uint32_t idesc = make_idesc_f16_m128(p.BN);
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % p.stages;
-      const uint32_t ph = (i / p.stages) & 1;
-      mbar_wait(full_bar + s, ph);
-      tc_fence_after();
-      if (i == 0) PTTS_TRACE(4);
-      if (elect_one()) {
-        const uint32_t m_addr = smem_u32(smem + s * stage_bytes);
-        const uint64_t da = make_sw128_kmajor_desc(m_addr);
-        const uint64_t db = make_sw128_kmajor_desc(m_addr + m_tile_bytes);
+    if (elect_one()) {
+      const uint64_t d0 = make_sw128_kmajor_desc(smem_u32(smem));
+      const uint32_t stage_adv = static_cast<uint32_t>(stage_bytes) >> 4, b_adv = static_cast<uint32_t>(m_tile_bytes) >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        if (i == 0) PTTS_TRACE(4);
+        const uint64_t da = d0 + static_cast<uint64_t>(s) * stage_adv;
+        const uint64_t db = da + b_adv;
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k) {
           // +32 B along K inside the 128-B swizzle row = +2 in the 16-byte address field
@@ -498,9 +525,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         }
         umma_commit(empty_bar + s);  // frees this smem stage once the MMAs above have read it
         if (i == nkb - 1) umma_commit(tmem_full_bar);
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
-      __syncwarp();
     }
+    __syncwarp();
     PTTS_TRACE(5);
   } else if (warp < 6) {
     // ===== epilogue, first half: TMEM -> registers -> smem tile [activation row][feature] (raw f32) =====
@@ -540,7 +568,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   pdl_wait();  // residual / gate / output tensors belong to earlier kernels until they have completed
   epi_dispatch(p, smem_u32(smem), (p.swap ? GEMM_BM : p.BN) + 4, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
   if (warp == 2) PTTS_TRACE(8);
-  if (nsplit > 1) cluster_sync_all();  // peers may still be reading this CTA's tile
+  if (nsplit > 1) cluster_sync_relaxed();  // peers may still be reading this CTA's tile
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
   if (warp == 1) PTTS_TRACE(9);
 }
@@ -628,27 +656,29 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_f16_m128(p.BN);
-    int it = 0, j = 0;
-    for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x, ++j) {
-      const int as = j & 1;
-      mbar_wait(tempty_bar + as, ((j >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
-      tc_fence_after();
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % p.stages;
-        mbar_wait(full_bar + s, (it / p.stages) & 1);
+    if (elect_one()) {  // one thread runs the whole loop (see gemm_tc_kernel)
+      const uint64_t d0 = make_sw128_kmajor_desc(smem_u32(smem));
+      const uint32_t stage_adv = static_cast<uint32_t>(stage_bytes) >> 4, b_adv = static_cast<uint32_t>(m_tile_bytes) >> 4;
+      int s = 0, j = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x, ++j) {
+        const int as = j & 1;
+        mbar_wait(tempty_bar + as, ((j >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t m_addr = smem_u32(smem + s * stage_bytes);
-          const uint64_t da = make_sw128_kmajor_desc(m_addr);
-          const uint64_t db = make_sw128_kmajor_desc(m_addr + m_tile_bytes);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint64_t da = d0 + static_cast<uint64_t>(s) * stage_adv;
+          const uint64_t db = da + b_adv;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) umma_f16(tmem_base + as * p.BN, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           umma_commit(empty_bar + s);
           if (kb == nkb - 1) umma_commit(tfull_bar + as);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     const int etid = threadIdx.x - 64;
     pdl_wait();  // epilogue tensors (residual, outputs) belong to earlier kernels until they have completed
