@@ -102,7 +102,7 @@ struct Engine {
   bool diag_times = false;      // PTTS_DIAG_TIMES=1: event stamps around both paths of the last step, printed by sync
   cudaEvent_t ev_t[4] = {};
   int trig_a = 1, trig_b = 1;   // GemmParams::pdl_trigger per step stream (PTTS_TRIG_A / PTTS_TRIG_B)
-  int split_cta_cap = 64;   // a split-K GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
+  int split_cta_cap = 48;   // a split-K GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
@@ -742,6 +742,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     // the epilogue re-uses the stage buffers for its staged f32 tile
     while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;
     smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
+    p.resident = (swap && taps == 1 && n_streams == 1 && a.cap == 1 && p.kb_per_split <= p.stages && !cfg.debug_gemm &&
+                  cfg.reserved[6] == 0) ? 1 : 0;   // reserved[6] = 1: test hook, the staged pipeline instead
   }
   auto map_ok = [](const void* ptr, const RowMap& m) {
     return !ptr || ((reinterpret_cast<uintptr_t>(ptr) % 16 == 0) && m.ld % 4 == 0 && m.base % 4 == 0 && m.stream_stride % 4 == 0);
@@ -760,8 +762,10 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
       const long long n = rows * F;
       launch_k(use_pdl, gemm_simt_kernel, (unsigned)((n + 255) / 256), 256, 0, ls, 1, p);
     } else {
-      const CUtensorMap& ma = swap ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
-                                   : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
+      // resident decode GEMM: (64 k, rows, k-blocks) with the k-block as the slowest box dimension, see gemm.cuh
+      const CUtensorMap& ma = p.resident ? tmaps.get(a.ptr, 64, a.Tpad, a.C / 64, a.C, 64, p.BN, p.kb_per_split)
+                              : swap     ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
+                                         : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
       const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
       if (persistent) launch_k(use_pdl, gemm_tc_persistent_kernel, grid, GEMM_THREADS, smem, ls, 1, ma, mw, p);
       else launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);

@@ -75,6 +75,7 @@ struct GemmParams {
   int epi_mask;             // epi_mask_of(epi): selects the compiled store loop
   int n_act_tiles;          // activation tiles in total (persistent kernel walks them with stride gridDim.x)
   int pdl_trigger;          // where the CTA lets the next kernel launch: 0 entry, 1 all loads issued, 2 accumulator ready
+  int resident;             // swap-AB decode GEMM whose whole K slice fits the stages: one barrier, one activation box
   GemmEpi epi;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
@@ -473,7 +474,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     // Weights are constants, so their tiles for the first stages are requested BEFORE griddepcontrol.wait: the HBM
     // fetch of this GEMM's weights overlaps the tail of the kernel it depends on, and only the (L2-resident)
     // activation tiles remain on the critical path once the dependency resolves.
-    if (elect_one()) {
+    if (p.resident) {
+      // Decode shape: the CTA's whole K slice is resident, so everything lands on ONE barrier: the weight tiles
+      // [k-block][128][64] (requested before the dependency resolves), then a single activation box
+      // (64 k, BN rows, all k-blocks) = [k-block][row][64] behind them.  One TMA instead of one per k-block: each
+      // issue costs this thread ~0.3 us, which at eight k-blocks was the longest phase of the kernel.
+      if (elect_one()) {
+        mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(nkb * m_tile_bytes + p.kb_per_split * n_tile_bytes));
+        for (int i = 0; i < nkb; ++i) tma_load_3d(smem + i * m_tile_bytes, &map_w, full_bar, (kb0 + i) * GEMM_BK, f0, 0);
+        pdl_wait();
+        tma_load_3d(smem + p.kb_per_split * m_tile_bytes, &map_act, full_bar, 0, t0, kb0);
+        PTTS_TRACE(2);
+        if (p.pdl_trigger == 1) pdl_launch_dependents();
+        PTTS_TRACE(3);
+      }
+    } else if (elect_one()) {
       const uint32_t act_bytes = p.swap ? n_tile_bytes : (GEMM_BK * p.R * p.G * 2);
       const uint32_t w_bytes = p.swap ? m_tile_bytes : n_tile_bytes;
       const int npre = min(nkb, p.stages);
@@ -483,21 +498,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         tma_load_3d(p.swap ? m_tile : m_tile + m_tile_bytes, &map_w, full_bar + i, (kb0 + i) * GEMM_BK, f0, 0);
       }
       pdl_wait();
+      // stage, phase, tap and channel block advance by increments: the div/mod forms of these indices made every
+      // iteration a ~1000-cycle dependent chain on this one thread, i.e. one activation tile requested per 0.5 us
+      int s = 0, tap = kb0 / p.cblocks, cb = kb0 - tap * p.cblocks;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages;
-        const int kb = kb0 + i;
-        const int tap = kb / p.cblocks;
-        const int c0 = (kb - tap * p.cblocks) * GEMM_BK;
         uint8_t* m_tile = smem + s * stage_bytes;
         uint8_t* n_tile = m_tile + m_tile_bytes;
         if (i >= npre) {
-          const uint32_t ph = (i / p.stages) & 1;
           mbar_wait(empty_bar + s, ph ^ 1);
           mbar_arrive_expect_tx(full_bar + s, act_bytes + w_bytes);
-          tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
+          tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, (kb0 + i) * GEMM_BK, f0, 0);
         }
-        tma_load_3d(p.swap ? n_tile : m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
+        tma_load_3d(p.swap ? n_tile : m_tile, &map_act, full_bar + s, cb * GEMM_BK, t0 + tap, b0);
         if (i == 0) PTTS_TRACE(2);
+        if (++cb == p.cblocks) { cb = 0; ++tap; }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
       }
       if (p.pdl_trigger == 1) pdl_launch_dependents();
       PTTS_TRACE(3);
@@ -507,7 +523,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     // Per k-block: one barrier wait, four MMAs, one commit.  (Electing a lane, fencing and re-converging the warp in
     // every iteration cost ~600 cycles of single-thread latency per k-block, more than the MMAs themselves.)
     const uint32_t idesc = make_idesc_f16_m128(p.BN);
-    if (elect_one()) {
+    if (p.resident) {
+      if (elect_one()) {
+        const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem));
+        const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem + p.kb_per_split * m_tile_bytes));
+        const uint32_t a_adv = static_cast<uint32_t>(m_tile_bytes) >> 4, b_adv = static_cast<uint32_t>(n_tile_bytes) >> 4;
+        mbar_wait(full_bar, 0);
+        tc_fence_after();
+        PTTS_TRACE(4);
+        for (int i = 0; i < nkb; ++i) {
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_f16(tmem_base, da0 + static_cast<uint64_t>(i) * a_adv + 2 * k, db0 + static_cast<uint64_t>(i) * b_adv + 2 * k, idesc, (i | k) != 0);
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else if (elect_one()) {
       const uint64_t d0 = make_sw128_kmajor_desc(smem_u32(smem));
       const uint32_t stage_adv = static_cast<uint32_t>(stage_bytes) >> 4, b_adv = static_cast<uint32_t>(m_tile_bytes) >> 4;
       int s = 0;
@@ -635,22 +666,28 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
         tma_load_3d(smem + i * stage_bytes + m_tile_bytes, &map_w, full_bar + i, (i % nkb) * GEMM_BK, f0, 0);
       }
       pdl_wait();
-      int it = 0;
+      int it = 0, s = 0;
+      uint32_t ph = 0;
+      // (stream, first row) of the tile advance by increments as well: no division on this thread's critical path
+      int tb = static_cast<int>(blockIdx.x) / tiles_t, tt = static_cast<int>(blockIdx.x) - tb * tiles_t;
+      const int adv_b = static_cast<int>(gridDim.x) / tiles_t, adv_t = static_cast<int>(gridDim.x) - adv_b * tiles_t;
       for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x) {
-        const int tb = tile / tiles_t;
-        const int b0 = tb * p.G, t0 = (tile - tb * tiles_t) * p.R;
+        const int b0 = tb * p.G, t0 = tt * p.R;
+        int tap = 0, cb = 0;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % p.stages;
-          const int tap = kb / p.cblocks;
-          const int c0 = (kb - tap * p.cblocks) * GEMM_BK;
           uint8_t* m_tile = smem + s * stage_bytes;
           if (it >= npre) {
-            mbar_wait(empty_bar + s, ((it / p.stages) & 1) ^ 1);
+            mbar_wait(empty_bar + s, ph ^ 1);
             mbar_arrive_expect_tx(full_bar + s, bytes);
             tma_load_3d(m_tile + m_tile_bytes, &map_w, full_bar + s, kb * GEMM_BK, f0, 0);
           }
-          tma_load_3d(m_tile, &map_act, full_bar + s, c0, t0 + tap, b0);
+          tma_load_3d(m_tile, &map_act, full_bar + s, cb * GEMM_BK, t0 + tap, b0);
+          if (++cb == p.cblocks) { cb = 0; ++tap; }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
+        tb += adv_b;
+        tt += adv_t;
+        if (tt >= tiles_t) { tt -= tiles_t; ++tb; }
       }
       if (p.pdl_trigger != 0) pdl_launch_dependents();
     }

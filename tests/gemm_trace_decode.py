@@ -12,7 +12,7 @@ cases = [(64, 512, 512, "flow.mlp"), (64, 1024, 1024, "out_proj"), (64, 3072, 10
 MAXC = 160
 for rows, feats, k, nm in cases:
     us = C.c_float(); n = C.c_int32(); st = np.zeros(16 * MAXC, np.int64)
-    _lib.check(L.ptts_test_gemm_trace(0, rows, feats, k, 1, 0, 20, C.byref(us), st.ctypes.data_as(C.c_void_p), MAXC, C.byref(n)))
+    _lib.check(L.ptts_test_gemm_trace(0, rows, feats, k, 0, 0, 20, C.byref(us), st.ctypes.data_as(C.c_void_p), MAXC, C.byref(n)))
     s = st.reshape(MAXC, 16)[: n.value]
     print(f"{nm}: rows={rows} F={feats} K={k}: {us.value:.2f} us/launch back-to-back, {n.value} CTAs")
     ok = s[:, 9] >= 0
