@@ -309,7 +309,7 @@ def run_gpu(args):
                                    "same way is subtracted; all launches of the kernel function are pooled"}
         line["kernel_functions"] = [{"kernel": k, "launches_per_step": v["launches"] / n_prof, "us_per_step": v["us"] / n_prof,
                                      "share": v["us"] / tot} for k, v in sorted(fns.items(), key=lambda kv: -kv[1]["us"])]
-        line["kernel_classes"] = classes[:14]
+        line["kernel_classes"] = classes
         line["step_device_us_sum_of_kernels"] = tot / n_prof
         # time to first audio: open -> first 1920-sample frame on the host, single stream (configs[0] shape)
         ttfa = []

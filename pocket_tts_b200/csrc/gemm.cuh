@@ -27,6 +27,7 @@
 // then all 12 warps store the tile.  Launched with programmatic dependent launch: everything before
 // griddepcontrol.wait (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail.
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace ptts {
@@ -184,9 +185,34 @@ __device__ __forceinline__ void cluster_sync_relaxed() {
 // Must inline into the kernel: `p` then stays in the constant bank.  Out of line, the by-reference parameter block
 // lives in local memory, and with a 200 KB shared-memory carve-out the remaining L1 cannot hold 384 threads' copies,
 // so every field access became an L2 round trip (measured: 6-11 us per 128-row tile instead of ~1 us).
+// Tile-invariant part of the fast path below (lane -> (row slot, feature quad), per-feature vectors).  The persistent
+// kernel computes it once per CTA: done per tile it was ~260 instructions and a dependent global load (the bias) at the
+// head of every 128-row tile, as much work as the store loop itself (ncu: 2.5 M of 6.9 M warp instructions).
+struct EpiHoist {
+  int my_sub, q, rows_per_iter, f;
+  float bv[4], sv[4], wv[4];
+};
+__device__ __forceinline__ void epi_hoist_init(const GemmParams& p, int f0, int tid, EpiHoist& h) {
+  const GemmEpi& e = p.epi;
+  const int fv = (p.swap ? GEMM_BM : p.BN) / 4;
+  const int lane = tid & 31;
+  const int lanes_per_row = fv <= 32 ? fv : 32;
+  h.rows_per_iter = 32 / lanes_per_row;
+  h.my_sub = lane / lanes_per_row;
+  h.q = lane - h.my_sub * lanes_per_row;
+  h.f = f0 + h.q * 4;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { h.bv[c] = 0.f; h.sv[c] = 1.f; h.wv[c] = 1.f; }
+  if (h.my_sub < h.rows_per_iter && h.f < p.F) {
+    if (e.wscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(e.wscale + h.f)); h.wv[0] = t4.x; h.wv[1] = t4.y; h.wv[2] = t4.z; h.wv[3] = t4.w; }
+    if (e.bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(e.bias + h.f)); h.bv[0] = t4.x; h.bv[1] = t4.y; h.bv[2] = t4.z; h.bv[3] = t4.w; }
+    if (e.fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(e.fscale + h.f)); h.sv[0] = t4.x; h.sv[1] = t4.y; h.sv[2] = t4.z; h.sv[3] = t4.w; }
+  }
+}
+
 template <int V, int M>
 __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0,
-                                            int tid, int nthreads, int rank, int nsplit) {
+                                            int tid, int nthreads, int rank, int nsplit, const EpiHoist* hp = nullptr) {
   constexpr bool GEN = (M == EPI_GENERIC);
   const GemmEpi& e = p.epi;
   const bool has_bias = GEN ? e.bias != nullptr : (M & EPI_BIAS) != 0;
@@ -220,15 +246,13 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
     if (ok) {
       int nrows = min(tile_rows, T - t0);
       if (!swap) nrows = min(nrows, R);
-      const int lanes_per_row = fv;  // 4..32, divides 32 when a power of two; otherwise the spare lanes idle
-      const int rows_per_iter = 32 / lanes_per_row;
-      const int my_sub = lane / lanes_per_row, q = lane - my_sub * lanes_per_row;
-      const int f = f0 + q * 4;
+      EpiHoist hl;
+      if (!hp) epi_hoist_init(p, f0, tid, hl);  // one tile per CTA: nothing to hoist over
+      const EpiHoist& h = hp ? *hp : hl;
+      const int rows_per_iter = h.rows_per_iter, my_sub = h.my_sub, q = h.q, f = h.f;
       if (my_sub < rows_per_iter && f < F) {
-        float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f}, wv[4] = {1.f, 1.f, 1.f, 1.f};
-        if (GEN && wscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(wscale + f)); wv[0] = t4.x; wv[1] = t4.y; wv[2] = t4.z; wv[3] = t4.w; }
-        if (has_bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + f)); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
-        if (has_fscale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(fscale + f)); sv[0] = t4.x; sv[1] = t4.y; sv[2] = t4.z; sv[3] = t4.w; }
+        const float bv[4] = {h.bv[0], h.bv[1], h.bv[2], h.bv[3]}, sv[4] = {h.sv[0], h.sv[1], h.sv[2], h.sv[3]};
+        const float wv[4] = {h.wv[0], h.wv[1], h.wv[2], h.wv[3]};
         const int ld_g = e.gate_map.ld, ld_r = e.res_map.ld, ld_a = e.out32_map.ld, ld_h = e.out16_map.ld;
         const float* gate_p = has_gate ? e.gate + g0 + f : nullptr;
         const float* res_p = has_res ? e.res + r0 + f : nullptr;
@@ -238,67 +262,80 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 #pragma unroll
         for (int k = 0; k < GEMM_MAX_SPLIT; ++k) peer[k] = (nsplit > 1 && k < nsplit) ? map_to_rank(stile_addr, k) : stile_addr;
         const int step = nwarps * nsplit * rows_per_iter;
-        // Rows are taken two at a time: the residual / gate rows of both are requested before the first store (four at a
-        // time measured no faster and spilled in the persistent kernel).
-        // One row per trip made every trip a full memory round trip (the compiler may not move a load above the
-        // previous row's store to a possibly aliasing tensor), ~0.35 us x 7-11 trips per 128-row tile.
-        constexpr int U = GEN ? 1 : 2;  // the catch-all shape keeps every optional tensor live: no room to prefetch
+        // Rows are taken U at a time, branch-free: every load of the U rows (residual, gate, staged accumulators) is issued
+        // first, then the arithmetic of all rows interleaves, then the stores (predicated on row < nrows).  One row per
+        // trip was one full memory round trip per row (a load may not move above the previous row's store to a possibly
+        // aliasing tensor) and, with 2-3 warps per scheduler, one long dependent chain with nothing to overlap it.
+        // U = 4 for whole tiles (persistent / unsplit kernels); a split-K cluster hands each warp at most a row or two, where
+        // unrolling would only add clamped duplicate DSMEM reads; the catch-all shape has no registers to spare.
+        auto run = [&](auto uc) {
+        constexpr int U = decltype(uc)::value;
         for (int row_b = (rank * nwarps + warp) * rows_per_iter + my_sub; row_b < nrows; row_b += step * U) {
-          float4 g4[U], r4[U];
+          float4 g4[U], r4[U], a4[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int row = row_b + u * step;
-            if (row < nrows) {
-              if (has_gate) g4[u] = *reinterpret_cast<const float4*>(gate_p + static_cast<long long>(row) * ld_g);
-              if (has_res) r4[u] = *reinterpret_cast<const float4*>(res_p + static_cast<long long>(row) * ld_r);
-            }
+            const int row = min(row_b + u * step, nrows - 1);  // clamped: rows past the tile are computed and dropped
+            if (has_gate) g4[u] = *reinterpret_cast<const float4*>(gate_p + static_cast<long long>(row) * ld_g);
+            if (has_res) r4[u] = *reinterpret_cast<const float4*>(res_p + static_cast<long long>(row) * ld_r);
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const int row = row_b + u * step;
-            if (row >= nrows) break;
+            const int row = min(row_b + u * step, nrows - 1);
             const uint32_t toff = static_cast<uint32_t>(row * LD + q * 4) * 4u;
-            float4 a4;
             if (nsplit == 1) {
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(stile_addr + toff));
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a4[u].x), "=f"(a4[u].y), "=f"(a4[u].z), "=f"(a4[u].w) : "r"(stile_addr + toff));
             } else {  // split-K: sum the cluster's partial tiles in rank order (bit-reproducible)
               float4 t[GEMM_MAX_SPLIT];
 #pragma unroll
               for (int k = 0; k < GEMM_MAX_SPLIT; ++k)
                 if (k < nsplit) t[k] = ld_dsmem_f4(peer[k] + toff);
-              a4 = t[0];
+              a4[u] = t[0];
 #pragma unroll
               for (int k = 1; k < GEMM_MAX_SPLIT; ++k)
-                if (k < nsplit) { a4.x += t[k].x; a4.y += t[k].y; a4.z += t[k].z; a4.w += t[k].w; }
+                if (k < nsplit) { a4[u].x += t[k].x; a4[u].y += t[k].y; a4[u].z += t[k].z; a4[u].w += t[k].w; }
             }
-            float v[4] = {a4.x, a4.y, a4.z, a4.w};
+          }
+          float v[U][4];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const float av[4] = {a4[u].x, a4[u].y, a4[u].z, a4[u].w};
             const float gv[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
             const float rv[4] = {r4[u].x, r4[u].y, r4[u].z, r4[u].w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              float x = v[c];
+              float x = av[c];
               if (GEN && wscale) x *= wv[c];
               if (has_bias) x += bv[c];
               x = epi_act(act, x) * alpha;
               if (has_fscale) x *= sv[c];
               if (has_gate) x *= gv[c];
               if (has_res) x += rv[c];
-              v[c] = x;
+              v[u][c] = x;
             }
-            if (has_o32) *reinterpret_cast<float4*>(o32_p + static_cast<long long>(row) * ld_a) = make_float4(v[0], v[1], v[2], v[3]);
-            if (has_o16) {
-              if (elu16) {
+          }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) v[c] = elu1_fast(v[c]);
+          for (int u = 0; u < U; ++u) {
+            const int row = row_b + u * step;
+            if (row < nrows) {
+              if (has_o32) *reinterpret_cast<float4*>(o32_p + static_cast<long long>(row) * ld_a) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+              if (has_o16) {
+                float w4[4] = {v[u][0], v[u][1], v[u][2], v[u][3]};
+                if (elu16) {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) w4[c] = elu1_fast(w4[c]);
+                }
+                const __half2 h0v = __floats2half2_rn(w4[0], w4[1]), h1v = __floats2half2_rn(w4[2], w4[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&h0v);
+                pk.y = *reinterpret_cast<const uint32_t*>(&h1v);
+                *reinterpret_cast<uint2*>(o16_p + static_cast<long long>(row) * ld_h) = pk;
               }
-              const __half2 h0v = __floats2half2_rn(v[0], v[1]), h1v = __floats2half2_rn(v[2], v[3]);
-              uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&h0v);
-              pk.y = *reinterpret_cast<const uint32_t*>(&h1v);
-              *reinterpret_cast<uint2*>(o16_p + static_cast<long long>(row) * ld_h) = pk;
             }
           }
         }
+        };
+        if (GEN || nsplit > 1) run(std::integral_constant<int, 1>{});
+        else run(std::integral_constant<int, 4>{});
       }
       return;
     }
@@ -396,17 +433,17 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 }
 
 __device__ __forceinline__ void epi_dispatch(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0, int tid,
-                                             int nthreads, int rank, int nsplit) {
+                                             int nthreads, int rank, int nsplit, const EpiHoist* hp = nullptr) {
   if (!p.vec4) {
     epi_store_tile<1, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit);
     return;
   }
   switch (p.epi_mask) {
 #define PTTS_EPI_CASE(MASK) \
-  case (MASK): epi_store_tile<4, (MASK)>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit); break;
+  case (MASK): epi_store_tile<4, (MASK)>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit, hp); break;
     PTTS_EPI_SHAPES(PTTS_EPI_CASE)
 #undef PTTS_EPI_CASE
-    default: epi_store_tile<4, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit); break;
+    default: epi_store_tile<4, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit, hp); break;
   }
 }
 
@@ -718,6 +755,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
     __syncwarp();
   } else {
     const int etid = threadIdx.x - 64;
+    EpiHoist hoist;
+    epi_hoist_init(p, f0, etid, hoist);  // constants (bias, scales): before the dependency resolves
     pdl_wait();  // epilogue tensors (residual, outputs) belong to earlier kernels until they have completed
     int j = 0;
     for (int tile = blockIdx.x; tile < p.n_act_tiles; tile += gridDim.x, ++j) {
@@ -748,7 +787,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __g
       }
       asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // tile staged
       if (warp == 2 && j < 3) PTTS_TRACE(j * 4 + 2);
-      epi_dispatch(p, smem_u32(stile), LD, f0, t0, b0, etid, GEMM_THREADS - 64, 0, 1);
+      epi_dispatch(p, smem_u32(stile), LD, f0, t0, b0, etid, GEMM_THREADS - 64, 0, 1, p.vec4 ? &hoist : nullptr);
       if (warp == 2 && j < 3) PTTS_TRACE(j * 4 + 3);
       asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // staging buffer free
     }
