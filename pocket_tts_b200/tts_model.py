@@ -4,14 +4,13 @@
 Same names, argument meaning and error behaviour as the Rust API the `pocket-tts-cuda` crate keeps
 (INTEGRATION.md): `load` / `load_with_params`, `get_voice_state_from_prompt_file|tensor`,
 `generate`, `generate_stream`, plus the public fields `temp`, `lsd_decode_steps`, `eos_threshold`.
-Host text preparation follows tts_model.rs:968-969,1194-1237.  Tokenisation itself is outside the
-hot path: pass `tokenizer=` (any callable str -> list[int], e.g. a
-sentencepiece.SentencePieceProcessor(...).encode) or call the `*_tokens` methods with ids.
+Host text preparation (pause parsing, prompt normalisation, sentence packing, Unigram tokenizer) lives in `text.py`
+(SURVEY 8f N2), output formats in `audio.py` (N4).  Pass `tokenizer=` (a `text.UnigramTokenizer`, or any callable
+str -> list[int]) or call the `*_tokens` methods with ids.
 """
 from __future__ import annotations
 
 import json
-import re
 import struct
 from pathlib import Path
 from typing import Callable, Iterator
@@ -27,52 +26,18 @@ DEFAULT_LSD_DECODE_STEPS = 1
 DEFAULT_EOS_THRESHOLD = -4.0
 DEFAULT_VARIANT = "b6369a24"
 
-_PAUSE_RE = re.compile(r"\[pause:(\d+(?:\.\d+)?)(ms|s)\]")  # pause.rs:34-37
-
-
-def strip_pause_markers(text: str) -> str:
-    return _PAUSE_RE.sub(" ", text)
-
-
-def prepare_text_prompt(text: str) -> str:
-    """tts_model.rs:1194-1227"""
-    text = strip_pause_markers(text).strip()
-    if not text:
-        return "."
-    text = text.replace("\n", " ").replace("\r", " ").replace("  ", " ")
-    word_count = len(text.split())
-    if not text[0].isupper():
-        text = text[0].upper() + text[1:]
-    if text[-1].isalnum():
-        text += "."
-    if word_count < 5:
-        text = " " * 8 + text
-    return text
-
-
-def estimate_frames_after_eos(text: str) -> int:
-    """tts_model.rs:1230-1237"""
-    return 5 if len(text.split()) <= 4 else 3
-
-
-def estimate_generation_steps(text: str) -> int:
-    """tts_model.rs:968,1127-1130: (words(prepared) + 2) * 13"""
-    return (len(prepare_text_prompt(text).split()) + 2) * 13
-
-
-def silence_samples(duration_ms: int, sample_rate: int = SAMPLE_RATE) -> int:
-    """pause.rs:183-185"""
-    return (int(duration_ms) * int(sample_rate)) // 1000
+from .text import (UnigramTokenizer, estimate_frames_after_eos, estimate_generation_steps, long_form_segments,  # noqa: F401
+                   max_gen_len, parse_text_with_pauses, prepare_text_prompt, silence_samples, split_into_best_sentences,
+                   strip_pause_markers)
 
 
 def parse_pauses(text: str) -> list[tuple[str, int]]:
-    """Explicit `[pause:Xms|Xs]` segmentation of generate_stream_long (tts_model.rs:1074-1127):
-    returns [(text_segment, pause_ms_after)], pause 0 for the last segment."""
+    """Explicit `[pause:Xms|Xs]` markers only: [(text_segment, pause_ms_after)], pause 0 for the last segment.
+    (generate_stream_long itself also inserts natural pauses: text.long_form_segments.)"""
+    from .text import _EXPLICIT, _duration_ms
     out, last = [], 0
-    for m in _PAUSE_RE.finditer(text):
-        val, unit = float(m.group(1)), m.group(2)
-        ms = int(val) if unit == "ms" else int(val * 1000.0)
-        out.append((text[last:m.start()], ms))
+    for m in _EXPLICIT.finditer(text):
+        out.append((text[last:m.start()], _duration_ms(m.group(1), m.group(2))))
         last = m.end()
     out.append((text[last:], 0))
     return out
@@ -170,10 +135,17 @@ class TTSModel:
             self.engine.sync()
             self.engine.close_stream(int(slot))
 
+    def split_into_best_sentences(self, text: str) -> list[str]:
+        """tts_model.rs:603-684: chunks of at most 50 tokens on sentence boundaries."""
+        return split_into_best_sentences(text, lambda s: len(self._tokens(s)))
+
     def generate_stream(self, text: str, voice: Voice, seed: int = 0) -> Iterator[np.ndarray]:
-        prepared = prepare_text_prompt(text)
-        yield from self.generate_stream_tokens(self._tokens(prepared), voice, (len(prepared.split()) + 2) * 13,
-                                               estimate_frames_after_eos(text), seed=seed)
+        """tts_model.rs:894-913: every chunk restarts from the (immutable) voice state, frames come out in order."""
+        for chunk in self.split_into_best_sentences(text):
+            # generate_stream_segment re-prepares its chunk (tts_model.rs:941-969)
+            prepared = prepare_text_prompt(chunk)
+            yield from self.generate_stream_tokens(self._tokens(prepared), voice, max_gen_len(prepared),
+                                                   estimate_frames_after_eos(chunk), seed=seed)
 
     def generate(self, text: str, voice: Voice, seed: int = 0) -> np.ndarray:
         chunks = list(self.generate_stream(text, voice, seed))
@@ -182,12 +154,27 @@ class TTSModel:
         return np.concatenate(chunks, axis=2)[0]
 
     def generate_stream_long(self, text: str, voice: Voice, seed: int = 0) -> Iterator[np.ndarray]:
-        """tts_model.rs:1074-1127 for explicit pause markers: text segments interleaved with host zeros."""
-        for seg, pause_ms in parse_pauses(text):
-            if seg.strip():
-                yield from self.generate_stream(seg, voice, seed)
-            if pause_ms > 0:
-                yield np.zeros((1, 1, silence_samples(pause_ms, self.sample_rate)), np.float32)
+        """tts_model.rs:1074-1127: text segments interleaved with host zeros for explicit `[pause:..]` markers and
+        natural pauses (ellipsis 500 ms, comma 200 ms)."""
+        for kind, val in long_form_segments(text):
+            if kind == "text":
+                yield from self.generate_stream(val, voice, seed)
+            else:
+                yield np.zeros((1, 1, silence_samples(val, self.sample_rate)), np.float32)
+
+    def long_form_request(self, text: str, seed: int = 0, noise_fn=None) -> list[tuple]:
+        """The same segmentation as a BatchScheduler request: [("text", StreamSpec) | ("pause", ms)]."""
+        req: list[tuple] = []
+        for kind, val in long_form_segments(text):
+            if kind == "pause":
+                req.append(("pause", val))
+                continue
+            for chunk in self.split_into_best_sentences(val):
+                prepared = prepare_text_prompt(chunk)
+                req.append(("text", StreamSpec(self._tokens(prepared), max_gen_len(prepared), estimate_frames_after_eos(chunk),
+                                               self.eos_threshold, self.temp, seed,
+                                               noise_fn(max_gen_len(prepared)) if noise_fn else None)))
+        return req
 
     def close(self):
         self.engine.close()
