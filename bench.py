@@ -194,7 +194,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     wnp = synth.make_weights(1234)
-    eng = Engine(wnp, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3)
+    eng = Engine(wnp, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3, int8_weights=args.int8)
     del wnp
     voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
     base = rank * STREAMS  # request ids of this shard
@@ -351,7 +351,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=STREAMS,
                     help="concurrent streams per GPU (default 64 = BASELINE configs[1]; 256/512 explore configs[3]/[4] shapes)")
+    ap.add_argument("--int8", action="store_true",
+                    help="per-tensor int8 weights (reference quantize.rs scheme), one-byte codes expanded in the decode GEMMs: configs[3] with --streams 256")
     args = ap.parse_args()
+    if args.int8:
+        CONFIG["workload"] = CONFIG["workload"].replace("f16-operand", "int8-weight (non-headline)")
+        CONFIG["weights"] = "int8 per-tensor codes in HBM, f16 MMA operands, scale in the epilogue"
     if args.streams != STREAMS:
         globals()["STREAMS"] = args.streams
         CONFIG["streams_per_gpu"] = args.streams

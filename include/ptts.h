@@ -163,6 +163,12 @@ int32_t ptts_profile_overhead(ptts_engine* e, float* ms_out);
  * split_k > 1 exercises the atomic split-K epilogue. */
 int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const float* bias, float* d, int32_t rows,
                        int32_t feats, int32_t k, int32_t mode, int32_t split_k, int32_t act, int32_t use_simt);
+/* The int8 weight path of the decode (swap-AB) GEMM: w is quantised per tensor with the reference's scheme
+ * (crates/pocket-tts/src/quantize.rs:65-94: scale = absmax / 127, codes clamp(round(w / scale), -127, 127)),
+ * D = (A . codes^T) * scale.  storage 1 streams one-byte codes from HBM and expands them in shared memory
+ * (production), 0 streams an f16 copy of the same codes; both must give bit-identical D.  scale_out gets the scale. */
+int32_t ptts_test_gemm_int8(int32_t device, const float* a, const float* w, float* d, int32_t rows, int32_t feats,
+                            int32_t k, int32_t split_k, int32_t storage, float* scale_out);
 /* Bring-up probe: back-to-back launches of one GEMM with per-CTA %globaltimer stamps (10 per CTA, ns). */
 int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_t k, int32_t mode, int32_t split_k,
                              int32_t iters, float* us_per_launch, int64_t* stamps, int32_t max_ctas, int32_t* n_ctas);

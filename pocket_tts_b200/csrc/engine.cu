@@ -54,6 +54,7 @@ static constexpr int N_BINS = 4000;
 struct Weight16 {   // GEMM operand [Fpad][K] f16, K-major
   DevBuf<__half> w;
   DevBuf<float> wscale;  // int8 mode: the operand holds the integer codes, wscale[f] the per-tensor scale of row f
+  DevBuf<int8_t> q8;     // int8 mode: the same codes as one byte each, [Fpad][K]; what the decode (swap-AB) GEMMs stream from HBM
   int F = 0, Fpad = 0, K = 0;
 };
 
@@ -326,6 +327,14 @@ static void upload_f16(Weight16& dst, const std::vector<float>& rows, int F, int
     for (int f = 0; f < F; ++f) if (scales[f] > 0.f) ws[f] = scales[f];
     dst.wscale.alloc(ws.size());
     PTTS_CUDA(cudaMemcpy(dst.wscale.p, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
+    bool all = true;
+    for (int f = 0; f < F; ++f) all = all && scales[f] > 0.f;
+    if (all && K % 64 == 0) {  // every row quantised: one-byte codes for the in-kernel dequant path (gemm.cuh, w_int8)
+      std::vector<int8_t> q((size_t)dst.Fpad * K, 0);
+      for (size_t i = 0; i < (size_t)F * K; ++i) q[i] = (int8_t)__half2float(h[i]);  // |code| <= 127, exact
+      dst.q8.alloc(q.size());
+      PTTS_CUDA(cudaMemcpy(dst.q8.p, q.data(), q.size(), cudaMemcpyHostToDevice));
+    }
   }
 }
 
@@ -741,7 +750,10 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     p.tmem_cols = pow2_at_least(p.BN);
     // the epilogue re-uses the stage buffers for its staged f32 tile
     while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;
-    smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
+    // int8 storage: the weight tile arrives as bytes and warps 2-5 expand it to the f16 operand in shared memory
+    // (reserved[7] = 1: test hook, stream the f16 copy of the codes instead -- results must be bit-identical)
+    p.w_int8 = (swap && w.q8.p && !cfg.debug_gemm && cfg.reserved[7] == 0) ? 1 : 0;
+    smem = (size_t)p.stages * stage_bytes + 8 * (4 * p.stages + 1) + 16 + 1024;
     p.resident = (swap && taps == 1 && n_streams == 1 && a.cap == 1 && p.kb_per_split <= p.stages && !cfg.debug_gemm &&
                   cfg.reserved[6] == 0) ? 1 : 0;   // reserved[6] = 1: test hook, the staged pipeline instead
   }
@@ -753,7 +765,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
 
   // algorithmic traffic: weights once, the distinct activation rows once, every epilogue tensor once
   const double act_rows = (double)n_streams * (T + taps - 1);
-  double bytes = (double)F * w.K * 2 + act_rows * a.C * 2;
+  double bytes = (double)F * w.K * (p.w_int8 ? 1 : 2) + act_rows * a.C * 2;
   bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + (epi.res ? 4 : 0) + (epi.gate ? 4 : 0));
   {
     ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K,
@@ -766,7 +778,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
       const CUtensorMap& ma = p.resident ? tmaps.get(a.ptr, 64, a.Tpad, a.C / 64, a.C, 64, p.BN, p.kb_per_split)
                               : swap     ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
                                          : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
-      const CUtensorMap& mw = tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
+      const CUtensorMap& mw = p.w_int8 ? tmaps.get_u8(w.q8.p, w.K, w.Fpad, 128)
+                                       : tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
       if (persistent) launch_k(use_pdl, gemm_tc_persistent_kernel, grid, GEMM_THREADS, smem, ls, 1, ma, mw, p);
       else launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);
     }
@@ -1605,6 +1618,36 @@ int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const flo
   e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
   PTTS_CUDA(cudaStreamSynchronize(e.stream));
   PTTS_CUDA(cudaMemcpy(d, out.p, (size_t)rows * feats * 4, cudaMemcpyDeviceToHost));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_test_gemm_int8(int32_t device, const float* a, const float* w, float* d, int32_t rows, int32_t feats,
+                            int32_t k, int32_t split_k, int32_t storage, float* scale_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(a && w && d && rows > 0 && rows <= 256 && feats > 0 && k > 0 && k % 64 == 0, PTTS_ERR_INVALID, "bad test_gemm_int8 arguments");
+  TestCtx t(device, 0);
+  Engine& e = t.e;
+  e.cfg.reserved[0] = 2;                 // weights on MMA-M: the only placement with in-kernel int8 expansion
+  e.cfg.reserved[7] = storage ? 0 : 1;
+  DevBuf<__half> a16;
+  to_f16_dev(a16, a, (size_t)rows * k);
+  float amax = 0.f;
+  for (size_t i = 0; i < (size_t)feats * k; ++i) amax = std::max(amax, std::fabs(w[i]));
+  const float scale = amax / 127.f;
+  PTTS_REQUIRE(scale > 0.f, PTTS_ERR_INVALID, "all-zero weight");
+  Weight16 w16;
+  upload_f16(w16, std::vector<float>(w, w + (size_t)feats * k), feats, k, std::vector<float>(feats, scale));
+  PTTS_REQUIRE(w16.q8.p != nullptr, PTTS_ERR_STATE, "int8 codes were not built");
+  DevBuf<float> out;
+  out.alloc((size_t)rows * feats);
+  GemmEpi ep = epi_none();
+  ep.out32 = out.p; ep.out32_map = plain_map(feats);
+  e.cfg.reserved[2] = split_k;
+  e.gemm_rows(a16.p, rows, k, w16, feats, ep, split_k > 1);
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  PTTS_CUDA(cudaMemcpy(d, out.p, (size_t)rows * feats * 4, cudaMemcpyDeviceToHost));
+  if (scale_out) *scale_out = scale;
   return PTTS_OK;
   PTTS_CATCH
 }

@@ -77,6 +77,7 @@ struct GemmParams {
   int n_act_tiles;          // activation tiles in total (persistent kernel walks them with stride gridDim.x)
   int pdl_trigger;          // where the CTA lets the next kernel launch: 0 entry, 1 all loads issued, 2 accumulator ready
   int resident;             // swap-AB decode GEMM whose whole K slice fits the stages: one barrier, one activation box
+  int w_int8;               // swap-AB only: map_w views one-byte weight codes; warps 2-5 expand each tile to f16 in smem
   GemmEpi epi;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
@@ -176,6 +177,43 @@ __device__ __forceinline__ void cluster_sync_all() {
 // peers' reads does not need.
 __device__ __forceinline__ void cluster_sync_relaxed() {
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
+// int8 weight storage (reference quantize.rs:65-94: per-tensor symmetric codes in [-127, 127]).  TMA drops the raw
+// [128 features][64 k] byte tile (8 KB, dense) into the upper half of the 16 KB operand slot; the 128 threads of warps
+// 2-5 (thread = feature row) pull their 64 bytes into registers, meet at a named barrier (row r's f16 destination
+// overlaps the raw bytes of rows 2r-128 and 2r-127), and write the row back as 64 halves in the SWIZZLE_128B K-major
+// layout the MMA descriptor expects (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).  Codes are exact in
+// f16, so the accumulator is bit-identical to streaming an f16 copy of the codes; the scale stays in the epilogue.
+__device__ __forceinline__ void i8x4_to_f16x4(uint32_t w, uint32_t& lo, uint32_t& hi) {
+  // byte b -> half 0x6400 | (b ^ 0x80) = 1024 + (b + 128); minus 1152 gives b exactly
+  const uint32_t x = w ^ 0x80808080u;
+  const uint32_t a = __byte_perm(x, 0x64646464u, 0x4140);
+  const uint32_t b = __byte_perm(x, 0x64646464u, 0x4342);
+  const __half2 bias = __halves2half2(__ushort_as_half(0x6480), __ushort_as_half(0x6480));  // 1152.0
+  const __half2 ra = __hsub2(*reinterpret_cast<const __half2*>(&a), bias);
+  const __half2 rb = __hsub2(*reinterpret_cast<const __half2*>(&b), bias);
+  lo = *reinterpret_cast<const uint32_t*>(&ra);
+  hi = *reinterpret_cast<const uint32_t*>(&rb);
+}
+__device__ __forceinline__ void expand_i8_tile(uint8_t* tile, int row) {
+  const uint4* src = reinterpret_cast<const uint4*>(tile + GEMM_BM * GEMM_BK + row * GEMM_BK);
+  uint4 raw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) raw[j] = src[j];
+  asm volatile("bar.sync 2, 128;" ::: "memory");  // every raw row is in registers before any f16 row is written
+  uint8_t* dst = tile + row * 128;
+  const int sw = row & 7;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 o0, o1;
+    i8x4_to_f16x4(raw[j].x, o0.x, o0.y);
+    i8x4_to_f16x4(raw[j].y, o0.z, o0.w);
+    i8x4_to_f16x4(raw[j].z, o1.x, o1.y);
+    i8x4_to_f16x4(raw[j].w, o1.z, o1.w);
+    *reinterpret_cast<uint4*>(dst + (((2 * j) ^ sw) << 4)) = o0;
+    *reinterpret_cast<uint4*>(dst + (((2 * j + 1) ^ sw) << 4)) = o1;
+  }
 }
 
 // Second half of the epilogue.  The f32 accumulator tile sits in shared memory as [activation row][feature]
@@ -460,6 +498,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* wfull_bar = tmem_full_bar + 3;      // int8 storage: raw weight bytes landed (per stage)
+  uint64_t* conv_bar = wfull_bar + p.stages;    // int8 storage: f16 operand written by the four converter warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -494,6 +534,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       mbar_init(empty_bar + s, 1);
     }
     mbar_init(tmem_full_bar, 1);
+    if (p.w_int8) {
+      for (int s = 0; s < p.stages; ++s) {
+        mbar_init(wfull_bar + s, 1);
+        mbar_init(conv_bar + s, 4);
+      }
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -505,6 +551,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) PTTS_TRACE(1);
+  constexpr int RAW_OFF = GEMM_BM * GEMM_BK;      // raw byte tile sits in the upper half of its f16 slot
+  constexpr uint32_t RAW_BYTES = GEMM_BM * GEMM_BK;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -517,8 +565,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       // (64 k, BN rows, all k-blocks) = [k-block][row][64] behind them.  One TMA instead of one per k-block: each
       // issue costs this thread ~0.3 us, which at eight k-blocks was the longest phase of the kernel.
       if (elect_one()) {
-        mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(nkb * m_tile_bytes + p.kb_per_split * n_tile_bytes));
-        for (int i = 0; i < nkb; ++i) tma_load_3d(smem + i * m_tile_bytes, &map_w, full_bar, (kb0 + i) * GEMM_BK, f0, 0);
+        if (p.w_int8) {
+          mbar_arrive_expect_tx(wfull_bar, static_cast<uint32_t>(nkb) * RAW_BYTES);
+          for (int i = 0; i < nkb; ++i) tma_load_3d(smem + i * m_tile_bytes + RAW_OFF, &map_w, wfull_bar, (kb0 + i) * GEMM_BK, f0, 0);
+          mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(p.kb_per_split * n_tile_bytes));
+        } else {
+          mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(nkb * m_tile_bytes + p.kb_per_split * n_tile_bytes));
+          for (int i = 0; i < nkb; ++i) tma_load_3d(smem + i * m_tile_bytes, &map_w, full_bar, (kb0 + i) * GEMM_BK, f0, 0);
+        }
         pdl_wait();
         tma_load_3d(smem + p.kb_per_split * m_tile_bytes, &map_act, full_bar, 0, t0, kb0);
         PTTS_TRACE(2);
@@ -531,6 +585,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       const int npre = min(nkb, p.stages);
       for (int i = 0; i < npre; ++i) {
         uint8_t* m_tile = smem + i * stage_bytes;
+        if (p.w_int8) {  // swap only: weights on their own barrier so the expansion can start before the activations exist
+          mbar_arrive_expect_tx(wfull_bar + i, RAW_BYTES);
+          tma_load_3d(m_tile + RAW_OFF, &map_w, wfull_bar + i, (kb0 + i) * GEMM_BK, f0, 0);
+          mbar_arrive_expect_tx(full_bar + i, act_bytes);
+          continue;
+        }
         mbar_arrive_expect_tx(full_bar + i, act_bytes + w_bytes);
         tma_load_3d(p.swap ? m_tile : m_tile + m_tile_bytes, &map_w, full_bar + i, (kb0 + i) * GEMM_BK, f0, 0);
       }
@@ -544,8 +604,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         uint8_t* n_tile = m_tile + m_tile_bytes;
         if (i >= npre) {
           mbar_wait(empty_bar + s, ph ^ 1);
-          mbar_arrive_expect_tx(full_bar + s, act_bytes + w_bytes);
-          tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, (kb0 + i) * GEMM_BK, f0, 0);
+          if (p.w_int8) {
+            mbar_arrive_expect_tx(wfull_bar + s, RAW_BYTES);
+            tma_load_3d(m_tile + RAW_OFF, &map_w, wfull_bar + s, (kb0 + i) * GEMM_BK, f0, 0);
+            mbar_arrive_expect_tx(full_bar + s, act_bytes);
+          } else {
+            mbar_arrive_expect_tx(full_bar + s, act_bytes + w_bytes);
+            tma_load_3d(p.swap ? m_tile : n_tile, &map_w, full_bar + s, (kb0 + i) * GEMM_BK, f0, 0);
+          }
         }
         tma_load_3d(p.swap ? n_tile : m_tile, &map_act, full_bar + s, cb * GEMM_BK, t0 + tap, b0);
         if (i == 0) PTTS_TRACE(2);
@@ -565,6 +631,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem));
         const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem + p.kb_per_split * m_tile_bytes));
         const uint32_t a_adv = static_cast<uint32_t>(m_tile_bytes) >> 4, b_adv = static_cast<uint32_t>(n_tile_bytes) >> 4;
+        if (p.w_int8) mbar_wait(conv_bar, 0);
         mbar_wait(full_bar, 0);
         tc_fence_after();
         PTTS_TRACE(4);
@@ -581,6 +648,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
+        if (p.w_int8) mbar_wait(conv_bar + s, ph);
         mbar_wait(full_bar + s, ph);
         tc_fence_after();
         if (i == 0) PTTS_TRACE(4);
@@ -599,6 +667,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     __syncwarp();
     PTTS_TRACE(5);
   } else if (warp < 6) {
+    if (p.w_int8) {
+      // ===== int8 storage: expand the raw weight tiles to the f16 MMA operand (see expand_i8_tile) =====
+      const int row = (warp - 2) * 32 + lane;
+      if (p.resident) {
+        mbar_wait(wfull_bar, 0);
+        for (int i = 0; i < nkb; ++i) expand_i8_tile(smem + i * m_tile_bytes, row);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tcgen05.mma reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar);
+      } else {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(wfull_bar + s, ph);
+          expand_i8_tile(smem + s * stage_bytes, row);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(conv_bar + s);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
     // ===== epilogue, first half: TMEM -> registers -> smem tile [activation row][feature] (raw f32) =====
     // The pipeline stages are dead once tmem_full has arrived (every MMA has consumed its operands), so the tile
     // is staged over them.  Pitch = features + 4 floats: 16-byte aligned rows, conflict-free in both passes.

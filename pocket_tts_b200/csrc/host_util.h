@@ -127,6 +127,28 @@ class TmapCache {
     return maps_.emplace(k, m).first->second;
   }
 
+  // int8 tensor [d1][d0] (d0 contiguous) through a dense, unswizzled box {64 bytes, box1 rows}: the raw weight-code tile
+  // that the GEMM's converter warps expand to f16 in shared memory.
+  const CUtensorMap& get_u8(const int8_t* ptr, long long d0, long long d1, int box1) {
+    TmapKey k;
+    std::memset(&k, 0, sizeof k);
+    k.ptr = ptr; k.d0 = d0; k.d1 = d1; k.d2 = 1; k.s1 = d0; k.s2 = d0 * d1;
+    k.box1 = box1; k.box2 = -8;  // distinguishes the element type
+    auto it = maps_.find(k);
+    if (it != maps_.end()) return it->second;
+    PTTS_REQUIRE(d0 % 64 == 0 && box1 >= 1 && box1 <= 256, PTTS_ERR_INVALID, "bad int8 TMA geometry %lld x %lld box %d", d0, d1, box1);
+    CUtensorMap m;
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)d0, (cuuint64_t)(d0 * d1)};
+    cuuint32_t box[3] = {64, (cuuint32_t)box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(ptr), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PTTS_REQUIRE(r == CUDA_SUCCESS, PTTS_ERR_CUDA, "cuTensorMapEncodeTiled (u8) failed (%d) dims %lld,%lld box 64,%d", (int)r, d0, d1, box1);
+    return maps_.emplace(k, m).first->second;
+  }
+
  private:
   std::map<TmapKey, CUtensorMap> maps_;
 };

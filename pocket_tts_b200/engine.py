@@ -44,7 +44,8 @@ class Voice:
 
 class Engine:
     def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
-                 kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True, int8_weights: bool = False):
+                 kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True, int8_weights: bool = False,
+                 int8_storage: bool = True):
         L = _lib.lib()
         self._keep = []
         descs = (TensorDesc * len(weights))()
@@ -62,6 +63,7 @@ class Engine:
         cfg.max_batch = max_batch or max_slots
         cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, int(int8_weights), int(cuda_graph), debug_gemm
         cfg.reserved[0] = gemm_mode
+        cfg.reserved[7] = 0 if int8_storage else 1  # test hook: int8 mode streaming f16 copies of the codes instead of bytes
         h = C.c_void_p()
         check(L.ptts_engine_create(C.byref(cfg), descs, len(weights), C.byref(h)))
         self._h = h
@@ -206,6 +208,16 @@ def test_gemm(a, w, bias=None, mode=0, split_k=1, act=0, use_simt=0, device=0):
     check(_lib.lib().ptts_test_gemm(device, _ptr(a), _ptr(w), _ptr(b), _ptr(d), a.shape[0], w.shape[0], a.shape[1], mode,
                                     split_k, act, use_simt))
     return d
+
+
+def test_gemm_int8(a, w, split_k=1, storage=1, device=0):
+    """-> (D [rows, feats], per-tensor scale): the int8 weight path of the decode GEMM (ptts.h)."""
+    a = np.ascontiguousarray(a, np.float32); w = np.ascontiguousarray(w, np.float32)
+    d = np.zeros((a.shape[0], w.shape[0]), np.float32)
+    scale = C.c_float()
+    check(_lib.lib().ptts_test_gemm_int8(device, _ptr(a), _ptr(w), _ptr(d), a.shape[0], w.shape[0], a.shape[1], split_k,
+                                         storage, C.byref(scale)))
+    return d, float(scale.value)
 
 
 def test_conv1d(x, prev, w, bias, device=0):

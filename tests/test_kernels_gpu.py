@@ -53,6 +53,37 @@ def test_gemm(rows, feats, k, mode, split, act, simt):
     assert err < 2e-3, f"max abs err {err}"
 
 
+INT8_CASES = [
+    # rows, feats, k, split_k
+    (64, 3072, 1024, 2),    # FlowLM in_proj at B=64: resident decode mode, 2-CTA cluster
+    (64, 4096, 1024, 1),    # linear1: 16 k-blocks through the stage ring
+    (64, 1024, 4096, 4),    # linear2: ring + cluster split-K
+    (1, 1024, 1024, 8),     # B=1, 8-CTA cluster, two k-blocks per CTA
+    (200, 640, 512, 1),     # ragged rows / features (prefill shape)
+    (256, 128, 64, 1),      # one k-block
+]
+
+
+@pytest.mark.parametrize("rows,feats,k,split", INT8_CASES)
+def test_gemm_int8_storage(rows, feats, k, split):
+    """BASELINE configs[3]: one-byte weight codes streamed from HBM and expanded to f16 in shared memory must be
+    bit-identical to streaming an f16 copy of the same codes, and both equal A . (codes * scale)^T of the reference's
+    per-tensor scheme (crates/pocket-tts/src/quantize.rs:65-94)."""
+    from pocket_tts_b200.engine import test_gemm_int8 as run
+    rng = np.random.default_rng(rows + feats + k)
+    a = rng.standard_normal((rows, k), dtype=np.float32)
+    w = (rng.standard_normal((feats, k), dtype=np.float32) / np.sqrt(k)).astype(np.float32)  # f32: the codes are defined on f32 division
+    w[0, :8] = [w.max(), -np.abs(w).max(), 0.0, 1e-9, -1e-9, w.min(), 0.5 * w.max(), -0.5 * w.max()]  # extremes of the code range
+    got, scale = run(a, w, split_k=split, storage=1)
+    f16_codes, scale2 = run(a, w, split_k=split, storage=0)
+    assert scale == scale2 == np.float32(np.abs(w).max() / np.float32(127.0))
+    np.testing.assert_array_equal(got, f16_codes)
+    codes = np.clip(np.rint(w / np.float32(scale)), -127, 127)
+    want = (torch.from_numpy(f16r(a)).double() @ torch.from_numpy(codes).double().T * scale).float().numpy()
+    err = np.abs(got - want).max()
+    assert err < 2e-3, f"max abs err {err}"
+
+
 CONV_CASES = [(3, 16, 512, 512, 7), (2, 96, 256, 128, 3), (2, 480, 128, 64, 3), (1, 1920, 64, 64, 3), (9, 16, 512, 64, 7),
               (12, 1920, 64, 64, 3), (40, 480, 128, 64, 3)]  # the last two run the persistent kernel
 

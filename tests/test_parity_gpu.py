@@ -303,6 +303,19 @@ def test_int8_weight_mode_matches_reference_quantisation():
     eng.close()
     assert np.abs(np.stack(lat) - ref["latents"]).max() <= LAT_TOL
     assert snr(ref["pcm"], np.stack(pcm)) >= SNR_MIN
+    # one-byte storage (production) vs f16 copies of the same codes: the whole path must be bit-identical
+    eng2 = Engine(wnp, max_slots=2, kv_capacity=128, int8_weights=True, int8_storage=False)
+    voice2 = eng2.voice_from_prompt(prompt)
+    s2 = eng2.open_streams([voice2], [StreamSpec(tok, frames, 0, 1e30, noise=noise)])
+    for f in range(frames):
+        if f:
+            eng2.set_feedback(int(s2[0]), ref["latents"][f - 1])
+        p, _, l, _ = eng2.step(s2)
+        np.testing.assert_array_equal(l[0], lat[f])
+        np.testing.assert_array_equal(p[0], pcm[f])
+    eng2.close_stream(int(s2[0]))
+    voice2.close()
+    eng2.close()
 
 
 def test_continuous_batching_long_form():
