@@ -44,7 +44,12 @@ CONFIG = {"workload": "configs[1]: b6369a24 f16-operand batch 64 concurrent 10 s
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures in profiles/ (bytes)
-TRAFFIC_NCU: dict[str, float] = {}
+# (profiles/r01_top_kernels_ncu_full.csv: one mid-utterance step at 64 streams, mean over the captured launches of each
+# kernel function.  Below the algorithmic bytes because the activations of a step stay in the 126 MB L2.)
+TRAFFIC_NCU: dict[str, float] = {
+    "gemm_tc_kernel": 5.42e6, "flowlm_attn_decode_kernel": 13.76e6, "flow_head_kernel": 9.24e6,
+    "mimi_attn_kernel": 25.46e6, "gemm_tc_persistent_kernel": 20.11e6,
+}
 
 
 def peaks():
@@ -205,15 +210,17 @@ def run_gpu(args):
     def job(host: bool, profile=None):
         slots = eng.open_streams([voice] * STREAMS, specs)
         prev = None
+        t = eng.step_begin(slots) if host else None
         for f in range(FRAMES):
             if host:
-                # public pipelined call: flags of frame f are needed to form the next batch, PCM of frame f-1 is
-                # fetched while frame f's language-model half runs
-                t = eng.step_begin(slots)
+                # public pipelined calls: frame f+1 is enqueued ahead of frame f's flags (PTTS_STEP_AHEAD; every stream
+                # runs to max_gen_len here, so the host knows frame f is not the last), the flags of frame f are awaited
+                # and read, then the PCM of frame f-1 is fetched while the device is already on frame f+1
+                nxt = eng.step_begin(slots, ahead=True) if f + 1 < FRAMES else None
                 fin, _, _ = eng.step_flags(t)
                 if prev is not None:
                     pcm = eng.step_pcm(prev)
-                prev = t
+                prev, t = t, nxt
             elif profile is not None and f in profile:
                 eng.profile(True); eng.step_device(slots); eng.profile(False)
             else:

@@ -119,12 +119,21 @@ int32_t ptts_step(ptts_engine* e, const int32_t* slots, int32_t n, float* pcm_ou
 
 /* The same step split so the host can overlap frames: the codec half of frame n (Mimi transformer + SEANet, which
  * feeds nothing back) runs on its own CUDA stream while the language-model half of frame n+1 runs.
- *   ticket = ptts_step_begin(e, slots, n, want_pcm)        enqueue only, returns a ticket >= 0
+ *   ticket = ptts_step_begin(e, slots, n, flags)           enqueue only, returns a ticket >= 0
  *   ptts_step_flags(e, ticket, finished, latent, logit)    waits for the language-model half (needed to choose the
- *                                                          next batch); must precede the next ptts_step_begin
+ *                                                          next batch); in step order
  *   ptts_step_pcm(e, ticket, pcm_out)                      waits for the codec half; may follow the next begin
- * At most two steps are in flight.  ptts_step == begin + flags + pcm. */
-int64_t ptts_step_begin(ptts_engine* e, const int32_t* slots, int32_t n, int32_t want_pcm);
+ * flags: PTTS_STEP_PCM copies the frame's PCM back to the host; PTTS_STEP_AHEAD lets this step be enqueued before the
+ * flags of the previous one have been fetched, so the device never waits for the host between frames.  A stream that
+ * turns out to have ended on the previous step then runs one frame past its end: ptts_step_flags reports
+ * PTTS_FRAME_OVERRUN for that row, the caller drops the row's latent / PCM and closes the slot (the reference stops
+ * at the last frame, tts_model.rs:1055-1069; nothing of the overrun frame is ever emitted).  Needs one spare KV row
+ * (kv_capacity > tokens + max_gen_len), else PTTS_ERR_CAPACITY.  At most one step ahead of unfetched flags, three
+ * tickets in flight.  ptts_step == begin + flags + pcm. */
+#define PTTS_STEP_PCM 1
+#define PTTS_STEP_AHEAD 2
+#define PTTS_FRAME_OVERRUN 2 /* finished[] value: this frame lies past the stream's last one */
+int64_t ptts_step_begin(ptts_engine* e, const int32_t* slots, int32_t n, int32_t flags);
 int32_t ptts_step_flags(ptts_engine* e, int64_t ticket, uint8_t* finished, float* latent_out, float* eos_logit_out);
 int32_t ptts_step_pcm(ptts_engine* e, int64_t ticket, float* pcm_out);
 

@@ -178,11 +178,14 @@ struct Engine {
   DevBuf<__half> ph16, pattn16, pffn16;
   DevBuf<int> prow_seq, prow_pos, ptokens;
   // ---- pinned staging
-  float* pin_pcm[2] = {nullptr, nullptr}; unsigned char* pin_fin[2] = {nullptr, nullptr};
-  float* pin_lat[2] = {nullptr, nullptr}; float* pin_logit[2] = {nullptr, nullptr};
-  cudaEvent_t ev_flags[2] = {nullptr, nullptr}, ev_pcm[2] = {nullptr, nullptr};
+  // a ring of three tickets: with PTTS_STEP_AHEAD step n+1 is enqueued while the flags of step n and the PCM of
+  // step n-1 are still on their way to the host
+  static constexpr int NT = 3;
+  float* pin_pcm[NT] = {}; unsigned char* pin_fin[NT] = {};
+  float* pin_lat[NT] = {}; float* pin_logit[NT] = {};
+  cudaEvent_t ev_flags[NT] = {}, ev_pcm[NT] = {};
   struct Ticket { long long id = -1; int n = 0; bool flags_done = true, pcm_done = true, want_pcm = false; std::vector<int> slot_ids; };
-  Ticket tickets[2];
+  Ticket tickets[NT];
   long long next_ticket = 0;
   void sync_all() { PTTS_CUDA(cudaStreamSynchronize(stream)); PTTS_CUDA(cudaStreamSynchronize(stream_b)); }
   cudaEvent_t ev[10]{};
@@ -218,7 +221,7 @@ struct Engine {
 };
 
 Engine::~Engine() {
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < NT; ++i) {
     if (pin_pcm[i]) cudaFreeHost(pin_pcm[i]);
     if (pin_fin[i]) cudaFreeHost(pin_fin[i]);
     if (pin_lat[i]) cudaFreeHost(pin_lat[i]);
@@ -650,7 +653,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   px32.alloc((size_t)PR * D_MODEL); pqkv32.alloc((size_t)PR * 3 * D_MODEL); pqrot.alloc((size_t)PR * D_MODEL);
   ph16.alloc((size_t)PR * D_MODEL); pattn16.alloc((size_t)PR * D_MODEL); pffn16.alloc((size_t)PR * D_FFN);
   prow_seq.alloc(PR); prow_pos.alloc(PR); ptokens.alloc(PR);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < NT; ++i) {
     PTTS_CUDA(cudaMallocHost(&pin_pcm[i], (size_t)NB * FRAME * 4));
     PTTS_CUDA(cudaMallocHost(&pin_fin[i], NB));
     PTTS_CUDA(cudaMallocHost(&pin_lat[i], (size_t)NB * LDIM * 4));
@@ -1273,27 +1276,31 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
   PTTS_CATCH
 }
 
-static void check_slots(Engine& e, const int32_t* slot_ids, int n) {
+static void check_slots(Engine& e, const int32_t* slot_ids, int n, int steps_in_flight = 0) {
   PTTS_REQUIRE(slot_ids && n >= 1 && n <= e.NB, PTTS_ERR_INVALID, "step: n = %d (max_batch %d)", n, e.NB);
   for (int i = 0; i < n; ++i) {
     const int s = slot_ids[i];
     PTTS_REQUIRE(s >= 0 && s < e.NS && e.slots[s].in_use, PTTS_ERR_STATE, "step: slot %d is not open", s);
     PTTS_REQUIRE(!e.slots[s].finished, PTTS_ERR_STATE, "step: slot %d already finished", s);
-    PTTS_REQUIRE(e.slots[s].own_len < e.KVCAP, PTTS_ERR_CAPACITY, "step: slot %d KV full", s);
+    // a step enqueued ahead of unfetched flags may run past the stream's last frame: its KV row must still exist
+    PTTS_REQUIRE(e.slots[s].own_len + steps_in_flight < e.KVCAP, PTTS_ERR_CAPACITY, "step: slot %d KV full", s);
   }
 }
 
 // ---- pipelined step: begin (enqueue) / flags (language-model results) / pcm (codec result)
-static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, bool want_pcm) {
-  check_slots(e, slot_ids, n);
+static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, int flags) {
+  const bool want_pcm = (flags & PTTS_STEP_PCM) != 0, ahead = (flags & PTTS_STEP_AHEAD) != 0;
   const long long id = e.next_ticket;
-  Engine::Ticket& t = e.tickets[id & 1];
-  PTTS_REQUIRE(t.flags_done && t.pcm_done, PTTS_ERR_STATE, "step %lld still has unfetched results (two steps may be in flight)", t.id);
-  const Engine::Ticket& prev = e.tickets[(id + 1) & 1];
-  PTTS_REQUIRE(prev.flags_done, PTTS_ERR_STATE, "fetch the flags of step %lld before beginning the next step", prev.id);
+  Engine::Ticket& t = e.tickets[id % Engine::NT];
+  PTTS_REQUIRE(t.flags_done && t.pcm_done, PTTS_ERR_STATE, "step %lld still has unfetched results (three steps may be in flight)", t.id);
+  const Engine::Ticket& prev = e.tickets[(id + Engine::NT - 1) % Engine::NT];
+  const Engine::Ticket& prev2 = e.tickets[(id + Engine::NT - 2) % Engine::NT];
+  PTTS_REQUIRE(prev.flags_done || ahead, PTTS_ERR_STATE, "fetch the flags of step %lld before beginning the next step (or pass PTTS_STEP_AHEAD)", prev.id);
+  PTTS_REQUIRE(prev2.flags_done, PTTS_ERR_STATE, "only one step may be enqueued ahead of unfetched flags (step %lld)", prev2.id);
+  check_slots(e, slot_ids, n, prev.flags_done ? 0 : 1);
   e.upload_rows(slot_ids, n);
   e.run_step(n);
-  const int par = (int)(id & 1);
+  const int par = (int)(id % Engine::NT);
   PTTS_CUDA(cudaMemcpyAsync(e.pin_fin[par], e.finished_dev.p, n, cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaMemcpyAsync(e.pin_lat[par], e.latent_out.p, (size_t)n * LDIM * 4, cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaMemcpyAsync(e.pin_logit[par], e.logit_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e.stream));
@@ -1307,14 +1314,20 @@ static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, bool
 }
 
 static void step_flags_impl(Engine& e, long long id, uint8_t* finished, float* latent_out, float* eos_logit_out) {
-  Engine::Ticket& t = e.tickets[id & 1];
-  PTTS_REQUIRE(t.id == id && !t.flags_done, PTTS_ERR_STATE, "ticket %lld is not pending", id);
-  const int par = (int)(id & 1);
+  Engine::Ticket& t = e.tickets[id % Engine::NT];
+  PTTS_REQUIRE(id >= 0 && t.id == id && !t.flags_done, PTTS_ERR_STATE, "ticket %lld is not pending", id);
+  const Engine::Ticket& prev = e.tickets[(id + Engine::NT - 1) % Engine::NT];
+  PTTS_REQUIRE(prev.flags_done, PTTS_ERR_STATE, "flags are fetched in step order: step %lld first", prev.id);
+  const int par = (int)(id % Engine::NT);
   PTTS_CUDA(cudaEventSynchronize(e.ev_flags[par]));
   if (latent_out) std::memcpy(latent_out, e.pin_lat[par], (size_t)t.n * LDIM * 4);
   if (eos_logit_out) std::memcpy(eos_logit_out, e.pin_logit[par], (size_t)t.n * 4);
   for (int i = 0; i < t.n; ++i) {
     SlotHost& sh = e.slots[t.slot_ids[i]];
+    if (sh.finished) {  // enqueued ahead and the stream ended on the step before: this frame is past the end
+      if (finished) finished[i] = PTTS_FRAME_OVERRUN;
+      continue;
+    }
     sh.frames += 1; sh.own_len += 1;
     sh.finished = e.pin_fin[par][i] != 0;
     if (finished) finished[i] = e.pin_fin[par][i];
@@ -1323,9 +1336,9 @@ static void step_flags_impl(Engine& e, long long id, uint8_t* finished, float* l
 }
 
 static void step_pcm_impl(Engine& e, long long id, float* pcm_out) {
-  Engine::Ticket& t = e.tickets[id & 1];
-  PTTS_REQUIRE(t.id == id && !t.pcm_done, PTTS_ERR_STATE, "ticket %lld has no pending PCM", id);
-  const int par = (int)(id & 1);
+  Engine::Ticket& t = e.tickets[id % Engine::NT];
+  PTTS_REQUIRE(id >= 0 && t.id == id && !t.pcm_done, PTTS_ERR_STATE, "ticket %lld has no pending PCM", id);
+  const int par = (int)(id % Engine::NT);
   PTTS_CUDA(cudaEventSynchronize(e.ev_pcm[par]));
   if (pcm_out) {
     PTTS_REQUIRE(t.want_pcm, PTTS_ERR_STATE, "step %lld was begun without PCM read-back", id);
@@ -1334,11 +1347,11 @@ static void step_pcm_impl(Engine& e, long long id, float* pcm_out) {
   t.pcm_done = true;
 }
 
-int64_t ptts_step_begin(ptts_engine* h, const int32_t* slot_ids, int32_t n, int32_t want_pcm) {
+int64_t ptts_step_begin(ptts_engine* h, const int32_t* slot_ids, int32_t n, int32_t flags) {
   try {
     PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
     PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
-    return step_begin_impl(h->e, slot_ids, n, want_pcm != 0);
+    return step_begin_impl(h->e, slot_ids, n, flags);
   } catch (const ptts::Error& ex) {
     g_last_error = ex.what();
     return ex.code;
@@ -1369,7 +1382,7 @@ int32_t ptts_step(ptts_engine* h, const int32_t* slot_ids, int32_t n, float* pcm
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
   Engine& e = h->e;
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
-  const long long id = step_begin_impl(e, slot_ids, n, pcm_out != nullptr);
+  const long long id = step_begin_impl(e, slot_ids, n, pcm_out != nullptr ? PTTS_STEP_PCM : 0);
   step_flags_impl(e, id, finished, latent_out, eos_logit_out);
   step_pcm_impl(e, id, pcm_out);
   return PTTS_OK;

@@ -622,7 +622,8 @@ __global__ void step_begin_kernel(const int* __restrict__ row_seq, const StreamC
   float lat = 0.f, z = 0.f;
   if (k < LDIM) {
     lat = feedback[slot * LDIM + k];
-    if (c.noise) z = c.noise[static_cast<long long>(c.frame) * LDIM + k];
+    // a step enqueued ahead of the host (PTTS_STEP_AHEAD) may run one frame past the end: no noise row exists there
+    if (c.noise) z = c.frame < c.max_gen_len ? c.noise[static_cast<long long>(c.frame) * LDIM + k] : 0.f;
     else if (c.temp > 0.f) z = sqrtf(c.temp) * counter_normal(c.seed, c.frame, k);
     z32[b * LDIM + k] = z;
   }
@@ -649,6 +650,11 @@ __global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCt
     StreamCtl c = ctl[slot];
     const int step = c.frame;
     const float logit = eos_logit[b];
+    if (c.finished) {  // overrun frame of a step enqueued ahead: the stream's counters stay at its last real frame
+      finished_out[b] = 1;
+      logit_out[b] = logit;
+      return;
+    }
     if (logit > c.eos_threshold && c.eos_step < 0) c.eos_step = step;
     int fin = 0;
     if (c.eos_step >= 0 && step >= c.eos_step + c.frames_after_eos) fin = 1;

@@ -122,9 +122,11 @@ class Engine:
         return pcm, fin.astype(bool), lat, logit
 
     # ---- pipelined form: begin -> flags -> (next begin) -> pcm
-    def step_begin(self, slots: np.ndarray, want_pcm: bool = True) -> int:
+    def step_begin(self, slots: np.ndarray, want_pcm: bool = True, ahead: bool = False) -> int:
+        """Enqueue one frame.  ahead=True (PTTS_STEP_AHEAD): the previous step's flags need not have been fetched yet;
+        rows whose stream ended on that previous step come back from step_flags with fin == 2 (frame past the end)."""
         slots = np.ascontiguousarray(slots, dtype=np.int32)
-        t = int(_lib.lib().ptts_step_begin(self._h, _ptr(slots), len(slots), int(want_pcm)))
+        t = int(_lib.lib().ptts_step_begin(self._h, _ptr(slots), len(slots), (1 if want_pcm else 0) | (2 if ahead else 0)))
         check(t)
         self._pending_n = getattr(self, "_pending_n", {})
         self._pending_n[t] = len(slots)
@@ -136,6 +138,7 @@ class Engine:
         lat = np.empty((n, LDIM), np.float32)
         logit = np.empty(n, np.float32)
         check(_lib.lib().ptts_step_flags(self._h, ticket, _ptr(fin), _ptr(lat), _ptr(logit)))
+        self.last_overrun = fin == 2  # rows of a step enqueued ahead whose stream had already ended: drop their frame
         return fin.astype(bool), lat, logit
 
     def step_pcm(self, ticket: int, want: bool = True):

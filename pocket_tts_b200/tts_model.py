@@ -119,18 +119,34 @@ class TTSModel:
         (slot,) = self.engine.open_streams([voice], [spec])
         ids = np.array([slot], np.int32)
         try:
-            # frame n's codec half overlaps frame n+1's language-model half (ptts_step_begin/flags/pcm)
-            ticket = self.engine.step_begin(ids)
-            fin, _, _ = self.engine.step_flags(ticket)
+            # Frame n's codec half overlaps frame n+1's language-model half, and frame n+1 is enqueued before frame n's
+            # flags reach the host (PTTS_STEP_AHEAD) unless frame n is known to be the last (max_gen_len); if frame n
+            # turns out to end the stream at EOS, the frame enqueued ahead is retired unseen.
+            eng = self.engine
+            can_ahead = True
+            ticket = eng.step_begin(ids)
+            issued = 1
             while True:
                 nxt = None
-                if not fin[0]:
-                    nxt = self.engine.step_begin(ids)
-                    fin_next, _, _ = self.engine.step_flags(nxt)
-                yield self.engine.step_pcm(ticket).reshape(1, 1, FRAME)
-                if nxt is None:
+                if issued < max_gen_len and can_ahead:
+                    try:
+                        nxt = eng.step_begin(ids, ahead=True)
+                        issued += 1
+                    except Exception as e:  # no spare KV row: fall back to begin-after-flags
+                        if getattr(e, "code", 0) != -3:
+                            raise
+                        can_ahead = False
+                fin, _, _ = eng.step_flags(ticket)
+                if nxt is None and not fin[0] and issued < max_gen_len:
+                    nxt = eng.step_begin(ids)
+                    issued += 1
+                yield eng.step_pcm(ticket).reshape(1, 1, FRAME)
+                if fin[0] or nxt is None:
+                    if nxt is not None:  # enqueued ahead of an EOS finish: drain it
+                        eng.step_flags(nxt)
+                        eng.step_pcm(nxt, want=False)
                     break
-                ticket, fin = nxt, fin_next
+                ticket = nxt
         finally:
             self.engine.sync()
             self.engine.close_stream(int(slot))

@@ -259,6 +259,83 @@ def test_host_mirror_generate_stream_tokens():
     m.close()
 
 
+def test_step_ahead_matches_lockstep_and_never_emits_past_the_end():
+    """PTTS_STEP_AHEAD: frame n+1 enqueued before frame n's flags are fetched.  Same frames bit for bit as the lock-step
+    calls; a stream that ends at EOS (D2: frames = eos_step + frames_after_eos + 1, tts_model.rs:1055-1069) reports
+    its one overrun frame as such, its frame counters stay at the last real frame, and a batch keeps going for the
+    streams that did not end."""
+    from pocket_tts_b200.engine import StreamSpec
+    from pocket_tts_b200 import _lib
+    eng, _ = engine_for(1234, 0.01)
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(12, seed=3))
+    toks = [synth.make_tokens(7, seed=21), synth.make_tokens(5, seed=22)]
+    noise = [synth.make_noise(8, seed=31), synth.make_noise(8, seed=32)]
+
+    def specs(thr0):
+        # stream 0 ends by EOS when thr0 is -inf-like (eos at step 0, 3 frames after -> 4 frames); stream 1 runs 8 frames
+        return [StreamSpec(toks[0], 8, 3, thr0, noise=noise[0]), StreamSpec(toks[1], 8, 3, 1e30, noise=noise[1])]
+
+    # lock-step reference run
+    slots = eng.open_streams([voice, voice], specs(-1e30))
+    want = []
+    live = list(slots)
+    while live:
+        p, fin, l, _ = eng.step(np.array(live, np.int32))
+        want.append({int(s): (p[i].copy(), l[i].copy(), bool(fin[i])) for i, s in enumerate(live)})
+        live = [s for i, s in enumerate(live) if not fin[i]]
+    assert [len(w) for w in want] == [2, 2, 2, 2, 1, 1, 1, 1]
+    frames_lock = [eng.stream_frames(int(s)) for s in slots]
+    for s in slots:
+        eng.close_stream(int(s))
+
+    # the same job one step ahead of the host
+    slots = eng.open_streams([voice, voice], specs(-1e30))
+    live = [int(s) for s in slots]
+    got = []
+    ticket, rows = eng.step_begin(np.array(live, np.int32)), list(live)
+    issued = 1
+    while ticket is not None:
+        nxt = nxt_rows = None
+        if issued < 8 and live:
+            nxt_rows = list(live)           # chosen before this step's flags are known
+            nxt = eng.step_begin(np.array(nxt_rows, np.int32), ahead=True)
+            issued += 1
+        fin, lat, _ = eng.step_flags(ticket)
+        over = eng.last_overrun.copy()
+        pcm = eng.step_pcm(ticket)
+        got.append({s: (pcm[i].copy(), lat[i].copy(), bool(fin[i])) for i, s in enumerate(rows) if not over[i]})
+        live = [s for s in live if not any(s == r and fin[i] for i, r in enumerate(rows))]
+        ticket, rows = nxt, nxt_rows
+    assert len(got) == len(want)
+    for step, (g, w) in enumerate(zip(got, want)):
+        assert g.keys() == w.keys()
+        for s_g, s_w in zip(sorted(g), sorted(w)):
+            if step <= 4:
+                # same batch geometry as the lock-step run (step 4 carries the overrun row of stream 0 next to stream 1,
+                # the lock-step run has stream 1 alone: different split-K tiling, so only steps 0-3 are bit-identical)
+                cmp = np.testing.assert_array_equal if step < 4 else (lambda a, b: np.testing.assert_allclose(a, b, atol=5e-3))
+            else:
+                cmp = lambda a, b: np.testing.assert_allclose(a, b, atol=2e-2)  # free-running from step 4's rounding
+            cmp(g[s_g][0], w[s_w][0])
+            cmp(g[s_g][1], w[s_w][1])
+            assert g[s_g][2] == w[s_w][2]
+    assert [eng.stream_frames(int(s)) for s in slots] == frames_lock == [(4, 0), (8, -1)]
+    # rules: two steps ahead of unfetched flags is refused; a finished slot cannot be stepped
+    with pytest.raises(_lib.PttsError):
+        eng.step_begin(np.array([int(slots[0])], np.int32))
+    for s in slots:
+        eng.close_stream(int(s))
+    s2 = eng.open_streams([voice], [StreamSpec(toks[0], 8, 3, 1e30, noise=noise[0])])
+    t0 = eng.step_begin(s2)
+    t1 = eng.step_begin(s2, ahead=True)
+    with pytest.raises(_lib.PttsError):
+        eng.step_begin(s2, ahead=True)
+    for t in (t0, t1):
+        eng.step_flags(t); eng.step_pcm(t)
+    eng.close_stream(int(s2[0]))
+    voice.close()
+
+
 def test_int8_weight_mode_matches_reference_quantisation():
     """BASELINE configs[3]: per-tensor symmetric int8 with the reference's scheme and skip list
     (crates/pocket-tts/src/quantize.rs:27-41,65-94,117-154).  The oracle runs f32 math on the fake-quantised
