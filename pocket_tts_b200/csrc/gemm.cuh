@@ -132,12 +132,12 @@ __device__ __forceinline__ float epi_act(int act, float v) {
 // EPI_GENERIC keeps every test at run time and serves shapes outside the list.
 enum {
   EPI_BIAS = 1, EPI_FSCALE = 2, EPI_GATE = 4, EPI_RES = 8, EPI_OUT32 = 16, EPI_OUT16 = 32, EPI_ELU16 = 64,
-  EPI_ACT_SHIFT = 7 /* 2 bits */, EPI_ALPHA = 512, EPI_WSCALE = 1024 /* generic loop only */, EPI_GENERIC = -1
+  EPI_ACT_SHIFT = 7 /* 2 bits */, EPI_ALPHA = 512, EPI_GENERIC = -1
 };
 __host__ __device__ inline int epi_mask_of(const GemmEpi& e) {
   return (e.bias ? EPI_BIAS : 0) | (e.fscale ? EPI_FSCALE : 0) | (e.gate ? EPI_GATE : 0) | (e.res ? EPI_RES : 0) |
          (e.out32 ? EPI_OUT32 : 0) | (e.out16 ? EPI_OUT16 : 0) | ((e.out16 && e.act16 == ACT_ELU) ? EPI_ELU16 : 0) |
-         (e.act << EPI_ACT_SHIFT) | (e.alpha != 1.f ? EPI_ALPHA : 0) | (e.wscale ? EPI_WSCALE : 0);
+         (e.act << EPI_ACT_SHIFT) | (e.alpha != 1.f ? EPI_ALPHA : 0);
 }
 // every shape the engine issues (engine.cu: FlowLM, flow head, Mimi transformer, SEANet)
 #define PTTS_EPI_SHAPES(X)                                                                  \
@@ -180,8 +180,8 @@ __device__ __forceinline__ void cluster_sync_relaxed() {
 }
 
 // int8 weight storage (reference quantize.rs:65-94: per-tensor symmetric codes in [-127, 127]).  TMA drops the raw
-// [128 features][64 k] byte tile (8 KB, dense) into the upper half of the 16 KB operand slot; the 128 threads of warps
-// 2-5 (thread = feature row) pull their 64 bytes into registers, meet at a named barrier (row r's f16 destination
+// [128 features][64 k] byte tile (8 KB, dense) into the upper half of the 16 KB operand slot; the 256 threads of warps
+// 2-9 (two per feature row) pull their 32 bytes into registers, meet at a named barrier (row r's f16 destination
 // overlaps the raw bytes of rows 2r-128 and 2r-127), and write the row back as 64 halves in the SWIZZLE_128B K-major
 // layout the MMA descriptor expects (16-byte chunk c of row r at r*128 + ((c ^ (r & 7)) << 4)).  Codes are exact in
 // f16, so the accumulator is bit-identical to streaming an f16 copy of the codes; the scale stays in the epilogue.
@@ -196,23 +196,24 @@ __device__ __forceinline__ void i8x4_to_f16x4(uint32_t w, uint32_t& lo, uint32_t
   lo = *reinterpret_cast<const uint32_t*>(&ra);
   hi = *reinterpret_cast<const uint32_t*>(&rb);
 }
-__device__ __forceinline__ void expand_i8_tile(uint8_t* tile, int row) {
-  const uint4* src = reinterpret_cast<const uint4*>(tile + GEMM_BM * GEMM_BK + row * GEMM_BK);
-  uint4 raw[4];
+__device__ __forceinline__ void expand_i8_tile(uint8_t* tile, int row, int half) {
+  const uint4* src = reinterpret_cast<const uint4*>(tile + GEMM_BM * GEMM_BK + row * GEMM_BK + half * 32);
+  uint4 raw[2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) raw[j] = src[j];
-  asm volatile("bar.sync 2, 128;" ::: "memory");  // every raw row is in registers before any f16 row is written
+  for (int j = 0; j < 2; ++j) raw[j] = src[j];
+  asm volatile("bar.sync 2, 256;" ::: "memory");  // every raw row is in registers before any f16 row is written
   uint8_t* dst = tile + row * 128;
   const int sw = row & 7;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 2; ++j) {
     uint4 o0, o1;
     i8x4_to_f16x4(raw[j].x, o0.x, o0.y);
     i8x4_to_f16x4(raw[j].y, o0.z, o0.w);
     i8x4_to_f16x4(raw[j].z, o1.x, o1.y);
     i8x4_to_f16x4(raw[j].w, o1.z, o1.w);
-    *reinterpret_cast<uint4*>(dst + (((2 * j) ^ sw) << 4)) = o0;
-    *reinterpret_cast<uint4*>(dst + (((2 * j + 1) ^ sw) << 4)) = o1;
+    const int c = half * 4 + 2 * j;
+    *reinterpret_cast<uint4*>(dst + ((c ^ sw) << 4)) = o0;
+    *reinterpret_cast<uint4*>(dst + (((c + 1) ^ sw) << 4)) = o1;
   }
 }
 
@@ -264,7 +265,7 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
   const float alpha = (GEN || (M & EPI_ALPHA)) ? e.alpha : 1.f;
   const float* __restrict__ bias = e.bias;
   const float* __restrict__ fscale = e.fscale;
-  const float* __restrict__ wscale = GEN ? e.wscale : nullptr;
+  const float* __restrict__ wscale = e.wscale;  // int8 mode only; a run-time test in every shape (uniform, one FMUL)
   const int swap = p.swap, F = p.F, T = p.T, R = p.R, G = p.G, n_streams = p.n_streams;
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
@@ -342,7 +343,7 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               float x = av[c];
-              if (GEN && wscale) x *= wv[c];
+              x *= wv[c];  // int8 weight-code scale, 1 otherwise
               if (has_bias) x += bv[c];
               x = epi_act(act, x) * alpha;
               if (has_fscale) x *= sv[c];
@@ -439,7 +440,7 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 #pragma unroll
       for (int c = 0; c < V; ++c) {
         float x = v[c];
-        if (GEN && wscale) x *= __ldg(wscale + f + c);
+        if (wscale) x *= __ldg(wscale + f + c);
         if (has_bias) x += bv[c];
         x = epi_act(act, x) * alpha;
         if (has_fscale) x *= sv[c];
@@ -537,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     if (p.w_int8) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(wfull_bar + s, 1);
-        mbar_init(conv_bar + s, 4);
+        mbar_init(conv_bar + s, 8);
       }
     }
     mbar_fence_init();
@@ -666,13 +667,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     }
     __syncwarp();
     PTTS_TRACE(5);
-  } else if (warp < 6) {
-    if (p.w_int8) {
+  } else {
+    if (p.w_int8 && warp < 10) {
       // ===== int8 storage: expand the raw weight tiles to the f16 MMA operand (see expand_i8_tile) =====
-      const int row = (warp - 2) * 32 + lane;
+      const int idx = (warp - 2) * 32 + lane;
+      const int row = idx >> 1, half = idx & 1;
       if (p.resident) {
         mbar_wait(wfull_bar, 0);
-        for (int i = 0; i < nkb; ++i) expand_i8_tile(smem + i * m_tile_bytes, row);
+        for (int i = 0; i < nkb; ++i) expand_i8_tile(smem + i * m_tile_bytes, row, half);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tcgen05.mma reads
         __syncwarp();
         if (lane == 0) mbar_arrive(conv_bar);
@@ -681,7 +683,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         uint32_t ph = 0;
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(wfull_bar + s, ph);
-          expand_i8_tile(smem + s * stage_bytes, row);
+          expand_i8_tile(smem + s * stage_bytes, row, half);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(conv_bar + s);
@@ -689,6 +691,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         }
       }
     }
+    if (warp < 6) {
     // ===== epilogue, first half: TMEM -> registers -> smem tile [activation row][feature] (raw f32) =====
     // The pipeline stages are dead once tmem_full has arrived (every MMA has consumed its operands), so the tile
     // is staged over them.  Pitch = features + 4 floats: 16-byte aligned rows, conflict-free in both passes.
@@ -718,6 +721,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       }
     }
     if (warp == 2) PTTS_TRACE(7);
+    }
   }
   // ===== epilogue, second half: every warp of every CTA of the split-K cluster =====
   tc_fence_before();
