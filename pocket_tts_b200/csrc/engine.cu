@@ -782,15 +782,21 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;
     // int8 storage: the weight tile arrives as bytes and warps 2-5 expand it to the f16 operand in shared memory
     // (reserved[7] = 1: test hook, stream the f16 copy of the codes instead -- results must be bit-identical)
-    p.w_int8 = (swap && w.q8.p && !cfg.debug_gemm && cfg.reserved[7] == 0) ? 1 : 0;
-    smem = (size_t)p.stages * stage_bytes + 8 * (4 * p.stages + 4) + 2048 + 4096 + 1024;  // barriers, LN row statistics + gamma/beta slice, alignment
+    const bool w_int8 = swap && w.q8.p && !cfg.debug_gemm && cfg.reserved[7] == 0;
+    if (w_int8) p.epi.reserved |= GEMM_F_W_INT8;
+    // stages | barriers | alignment slack.  The plain launch must stay below the 196 KB shared-memory carve-out: a few KB
+    // more selects the 228 KB configuration, halves the L1 of every SM the GEMM touches and cost 2.7% of the whole step.
+    // The int8 barriers (16 B per stage) and the LayerNorm-in-front scratch (6 KB) are added only when used.
+    smem = (size_t)p.stages * stage_bytes + 8 * (2 * p.stages + 1) + 16 + 1024;
+    if (w_int8) smem += 16 * p.stages;
+    if (lnf.set) smem += 16 * p.stages + 8 + 2048 + 4096;
     p.resident = (swap && taps == 1 && n_streams == 1 && a.cap == 1 && p.kb_per_split <= p.stages && !cfg.debug_gemm &&
                   cfg.reserved[6] == 0) ? 1 : 0;   // reserved[6] = 1: test hook, the staged pipeline instead
   }
   if (lnf.set) {
     PTTS_REQUIRE(p.resident && p.BN <= 256, PTTS_ERR_STATE, "LayerNorm in front needs the resident decode GEMM (rows %lld, k-blocks per CTA %d, stages %d)",
                  rows, p.kb_per_split, p.stages);
-    p.ln_front = 1; p.ln_stats = ln_stats.p; p.ln_w = lnf.w; p.ln_b = lnf.b; p.ln_eps = lnf.eps;
+    p.epi.reserved |= GEMM_F_LN_FRONT; p.ln_stats = ln_stats.p; p.ln_w = lnf.w; p.ln_b = lnf.b; p.ln_eps = lnf.eps;
   }
   if (p.epi.stats) PTTS_REQUIRE(swap && F % 128 == 0 && (size_t)rows * (F / 128) * 2 <= ln_stats.n, PTTS_ERR_STATE, "row statistics need the swap-AB GEMM with whole 128-feature tiles");
   auto map_ok = [](const void* ptr, const RowMap& m) {
@@ -801,7 +807,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
 
   // algorithmic traffic: weights once, the distinct activation rows once, every epilogue tensor once
   const double act_rows = (double)n_streams * (T + taps - 1);
-  double bytes = (double)F * w.K * (p.w_int8 ? 1 : 2) + act_rows * a.C * 2;
+  const bool w_int8 = (p.epi.reserved & GEMM_F_W_INT8) != 0;
+  double bytes = (double)F * w.K * (w_int8 ? 1 : 2) + act_rows * a.C * 2;
   bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + (epi.res ? 4 : 0) + (epi.gate ? 4 : 0));
   {
     ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K,
@@ -814,7 +821,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
       const CUtensorMap& ma = p.resident ? tmaps.get(a.ptr, 64, a.Tpad, a.C / 64, a.C, 64, p.BN, p.kb_per_split)
                               : swap     ? tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.BN, 1)
                                          : tmaps.get(a.ptr, a.C, a.Tpad, a.cap, a.C, (long long)a.Tpad * a.C, p.R, p.G);
-      const CUtensorMap& mw = p.w_int8 ? tmaps.get_u8(w.q8.p, w.K, w.Fpad, 128)
+      const CUtensorMap& mw = w_int8 ? tmaps.get_u8(w.q8.p, w.K, w.Fpad, 128)
                                        : tmaps.get(w.w.p, w.K, w.Fpad, 1, w.K, (long long)w.Fpad * w.K, swap ? 128 : p.BN, 1);
       if (persistent) launch_k(use_pdl, gemm_tc_persistent_kernel, grid, GEMM_THREADS, smem, ls, 1, ma, mw, p);
       else launch_k(use_pdl, gemm_tc_kernel, grid, GEMM_THREADS, smem, ls, (int)grid.z, ma, mw, p);

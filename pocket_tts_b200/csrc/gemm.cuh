@@ -59,7 +59,7 @@ struct GemmEpi {
   int act;              // applied to acc + bias
   int act16;            // applied to the f16 copy only (ELU in front of the next SEANet conv)
   float alpha;          // multiplies after the activation
-  int reserved;
+  int reserved;         // inside GemmParams: GEMM_F_* switches of the optional paths
   const float* wscale;  // [F] int8 mode: weight-code scale applied to the accumulator first, else null
   float* stats;         // [rows][F/128][2] or null: (sum, centred sum of squares) of each 128-feature segment of the
                         // f32 output row, for the LayerNorm the consuming GEMM applies to its operand (GemmParams::ln_front)
@@ -79,15 +79,6 @@ struct GemmParams {
   int n_act_tiles;          // activation tiles in total (persistent kernel walks them with stride gridDim.x)
   int pdl_trigger;          // where the CTA lets the next kernel launch: 0 entry, 1 all loads issued, 2 accumulator ready
   int resident;             // swap-AB decode GEMM whose whole K slice fits the stages: one barrier, one activation box
-  int w_int8;               // swap-AB only: map_w views one-byte weight codes; warps 2-9 expand each tile to f16 in smem
-  // LayerNorm in front (resident decode GEMM only): the activation tensor is the UN-normalised f16 copy of the f32
-  // residual stream that the producing GEMM wrote next to it; once TMA has landed the operand tiles, warps 2-11
-  // normalise them in place in shared memory (row statistics from the producer's epilogue, GemmEpi::stats).
-  int ln_front;
-  const float* ln_stats;    // [rows][K/128][2]
-  const float* ln_w;        // [K]
-  const float* ln_b;        // [K]
-  float ln_eps;
   GemmEpi epi;
   // raw view, used by the SIMT cross-check kernel only
   const __half* act;
@@ -95,7 +86,19 @@ struct GemmParams {
   int act_ld;
   const __half* w;
   unsigned long long* trace;  // optional [grid][16] %globaltimer stamps (bring-up only)
+  // ---- optional paths.  Their switches live in epi.reserved (GEMM_F_*) and their arguments down here, so every field
+  // above keeps the offset it had before they existed: growing the hot part of the parameter block by 40 bytes cost
+  // ~0.5 us per launch (more constant-bank lines on the prologue's critical path), 2.7% of the whole step.
+  // GEMM_F_W_INT8 (swap-AB only): map_w views one-byte weight codes; warps 2-9 expand each tile to f16 in smem.
+  // GEMM_F_LN_FRONT (resident decode GEMM only): the activation tensor is the UN-normalised f16 copy of the f32
+  // residual stream that the producing GEMM wrote next to it; once TMA has landed the operand tiles, warps 2-11
+  // normalise them in place in shared memory (row statistics from the producer's epilogue, GemmEpi::stats).
+  const float* ln_stats;    // [rows][K/128][2]
+  const float* ln_w;        // [K]
+  const float* ln_b;        // [K]
+  float ln_eps;
 };
+enum { GEMM_F_W_INT8 = 1, GEMM_F_LN_FRONT = 2 };
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -549,6 +552,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   const int lane = threadIdx.x & 31;
   if (p.pdl_trigger == 0) pdl_launch_dependents();
   if (warp == 0) PTTS_TRACE(0);
+  const bool w_int8 = (p.epi.reserved & GEMM_F_W_INT8) != 0, ln_front = (p.epi.reserved & GEMM_F_LN_FRONT) != 0;
 
   // tile coordinates
   const int tiles_t = (p.T + p.R - 1) / p.R;
@@ -578,13 +582,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       mbar_init(empty_bar + s, 1);
     }
     mbar_init(tmem_full_bar, 1);
-    if (p.w_int8) {
+    if (w_int8) {
       for (int s = 0; s < p.stages; ++s) {
         mbar_init(wfull_bar + s, 1);
         mbar_init(conv_bar + s, 8);
       }
     }
-    if (p.ln_front) mbar_init(actc_bar, 10);
+    if (ln_front) mbar_init(actc_bar, 10);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -610,7 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       // (64 k, BN rows, all k-blocks) = [k-block][row][64] behind them.  One TMA instead of one per k-block: each
       // issue costs this thread ~0.3 us, which at eight k-blocks was the longest phase of the kernel.
       if (elect_one()) {
-        if (p.w_int8) {
+        if (w_int8) {
           mbar_arrive_expect_tx(wfull_bar, static_cast<uint32_t>(nkb) * RAW_BYTES);
           for (int i = 0; i < nkb; ++i) tma_load_3d(smem + i * m_tile_bytes + RAW_OFF, &map_w, wfull_bar, (kb0 + i) * GEMM_BK, f0, 0);
           mbar_arrive_expect_tx(full_bar, static_cast<uint32_t>(p.kb_per_split * n_tile_bytes));
@@ -630,7 +634,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       const int npre = min(nkb, p.stages);
       for (int i = 0; i < npre; ++i) {
         uint8_t* m_tile = smem + i * stage_bytes;
-        if (p.w_int8) {  // swap only: weights on their own barrier so the expansion can start before the activations exist
+        if (w_int8) {  // swap only: weights on their own barrier so the expansion can start before the activations exist
           mbar_arrive_expect_tx(wfull_bar + i, RAW_BYTES);
           tma_load_3d(m_tile + RAW_OFF, &map_w, wfull_bar + i, (kb0 + i) * GEMM_BK, f0, 0);
           mbar_arrive_expect_tx(full_bar + i, act_bytes);
@@ -649,7 +653,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         uint8_t* n_tile = m_tile + m_tile_bytes;
         if (i >= npre) {
           mbar_wait(empty_bar + s, ph ^ 1);
-          if (p.w_int8) {
+          if (w_int8) {
             mbar_arrive_expect_tx(wfull_bar + s, RAW_BYTES);
             tma_load_3d(m_tile + RAW_OFF, &map_w, wfull_bar + s, (kb0 + i) * GEMM_BK, f0, 0);
             mbar_arrive_expect_tx(full_bar + s, act_bytes);
@@ -676,9 +680,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem));
         const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem + p.kb_per_split * m_tile_bytes));
         const uint32_t a_adv = static_cast<uint32_t>(m_tile_bytes) >> 4, b_adv = static_cast<uint32_t>(n_tile_bytes) >> 4;
-        if (p.w_int8) mbar_wait(conv_bar, 0);
+        if (w_int8) mbar_wait(conv_bar, 0);
         mbar_wait(full_bar, 0);
-        if (p.ln_front) mbar_wait(actc_bar, 0);
+        if (ln_front) mbar_wait(actc_bar, 0);
         tc_fence_after();
         PTTS_TRACE(4);
         for (int i = 0; i < nkb; ++i) {
@@ -694,7 +698,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        if (p.w_int8) mbar_wait(conv_bar + s, ph);
+        if (w_int8) mbar_wait(conv_bar + s, ph);
         mbar_wait(full_bar + s, ph);
         tc_fence_after();
         if (i == 0) PTTS_TRACE(4);
@@ -713,7 +717,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
     __syncwarp();
     PTTS_TRACE(5);
   } else {
-    if (p.w_int8 && warp < 10) {
+    if (w_int8 && warp < 10) {
       // ===== int8 storage: expand the raw weight tiles to the f16 MMA operand (see expand_i8_tile) =====
       const int idx = (warp - 2) * 32 + lane;
       const int row = idx >> 1, half = idx & 1;
@@ -736,7 +740,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         }
       }
     }
-    if (p.ln_front) {
+    if (ln_front) {
       // ===== LayerNorm in front: the landed operand tiles hold f16(x); rewrite them in place as f16(LN(x) * w + b) =====
       // (reference modules/mlp.rs:29-58: biased variance, eps inside the sqrt).  Row statistics come from the producing
       // GEMM's epilogue as per-128-feature (sum, centred M2) pairs over the f32 row, merged with Chan's update.  Pulling
