@@ -178,12 +178,6 @@ int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const flo
  * (production), 0 streams an f16 copy of the same codes; both must give bit-identical D.  scale_out gets the scale. */
 int32_t ptts_test_gemm_int8(int32_t device, const float* a, const float* w, float* d, int32_t rows, int32_t feats,
                             int32_t k, int32_t split_k, int32_t storage, float* scale_out);
-/* LayerNorm fused in front of a decode GEMM (rows <= 64): X = A0 . W0^T is produced by one GEMM whose epilogue leaves
- * per-row statistics, then D = (LN(X) * gamma + beta) . W1^T by a GEMM that normalises its own operand rows in shared
- * memory (no LayerNorm launch, reference modules/mlp.rs:29-58 semantics).  Returns X [rows,k] and D [rows,feats]. */
-int32_t ptts_test_gemm_ln_front(int32_t device, const float* a0, const float* w0, const float* gamma, const float* beta,
-                                const float* w1, float* x_out, float* d_out, int32_t rows, int32_t k0, int32_t k,
-                                int32_t feats, float eps);
 /* Bring-up probe: back-to-back launches of one GEMM with per-CTA %globaltimer stamps (10 per CTA, ns). */
 int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_t k, int32_t mode, int32_t split_k,
                              int32_t iters, float* us_per_launch, int64_t* stamps, int32_t max_ctas, int32_t* n_ctas);

@@ -13,7 +13,7 @@ SYMBOLS = [
     "ptts_engine_set_lsd_steps", "ptts_voice_from_prompt", "ptts_voice_destroy", "ptts_voice_len",
     "ptts_streams_open", "ptts_step", "ptts_step_begin", "ptts_step_flags", "ptts_step_pcm", "ptts_step_device", "ptts_sync", "ptts_stream_set_feedback",
     "ptts_stream_close", "ptts_stream_frames", "ptts_debug_read", "ptts_launch_count", "ptts_step_timed",
-    "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report", "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemm_ln_front", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
+    "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report", "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
 ]
 
 
@@ -79,7 +79,6 @@ def lib() -> C.CDLL:
     L.ptts_profile_overhead.argtypes = [vp, vp]
     L.ptts_test_gemm.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]
     L.ptts_test_gemm_int8.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]
-    L.ptts_test_gemm_ln_front.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, C.c_float]
     L.ptts_test_gemm_trace.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]
     L.ptts_test_conv1d.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
     L.ptts_test_convtr1d.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]

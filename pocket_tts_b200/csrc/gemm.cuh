@@ -59,11 +59,14 @@ struct GemmEpi {
   int act;              // applied to acc + bias
   int act16;            // applied to the f16 copy only (ELU in front of the next SEANet conv)
   float alpha;          // multiplies after the activation
-  int reserved;         // inside GemmParams: GEMM_F_* switches of the optional paths
+  int reserved;         // inside GemmParams: GEMM_F_* switches of optional paths (kept here so that no field of the
+                        // parameter block moved when they were added: 40 more bytes in its hot part measured ~0.5 us
+                        // per launch, more constant-bank lines on the prologue's critical path)
   const float* wscale;  // [F] int8 mode: weight-code scale applied to the accumulator first, else null
-  float* stats;         // [rows][F/128][2] or null: (sum, centred sum of squares) of each 128-feature segment of the
-                        // f32 output row, for the LayerNorm the consuming GEMM applies to its operand (GemmParams::ln_front)
 };
+
+// GEMM_F_W_INT8 (swap-AB only): map_w views one-byte weight codes; warps 2-9 expand each tile to f16 in shared memory.
+enum { GEMM_F_W_INT8 = 1 };
 
 struct GemmParams {
   int swap;
@@ -86,19 +89,7 @@ struct GemmParams {
   int act_ld;
   const __half* w;
   unsigned long long* trace;  // optional [grid][16] %globaltimer stamps (bring-up only)
-  // ---- optional paths.  Their switches live in epi.reserved (GEMM_F_*) and their arguments down here, so every field
-  // above keeps the offset it had before they existed: growing the hot part of the parameter block by 40 bytes cost
-  // ~0.5 us per launch (more constant-bank lines on the prologue's critical path), 2.7% of the whole step.
-  // GEMM_F_W_INT8 (swap-AB only): map_w views one-byte weight codes; warps 2-9 expand each tile to f16 in smem.
-  // GEMM_F_LN_FRONT (resident decode GEMM only): the activation tensor is the UN-normalised f16 copy of the f32
-  // residual stream that the producing GEMM wrote next to it; once TMA has landed the operand tiles, warps 2-11
-  // normalise them in place in shared memory (row statistics from the producer's epilogue, GemmEpi::stats).
-  const float* ln_stats;    // [rows][K/128][2]
-  const float* ln_w;        // [K]
-  const float* ln_b;        // [K]
-  float ln_eps;
 };
-enum { GEMM_F_W_INT8 = 1, GEMM_F_LN_FRONT = 2 };
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -145,12 +136,12 @@ __device__ __forceinline__ float epi_act(int act, float v) {
 // EPI_GENERIC keeps every test at run time and serves shapes outside the list.
 enum {
   EPI_BIAS = 1, EPI_FSCALE = 2, EPI_GATE = 4, EPI_RES = 8, EPI_OUT32 = 16, EPI_OUT16 = 32, EPI_ELU16 = 64,
-  EPI_ACT_SHIFT = 7 /* 2 bits */, EPI_ALPHA = 512, EPI_WSCALE = 1024 /* catch-all loop only */, EPI_STATS = 2048, EPI_GENERIC = -1
+  EPI_ACT_SHIFT = 7 /* 2 bits */, EPI_ALPHA = 512, EPI_GENERIC = -1
 };
 __host__ __device__ inline int epi_mask_of(const GemmEpi& e) {
   return (e.bias ? EPI_BIAS : 0) | (e.fscale ? EPI_FSCALE : 0) | (e.gate ? EPI_GATE : 0) | (e.res ? EPI_RES : 0) |
          (e.out32 ? EPI_OUT32 : 0) | (e.out16 ? EPI_OUT16 : 0) | ((e.out16 && e.act16 == ACT_ELU) ? EPI_ELU16 : 0) |
-         (e.act << EPI_ACT_SHIFT) | (e.alpha != 1.f ? EPI_ALPHA : 0) | (e.wscale ? EPI_WSCALE : 0) | (e.stats ? EPI_STATS : 0);
+         (e.act << EPI_ACT_SHIFT) | (e.alpha != 1.f ? EPI_ALPHA : 0);
 }
 // every shape the engine issues (engine.cu: FlowLM, flow head, Mimi transformer, SEANet)
 #define PTTS_EPI_SHAPES(X)                                                                  \
@@ -166,12 +157,6 @@ __host__ __device__ inline int epi_mask_of(const GemmEpi& e) {
   X(EPI_BIAS | EPI_OUT16 | EPI_ELU16)                                                       \
   X(EPI_BIAS | EPI_OUT32 | EPI_OUT16 | EPI_ELU16)                                           \
   X(EPI_BIAS | EPI_RES | EPI_OUT16 | EPI_ELU16)
-
-// shapes only the decode GEMMs (gemm_tc_kernel) issue: compiled into the persistent kernel as well they cost it
-// registers (152 -> 168 with spills) for code it never runs
-#define PTTS_EPI_SHAPES_DECODE(X)                                                           \
-  X(EPI_OUT32 | EPI_OUT16 | EPI_STATS)                                                      \
-  X(EPI_RES | EPI_OUT32 | EPI_OUT16 | EPI_STATS)
 
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
   float4 v;
@@ -268,7 +253,7 @@ __device__ __forceinline__ void epi_hoist_init(const GemmParams& p, int f0, int 
   }
 }
 
-template <int V, int M, bool DECODE = false>
+template <int V, int M>
 __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0,
                                             int tid, int nthreads, int rank, int nsplit, const EpiHoist* hp = nullptr) {
   constexpr bool GEN = (M == EPI_GENERIC);
@@ -282,10 +267,9 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
   const bool elu16 = GEN ? e.act16 == ACT_ELU : (M & EPI_ELU16) != 0;
   const int act = GEN ? e.act : ((M >> EPI_ACT_SHIFT) & 3);
   const float alpha = (GEN || (M & EPI_ALPHA)) ? e.alpha : 1.f;
-  const bool has_stats = DECODE && (GEN ? e.stats != nullptr : (M & EPI_STATS) != 0);  // never in the persistent kernel
   const float* __restrict__ bias = e.bias;
   const float* __restrict__ fscale = e.fscale;
-  const float* __restrict__ wscale = GEN ? e.wscale : nullptr;  // int8 decode GEMMs take the catch-all loop (one row per trip anyway)
+  const float* __restrict__ wscale = e.wscale;  // int8 mode only; a run-time test in every shape (uniform, one FMUL)
   const int swap = p.swap, F = p.F, T = p.T, R = p.R, G = p.G, n_streams = p.n_streams;
   const int tile_rows = swap ? p.BN : GEMM_BM;                 // activation rows covered by the tile
   const int fv = (swap ? GEMM_BM : p.BN) / V;                  // feature groups per activation row
@@ -363,27 +347,13 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               float x = av[c];
-              if (GEN && wscale) x *= wv[c];
+              x *= wv[c];  // int8 weight-code scale, 1 otherwise
               if (has_bias) x += bv[c];
               x = epi_act(act, x) * alpha;
               if (has_fscale) x *= sv[c];
               if (has_gate) x *= gv[c];
               if (has_res) x += rv[c];
               v[u][c] = x;
-            }
-          }
-          if (has_stats && rows_per_iter == 1) {
-            // statistics of the row segment this warp holds (32 lanes x 4 features = one 128-feature tile), two-pass
-            // inside the segment; the consumer merges the segments (Chan's parallel-variance update)
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const int row = row_b + u * step;
-              const float sum = warp_sum((v[u][0] + v[u][1]) + (v[u][2] + v[u][3]));
-              const float m = sum * (1.f / 128.f);
-              const float d0 = v[u][0] - m, d1 = v[u][1] - m, d2 = v[u][2] - m, d3 = v[u][3] - m;
-              const float m2 = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
-              if (lane == 0 && row < nrows)
-                *reinterpret_cast<float2*>(e.stats + (static_cast<long long>(t0 + row) * (F >> 7) + (f0 >> 7)) * 2) = make_float2(sum, m2);
             }
           }
 #pragma unroll
@@ -474,7 +444,7 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
 #pragma unroll
       for (int c = 0; c < V; ++c) {
         float x = v[c];
-        if (GEN && wscale) x *= __ldg(wscale + f + c);
+        if (wscale) x *= __ldg(wscale + f + c);
         if (has_bias) x += bv[c];
         x = epi_act(act, x) * alpha;
         if (has_fscale) x *= sv[c];
@@ -505,28 +475,18 @@ __device__ __forceinline__ void epi_store_tile(const GemmParams& p, uint32_t sti
   }
 }
 
-template <bool DECODE = false>
 __device__ __forceinline__ void epi_dispatch(const GemmParams& p, uint32_t stile_addr, int LD, int f0, int t0, int b0, int tid,
                                              int nthreads, int rank, int nsplit, const EpiHoist* hp = nullptr) {
   if (!p.vec4) {
-    epi_store_tile<1, EPI_GENERIC, DECODE>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit);
+    epi_store_tile<1, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit);
     return;
-  }
-  if (DECODE) {
-    switch (p.epi_mask) {
-#define PTTS_EPI_CASE(MASK) \
-  case (MASK): epi_store_tile<4, (MASK), true>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit, hp); return;
-      PTTS_EPI_SHAPES_DECODE(PTTS_EPI_CASE)
-#undef PTTS_EPI_CASE
-      default: break;
-    }
   }
   switch (p.epi_mask) {
 #define PTTS_EPI_CASE(MASK) \
   case (MASK): epi_store_tile<4, (MASK)>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit, hp); break;
     PTTS_EPI_SHAPES(PTTS_EPI_CASE)
 #undef PTTS_EPI_CASE
-    default: epi_store_tile<4, EPI_GENERIC, DECODE>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit, hp); break;
+    default: epi_store_tile<4, EPI_GENERIC>(p, stile_addr, LD, f0, t0, b0, tid, nthreads, rank, nsplit, hp); break;
   }
 }
 
@@ -544,15 +504,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   uint64_t* wfull_bar = tmem_full_bar + 3;      // int8 storage: raw weight bytes landed (per stage)
-  uint64_t* conv_bar = wfull_bar + p.stages;    // int8 storage: f16 operand written by the eight converter warps
-  uint64_t* actc_bar = conv_bar + p.stages;     // LayerNorm in front: normalised f16 activation operand written (10 warps)
-  float* ln_stat_s = reinterpret_cast<float*>(actc_bar + 1);  // [256] mean | [256] rstd | gamma, beta of the K slice
+  uint64_t* conv_bar = wfull_bar + p.stages;    // int8 storage: f16 operand written by the four converter warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (p.pdl_trigger == 0) pdl_launch_dependents();
   if (warp == 0) PTTS_TRACE(0);
-  const bool w_int8 = (p.epi.reserved & GEMM_F_W_INT8) != 0, ln_front = (p.epi.reserved & GEMM_F_LN_FRONT) != 0;
+  const bool w_int8 = (p.epi.reserved & GEMM_F_W_INT8) != 0;
 
   // tile coordinates
   const int tiles_t = (p.T + p.R - 1) / p.R;
@@ -588,7 +546,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         mbar_init(conv_bar + s, 8);
       }
     }
-    if (ln_front) mbar_init(actc_bar, 10);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -682,7 +639,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         const uint32_t a_adv = static_cast<uint32_t>(m_tile_bytes) >> 4, b_adv = static_cast<uint32_t>(n_tile_bytes) >> 4;
         if (w_int8) mbar_wait(conv_bar, 0);
         mbar_wait(full_bar, 0);
-        if (ln_front) mbar_wait(actc_bar, 0);
         tc_fence_after();
         PTTS_TRACE(4);
         for (int i = 0; i < nkb; ++i) {
@@ -740,81 +696,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
         }
       }
     }
-    if (ln_front) {
-      // ===== LayerNorm in front: the landed operand tiles hold f16(x); rewrite them in place as f16(LN(x) * w + b) =====
-      // (reference modules/mlp.rs:29-58: biased variance, eps inside the sqrt).  Row statistics come from the producing
-      // GEMM's epilogue as per-128-feature (sum, centred M2) pairs over the f32 row, merged with Chan's update.  Pulling
-      // the f32 rows instead (128 KB per CTA at the ~70 GB/s one SM ingests) measured +7 us per GEMM; the f16 copy is
-      // the 64 KB the GEMM loads anyway, and the rewrite is shared-memory traffic only.
-      const int cidx = threadIdx.x - 64;           // 0..319
-      const int ntile = p.K >> 7;
-      const int BN = p.BN, T = p.T;
-      float* gam_s = ln_stat_s + 2 * 256;          // gamma | beta of this CTA's K slice
-      float* bet_s = gam_s + GEMM_MAX_SPLIT * GEMM_BK;
-      for (int i = cidx; i < nkb * (GEMM_BK / 4); i += 320) {   // constants: before the dependency resolves
-        reinterpret_cast<float4*>(gam_s)[i] = __ldg(reinterpret_cast<const float4*>(p.ln_w + kb0 * GEMM_BK) + i);
-        reinterpret_cast<float4*>(bet_s)[i] = __ldg(reinterpret_cast<const float4*>(p.ln_b + kb0 * GEMM_BK) + i);
-      }
-      pdl_wait();                                  // the statistics belong to the previous kernel
-      if (warp == 2) PTTS_TRACE(10);
-      const uint32_t stat_a = smem_u32(ln_stat_s);   // [256] (mean, rstd) pairs
-      if (cidx < BN) {
-        float mean = 0.f, rstd = 0.f;
-        if (cidx < T) {
-          const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(t0 + cidx) * ntile;
-          float2 sv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sv[i] = i < ntile ? st[i] : make_float2(0.f, 0.f);  // all requested before any is used
-          float tot = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) tot += sv[i].x;
-          mean = tot / static_cast<float>(p.K);
-          float m2 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float d = sv[i].x * (1.f / 128.f) - mean;
-            if (i < ntile) m2 += sv[i].y + 128.f * d * d;
-          }
-          rstd = 1.f / sqrtf(m2 / static_cast<float>(p.K) + p.ln_eps);
-        }
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(stat_a + cidx * 8), "f"(mean), "f"(rstd) : "memory");
-      }
-      if (warp == 2) PTTS_TRACE(11);
-      asm volatile("bar.sync 3, 320;" ::: "memory");
-      mbar_wait(full_bar, 0);                      // operand tiles (and f16 weights) have landed
-      if (warp == 2) PTTS_TRACE(14);
-      const uint32_t act_a = smem_u32(smem + p.kb_per_split * m_tile_bytes);
-      const uint32_t gam_a = smem_u32(gam_s), bet_a = smem_u32(bet_s);
-      const int chunks = nkb * BN * 8;             // 16-byte chunks = 8 consecutive k of one row
-      for (int q = cidx; q < chunks; q += 320) {
-        const int kb = q / (BN * 8);
-        const int rem = q - kb * (BN * 8);
-        const int row = rem >> 3;
-        const int c = (rem & 7) ^ (row & 7);       // SWIZZLE_128B: physical chunk (rem & 7) of row r holds logical chunk c
-        const uint32_t addr = act_a + kb * n_tile_bytes + rem * 16;
-        uint32_t h[4];
-        float g[8], b[8], mean, rstd;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(addr));
-        const uint32_t ko = (kb * GEMM_BK + c * 8) * 4;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]) : "r"(gam_a + ko));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7]) : "r"(gam_a + ko + 16));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]) : "r"(bet_a + ko));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]) : "r"(bet_a + ko + 16));
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(mean), "=f"(rstd) : "r"(stat_a + row * 8));
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
-          const __half2 y = __floats2half2_rn((x.x - mean) * rstd * g[2 * j] + b[2 * j], (x.y - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
-          o[j] = row < T ? *reinterpret_cast<const uint32_t*>(&y) : 0u;   // rows past the batch stay zero
-        }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(actc_bar);
-      if (warp == 2) PTTS_TRACE(15);
-    }
     if (warp < 6) {
     // ===== epilogue, first half: TMEM -> registers -> smem tile [activation row][feature] (raw f32) =====
     // The pipeline stages are dead once tmem_full has arrived (every MMA has consumed its operands), so the tile
@@ -852,7 +733,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   __syncthreads();
   if (nsplit > 1) cluster_sync_all();  // all partial tiles are staged and visible cluster-wide
   pdl_wait();  // residual / gate / output tensors belong to earlier kernels until they have completed
-  epi_dispatch<true>(p, smem_u32(smem), (p.swap ? GEMM_BM : p.BN) + 4, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
+  epi_dispatch(p, smem_u32(smem), (p.swap ? GEMM_BM : p.BN) + 4, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
   if (warp == 2) PTTS_TRACE(8);
   if (nsplit > 1) cluster_sync_relaxed();  // peers may still be reading this CTA's tile
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);

@@ -45,7 +45,7 @@ class Voice:
 class Engine:
     def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
                  kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True, int8_weights: bool = False,
-                 int8_storage: bool = True, ln_fusion: bool = False):
+                 int8_storage: bool = True):
         L = _lib.lib()
         self._keep = []
         descs = (TensorDesc * len(weights))()
@@ -63,7 +63,6 @@ class Engine:
         cfg.max_batch = max_batch or max_slots
         cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, int(int8_weights), int(cuda_graph), debug_gemm
         cfg.reserved[0] = gemm_mode
-        cfg.reserved[8] = 1 if ln_fusion else 0     # opt-in: LayerNorm fused in front of in_proj / linear1 (decode, <= 64 rows)
         cfg.reserved[7] = 0 if int8_storage else 1  # test hook: int8 mode streaming f16 copies of the codes instead of bytes
         h = C.c_void_p()
         check(L.ptts_engine_create(C.byref(cfg), descs, len(weights), C.byref(h)))
@@ -222,19 +221,6 @@ def test_gemm_int8(a, w, split_k=1, storage=1, device=0):
     check(_lib.lib().ptts_test_gemm_int8(device, _ptr(a), _ptr(w), _ptr(d), a.shape[0], w.shape[0], a.shape[1], split_k,
                                          storage, C.byref(scale)))
     return d, float(scale.value)
-
-
-def test_gemm_ln_front(a0, w0, gamma, beta, w1, eps=1e-5, device=0):
-    """-> (X = A0 W0^T [rows,k], D = (LN(X) gamma + beta) W1^T [rows,feats]) with the LayerNorm fused in front of the
-    second GEMM (ptts.h)."""
-    a0, w0, w1 = (np.ascontiguousarray(v, np.float32) for v in (a0, w0, w1))
-    gamma, beta = np.ascontiguousarray(gamma, np.float32), np.ascontiguousarray(beta, np.float32)
-    rows, k0 = a0.shape
-    k, feats = w0.shape[0], w1.shape[0]
-    x = np.zeros((rows, k), np.float32); d = np.zeros((rows, feats), np.float32)
-    check(_lib.lib().ptts_test_gemm_ln_front(device, _ptr(a0), _ptr(w0), _ptr(gamma), _ptr(beta), _ptr(w1), _ptr(x), _ptr(d),
-                                             rows, k0, k, feats, eps))
-    return x, d
 
 
 def test_conv1d(x, prev, w, bias, device=0):

@@ -7,22 +7,15 @@ import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from pocket_tts_b200 import _lib
 L = _lib.lib()
-cases = [(64, 3072, 1024, "in_proj + LN in front", 20), (64, 4096, 1024, "linear1 + LN in front", 20), (64, 1024, 1024, "out_proj + stats", 21),
-         (64, 1024, 64, "input_linear + stats", 21), (64, 1024, 64, "input_linear", 0),
-         (64, 512, 512, "flow.mlp"), (64, 1024, 1024, "out_proj"), (64, 3072, 1024, "in_proj"), (64, 4096, 1024, "linear1"),
+cases = [(64, 512, 512, "flow.mlp"), (64, 1024, 1024, "out_proj"), (64, 3072, 1024, "in_proj"), (64, 4096, 1024, "linear1"),
          (64, 1024, 4096, "linear2"), (1024, 1536, 512, "mimi.in_proj"), (1024, 2048, 512, "mimi.linear1")]
 MAXC = 160
-for case in cases:
-    rows, feats, k, nm = case[:4]
-    mode = case[4] if len(case) > 4 else 0
+for rows, feats, k, nm in cases:
     us = C.c_float(); n = C.c_int32(); st = np.zeros(16 * MAXC, np.int64)
-    _lib.check(L.ptts_test_gemm_trace(0, rows, feats, k, mode, 0, 20, C.byref(us), st.ctypes.data_as(C.c_void_p), MAXC, C.byref(n)))
+    _lib.check(L.ptts_test_gemm_trace(0, rows, feats, k, 0, 0, 20, C.byref(us), st.ctypes.data_as(C.c_void_p), MAXC, C.byref(n)))
     s = st.reshape(MAXC, 16)[: n.value]
     print(f"{nm}: rows={rows} F={feats} K={k}: {us.value:.2f} us/launch back-to-back, {n.value} CTAs")
     ok = s[:, 9] >= 0
     rel = s[ok][:, :10] - s[ok][:, :1]
     print("   median per-CTA stamps rel. entry:", np.median(rel, axis=0).astype(int).tolist())
-    if mode == 20:
-        ln = s[ok][:, [10, 11, 14, 15]] - s[ok][:, :1]
-        print("   LN converter stamps [after wait, x requested + stats, barrier passed, operand written]:", np.median(ln, axis=0).astype(int).tolist())
     print("   entry spread", int(s[ok][:, 0].max() - s[ok][:, 0].min()), " kernel span", int(s[ok][:, 9].max() - s[ok][:, 0].min()))

@@ -84,35 +84,6 @@ def test_gemm_int8_storage(rows, feats, k, split):
     assert err < 2e-3, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("rows,k0,k,feats", [(64, 64, 1024, 3072), (64, 1024, 1024, 4096), (1, 64, 1024, 3072), (37, 256, 1024, 640),
-                                             (64, 128, 512, 512)])
-def test_gemm_layernorm_in_front(rows, k0, k, feats):
-    """FlowLM decode at <= 64 rows: the GEMM that writes the residual stream leaves per-row statistics and the next GEMM
-    normalises its own operand tiles in shared memory (no LayerNorm launch).  Checked against LayerNorm (biased variance,
-    eps inside the sqrt: reference modules/mlp.rs:29-58) of the X the first GEMM actually produced, then a plain
-    f16-operand product."""
-    from pocket_tts_b200.engine import test_gemm_ln_front as run
-    rng = np.random.default_rng(rows + k + feats)
-    a0 = rng.standard_normal((rows, k0)).astype(np.float32)
-    w0 = (rng.standard_normal((k, k0)) / np.sqrt(k0)).astype(np.float32)
-    w0 += np.float32(0.6 / np.sqrt(k0))  # a row mean of the order of the row's spread, so a wrong mean would show
-    gamma = (1.0 + 0.2 * rng.standard_normal(k)).astype(np.float32)
-    beta = (0.1 * rng.standard_normal(k)).astype(np.float32)
-    w1 = (rng.standard_normal((feats, k)) / np.sqrt(k)).astype(np.float32)
-    x, d = run(a0, w0, gamma, beta, w1)
-    np.testing.assert_allclose(x, ref_gemm(a0, w0), atol=5e-3)
-    xt = torch.from_numpy(x).double()
-    # the kernel normalises the f16 copy of x with the statistics of the f32 rows
-    mean, var = xt.mean(1, keepdim=True), xt.var(1, unbiased=False, keepdim=True)
-    h = (torch.from_numpy(f16r(x)).double() - mean) / torch.sqrt(var + 1e-5) * torch.from_numpy(gamma).double() + torch.from_numpy(beta).double()
-    want = ref_gemm(h.float().numpy(), w1)
-    err = np.abs(d - want).max()
-    assert err < 2e-3, f"max abs err {err}"
-    # and it stays close to LayerNorm of the unrounded rows (what the separate LayerNorm launch computes)
-    exact = ref_gemm(F.layer_norm(xt, (k,), torch.from_numpy(gamma).double(), torch.from_numpy(beta).double(), 1e-5).float().numpy(), w1)
-    assert np.abs(d - exact).max() < 6e-3
-
-
 CONV_CASES = [(3, 16, 512, 512, 7), (2, 96, 256, 128, 3), (2, 480, 128, 64, 3), (1, 1920, 64, 64, 3), (9, 16, 512, 64, 7),
               (12, 1920, 64, 64, 3), (40, 480, 128, 64, 3)]  # the last two run the persistent kernel
 

@@ -259,26 +259,6 @@ def test_host_mirror_generate_stream_tokens():
     m.close()
 
 
-def test_layernorm_fusion_opt_in_stays_inside_tolerance(golden_dir):
-    """Engine(ln_fusion=True): no LayerNorm launches in the FlowLM decode step (<= 64 rows); in_proj / linear1 normalise
-    their own operand tiles.  Same tolerances as the default path, against the reference goldens."""
-    from pocket_tts_b200.engine import Engine
-    for e in _cache.values():
-        e[0].close()
-    _cache.clear()
-    g = np.load(golden_dir / "cfg1_lsd1.npz")
-    eng = Engine(synth.make_weights(int(g["weight_seed"]), layer_scale=float(g["layer_scale"])), max_slots=4, kv_capacity=512,
-                 ln_fusion=True)
-    voice = eng.voice_from_prompt(synth.make_voice_prompt(int(g["voice_rows"]), seed=7))
-    lat, pcm, logit = run_engine(eng, voice, g)
-    launches = eng.launch_count()
-    voice.close()
-    eng.close()
-    assert np.abs(lat - g["tanh_latents"]).max() <= LAT_TOL
-    assert snr(g["tanh_pcm"], pcm) >= SNR_MIN
-    assert np.abs(logit - g["tanh_eos_logits"]).max() < 2e-2
-
-
 def test_step_ahead_matches_lockstep_and_never_emits_past_the_end():
     """PTTS_STEP_AHEAD: frame n+1 enqueued before frame n's flags are fetched.  Same frames bit for bit as the lock-step
     calls; a stream that ends at EOS (D2: frames = eos_step + frames_after_eos + 1, tts_model.rs:1055-1069) reports
