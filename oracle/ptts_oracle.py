@@ -332,6 +332,78 @@ def mimi_decode_step(W, latent, st: MimiState, gelu_kind="tanh", trace: dict | N
     return x.reshape(-1)
 
 
+# --------------------------------------------------------------------------- Mimi encoder (voice cloning from PCM, N1)
+def streaming_conv1d_strided(W, name: str, x, st: MimiState, stride: int, replicate_first: bool = False):
+    """RS modules/conv.rs:90-136 for any stride: x' = [previous | x] with previous = the last k - stride columns,
+    y = conv(x', stride); `replicate` pad mode on a first call (step == 0) pads with the first column instead
+    (conv.rs:114-123).  x [Cin, T], T a multiple of the stride."""
+    w = W[name + ".conv.weight"]
+    b = W.get(name + ".conv.bias")
+    k = w.shape[-1]
+    assert x.shape[1] > 0 and x.shape[1] % stride == 0, "Steps must be multiple of stride"
+    pad = k - stride
+    if pad > 0:
+        if replicate_first:
+            prev = x[:, :1].expand(-1, pad)
+        else:
+            prev = st.conv_prev.get(name)
+            if prev is None:
+                prev = torch.zeros(x.shape[0], pad)
+        xp = torch.cat([prev, x], dim=1)
+        st.conv_prev[name] = xp[:, -pad:].clone()
+    else:
+        xp = x
+    return F.conv1d(_a(xp).unsqueeze(0), w, b, stride=stride).squeeze(0)
+
+
+def mimi_encode_chunk(W, pcm, st: MimiState, gelu_kind="tanh"):
+    """RS models/mimi.rs:113-141 encode_to_latent (called with step = 0 for every chunk, tts_model.rs:540):
+    SEANetEncoder (seanet.rs:148-247: conv k7, then per ratio [4, 5, 6] a ResBlock and an ELU + strided conv with
+    k = 2 * ratio, then ELU + conv k3) -> encoder ProjectedTransformer (context 250, LayerScale) -> ConvDownsample1d
+    (stride 16, k 32, no bias, replicate padding; conv.rs:278-312).  pcm [T], T a multiple of 1920 -> [512, T / 1920]."""
+    e = "mimi.encoder.model."
+    x = streaming_conv1d_strided(W, e + "0", pcm.view(1, -1), st, 1)
+    for res, conv, stride in ((1, 3, 4), (4, 6, 5), (7, 9, 6)):
+        r = e + f"{res}.block."
+        v = streaming_conv1d_strided(W, r + "1", elu(x), st, 1)
+        v = streaming_conv1d_strided(W, r + "3", elu(v), st, 1)
+        x = x + v  # seanet.rs:82-88
+        x = streaming_conv1d_strided(W, e + str(conv), elu(x), st, stride)
+    x = streaming_conv1d_strided(W, e + "11", elu(x), st, 1)  # [512, T / 120]
+    x = transformer_forward(W, "mimi.encoder_transformer.transformer", x.T.contiguous(), st.attn, MIMI_LAYERS, MIMI_HEADS,
+                            MIMI_CONTEXT, True, gelu_kind).T.contiguous()
+    return streaming_conv1d_strided(W, "mimi.downsample.conv", x, st, 16, replicate_first=True)
+
+
+def voice_prompt_chunk_frames(total_frames: int) -> int:
+    """RS tts_model.rs:562-577 adaptive_voice_prompt_chunk_frames."""
+    if total_frames <= 120:
+        return max(total_frames, 1)
+    if total_frames <= 600:
+        return 120
+    if total_frames <= 1800:
+        return 180
+    return 240
+
+
+def audio_prompt_from_pcm(W, pcm, gelu_kind="tanh", chunk_frames: int | None = None):
+    """RS tts_model.rs:504-556 get_voice_state_from_tensor up to the conditioning rows: zero-pad to whole frames,
+    encode in chunks with one carried Mimi state, transpose, project with speaker_proj_weight.
+    pcm [T] at 24 kHz -> audio_prompt [frames, 1024] (what voice_state_from_prompt consumes)."""
+    pcm = torch.as_tensor(pcm).float().reshape(-1)
+    pad = (-pcm.numel()) % FRAME_SAMPLES
+    if pad:
+        pcm = torch.cat([pcm, torch.zeros(pad)])
+    frames = pcm.numel() // FRAME_SAMPLES
+    step = (chunk_frames or voice_prompt_chunk_frames(frames)) * FRAME_SAMPLES
+    st = MimiState()
+    st.attn = AttnState()
+    st.conv_prev = {}
+    lat = [mimi_encode_chunk(W, pcm[s:s + step], st, gelu_kind) for s in range(0, pcm.numel(), step)]
+    lat = torch.cat(lat, dim=1).T.contiguous()  # [frames, 512]
+    return _a(lat) @ W["flow_lm.speaker_proj_weight"].T
+
+
 # --------------------------------------------------------------------------- host control (A17)
 def strip_pause_markers(text: str) -> str:
     """RS pause.rs:34-37 EXPLICIT_PAUSE_REGEX (case-sensitive): `[pause:Xms|Xs]` -> single space."""

@@ -172,6 +172,67 @@ def make_weights(seed: int = 1234, layer_scale: float = 0.01, gain: float = 1.0)
     return out
 
 
+def encoder_weight_shapes() -> dict[str, tuple[int, ...]]:
+    """Mimi encoder side (voice cloning from PCM): SEANetEncoder, encoder transformer, downsample.
+    Key names and layouts of the checkpoint (reference build sites: models/seanet.rs:148-247, models/mimi.rs:60-98)."""
+    s: dict[str, tuple[int, ...]] = {}
+    e = "mimi.encoder.model."
+    conv = {
+        "0.conv": (64, 1, 7),
+        "1.block.1.conv": (32, 64, 3), "1.block.3.conv": (64, 32, 1),
+        "3.conv": (128, 64, 8),
+        "4.block.1.conv": (64, 128, 3), "4.block.3.conv": (128, 64, 1),
+        "6.conv": (256, 128, 10),
+        "7.block.1.conv": (128, 256, 3), "7.block.3.conv": (256, 128, 1),
+        "9.conv": (512, 256, 12),
+        "11.conv": (512, 512, 3),
+    }
+    for k, shp in conv.items():
+        s[e + k + ".weight"] = shp
+        s[e + k + ".bias"] = (shp[0],)
+    for i in range(MIMI_LAYERS):
+        p = f"mimi.encoder_transformer.transformer.layers.{i}."
+        s[p + "self_attn.in_proj.weight"] = (3 * MIMI_DIM, MIMI_DIM)
+        s[p + "self_attn.out_proj.weight"] = (MIMI_DIM, MIMI_DIM)
+        for n in ("norm1", "norm2"):
+            s[p + n + ".weight"] = (MIMI_DIM,)
+            s[p + n + ".bias"] = (MIMI_DIM,)
+        s[p + "linear1.weight"] = (MIMI_FFN, MIMI_DIM)
+        s[p + "linear2.weight"] = (MIMI_DIM, MIMI_FFN)
+        s[p + "layer_scale_1.scale"] = (MIMI_DIM,)
+        s[p + "layer_scale_2.scale"] = (MIMI_DIM,)
+    s["mimi.downsample.conv.conv.weight"] = (MIMI_DIM, MIMI_DIM, 2 * UPSAMPLE_STRIDE)
+    return s
+
+
+def make_encoder_weights(seed: int = 4321, layer_scale: float = 0.01) -> dict[str, np.ndarray]:
+    """Seeded encoder-side tensors from their OWN generator, so adding them never changes make_weights()' tensors
+    (the committed goldens depend on those)."""
+    rng = np.random.default_rng(seed)
+    out: dict[str, np.ndarray] = {}
+    for name, shape in encoder_weight_shapes().items():
+        g = rng.standard_normal(int(np.prod(shape)), dtype=np.float32).reshape(shape)
+        if name.endswith("layer_scale_1.scale") or name.endswith("layer_scale_2.scale"):
+            w = layer_scale * (1.0 + 0.25 * g)
+        elif len(shape) == 1 and name.endswith(".weight"):
+            w = 1.0 + 0.1 * g
+        elif len(shape) == 1:
+            w = 0.05 * g
+        else:
+            w = g * np.float32(np.sqrt(1.0 / _fan_in(name, shape)))
+        out[name] = bf16_round(w.astype(np.float32))
+    return out
+
+
+def make_pcm(n_samples: int, seed: int = 3) -> np.ndarray:
+    """Synthetic 24 kHz mono prompt: a few decaying partials plus noise, peak ~0.5."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float64) / 24000.0
+    x = sum(a * np.sin(2 * np.pi * f * t + ph) for a, f, ph in zip((0.3, 0.15, 0.1), (180.0, 410.0, 1230.0), rng.uniform(0, 6.28, 3)))
+    x = x * (0.6 + 0.4 * np.sin(2 * np.pi * 3.0 * t)) + 0.02 * rng.standard_normal(n_samples)
+    return x.astype(np.float32)
+
+
 def make_voice_prompt(n_rows: int = 87, seed: int = 7) -> np.ndarray:
     """Synthetic `audio_prompt` [T, 1024] with the magnitude of the reference's
     assets/ref_voice_conditioning.safetensors (max-abs ~0.9, 87 rows)."""

@@ -37,7 +37,7 @@ from pocket_tts_b200 import synth  # noqa: E402
 torch.set_grad_enabled(False)
 
 
-def build_reference_model(weights: dict[str, np.ndarray], lsd_steps: int):
+def build_reference_model(weights: dict[str, np.ndarray], lsd_steps: int, allow_missing_encoder: bool = True):
     import pocket_tts.conditioners.text as ctext
 
     # The tokenizer download is the only constructor side effect; token IDs are fed directly.
@@ -55,6 +55,8 @@ def build_reference_model(weights: dict[str, np.ndarray], lsd_steps: int):
     # only the Mimi *encoder* side (voice cloning from PCM) is not covered by synth weights
     assert all(m.startswith(("mimi.encoder", "mimi.downsample", "flow_lm.flow_net.time_embed")) and
                ("freqs" in m or m.startswith("mimi.")) for m in missing), missing
+    if not allow_missing_encoder:
+        assert not any(m.startswith("mimi.") for m in missing), missing
     model.eval()
     return model
 
@@ -117,8 +119,35 @@ CASES = [
 ]
 
 
+def make_encoder_golden(out_dir: Path):
+    """Voice cloning from PCM: the package's own `_encode_audio` (models/tts_model.py:258-262 =
+    mimi.encode_to_latent -> transpose -> F.linear(speaker_proj_weight)) on seeded encoder weights and a seeded prompt.
+    The prompt length is not a multiple of the frame size, so the package's own end padding is exercised."""
+    import torch.nn.functional as F
+    weights = dict(synth.make_weights(1234, layer_scale=0.01))
+    weights.update(synth.make_encoder_weights(4321, layer_scale=0.5))  # LayerScale large enough for attention to show
+    model = build_reference_model(weights, 1, allow_missing_encoder=False)
+    n_samples = 22 * 1920 - 700   # 22 frames = 352 encoder-transformer positions: crosses the 250-position window
+    pcm = synth.make_pcm(n_samples, seed=3)
+    blob = dict(n_samples=n_samples, pcm_seed=3, enc_seed=4321, enc_layer_scale=0.5)
+    orig = F.gelu
+    try:
+        for kind in ("erf", "tanh"):
+            if kind == "tanh":
+                F.gelu = lambda x: orig(x, approximate="tanh")
+            out = model._encode_audio(torch.from_numpy(pcm).view(1, 1, -1))[0].numpy()
+            blob[f"{kind}_audio_prompt"] = out.astype(np.float32)
+            print("encoder", kind, out.shape, "absmax", float(np.abs(out).max()))
+    finally:
+        F.gelu = orig
+    np.savez_compressed(out_dir / "enc_pcm22.npz", **blob)
+    print("wrote", out_dir / "enc_pcm22.npz", os.path.getsize(out_dir / "enc_pcm22.npz"))
+
+
 def main():
     out_dir = Path(__file__).resolve().parent
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        return make_encoder_golden(out_dir)
     cache = {}
     for name, wseed, ls, vrows, ntok, frames, lsd in CASES:
         key = (wseed, ls)

@@ -48,3 +48,40 @@ def test_oracle_decoder_stages_frame0(golden_dir, case):
     np.testing.assert_allclose(trace["mimi.after_decoder_transformer"].numpy(),
                                g["tanh_stage_after_decoder_transformer"], atol=1e-4)
     np.testing.assert_allclose(pcm.numpy(), g["tanh_pcm"][0], atol=5e-4)
+
+
+def encoder_weights(g):
+    w = dict(synth.make_weights(1234, layer_scale=0.01))
+    w.update(synth.make_encoder_weights(int(g["enc_seed"]), layer_scale=float(g["enc_layer_scale"])))
+    return O.to_torch(w)
+
+
+@pytest.mark.parametrize("kind", ["erf", "tanh"])
+def test_oracle_voice_cloning_encoder_matches_reference_package(golden_dir, kind):
+    """SURVEY 8f N1 (oracle side): PCM -> SEANetEncoder -> encoder transformer -> downsample -> speaker_proj equals the
+    unmodified package's `_encode_audio` (22 frames: 352 transformer positions cross the 250-position window; the
+    prompt length is ragged, so the zero end-padding of tts_model.rs:514-527 is exercised)."""
+    g = np.load(golden_dir / "enc_pcm22.npz")
+    W = encoder_weights(g)
+    pcm = synth.make_pcm(int(g["n_samples"]), seed=int(g["pcm_seed"]))
+    got = O.audio_prompt_from_pcm(W, pcm, kind).numpy()
+    want = g[f"{kind}_audio_prompt"]
+    assert got.shape == want.shape == (22, 1024)
+    np.testing.assert_allclose(got, want, atol=3e-4, rtol=0)
+
+
+def test_oracle_encoder_chunking_follows_the_reference():
+    """RS encodes long prompts in chunks with one carried state (tts_model.rs:528-541) and passes step = 0 for every
+    chunk, so only the replicate padding of the downsample restarts at a chunk boundary (conv.rs:114-123): every
+    other layer is exactly streaming, and the frames after a boundary differ from the unchunked run only through that
+    one convolution's first window."""
+    g_w = dict(synth.make_weights(1234, layer_scale=0.01))
+    g_w.update(synth.make_encoder_weights(4321, layer_scale=0.5))
+    W = O.to_torch(g_w)
+    pcm = synth.make_pcm(6 * 1920, seed=5)
+    whole = O.audio_prompt_from_pcm(W, pcm, "tanh", chunk_frames=6).numpy()
+    halves = O.audio_prompt_from_pcm(W, pcm, "tanh", chunk_frames=3).numpy()
+    np.testing.assert_allclose(halves[:3], whole[:3], atol=1e-5)      # before the boundary: identical
+    assert np.abs(halves[3] - whole[3]).max() > 1e-3                   # the boundary frame sees replicated padding
+    np.testing.assert_allclose(halves[4:], whole[4:], atol=2e-4)      # later frames: streaming again
+    assert [O.voice_prompt_chunk_frames(n) for n in (1, 87, 120, 121, 600, 601, 1800, 1801)] == [1, 87, 120, 120, 120, 180, 180, 240]
