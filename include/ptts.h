@@ -98,6 +98,18 @@ int32_t ptts_engine_set_lsd_steps(ptts_engine* e, int32_t lsd_steps);
  * run_flow_lm_prompt :580-599): FlowLM prefill over audio_prompt [T,1024] f32 (host);
  * the resulting KV snapshot is immutable and shared by every stream opened with it. */
 int32_t ptts_voice_from_prompt(ptts_engine* e, const float* audio_prompt, int32_t n_rows, ptts_voice** out);
+
+/* Replaces TTSModel::get_voice_state / get_voice_state_from_tensor (tts_model.rs:449-556): voice cloning from 24 kHz
+ * mono PCM (host f32; the WAV read and resample of tts_model.rs:449-466 stay host code).  The prompt is zero-padded to
+ * whole 1920-sample frames and run through the Mimi encoder (SEANetEncoder -> encoder transformer -> ConvDownsample1d,
+ * models/mimi.rs:113-141) and speaker_proj_weight; the FlowLM prefill of ptts_voice_from_prompt follows.  Needs the
+ * encoder tensors in the checkpoint (PTTS_ERR_STATE otherwise); prompts of up to 120 frames (9.6 s), which the
+ * reference encodes in one chunk (tts_model.rs:562-577) -- longer ones give PTTS_ERR_CAPACITY.
+ * ptts_audio_prompt_from_pcm stops after the conditioning rows [n_rows,1024] (the tensor the reference stores under
+ * `audio_prompt`); audio_prompt_out may be NULL to query n_rows only. */
+int32_t ptts_voice_from_pcm(ptts_engine* e, const float* pcm24k, int32_t n_samples, ptts_voice** out);
+int32_t ptts_audio_prompt_from_pcm(ptts_engine* e, const float* pcm24k, int32_t n_samples, float* audio_prompt_out,
+                                   int32_t cap_rows, int32_t* n_rows_out);
 void ptts_voice_destroy(ptts_engine* e, ptts_voice* v);
 int32_t ptts_voice_len(const ptts_voice* v);
 

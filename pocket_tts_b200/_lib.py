@@ -10,7 +10,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libptts_cuda.so"
 # every symbol include/ptts.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "ptts_last_error", "ptts_abi_version", "ptts_engine_create", "ptts_engine_destroy",
-    "ptts_engine_set_lsd_steps", "ptts_voice_from_prompt", "ptts_voice_destroy", "ptts_voice_len",
+    "ptts_engine_set_lsd_steps", "ptts_voice_from_prompt", "ptts_voice_from_pcm", "ptts_audio_prompt_from_pcm", "ptts_voice_destroy", "ptts_voice_len",
     "ptts_streams_open", "ptts_step", "ptts_step_begin", "ptts_step_flags", "ptts_step_pcm", "ptts_step_device", "ptts_sync", "ptts_stream_set_feedback",
     "ptts_stream_close", "ptts_stream_frames", "ptts_debug_read", "ptts_launch_count", "ptts_step_timed",
     "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report", "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
@@ -52,6 +52,8 @@ def lib() -> C.CDLL:
     L.ptts_engine_destroy.restype = None
     L.ptts_engine_set_lsd_steps.argtypes = [vp, i32]
     L.ptts_voice_from_prompt.argtypes = [vp, vp, i32, C.POINTER(vp)]
+    L.ptts_voice_from_pcm.argtypes = [vp, vp, i32, C.POINTER(vp)]
+    L.ptts_audio_prompt_from_pcm.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32)]
     L.ptts_voice_destroy.argtypes = [vp, vp]
     L.ptts_voice_destroy.restype = None
     L.ptts_voice_len.argtypes = [vp]

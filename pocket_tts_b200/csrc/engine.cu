@@ -145,6 +145,15 @@ struct Engine {
   DevBuf<float> wq, wup;
   Weight16 m_inproj[MIMI_LAYERS], m_outproj[MIMI_LAYERS], m_lin1[MIMI_LAYERS], m_lin2[MIMI_LAYERS];
   DevBuf<float> m_ln1_w[MIMI_LAYERS], m_ln1_b[MIMI_LAYERS], m_ln2_w[MIMI_LAYERS], m_ln2_b[MIMI_LAYERS], m_ls1[MIMI_LAYERS], m_ls2[MIMI_LAYERS];
+  // Mimi encoder side (voice cloning from PCM); present only when the checkpoint carries the encoder tensors
+  bool has_encoder = false;
+  DevBuf<float> en_conv0_w, en_conv0_b;                   // [7][64], [64]
+  Weight16 en_r1[3], en_r3[3], en_down[3], en_c11;         // ResBlock k3 / k1 convs and the strided conv of each level; last conv
+  DevBuf<float> enb_r1[3], enb_r3[3], enb_down[3], enb_c11;
+  Weight16 et_inproj[MIMI_LAYERS], et_outproj[MIMI_LAYERS], et_lin1[MIMI_LAYERS], et_lin2[MIMI_LAYERS], en_ds, w_spk;
+  DevBuf<float> et_ln1_w[MIMI_LAYERS], et_ln1_b[MIMI_LAYERS], et_ln2_w[MIMI_LAYERS], et_ln2_b[MIMI_LAYERS], et_ls1[MIMI_LAYERS], et_ls2[MIMI_LAYERS];
+  void load_encoder_weights();
+  void encode_prompt(const float* pcm_host, int n_samples, std::vector<float>& prompt, int* frames);
   Weight16 s_conv0, s_ct2, s_r3a, s_r3b, s_ct5, s_r6a, s_r6b, s_ct8, s_r9a, s_r9b;
   DevBuf<float> sb_conv0, sb_ct2, sb_r3a, sb_r3b, sb_ct5, sb_r6a, sb_r6b, sb_ct8, sb_r9a, sb_r9b, s_final_w, s_final_b;
 
@@ -520,6 +529,53 @@ void Engine::load_weights(const ptts_tensor_desc* w, int nw) {
     PTTS_CUDA(cudaMemcpy(s_final_w.p, g.data(), 192 * 4, cudaMemcpyHostToDevice));
     vec(s_final_b, d + "11.conv.bias", 1);
   }
+  has_encoder = host.count("mimi.encoder.model.0.conv.weight") != 0;
+  if (has_encoder) load_encoder_weights();
+}
+
+// Encoder side of Mimi (reference models/seanet.rs:148-247, models/mimi.rs:60-98, tts_model.rs:315-330): SEANetEncoder
+// with ratios [4, 5, 6], the encoder transformer, ConvDownsample1d (stride 16) and speaker_proj_weight.
+void Engine::load_encoder_weights() {
+  const std::string e = "mimi.encoder.model.";
+  {
+    const HostTensor& tw = T(e + "0.conv.weight", {64, 1, 7});
+    std::vector<float> g(7 * 64);
+    for (int c = 0; c < 64; ++c) for (int j = 0; j < 7; ++j) g[j * 64 + c] = tw.f32[c * 7 + j];
+    en_conv0_w.alloc(g.size());
+    PTTS_CUDA(cudaMemcpy(en_conv0_w.p, g.data(), g.size() * 4, cudaMemcpyHostToDevice));
+    vec(en_conv0_b, e + "0.conv.bias", 64);
+  }
+  const int res_idx[3] = {1, 4, 7}, down_idx[3] = {3, 6, 9}, ratio[3] = {4, 5, 6};
+  for (int l = 0; l < 3; ++l) {
+    const int C = 64 << l, H = C / 2, Hp = std::max(H, 64);
+    const std::string r = e + std::to_string(res_idx[l]) + ".block.";
+    // a 32-wide hidden layer is padded to 64 channels exactly like the decoder's last ResBlock
+    conv_weight(en_r1[l], enb_r1[l], T(r + "1.conv.weight", {H, C, 3}), T(r + "1.conv.bias", {H}), H, C, 3, Hp, C);
+    conv_weight(en_r3[l], enb_r3[l], T(r + "3.conv.weight", {C, H, 1}), T(r + "3.conv.bias", {C}), C, H, 1, C, Hp);
+    // strided conv, k = 2 * ratio: [cout][j][cin] flattened is at once the two-tap weight over rows of `ratio` frames
+    const std::string dn = e + std::to_string(down_idx[l]);
+    conv_weight(en_down[l], enb_down[l], T(dn + ".conv.weight", {2 * C, C, 2 * ratio[l]}), T(dn + ".conv.bias", {2 * C}), 2 * C, C,
+                2 * ratio[l], 2 * C, C);
+  }
+  conv_weight(en_c11, enb_c11, T(e + "11.conv.weight", {512, 512, 3}), T(e + "11.conv.bias", {512}), 512, 512, 3, 512, 512);
+  for (int l = 0; l < MIMI_LAYERS; ++l) {
+    const std::string p = "mimi.encoder_transformer.transformer.layers." + std::to_string(l) + ".";
+    linear(et_inproj[l], p + "self_attn.in_proj.weight", 3 * MIMI_DIM, MIMI_DIM, 0, false);
+    linear(et_outproj[l], p + "self_attn.out_proj.weight", MIMI_DIM, MIMI_DIM, 0, false);
+    linear(et_lin1[l], p + "linear1.weight", MIMI_FFN, MIMI_DIM, 0, false);
+    linear(et_lin2[l], p + "linear2.weight", MIMI_DIM, MIMI_FFN, 0, false);
+    vec(et_ln1_w[l], p + "norm1.weight", MIMI_DIM); vec(et_ln1_b[l], p + "norm1.bias", MIMI_DIM);
+    vec(et_ln2_w[l], p + "norm2.weight", MIMI_DIM); vec(et_ln2_b[l], p + "norm2.bias", MIMI_DIM);
+    vec(et_ls1[l], p + "layer_scale_1.scale", MIMI_DIM); vec(et_ls2[l], p + "layer_scale_2.scale", MIMI_DIM);
+  }
+  {
+    const HostTensor& tw = T("mimi.downsample.conv.conv.weight", {512, 512, 32});
+    HostTensor nob{};
+    nob.f32.assign(512, 0.f);
+    DevBuf<float> unused;
+    conv_weight(en_ds, unused, tw, nob, 512, 512, 32, 512, 512);
+  }
+  linear(w_spk, "flow_lm.speaker_proj_weight", D_MODEL, MIMI_DIM, 0, false);
 }
 
 // TimestepEmbedder + combine on the host in f32 (reference modules/mlp.rs:84-133,296-319); hoisted out of the
@@ -1115,6 +1171,86 @@ void Engine::run_step(int n) {
   PTTS_CUDA(cudaGetLastError());
 }
 
+// PCM -> audio_prompt rows (reference tts_model.rs:504-556 up to the conditioning; models/mimi.rs:113-141):
+// zero-pad to whole frames, SEANetEncoder, encoder transformer, ConvDownsample1d, speaker_proj.  One pass over the whole
+// prompt, which is what the reference does for prompts of up to 120 frames (9.6 s; adaptive_voice_prompt_chunk_frames,
+// tts_model.rs:562-577).  Every conv is the same implicit GEMM the decoder uses: a strided conv with k = 2*stride is
+// a two-tap conv over the activation viewed as rows of `stride` frames ([T/s][s*C]), so no new GEMM path exists.
+void Engine::encode_prompt(const float* pcm_host, int n_samples, std::vector<float>& prompt, int* frames_out) {
+  PTTS_REQUIRE(has_encoder, PTTS_ERR_STATE, "this checkpoint has no Mimi encoder tensors (voice cloning needs mimi.encoder.*, mimi.encoder_transformer.*, mimi.downsample.*)");
+  const int F = (n_samples + FRAME - 1) / FRAME;
+  PTTS_REQUIRE(n_samples >= 1 && F <= 120, PTTS_ERR_CAPACITY, "voice prompt of %d samples = %d frames (supported: 1..120 frames; the reference "
+               "encodes longer prompts in chunks with a restarted downsample padding, not built)", n_samples, F);
+  ls = stream;
+  const int T0 = F * FRAME, ratio[3] = {4, 5, 6};
+  int Tl[4] = {T0, T0 / 4, T0 / 20, T0 / 120};
+  const int P = Tl[3];
+  DevBuf<float> pcm_d, xcur, xnext, tx, tqkv, prompt_d;
+  DevBuf<__half> ecur, enext, hbuf, esbuf, th16, ta16, tffn, d16, lat16;
+  pcm_d.alloc(T0);  // zero-filled: the tail past n_samples is the reference's end padding (tts_model.rs:514-527)
+  PTTS_CUDA(cudaMemcpyAsync(pcm_d.p, pcm_host, (size_t)n_samples * 4, cudaMemcpyHostToDevice, ls));
+  xcur.alloc((size_t)T0 * 64);
+  ecur.alloc((size_t)(2 + T0) * 64);
+  launch_k(false, enc_conv0_kernel, (unsigned)(((long long)T0 * 64 + 255) / 256), 256, 0, ls, 1, pcm_d.p, T0, en_conv0_w.p, en_conv0_b.p, xcur.p, ecur.p);
+  GemmEpi e;
+  for (int l = 0; l < 3; ++l) {
+    const int C = 64 << l, Hp = std::max(C / 2, 64), T = Tl[l], s = ratio[l], Tn = Tl[l + 1];
+    // ResBlock (seanet.rs:82-88): v = conv_k1(ELU(conv_k3(ELU(x)))); x += v; then ELU in front of the strided conv
+    hbuf.alloc((size_t)T * Hp);
+    e = epi_none(); e.bias = enb_r1[l].p; e.out16 = hbuf.p; e.act16 = ACT_ELU; e.out16_map = plain_map(Hp);
+    tag("encoder.res_a"); gemm(ActView{ecur.p, C, 2 + T, 1}, 1, T, 3, 128, 1, en_r1[l], Hp, e);
+    esbuf.alloc((size_t)(s + T) * C);  // `s` zero rows of left context in front (k - stride = stride)
+    e = epi_none(); e.bias = enb_r3[l].p; e.res = xcur.p; e.res_map = plain_map(C);
+    e.out16 = esbuf.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T, C, (long long)(s + T) * C, (long long)s * C);
+    tag("encoder.res_b"); gemm_rows(hbuf.p, T, Hp, en_r3[l], C, e);
+    // strided conv C -> 2C, k = 2s: two taps over [ (s+T)/s ][ s*C ]
+    xnext.alloc((size_t)Tn * 2 * C);
+    enext.alloc((size_t)(2 + Tn) * 2 * C);
+    e = epi_none(); e.bias = enb_down[l].p; e.out32 = xnext.p; e.out32_map = plain_map(2 * C);
+    e.out16 = enext.p; e.act16 = ACT_ELU; e.out16_map = stream_map(Tn, 2 * C, (long long)(2 + Tn) * 2 * C, (long long)2 * 2 * C);
+    tag("encoder.down"); gemm(ActView{esbuf.p, s * C, (s + T) / s, 1}, 1, Tn, 2, 128, 1, en_down[l], 2 * C, e);
+    PTTS_CUDA(cudaStreamSynchronize(ls));  // the buffers swapped below are freed by their DevBuf
+    std::swap(xcur, xnext);
+    std::swap(ecur, enext);
+  }
+  // last conv k3 512 -> 512 on ELU(x) (seanet.rs:236-246)
+  tx.alloc((size_t)P * MIMI_DIM);
+  e = epi_none(); e.bias = enb_c11.p; e.out32 = tx.p; e.out32_map = plain_map(MIMI_DIM);
+  tag("encoder.conv11"); gemm(ActView{ecur.p, MIMI_DIM, 2 + P, 1}, 1, P, 3, 128, 1, en_c11, MIMI_DIM, e);
+  // encoder transformer (mimi.rs:129-131; transformer.rs:227-251): causal, context 250, LayerScale
+  tqkv.alloc((size_t)P * 3 * MIMI_DIM); th16.alloc((size_t)P * MIMI_DIM); ta16.alloc((size_t)P * MIMI_DIM); tffn.alloc((size_t)P * MIMI_FFN);
+  tag("encoder.layernorm"); ln<MIMI_DIM>(tx.p, P, et_ln1_w[0].p, et_ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, th16.p, MIMI_DIM);
+  for (int l = 0; l < MIMI_LAYERS; ++l) {
+    e = epi_none(); e.out32 = tqkv.p; e.out32_map = plain_map(3 * MIMI_DIM);
+    tag("encoder.in_proj"); gemm_rows(th16.p, P, MIMI_DIM, et_inproj[l], 3 * MIMI_DIM, e);
+    launch_k(false, enc_rope_kernel, dim3(P, MIMI_HEADS), 32, 0, ls, 1, tqkv.p, 0);
+    launch_k(false, enc_attn_kernel, (unsigned)((P * MIMI_HEADS * 32 + 127) / 128), 128, 0, ls, 1, (const float*)tqkv.p, P, 250, ta16.p);
+    e = epi_none(); e.fscale = et_ls1[l].p; e.res = tx.p; e.res_map = plain_map(MIMI_DIM); e.out32 = tx.p; e.out32_map = plain_map(MIMI_DIM);
+    ln_after_next_gemm("encoder.layernorm", tx.p, P, MIMI_DIM, et_ln2_w[l].p, et_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, th16.p, MIMI_DIM);
+    tag("encoder.out_proj"); gemm_rows(ta16.p, P, MIMI_DIM, et_outproj[l], MIMI_DIM, e, true);
+    e = epi_none(); e.act = ACT_GELU; e.out16 = tffn.p; e.out16_map = plain_map(MIMI_FFN);
+    tag("encoder.linear1"); gemm_rows(th16.p, P, MIMI_DIM, et_lin1[l], MIMI_FFN, e);
+    e = epi_none(); e.fscale = et_ls2[l].p; e.res = tx.p; e.res_map = plain_map(MIMI_DIM); e.out32 = tx.p; e.out32_map = plain_map(MIMI_DIM);
+    if (l + 1 < MIMI_LAYERS)
+      ln_after_next_gemm("encoder.layernorm", tx.p, P, MIMI_DIM, et_ln1_w[l + 1].p, et_ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, th16.p, MIMI_DIM);
+    tag("encoder.linear2"); gemm_rows(tffn.p, P, MIMI_FFN, et_lin2[l], MIMI_DIM, e, true);
+  }
+  // ConvDownsample1d: stride 16, k 32, no bias, replicate padding (conv.rs:278-312) -> [F][512]; then speaker_proj
+  d16.alloc((size_t)(16 + P) * MIMI_DIM);
+  launch_k(false, enc_downsample_prep_kernel, 16 + P, 128, 0, ls, 1, (const float*)tx.p, d16.p);
+  lat16.alloc((size_t)std::max(F, 128) * MIMI_DIM);
+  e = epi_none(); e.out16 = lat16.p; e.out16_map = plain_map(MIMI_DIM);
+  tag("encoder.downsample"); gemm(ActView{d16.p, 16 * MIMI_DIM, (16 + P) / 16, 1}, 1, F, 2, 128, 1, en_ds, MIMI_DIM, e, true);
+  prompt_d.alloc((size_t)F * D_MODEL);
+  e = epi_none(); e.out32 = prompt_d.p; e.out32_map = plain_map(D_MODEL);
+  tag("encoder.speaker_proj"); gemm_rows(lat16.p, F, MIMI_DIM, w_spk, D_MODEL, e);
+  prompt.resize((size_t)F * D_MODEL);
+  PTTS_CUDA(cudaMemcpyAsync(prompt.data(), prompt_d.p, prompt.size() * 4, cudaMemcpyDeviceToHost, ls));
+  PTTS_CUDA(cudaStreamSynchronize(ls));
+  PTTS_CUDA(cudaGetLastError());
+  *frames_out = F;
+}
+
 void Engine::prefill(int rows) {
   ls = stream;
   tag("flowlm.layernorm"); ln<D_MODEL>(px32.p, rows, ln1_w[0].p, ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, ph16.p, D_MODEL);
@@ -1195,6 +1331,38 @@ int32_t ptts_voice_from_prompt(ptts_engine* h, const float* audio_prompt, int32_
   PTTS_CUDA(cudaStreamSynchronize(e.stream));
   *out = v.release();
   return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_audio_prompt_from_pcm(ptts_engine* h, const float* pcm24k, int32_t n_samples, float* audio_prompt_out, int32_t cap_rows,
+                                   int32_t* n_rows_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && pcm24k && n_rows_out, PTTS_ERR_INVALID, "ptts_audio_prompt_from_pcm: null argument");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  e.sync_all();
+  std::vector<float> prompt;
+  int frames = 0;
+  e.encode_prompt(pcm24k, n_samples, prompt, &frames);
+  *n_rows_out = frames;
+  if (audio_prompt_out) {
+    PTTS_REQUIRE(cap_rows >= frames, PTTS_ERR_INVALID, "audio_prompt_out holds %d rows, the prompt has %d", cap_rows, frames);
+    std::memcpy(audio_prompt_out, prompt.data(), prompt.size() * 4);
+  }
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_voice_from_pcm(ptts_engine* h, const float* pcm24k, int32_t n_samples, ptts_voice** out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && pcm24k && out, PTTS_ERR_INVALID, "ptts_voice_from_pcm: null argument");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  e.sync_all();
+  std::vector<float> prompt;
+  int frames = 0;
+  e.encode_prompt(pcm24k, n_samples, prompt, &frames);
+  return ptts_voice_from_prompt(h, prompt.data(), frames, out);
   PTTS_CATCH
 }
 

@@ -344,6 +344,72 @@ __global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, cons
   if (tid < 64) out16[static_cast<long long>(r) * d_model + h * HD + tid] = __float2half_rn(red_s[tid]);
 }
 
+// ---------------------------------------------------------------- Mimi encoder (voice cloning from PCM)
+// First SEANetEncoder layer: Conv1d 1 -> 64, k7, causal with zero left context (reference seanet.rs:160-170 over
+// conv.rs:90-136).  One input channel is no GEMM: one thread per (sample, channel).  Writes the f32 activation (the
+// ResBlock's skip) and ELU(x) as the f16 operand of the block's k3 conv behind its two left-context rows.
+__global__ void enc_conv0_kernel(const float* __restrict__ pcm, int T, const float* __restrict__ w /*[7][64]*/,
+                                 const float* __restrict__ bias, float* __restrict__ x32 /*[T][64]*/,
+                                 __half* __restrict__ e16 /*[2+T][64]*/) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int t = static_cast<int>(idx >> 6), c = static_cast<int>(idx & 63);
+  if (t >= T) return;
+  float acc = bias[c];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int tt = t + j - 6;
+    if (tt >= 0) acc += __ldg(w + j * 64 + c) * __ldg(pcm + tt);
+  }
+  x32[static_cast<long long>(t) * 64 + c] = acc;
+  e16[static_cast<long long>(2 + t) * 64 + c] = __float2half_rn(elu1(acc));
+}
+
+// Encoder transformer attention over a whole prompt (reference attention.rs:104-283 with the causal + window mask of
+// sdpa.rs:129-171: row i sees keys (i - context, i]).  Runs once per voice, so it is plain SIMT.
+// Step 1: RoPE on q and k in place at the absolute position.  qkv f32 [P][3*512] (q | k | v thirds, heads inside).
+__global__ void enc_rope_kernel(float* __restrict__ qkv, int pos0) {
+  const int r = blockIdx.x, h = blockIdx.y, i = threadIdx.x;  // 32 threads = 32 pairs
+  float* q = qkv + static_cast<long long>(r) * (3 * 512) + h * HD;
+  float* k = q + 512;
+  float a, b;
+  rope_pair(q[2 * i], q[2 * i + 1], pos0 + r, i, a, b);
+  q[2 * i] = a; q[2 * i + 1] = b;
+  rope_pair(k[2 * i], k[2 * i + 1], pos0 + r, i, a, b);
+  k[2 * i] = a; k[2 * i + 1] = b;
+}
+// Step 2: one warp per (row, head), lane = two head dims, single pass with a running maximum over the window.
+__global__ void enc_attn_kernel(const float* __restrict__ qkv, int P, int context, __half* __restrict__ out16 /*[P][512]*/) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int r = w >> 3, h = w & 7;
+  if (r >= P) return;
+  const float* base = qkv + h * HD + 2 * lane;
+  const float2 q = *reinterpret_cast<const float2*>(base + static_cast<long long>(r) * 1536);
+  float m = -INFINITY, l = 0.f, a0 = 0.f, a1 = 0.f;
+  for (int j = max(0, r - context + 1); j <= r; ++j) {
+    const float2 kk = *reinterpret_cast<const float2*>(base + static_cast<long long>(j) * 1536 + 512);
+    const float2 vv = *reinterpret_cast<const float2*>(base + static_cast<long long>(j) * 1536 + 1024);
+    const float sc = warp_sum(q.x * kk.x + q.y * kk.y) * 0.125f;
+    const float m_new = fmaxf(m, sc);
+    const float corr = expf(m - m_new), p = expf(sc - m_new);
+    l = l * corr + p;
+    a0 = a0 * corr + p * vv.x;
+    a1 = a1 * corr + p * vv.y;
+    m = m_new;
+  }
+  *reinterpret_cast<__half2*>(out16 + static_cast<long long>(r) * 512 + h * HD + 2 * lane) = __floats2half2_rn(a0 / l, a1 / l);
+}
+// ConvDownsample1d operand (reference conv.rs:278-312, `replicate` padding on a first call, conv.rs:114-123): the f16
+// rows of the transformer output behind 16 copies of its first row.
+__global__ void enc_downsample_prep_kernel(const float* __restrict__ x /*[P][512]*/, __half* __restrict__ d16 /*[16+P][512]*/) {
+  const int row = blockIdx.x, src = row < 16 ? 0 : row - 16;
+  const float4 v = reinterpret_cast<const float4*>(x + static_cast<long long>(src) * 512)[threadIdx.x];  // 128 threads
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+  reinterpret_cast<uint2*>(d16 + static_cast<long long>(row) * 512)[threadIdx.x] = pk;
+}
+
 // ---------------------------------------------------------------- Mimi front end
 // latent de-norm (tts_model.rs:1033-1035) -> Quantizer 1x1 conv 32->512 (mimi.rs:32-36) -> depthwise
 // ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid (n, 4), block 128: one channel per

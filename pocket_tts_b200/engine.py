@@ -90,6 +90,22 @@ class Engine:
         check(_lib.lib().ptts_voice_from_prompt(self._h, _ptr(a), a.shape[0], C.byref(h)))
         return Voice(self, h)
 
+    def voice_from_pcm(self, pcm24k: np.ndarray) -> Voice:
+        """Voice cloning from 24 kHz mono PCM (ptts_voice_from_pcm): Mimi encoder + speaker projection + FlowLM prefill."""
+        a = np.ascontiguousarray(pcm24k, dtype=np.float32).reshape(-1)
+        h = C.c_void_p()
+        check(_lib.lib().ptts_voice_from_pcm(self._h, _ptr(a), a.shape[0], C.byref(h)))
+        return Voice(self, h)
+
+    def audio_prompt_from_pcm(self, pcm24k: np.ndarray) -> np.ndarray:
+        """The conditioning rows [frames, 1024] of a PCM prompt (what the reference stores as `audio_prompt`)."""
+        a = np.ascontiguousarray(pcm24k, dtype=np.float32).reshape(-1)
+        n = C.c_int32()
+        check(_lib.lib().ptts_audio_prompt_from_pcm(self._h, _ptr(a), a.shape[0], None, 0, C.byref(n)))
+        out = np.empty((n.value, 1024), np.float32)
+        check(_lib.lib().ptts_audio_prompt_from_pcm(self._h, _ptr(a), a.shape[0], _ptr(out), n.value, C.byref(n)))
+        return out
+
     def open_streams(self, voices: list[Voice], specs: list[StreamSpec]) -> np.ndarray:
         n = len(specs)
         toks = np.concatenate([np.asarray(s.tokens, dtype=np.int32) for s in specs]) if n else np.zeros(0, np.int32)

@@ -100,6 +100,22 @@ class TTSModel:
     def get_voice_state_from_prompt_tensor(self, prompt: np.ndarray) -> Voice:
         return self.engine.voice_from_prompt(np.asarray(prompt, np.float32).reshape(-1, self.dim))
 
+    def get_voice_state_from_tensor(self, audio: np.ndarray) -> Voice:
+        """tts_model.rs:504-556: audio f32 [1, 1, T] (or [T]) at the model's sample rate -> voice (Mimi encoder on the GPU)."""
+        return self.engine.voice_from_pcm(np.asarray(audio, np.float32).reshape(-1))
+
+    def get_voice_state(self, path: str | Path) -> Voice:
+        """tts_model.rs:449-466 for a mono 16-bit PCM WAV already at 24 kHz (the WAV reader variants and the resampler of
+        audio.rs are product-shell code and not built; Mimi takes one channel, mimi.channels = 1)."""
+        import wave
+        with wave.open(str(path), "rb") as w:
+            if w.getsampwidth() != 2 or w.getnchannels() != 1:
+                raise ValueError("only mono 16-bit PCM WAV is supported")
+            if w.getframerate() != self.sample_rate:
+                raise ValueError(f"WAV sample rate {w.getframerate()} != {self.sample_rate}: resample first")
+            pcm = np.frombuffer(w.readframes(w.getnframes()), "<i2").astype(np.float32) / 32768.0
+        return self.get_voice_state_from_tensor(pcm)
+
     # ---- generation (tts_model.rs:687-703, 894-1071)
     def _sync_params(self):
         if self._lsd_on_device != self.lsd_decode_steps:

@@ -259,6 +259,70 @@ def test_host_mirror_generate_stream_tokens():
     m.close()
 
 
+def _encoder_engine(g, **kw):
+    from pocket_tts_b200.engine import Engine
+    for e in _cache.values():
+        e[0].close()
+    _cache.clear()
+    w = dict(synth.make_weights(1234, layer_scale=0.01))
+    w.update(synth.make_encoder_weights(int(g["enc_seed"]), layer_scale=float(g["enc_layer_scale"])))
+    return Engine(w, max_slots=2, kv_capacity=256, **kw), w
+
+
+def test_voice_cloning_from_pcm_matches_reference(golden_dir):
+    """BASELINE configs[2] / SURVEY 8f N1: PCM -> SEANetEncoder -> encoder transformer -> ConvDownsample1d -> speaker_proj
+    on the GPU against the unmodified reference package's `_encode_audio` (tanh-GELU golden) and the oracle.  The
+    reference's own tolerance for this tensor is 2e-2 max-abs (crates/pocket-tts/tests/parity_tests.rs:60-142);
+    f16 operands stay well inside it.  Then the voice built from PCM must behave like the voice built from the same
+    conditioning rows."""
+    from oracle import ptts_oracle as O
+    from pocket_tts_b200.engine import StreamSpec
+    g = np.load(golden_dir / "enc_pcm22.npz")
+    eng, w = _encoder_engine(g)
+    pcm = synth.make_pcm(int(g["n_samples"]), seed=int(g["pcm_seed"]))
+    got = eng.audio_prompt_from_pcm(pcm)
+    want = g["tanh_audio_prompt"]
+    assert got.shape == want.shape == (22, 1024)
+    err = np.abs(got - want).max()
+    assert err <= 2e-2, f"audio_prompt max-abs {err}"
+    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert rel < 5e-3, rel
+    # ragged lengths: one sample, one frame minus one, exactly one frame
+    W = O.to_torch(w)
+    for n in (1, 1919, 1920, 1921):
+        p = synth.make_pcm(n, seed=n)
+        a = eng.audio_prompt_from_pcm(p)
+        b = O.audio_prompt_from_pcm(W, p, "tanh").numpy()
+        assert a.shape == b.shape == ((n + 1919) // 1920, 1024)
+        assert np.abs(a - b).max() <= 2e-2
+    # voice from PCM == voice from its conditioning rows (same prefill either way)
+    tok = synth.make_tokens(7, seed=3)
+    noise = synth.make_noise(3, seed=4)
+    outs = []
+    for voice in (eng.voice_from_pcm(pcm), eng.voice_from_prompt(got)):
+        s = eng.open_streams([voice], [StreamSpec(tok, 3, 0, 1e30, noise=noise)])
+        frames = [eng.step(s) for _ in range(3)]
+        outs.append((np.stack([f[0][0] for f in frames]), np.stack([f[2][0] for f in frames])))
+        eng.close_stream(int(s[0]))
+        voice.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    # too long for the single-chunk path: refused, not silently different
+    from pocket_tts_b200 import _lib
+    with pytest.raises(_lib.PttsError) as ei:
+        eng.audio_prompt_from_pcm(np.zeros(121 * 1920, np.float32))
+    assert ei.value.code == -3
+    eng.close()
+
+
+def test_voice_cloning_needs_encoder_tensors():
+    from pocket_tts_b200 import _lib
+    eng, _ = engine_for(1234, 0.01)
+    with pytest.raises(_lib.PttsError) as ei:
+        eng.voice_from_pcm(np.zeros(1920, np.float32))
+    assert ei.value.code == -4
+
+
 def test_step_ahead_matches_lockstep_and_never_emits_past_the_end():
     """PTTS_STEP_AHEAD: frame n+1 enqueued before frame n's flags are fetched.  Same frames bit for bit as the lock-step
     calls; a stream that ends at EOS (D2: frames = eos_step + frames_after_eos + 1, tts_model.rs:1055-1069) reports
