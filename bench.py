@@ -199,6 +199,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     wnp = synth.make_weights(1234)
+    wnp.update(synth.make_encoder_weights(4321))  # voice-cloning side, only used by the voice_from_pcm timing below
     eng = Engine(wnp, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3, int8_weights=args.int8)
     del wnp
     voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
@@ -333,7 +334,17 @@ def run_gpu(args):
         t64 = 1000 * (time.perf_counter() - t0)
         for x in s:
             eng.close_stream(int(x))
-        line["ttfa_ms"] = {"p50_single_stream": statistics.median(ttfa[2:]), "batch64_first_frames": t64}
+        # voice cloning from PCM (configs[2] shape: an 87-frame prompt like assets/ref.wav): Mimi encoder + speaker_proj +
+        # FlowLM prefill, host PCM in, voice handle out
+        pcm = synth.make_pcm(VOICE_ROWS * 1920, seed=3)
+        tv = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            v = eng.voice_from_pcm(pcm)
+            tv.append(1000 * (time.perf_counter() - t0))
+            v.close()
+        line["ttfa_ms"] = {"p50_single_stream": statistics.median(ttfa[2:]), "batch64_first_frames": t64,
+                           "voice_from_pcm_87_frames": statistics.median(tv[1:])}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             procs = max(1, min(cores, 32))

@@ -103,8 +103,9 @@ int32_t ptts_voice_from_prompt(ptts_engine* e, const float* audio_prompt, int32_
  * mono PCM (host f32; the WAV read and resample of tts_model.rs:449-466 stay host code).  The prompt is zero-padded to
  * whole 1920-sample frames and run through the Mimi encoder (SEANetEncoder -> encoder transformer -> ConvDownsample1d,
  * models/mimi.rs:113-141) and speaker_proj_weight; the FlowLM prefill of ptts_voice_from_prompt follows.  Needs the
- * encoder tensors in the checkpoint (PTTS_ERR_STATE otherwise); prompts of up to 120 frames (9.6 s), which the
- * reference encodes in one chunk (tts_model.rs:562-577) -- longer ones give PTTS_ERR_CAPACITY.
+ * encoder tensors in the checkpoint (PTTS_ERR_STATE otherwise); up to 1024 frames.  Prompts of more than 120 frames
+ * follow the reference's chunked encoding (tts_model.rs:528-541,562-577): one carried state, the downsample's
+ * replicate padding restarted at every chunk.
  * ptts_audio_prompt_from_pcm stops after the conditioning rows [n_rows,1024] (the tensor the reference stores under
  * `audio_prompt`); audio_prompt_out may be NULL to query n_rows only. */
 int32_t ptts_voice_from_pcm(ptts_engine* e, const float* pcm24k, int32_t n_samples, ptts_voice** out);

@@ -1173,14 +1173,17 @@ void Engine::run_step(int n) {
 
 // PCM -> audio_prompt rows (reference tts_model.rs:504-556 up to the conditioning; models/mimi.rs:113-141):
 // zero-pad to whole frames, SEANetEncoder, encoder transformer, ConvDownsample1d, speaker_proj.  One pass over the whole
-// prompt, which is what the reference does for prompts of up to 120 frames (9.6 s; adaptive_voice_prompt_chunk_frames,
-// tts_model.rs:562-577).  Every conv is the same implicit GEMM the decoder uses: a strided conv with k = 2*stride is
+// prompt (the reference's chunked encoding of long prompts carries one state, i.e. is the same streaming pass; its one
+// deviation, the downsample's restarted padding, is patched per chunk boundary below).  Every conv is the same implicit GEMM the decoder uses: a strided conv with k = 2*stride is
 // a two-tap conv over the activation viewed as rows of `stride` frames ([T/s][s*C]), so no new GEMM path exists.
 void Engine::encode_prompt(const float* pcm_host, int n_samples, std::vector<float>& prompt, int* frames_out) {
   PTTS_REQUIRE(has_encoder, PTTS_ERR_STATE, "this checkpoint has no Mimi encoder tensors (voice cloning needs mimi.encoder.*, mimi.encoder_transformer.*, mimi.downsample.*)");
   const int F = (n_samples + FRAME - 1) / FRAME;
-  PTTS_REQUIRE(n_samples >= 1 && F <= 120, PTTS_ERR_CAPACITY, "voice prompt of %d samples = %d frames (supported: 1..120 frames; the reference "
-               "encodes longer prompts in chunks with a restarted downsample padding, not built)", n_samples, F);
+  PTTS_REQUIRE(n_samples >= 1 && F <= 1024, PTTS_ERR_CAPACITY, "voice prompt of %d samples = %d frames (supported: 1..1024 frames)", n_samples, F);
+  // tts_model.rs:562-577: the reference encodes long prompts in chunks with ONE carried state, which is exactly one
+  // streaming pass -- except that its downsample restarts its replicate padding at every chunk (step = 0, tts_model.rs:540)
+  const int chunk_frames = F <= 120 ? F : F <= 600 ? 120 : F <= 1800 ? 180 : 240;
+  const int n_boundaries = (F - 1) / chunk_frames;
   ls = stream;
   const int T0 = F * FRAME, ratio[3] = {4, 5, 6};
   int Tl[4] = {T0, T0 / 4, T0 / 20, T0 / 120};
@@ -1241,6 +1244,14 @@ void Engine::encode_prompt(const float* pcm_host, int n_samples, std::vector<flo
   lat16.alloc((size_t)std::max(F, 128) * MIMI_DIM);
   e = epi_none(); e.out16 = lat16.p; e.out16_map = plain_map(MIMI_DIM);
   tag("encoder.downsample"); gemm(ActView{d16.p, 16 * MIMI_DIM, (16 + P) / 16, 1}, 1, F, 2, 128, 1, en_ds, MIMI_DIM, e, true);
+  DevBuf<__half> d16b;
+  if (n_boundaries > 0) {  // first frame of every later chunk: replicate padding instead of the previous 16 positions
+    d16b.alloc((size_t)n_boundaries * 32 * MIMI_DIM);
+    launch_k(false, enc_downsample_boundary_prep_kernel, dim3(n_boundaries, 32), 128, 0, ls, 1, (const float*)tx.p, chunk_frames, d16b.p);
+    e = epi_none(); e.out16 = lat16.p;
+    e.out16_map = stream_map(1, MIMI_DIM, (long long)chunk_frames * MIMI_DIM, (long long)chunk_frames * MIMI_DIM);
+    tag("encoder.downsample"); gemm(ActView{d16b.p, 16 * MIMI_DIM, 2, n_boundaries}, n_boundaries, 1, 2, 1, 128, en_ds, MIMI_DIM, e, true);
+  }
   prompt_d.alloc((size_t)F * D_MODEL);
   e = epi_none(); e.out32 = prompt_d.p; e.out32_map = plain_map(D_MODEL);
   tag("encoder.speaker_proj"); gemm_rows(lat16.p, F, MIMI_DIM, w_spk, D_MODEL, e);

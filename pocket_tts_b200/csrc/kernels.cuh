@@ -410,6 +410,22 @@ __global__ void enc_downsample_prep_kernel(const float* __restrict__ x /*[P][512
   reinterpret_cast<uint2*>(d16 + static_cast<long long>(row) * 512)[threadIdx.x] = pk;
 }
 
+// The same operand for the first frame of every later chunk of a long prompt: the reference encodes prompts of more
+// than 120 frames chunk by chunk and calls the downsample with step = 0 each time (tts_model.rs:540), so its replicate
+// padding restarts there.  Block (b, row): 32 operand rows per boundary b at frame (b + 1) * chunk_frames.
+__global__ void enc_downsample_boundary_prep_kernel(const float* __restrict__ x /*[P][512]*/, int chunk_frames,
+                                                    __half* __restrict__ d16 /*[n_b][32][512]*/) {
+  const int b = blockIdx.x, row = blockIdx.y;
+  const long long first = static_cast<long long>(b + 1) * chunk_frames * 16;
+  const long long src = row < 16 ? first : first + row - 16;
+  const float4 v = reinterpret_cast<const float4*>(x + src * 512)[threadIdx.x];
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+  reinterpret_cast<uint2*>(d16 + (static_cast<long long>(b) * 32 + row) * 512)[threadIdx.x] = pk;
+}
+
 // ---------------------------------------------------------------- Mimi front end
 // latent de-norm (tts_model.rs:1033-1035) -> Quantizer 1x1 conv 32->512 (mimi.rs:32-36) -> depthwise
 // ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid (n, 4), block 128: one channel per

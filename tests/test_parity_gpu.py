@@ -307,10 +307,18 @@ def test_voice_cloning_from_pcm_matches_reference(golden_dir):
         voice.close()
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
     np.testing.assert_array_equal(outs[0][1], outs[1][1])
-    # too long for the single-chunk path: refused, not silently different
+    # a prompt of more than 120 frames: the reference's chunked encoding (one carried state, the downsample's replicate
+    # padding restarted at frame 120, tts_model.rs:528-541)
+    p = synth.make_pcm(123 * 1920 - 5, seed=9)
+    a = eng.audio_prompt_from_pcm(p)
+    b = O.audio_prompt_from_pcm(W, p, "tanh").numpy()
+    assert a.shape == b.shape == (123, 1024)
+    assert np.abs(a - b).max() <= 2e-2
+    unchunked = O.audio_prompt_from_pcm(W, p, "tanh", chunk_frames=123).numpy()
+    assert np.abs(b[120] - unchunked[120]).max() > 10 * np.abs(a[120] - b[120]).max()  # the boundary frame really is the restarted one
     from pocket_tts_b200 import _lib
     with pytest.raises(_lib.PttsError) as ei:
-        eng.audio_prompt_from_pcm(np.zeros(121 * 1920, np.float32))
+        eng.audio_prompt_from_pcm(np.zeros(1025 * 1920, np.float32))
     assert ei.value.code == -3
     eng.close()
 
