@@ -323,6 +323,55 @@ def test_voice_cloning_from_pcm_matches_reference(golden_dir):
     eng.close()
 
 
+def test_cfg3_voice_cloning_batch32_lsd4(golden_dir):
+    """BASELINE configs[2] at its own shape: the voice comes from an 87-frame PCM prompt (the length of the reference's
+    assets/ref.wav) through the GPU Mimi encoder, lsd_decode_steps = 4, 32 concurrent streams.  Two of the streams are
+    teacher-forced against the oracle run end to end from the same PCM (oracle encoder -> oracle prefill -> oracle
+    frames); the others only have to finish with finite audio and the right frame counts."""
+    from oracle import ptts_oracle as O
+    from pocket_tts_b200.engine import Engine, StreamSpec
+    g = np.load(golden_dir / "enc_pcm22.npz")
+    for e in _cache.values():
+        e[0].close()
+    _cache.clear()
+    w = dict(synth.make_weights(1234, layer_scale=0.01))
+    w.update(synth.make_encoder_weights(int(g["enc_seed"]), layer_scale=float(g["enc_layer_scale"])))
+    eng = Engine(w, max_slots=32, kv_capacity=128)
+    eng.set_lsd_steps(4)
+    W = O.to_torch(w)
+    pcm = synth.make_pcm(87 * 1920 - 123, seed=17)
+    voice = eng.voice_from_pcm(pcm)
+    ov = O.voice_state_from_prompt(W, O.audio_prompt_from_pcm(W, pcm, "tanh"))
+    n, frames = 32, 3
+    checked = (0, 31)
+    specs, refs = [], {}
+    for i in range(n):
+        tok = synth.make_tokens(4 + (i * 7) % 30, seed=300 + i)
+        noise = synth.make_noise(frames, seed=400 + i)
+        specs.append(StreamSpec(tok, frames, 0, 1e30, noise=noise))
+        if i in checked:
+            refs[i] = O.generate_segment(W, ov, tok, noise, frames, 0, float("inf"), lsd_steps=4)
+    slots = eng.open_streams([voice] * n, specs)
+    lat = {i: [] for i in checked}
+    pcm_out = {i: [] for i in checked}
+    for f in range(frames):
+        if f:
+            for i in checked:
+                eng.set_feedback(int(slots[i]), refs[i]["latents"][f - 1])
+        p, fin, l, _ = eng.step(slots)
+        assert np.isfinite(p).all() and bool(fin.all()) == (f == frames - 1)
+        for i in checked:
+            lat[i].append(l[i]); pcm_out[i].append(p[i])
+    for i in checked:
+        assert np.abs(np.stack(lat[i]) - refs[i]["latents"]).max() <= LAT_TOL
+        assert snr(refs[i]["pcm"], np.stack(pcm_out[i])) >= SNR_MIN
+    assert all(eng.stream_frames(int(s))[0] == frames for s in slots)
+    for s in slots:
+        eng.close_stream(int(s))
+    voice.close()
+    eng.close()
+
+
 def test_voice_cloning_needs_encoder_tensors():
     from pocket_tts_b200 import _lib
     eng, _ = engine_for(1234, 0.01)
