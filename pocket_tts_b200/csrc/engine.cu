@@ -1063,7 +1063,10 @@ void Engine::step_part_b(int n, bool marks) {
   tag("seanet.res3a"); gemm(ActView{e2.p, 256, 98, NB}, n, 96, 3, 96, 1, s_r3a, 128, e);
   e = epi_none(); e.bias = sb_r3b.p; e.res = x2.p; e.res_map = plain_map(256);
   e.out16 = a3.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 256, 97 * 256, 256);
-  tag("seanet.res3b"); gemm_rows(h3.p, n * 96, 128, s_r3b, 256, e);
+  // the k1 convs run per stream (T rows each) rather than as one flat [n*T] matrix: the epilogue's affine fast path
+  // needs the output map's stream structure to match the GEMM's, and the flat form silently took the row-by-row path
+  // with a division per row (res9b: 52 us in the step against 23 us for the same GEMM with plain maps)
+  tag("seanet.res3b"); gemm(ActView{h3.p, 128, 96, NB}, n, 96, 1, 96, 1, s_r3b, 256, e);
   e = epi_none(); e.bias = sb_ct5.p; e.out32 = x5.p; e.out32_map = stream_map(96, 640, 480 * 128, 0);
   e.out16 = e5.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 640, 482 * 128, 2 * 128);
   tag("seanet.convtr5"); gemm(ActView{a3.p, 256, 97, NB}, n, 96, 2, 96, 1, s_ct5, 640, e);
@@ -1071,7 +1074,7 @@ void Engine::step_part_b(int n, bool marks) {
   tag("seanet.res6a"); gemm(ActView{e5.p, 128, 482, NB}, n, 480, 3, 120, 1, s_r6a, 64, e);
   e = epi_none(); e.bias = sb_r6b.p; e.res = x5.p; e.res_map = plain_map(128);
   e.out16 = a6.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 128, 481 * 128, 128);
-  tag("seanet.res6b"); gemm_rows(h6.p, n * 480, 64, s_r6b, 128, e);
+  tag("seanet.res6b"); gemm(ActView{h6.p, 64, 480, NB}, n, 480, 1, 120, 1, s_r6b, 128, e);
   e = epi_none(); e.bias = sb_ct8.p; e.out32 = x8.p; e.out32_map = stream_map(480, 256, 1920 * 64, 0);
   e.out16 = e8.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 256, 1922 * 64, 2 * 64);
   tag("seanet.convtr8"); gemm(ActView{a6.p, 128, 481, NB}, n, 480, 2, 120, 1, s_ct8, 256, e);
@@ -1079,7 +1082,7 @@ void Engine::step_part_b(int n, bool marks) {
   tag("seanet.res9a"); gemm(ActView{e8.p, 64, 1922, NB}, n, 1920, 3, 128, 1, s_r9a, 64, e);
   e = epi_none(); e.bias = sb_r9b.p; e.res = x8.p; e.res_map = plain_map(64);
   e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(1920, 64, 1922 * 64, 128);
-  tag("seanet.res9b"); gemm_rows(h9.p, n * 1920, 64, s_r9b, 64, e);
+  tag("seanet.res9b"); gemm(ActView{h9.p, 64, 1920, NB}, n, 1920, 1, 128, 1, s_r9b, 64, e);
   { ProfScope ps(*this, "seanet.final_conv", (double)n * (1922.0 * 128 + 1920 * 4), 2.0 * n * 1920 * 192);
     launch_k(use_pdl, seanet_final_conv_kernel, dim3((FRAME + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, pcm.p); }
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
