@@ -103,7 +103,8 @@ struct Engine {
   bool diag_times = false;      // PTTS_DIAG_TIMES=1: event stamps around both paths of the last step, printed by sync
   cudaEvent_t ev_t[4] = {};
   int trig_a = 1, trig_b = 1;   // GemmParams::pdl_trigger per step stream (PTTS_TRIG_A / PTTS_TRIG_B)
-  int split_cta_cap = 48;   // a split-K GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
+  int split_cta_cap = 48;   // a split-K decode (swap-AB) GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
+  int split_cta_cap_b = 48; // the same for the activation-as-M GEMMs of the codec half (PTTS_MAX_CTAS_B)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
@@ -648,6 +649,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     PTTS_CUDA(cudaStreamCreateWithPriority(&stream_b, cudaStreamNonBlocking, lo));
     if (const char* v = std::getenv("PTTS_B_SMS")) persistent_ctas = std::max(8, std::atoi(v));
     if (const char* v = std::getenv("PTTS_MAX_CTAS")) split_cta_cap = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_MAX_CTAS_B")) split_cta_cap_b = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_TRIG_A")) trig_a = std::atoi(v);
     if (const char* v = std::getenv("PTTS_TRIG_B")) trig_b = std::atoi(v);
   }
@@ -791,7 +793,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   // power-of-two cluster sizes only (they pack into a GPC), and the whole grid must fit one wave with slack for
   // cluster placement: 24 tiles x 4 (96 CTAs) beats 24 x 6 (144 CTAs, measured 8.5 vs 15 us)
   if (!persistent && total_kb >= 4) {
-    while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= split_cta_cap && splits * 2 <= total_kb / 2) splits *= 2;
+    const int cap = swap ? split_cta_cap : split_cta_cap_b;
+    while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= cap && splits * 2 <= total_kb / 2) splits *= 2;
   }
   const LnSpec lnreq = next_ln;
   next_ln.set = false;
