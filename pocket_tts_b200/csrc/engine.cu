@@ -180,8 +180,13 @@ struct Engine {
   DevBuf<__half> mh16, mattn16, mffn16;
   DevBuf<__half> tr16, a0, e2, h3, a3, e5, h6, a6, e8, h9, a9;
   DevBuf<float> x2, x5, x8, pcm;
-  DevBuf<unsigned char> finished_dev;
-  DevBuf<float> latent_out, logit_out;
+  // per-step host-visible results in ONE buffer ([NB][32] latents | [NB] EOS logits | [NB] finished bytes) so that a
+  // step's flags reach the host with one D2H copy on the language-model stream instead of three
+  DevBuf<SeqDesc> row_desc;    // [NB] per batch row: KV descriptor + cursor of its stream, rebuilt by step_begin_kernel
+  DevBuf<unsigned char> step_out;
+  struct { float* p; } latent_out, logit_out;
+  struct { unsigned char* p; } finished_dev;
+  size_t step_out_bytes() const { return (size_t)NB * (LDIM * 4 + 4 + 1); }
   ConvSegs segs{};
   // ---- prefill scratch
   DevBuf<float> px32, pqkv32, pqrot;
@@ -233,9 +238,7 @@ struct Engine {
 Engine::~Engine() {
   for (int i = 0; i < NT; ++i) {
     if (pin_pcm[i]) cudaFreeHost(pin_pcm[i]);
-    if (pin_fin[i]) cudaFreeHost(pin_fin[i]);
-    if (pin_lat[i]) cudaFreeHost(pin_lat[i]);
-    if (pin_logit[i]) cudaFreeHost(pin_logit[i]);
+    if (pin_lat[i]) cudaFreeHost(pin_lat[i]);  // pin_logit / pin_fin point into it
     if (ev_flags[i]) cudaEventDestroy(ev_flags[i]);
     if (ev_pcm[i]) cudaEventDestroy(ev_pcm[i]);
   }
@@ -704,7 +707,12 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   a3.alloc((size_t)NB * 97 * 256); x5.alloc((size_t)NB * 480 * 128); e5.alloc((size_t)NB * 482 * 128);
   h6.alloc((size_t)NB * 480 * 64); a6.alloc((size_t)NB * 481 * 128); x8.alloc((size_t)NB * 1920 * 64);
   e8.alloc((size_t)NB * 1922 * 64); h9.alloc((size_t)NB * 1920 * 64); a9.alloc((size_t)NB * 1922 * 64);
-  pcm.alloc((size_t)NB * FRAME); finished_dev.alloc(NB); latent_out.alloc((size_t)NB * LDIM); logit_out.alloc(NB);
+  pcm.alloc((size_t)NB * FRAME);
+  step_out.alloc(step_out_bytes());
+  row_desc.alloc(NB);
+  latent_out.p = reinterpret_cast<float*>(step_out.p);
+  logit_out.p = latent_out.p + (size_t)NB * LDIM;
+  finished_dev.p = reinterpret_cast<unsigned char*>(logit_out.p + NB);
   segs.s[0] = ConvSeg{tr16.p, st_tr.p, 6, 16, 512, 0};
   segs.s[1] = ConvSeg{a0.p, st_a0.p, 1, 16, 512, 0};
   segs.s[2] = ConvSeg{e2.p, st_e2.p, 2, 96, 256, 0};
@@ -719,9 +727,9 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   prow_seq.alloc(PR); prow_pos.alloc(PR); ptokens.alloc(PR);
   for (int i = 0; i < NT; ++i) {
     PTTS_CUDA(cudaMallocHost(&pin_pcm[i], (size_t)NB * FRAME * 4));
-    PTTS_CUDA(cudaMallocHost(&pin_fin[i], NB));
-    PTTS_CUDA(cudaMallocHost(&pin_lat[i], (size_t)NB * LDIM * 4));
-    PTTS_CUDA(cudaMallocHost(&pin_logit[i], (size_t)NB * 4));
+    PTTS_CUDA(cudaMallocHost(&pin_lat[i], step_out_bytes()));  // same layout as step_out
+    pin_logit[i] = pin_lat[i] + (size_t)NB * LDIM;
+    pin_fin[i] = reinterpret_cast<unsigned char*>(pin_logit[i] + NB);
     PTTS_CUDA(cudaEventCreateWithFlags(&ev_flags[i], cudaEventDisableTiming));
     PTTS_CUDA(cudaEventCreateWithFlags(&ev_pcm[i], cudaEventDisableTiming));
   }
@@ -889,7 +897,7 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
         launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
       { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0, "flowlm_attn_decode_kernel");
-        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qkv, rseq, seqs.p, own_len.p, l, N_HEADS, attn); }
+        launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qkv, (const SeqDesc*)row_desc.p, l, N_HEADS, attn); }
     }
     // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue; h = LN2(x)
     e = epi_none();
@@ -963,7 +971,8 @@ void Engine::flow_head_fused(int n) {
 void Engine::step_part_a(int n, bool marks) {
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
   { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
-    launch_k(use_pdl, step_begin_kernel, n, 64, 0, ls, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p); }
+    launch_k(use_pdl, step_begin_kernel, n, 64, 0, ls, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p, (const SeqDesc*)seqs.p,
+             (const int*)own_len.p, row_desc.p); }
   GemmEpi e = epi_none();
   e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
   ln_after_next_gemm("flowlm.layernorm", x32.p, n, D_MODEL, ln1_w[0].p, ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, h16.p, D_MODEL);
@@ -1496,9 +1505,7 @@ static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, int 
   e.upload_rows(slot_ids, n);
   e.run_step(n);
   const int par = (int)(id % Engine::NT);
-  PTTS_CUDA(cudaMemcpyAsync(e.pin_fin[par], e.finished_dev.p, n, cudaMemcpyDeviceToHost, e.stream));
-  PTTS_CUDA(cudaMemcpyAsync(e.pin_lat[par], e.latent_out.p, (size_t)n * LDIM * 4, cudaMemcpyDeviceToHost, e.stream));
-  PTTS_CUDA(cudaMemcpyAsync(e.pin_logit[par], e.logit_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.pin_lat[par], e.step_out.p, e.step_out_bytes(), cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaEventRecord(e.ev_flags[par], e.stream));
   if (want_pcm) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm[par], e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream_b));
   PTTS_CUDA(cudaEventRecord(e.ev_pcm[par], e.stream_b));

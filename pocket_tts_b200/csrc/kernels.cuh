@@ -268,9 +268,9 @@ __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int h
 // FlowLM decode attention, one new row per stream (reference modules/attention.rs:104-231 with t = 1):
 // RoPE(q,k) at the absolute position, append K,V at the cursor, causal SDPA over prefix + own rows, all fused.
 // grid (n, heads), block ATTN_THREADS.
-__global__ void __launch_bounds__(ATTN_THREADS, 7) flowlm_attn_decode_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
-                                          const SeqDesc* __restrict__ seqs, const int* __restrict__ own_len, int layer,
-                                          int n_heads, __half* __restrict__ out16) {
+__global__ void __launch_bounds__(ATTN_THREADS, 7) flowlm_attn_decode_kernel(const float* __restrict__ qkv,
+                                          const SeqDesc* __restrict__ row_desc /*[n], cursor in .pad (step_begin_kernel)*/,
+                                          int layer, int n_heads, __half* __restrict__ out16) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sm[64 + 64 + 4 * 66];
@@ -278,10 +278,8 @@ __global__ void __launch_bounds__(ATTN_THREADS, 7) flowlm_attn_decode_kernel(con
   float* red_s = sm + 64;
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
   const int d_model = n_heads * HD;
-  const int seq = row_seq[b];
-  const SeqDesc sd = seqs[seq];
-  const int lo = own_len[seq];
-  const int pos = sd.prefix_len + lo;
+  const SeqDesc sd = row_desc[b];
+  const int pos = sd.prefix_len + sd.pad;
   const float* row = qkv + static_cast<long long>(b) * 3 * d_model;
   if (tid < 32) {
     float qr, qi, kr, ki;
@@ -693,13 +691,22 @@ __device__ __forceinline__ float counter_normal(unsigned long long seed, int fra
 
 // Gathers the AR feedback latent (BOS at frame 0, reference tts_model.rs:971,1065) as the f16 operand of
 // input_linear (K padded 32 -> 64) and the flow head's starting point x_0 (flow_lm.rs:148-153).
+// Also flattens the row -> slot -> (KV descriptor, cursor) chain into one 32-byte record per batch row (the cursor rides in
+// SeqDesc::pad): the six attention launches of the step then start from one load instead of two dependent round trips.
 __global__ void step_begin_kernel(const int* __restrict__ row_seq, const StreamCtl* __restrict__ ctl,
                                   const float* __restrict__ feedback /*[slots,32]*/, __half* __restrict__ lat16 /*[n,64]*/,
-                                  float* __restrict__ z32 /*[n,32]*/, __half* __restrict__ z16 /*[n,64]*/) {
+                                  float* __restrict__ z32 /*[n,32]*/, __half* __restrict__ z16 /*[n,64]*/,
+                                  const SeqDesc* __restrict__ seqs, const int* __restrict__ own_len,
+                                  SeqDesc* __restrict__ row_desc /*[n]*/) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x, k = threadIdx.x;  // 64 threads
   const int slot = row_seq[b];
+  if (k == 63) {
+    SeqDesc d = seqs[slot];
+    d.pad = own_len[slot];
+    row_desc[b] = d;
+  }
   const StreamCtl c = ctl[slot];
   float lat = 0.f, z = 0.f;
   if (k < LDIM) {
