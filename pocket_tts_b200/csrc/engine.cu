@@ -105,6 +105,8 @@ struct Engine {
   int trig_a = 1, trig_b = 1;   // GemmParams::pdl_trigger per step stream (PTTS_TRIG_A / PTTS_TRIG_B)
   int split_cta_cap = 48;   // a split-K decode (swap-AB) GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
   int split_cta_cap_b = 48; // the same for the activation-as-M GEMMs of the codec half (PTTS_MAX_CTAS_B)
+  int split_cap_override = 0;  // one-shot cap for the next GEMM
+  int lin1_ctas = 48;          // linear1 (32 feature tiles): 64 lets it split in two and keep its K slice resident (PTTS_LIN1_CTAS)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
@@ -653,6 +655,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     if (const char* v = std::getenv("PTTS_B_SMS")) persistent_ctas = std::max(8, std::atoi(v));
     if (const char* v = std::getenv("PTTS_MAX_CTAS")) split_cta_cap = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_MAX_CTAS_B")) split_cta_cap_b = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_LIN1_CTAS")) lin1_ctas = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_TRIG_A")) trig_a = std::atoi(v);
     if (const char* v = std::getenv("PTTS_TRIG_B")) trig_b = std::atoi(v);
   }
@@ -801,7 +804,9 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   // power-of-two cluster sizes only (they pack into a GPC), and the whole grid must fit one wave with slack for
   // cluster placement: 24 tiles x 4 (96 CTAs) beats 24 x 6 (144 CTAs, measured 8.5 vs 15 us)
   if (!persistent && total_kb >= 4) {
-    const int cap = swap ? split_cta_cap : split_cta_cap_b;
+    int cap = swap ? split_cta_cap : split_cta_cap_b;
+    if (split_cap_override > 0) cap = split_cap_override;
+    split_cap_override = 0;
     while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= cap && splits * 2 <= total_kb / 2) splits *= 2;
   }
   const LnSpec lnreq = next_ln;
@@ -906,6 +911,7 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
     tag(is_prefill ? "prefill.out_proj" : "flowlm.out_proj"); gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = ffn; e.out16_map = plain_map(D_FFN);
+    if (!is_prefill) split_cap_override = lin1_ctas;
     tag(is_prefill ? "prefill.linear1" : "flowlm.linear1"); gemm_rows(h, rows, D_MODEL, w_lin1[l], D_FFN, e);
     e = epi_none();
     e.out32 = x; e.out32_map = plain_map(D_MODEL); e.res = x; e.res_map = plain_map(D_MODEL);
