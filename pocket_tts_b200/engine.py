@@ -100,11 +100,11 @@ class Engine:
     def audio_prompt_from_pcm(self, pcm24k: np.ndarray) -> np.ndarray:
         """The conditioning rows [frames, 1024] of a PCM prompt (what the reference stores as `audio_prompt`)."""
         a = np.ascontiguousarray(pcm24k, dtype=np.float32).reshape(-1)
+        rows = (a.shape[0] + FRAME - 1) // FRAME   # the prompt is zero-padded to whole frames (tts_model.rs:514-527)
+        out = np.empty((max(rows, 1), 1024), np.float32)
         n = C.c_int32()
-        check(_lib.lib().ptts_audio_prompt_from_pcm(self._h, _ptr(a), a.shape[0], None, 0, C.byref(n)))
-        out = np.empty((n.value, 1024), np.float32)
-        check(_lib.lib().ptts_audio_prompt_from_pcm(self._h, _ptr(a), a.shape[0], _ptr(out), n.value, C.byref(n)))
-        return out
+        check(_lib.lib().ptts_audio_prompt_from_pcm(self._h, _ptr(a), a.shape[0], _ptr(out), out.shape[0], C.byref(n)))
+        return out[:n.value]
 
     def open_streams(self, voices: list[Voice], specs: list[StreamSpec]) -> np.ndarray:
         n = len(specs)
