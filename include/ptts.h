@@ -182,7 +182,7 @@ int32_t ptts_profile_overhead(ptts_engine* e, float* ms_out);
 /* Isolated kernel entry points (tests/test_kernels_gpu.py): D[r,f] = sum_k A[r,k] * W[f,k] on
  * host f32 buffers, run through the production GEMM (operands converted to f16).  mode 0 lets the
  * engine choose the tiling, 1 forces activation-as-M, 2 forces weight-as-M (swap-AB);
- * split_k > 1 exercises the atomic split-K epilogue. */
+ * split_k > 1 exercises the cluster split-K epilogue (partials summed over DSMEM in rank order, no atomics). */
 int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const float* bias, float* d, int32_t rows,
                        int32_t feats, int32_t k, int32_t mode, int32_t split_k, int32_t act, int32_t use_simt);
 /* The int8 weight path of the decode (swap-AB) GEMM: w is quantised per tensor with the reference's scheme

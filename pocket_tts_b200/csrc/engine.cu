@@ -831,7 +831,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     p.tmem_cols = pow2_at_least(p.BN);
     // the epilogue re-uses the stage buffers for its staged f32 tile
     while ((size_t)p.stages * stage_bytes < tile_bytes) ++p.stages;
-    // int8 storage: the weight tile arrives as bytes and warps 2-5 expand it to the f16 operand in shared memory
+    // int8 storage: the weight tile arrives as bytes and warps 2-9 expand it to the f16 operand in shared memory
     // (reserved[7] = 1: test hook, stream the f16 copy of the codes instead -- results must be bit-identical)
     if (swap && w.q8.p && !cfg.debug_gemm && cfg.reserved[7] == 0) p.epi.reserved |= GEMM_F_W_INT8;
     // stages | barriers | alignment slack; stays below the 196 KB shared-memory carve-out (a few KB more would select the

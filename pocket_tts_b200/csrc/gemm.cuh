@@ -23,7 +23,8 @@
 // in rank order (bit-reproducible) and stores only those rows.  No workspace, no atomics, and the epilogue
 // work is spread over the whole cluster.
 //
-// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + tcgen05.mma issuer, warps 2-5 TMEM -> smem staging,
+// Warp roles: warp 0 TMA producer, warp 1 TMEM owner + tcgen05.mma issuer, warps 2-5 TMEM -> smem staging (warps 2-9 first
+// expand int8 weight tiles when the weights are stored as bytes),
 // then all 12 warps store the tile.  Launched with programmatic dependent launch: everything before
 // griddepcontrol.wait (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail.
 #pragma once
@@ -504,7 +505,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   uint64_t* wfull_bar = tmem_full_bar + 3;      // int8 storage: raw weight bytes landed (per stage)
-  uint64_t* conv_bar = wfull_bar + p.stages;    // int8 storage: f16 operand written by the four converter warps
+  uint64_t* conv_bar = wfull_bar + p.stages;    // int8 storage: f16 operand written by the eight converter warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
