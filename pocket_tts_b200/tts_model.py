@@ -69,13 +69,33 @@ def read_safetensors(path: str | Path) -> dict[str, np.ndarray]:
     return out
 
 
+def sample_clamped_noise(frames: int, temp: float, limit: float, seed: int = 0, ldim: int = LDIM) -> np.ndarray:
+    """models/flow_lm.rs:39-65 with `noise_clamp = Some(limit)`: i.i.d. N(0, temp) (std = sqrt(temp)) by rejection
+    sampling, every value kept only if |v| <= limit.  The reference draws from an unseedable thread RNG; here the draw
+    is seeded and handed to the engine as the stream's injected noise [frames, ldim]."""
+    if temp <= 0.0:
+        return np.zeros((frames, ldim), np.float32)
+    if limit <= 0.0:
+        raise ValueError("noise_clamp must be positive")
+    rng = np.random.default_rng(seed)
+    std = np.float32(np.sqrt(np.float32(temp)))
+    out = np.empty(frames * ldim, np.float32)
+    have = 0
+    while have < out.size:
+        v = (rng.standard_normal(max(out.size - have, 64), dtype=np.float32) * std).astype(np.float32)
+        v = v[np.abs(v) <= limit][: out.size - have]
+        out[have:have + v.size] = v
+        have += v.size
+    return out.reshape(frames, ldim)
+
+
 class TTSModel:
     def __init__(self, weights: dict[str, np.ndarray], temp: float = DEFAULT_TEMPERATURE,
                  lsd_decode_steps: int = DEFAULT_LSD_DECODE_STEPS, eos_threshold: float = DEFAULT_EOS_THRESHOLD,
                  device: int = 0, max_slots: int = 64, kv_capacity: int = 1024,
                  tokenizer: Callable[[str], list[int]] | None = None):
         self.temp, self.lsd_decode_steps, self.eos_threshold = temp, lsd_decode_steps, eos_threshold
-        self.noise_clamp = None  # reference field (tts_model.rs:34); rejection sampling is not on the device path
+        self.noise_clamp = None  # reference field (tts_model.rs:34): host-side rejection sampling, injected as the stream's noise
         self.sample_rate, self.dim, self.ldim = SAMPLE_RATE, 1024, LDIM
         self.tokenizer = tokenizer
         self.engine = Engine(weights, device=device, max_slots=max_slots, kv_capacity=kv_capacity)
@@ -131,6 +151,8 @@ class TTSModel:
                                seed: int = 0) -> Iterator[np.ndarray]:
         """One segment (generate_stream_segment, tts_model.rs:935-1071): yields f32 [1,1,1920] per frame."""
         self._sync_params()
+        if noise is None and self.noise_clamp is not None:
+            noise = sample_clamped_noise(max_gen_len, self.temp, float(self.noise_clamp), seed, self.ldim)
         spec = StreamSpec(np.asarray(tokens, np.int32), max_gen_len, frames_after_eos, self.eos_threshold, self.temp, seed, noise)
         (slot,) = self.engine.open_streams([voice], [spec])
         ids = np.array([slot], np.int32)

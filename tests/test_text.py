@@ -202,3 +202,20 @@ def test_pcm_i16_and_wav():
     assert A.stream_chunk_bytes(a[None, :, :1920]) == A.pcm_i16_le_bytes(a[:, :1920])
     np.testing.assert_allclose(np.abs(A.normalize_peak(a)).max(), 1.0, rtol=1e-6)
     assert not A.normalize_peak(np.zeros((1, 4), np.float32)).any()
+
+
+def test_noise_clamp_rejection_sampling():
+    """models/flow_lm.rs:39-65: truncated normal by rejection; std = sqrt(temp); temp = 0 gives exact zeros."""
+    from pocket_tts_b200.tts_model import sample_clamped_noise
+    z = sample_clamped_noise(200, 0.7, 1.0, seed=3)
+    assert z.shape == (200, 32) and z.dtype == np.float32
+    assert np.abs(z).max() <= 1.0
+    # N(0, 0.7) truncated at |v| <= 1 has std 0.5239 (scipy.stats.truncnorm)
+    assert abs(z.std() - 0.5239) < 0.01 and abs(z.mean()) < 0.02
+    np.testing.assert_array_equal(z, sample_clamped_noise(200, 0.7, 1.0, seed=3))
+    assert not np.array_equal(z, sample_clamped_noise(200, 0.7, 1.0, seed=4))
+    wide = sample_clamped_noise(200, 0.7, 10.0, seed=3)
+    assert abs(wide.std() - np.sqrt(0.7)) < 0.01          # an inactive clamp leaves N(0, temp)
+    assert not sample_clamped_noise(5, 0.0, 1.0).any()
+    with pytest.raises(ValueError):
+        sample_clamped_noise(5, 0.7, 0.0)
