@@ -46,3 +46,96 @@ def test_two_rank_aggregate_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert frames == 129 * 125 and ms == 11.0
+
+
+class _FakeEngine:
+    """Host-only stand-in for the engine: a stream's frame f is the constant (spec id * 1000 + f); a stream finishes
+    after spec.max_gen_len frames.  Same call protocol as pocket_tts_b200.engine.Engine (open / begin / flags / pcm /
+    close), with the protocol's ordering rules asserted."""
+
+    def __init__(self, max_batch):
+        import numpy as np
+        self.np, self.max_batch = np, max_batch
+        self.free = list(range(max_batch))
+        self.live = {}       # slot -> [spec, frames done]
+        self.tickets = {}    # ticket -> (slots, per-row frame index, flags fetched)
+        self.next = 0
+        self.batch_sizes = []
+
+    def open_streams(self, voices, specs):
+        assert len(voices) == len(specs) <= len(self.free)
+        out = []
+        for s in specs:
+            slot = self.free.pop(0)
+            self.live[slot] = [s, 0]
+            out.append(slot)
+        return self.np.asarray(out, self.np.int32)
+
+    def step_begin(self, slots, want_pcm=True, ahead=False):
+        assert all(int(s) in self.live for s in slots) and len(set(map(int, slots))) == len(slots)
+        assert all(t[2] for t in self.tickets.values()), "flags of the previous step must be fetched first"
+        self.batch_sizes.append(len(slots))
+        rows = []
+        for s in slots:
+            st = self.live[int(s)]
+            rows.append(st[1])
+            st[1] += 1
+        self.tickets[self.next] = ([int(s) for s in slots], rows, False)
+        self.next += 1
+        return self.next - 1
+
+    def step_flags(self, t):
+        slots, rows, _ = self.tickets[t]
+        self.tickets[t] = (slots, rows, True)
+        fin = self.np.array([self.live[s][1] >= self.live[s][0].max_gen_len for s in slots])
+        return fin, None, None
+
+    def step_pcm(self, t, want=True):
+        slots, rows, fetched = self.tickets.pop(t)
+        assert fetched
+        return self.np.stack([self.np.full(4, self.live_or_closed[s] * 1000 + f, self.np.float32) for s, f in zip(slots, rows)])
+
+    def close_stream(self, slot):
+        assert not any(slot in t[0] for t in self.tickets.values()), "a closed slot still has an undrained step"
+        self.free.append(slot)
+        del self.live[slot]
+
+    @property
+    def live_or_closed(self):
+        return {s: v[0].tokens for s, v in self.live.items()}
+
+
+def test_continuous_batching_host_logic_without_gpu():
+    """BASELINE configs[4] host logic (tts_model.BatchScheduler): chunks of one request in order, pauses as exact zero
+    runs (pause.rs:183-185), different requests share the batch, never more than max_batch rows, slots recycled."""
+    import numpy as np
+    from types import SimpleNamespace
+    from pocket_tts_b200.tts_model import BatchScheduler
+    eng = _FakeEngine(max_batch=3)
+
+    def chunk(cid, frames):
+        return ("text", SimpleNamespace(tokens=cid, max_gen_len=frames))
+
+    requests = [
+        [chunk(1, 2), ("pause", 500), chunk(2, 3)],
+        [chunk(3, 1)],
+        [("pause", 100), chunk(4, 4), chunk(5, 1), ("pause", 250)],
+        [chunk(6, 2)],
+        [],
+    ]
+    # the fake engine's frame is 4 samples long; silence_samples is in real samples
+    out = BatchScheduler(eng, voice=None, max_batch=3).run(requests)
+
+    def frames(cid, n):
+        return np.concatenate([np.full(4, cid * 1000 + f, np.float32) for f in range(n)])
+
+    want = [
+        np.concatenate([frames(1, 2), np.zeros(12000, np.float32), frames(2, 3)]),
+        frames(3, 1),
+        np.concatenate([np.zeros(2400, np.float32), frames(4, 4), frames(5, 1), np.zeros(6000, np.float32)]),
+        frames(6, 2),
+        np.zeros(0, np.float32),
+    ]
+    for got, w in zip(out, want):
+        np.testing.assert_array_equal(got, w)
+    assert max(eng.batch_sizes) <= 3 and sorted(eng.free) == [0, 1, 2] and not eng.live and not eng.tickets
