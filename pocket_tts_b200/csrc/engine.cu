@@ -155,6 +155,7 @@ struct Engine {
   DevBuf<float> enb_r1[3], enb_r3[3], enb_down[3], enb_c11;
   Weight16 et_inproj[MIMI_LAYERS], et_outproj[MIMI_LAYERS], et_lin1[MIMI_LAYERS], et_lin2[MIMI_LAYERS], en_ds, w_spk;
   DevBuf<float> et_ln1_w[MIMI_LAYERS], et_ln1_b[MIMI_LAYERS], et_ln2_w[MIMI_LAYERS], et_ln2_b[MIMI_LAYERS], et_ls1[MIMI_LAYERS], et_ls2[MIMI_LAYERS];
+  DevBuf<unsigned char> enc_arena;   // encoder scratch, grown on demand, reused by every voice_from_pcm call
   void load_encoder_weights();
   void encode_prompt(const float* pcm_host, int n_samples, std::vector<float>& prompt, int* frames);
   Weight16 s_conv0, s_ct2, s_r3a, s_r3b, s_ct5, s_r6a, s_r6b, s_ct8, s_r9a, s_r9b;
@@ -1209,75 +1210,89 @@ void Engine::encode_prompt(const float* pcm_host, int n_samples, std::vector<flo
   const int T0 = F * FRAME, ratio[3] = {4, 5, 6};
   int Tl[4] = {T0, T0 / 4, T0 / 20, T0 / 120};
   const int P = Tl[3];
-  DevBuf<float> pcm_d, xcur, xnext, tx, tqkv, prompt_d;
-  DevBuf<__half> ecur, enext, hbuf, esbuf, th16, ta16, tffn, d16, lat16;
-  pcm_d.alloc(T0);  // zero-filled: the tail past n_samples is the reference's end padding (tts_model.rs:514-527)
-  PTTS_CUDA(cudaMemcpyAsync(pcm_d.p, pcm_host, (size_t)n_samples * 4, cudaMemcpyHostToDevice, ls));
-  xcur.alloc((size_t)T0 * 64);
-  ecur.alloc((size_t)(2 + T0) * 64);
-  launch_k(false, enc_conv0_kernel, (unsigned)(((long long)T0 * 64 + 255) / 256), 256, 0, ls, 1, pcm_d.p, T0, en_conv0_w.p, en_conv0_b.p, xcur.p, ecur.p);
+  // Scratch comes from one arena that only ever grows (about 2.4 MB per prompt frame): allocating and freeing a dozen
+  // buffers of tens of MB per call made the same 87-frame prompt take anywhere from 12 to 800 ms.
+  const size_t need = (size_t)F * 2400000 + (8u << 20);
+  if (enc_arena.n < need) { PTTS_CUDA(cudaStreamSynchronize(ls)); enc_arena.alloc(need); }
+  PTTS_CUDA(cudaMemsetAsync(enc_arena.p, 0, need, ls));  // zero left-context rows, zero end padding of the prompt
+  size_t arena_off = 0;
+  auto carve = [&](size_t bytes) {
+    void* ptr = enc_arena.p + arena_off;
+    arena_off += (bytes + 1023) & ~(size_t)1023;
+    PTTS_REQUIRE(arena_off <= need, PTTS_ERR_STATE, "encoder scratch arena too small (%zu > %zu)", arena_off, need);
+    return ptr;
+  };
+  auto f32buf = [&](size_t n) { return static_cast<float*>(carve(n * 4)); };
+  auto f16buf = [&](size_t n) { return static_cast<__half*>(carve(n * 2)); };
+  float* pcm_d = f32buf(T0);  // the tail past n_samples stays zero: the reference's end padding (tts_model.rs:514-527)
+  PTTS_CUDA(cudaMemcpyAsync(pcm_d, pcm_host, (size_t)n_samples * 4, cudaMemcpyHostToDevice, ls));
+  float* xcur = f32buf((size_t)T0 * 64);
+  __half* ecur = f16buf((size_t)(2 + T0) * 64);
+  launch_k(false, enc_conv0_kernel, (unsigned)(((long long)T0 * 64 + 255) / 256), 256, 0, ls, 1, (const float*)pcm_d, T0, (const float*)en_conv0_w.p,
+           (const float*)en_conv0_b.p, xcur, ecur);
   GemmEpi e;
   for (int l = 0; l < 3; ++l) {
     const int C = 64 << l, Hp = std::max(C / 2, 64), T = Tl[l], s = ratio[l], Tn = Tl[l + 1];
     // ResBlock (seanet.rs:82-88): v = conv_k1(ELU(conv_k3(ELU(x)))); x += v; then ELU in front of the strided conv
-    hbuf.alloc((size_t)T * Hp);
-    e = epi_none(); e.bias = enb_r1[l].p; e.out16 = hbuf.p; e.act16 = ACT_ELU; e.out16_map = plain_map(Hp);
-    tag("encoder.res_a"); gemm(ActView{ecur.p, C, 2 + T, 1}, 1, T, 3, 128, 1, en_r1[l], Hp, e);
-    esbuf.alloc((size_t)(s + T) * C);  // `s` zero rows of left context in front (k - stride = stride)
-    e = epi_none(); e.bias = enb_r3[l].p; e.res = xcur.p; e.res_map = plain_map(C);
-    e.out16 = esbuf.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T, C, (long long)(s + T) * C, (long long)s * C);
-    tag("encoder.res_b"); gemm_rows(hbuf.p, T, Hp, en_r3[l], C, e);
+    __half* hbuf = f16buf((size_t)T * Hp);
+    e = epi_none(); e.bias = enb_r1[l].p; e.out16 = hbuf; e.act16 = ACT_ELU; e.out16_map = plain_map(Hp);
+    tag("encoder.res_a"); gemm(ActView{ecur, C, 2 + T, 1}, 1, T, 3, 128, 1, en_r1[l], Hp, e);
+    __half* esbuf = f16buf((size_t)(s + T) * C);  // `s` zero rows of left context in front (k - stride = stride)
+    e = epi_none(); e.bias = enb_r3[l].p; e.res = xcur; e.res_map = plain_map(C);
+    e.out16 = esbuf; e.act16 = ACT_ELU; e.out16_map = stream_map(T, C, (long long)(s + T) * C, (long long)s * C);
+    tag("encoder.res_b"); gemm_rows(hbuf, T, Hp, en_r3[l], C, e);
     // strided conv C -> 2C, k = 2s: two taps over [ (s+T)/s ][ s*C ]
-    xnext.alloc((size_t)Tn * 2 * C);
-    enext.alloc((size_t)(2 + Tn) * 2 * C);
-    e = epi_none(); e.bias = enb_down[l].p; e.out32 = xnext.p; e.out32_map = plain_map(2 * C);
-    e.out16 = enext.p; e.act16 = ACT_ELU; e.out16_map = stream_map(Tn, 2 * C, (long long)(2 + Tn) * 2 * C, (long long)2 * 2 * C);
-    tag("encoder.down"); gemm(ActView{esbuf.p, s * C, (s + T) / s, 1}, 1, Tn, 2, 128, 1, en_down[l], 2 * C, e);
-    PTTS_CUDA(cudaStreamSynchronize(ls));  // the buffers swapped below are freed by their DevBuf
-    std::swap(xcur, xnext);
-    std::swap(ecur, enext);
+    float* xnext = f32buf((size_t)Tn * 2 * C);
+    __half* enext = f16buf((size_t)(2 + Tn) * 2 * C);
+    e = epi_none(); e.bias = enb_down[l].p; e.out32 = xnext; e.out32_map = plain_map(2 * C);
+    e.out16 = enext; e.act16 = ACT_ELU; e.out16_map = stream_map(Tn, 2 * C, (long long)(2 + Tn) * 2 * C, (long long)2 * 2 * C);
+    tag("encoder.down"); gemm(ActView{esbuf, s * C, (s + T) / s, 1}, 1, Tn, 2, 128, 1, en_down[l], 2 * C, e);
+    xcur = xnext;
+    ecur = enext;
   }
   // last conv k3 512 -> 512 on ELU(x) (seanet.rs:236-246)
-  tx.alloc((size_t)P * MIMI_DIM);
-  e = epi_none(); e.bias = enb_c11.p; e.out32 = tx.p; e.out32_map = plain_map(MIMI_DIM);
-  tag("encoder.conv11"); gemm(ActView{ecur.p, MIMI_DIM, 2 + P, 1}, 1, P, 3, 128, 1, en_c11, MIMI_DIM, e);
+  float* tx = f32buf((size_t)P * MIMI_DIM);
+  e = epi_none(); e.bias = enb_c11.p; e.out32 = tx; e.out32_map = plain_map(MIMI_DIM);
+  tag("encoder.conv11"); gemm(ActView{ecur, MIMI_DIM, 2 + P, 1}, 1, P, 3, 128, 1, en_c11, MIMI_DIM, e);
   // encoder transformer (mimi.rs:129-131; transformer.rs:227-251): causal, context 250, LayerScale
-  tqkv.alloc((size_t)P * 3 * MIMI_DIM); th16.alloc((size_t)P * MIMI_DIM); ta16.alloc((size_t)P * MIMI_DIM); tffn.alloc((size_t)P * MIMI_FFN);
-  tag("encoder.layernorm"); ln<MIMI_DIM>(tx.p, P, et_ln1_w[0].p, et_ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, th16.p, MIMI_DIM);
+  float* tqkv = f32buf((size_t)P * 3 * MIMI_DIM);
+  __half* th16 = f16buf((size_t)P * MIMI_DIM);
+  __half* ta16 = f16buf((size_t)P * MIMI_DIM);
+  __half* tffn = f16buf((size_t)P * MIMI_FFN);
+  tag("encoder.layernorm"); ln<MIMI_DIM>(tx, P, et_ln1_w[0].p, et_ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, th16, MIMI_DIM);
   for (int l = 0; l < MIMI_LAYERS; ++l) {
-    e = epi_none(); e.out32 = tqkv.p; e.out32_map = plain_map(3 * MIMI_DIM);
-    tag("encoder.in_proj"); gemm_rows(th16.p, P, MIMI_DIM, et_inproj[l], 3 * MIMI_DIM, e);
-    launch_k(false, enc_rope_kernel, dim3(P, MIMI_HEADS), 32, 0, ls, 1, tqkv.p, 0);
-    launch_k(false, enc_attn_kernel, (unsigned)((P * MIMI_HEADS * 32 + 127) / 128), 128, 0, ls, 1, (const float*)tqkv.p, P, 250, ta16.p);
-    e = epi_none(); e.fscale = et_ls1[l].p; e.res = tx.p; e.res_map = plain_map(MIMI_DIM); e.out32 = tx.p; e.out32_map = plain_map(MIMI_DIM);
-    ln_after_next_gemm("encoder.layernorm", tx.p, P, MIMI_DIM, et_ln2_w[l].p, et_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, th16.p, MIMI_DIM);
-    tag("encoder.out_proj"); gemm_rows(ta16.p, P, MIMI_DIM, et_outproj[l], MIMI_DIM, e, true);
-    e = epi_none(); e.act = ACT_GELU; e.out16 = tffn.p; e.out16_map = plain_map(MIMI_FFN);
-    tag("encoder.linear1"); gemm_rows(th16.p, P, MIMI_DIM, et_lin1[l], MIMI_FFN, e);
-    e = epi_none(); e.fscale = et_ls2[l].p; e.res = tx.p; e.res_map = plain_map(MIMI_DIM); e.out32 = tx.p; e.out32_map = plain_map(MIMI_DIM);
+    e = epi_none(); e.out32 = tqkv; e.out32_map = plain_map(3 * MIMI_DIM);
+    tag("encoder.in_proj"); gemm_rows(th16, P, MIMI_DIM, et_inproj[l], 3 * MIMI_DIM, e);
+    launch_k(false, enc_rope_kernel, dim3(P, MIMI_HEADS), 32, 0, ls, 1, tqkv, 0);
+    launch_k(false, enc_attn_kernel, (unsigned)((P * MIMI_HEADS * 32 + 127) / 128), 128, 0, ls, 1, (const float*)tqkv, P, 250, ta16);
+    e = epi_none(); e.fscale = et_ls1[l].p; e.res = tx; e.res_map = plain_map(MIMI_DIM); e.out32 = tx; e.out32_map = plain_map(MIMI_DIM);
+    ln_after_next_gemm("encoder.layernorm", tx, P, MIMI_DIM, et_ln2_w[l].p, et_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, th16, MIMI_DIM);
+    tag("encoder.out_proj"); gemm_rows(ta16, P, MIMI_DIM, et_outproj[l], MIMI_DIM, e, true);
+    e = epi_none(); e.act = ACT_GELU; e.out16 = tffn; e.out16_map = plain_map(MIMI_FFN);
+    tag("encoder.linear1"); gemm_rows(th16, P, MIMI_DIM, et_lin1[l], MIMI_FFN, e);
+    e = epi_none(); e.fscale = et_ls2[l].p; e.res = tx; e.res_map = plain_map(MIMI_DIM); e.out32 = tx; e.out32_map = plain_map(MIMI_DIM);
     if (l + 1 < MIMI_LAYERS)
-      ln_after_next_gemm("encoder.layernorm", tx.p, P, MIMI_DIM, et_ln1_w[l + 1].p, et_ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, th16.p, MIMI_DIM);
-    tag("encoder.linear2"); gemm_rows(tffn.p, P, MIMI_FFN, et_lin2[l], MIMI_DIM, e, true);
+      ln_after_next_gemm("encoder.layernorm", tx, P, MIMI_DIM, et_ln1_w[l + 1].p, et_ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, th16, MIMI_DIM);
+    tag("encoder.linear2"); gemm_rows(tffn, P, MIMI_FFN, et_lin2[l], MIMI_DIM, e, true);
   }
   // ConvDownsample1d: stride 16, k 32, no bias, replicate padding (conv.rs:278-312) -> [F][512]; then speaker_proj
-  d16.alloc((size_t)(16 + P) * MIMI_DIM);
-  launch_k(false, enc_downsample_prep_kernel, 16 + P, 128, 0, ls, 1, (const float*)tx.p, d16.p);
-  lat16.alloc((size_t)std::max(F, 128) * MIMI_DIM);
-  e = epi_none(); e.out16 = lat16.p; e.out16_map = plain_map(MIMI_DIM);
-  tag("encoder.downsample"); gemm(ActView{d16.p, 16 * MIMI_DIM, (16 + P) / 16, 1}, 1, F, 2, 128, 1, en_ds, MIMI_DIM, e, true);
-  DevBuf<__half> d16b;
+  __half* d16 = f16buf((size_t)(16 + P) * MIMI_DIM);
+  launch_k(false, enc_downsample_prep_kernel, 16 + P, 128, 0, ls, 1, (const float*)tx, d16);
+  __half* lat16 = f16buf((size_t)std::max(F, 256) * MIMI_DIM);
+  e = epi_none(); e.out16 = lat16; e.out16_map = plain_map(MIMI_DIM);
+  tag("encoder.downsample"); gemm(ActView{d16, 16 * MIMI_DIM, (16 + P) / 16, 1}, 1, F, 2, 128, 1, en_ds, MIMI_DIM, e, true);
   if (n_boundaries > 0) {  // first frame of every later chunk: replicate padding instead of the previous 16 positions
-    d16b.alloc((size_t)n_boundaries * 32 * MIMI_DIM);
-    launch_k(false, enc_downsample_boundary_prep_kernel, dim3(n_boundaries, 32), 128, 0, ls, 1, (const float*)tx.p, chunk_frames, d16b.p);
-    e = epi_none(); e.out16 = lat16.p;
+    __half* d16b = f16buf((size_t)n_boundaries * 32 * MIMI_DIM);
+    launch_k(false, enc_downsample_boundary_prep_kernel, dim3(n_boundaries, 32), 128, 0, ls, 1, (const float*)tx, chunk_frames, d16b);
+    e = epi_none(); e.out16 = lat16;
     e.out16_map = stream_map(1, MIMI_DIM, (long long)chunk_frames * MIMI_DIM, (long long)chunk_frames * MIMI_DIM);
-    tag("encoder.downsample"); gemm(ActView{d16b.p, 16 * MIMI_DIM, 2, n_boundaries}, n_boundaries, 1, 2, 1, 128, en_ds, MIMI_DIM, e, true);
+    tag("encoder.downsample"); gemm(ActView{d16b, 16 * MIMI_DIM, 2, n_boundaries}, n_boundaries, 1, 2, 1, 128, en_ds, MIMI_DIM, e, true);
   }
-  prompt_d.alloc((size_t)F * D_MODEL);
-  e = epi_none(); e.out32 = prompt_d.p; e.out32_map = plain_map(D_MODEL);
-  tag("encoder.speaker_proj"); gemm_rows(lat16.p, F, MIMI_DIM, w_spk, D_MODEL, e);
+  float* prompt_d = f32buf((size_t)F * D_MODEL);
+  e = epi_none(); e.out32 = prompt_d; e.out32_map = plain_map(D_MODEL);
+  tag("encoder.speaker_proj"); gemm_rows(lat16, F, MIMI_DIM, w_spk, D_MODEL, e);
   prompt.resize((size_t)F * D_MODEL);
-  PTTS_CUDA(cudaMemcpyAsync(prompt.data(), prompt_d.p, prompt.size() * 4, cudaMemcpyDeviceToHost, ls));
+  PTTS_CUDA(cudaMemcpyAsync(prompt.data(), prompt_d, prompt.size() * 4, cudaMemcpyDeviceToHost, ls));
   PTTS_CUDA(cudaStreamSynchronize(ls));
   PTTS_CUDA(cudaGetLastError());
   *frames_out = F;
