@@ -170,7 +170,9 @@ class UnigramTokenizer:
     """Unigram language-model tokenizer with a Metaspace pre-tokenizer (`split = false`), as the reference builds it.
 
     native (`.model`, text.rs:57-80): prepend '▁' always, no BOS.  `tokenizer.json` (assets/, WASM): whatever the file
-    says (the shipped one: prepend never, `<s>` = 1 in front)."""
+    says (the shipped one: prepend never, `<s>` = 1 in front).  Not modelled: the json file's `added_tokens` pre-pass
+    (a literal "<s>" / "</s>" / "<unk>" / "<pad>" typed into the text is split off before the Unigram model there;
+    here, as in the native `.model` path, it goes through the Unigram search like any other characters)."""
     UNK_PENALTY = 10.0  # tokenizers `K_UNK_PENALTY`
 
     def __init__(self, vocab: list[tuple[str, float]], unk_id: int | None = 0, byte_fallback: bool = True,
