@@ -372,6 +372,52 @@ def test_cfg3_voice_cloning_batch32_lsd4(golden_dir):
     eng.close()
 
 
+def test_facade_text_to_audio_end_to_end(tmp_path):
+    """BASELINE configs[0] through the host mirror of the reference surface: WAV voice prompt -> get_voice_state,
+    text -> prepare / sentence split / Unigram tokenizer -> generate / generate_stream_long -> WAV, with the frame
+    arithmetic of tts_model.rs:968,1055-1069 and the pause arithmetic of pause.rs:183-185."""
+    from pocket_tts_b200 import audio as A
+    from pocket_tts_b200 import text as T
+    from pocket_tts_b200.tts_model import TTSModel
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("_text_fixtures", Path(__file__).with_name("test_text.py"))
+    fixtures = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fixtures)
+    _synthetic_vocab = fixtures._synthetic_vocab
+    for e in _cache.values():
+        e[0].close()
+    _cache.clear()
+    w = dict(synth.make_weights(1234, layer_scale=0.01))
+    w.update(synth.make_encoder_weights(4321))
+    tok = T.UnigramTokenizer(_synthetic_vocab(), 0, True, "always", ())
+    m = TTSModel(w, temp=0.7, max_slots=2, kv_capacity=256, tokenizer=tok)
+    wav = tmp_path / "prompt.wav"
+    prompt_pcm = synth.make_pcm(5 * 1920 + 77, seed=2)[None]
+    A.write_wav(wav, prompt_pcm, 24000)
+    voice = m.get_voice_state(wav)
+    assert len(voice) == 6                                    # 5 frames + 77 samples -> padded to 6 frames
+    m.eos_threshold = 1e30                                    # never EOS: runs to max_gen_len = (words + 2) * 13
+    pcm = m.generate("Hello, world!", voice)
+    assert pcm.shape == (1, (2 + 2) * 13 * 1920) and np.isfinite(pcm).all() and np.abs(pcm).max() > 0
+    m.eos_threshold = -1e30                                   # EOS at step 0: 0 + frames_after_eos (5 for <= 4 words) + 1
+    pcm = m.generate("Hello, world!", voice)
+    assert pcm.shape == (1, 6 * 1920)
+    chunks = list(m.generate_stream_long("Hello there [pause:250ms] world", voice))
+    sizes = [c.shape[-1] for c in chunks]
+    assert sizes.count(6000) == 1 and all(c.shape[:2] == (1, 1) for c in chunks)   # 250 ms at 24 kHz
+    assert not chunks[sizes.index(6000)].any() and sum(sizes) == 6000 + 2 * 6 * 1920
+    out = tmp_path / "out.wav"
+    A.write_wav(out, np.concatenate(chunks, axis=2)[0], m.sample_rate)
+    import wave
+    with wave.open(str(out)) as f:
+        assert f.getnframes() == sum(sizes) and f.getframerate() == 24000
+    m.noise_clamp = 1.0                                       # host-side rejection sampling feeds the stream's noise
+    assert m.generate("Hello, world!", voice).shape == (1, 6 * 1920)
+    voice.close()
+    m.close()
+
+
 def test_voice_cloning_needs_encoder_tensors():
     from pocket_tts_b200 import _lib
     eng, _ = engine_for(1234, 0.01)
