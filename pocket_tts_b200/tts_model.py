@@ -156,38 +156,60 @@ class TTSModel:
         spec = StreamSpec(np.asarray(tokens, np.int32), max_gen_len, frames_after_eos, self.eos_threshold, self.temp, seed, noise)
         (slot,) = self.engine.open_streams([voice], [spec])
         ids = np.array([slot], np.int32)
+        eng = self.engine
+        outstanding: dict[int, bool] = {}   # ticket -> flags already fetched
+
+        def begin(ahead=False):
+            t = eng.step_begin(ids, ahead=ahead)
+            outstanding[t] = False
+            return t
+
+        def flags(t):
+            r = eng.step_flags(t)
+            outstanding[t] = True
+            return r
+
+        def pcm(t, want=True):
+            r = eng.step_pcm(t, want)
+            outstanding.pop(t)
+            return r
+
         try:
             # Frame n's codec half overlaps frame n+1's language-model half, and frame n+1 is enqueued before frame n's
             # flags reach the host (PTTS_STEP_AHEAD) unless frame n is known to be the last (max_gen_len); if frame n
             # turns out to end the stream at EOS, the frame enqueued ahead is retired unseen.
-            eng = self.engine
             can_ahead = True
-            ticket = eng.step_begin(ids)
+            ticket = begin()
             issued = 1
             while True:
                 nxt = None
                 if issued < max_gen_len and can_ahead:
                     try:
-                        nxt = eng.step_begin(ids, ahead=True)
+                        nxt = begin(ahead=True)
                         issued += 1
                     except Exception as e:  # no spare KV row: fall back to begin-after-flags
                         if getattr(e, "code", 0) != -3:
                             raise
                         can_ahead = False
-                fin, _, _ = eng.step_flags(ticket)
+                fin, _, _ = flags(ticket)
                 if nxt is None and not fin[0] and issued < max_gen_len:
-                    nxt = eng.step_begin(ids)
+                    nxt = begin()
                     issued += 1
-                yield eng.step_pcm(ticket).reshape(1, 1, FRAME)
+                frame = pcm(ticket).reshape(1, 1, FRAME)
+                yield frame
                 if fin[0] or nxt is None:
-                    if nxt is not None:  # enqueued ahead of an EOS finish: drain it
-                        eng.step_flags(nxt)
-                        eng.step_pcm(nxt, want=False)
                     break
                 ticket = nxt
         finally:
-            self.engine.sync()
-            self.engine.close_stream(int(slot))
+            # retire whatever is still in flight: the frame enqueued ahead of an EOS finish, or everything when the
+            # consumer drops the iterator early (the reference's iterator simply stops being polled)
+            for t in sorted(outstanding):
+                if not outstanding[t]:
+                    eng.step_flags(t)
+                eng.step_pcm(t, want=False)
+            outstanding.clear()
+            eng.sync()
+            eng.close_stream(int(slot))
 
     def split_into_best_sentences(self, text: str) -> list[str]:
         """tts_model.rs:603-684: chunks of at most 50 tokens on sentence boundaries."""

@@ -412,6 +412,13 @@ def test_facade_text_to_audio_end_to_end(tmp_path):
     import wave
     with wave.open(str(out)) as f:
         assert f.getnframes() == sum(sizes) and f.getframerate() == 24000
+    # a consumer that drops the iterator after one frame leaves nothing in flight behind it
+    m.eos_threshold = 1e30
+    it = m.generate_stream("Hello, world!", voice)
+    assert next(it).shape == (1, 1, 1920)
+    it.close()
+    m.eos_threshold = -1e30
+    assert m.generate("Hello, world!", voice).shape == (1, 6 * 1920)
     m.noise_clamp = 1.0                                       # host-side rejection sampling feeds the stream's noise
     assert m.generate("Hello, world!", voice).shape == (1, 6 * 1920)
     voice.close()
