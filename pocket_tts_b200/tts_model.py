@@ -312,23 +312,38 @@ class BatchScheduler:
             for row, r in enumerate(owners):
                 out[r].append(pcm[row])
 
-        admit()
-        while active:
-            slots = np.fromiter(active.keys(), np.int32, len(active))
-            owners = [active[int(s)] for s in slots]
-            ticket = eng.step_begin(slots)
-            fin, _, _ = eng.step_flags(ticket)
+        try:
+            admit()
+            while active:
+                slots = np.fromiter(active.keys(), np.int32, len(active))
+                owners = [active[int(s)] for s in slots]
+                ticket = eng.step_begin(slots)
+                fin, _, _ = eng.step_flags(ticket)
+                if pending is not None:
+                    collect(pending)
+                pending = (ticket, owners)
+                done = [int(s) for s, f in zip(slots, fin) if f]
+                if done:
+                    collect(pending)  # a finished slot is closed below: drain the step that still reads it
+                    pending = None
+                    for s in done:
+                        eng.close_stream(s)
+                        waiting.append(active.pop(s))
+                    admit()
             if pending is not None:
                 collect(pending)
-            pending = (ticket, owners)
-            done = [int(s) for s, f in zip(slots, fin) if f]
-            if done:
-                collect(pending)  # a finished slot is closed below: drain the step that still reads it
                 pending = None
-                for s in done:
+        finally:
+            # an error part-way (a bad spec, capacity) must not leave steps in flight or slots open on the shared engine
+            if pending is not None:
+                try:
+                    eng.step_pcm(pending[0], want=False)
+                except Exception:
+                    pass
+            for s in list(active):
+                try:
                     eng.close_stream(s)
-                    waiting.append(active.pop(s))
-                admit()
-        if pending is not None:
-            collect(pending)
+                except Exception:
+                    pass
+                active.pop(s, None)
         return [np.concatenate(o) if o else np.zeros(0, np.float32) for o in out]
