@@ -7,8 +7,9 @@
 //     64 activation rows = MMA-N), the next layer's 128 KB land (two TMA boxes) while this layer's epilogue runs.
 //   * the residual stream x never leaves registers: thread = feature, 64 rows per thread (the TMEM accumulator
 //     layout), so bias / gate / residual are register arithmetic straight after tcgen05.ld.
-//   * LayerNorm needs row statistics over all 512 features: a 62-shuffle transpose-reduce per warp, 16 partials
-//     per row exchanged through distributed shared memory, two passes (mean, then centred squares) like the oracle.
+//   * LayerNorm needs row statistics over all 512 features: two transpose-reduces per warp give (sum, M2 about the
+//     warp's own mean) of its 32 features, 16 such partials per row are exchanged through distributed shared memory
+//     once and merged with Chan's update (equal to the oracle's two-pass variance up to rounding).
 //   * the f16 operand of the next Linear (h or g, 64 x 512) is all-gathered through L2: each CTA stores its 128
 //     columns, one cluster barrier, then TMA brings the full rows back in the swizzled operand layout.
 // Every reduction has a fixed order, so results are bit-reproducible.  One cluster per 64 rows of the batch.
@@ -165,7 +166,7 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
       }
       __syncwarp();
       if (L == FH_LAYERS - 1) break;
-      if (has_ln(L)) { cluster_sync_all(); cluster_sync_all(); }
+      if (has_ln(L)) cluster_sync_all();  // the LayerNorm statistics exchange
       cluster_sync_all();
     }
   } else if (warp == 1) {
@@ -207,7 +208,7 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
         if (p.trace && rank == 0 && blockIdx.x == 0 && lane == 0) p.trace[L * 8 + 6] = gtime();
       }
       if (L == FH_LAYERS - 1) break;
-      if (has_ln(L)) { cluster_sync_all(); cluster_sync_all(); }
+      if (has_ln(L)) cluster_sync_all();  // the LayerNorm statistics exchange
       cluster_sync_all();
     }
   } else {
@@ -313,26 +314,33 @@ flow_head_kernel(const __grid_constant__ CUtensorMap map_win, const __grid_const
           sc[r] = __ldg(scale + r * FH_MOD_LD);
           sh[r] = __ldg(shift + r * FH_MOD_LD);
         }
-        float e = warp_rows_sum32([&](int r) { return x[r]; }, lane);
+        // Row statistics over all 512 features in ONE exchange: every warp reduces its 32 features of each row to
+        // (sum, M2 about its own mean) -- two transposes, the local means handed back by shuffle -- the 16 partials per
+        // row meet in every CTA's shared memory after one cluster barrier and are merged with Chan's update, which is
+        // the two-pass variance up to rounding.  (Two exchanges, mean then centred squares, cost one more cluster
+        // barrier per LayerNorm: ~0.9 us x 7 per step.)
+        const float e = warp_rows_sum32([&](int r) { return x[r]; }, lane);
+        const float mloc = e * (1.f / 32.f);  // lane l: mean of row l over this warp's features
+        const float e2 = warp_rows_sum32([&](int r) { const float d = x[r] - __shfl_sync(0xffffffffu, mloc, r); return d * d; }, lane);
 #pragma unroll
-        for (int k = 0; k < FH_CLUSTER; ++k) st_dsmem_f1(stat_peer[k] + stat_off, e);
-        cluster_sync_all();
-        if (etid < FH_ROWS) {
-          float s = 0.f;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) s += stat_s[k * FH_ROWS + etid];
-          mean_s[etid] = s * (1.f / FH_DIM);
+        for (int k = 0; k < FH_CLUSTER; ++k) {
+          st_dsmem_f1(stat_peer[k] + stat_off, e);
+          st_dsmem_f1(stat_peer[k] + 16 * FH_ROWS * 4 + stat_off, e2);
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        e = warp_rows_sum32([&](int r) { const float d = x[r] - mean_h[r]; return d * d; }, lane);
-#pragma unroll
-        for (int k = 0; k < FH_CLUSTER; ++k) st_dsmem_f1(stat_peer[k] + 16 * FH_ROWS * 4 + stat_off, e);
         cluster_sync_all();
         if (etid < FH_ROWS) {
-          float s = 0.f;
+          float tot = 0.f;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) s += stat_s[(16 + k) * FH_ROWS + etid];
-          rstd_s[etid] = 1.f / sqrtf(s * (1.f / FH_DIM) + 1e-6f);
+          for (int k = 0; k < 16; ++k) tot += stat_s[k * FH_ROWS + etid];
+          const float mean = tot * (1.f / FH_DIM);
+          float m2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float d = stat_s[k * FH_ROWS + etid] * (1.f / 32.f) - mean;
+            m2 += stat_s[(16 + k) * FH_ROWS + etid] + 32.f * d * d;
+          }
+          mean_s[etid] = mean;
+          rstd_s[etid] = 1.f / sqrtf(m2 * (1.f / FH_DIM) + 1e-6f);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const bool affine = j < FH_DEPTH;
