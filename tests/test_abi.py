@@ -63,3 +63,25 @@ def test_product_never_imports_oracle():
     for p in (ROOT / "pocket_tts_b200").rglob("*.py"):
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
+
+
+def test_plain_c_caller(built_lib, tmp_path):
+    """include/ptts.h is valid C11 and a plain C host can link the library (the boundary the Rust crate binds,
+    INTEGRATION.md): struct sizes match the ctypes binding, null arguments are refused, and without a device the engine
+    refuses to exist (PTTS_ERR_CUDA) instead of computing on the CPU."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = tmp_path / "abi_check"
+    lib_dir = built_lib.LIB_PATH.parent
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "c_abi" / "abi_check.c"),
+                        "-o", str(exe), f"-L{lib_dir}", "-lptts_cuda", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    args = [str(exe)] + ([] if torch.cuda.is_available() else ["--no-gpu"])
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok header" in r.stdout and "FAIL" not in r.stdout
+    # the same sizes the ctypes structures have
+    assert C.sizeof(built_lib.EngineCfg) == 64 and C.sizeof(built_lib.TensorDesc) == 56 and C.sizeof(built_lib.StreamParams) == 32
