@@ -256,6 +256,101 @@ class TTSModel:
         self.engine.close()
 
 
+def _run_ahead(sched: "BatchScheduler", requests: list[list[tuple]]) -> list[np.ndarray]:
+    """BatchScheduler.run with the device kept one step ahead of the host (PTTS_STEP_AHEAD): while the host unpacks step
+    n (flags, PCM rows, bookkeeping) the device already runs step n+1 on the same rows.  A step is only enqueued ahead
+    when no row can reach its max_gen_len on the current step (the host knows that); a row that ends at EOS instead
+    shows up in the step enqueued ahead as an overrun row (dropped) and its slot is closed once that step is drained."""
+    eng = sched.engine
+    out: list[list[np.ndarray]] = [[] for _ in requests]
+    cursor = [0] * len(requests)
+    waiting = list(range(len(requests)))
+    active: dict[int, int] = {}      # slot -> request
+    budget: dict[int, int] = {}      # slot -> frames the stream may still produce (max_gen_len - frames begun)
+
+    def admit():
+        specs, owners, still = [], [], []
+        for r in waiting:
+            while cursor[r] < len(requests[r]) and requests[r][cursor[r]][0] == "pause":
+                out[r].append(np.zeros(silence_samples(requests[r][cursor[r]][1]), np.float32))
+                cursor[r] += 1
+            if cursor[r] >= len(requests[r]):
+                continue
+            if len(active) + len(specs) < sched.max_batch:
+                specs.append(requests[r][cursor[r]][1])
+                owners.append(r)
+                cursor[r] += 1
+            else:
+                still.append(r)
+        waiting[:] = still
+        if specs:
+            for slot, r, sp in zip(eng.open_streams([sched.voice] * len(specs), specs), owners, specs):
+                active[int(slot)] = r
+                budget[int(slot)] = int(sp.max_gen_len)
+
+    def begin(slots, ahead):
+        t = eng.step_begin(slots, ahead=ahead)
+        for s in slots:
+            budget[int(s)] -= 1
+        return t
+
+    inflight: list[tuple] = []        # [(ticket, slots, owners)] in step order, at most two
+    try:
+        admit()
+        while active or inflight:
+            if not inflight:
+                slots = np.fromiter(active.keys(), np.int32, len(active))
+                inflight.append((begin(slots, False), slots, [active[int(s)] for s in slots]))
+            ticket, slots, owners = inflight[0]
+            # the same rows again, ahead of this step's flags, unless one of them is on its last possible frame
+            if len(inflight) == 1 and all(budget[int(s)] > 0 for s in slots):
+                try:
+                    inflight.append((begin(slots, True), slots, owners))
+                except Exception as e:
+                    if getattr(e, "code", 0) != -3:   # no spare KV row: stay in lock step
+                        raise
+            fin, _, _ = eng.step_flags(ticket)
+            over = eng.last_overrun.copy() if hasattr(eng, "last_overrun") else np.zeros(len(slots), bool)
+            pcm = eng.step_pcm(ticket)
+            inflight.pop(0)
+            for row, r in enumerate(owners):
+                if not over[row]:
+                    out[r].append(pcm[row])
+            done = [int(s) for s, f, o in zip(slots, fin, over) if f and not o]
+            if done:
+                if inflight:   # the step enqueued ahead still reads the finished slots: drain it first
+                    t2, s2, o2 = inflight.pop(0)
+                    fin2, _, _ = eng.step_flags(t2)
+                    over2 = eng.last_overrun.copy() if hasattr(eng, "last_overrun") else np.zeros(len(s2), bool)
+                    pcm2 = eng.step_pcm(t2)
+                    for row, r in enumerate(o2):
+                        if not over2[row]:
+                            out[r].append(pcm2[row])
+                    done += [int(s) for s, f, o in zip(s2, fin2, over2) if f and not o and int(s) not in done]
+                for s in done:
+                    eng.close_stream(s)
+                    waiting.append(active.pop(s))
+                    budget.pop(s, None)
+                admit()
+    finally:
+        for t, _, _ in inflight:
+            try:
+                eng.step_flags(t)
+            except Exception:
+                pass
+            try:
+                eng.step_pcm(t, want=False)
+            except Exception:
+                pass
+        for s in list(active):
+            try:
+                eng.close_stream(s)
+            except Exception:
+                pass
+            active.pop(s, None)
+    return [np.concatenate(o) if o else np.zeros(0, np.float32) for o in out]
+
+
 def shard_requests(n_requests: int, world_size: int, rank: int) -> range:
     """Request sharding across the GPUs of one box: contiguous, disjoint, covering; streams are
     independent so no data-path collective exists."""
@@ -277,7 +372,10 @@ class BatchScheduler:
         self.engine, self.voice = engine, voice
         self.max_batch = max_batch or engine.max_batch
 
-    def run(self, requests: list[list[tuple]]) -> list[np.ndarray]:
+    def run(self, requests: list[list[tuple]], ahead: bool = False) -> list[np.ndarray]:
+        """ahead=True keeps the device one step ahead of the host (see _run_ahead); the default is the lock-step loop."""
+        if ahead:
+            return _run_ahead(self, requests)
         eng = self.engine
         out: list[list[np.ndarray]] = [[] for _ in requests]
         cursor = [0] * len(requests)          # next segment of each request

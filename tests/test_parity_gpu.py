@@ -589,6 +589,22 @@ def test_continuous_batching_long_form():
         [("text", chunk(9, 4)), ("pause", 1000)],
     ]
     got = BatchScheduler(eng, voice, max_batch=3).run(requests)
+    # the same job with the device kept one step ahead of the host (PTTS_STEP_AHEAD) and with EOS endings, which the host
+    # only learns one step late: same audio, nothing of an overrun frame emitted
+    got_ahead = BatchScheduler(eng, voice, max_batch=3).run(requests, ahead=True)
+    for a, b in zip(got_ahead, got):
+        assert a.shape == b.shape and (snr(b, a) >= 60.0 or np.abs(b).max() == 0)
+
+    def eos_chunk(seed, frames):   # ends at EOS on step 0 + frames_after_eos 2 -> 3 frames, well before max_gen_len
+        return StreamSpec(synth.make_tokens(5 + seed % 7, seed=seed), frames, 2, -1e30, temp=0.0)
+
+    eos_requests = [[("text", eos_chunk(11, 9)), ("pause", 100), ("text", chunk(12, 4))], [("text", chunk(13, 6))],
+                    [("text", eos_chunk(14, 7)), ("text", eos_chunk(15, 8))]]
+    lock = BatchScheduler(eng, voice, max_batch=3).run(eos_requests)
+    ahead = BatchScheduler(eng, voice, max_batch=3).run(eos_requests, ahead=True)
+    assert [len(x) for x in lock] == [3 * 1920 + 2400 + 4 * 1920, 6 * 1920, 6 * 1920]
+    for a, b in zip(ahead, lock):
+        assert a.shape == b.shape and snr(b, a) >= 60.0
 
     def alone(spec):
         s = eng.open_streams([voice], [spec])

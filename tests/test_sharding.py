@@ -50,59 +50,69 @@ def test_two_rank_aggregate_gloo():
 
 class _FakeEngine:
     """Host-only stand-in for the engine: a stream's frame f is the constant (spec id * 1000 + f); a stream finishes
-    after spec.max_gen_len frames.  Same call protocol as pocket_tts_b200.engine.Engine (open / begin / flags / pcm /
-    close), with the protocol's ordering rules asserted."""
+    after min(spec.eos_at, spec.max_gen_len) frames.  Same call protocol as pocket_tts_b200.engine.Engine (open / begin /
+    flags / pcm / close, PTTS_STEP_AHEAD with overrun rows), with the protocol's ordering rules asserted."""
 
     def __init__(self, max_batch):
         import numpy as np
         self.np, self.max_batch = np, max_batch
         self.free = list(range(max_batch))
-        self.live = {}       # slot -> [spec, frames done]
-        self.tickets = {}    # ticket -> (slots, per-row frame index, flags fetched)
+        self.live = {}       # slot -> [spec, frames done, finished]
+        self.tickets = {}    # ticket -> [slots, per-row frame index (-1 = overrun), per-row last-frame flag, flags fetched]
         self.next = 0
         self.batch_sizes = []
+        self.ahead_steps = 0
+        self.last_overrun = None
 
     def open_streams(self, voices, specs):
         assert len(voices) == len(specs) <= len(self.free)
         out = []
         for s in specs:
             slot = self.free.pop(0)
-            self.live[slot] = [s, 0]
+            self.live[slot] = [s, 0, False]
             out.append(slot)
         return self.np.asarray(out, self.np.int32)
 
     def step_begin(self, slots, want_pcm=True, ahead=False):
         assert all(int(s) in self.live for s in slots) and len(set(map(int, slots))) == len(slots)
-        assert all(t[2] for t in self.tickets.values()), "flags of the previous step must be fetched first"
+        unfetched = [t for t, v in self.tickets.items() if not v[3]]
+        assert len(unfetched) <= (1 if ahead else 0), "flags of the previous step must be fetched first (one step ahead at most)"
+        assert len(self.tickets) < 3
+        self.ahead_steps += bool(ahead)
         self.batch_sizes.append(len(slots))
-        rows = []
+        rows, last = [], []
         for s in slots:
             st = self.live[int(s)]
+            if st[2]:
+                assert ahead, "a finished stream may only be stepped by a step enqueued ahead"
+                rows.append(-1); last.append(True)
+                continue
             rows.append(st[1])
             st[1] += 1
-        self.tickets[self.next] = ([int(s) for s in slots], rows, False)
+            st[2] = st[1] >= min(getattr(st[0], "eos_at", 1 << 30), st[0].max_gen_len)
+            last.append(st[2])
+        self.tickets[self.next] = [[int(s) for s in slots], rows, last, False]
         self.next += 1
         return self.next - 1
 
     def step_flags(self, t):
-        slots, rows, _ = self.tickets[t]
-        self.tickets[t] = (slots, rows, True)
-        fin = self.np.array([self.live[s][1] >= self.live[s][0].max_gen_len for s in slots])
-        return fin, None, None
+        assert all(v[3] for k, v in self.tickets.items() if k < t), "flags are fetched in step order"
+        slots, rows, last, _ = self.tickets[t]
+        self.tickets[t][3] = True
+        self.last_overrun = self.np.array([r < 0 for r in rows])
+        return self.np.array(last), None, None
 
     def step_pcm(self, t, want=True):
-        slots, rows, fetched = self.tickets.pop(t)
+        slots, rows, _, fetched = self.tickets.pop(t)
         assert fetched
-        return self.np.stack([self.np.full(4, self.live_or_closed[s] * 1000 + f, self.np.float32) for s, f in zip(slots, rows)])
+        if not want:
+            return None
+        return self.np.stack([self.np.full(4, self.live[s][0].tokens * 1000 + f, self.np.float32) for s, f in zip(slots, rows)])
 
     def close_stream(self, slot):
         assert not any(slot in t[0] for t in self.tickets.values()), "a closed slot still has an undrained step"
         self.free.append(slot)
         del self.live[slot]
-
-    @property
-    def live_or_closed(self):
-        return {s: v[0].tokens for s, v in self.live.items()}
 
 
 def test_continuous_batching_host_logic_without_gpu():
@@ -139,3 +149,23 @@ def test_continuous_batching_host_logic_without_gpu():
     for got, w in zip(out, want):
         np.testing.assert_array_equal(got, w)
     assert max(eng.batch_sizes) <= 3 and sorted(eng.free) == [0, 1, 2] and not eng.live and not eng.tickets
+    # the same job with the device kept one step ahead of the host, and with streams that end early at "EOS"
+    # (the step enqueued ahead then carries an overrun row, which must never reach the output)
+    def chunk_eos(cid, frames, eos_at):
+        return ("text", SimpleNamespace(tokens=cid, max_gen_len=frames, eos_at=eos_at))
+
+    eos_requests = [
+        [chunk_eos(1, 9, 3), ("pause", 100), chunk(2, 3)],
+        [chunk_eos(3, 6, 6), chunk_eos(4, 8, 1)],
+        [chunk(5, 5)],
+        [chunk_eos(6, 7, 2)],
+    ]
+    for reqs in (requests, eos_requests):
+        lock = BatchScheduler(_FakeEngine(max_batch=3), voice=None, max_batch=3).run(reqs)
+        eng2 = _FakeEngine(max_batch=3)
+        ahead = BatchScheduler(eng2, voice=None, max_batch=3).run(reqs, ahead=True)
+        for a, b in zip(ahead, lock):
+            np.testing.assert_array_equal(a, b)
+        assert sorted(eng2.free) == [0, 1, 2] and not eng2.live and not eng2.tickets
+        if reqs is eos_requests:   # (in the first job some row is on its last possible frame at every step)
+            assert eng2.ahead_steps >= 3
