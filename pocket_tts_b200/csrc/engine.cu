@@ -50,6 +50,7 @@ static constexpr int D_MODEL = 1024, N_HEADS = 16, N_LAYERS = 6, D_FFN = 4096;
 static constexpr int FLOW_DIM = 512, FLOW_DEPTH = 6, MOD_LD = FLOW_DEPTH * 3 * FLOW_DIM + 2 * FLOW_DIM;  // 10240
 static constexpr int MIMI_DIM = 512, MIMI_HEADS = 8, MIMI_LAYERS = 2, MIMI_FFN = 2048, MIMI_T = 16;
 static constexpr int N_BINS = 4000;
+static constexpr int MAX_LSD = 64;   // ptts_engine_set_lsd_steps cap; time_emb is sized for it once
 
 struct Weight16 {   // GEMM operand [Fpad][K] f16, K-major
   DevBuf<__half> w;
@@ -171,6 +172,7 @@ struct Engine {
   DevBuf<__half> mimi_ring;     // [NS][2][2][8][272][64]
   DevBuf<__half> st_tr, st_a0, st_e2, st_a3, st_e5, st_a6, st_e8, st_a9;  // conv left-context rows per slot
   std::vector<SlotHost> slots;
+  std::vector<unsigned char> slot_mark;   // check_slots scratch
   std::vector<std::unique_ptr<Voice>> voices;
 
   // ---- decode scratch (compact by batch row)
@@ -204,6 +206,14 @@ struct Engine {
   cudaEvent_t ev_flags[NT] = {}, ev_pcm[NT] = {};
   struct Ticket { long long id = -1; int n = 0; bool flags_done = true, pcm_done = true, want_pcm = false; std::vector<int> slot_ids; };
   Ticket tickets[NT];
+  // a ticket whose flags have not been fetched still lists its slots: closing / reopening one of them in between would make
+  // step_flags_impl book the overrun row of the OLD stream onto the NEW one
+  bool slot_in_pending_ticket(int s) const {
+    for (const Ticket& t : tickets)
+      if (!t.flags_done)
+        for (int id : t.slot_ids) if (id == s) return true;
+    return false;
+  }
   long long next_ticket = 0;
   void sync_all() { PTTS_CUDA(cudaStreamSynchronize(stream)); PTTS_CUDA(cudaStreamSynchronize(stream_b)); }
   cudaEvent_t ev[10]{};
@@ -624,7 +634,10 @@ void Engine::compute_time_embeddings(int steps) {
       for (int o = 0; o < FLOW_DIM; ++o) te[(size_t)s * FLOW_DIM + o] += 0.5f * h2[o] * al.f32[o] * r;
     }
   }
-  time_emb.alloc(te.size());
+  // one allocation at the maximum size (lsd_steps <= MAX_LSD), overwritten in place: the captured step graphs have
+  // time_emb.p + s * FLOW_DIM baked into their kernel arguments, so the buffer must never move
+  PTTS_REQUIRE(steps >= 1 && steps <= MAX_LSD, PTTS_ERR_INVALID, "lsd_steps %d outside [1,%d]", steps, MAX_LSD);
+  if (!time_emb.p) time_emb.alloc((size_t)MAX_LSD * FLOW_DIM);
   PTTS_CUDA(cudaMemcpy(time_emb.p, te.data(), te.size() * 4, cudaMemcpyHostToDevice));
   lsd_steps = steps;
 }
@@ -1154,7 +1167,15 @@ cudaGraphExec_t Engine::capture(cudaStream_t st, int n, int part, long long* ker
 // ~100 dependent launches of a few microseconds; every pointer is a fixed engine buffer and the batch composition is
 // data, so one pair of graphs per (rows, lsd_steps) serves every step of that size).
 void Engine::run_step(int n) {
-  if (profiling) return step_kernels(n, nullptr);
+  if (profiling) {
+    // sequential form on `stream`; the codec stream (PCM copy, ev_pcm) must still order behind it
+    step_kernels(n, nullptr);
+    PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
+    PTTS_CUDA(cudaEventRecord(ev_front_done, stream));
+    PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_front_done, 0));
+    PTTS_CUDA(cudaEventRecord(ev_b_done, stream_b));
+    return;
+  }
   // A(n) may not overwrite z32 / advance the frame counters before front(n-1) has consumed them
   PTTS_CUDA(cudaStreamWaitEvent(stream, ev_front_done, 0));
   if (cfg.use_cuda_graph) {
@@ -1350,9 +1371,9 @@ void ptts_engine_destroy(ptts_engine* e) {
 
 int32_t ptts_engine_set_lsd_steps(ptts_engine* h, int32_t lsd_steps) {
   PTTS_TRY
-  PTTS_REQUIRE(h && lsd_steps >= 1 && lsd_steps <= 64, PTTS_ERR_INVALID, "lsd_steps must be in [1,64]");
+  PTTS_REQUIRE(h && lsd_steps >= 1 && lsd_steps <= MAX_LSD, PTTS_ERR_INVALID, "lsd_steps must be in [1,64]");
   PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
-  PTTS_CUDA(cudaStreamSynchronize(h->e.stream));
+  h->e.sync_all();  // no step may be reading the time embeddings while they are rewritten
   h->e.compute_time_embeddings(lsd_steps);
   return PTTS_OK;
   PTTS_CATCH
@@ -1444,6 +1465,12 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
       PTTS_REQUIRE(tokens[j] >= 0 && tokens[j] <= N_BINS, PTTS_ERR_INVALID, "stream %d: token id %d out of range", i, tokens[j]);
   }
   const size_t per_slot_kv = (size_t)N_LAYERS * 2 * N_HEADS * e.KVCAP * HD;
+  // from here on slots are claimed: a failure part-way (allocation, copy, launch) releases every slot claimed so far,
+  // because the caller has no ids yet with which to close them
+  struct Rollback {
+    Engine& e; const std::vector<int>& ids; bool armed = true;
+    ~Rollback() { if (armed) { cudaStreamSynchronize(e.stream); for (int s : ids) e.slots[s] = SlotHost{}; e.row_seq_host.clear(); } }
+  } rollback{e, free_slots};
   std::vector<SeqDesc> sds(n);
   std::vector<StreamCtl> ctls(n);
   std::vector<int> lens(n);
@@ -1497,15 +1524,20 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
     i0 = i1;
   }
   e.row_seq_host.clear();
+  rollback.armed = false;
   return PTTS_OK;
   PTTS_CATCH
 }
 
 static void check_slots(Engine& e, const int32_t* slot_ids, int n, int steps_in_flight = 0) {
   PTTS_REQUIRE(slot_ids && n >= 1 && n <= e.NB, PTTS_ERR_INVALID, "step: n = %d (max_batch %d)", n, e.NB);
+  e.slot_mark.assign(e.NS, 0);
   for (int i = 0; i < n; ++i) {
     const int s = slot_ids[i];
     PTTS_REQUIRE(s >= 0 && s < e.NS && e.slots[s].in_use, PTTS_ERR_STATE, "step: slot %d is not open", s);
+    // two rows of one batch on the same slot would race on its KV rows and counters
+    PTTS_REQUIRE(!e.slot_mark[s], PTTS_ERR_INVALID, "step: slot %d listed twice", s);
+    e.slot_mark[s] = 1;
     PTTS_REQUIRE(!e.slots[s].finished, PTTS_ERR_STATE, "step: slot %d already finished", s);
     // a step enqueued ahead of unfetched flags may run past the stream's last frame: its KV row must still exist
     PTTS_REQUIRE(e.slots[s].own_len + steps_in_flight < e.KVCAP, PTTS_ERR_CAPACITY, "step: slot %d KV full", s);
@@ -1578,6 +1610,9 @@ int64_t ptts_step_begin(ptts_engine* h, const int32_t* slot_ids, int32_t n, int3
   } catch (const ptts::Error& ex) {
     g_last_error = ex.what();
     return ex.code;
+  } catch (const std::exception& ex) {  // bad_alloc / length_error from the ticket bookkeeping must not cross the C ABI
+    g_last_error = ex.what();
+    return PTTS_ERR_INVALID;
   }
 }
 
@@ -1691,6 +1726,7 @@ int32_t ptts_stream_close(ptts_engine* h, int32_t slot) {
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
   Engine& e = h->e;
   PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
+  PTTS_REQUIRE(!e.slot_in_pending_ticket(slot), PTTS_ERR_STATE, "slot %d is part of a step whose flags have not been fetched (ptts_step_flags first)", slot);
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
   e.sync_all();
   e.slots[slot] = SlotHost{};
