@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 #include "host_util.h"
 #include "kernels.cuh"
+#include "lm_step.cuh"
 
 namespace ptts {
 
@@ -142,7 +143,19 @@ struct Engine {
   Weight16 w_cond, w_finproj, w_ada, w_mlp0[FLOW_DEPTH], w_mlp2[FLOW_DEPTH], w_final;
   DevBuf<__half> w_flowpack;   // mlp.0 / mlp.2 of the six blocks and the final Linear, one [6272][512] operand (flow_head.cuh)
   bool fused_flow = true;      // ptts_engine_cfg.reserved[5] = 1 or debug_gemm: the per-layer launches instead
-  void flow_head_fused(int n);
+  void flow_head_fused(int n, const float* mod);
+  // ---- persistent FlowLM step kernel (lm_step.cuh): tiled weight images, operand images, split-K workspace, grid barrier
+  bool lm_enabled = false;     // built at init unless int8 weights / debug GEMM / PTTS_LM_MEGA=0 / cfg.reserved[8] = 1
+  int lm_ctas = 0;             // grid of the step kernel (PTTS_LM_CTAS; default: every SM)
+  int lm_flags = 0;            // LmStepParams::flags (PTTS_LM_FLAGS, bring-up)
+  DevBuf<uint8_t> lm_wt, lm_hA, lm_attnA, lm_ffnA, lm_yA;
+  DevBuf<float> lm_ws, lm_mod;
+  DevBuf<unsigned long long> lm_bar, lm_trace;
+  LmStepParams lm_params{};
+  double lm_weight_bytes = 0;
+  void lm_build();
+  bool lm_usable(int n) const { return lm_enabled && n >= 1 && n <= LM_ROWS && lsd_steps <= LM_MAX_LSD; }
+  void lm_step(int n);
   DevBuf<unsigned long long> fh_trace;  // PTTS_FH_TRACE=1: stage stamps of the fused flow head, printed by sync
   DevBuf<float> b_cond, b_finproj, b_ada, b_mlp0[FLOW_DEPTH], b_mlp2[FLOW_DEPTH], b_final, inln_w[FLOW_DEPTH], inln_b[FLOW_DEPTH];
   DevBuf<float> time_emb;  // [S,512]
@@ -750,6 +763,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     PTTS_CUDA(cudaEventCreateWithFlags(&ev_flags[i], cudaEventDisableTiming));
     PTTS_CUDA(cudaEventCreateWithFlags(&ev_pcm[i], cudaEventDisableTiming));
   }
+  lm_build();
   for (auto it = host.begin(); it != host.end();)  // only the time-embedding MLPs are needed again (set_lsd_steps)
     it = (it->first.find("time_embed") == std::string::npos) ? host.erase(it) : std::next(it);
   PTTS_CUDA(cudaDeviceSynchronize());
@@ -958,7 +972,7 @@ static RowMap stream_map(int T, int ld, long long stream_stride, long long base)
 // Frame n+1's A depends only on frame n's A, so run_step() puts A on one stream and front+B on another: the codec
 // of frame n overlaps the language model of frame n+1.
 // input_proj + six AdaLN residual blocks + final layer of one LSD step as a single cluster kernel (flow_head.cuh)
-void Engine::flow_head_fused(int n) {
+void Engine::flow_head_fused(int n, const float* mod) {
   FlowHeadParams fp{};
   fp.b_in = b_finproj.p; fp.b_final = b_final.p;
   fp.ws_in = w_finproj.wscale.p; fp.ws_final = w_final.wscale.p;
@@ -967,7 +981,7 @@ void Engine::flow_head_fused(int n) {
     fp.ln_w[i] = inln_w[i].p; fp.ln_b[i] = inln_b[i].p;
     fp.ws0[i] = w_mlp0[i].wscale.p; fp.ws2[i] = w_mlp2[i].wscale.p;
   }
-  fp.mod = mod32.p; fp.z32 = z32.p; fp.z16 = z16.p; fp.h16 = fh16.p; fp.g16 = fg16.p; fp.x_dbg = fx32.p;
+  fp.mod = mod; fp.z32 = z32.p; fp.z16 = z16.p; fp.h16 = fh16.p; fp.g16 = fg16.p; fp.x_dbg = fx32.p;
   fp.n = n; fp.alpha = 1.f / (float)lsd_steps;
   fp.trace = fh_trace.p;
   const CUtensorMap& m_win = tmaps.get(w_finproj.w.p, 64, w_finproj.Fpad, 1, 64, (long long)w_finproj.Fpad * 64, 128, 1);
@@ -988,7 +1002,108 @@ void Engine::flow_head_fused(int n) {
   PTTS_CUDA(cudaGetLastError());
 }
 
+// The language-model half through the persistent step kernel: ONE launch for the feedback gather, input_linear, six
+// transformer layers, out_norm + EOS, cond_embed and the adaLN modulations of every LSD step; then the fused flow head
+// per LSD step and the EOS bookkeeping.
+void Engine::lm_step(int n) {
+  LmStepParams& q = lm_params;
+  q.n = n;
+  q.lsd_steps = lsd_steps;
+  q.time_emb = time_emb.p;
+  q.trace = lm_trace.p;
+  q.flags = lm_flags;
+  q.stop_phase = std::getenv("PTTS_LM_STOP") ? std::atoi(std::getenv("PTTS_LM_STOP")) : 0;
+  {
+    const double kv = 6.0 * step_kv_bytes;
+    const double bytes = lm_weight_bytes + (double)lsd_steps * MOD_LD * FLOW_DIM * 2 + kv + (double)n * (D_MODEL * 8 + lsd_steps * MOD_LD * 4.0);
+    const double flops = 2.0 * n * ((double)N_LAYERS * 12 * D_MODEL * D_MODEL + (double)D_MODEL * FLOW_DIM + (double)lsd_steps * MOD_LD * FLOW_DIM) + kv;
+    ProfScope ps(*this, "flowlm.step_kernel", bytes, flops, "flowlm_step_kernel");
+    launch_k(use_pdl, flowlm_step_kernel, lm_ctas, LM_THREADS, LM_SMEM, ls, 1, q);
+    PTTS_CUDA(cudaGetLastError());
+  }
+}
+
+void Engine::lm_build() {
+  lm_enabled = false;
+  if (cfg.weight_mode != PTTS_W_F16 || cfg.debug_gemm || cfg.reserved[8] == 1) return;
+  if (const char* v = std::getenv("PTTS_LM_MEGA")) if (std::atoi(v) == 0) return;
+  cudaDeviceProp prop;
+  PTTS_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+  lm_ctas = prop.multiProcessorCount;
+  if (const char* v = std::getenv("PTTS_LM_CTAS")) lm_ctas = std::max(16, std::min(prop.multiProcessorCount, std::atoi(v)));  // attention needs one CTA per head
+  if (const char* v = std::getenv("PTTS_LM_FLAGS")) lm_flags = std::atoi(v);
+  PTTS_CUDA(cudaFuncSetAttribute(flowlm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
+  // tile images of every weight the step kernel streams
+  size_t total = 0;
+  auto sz = [](const Weight16& w) { return (size_t)w.Fpad * w.K * 2; };
+  for (int l = 0; l < N_LAYERS; ++l) total += sz(w_inproj[l]) + sz(w_outproj[l]) + sz(w_lin1[l]) + sz(w_lin2[l]);
+  total += sz(w_cond) + sz(w_ada);
+  lm_wt.alloc(total);
+  size_t off = 0;
+  auto tile = [&](const Weight16& w) {
+    PTTS_REQUIRE(w.Fpad % 128 == 0 && w.K % 64 == 0, PTTS_ERR_INVALID, "step kernel: weight %d x %d is not tileable", w.Fpad, w.K);
+    const long long chunks = (long long)w.Fpad * w.K / 8;
+    lm_tile_weight_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(w.w.p, w.Fpad, w.K, lm_wt.p + off);
+    const uint8_t* at = lm_wt.p + off;
+    off += sz(w);
+    return at;
+  };
+  LmStepParams& q = lm_params;
+  q = LmStepParams{};
+  for (int l = 0; l < N_LAYERS; ++l) {
+    q.w_inproj[l] = tile(w_inproj[l]); q.w_outproj[l] = tile(w_outproj[l]);
+    q.w_lin1[l] = tile(w_lin1[l]); q.w_lin2[l] = tile(w_lin2[l]);
+    q.ln1_w[l] = ln1_w[l].p; q.ln1_b[l] = ln1_b[l].p; q.ln2_w[l] = ln2_w[l].p; q.ln2_b[l] = ln2_b[l].p;
+  }
+  q.w_cond = tile(w_cond); q.w_ada = tile(w_ada);
+  PTTS_CUDA(cudaGetLastError());
+  lm_weight_bytes = (double)total - (double)sz(w_ada);  // the adaLN weights are counted per LSD step
+  q.w_input = w_input.w.p;
+  q.outnorm_w = outnorm_w.p; q.outnorm_b = outnorm_b.p; q.eos_w = eos_w.p; q.eos_b = eos_b.p;
+  q.b_cond = b_cond.p; q.b_ada = b_ada.p;
+  // split every GEMM phase over the grid: units = feature tiles x K splits, at most LM_ACT_KB k-blocks per unit
+  auto shape = [&](int F, int K, bool unsplit) {
+    LmGemmShape sh{};
+    sh.Mt = F / 128; sh.KB = K / 64;
+    int S = unsplit ? 1 : std::max(1, std::min(sh.KB, lm_ctas / sh.Mt));
+    sh.kbps = std::min(LM_ACT_KB, (sh.KB + S - 1) / S);
+    sh.S = (sh.KB + sh.kbps - 1) / sh.kbps;
+    return sh;
+  };
+  q.shape[LM_G_INPROJ] = shape(3 * D_MODEL, D_MODEL, false);
+  q.shape[LM_G_OUTPROJ] = shape(D_MODEL, D_MODEL, false);
+  q.shape[LM_G_LIN1] = shape(D_FFN, D_MODEL, false);
+  q.shape[LM_G_LIN2] = shape(D_MODEL, D_FFN, false);
+  q.shape[LM_G_COND] = shape(FLOW_DIM, D_MODEL, false);
+  q.shape[LM_G_ADA] = shape(MOD_LD, FLOW_DIM, true);   // written straight to the modulation rows: no split
+  PTTS_REQUIRE(q.shape[LM_G_ADA].S == 1 && w_ada.Fpad == MOD_LD && w_cond.Fpad == FLOW_DIM, PTTS_ERR_STATE, "step kernel: adaLN / cond shapes");
+  size_t ws_floats = 0;
+  const int Fs[LM_G_KINDS] = {3 * D_MODEL, D_MODEL, D_FFN, D_MODEL, FLOW_DIM, 0};
+  for (int k = 0; k < LM_G_KINDS; ++k) ws_floats = std::max(ws_floats, (size_t)q.shape[k].S * LM_ROWS * Fs[k]);
+  lm_ws.alloc(ws_floats);
+  lm_hA.alloc((size_t)(D_MODEL / 64) * LM_ATILE); lm_attnA.alloc((size_t)(D_MODEL / 64) * LM_ATILE);
+  lm_ffnA.alloc((size_t)(D_FFN / 64) * LM_ATILE); lm_yA.alloc((size_t)LM_MAX_LSD * (FLOW_DIM / 64) * LM_ATILE);
+  lm_mod.alloc((size_t)LM_MAX_LSD * LM_ROWS * MOD_LD);
+  lm_bar.alloc(2);
+  if (std::getenv("PTTS_LM_TRACE")) lm_trace.alloc(2 * 64);
+  q.row_seq = row_seq.p; q.ctl = ctl.p; q.feedback = feedback.p; q.seqs = seqs.p; q.own_len = own_len.p; q.row_desc = row_desc.p;
+  q.x32 = x32.p; q.hA = lm_hA.p; q.attnA = lm_attnA.p; q.ffnA = lm_ffnA.p; q.yA = lm_yA.p; q.ws = lm_ws.p;
+  q.z32 = z32.p; q.z16 = z16.p; q.eos_logit = eos_logit.p; q.c32 = c32.p; q.mod32 = lm_mod.p; q.h32dbg = h32dbg.p;
+  q.bar = lm_bar.p;
+  PTTS_CUDA(cudaStreamSynchronize(stream));
+  lm_enabled = true;
+}
+
 void Engine::step_part_a(int n, bool marks) {
+  if (lm_usable(n)) {
+    lm_step(n);
+    if (marks) PTTS_CUDA(cudaEventRecord(ev[1], ls));
+    for (int s = 0; s < lsd_steps; ++s) flow_head_fused(n, lm_mod.p + (size_t)s * LM_ROWS * MOD_LD);
+    { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
+      launch_k(use_pdl, step_end_kernel, n, 32, 0, ls, 1, row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
+                                            latent_out.p, logit_out.p); }
+    return;
+  }
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
   { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
     launch_k(use_pdl, step_begin_kernel, n, 64, 0, ls, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p, (const SeqDesc*)seqs.p,
@@ -1013,7 +1128,7 @@ void Engine::step_part_a(int n, bool marks) {
     e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
     tag("flow.adaln"); gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
     if (fused_flow) {
-      flow_head_fused(n);
+      flow_head_fused(n, mod32.p);
       continue;
     }
     e = epi_none();
@@ -1697,6 +1812,21 @@ int32_t ptts_sync(ptts_engine* h) {
                      (long long)(st[L * 8 + 2] - st[0]), (long long)(st[L * 8 + 3] - st[0]));
     }
   }
+  if (h->e.lm_trace.p) {
+    unsigned long long st[128];
+    if (cudaMemcpy(st, h->e.lm_trace.p, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess && st[0]) {
+      const int nph = LM_PH_ADA + h->e.lsd_steps;
+      std::fprintf(stderr, "ptts step kernel trace (CTA 0, ns): phase: start(since phase 0) work barrier\n");
+      for (int ph = 0; ph < nph; ++ph) {
+        const long long start = (long long)(st[ph * 2] - st[0]), work = (long long)(st[ph * 2 + 1] - st[ph * 2]);
+        const long long bar = ph + 1 < nph ? (long long)(st[ph * 2 + 2] - st[ph * 2 + 1]) : 0;
+        std::fprintf(stderr, "  ph%02d: %7lld %6lld %6lld\n", ph, start, work, bar);
+      }
+      std::fprintf(stderr, "  attention of layer 1, CTA 0 warp 0 (ns since its phase start): ");
+      for (int i = 0; i < 21; ++i) std::fprintf(stderr, "%lld ", st[104 + i] ? (long long)(st[104 + i] - st[10 * 2]) : -1LL);
+      std::fprintf(stderr, "\n");
+    }
+  }
   if (h->e.diag_times) {
     float a = 0, b = 0, ab = 0, ae = 0;
     if (cudaEventElapsedTime(&a, h->e.ev_t[0], h->e.ev_t[1]) == cudaSuccess && cudaEventElapsedTime(&b, h->e.ev_t[2], h->e.ev_t[3]) == cudaSuccess &&
@@ -1771,6 +1901,11 @@ int64_t ptts_debug_read(ptts_engine* h, const char* name, int32_t row, float* ou
     else if (n == "seanet.convtr5") { src = e.x5.p + (size_t)row * 480 * 128; cnt = 480 * 128; }
     else if (n == "seanet.convtr8") { src = e.x8.p + (size_t)row * 1920 * 64; cnt = 1920 * 64; }
     else if (n == "pcm") { src = e.pcm.p + (size_t)row * FRAME; cnt = FRAME; }
+    // raw buffers of the persistent step kernel (bring-up): `row` selects a 1 M-float window
+    else if (n == "lm.ws") { src = e.lm_ws.p + (size_t)row * (1 << 20); cnt = std::min<int64_t>(1 << 20, (int64_t)e.lm_ws.n - (int64_t)row * (1 << 20)); }
+    else if (n == "lm.hA") { src = reinterpret_cast<const float*>(e.lm_hA.p); cnt = (int64_t)e.lm_hA.n / 4; }
+    else if (n == "lm.attnA") { src = reinterpret_cast<const float*>(e.lm_attnA.p); cnt = (int64_t)e.lm_attnA.n / 4; }
+    else if (n == "lm.ffnA") { src = reinterpret_cast<const float*>(e.lm_ffnA.p); cnt = (int64_t)e.lm_ffnA.n / 4; }
     else PTTS_REQUIRE(false, PTTS_ERR_INVALID, "unknown tap '%s'", name);
     PTTS_REQUIRE(cnt <= cap, PTTS_ERR_INVALID, "tap '%s' needs %lld floats, buffer holds %lld", name, (long long)cnt, (long long)cap);
     PTTS_CUDA(cudaMemcpy(out, src, cnt * 4, cudaMemcpyDeviceToHost));
