@@ -145,7 +145,7 @@ struct Engine {
   bool fused_flow = true;      // ptts_engine_cfg.reserved[5] = 1 or debug_gemm: the per-layer launches instead
   void flow_head_fused(int n, const float* mod);
   // ---- persistent FlowLM step kernel (lm_step.cuh): tiled weight images, operand images, split-K workspace, grid barrier
-  bool lm_enabled = false;     // built at init unless int8 weights / debug GEMM / PTTS_LM_MEGA=0 / cfg.reserved[8] = 1
+  bool lm_enabled = false;     // built at init when selected (see lm_build) and the weights are f16
   int lm_ctas = 0;             // grid of the step kernel (PTTS_LM_CTAS; default: every SM)
   int lm_flags = 0;            // LmStepParams::flags (PTTS_LM_FLAGS, bring-up)
   DevBuf<uint8_t> lm_wt, lm_hA, lm_attnA, lm_ffnA, lm_yA;
@@ -845,7 +845,8 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   p.epi_mask = epi_mask_of(p.epi);
   p.pdl_trigger = (ls == stream_b) ? trig_b : trig_a;
   grid.z = splits;
-  const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : 200) * 1024LL;  // one CTA per SM
+  static const int env_smem_kb = std::getenv("PTTS_GEMM_SMEM_KB") ? std::atoi(std::getenv("PTTS_GEMM_SMEM_KB")) : 0;
+  const long long kSmemBudget = (cfg.reserved[4] > 0 ? cfg.reserved[4] : env_smem_kb > 0 ? env_smem_kb : 200) * 1024LL;  // one CTA per SM
   const int stage_bytes = GEMM_BM * GEMM_BK * 2 + p.BN * GEMM_BK * 2;
   const size_t tile_bytes = swap ? (size_t)p.BN * (GEMM_BM + 4) * 4 : (size_t)GEMM_BM * (p.BN + 4) * 4;
   size_t smem;
@@ -1024,9 +1025,15 @@ void Engine::lm_step(int n) {
 }
 
 void Engine::lm_build() {
+  // Selection (ptts_engine_cfg.reserved[8], else PTTS_LM_STEP_KERNEL): 0 = auto, 1 = never, 2 = always when legal.
+  // Auto currently means off: at 64 streams the kernel finishes the language-model half in ~300 us against ~365 us of
+  // per-layer launches, but it holds every SM it runs on for that whole time, and the codec half of the previous frame
+  // (which the per-layer path overlaps on the SMs its small grids leave free) then has nowhere to run; measured
+  // 8.5 k audio-s/s (96 CTAs) against 9.2 k.  DESIGN.md section 10 has the numbers.
   lm_enabled = false;
-  if (cfg.weight_mode != PTTS_W_F16 || cfg.debug_gemm || cfg.reserved[8] == 1) return;
-  if (const char* v = std::getenv("PTTS_LM_MEGA")) if (std::atoi(v) == 0) return;
+  int mode = cfg.reserved[8];
+  if (mode == 0) if (const char* v = std::getenv("PTTS_LM_STEP_KERNEL")) mode = std::atoi(v) ? 2 : 1;
+  if (cfg.weight_mode != PTTS_W_F16 || cfg.debug_gemm || mode != 2) return;
   cudaDeviceProp prop;
   PTTS_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
   lm_ctas = prop.multiProcessorCount;

@@ -105,7 +105,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 static constexpr int GEMM_BM = 128;
 static constexpr int GEMM_BK = 64;
-static constexpr int GEMM_THREADS = 384;  // 12 warps, one CTA per SM (8 warps x 2 CTAs per SM measured 7% slower: the store loops want warps)
+#ifndef PTTS_GEMM_THREADS
+#define PTTS_GEMM_THREADS 384
+#endif
+#ifndef PTTS_GEMM_MINBLOCKS
+#define PTTS_GEMM_MINBLOCKS 1
+#endif
+static constexpr int GEMM_THREADS = PTTS_GEMM_THREADS;  // 12 warps, one CTA per SM (8 warps x 2 CTAs per SM measured 7% slower: the store loops want warps)
 static constexpr int GEMM_MAX_SPLIT = 8;  // portable cluster size
 
 // Row part of a RowMap offset (everything except "+ f"); no integer division when the map is a plain
@@ -491,7 +497,7 @@ __device__ __forceinline__ void epi_dispatch(const GemmParams& p, uint32_t stile
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, PTTS_GEMM_MINBLOCKS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w,
                const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -747,7 +753,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
 // pipeline runs ahead across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of
 // tile j (10 warps: 4 TMEM readers stage the tile in shared memory, all 10 store it) overlaps the MMAs of tile j+1,
 // and barrier setup / TMEM allocation are paid once per SM instead of once per tile.  Activations on MMA-M only.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, PTTS_GEMM_MINBLOCKS)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w,
                           const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];

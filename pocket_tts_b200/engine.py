@@ -45,7 +45,7 @@ class Voice:
 class Engine:
     def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
                  kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True, int8_weights: bool = False,
-                 int8_storage: bool = True, lm_step_kernel: bool = True):
+                 int8_storage: bool = True, lm_step_kernel: bool | None = None):
         L = _lib.lib()
         self._keep = []
         descs = (TensorDesc * len(weights))()
@@ -64,7 +64,8 @@ class Engine:
         cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, int(int8_weights), int(cuda_graph), debug_gemm
         cfg.reserved[0] = gemm_mode
         cfg.reserved[7] = 0 if int8_storage else 1  # test hook: int8 mode streaming f16 copies of the codes instead of bytes
-        cfg.reserved[8] = 0 if lm_step_kernel else 1  # test hook: the per-layer launches instead of the persistent FlowLM step kernel
+        # the persistent FlowLM step kernel (csrc/lm_step.cuh): None = the library's default, True / False = force
+        cfg.reserved[8] = 0 if lm_step_kernel is None else (2 if lm_step_kernel else 1)
         h = C.c_void_p()
         check(L.ptts_engine_create(C.byref(cfg), descs, len(weights), C.byref(h)))
         self._h = h

@@ -15,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     from pocket_tts_b200.engine import Engine, StreamSpec
     n = int(sys.argv[2])
     w = synth.make_weights(1234)
-    eng = Engine(w, max_slots=max(n, 2), kv_capacity=256)
+    eng = Engine(w, max_slots=max(n, 2), kv_capacity=256, lm_step_kernel=True)
     voice = eng.voice_from_prompt(synth.make_voice_prompt(23, seed=7))
     specs = [StreamSpec(synth.make_tokens(5 + (i % 7), seed=100 + i), 4, 0, 1e30, noise=synth.make_noise(4, seed=200 + i)) for i in range(n)]
     slots = eng.open_streams([voice] * n, specs)

@@ -11,7 +11,7 @@ from pocket_tts_b200.engine import Engine, StreamSpec  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-eng = Engine(synth.make_weights(1234), max_slots=n, kv_capacity=256)
+eng = Engine(synth.make_weights(1234), max_slots=n, kv_capacity=256, lm_step_kernel=True)
 voice = eng.voice_from_prompt(synth.make_voice_prompt(87, seed=7))
 specs = [StreamSpec(synth.make_tokens(40, seed=100 + i), 200, 0, 1e30, temp=0.7, seed=i) for i in range(n)]
 slots = eng.open_streams([voice] * n, specs)
