@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PTTS_ABI_VERSION 1
+#define PTTS_ABI_VERSION 2
 
 typedef enum {
   PTTS_OK = 0,
@@ -62,7 +62,7 @@ typedef struct {
   int32_t weight_mode;     /* ptts_weight_mode */
   int32_t use_cuda_graph;  /* capture the decode step per batch bucket */
   int32_t debug_gemm;      /* 0 = tcgen05 path; 1 = SIMT cross-check kernel (tests only) */
-  int32_t reserved[9];
+  int32_t reserved[9];     /* zero in production; test switches documented in ptts_internal.h */
 } ptts_engine_cfg;
 
 typedef struct ptts_engine ptts_engine;
@@ -76,7 +76,8 @@ typedef struct {
   int32_t frames_after_eos;  /* estimate_frames_after_eos, tts_model.rs:1230-1237 */
   float eos_threshold;       /* config.rs:123, default -4.0 */
   float temp;                /* config.rs:120, default 0.7; used only when noise == NULL */
-  uint64_t seed;             /* device Philox stream when noise == NULL */
+  uint64_t seed;             /* seed of the device generator when noise == NULL: counter-based (hash of seed, frame,
+                                lane -> two uniforms -> Box-Muller), one N(0, temp) draw per latent value per frame */
   const float* noise;        /* optional [max_gen_len, 32] injected x_0 per frame, already
                                 scaled by sqrt(temp) (reference draws it at flow_lm.rs:148-153) */
 } ptts_stream_params;
@@ -114,6 +115,21 @@ int32_t ptts_audio_prompt_from_pcm(ptts_engine* e, const float* pcm24k, int32_t 
 void ptts_voice_destroy(ptts_engine* e, ptts_voice* v);
 int32_t ptts_voice_len(const ptts_voice* v);
 
+/* Voice-state safetensors.  The reference's voice files hold one tensor, `audio_prompt` f32 [1,T,1024]
+ * (tts_model.rs:467-487, pocket-tts-cli voice.rs:122-131); ptts_voice_load reads exactly that (F32 / F16 / BF16) and
+ * runs the prefill like ptts_voice_from_prompt.  ptts_voice_save writes `audio_prompt` and, with include_kv != 0, also
+ * the prefilled FlowLM KV rows as `flow_lm_kv` f16 [6,2,16,T,64] -- the reference never serialises its ModelState; a
+ * file with that tensor loads without running the prefill again (the file stays a valid voice file for the reference,
+ * which ignores unknown keys). */
+int32_t ptts_voice_save(ptts_engine* e, const ptts_voice* v, const char* path, int32_t include_kv);
+int32_t ptts_voice_load(ptts_engine* e, const char* path, ptts_voice** out);
+
+/* Replaces load_config + the dimension checks of TTSModel::from_config (config.rs:111, tts_model.rs:182-426): reads a
+ * model YAML (crates/pocket-tts/config/b6369a24.yaml) and verifies every dimension this library is compiled for
+ * (FlowLM 1024 x 16 heads x 6 layers, flow head 512 x 6, Mimi 512 x 8 heads x 2 layers, context 250, SEANet ratios
+ * [6,5,4], 24 kHz, 12.5 fps, 4000 bins, latent 32).  PTTS_ERR_INVALID names the first mismatch.  No device needed. */
+int32_t ptts_config_check(const char* yaml_path);
+
 /* Replaces the head of TTSModel::generate_stream_segment (tts_model.rs:935-1004) for n
  * streams at once: clone voice state, embed tokens (conditioners/text.rs:289-303), text
  * prefill (tts_model.rs:958-964).  tokens are concatenated, token_offsets has n+1 entries.
@@ -145,10 +161,14 @@ int32_t ptts_step(ptts_engine* e, const int32_t* slots, int32_t n, float* pcm_ou
  * tickets in flight.  ptts_step == begin + flags + pcm. */
 #define PTTS_STEP_PCM 1
 #define PTTS_STEP_AHEAD 2
+#define PTTS_STEP_PCM_I16 4  /* read the frame back as i16 instead (ptts_step_pcm_i16): the reference's wire format,
+                                audio.rs:129-146 pcm_i16_le_bytes = clamp to [-1, 1], * 32767, truncating cast, packed by
+                                the last SEANet conv on the device; half the bytes of the f32 frame */
 #define PTTS_FRAME_OVERRUN 2 /* finished[] value: this frame lies past the stream's last one */
 int64_t ptts_step_begin(ptts_engine* e, const int32_t* slots, int32_t n, int32_t flags);
 int32_t ptts_step_flags(ptts_engine* e, int64_t ticket, uint8_t* finished, float* latent_out, float* eos_logit_out);
 int32_t ptts_step_pcm(ptts_engine* e, int64_t ticket, float* pcm_out);
+int32_t ptts_step_pcm_i16(ptts_engine* e, int64_t ticket, int16_t* pcm_out);
 
 /* Same step with every buffer resident on the device (no host copies, no sync): used to time the
  * kernels alone.  pcm_dev may be NULL to keep the PCM in the engine's own buffer. */
@@ -158,49 +178,40 @@ int32_t ptts_sync(ptts_engine* e);
 /* Teacher forcing for parity tests: overrides the latent fed back into FlowLM at the next
  * step of `slot` (the reference feeds next_latent back at tts_model.rs:1065). */
 int32_t ptts_stream_set_feedback(ptts_engine* e, int32_t slot, const float* latent32);
+/* Closing is host bookkeeping only (no device synchronisation): work already enqueued for the slot completes, and a
+ * later open of the same slot orders itself behind it on the device.  A slot listed by a step whose flags have not been
+ * fetched cannot be closed (PTTS_ERR_STATE). */
 int32_t ptts_stream_close(ptts_engine* e, int32_t slot);
+int32_t ptts_streams_close(ptts_engine* e, const int32_t* slots, int32_t n);
 int32_t ptts_stream_frames(ptts_engine* e, int32_t slot, int32_t* frames_out, int32_t* eos_step_out);
 
-/* Parity taps: copy a named intermediate of the last step for batch row `row`
- * (e.g. "flowlm.h", "mimi.after_upsample", "mimi.after_decoder_transformer", "seanet.convtr2").
- * Returns the number of floats written or a negative status. */
-int64_t ptts_debug_read(ptts_engine* e, const char* name, int32_t row, float* out, int64_t cap);
-
-/* Device-time accounting for bench.py: kernel launches issued by the engine since the last reset,
- * and CUDA-event time (ms) of the stages of the most recent ptts_step_timed call. */
-int64_t ptts_launch_count(ptts_engine* e, int32_t reset);
-int32_t ptts_step_timed(ptts_engine* e, const int32_t* slots, int32_t n, float* stage_ms /*[8]*/);
-void* ptts_cuda_stream(ptts_engine* e);
-/* Per-launch CUDA-event profile for bench.py's roofline line.  While enabled every kernel launch is
- * bracketed by events on the engine's stream; the report has one text line per kernel class:
- * "<class> <launches> <total_ms> <algorithmic_bytes> <algorithmic_flops>".  Returns the string length. */
-int32_t ptts_profile_enable(ptts_engine* e, int32_t on);
-int64_t ptts_profile_report(ptts_engine* e, char* buf, int64_t cap);
-/* Event time (ms) of an empty kernel bracketed the same way: the fixed cost inside every per-launch figure. */
-int32_t ptts_profile_overhead(ptts_engine* e, float* ms_out);
-
-/* Isolated kernel entry points (tests/test_kernels_gpu.py): D[r,f] = sum_k A[r,k] * W[f,k] on
- * host f32 buffers, run through the production GEMM (operands converted to f16).  mode 0 lets the
- * engine choose the tiling, 1 forces activation-as-M, 2 forces weight-as-M (swap-AB);
- * split_k > 1 exercises the cluster split-K epilogue (partials summed over DSMEM in rank order, no atomics). */
-int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const float* bias, float* d, int32_t rows,
-                       int32_t feats, int32_t k, int32_t mode, int32_t split_k, int32_t act, int32_t use_simt);
-/* The int8 weight path of the decode (swap-AB) GEMM: w is quantised per tensor with the reference's scheme
- * (crates/pocket-tts/src/quantize.rs:65-94: scale = absmax / 127, codes clamp(round(w / scale), -127, 127)),
- * D = (A . codes^T) * scale.  storage 1 streams one-byte codes from HBM and expands them in shared memory
- * (production), 0 streams an f16 copy of the same codes; both must give bit-identical D.  scale_out gets the scale. */
-int32_t ptts_test_gemm_int8(int32_t device, const float* a, const float* w, float* d, int32_t rows, int32_t feats,
-                            int32_t k, int32_t split_k, int32_t storage, float* scale_out);
-/* Bring-up probe: back-to-back launches of one GEMM with per-CTA %globaltimer stamps (10 per CTA, ns). */
-int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_t k, int32_t mode, int32_t split_k,
-                             int32_t iters, float* us_per_launch, int64_t* stamps, int32_t max_ctas, int32_t* n_ctas);
-/* Implicit-GEMM streaming convs on host buffers, channels-last x [n, t, cin], state [n, k-1 (or 1), cin]. */
-int32_t ptts_test_conv1d(int32_t device, const float* x, const float* prev, const float* w /*[cout,cin,k]*/,
-                         const float* bias, float* y /*[n,t,cout]*/, int32_t n, int32_t t, int32_t cin, int32_t cout,
-                         int32_t k);
-int32_t ptts_test_convtr1d(int32_t device, const float* x, const float* prev_row, const float* w /*[cin,cout,2s]*/,
-                           const float* bias, float* y /*[n,t*s,cout]*/, int32_t n, int32_t t, int32_t cin,
-                           int32_t cout, int32_t stride);
+/* Continuous batching of many long-form requests inside the library (BASELINE configs[4]: thousands of concurrent 60 s
+ * requests with [pause:Xms]).  Replaces the loop of TTSModel::generate_stream_long (tts_model.rs:1074-1127) over
+ * generate_stream (tts_model.rs:894-913) for a whole population of requests: a request is an ordered list of segments,
+ * PTTS_SEG_TEXT (one <= 50-token chunk: tokens + per-segment parameters, exactly what ptts_streams_open takes) or
+ * PTTS_SEG_PAUSE (host silence of pause_ms, pause.rs:183-185 = ms * 24 samples).  The chunks of one request run one after
+ * the other, each restarting from the voice state, while different requests fill the batch; whenever streams finish the
+ * next chunks are opened together (one packed open, one batched prefill) and join the next step; the device is kept one
+ * step ahead of the host (PTTS_STEP_AHEAD).  ptts_sched_run returns when every submitted request is complete; the PCM
+ * of a request (all its segments concatenated, f32 or i16 as chosen at run) is then read with ptts_sched_result. */
+typedef struct ptts_sched ptts_sched;
+#define PTTS_SEG_TEXT 0
+#define PTTS_SEG_PAUSE 1
+typedef struct {
+  int32_t kind;               /* PTTS_SEG_TEXT | PTTS_SEG_PAUSE */
+  int32_t n_tokens;           /* text */
+  const int32_t* tokens;      /* text: n_tokens ids (copied at submit) */
+  ptts_stream_params params;  /* text (params.noise is copied at submit when not NULL) */
+  int32_t pause_ms;           /* pause */
+  int32_t reserved;
+} ptts_segment;
+int32_t ptts_sched_create(ptts_engine* e, ptts_voice* voice, int32_t max_batch, ptts_sched** out);
+void ptts_sched_destroy(ptts_sched* s);
+int64_t ptts_sched_submit(ptts_sched* s, const ptts_segment* segments, int32_t n_segments); /* -> request id >= 0 */
+int32_t ptts_sched_run(ptts_sched* s, int32_t pcm_i16);
+int64_t ptts_sched_result_samples(const ptts_sched* s, int64_t request);
+int32_t ptts_sched_result(const ptts_sched* s, int64_t request, void* pcm_out, int64_t cap_samples);
+int64_t ptts_sched_steps(const ptts_sched* s); /* decode steps the last run took */
 
 #ifdef __cplusplus
 }

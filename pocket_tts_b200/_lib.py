@@ -7,14 +7,23 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "libptts_cuda.so"
 
-# every symbol include/ptts.h declares (tests/test_abi.py checks the header against this list)
-SYMBOLS = [
-    "ptts_last_error", "ptts_abi_version", "ptts_engine_create", "ptts_engine_destroy",
-    "ptts_engine_set_lsd_steps", "ptts_voice_from_prompt", "ptts_voice_from_pcm", "ptts_audio_prompt_from_pcm", "ptts_voice_destroy", "ptts_voice_len",
-    "ptts_streams_open", "ptts_step", "ptts_step_begin", "ptts_step_flags", "ptts_step_pcm", "ptts_step_device", "ptts_sync", "ptts_stream_set_feedback",
-    "ptts_stream_close", "ptts_stream_frames", "ptts_debug_read", "ptts_launch_count", "ptts_step_timed",
-    "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report", "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
+# every symbol include/ptts.h (product ABI) and include/ptts_internal.h (test hooks, probes) declare; tests/test_abi.py
+# checks both headers against these lists
+PRODUCT_SYMBOLS = [
+    "ptts_last_error", "ptts_abi_version", "ptts_engine_create", "ptts_engine_destroy", "ptts_engine_set_lsd_steps",
+    "ptts_voice_from_prompt", "ptts_voice_from_pcm", "ptts_audio_prompt_from_pcm", "ptts_voice_destroy", "ptts_voice_len",
+    "ptts_voice_save", "ptts_voice_load", "ptts_config_check",
+    "ptts_streams_open", "ptts_step", "ptts_step_begin", "ptts_step_flags", "ptts_step_pcm", "ptts_step_pcm_i16", "ptts_step_device",
+    "ptts_sync", "ptts_stream_set_feedback", "ptts_stream_close", "ptts_streams_close", "ptts_stream_frames",
+    "ptts_sched_create", "ptts_sched_destroy", "ptts_sched_submit", "ptts_sched_run", "ptts_sched_result_samples", "ptts_sched_result",
+    "ptts_sched_steps",
 ]
+INTERNAL_SYMBOLS = [
+    "ptts_debug_read", "ptts_launch_count", "ptts_step_timed", "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report",
+    "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
+    "ptts_test_noise", "ptts_debug_f16_overflow",
+]
+SYMBOLS = PRODUCT_SYMBOLS + INTERNAL_SYMBOLS
 
 
 class TensorDesc(C.Structure):
@@ -31,6 +40,11 @@ class EngineCfg(C.Structure):
 class StreamParams(C.Structure):
     _fields_ = [("max_gen_len", C.c_int32), ("frames_after_eos", C.c_int32), ("eos_threshold", C.c_float),
                 ("temp", C.c_float), ("seed", C.c_uint64), ("noise", C.c_void_p)]
+
+
+class Segment(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_tokens", C.c_int32), ("tokens", C.c_void_p), ("params", StreamParams),
+                ("pause_ms", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -84,6 +98,24 @@ def lib() -> C.CDLL:
     L.ptts_test_gemm_trace.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]
     L.ptts_test_conv1d.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
     L.ptts_test_convtr1d.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
+    L.ptts_voice_save.argtypes = [vp, vp, C.c_char_p, i32]
+    L.ptts_voice_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.ptts_config_check.argtypes = [C.c_char_p]
+    L.ptts_step_pcm_i16.argtypes = [vp, i64, vp]
+    L.ptts_streams_close.argtypes = [vp, vp, i32]
+    L.ptts_sched_create.argtypes = [vp, vp, i32, C.POINTER(vp)]
+    L.ptts_sched_destroy.argtypes = [vp]
+    L.ptts_sched_destroy.restype = None
+    L.ptts_sched_submit.argtypes = [vp, C.POINTER(Segment), i32]
+    L.ptts_sched_submit.restype = i64
+    L.ptts_sched_run.argtypes = [vp, i32]
+    L.ptts_sched_result_samples.argtypes = [vp, i64]
+    L.ptts_sched_result_samples.restype = i64
+    L.ptts_sched_result.argtypes = [vp, i64, vp, i64]
+    L.ptts_sched_steps.argtypes = [vp]
+    L.ptts_sched_steps.restype = i64
+    L.ptts_test_noise.argtypes = [i32, C.c_uint64, i32, vp]
+    L.ptts_debug_f16_overflow.argtypes = [vp, C.POINTER(i64)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:  # default: status code

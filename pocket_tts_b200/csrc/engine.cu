@@ -8,6 +8,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <fstream>
+#include <sstream>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -15,6 +17,7 @@
 #include "flow_head.cuh"
 #include "gemm.cuh"
 #include "host_util.h"
+#include "../../include/ptts_internal.h"
 #include "kernels.cuh"
 #include "lm_step.cuh"
 
@@ -79,6 +82,7 @@ static float bf16_to_f32(uint16_t v) { uint32_t u = (uint32_t)v << 16; float f; 
 struct Voice {
   DevBuf<__half> kv;  // [layer][k|v][head][len][64]
   int len = 0;
+  std::vector<float> prompt;  // the conditioning rows [len][1024] the KV was built from (`audio_prompt`, for ptts_voice_save)
 };
 
 struct SlotHost {
@@ -89,7 +93,6 @@ struct SlotHost {
   int own_len = 0;
   int max_gen_len = 0;
   Voice* voice = nullptr;
-  DevBuf<float> noise;
 };
 
 struct Engine {
@@ -198,6 +201,15 @@ struct Engine {
   DevBuf<__half> mh16, mattn16, mffn16;
   DevBuf<__half> tr16, a0, e2, h3, a3, e5, h6, a6, e8, h9, a9;
   DevBuf<float> x2, x5, x8, pcm;
+  DevBuf<short> pcm16;          // the same frame as i16 (audio.rs:129-146), written by the last SEANet conv
+  short* pin_pcm16[3] = {};
+  // stream open: pinned records -> one copy -> scatter kernel; injected noise in per-slot buffers that only grow (a
+  // cudaFree per close would be a device-wide synchronisation)
+  DevBuf<OpenRec> open_recs;
+  OpenRec* pin_open[2] = {};
+  cudaEvent_t ev_open[2] = {};
+  int open_parity = 0;
+  std::vector<DevBuf<float>> noise_pool;
   // per-step host-visible results in ONE buffer ([NB][32] latents | [NB] EOS logits | [NB] finished bytes) so that a
   // step's flags reach the host with one D2H copy on the language-model stream instead of three
   DevBuf<SeqDesc> row_desc;    // [NB] per batch row: KV descriptor + cursor of its stream, rebuilt by step_begin_kernel
@@ -217,7 +229,7 @@ struct Engine {
   float* pin_pcm[NT] = {}; unsigned char* pin_fin[NT] = {};
   float* pin_lat[NT] = {}; float* pin_logit[NT] = {};
   cudaEvent_t ev_flags[NT] = {}, ev_pcm[NT] = {};
-  struct Ticket { long long id = -1; int n = 0; bool flags_done = true, pcm_done = true, want_pcm = false; std::vector<int> slot_ids; };
+  struct Ticket { long long id = -1; int n = 0; bool flags_done = true, pcm_done = true, want_pcm = false, want_i16 = false; std::vector<int> slot_ids; };
   Ticket tickets[NT];
   // a ticket whose flags have not been fetched still lists its slots: closing / reopening one of them in between would make
   // step_flags_impl book the overrun row of the OLD stream onto the NEW one
@@ -264,10 +276,12 @@ struct Engine {
 Engine::~Engine() {
   for (int i = 0; i < NT; ++i) {
     if (pin_pcm[i]) cudaFreeHost(pin_pcm[i]);
+    if (pin_pcm16[i]) cudaFreeHost(pin_pcm16[i]);
     if (pin_lat[i]) cudaFreeHost(pin_lat[i]);  // pin_logit / pin_fin point into it
     if (ev_flags[i]) cudaEventDestroy(ev_flags[i]);
     if (ev_pcm[i]) cudaEventDestroy(ev_pcm[i]);
   }
+  for (int i = 0; i < 2; ++i) { if (pin_open[i]) cudaFreeHost(pin_open[i]); if (ev_open[i]) cudaEventDestroy(ev_open[i]); }
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   for (auto& e : prof_pool) cudaEventDestroy(e);
   for (auto& g : graphs) { cudaGraphExecDestroy(g.second.a); cudaGraphExecDestroy(g.second.b); }
@@ -738,6 +752,13 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   h6.alloc((size_t)NB * 480 * 64); a6.alloc((size_t)NB * 481 * 128); x8.alloc((size_t)NB * 1920 * 64);
   e8.alloc((size_t)NB * 1922 * 64); h9.alloc((size_t)NB * 1920 * 64); a9.alloc((size_t)NB * 1922 * 64);
   pcm.alloc((size_t)NB * FRAME);
+  pcm16.alloc((size_t)NB * FRAME);
+  open_recs.alloc(NS);
+  for (int i = 0; i < 2; ++i) {
+    PTTS_CUDA(cudaMallocHost(&pin_open[i], (size_t)NS * sizeof(OpenRec)));
+    PTTS_CUDA(cudaEventCreateWithFlags(&ev_open[i], cudaEventDisableTiming));
+  }
+  noise_pool.resize(NS);
   step_out.alloc(step_out_bytes());
   row_desc.alloc(NB);
   latent_out.p = reinterpret_cast<float*>(step_out.p);
@@ -757,6 +778,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   prow_seq.alloc(PR); prow_pos.alloc(PR); ptokens.alloc(PR);
   for (int i = 0; i < NT; ++i) {
     PTTS_CUDA(cudaMallocHost(&pin_pcm[i], (size_t)NB * FRAME * 4));
+    PTTS_CUDA(cudaMallocHost(&pin_pcm16[i], (size_t)NB * FRAME * 2));
     PTTS_CUDA(cudaMallocHost(&pin_lat[i], step_out_bytes()));  // same layout as step_out
     pin_logit[i] = pin_lat[i] + (size_t)NB * LDIM;
     pin_fin[i] = reinterpret_cast<unsigned char*>(pin_logit[i] + NB);
@@ -959,7 +981,7 @@ void Engine::upload_rows(const int* slot_ids, int n) {
     step_kv_bytes += (double)((sh.voice ? sh.voice->len : 0) + sh.own_len + 1) * N_HEADS * HD * 2 * 2;
   }
   if ((int)row_seq_host.size() == n && std::equal(slot_ids, slot_ids + n, row_seq_host.begin())) return;
-  PTTS_CUDA(cudaStreamSynchronize(stream_b));  // the codec stream may still be reading the previous batch map
+  PTTS_CUDA(cudaStreamWaitEvent(stream, ev_b_done, 0));  // the codec stream may still be reading the previous batch map
   row_seq_host.assign(slot_ids, slot_ids + n);
   PTTS_CUDA(cudaMemcpyAsync(row_seq.p, row_seq_host.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
 }
@@ -1238,7 +1260,7 @@ void Engine::step_part_b(int n, bool marks) {
   e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(1920, 64, 1922 * 64, 128);
   tag("seanet.res9b"); gemm(ActView{h9.p, 64, 1920, NB}, n, 1920, 1, 128, 1, s_r9b, 64, e);
   { ProfScope ps(*this, "seanet.final_conv", (double)n * (1922.0 * 128 + 1920 * 4), 2.0 * n * 1920 * 192);
-    launch_k(use_pdl, seanet_final_conv_kernel, dim3((FRAME + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, pcm.p); }
+    launch_k(use_pdl, seanet_final_conv_kernel, dim3((FRAME + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, pcm.p, pcm16.p); }
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
     launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, segs, row_seq.p, 1); }
 }
@@ -1509,6 +1531,7 @@ int32_t ptts_voice_from_prompt(ptts_engine* h, const float* audio_prompt, int32_
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
   std::unique_ptr<ptts_voice> v(new ptts_voice);
   v->v.len = n_rows;
+  v->v.prompt.assign(audio_prompt, audio_prompt + (size_t)n_rows * D_MODEL);
   v->v.kv.alloc((size_t)N_LAYERS * 2 * N_HEADS * n_rows * HD);
   SeqDesc sd{v->v.kv.p, nullptr, n_rows, 0, 0, 0};
   PTTS_CUDA(cudaMemcpyAsync(e.seqs.p + e.NS, &sd, sizeof sd, cudaMemcpyHostToDevice, e.stream));
@@ -1564,15 +1587,13 @@ void ptts_voice_destroy(ptts_engine* h, ptts_voice* v) {
 
 int32_t ptts_voice_len(const ptts_voice* v) { return v ? v->v.len : -1; }
 
-int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, const int32_t* tokens,
-                          const int32_t* token_offsets, const ptts_stream_params* params, int32_t* slots_out) {
-  PTTS_TRY
-  PTTS_REQUIRE(h && voices && tokens && token_offsets && params && slots_out && n >= 1, PTTS_ERR_INVALID,
-               "ptts_streams_open: null argument");
-  Engine& e = h->e;
-  PTTS_CUDA(cudaSetDevice(e.cfg.device));
-  PTTS_CUDA(cudaStreamSynchronize(e.stream_b));  // a recycled slot's codec state may still be in use
-  // validate everything before touching state
+// Opens n streams: validates everything, claims free slots, stages one record per stream in pinned memory, ONE copy,
+// one scatter kernel (KV descriptor, control block, cursor, BOS feedback, zeroed streaming state), then the batched text
+// prefill.  No host synchronisation: a recycled slot's last codec frame may still be running on the codec stream, so the
+// language-model stream waits for it on the device (ev_b_done), and every host buffer is either pinned and owned by the
+// engine until the next open or pageable (staged by the runtime before cudaMemcpyAsync returns).
+static void streams_open_impl(Engine& e, int n, ptts_voice* const* voices, const int32_t* tokens, const int32_t* token_offsets,
+                              const ptts_stream_params* params, int32_t* slots_out) {
   std::vector<int> free_slots;
   for (int s = 0; s < e.NS && (int)free_slots.size() < n; ++s) if (!e.slots[s].in_use) free_slots.push_back(s);
   PTTS_REQUIRE((int)free_slots.size() == n, PTTS_ERR_CAPACITY, "%d streams requested, %zu slots free", n, free_slots.size());
@@ -1586,16 +1607,18 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
     for (int j = token_offsets[i]; j < token_offsets[i + 1]; ++j)
       PTTS_REQUIRE(tokens[j] >= 0 && tokens[j] <= N_BINS, PTTS_ERR_INVALID, "stream %d: token id %d out of range", i, tokens[j]);
   }
+  // the records staged two opens ago must have left this pinned buffer (long done in practice), and the codec stream must
+  // be done with the slots being recycled (ordered on the device)
+  const int ob = e.open_parity;
+  e.open_parity ^= 1;
+  PTTS_CUDA(cudaEventSynchronize(e.ev_open[ob]));
+  PTTS_CUDA(cudaStreamWaitEvent(e.stream, e.ev_b_done, 0));
   const size_t per_slot_kv = (size_t)N_LAYERS * 2 * N_HEADS * e.KVCAP * HD;
-  // from here on slots are claimed: a failure part-way (allocation, copy, launch) releases every slot claimed so far,
-  // because the caller has no ids yet with which to close them
+  // from here on slots are claimed: a failure part-way releases every slot claimed so far (the caller has no ids yet)
   struct Rollback {
     Engine& e; const std::vector<int>& ids; bool armed = true;
     ~Rollback() { if (armed) { cudaStreamSynchronize(e.stream); for (int s : ids) e.slots[s] = SlotHost{}; e.row_seq_host.clear(); } }
   } rollback{e, free_slots};
-  std::vector<SeqDesc> sds(n);
-  std::vector<StreamCtl> ctls(n);
-  std::vector<int> lens(n);
   for (int i = 0; i < n; ++i) {
     const int s = free_slots[i];
     SlotHost& sh = e.slots[s];
@@ -1604,27 +1627,26 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
     sh.in_use = true; sh.voice = &voices[i]->v; sh.own_len = nt; sh.max_gen_len = params[i].max_gen_len;
     const float* noise_dev = nullptr;
     if (params[i].noise) {
-      sh.noise.alloc((size_t)params[i].max_gen_len * LDIM);
-      PTTS_CUDA(cudaMemcpyAsync(sh.noise.p, params[i].noise, sh.noise.n * 4, cudaMemcpyHostToDevice, e.stream));
-      noise_dev = sh.noise.p;
+      DevBuf<float>& nb = e.noise_pool[s];
+      const size_t need = (size_t)params[i].max_gen_len * LDIM;
+      if (nb.n < need) { PTTS_CUDA(cudaStreamSynchronize(e.stream_b)); nb.alloc(need); }  // grow only; never freed at close
+      PTTS_CUDA(cudaMemcpyAsync(nb.p, params[i].noise, need * 4, cudaMemcpyHostToDevice, e.stream));
+      noise_dev = nb.p;
     }
-    sds[i] = SeqDesc{e.kv.p + (size_t)s * per_slot_kv, sh.voice->kv.p, e.KVCAP, sh.voice->len, sh.voice->len, 0};
-    ctls[i] = StreamCtl{params[i].max_gen_len, params[i].frames_after_eos, params[i].eos_threshold, params[i].temp,
-                        (unsigned long long)params[i].seed, noise_dev, 0, -1, 0, 0};
-    lens[i] = nt;
-    PTTS_CUDA(cudaMemcpyAsync(e.seqs.p + s, &sds[i], sizeof(SeqDesc), cudaMemcpyHostToDevice, e.stream));
-    PTTS_CUDA(cudaMemcpyAsync(e.ctl.p + s, &ctls[i], sizeof(StreamCtl), cudaMemcpyHostToDevice, e.stream));
-    PTTS_CUDA(cudaMemcpyAsync(e.own_len.p + s, &lens[i], sizeof(int), cudaMemcpyHostToDevice, e.stream));
-    PTTS_CUDA(cudaMemcpyAsync(e.feedback.p + (size_t)s * LDIM, e.bos.p, LDIM * 4, cudaMemcpyDeviceToDevice, e.stream));
+    OpenRec& r = e.pin_open[ob][i];
+    r.sd = SeqDesc{e.kv.p + (size_t)s * per_slot_kv, sh.voice->kv.p, e.KVCAP, sh.voice->len, sh.voice->len, 0};
+    r.ctl = StreamCtl{params[i].max_gen_len, params[i].frames_after_eos, params[i].eos_threshold, params[i].temp,
+                      (unsigned long long)params[i].seed, noise_dev, 0, -1, 0, 0};
+    r.slot = s; r.own_len = nt; r.pad[0] = r.pad[1] = 0;
     slots_out[i] = s;
   }
-  // zero the streaming state of the new slots (slot list staged through the prefill row buffer)
-  PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, free_slots.data(), n * 4, cudaMemcpyHostToDevice, e.stream));
+  PTTS_CUDA(cudaMemcpyAsync(e.open_recs.p, e.pin_open[ob], (size_t)n * sizeof(OpenRec), cudaMemcpyHostToDevice, e.stream));
+  PTTS_CUDA(cudaEventRecord(e.ev_open[ob], e.stream));
   for (int off = 0; off < n; off += 32768) {
     const int cnt = std::min(32768, n - off);
-    launch_k(e.use_pdl, slot_reset_kernel, dim3(cnt, 9), 128, 0, e.stream, 1, e.segs, e.up_partial.p, e.prow_seq.p + off);
+    launch_k(e.use_pdl, slot_open_kernel, dim3(cnt, 10), 128, 0, e.stream, 1, (const OpenRec*)(e.open_recs.p + off), e.segs, e.up_partial.p,
+             e.seqs.p, e.ctl.p, e.own_len.p, e.feedback.p, (const float*)e.bos.p);
   }
-  PTTS_CUDA(cudaStreamSynchronize(e.stream));
   // text prefill in groups of at most PR rows (reference tts_model.rs:944-964)
   int i0 = 0;
   while (i0 < n) {
@@ -1641,12 +1663,20 @@ int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, 
       { ProfScope ps(e, "prefill.embed", (double)rows * 1024 * 8, 0);
         launch_k(e.use_pdl, embed_rows_kernel, rows, 256, 0, e.stream, 1, e.ptokens.p, rows, e.lut.p, e.px32.p); }
       e.prefill(rows);
-      PTTS_CUDA(cudaStreamSynchronize(e.stream));
     }
     i0 = i1;
   }
   e.row_seq_host.clear();
   rollback.armed = false;
+}
+
+int32_t ptts_streams_open(ptts_engine* h, int32_t n, ptts_voice* const* voices, const int32_t* tokens,
+                          const int32_t* token_offsets, const ptts_stream_params* params, int32_t* slots_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && voices && tokens && token_offsets && params && slots_out && n >= 1, PTTS_ERR_INVALID,
+               "ptts_streams_open: null argument");
+  PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+  streams_open_impl(h->e, n, voices, tokens, token_offsets, params, slots_out);
   return PTTS_OK;
   PTTS_CATCH
 }
@@ -1668,7 +1698,8 @@ static void check_slots(Engine& e, const int32_t* slot_ids, int n, int steps_in_
 
 // ---- pipelined step: begin (enqueue) / flags (language-model results) / pcm (codec result)
 static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, int flags) {
-  const bool want_pcm = (flags & PTTS_STEP_PCM) != 0, ahead = (flags & PTTS_STEP_AHEAD) != 0;
+  const bool want_i16 = (flags & PTTS_STEP_PCM_I16) != 0;
+  const bool want_pcm = (flags & PTTS_STEP_PCM) != 0 || want_i16, ahead = (flags & PTTS_STEP_AHEAD) != 0;
   const long long id = e.next_ticket;
   Engine::Ticket& t = e.tickets[id % Engine::NT];
   PTTS_REQUIRE(t.flags_done && t.pcm_done, PTTS_ERR_STATE, "step %lld still has unfetched results (three steps may be in flight)", t.id);
@@ -1682,9 +1713,10 @@ static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, int 
   const int par = (int)(id % Engine::NT);
   PTTS_CUDA(cudaMemcpyAsync(e.pin_lat[par], e.step_out.p, e.step_out_bytes(), cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaEventRecord(e.ev_flags[par], e.stream));
-  if (want_pcm) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm[par], e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream_b));
+  if (want_i16) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm16[par], e.pcm16.p, (size_t)n * FRAME * 2, cudaMemcpyDeviceToHost, e.stream_b));
+  else if (want_pcm) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm[par], e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream_b));
   PTTS_CUDA(cudaEventRecord(e.ev_pcm[par], e.stream_b));
-  t.id = id; t.n = n; t.flags_done = false; t.pcm_done = false; t.want_pcm = want_pcm;
+  t.id = id; t.n = n; t.flags_done = false; t.pcm_done = false; t.want_pcm = want_pcm; t.want_i16 = want_i16;
   t.slot_ids.assign(slot_ids, slot_ids + n);
   e.next_ticket = id + 1;
   return id;
@@ -1712,14 +1744,18 @@ static void step_flags_impl(Engine& e, long long id, uint8_t* finished, float* l
   t.flags_done = true;
 }
 
-static void step_pcm_impl(Engine& e, long long id, float* pcm_out) {
+static void step_pcm_impl(Engine& e, long long id, float* pcm_out, int16_t* pcm16_out = nullptr) {
   Engine::Ticket& t = e.tickets[id % Engine::NT];
   PTTS_REQUIRE(id >= 0 && t.id == id && !t.pcm_done, PTTS_ERR_STATE, "ticket %lld has no pending PCM", id);
   const int par = (int)(id % Engine::NT);
   PTTS_CUDA(cudaEventSynchronize(e.ev_pcm[par]));
   if (pcm_out) {
-    PTTS_REQUIRE(t.want_pcm, PTTS_ERR_STATE, "step %lld was begun without PCM read-back", id);
+    PTTS_REQUIRE(t.want_pcm && !t.want_i16, PTTS_ERR_STATE, "step %lld was not begun with PTTS_STEP_PCM", id);
     std::memcpy(pcm_out, e.pin_pcm[par], (size_t)t.n * FRAME * 4);
+  }
+  if (pcm16_out) {
+    PTTS_REQUIRE(t.want_i16, PTTS_ERR_STATE, "step %lld was not begun with PTTS_STEP_PCM_I16", id);
+    std::memcpy(pcm16_out, e.pin_pcm16[par], (size_t)t.n * FRAME * 2);
   }
   t.pcm_done = true;
 }
@@ -1752,6 +1788,15 @@ int32_t ptts_step_pcm(ptts_engine* h, int64_t ticket, float* pcm_out) {
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
   PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
   step_pcm_impl(h->e, ticket, pcm_out);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_step_pcm_i16(ptts_engine* h, int64_t ticket, int16_t* pcm_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  PTTS_CUDA(cudaSetDevice(h->e.cfg.device));
+  step_pcm_impl(h->e, ticket, nullptr, pcm_out);
   return PTTS_OK;
   PTTS_CATCH
 }
@@ -1858,16 +1903,27 @@ int32_t ptts_stream_set_feedback(ptts_engine* h, int32_t slot, const float* late
   PTTS_CATCH
 }
 
+// Closing is host bookkeeping: nothing of a slot is freed (its injected-noise buffer belongs to a pool), kernels already
+// enqueued for it run to completion, and the next open of the slot orders itself behind them on the device.
+static void stream_close_impl(Engine& e, int slot) {
+  PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
+  PTTS_REQUIRE(!e.slot_in_pending_ticket(slot), PTTS_ERR_STATE, "slot %d is part of a step whose flags have not been fetched (ptts_step_flags first)", slot);
+  e.slots[slot] = SlotHost{};
+  e.row_seq_host.clear();
+}
+
 int32_t ptts_stream_close(ptts_engine* h, int32_t slot) {
   PTTS_TRY
   PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
-  Engine& e = h->e;
-  PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
-  PTTS_REQUIRE(!e.slot_in_pending_ticket(slot), PTTS_ERR_STATE, "slot %d is part of a step whose flags have not been fetched (ptts_step_flags first)", slot);
-  PTTS_CUDA(cudaSetDevice(e.cfg.device));
-  e.sync_all();
-  e.slots[slot] = SlotHost{};
-  e.row_seq_host.clear();
+  stream_close_impl(h->e, slot);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_streams_close(ptts_engine* h, const int32_t* slots, int32_t n) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && slots && n >= 0, PTTS_ERR_INVALID, "ptts_streams_close: null argument");
+  for (int i = 0; i < n; ++i) stream_close_impl(h->e, slots[i]);
   return PTTS_OK;
   PTTS_CATCH
 }
@@ -1987,6 +2043,454 @@ int64_t ptts_profile_report(ptts_engine* h, char* buf, int64_t cap) {
     return ex.code;
   }
 }
+
+
+// ------------------------------------------------------------------------------------------------ voice files, config
+namespace {
+
+// The few safetensors features a voice file needs: 8-byte header length, JSON header with one object per tensor
+// ({"dtype", "shape", "data_offsets"}), raw little-endian data behind it.
+struct StTensor { std::string dtype; std::vector<int64_t> shape; size_t begin = 0, end = 0; };
+
+std::map<std::string, StTensor> st_parse_header(const std::string& js) {
+  std::map<std::string, StTensor> out;
+  size_t i = 0;
+  auto skip_ws = [&]() { while (i < js.size() && (js[i] == ' ' || js[i] == '\n' || js[i] == '\t' || js[i] == '\r')) ++i; };
+  auto parse_string = [&]() {
+    PTTS_REQUIRE(i < js.size() && js[i] == '"', PTTS_ERR_INVALID, "safetensors header: string expected at %zu", i);
+    std::string v;
+    for (++i; i < js.size() && js[i] != '"'; ++i) { if (js[i] == '\\' && i + 1 < js.size()) ++i; v.push_back(js[i]); }
+    ++i;
+    return v;
+  };
+  skip_ws();
+  PTTS_REQUIRE(i < js.size() && js[i] == '{', PTTS_ERR_INVALID, "safetensors header is not a JSON object");
+  ++i;
+  while (true) {
+    skip_ws();
+    if (i >= js.size() || js[i] == '}') break;
+    if (js[i] == ',') { ++i; continue; }
+    const std::string name = parse_string();
+    skip_ws();
+    PTTS_REQUIRE(i < js.size() && js[i] == ':', PTTS_ERR_INVALID, "safetensors header: ':' expected");
+    ++i;
+    skip_ws();
+    PTTS_REQUIRE(i < js.size() && js[i] == '{', PTTS_ERR_INVALID, "safetensors header: object expected for '%s'", name.c_str());
+    const size_t obj0 = i;
+    int depth = 0;
+    for (; i < js.size(); ++i) {  // strings in a tensor / metadata object may hold braces only inside quotes
+      if (js[i] == '"') { for (++i; i < js.size() && js[i] != '"'; ++i) if (js[i] == '\\') ++i; continue; }
+      if (js[i] == '{') ++depth;
+      if (js[i] == '}' && --depth == 0) { ++i; break; }
+    }
+    if (name == "__metadata__") continue;
+    const std::string obj = js.substr(obj0, i - obj0);
+    StTensor t;
+    auto field = [&](const char* key) {
+      const size_t k = obj.find(std::string("\"") + key + "\"");
+      PTTS_REQUIRE(k != std::string::npos, PTTS_ERR_INVALID, "safetensors tensor '%s' has no %s", name.c_str(), key);
+      return obj.find(':', k) + 1;
+    };
+    { size_t k = field("dtype"); k = obj.find('"', k); t.dtype = obj.substr(k + 1, obj.find('"', k + 1) - k - 1); }
+    auto ints = [&](size_t k) {
+      std::vector<int64_t> v;
+      k = obj.find('[', k);
+      const size_t e = obj.find(']', k);
+      std::stringstream ss(obj.substr(k + 1, e - k - 1));
+      std::string tok;
+      while (std::getline(ss, tok, ',')) if (tok.find_first_of("0123456789") != std::string::npos) v.push_back(std::stoll(tok));
+      return v;
+    };
+    t.shape = ints(field("shape"));
+    const std::vector<int64_t> off = ints(field("data_offsets"));
+    PTTS_REQUIRE(off.size() == 2 && off[0] <= off[1], PTTS_ERR_INVALID, "safetensors tensor '%s': bad data_offsets", name.c_str());
+    t.begin = (size_t)off[0]; t.end = (size_t)off[1];
+    out[name] = t;
+  }
+  return out;
+}
+
+std::vector<float> st_to_f32(const StTensor& t, const unsigned char* data) {
+  size_t n = 1;
+  for (auto d : t.shape) n *= (size_t)d;
+  std::vector<float> v(n);
+  const unsigned char* p = data + t.begin;
+  if (t.dtype == "F32") { PTTS_REQUIRE(t.end - t.begin == n * 4, PTTS_ERR_INVALID, "safetensors: size mismatch"); std::memcpy(v.data(), p, n * 4); }
+  else if (t.dtype == "BF16") { PTTS_REQUIRE(t.end - t.begin == n * 2, PTTS_ERR_INVALID, "safetensors: size mismatch"); for (size_t i = 0; i < n; ++i) { uint16_t u; std::memcpy(&u, p + 2 * i, 2); v[i] = bf16_to_f32(u); } }
+  else if (t.dtype == "F16") { PTTS_REQUIRE(t.end - t.begin == n * 2, PTTS_ERR_INVALID, "safetensors: size mismatch"); for (size_t i = 0; i < n; ++i) { __half hv; std::memcpy(&hv, p + 2 * i, 2); v[i] = __half2float(hv); } }
+  else PTTS_REQUIRE(false, PTTS_ERR_INVALID, "safetensors dtype %s not supported for a voice prompt", t.dtype.c_str());
+  return v;
+}
+
+// A YAML subset: nested maps by indentation, scalars, block lists ("- 6").  -> {"mimi.seanet.ratios.0": "6", ...}
+std::map<std::string, std::string> yaml_flatten(std::istream& in) {
+  std::map<std::string, std::string> out;
+  std::vector<std::pair<int, std::string>> stack;  // (indent, key)
+  std::map<std::string, int> list_len;
+  std::string line;
+  auto trim = [](std::string v) {
+    const size_t a = v.find_first_not_of(" \t\r"), b = v.find_last_not_of(" \t\r");
+    return a == std::string::npos ? std::string() : v.substr(a, b - a + 1);
+  };
+  while (std::getline(in, line)) {
+    const size_t hash = line.find('#');
+    if (hash != std::string::npos && (hash == 0 || line[hash - 1] == ' ')) line = line.substr(0, hash);
+    if (trim(line).empty()) continue;
+    const int indent = (int)line.find_first_not_of(' ');
+    std::string body = trim(line);
+    if (body[0] == '-') {  // list item under the innermost key at a smaller-or-equal indent
+      while (!stack.empty() && stack.back().first > indent) stack.pop_back();
+      while (stack.size() > 1 && stack.back().first == indent && stack[stack.size() - 2].first == indent) stack.pop_back();
+      std::string path;
+      for (auto& kv : stack) path += (path.empty() ? "" : ".") + kv.second;
+      out[path + "." + std::to_string(list_len[path]++)] = trim(body.substr(1));
+      continue;
+    }
+    const size_t colon = body.find(':');
+    if (colon == std::string::npos) continue;
+    while (!stack.empty() && stack.back().first >= indent) stack.pop_back();
+    stack.push_back({indent, trim(body.substr(0, colon))});
+    const std::string val = trim(body.substr(colon + 1));
+    if (!val.empty()) {
+      std::string path;
+      for (auto& kv : stack) path += (path.empty() ? "" : ".") + kv.second;
+      out[path] = val;
+    }
+  }
+  return out;
+}
+
+}  // namespace
+
+int32_t ptts_voice_save(ptts_engine* h, const ptts_voice* v, const char* path, int32_t include_kv) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && v && path, PTTS_ERR_INVALID, "ptts_voice_save: null argument");
+  Engine& e = h->e;
+  const int T = v->v.len;
+  PTTS_REQUIRE((int)v->v.prompt.size() == T * D_MODEL, PTTS_ERR_STATE, "voice has no conditioning rows to save");
+  const size_t n_prompt = (size_t)T * D_MODEL * 4, n_kv = include_kv ? v->v.kv.n * 2 : 0;
+  std::string js = fmt("{\"audio_prompt\":{\"dtype\":\"F32\",\"shape\":[1,%d,%d],\"data_offsets\":[0,%zu]}", T, D_MODEL, n_prompt);
+  if (include_kv)
+    js += fmt(",\"flow_lm_kv\":{\"dtype\":\"F16\",\"shape\":[%d,2,%d,%d,%d],\"data_offsets\":[%zu,%zu]}", N_LAYERS, N_HEADS, T, HD, n_prompt, n_prompt + n_kv);
+  js += "}";
+  while (js.size() % 8) js.push_back(' ');
+  std::vector<__half> kv;
+  if (include_kv) {
+    PTTS_CUDA(cudaSetDevice(e.cfg.device));
+    e.sync_all();
+    kv.resize(v->v.kv.n);
+    PTTS_CUDA(cudaMemcpy(kv.data(), v->v.kv.p, n_kv, cudaMemcpyDeviceToHost));
+  }
+  std::ofstream f(path, std::ios::binary);
+  PTTS_REQUIRE(f.good(), PTTS_ERR_INVALID, "cannot open '%s' for writing", path);
+  const uint64_t hl = js.size();
+  f.write(reinterpret_cast<const char*>(&hl), 8);
+  f.write(js.data(), (std::streamsize)js.size());
+  f.write(reinterpret_cast<const char*>(v->v.prompt.data()), (std::streamsize)n_prompt);
+  if (include_kv) f.write(reinterpret_cast<const char*>(kv.data()), (std::streamsize)n_kv);
+  PTTS_REQUIRE(f.good(), PTTS_ERR_INVALID, "short write to '%s'", path);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_voice_load(ptts_engine* h, const char* path, ptts_voice** out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && path && out, PTTS_ERR_INVALID, "ptts_voice_load: null argument");
+  std::ifstream f(path, std::ios::binary);
+  PTTS_REQUIRE(f.good(), PTTS_ERR_INVALID, "cannot open '%s'", path);
+  std::vector<unsigned char> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  PTTS_REQUIRE(buf.size() >= 8, PTTS_ERR_INVALID, "'%s' is not a safetensors file", path);
+  uint64_t hl;
+  std::memcpy(&hl, buf.data(), 8);
+  PTTS_REQUIRE(hl <= buf.size() - 8, PTTS_ERR_INVALID, "'%s': header length %llu beyond the file", path, (unsigned long long)hl);
+  const auto tensors = st_parse_header(std::string(reinterpret_cast<const char*>(buf.data()) + 8, (size_t)hl));
+  const unsigned char* data = buf.data() + 8 + hl;
+  const size_t data_len = buf.size() - 8 - hl;
+  auto it = tensors.find("audio_prompt");
+  PTTS_REQUIRE(it != tensors.end(), PTTS_ERR_INVALID, "'audio_prompt' not found in safetensors file");  // tts_model.rs:474
+  const StTensor& tp = it->second;
+  PTTS_REQUIRE(tp.end <= data_len, PTTS_ERR_INVALID, "'%s': audio_prompt data beyond the file", path);
+  PTTS_REQUIRE(!tp.shape.empty() && tp.shape.back() == D_MODEL, PTTS_ERR_INVALID, "audio_prompt must be [..., %d]", D_MODEL);
+  const std::vector<float> prompt = st_to_f32(tp, data);
+  const int T = (int)(prompt.size() / D_MODEL);
+  auto kvit = tensors.find("flow_lm_kv");
+  const std::vector<int64_t> want{N_LAYERS, 2, N_HEADS, T, HD};
+  if (kvit != tensors.end() && kvit->second.dtype == "F16" && kvit->second.shape == want && kvit->second.end <= data_len &&
+      kvit->second.end - kvit->second.begin == (size_t)N_LAYERS * 2 * N_HEADS * T * HD * 2) {
+    // the prefilled KV rows travel with the file: no prefill
+    Engine& e = h->e;
+    PTTS_REQUIRE(T >= 1 && T <= 1024, PTTS_ERR_CAPACITY, "voice prompt of %d rows (supported: 1..1024)", T);
+    PTTS_CUDA(cudaSetDevice(e.cfg.device));
+    std::unique_ptr<ptts_voice> v(new ptts_voice);
+    v->v.len = T;
+    v->v.prompt = prompt;
+    v->v.kv.alloc((size_t)N_LAYERS * 2 * N_HEADS * T * HD);
+    PTTS_CUDA(cudaMemcpy(v->v.kv.p, data + kvit->second.begin, v->v.kv.n * 2, cudaMemcpyHostToDevice));
+    *out = v.release();
+    return PTTS_OK;
+  }
+  return ptts_voice_from_prompt(h, prompt.data(), T, out);
+  PTTS_CATCH
+}
+
+int32_t ptts_config_check(const char* yaml_path) {
+  PTTS_TRY
+  PTTS_REQUIRE(yaml_path, PTTS_ERR_INVALID, "ptts_config_check: null path");
+  std::ifstream f(yaml_path);
+  PTTS_REQUIRE(f.good(), PTTS_ERR_INVALID, "cannot open config '%s'", yaml_path);
+  const auto y = yaml_flatten(f);
+  auto num = [&](const char* key) {
+    auto it = y.find(key);
+    PTTS_REQUIRE(it != y.end(), PTTS_ERR_INVALID, "config '%s' has no key %s", yaml_path, key);
+    return std::stod(it->second);
+  };
+  auto want = [&](const char* key, double v) {
+    const double got = num(key);
+    PTTS_REQUIRE(got == v, PTTS_ERR_INVALID, "config %s = %g, this library is built for %g", key, got, v);
+  };
+  want("flow_lm.flow.depth", FLOW_DEPTH); want("flow_lm.flow.dim", FLOW_DIM);
+  want("flow_lm.transformer.d_model", D_MODEL); want("flow_lm.transformer.hidden_scale", D_FFN / D_MODEL);
+  want("flow_lm.transformer.max_period", 10000); want("flow_lm.transformer.num_heads", N_HEADS);
+  want("flow_lm.transformer.num_layers", N_LAYERS);
+  want("flow_lm.lookup_table.dim", D_MODEL); want("flow_lm.lookup_table.n_bins", N_BINS);
+  want("mimi.sample_rate", 24000); want("mimi.channels", 1); want("mimi.frame_rate", 12.5);
+  want("mimi.seanet.dimension", MIMI_DIM); want("mimi.seanet.n_filters", 64); want("mimi.seanet.n_residual_layers", 1);
+  want("mimi.seanet.ratios.0", 6); want("mimi.seanet.ratios.1", 5); want("mimi.seanet.ratios.2", 4);
+  PTTS_REQUIRE(y.find("mimi.seanet.ratios.3") == y.end(), PTTS_ERR_INVALID, "config mimi.seanet.ratios has more than three entries");
+  want("mimi.seanet.kernel_size", 7); want("mimi.seanet.residual_kernel_size", 3); want("mimi.seanet.last_kernel_size", 3);
+  want("mimi.seanet.compress", 2);
+  { auto it = y.find("mimi.seanet.pad_mode");
+    PTTS_REQUIRE(it != y.end() && it->second == "constant", PTTS_ERR_INVALID, "config mimi.seanet.pad_mode must be 'constant'"); }
+  want("mimi.transformer.d_model", MIMI_DIM); want("mimi.transformer.num_heads", MIMI_HEADS);
+  want("mimi.transformer.num_layers", MIMI_LAYERS); want("mimi.transformer.context", MIMI_CTX);
+  want("mimi.transformer.dim_feedforward", MIMI_FFN);
+  want("mimi.quantizer.dimension", LDIM); want("mimi.quantizer.output_dimension", MIMI_DIM);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_test_noise(int32_t device, uint64_t seed, int32_t frames, float* out) {
+  PTTS_TRY
+  PTTS_REQUIRE(out && frames >= 1, PTTS_ERR_INVALID, "ptts_test_noise: bad arguments");
+  int ndev = 0;
+  PTTS_CUDA(cudaGetDeviceCount(&ndev));
+  PTTS_REQUIRE(device >= 0 && device < ndev, PTTS_ERR_CUDA, "CUDA device %d not present", device);
+  PTTS_CUDA(cudaSetDevice(device));
+  DevBuf<float> d;
+  d.alloc((size_t)frames * LDIM);
+  noise_probe_kernel<<<(frames * LDIM + 255) / 256, 256>>>((unsigned long long)seed, frames, d.p);
+  PTTS_CUDA(cudaGetLastError());
+  PTTS_CUDA(cudaMemcpy(out, d.p, d.n * 4, cudaMemcpyDeviceToHost));
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int32_t ptts_debug_f16_overflow(ptts_engine* h, int64_t* count_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && count_out, PTTS_ERR_INVALID, "null argument");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  e.sync_all();
+  DevBuf<unsigned long long> cnt;
+  cnt.alloc(1);
+  auto scan = [&](const __half* p, size_t n) {
+    if (p && n) count_nonfinite_f16_kernel<<<(unsigned)std::min<size_t>(1184, (n + 255) / 256), 256, 0, e.stream>>>(p, (long long)n, cnt.p);
+  };
+  for (DevBuf<__half>* b : {&e.h16, &e.attn16, &e.ffn16, &e.lat16, &e.y16, &e.fh16, &e.fg16, &e.z16, &e.mh16, &e.mattn16, &e.mffn16, &e.tr16,
+                            &e.a0, &e.e2, &e.h3, &e.a3, &e.e5, &e.h6, &e.a6, &e.e8, &e.h9, &e.a9, &e.kv, &e.mimi_ring})
+    scan(b->p, b->n);
+  scan(reinterpret_cast<const __half*>(e.lm_hA.p), e.lm_hA.n / 2);
+  scan(reinterpret_cast<const __half*>(e.lm_attnA.p), e.lm_attnA.n / 2);
+  scan(reinterpret_cast<const __half*>(e.lm_ffnA.p), e.lm_ffnA.n / 2);
+  PTTS_CUDA(cudaGetLastError());
+  unsigned long long c = 0;
+  PTTS_CUDA(cudaStreamSynchronize(e.stream));
+  PTTS_CUDA(cudaMemcpy(&c, cnt.p, 8, cudaMemcpyDeviceToHost));
+  *count_out = (int64_t)c;
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------ native scheduler
+struct ptts_sched {
+  struct Seg { int kind = 0; std::vector<int32_t> tokens; ptts_stream_params params{}; std::vector<float> noise; int pause_ms = 0; };
+  struct Req { std::vector<Seg> segs; size_t cursor = 0; std::vector<float> out32; std::vector<int16_t> out16; };
+  ptts_engine* eng = nullptr;
+  ptts_voice* voice = nullptr;
+  int max_batch = 0;
+  std::vector<Req> reqs;
+  long long steps = 0;
+};
+
+int32_t ptts_sched_create(ptts_engine* h, ptts_voice* voice, int32_t max_batch, ptts_sched** out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && voice && out, PTTS_ERR_INVALID, "ptts_sched_create: null argument");
+  std::unique_ptr<ptts_sched> s(new ptts_sched);
+  s->eng = h; s->voice = voice;
+  s->max_batch = max_batch > 0 ? std::min(max_batch, h->e.NB) : h->e.NB;
+  *out = s.release();
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+void ptts_sched_destroy(ptts_sched* s) { delete s; }
+
+int64_t ptts_sched_submit(ptts_sched* s, const ptts_segment* segs, int32_t n) {
+  try {
+    PTTS_REQUIRE(s && segs && n >= 1, PTTS_ERR_INVALID, "ptts_sched_submit: null argument");
+    ptts_sched::Req r;
+    for (int i = 0; i < n; ++i) {
+      ptts_sched::Seg g;
+      g.kind = segs[i].kind;
+      if (g.kind == PTTS_SEG_TEXT) {
+        PTTS_REQUIRE(segs[i].n_tokens >= 0 && (segs[i].tokens || segs[i].n_tokens == 0), PTTS_ERR_INVALID, "segment %d: bad tokens", i);
+        PTTS_REQUIRE(segs[i].params.max_gen_len >= 1, PTTS_ERR_INVALID, "segment %d: max_gen_len %d", i, segs[i].params.max_gen_len);
+        g.tokens.assign(segs[i].tokens, segs[i].tokens + segs[i].n_tokens);
+        g.params = segs[i].params;
+        if (segs[i].params.noise) g.noise.assign(segs[i].params.noise, segs[i].params.noise + (size_t)segs[i].params.max_gen_len * LDIM);
+      } else {
+        PTTS_REQUIRE(g.kind == PTTS_SEG_PAUSE && segs[i].pause_ms >= 0, PTTS_ERR_INVALID, "segment %d: unknown kind / negative pause", i);
+        g.pause_ms = segs[i].pause_ms;
+      }
+      r.segs.push_back(std::move(g));
+    }
+    s->reqs.push_back(std::move(r));
+    return (int64_t)s->reqs.size() - 1;
+  } catch (const ptts::Error& ex) { g_last_error = ex.what(); return ex.code; }
+  catch (const std::exception& ex) { g_last_error = ex.what(); return PTTS_ERR_INVALID; }
+}
+
+// The loop of tts_model.BatchScheduler (ahead form) in C++: one step is kept enqueued ahead of the flags of the current
+// one whenever no row can reach its max_gen_len on the current step; a row that ends at EOS instead comes back from the
+// step enqueued ahead as an overrun row (dropped) and its slot is closed once that step has been drained.
+int32_t ptts_sched_run(ptts_sched* s, int32_t pcm_i16) {
+  PTTS_TRY
+  PTTS_REQUIRE(s, PTTS_ERR_INVALID, "null scheduler");
+  Engine& e = s->eng->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  const int pcm_flag = pcm_i16 ? PTTS_STEP_PCM_I16 : PTTS_STEP_PCM;
+  const size_t NR = s->reqs.size();
+  for (auto& r : s->reqs) { r.cursor = 0; r.out32.clear(); r.out16.clear(); }
+  s->steps = 0;
+  std::vector<int> waiting(NR);
+  for (size_t i = 0; i < NR; ++i) waiting[i] = (int)i;
+  std::vector<int> owner(e.NS, -1), budget(e.NS, 0);   // slot -> request, frames the stream may still begin
+  std::vector<int> active;                              // slots, in batch row order
+  auto silence = [&](ptts_sched::Req& r, int ms) {
+    const size_t n = (size_t)ms * 24;                   // pause.rs:183-185 at 24 kHz
+    if (pcm_i16) r.out16.insert(r.out16.end(), n, 0); else r.out32.insert(r.out32.end(), n, 0.f);
+  };
+  auto admit = [&]() {
+    std::vector<int> still, owners;
+    std::vector<ptts_voice*> voices;
+    std::vector<int32_t> toks, offs{0};
+    std::vector<ptts_stream_params> params;
+    for (int ri : waiting) {
+      ptts_sched::Req& r = s->reqs[ri];
+      while (r.cursor < r.segs.size() && r.segs[r.cursor].kind == PTTS_SEG_PAUSE) silence(r, r.segs[r.cursor++].pause_ms);
+      if (r.cursor >= r.segs.size()) continue;
+      if ((int)(active.size() + owners.size()) < s->max_batch) {
+        ptts_sched::Seg& g = r.segs[r.cursor++];
+        toks.insert(toks.end(), g.tokens.begin(), g.tokens.end());
+        offs.push_back((int32_t)toks.size());
+        ptts_stream_params p = g.params;
+        p.noise = g.noise.empty() ? nullptr : g.noise.data();
+        params.push_back(p);
+        voices.push_back(s->voice);
+        owners.push_back(ri);
+      } else {
+        still.push_back(ri);
+      }
+    }
+    waiting.swap(still);
+    if (owners.empty()) return;
+    std::vector<int32_t> slots(owners.size());
+    if (toks.empty()) toks.push_back(0);
+    streams_open_impl(e, (int)owners.size(), voices.data(), toks.data(), offs.data(), params.data(), slots.data());
+    for (size_t i = 0; i < owners.size(); ++i) { owner[slots[i]] = owners[i]; budget[slots[i]] = params[i].max_gen_len; active.push_back(slots[i]); }
+  };
+  struct Flight { long long ticket; std::vector<int> slots; };
+  std::vector<Flight> inflight;
+  std::vector<uint8_t> fin;
+  std::vector<float> pcm32;
+  std::vector<int16_t> pcm16;
+  auto begin = [&](const std::vector<int>& slots, bool ahead) {
+    const long long t = step_begin_impl(e, slots.data(), (int)slots.size(), pcm_flag | (ahead ? PTTS_STEP_AHEAD : 0));
+    for (int sl : slots) --budget[sl];
+    ++s->steps;
+    return t;
+  };
+  // fetches flags + PCM of the oldest step in flight, appends its frames, returns the slots that finished on it
+  auto drain = [&](std::vector<int>& done) {
+    Flight f = std::move(inflight.front());
+    inflight.erase(inflight.begin());
+    const int n = (int)f.slots.size();
+    fin.assign(n, 0);
+    step_flags_impl(e, f.ticket, fin.data(), nullptr, nullptr);
+    if (pcm_i16) { pcm16.resize((size_t)n * FRAME); step_pcm_impl(e, f.ticket, nullptr, pcm16.data()); }
+    else { pcm32.resize((size_t)n * FRAME); step_pcm_impl(e, f.ticket, pcm32.data()); }
+    for (int i = 0; i < n; ++i) {
+      if (fin[i] == PTTS_FRAME_OVERRUN) continue;
+      ptts_sched::Req& r = s->reqs[owner[f.slots[i]]];
+      if (pcm_i16) r.out16.insert(r.out16.end(), pcm16.begin() + (size_t)i * FRAME, pcm16.begin() + (size_t)(i + 1) * FRAME);
+      else r.out32.insert(r.out32.end(), pcm32.begin() + (size_t)i * FRAME, pcm32.begin() + (size_t)(i + 1) * FRAME);
+      if (fin[i] && std::find(done.begin(), done.end(), f.slots[i]) == done.end()) done.push_back(f.slots[i]);
+    }
+  };
+  try {
+    admit();
+    while (!active.empty() || !inflight.empty()) {
+      if (inflight.empty()) inflight.push_back(Flight{begin(active, false), active});
+      if (inflight.size() == 1) {
+        bool room = true;
+        for (int sl : inflight[0].slots) room = room && budget[sl] > 0 && e.slots[sl].own_len + 2 < e.KVCAP;
+        if (room) inflight.push_back(Flight{begin(inflight[0].slots, true), inflight[0].slots});
+      }
+      std::vector<int> done;
+      drain(done);
+      if (!done.empty()) {
+        while (!inflight.empty()) drain(done);   // the step enqueued ahead still lists the finished slots
+        for (int sl : done) {
+          stream_close_impl(e, sl);
+          waiting.push_back(owner[sl]);
+          owner[sl] = -1;
+          active.erase(std::find(active.begin(), active.end(), sl));
+        }
+        admit();
+      }
+    }
+  } catch (...) {
+    // leave nothing in flight and no slot open on the shared engine
+    for (auto& f : inflight) {
+      try { step_flags_impl(e, f.ticket, nullptr, nullptr, nullptr); } catch (...) {}
+      try { step_pcm_impl(e, f.ticket, nullptr); } catch (...) {}
+    }
+    for (int sl : active) { try { stream_close_impl(e, sl); } catch (...) {} }
+    throw;
+  }
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int64_t ptts_sched_result_samples(const ptts_sched* s, int64_t req) {
+  if (!s || req < 0 || req >= (int64_t)s->reqs.size()) return PTTS_ERR_INVALID;
+  const auto& r = s->reqs[(size_t)req];
+  return (int64_t)std::max(r.out32.size(), r.out16.size());
+}
+
+int32_t ptts_sched_result(const ptts_sched* s, int64_t req, void* pcm_out, int64_t cap) {
+  PTTS_TRY
+  PTTS_REQUIRE(s && pcm_out && req >= 0 && req < (int64_t)s->reqs.size(), PTTS_ERR_INVALID, "ptts_sched_result: bad arguments");
+  const auto& r = s->reqs[(size_t)req];
+  const int64_t n = (int64_t)std::max(r.out32.size(), r.out16.size());
+  PTTS_REQUIRE(cap >= n, PTTS_ERR_INVALID, "request %lld has %lld samples, buffer holds %lld", (long long)req, (long long)n, (long long)cap);
+  if (!r.out16.empty()) std::memcpy(pcm_out, r.out16.data(), r.out16.size() * 2);
+  else if (!r.out32.empty()) std::memcpy(pcm_out, r.out32.data(), r.out32.size() * 4);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
+int64_t ptts_sched_steps(const ptts_sched* s) { return s ? s->steps : -1; }
 
 // ------------------------------------------------------------------------------------------------ isolated kernel tests
 struct TestCtx {

@@ -760,8 +760,11 @@ __global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCt
 // ---------------------------------------------------------------- SEANet tail and streaming state
 // Last layer: ELU (already applied by the producer) -> Conv1d 64->1 k3 (reference seanet.rs:379-392).
 // One thread per output sample; the 3x64 window of sample t is 384 contiguous bytes.
+// Also packs the frame as the reference's wire format (audio.rs:129-146 pcm_i16_le_bytes: clamp to [-1, 1], * 32767,
+// truncating cast), so a host that streams i16 PCM reads back half the bytes and converts nothing.
 __global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+1920][64]*/, const float* __restrict__ w /*[3][64]*/,
-                                         const float* __restrict__ bias, int n, float* __restrict__ pcm /*[n,1920]*/) {
+                                         const float* __restrict__ bias, int n, float* __restrict__ pcm /*[n,1920]*/,
+                                         short* __restrict__ pcm16 /*[n,1920] or null*/) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float w_s[192];
@@ -783,6 +786,7 @@ __global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+19
     }
   }
   pcm[static_cast<long long>(b) * FRAME + t] = acc;
+  if (pcm16) pcm16[static_cast<long long>(b) * FRAME + t] = static_cast<short>(fminf(fmaxf(acc, -1.f), 1.f) * 32767.f);
 }
 
 // Left-context rows of every streaming conv (reference `previous`, conv.rs:125-128; and the previous input row
@@ -824,6 +828,54 @@ __global__ void slot_reset_kernel(const ConvSegs segs, float* __restrict__ parti
     float4* p = reinterpret_cast<float4*>(partial + static_cast<long long>(slot) * 16 * 512);
     for (int i = threadIdx.x; i < 16 * 512 / 4; i += blockDim.x) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+}
+
+// Stream open, packed: the host stages one record per new stream in pinned memory, ONE copy brings them over, and this
+// kernel scatters them into the slot arena (KV descriptor, control block, cursor, BOS as the first AR feedback) and
+// zeroes the slot's streaming state (reference init_state zeros: conv.rs:71-88,205-217).  grid (n, 10), block 128.
+struct OpenRec {
+  SeqDesc sd;
+  StreamCtl ctl;
+  int slot;
+  int own_len;
+  int pad[2];
+};
+__global__ void slot_open_kernel(const OpenRec* __restrict__ recs, const ConvSegs segs, float* __restrict__ partial,
+                                 SeqDesc* __restrict__ seqs, StreamCtl* __restrict__ ctl, int* __restrict__ own_len,
+                                 float* __restrict__ feedback, const float* __restrict__ bos) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const OpenRec r = recs[blockIdx.x];
+  const int slot = r.slot;
+  if (blockIdx.y < 8) {
+    const ConvSeg g = segs.s[blockIdx.y];
+    uint4* st = reinterpret_cast<uint4*>(g.state + static_cast<long long>(slot) * g.pad * g.C);
+    for (int i = threadIdx.x; i < g.pad * g.C / 8; i += blockDim.x) st[i] = make_uint4(0, 0, 0, 0);
+  } else if (blockIdx.y == 8) {
+    float4* p = reinterpret_cast<float4*>(partial + static_cast<long long>(slot) * 16 * 512);
+    for (int i = threadIdx.x; i < 16 * 512 / 4; i += blockDim.x) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    if (threadIdx.x == 0) { seqs[slot] = r.sd; ctl[slot] = r.ctl; own_len[slot] = r.own_len; }
+    if (threadIdx.x < LDIM) feedback[slot * LDIM + threadIdx.x] = bos[threadIdx.x];
+  }
+}
+
+// The device noise generator on its own (tests: distribution of counter_normal).
+__global__ void noise_probe_kernel(unsigned long long seed, int frames, float* __restrict__ out /*[frames,32]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < frames * LDIM) out[i] = counter_normal(seed, i / LDIM, i % LDIM);
+}
+
+// Debug: how many f16 values of a buffer are not finite (an f32 -> f16 store saturates to +-inf above 65504).
+__global__ void count_nonfinite_f16_kernel(const __half* __restrict__ p, long long n, unsigned long long* __restrict__ count) {
+  long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  unsigned int local = 0;
+  for (; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const unsigned short u = __half_as_ushort(p[i]);
+    local += ((u & 0x7c00u) == 0x7c00u) ? 1u : 0u;
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, static_cast<unsigned long long>(local));
 }
 
 __global__ void fill_f32_kernel(float* p, float v, long long n) {

@@ -8,7 +8,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import EngineCfg, StreamParams, TensorDesc, check
+from ._lib import EngineCfg, Segment, StreamParams, TensorDesc, check
 
 FRAME = 1920
 LDIM = 32
@@ -40,6 +40,11 @@ class Voice:
         if self._h:
             _lib.lib().ptts_voice_destroy(self._engine._h, self._h)
             self._h = None
+
+    def save(self, path, include_kv: bool = False):
+        """Voice-state safetensors (ptts_voice_save): `audio_prompt` f32 [1,T,1024] as the reference reads it
+        (tts_model.rs:467-487); include_kv adds the prefilled FlowLM KV rows so that a later load skips the prefill."""
+        check(_lib.lib().ptts_voice_save(self._engine._h, self._h, str(path).encode(), int(include_kv)))
 
 
 class Engine:
@@ -99,6 +104,12 @@ class Engine:
         check(_lib.lib().ptts_voice_from_pcm(self._h, _ptr(a), a.shape[0], C.byref(h)))
         return Voice(self, h)
 
+    def voice_load(self, path) -> Voice:
+        """ptts_voice_load: `audio_prompt` from a voice-state safetensors file (+ the KV snapshot when the file has one)."""
+        h = C.c_void_p()
+        check(_lib.lib().ptts_voice_load(self._h, str(path).encode(), C.byref(h)))
+        return Voice(self, h)
+
     def audio_prompt_from_pcm(self, pcm24k: np.ndarray) -> np.ndarray:
         """The conditioning rows [frames, 1024] of a PCM prompt (what the reference stores as `audio_prompt`)."""
         a = np.ascontiguousarray(pcm24k, dtype=np.float32).reshape(-1)
@@ -140,11 +151,12 @@ class Engine:
         return pcm, fin.astype(bool), lat, logit
 
     # ---- pipelined form: begin -> flags -> (next begin) -> pcm
-    def step_begin(self, slots: np.ndarray, want_pcm: bool = True, ahead: bool = False) -> int:
+    def step_begin(self, slots: np.ndarray, want_pcm: bool = True, ahead: bool = False, i16: bool = False) -> int:
         """Enqueue one frame.  ahead=True (PTTS_STEP_AHEAD): the previous step's flags need not have been fetched yet;
-        rows whose stream ended on that previous step come back from step_flags with fin == 2 (frame past the end)."""
+        rows whose stream ended on that previous step come back from step_flags with fin == 2 (frame past the end).
+        i16=True (PTTS_STEP_PCM_I16): the frame is read back as i16 with step_pcm_i16."""
         slots = np.ascontiguousarray(slots, dtype=np.int32)
-        t = int(_lib.lib().ptts_step_begin(self._h, _ptr(slots), len(slots), (1 if want_pcm else 0) | (2 if ahead else 0)))
+        t = int(_lib.lib().ptts_step_begin(self._h, _ptr(slots), len(slots), (4 if i16 else (1 if want_pcm else 0)) | (2 if ahead else 0)))
         check(t)
         self._pending_n = getattr(self, "_pending_n", {})
         self._pending_n[t] = len(slots)
@@ -163,6 +175,12 @@ class Engine:
         n = self._pending_n.pop(ticket)
         pcm = np.empty((n, FRAME), np.float32) if want else None
         check(_lib.lib().ptts_step_pcm(self._h, ticket, _ptr(pcm)))
+        return pcm
+
+    def step_pcm_i16(self, ticket: int) -> np.ndarray:
+        n = self._pending_n.pop(ticket)
+        pcm = np.empty((n, FRAME), np.int16)
+        check(_lib.lib().ptts_step_pcm_i16(self._h, ticket, _ptr(pcm)))
         return pcm
 
     def step_device(self, slots: np.ndarray):
@@ -184,6 +202,15 @@ class Engine:
 
     def close_stream(self, slot: int):
         check(_lib.lib().ptts_stream_close(self._h, int(slot)))
+
+    def close_streams(self, slots):
+        a = np.ascontiguousarray(slots, dtype=np.int32)
+        check(_lib.lib().ptts_streams_close(self._h, _ptr(a), len(a)))
+
+    def f16_overflow_count(self) -> int:
+        v = C.c_int64()
+        check(_lib.lib().ptts_debug_f16_overflow(self._h, C.byref(v)))
+        return int(v.value)
 
     def stream_frames(self, slot: int) -> tuple[int, int]:
         f, e = C.c_int32(), C.c_int32()
@@ -220,6 +247,74 @@ class Engine:
 
     def launch_count(self, reset: bool = False) -> int:
         return int(_lib.lib().ptts_launch_count(self._h, int(reset)))
+
+
+class NativeScheduler:
+    """ptts_sched_*: continuous batching of long-form requests inside the library (C++), the host only submits segment
+    lists and collects PCM.  A request is [("text", StreamSpec) | ("pause", ms)], like tts_model.BatchScheduler."""
+
+    def __init__(self, engine: Engine, voice: Voice, max_batch: int | None = None):
+        self._engine = engine
+        h = C.c_void_p()
+        check(_lib.lib().ptts_sched_create(engine._h, voice._h, int(max_batch or 0), C.byref(h)))
+        self._h = h
+        self.n_requests = 0
+
+    def submit(self, request: list[tuple]) -> int:
+        segs = (Segment * len(request))()
+        keep = []
+        for i, (kind, val) in enumerate(request):
+            if kind == "pause":
+                segs[i].kind, segs[i].pause_ms = 1, int(val)
+                continue
+            tok = np.ascontiguousarray(val.tokens, dtype=np.int32)
+            keep.append(tok)
+            segs[i].kind, segs[i].n_tokens, segs[i].tokens = 0, len(tok), tok.ctypes.data
+            p = segs[i].params
+            p.max_gen_len, p.frames_after_eos, p.eos_threshold, p.temp, p.seed = val.max_gen_len, val.frames_after_eos, val.eos_threshold, val.temp, val.seed
+            if val.noise is not None:
+                nz = np.ascontiguousarray(val.noise, dtype=np.float32)
+                assert nz.shape == (val.max_gen_len, LDIM), nz.shape
+                keep.append(nz)
+                p.noise = nz.ctypes.data
+        r = int(_lib.lib().ptts_sched_submit(self._h, segs, len(request)))
+        check(r)
+        self.n_requests = r + 1
+        return r
+
+    def run(self, requests: list[list[tuple]] | None = None, i16: bool = False) -> list[np.ndarray]:
+        for r in requests or []:
+            self.submit(r)
+        check(_lib.lib().ptts_sched_run(self._h, int(i16)))
+        out = []
+        for r in range(self.n_requests):
+            n = int(_lib.lib().ptts_sched_result_samples(self._h, r))
+            a = np.empty(max(n, 0), np.int16 if i16 else np.float32)
+            if n > 0:
+                check(_lib.lib().ptts_sched_result(self._h, r, _ptr(a), n))
+            out.append(a)
+        return out
+
+    @property
+    def steps(self) -> int:
+        return int(_lib.lib().ptts_sched_steps(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lib().ptts_sched_destroy(self._h)
+            self._h = None
+
+
+def config_check(yaml_path) -> None:
+    """ptts_config_check: the model YAML against the dimensions the library is compiled for (raises PttsError)."""
+    check(_lib.lib().ptts_config_check(str(yaml_path).encode()))
+
+
+def device_noise(seed: int, frames: int, device: int = 0) -> np.ndarray:
+    """The N(0, 1) draws of the device generator for one stream (ptts_test_noise)."""
+    out = np.empty((frames, LDIM), np.float32)
+    check(_lib.lib().ptts_test_noise(device, seed, frames, _ptr(out)))
+    return out
 
 
 def test_gemm(a, w, bias=None, mode=0, split_k=1, act=0, use_simt=0, device=0):

@@ -249,3 +249,40 @@ def make_noise(frames: int, seed: int, temp: float = 0.7) -> np.ndarray:
     """Injected x_0 per frame: N(0, temp) like flow_lm.rs:39-48 (std = sqrt(temp))."""
     rng = np.random.default_rng(seed)
     return (np.sqrt(np.float32(temp)) * rng.standard_normal((frames, LDIM), dtype=np.float32)).astype(np.float32)
+
+
+def make_config_yaml(**override) -> str:
+    """A model YAML in the schema of the reference's config.rs:6-108 (the layout of config/b6369a24.yaml) filled with the
+    b6369a24 dimensions; `override` replaces leaf values by dotted path (tests of ptts_config_check)."""
+    cfg = {
+        "flow_lm": {"dtype": "float32", "flow": {"depth": 6, "dim": 512},
+                    "transformer": {"d_model": 1024, "hidden_scale": 4, "max_period": 10000, "num_heads": 16, "num_layers": 6},
+                    "lookup_table": {"dim": 1024, "n_bins": 4000, "tokenizer": "sentencepiece"}},
+        "mimi": {"dtype": "float32", "sample_rate": 24000, "channels": 1, "frame_rate": 12.5,
+                 "seanet": {"dimension": 512, "channels": 1, "n_filters": 64, "n_residual_layers": 1, "ratios": [6, 5, 4],
+                            "kernel_size": 7, "residual_kernel_size": 3, "last_kernel_size": 3, "dilation_base": 2,
+                            "pad_mode": "constant", "compress": 2},
+                 "transformer": {"d_model": 512, "num_heads": 8, "num_layers": 2, "layer_scale": 0.01, "context": 250,
+                                 "dim_feedforward": 2048, "input_dimension": 512, "output_dimensions": [512]},
+                 "quantizer": {"dimension": 32, "output_dimension": 512}},
+    }
+    for path, val in override.items():
+        node = cfg
+        keys = path.split(".")
+        for k in keys[:-1]:
+            node = node[k]
+        node[keys[-1]] = val
+
+    def emit(node, indent):
+        out = []
+        for k, v in node.items():
+            if isinstance(v, dict):
+                out.append(" " * indent + f"{k}:")
+                out += emit(v, indent + 2)
+            elif isinstance(v, list):
+                out.append(" " * indent + f"{k}:")
+                out += [" " * indent + f"- {x}" for x in v]
+            else:
+                out.append(" " * indent + f"{k}: {v}")
+        return out
+    return "# generated by pocket_tts_b200.synth.make_config_yaml\n" + "\n".join(emit(cfg, 0)) + "\n"

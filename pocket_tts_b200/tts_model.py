@@ -100,6 +100,11 @@ class TTSModel:
         self.tokenizer = tokenizer
         self.engine = Engine(weights, device=device, max_slots=max_slots, kv_capacity=kv_capacity)
         self._lsd_on_device = 1
+        # steps in flight of every live generate_stream iterator: ticket -> {"owner", "flags", "pcm"}.  The engine's ticket
+        # ring is shared and its flags come back in step order, while the reference's iterators are independent
+        # (tts_model.rs:894-913: each owns a clone of the state): an iterator that needs the engine while another one has
+        # a step outstanding fetches that step's results on the other's behalf and parks them here.
+        self._tickets: dict[int, dict] = {}
 
     # ---- loading (tts_model.rs:59-86)
     @classmethod
@@ -107,7 +112,17 @@ class TTSModel:
         return cls.load_with_params(weights_path, DEFAULT_TEMPERATURE, DEFAULT_LSD_DECODE_STEPS, DEFAULT_EOS_THRESHOLD, **kw)
 
     @classmethod
-    def load_with_params(cls, weights_path: str | Path, temp: float, lsd_decode_steps: int, eos_threshold: float, **kw) -> "TTSModel":
+    def load_with_params(cls, weights_path: str | Path, temp: float, lsd_decode_steps: int, eos_threshold: float,
+                         config: str | Path | None = None, **kw) -> "TTSModel":
+        """tts_model.rs:69-86.  `config` = the variant's model YAML (config/{variant}.yaml, config.rs:111): its dimensions are
+        checked against the ones the library is compiled for before any weight is read (ptts_config_check); when it is
+        None, a `<variant>.yaml` next to the weights file is used if present."""
+        from .engine import config_check
+        if config is None:
+            cand = Path(weights_path).with_suffix(".yaml")
+            config = cand if cand.exists() else None
+        if config is not None:
+            config_check(config)
         return cls(read_safetensors(weights_path), temp, lsd_decode_steps, eos_threshold, **kw)
 
     # ---- voice state (tts_model.rs:467-501)
@@ -147,9 +162,41 @@ class TTSModel:
             raise RuntimeError("no tokenizer attached: pass tokenizer= or use generate_stream_tokens")
         return np.asarray(self.tokenizer(prepared), np.int32)
 
+    # ---- steps in flight, shared by every live iterator of this model
+    def _park(self, t: int):
+        st = self._tickets[t]
+        if st["flags"] is None:
+            st["flags"] = self.engine.step_flags(t)
+        if st["pcm"] is None:
+            st["pcm"] = self.engine.step_pcm(t)
+
+    def _begin(self, owner, ids, ahead=False) -> int:
+        for t in sorted(self._tickets):          # another iterator's step: finish it for them first
+            if self._tickets[t]["owner"] is not owner:
+                self._park(t)
+        t = self.engine.step_begin(ids, ahead=ahead)
+        self._tickets[t] = {"owner": owner, "flags": None, "pcm": None}
+        return t
+
+    def _flags(self, t: int):
+        for u in sorted(self._tickets):          # flags come back in step order
+            if u < t and self._tickets[u]["flags"] is None:
+                self._park(u)
+        st = self._tickets[t]
+        if st["flags"] is None:
+            st["flags"] = self.engine.step_flags(t)
+        return st["flags"]
+
+    def _pcm(self, t: int, want=True):
+        st = self._tickets.pop(t)
+        if st["flags"] is None:
+            self.engine.step_flags(t)
+        return st["pcm"] if st["pcm"] is not None else self.engine.step_pcm(t, want)
+
     def generate_stream_tokens(self, tokens, voice: Voice, max_gen_len: int, frames_after_eos: int, noise=None,
                                seed: int = 0) -> Iterator[np.ndarray]:
-        """One segment (generate_stream_segment, tts_model.rs:935-1071): yields f32 [1,1,1920] per frame."""
+        """One segment (generate_stream_segment, tts_model.rs:935-1071): yields f32 [1,1,1920] per frame.  Several
+        iterators of one model may be consumed in any interleaving, like the reference's (each owns its state)."""
         self._sync_params()
         if noise is None and self.noise_clamp is not None:
             noise = sample_clamped_noise(max_gen_len, self.temp, float(self.noise_clamp), seed, self.ldim)
@@ -157,22 +204,13 @@ class TTSModel:
         (slot,) = self.engine.open_streams([voice], [spec])
         ids = np.array([slot], np.int32)
         eng = self.engine
-        outstanding: dict[int, bool] = {}   # ticket -> flags already fetched
+        owner = object()
+        mine: list[int] = []
 
         def begin(ahead=False):
-            t = eng.step_begin(ids, ahead=ahead)
-            outstanding[t] = False
+            t = self._begin(owner, ids, ahead=ahead)
+            mine.append(t)
             return t
-
-        def flags(t):
-            r = eng.step_flags(t)
-            outstanding[t] = True
-            return r
-
-        def pcm(t, want=True):
-            r = eng.step_pcm(t, want)
-            outstanding.pop(t)
-            return r
 
         try:
             # Frame n's codec half overlaps frame n+1's language-model half, and frame n+1 is enqueued before frame n's
@@ -183,7 +221,11 @@ class TTSModel:
             issued = 1
             while True:
                 nxt = None
-                if issued < max_gen_len and can_ahead:
+                # (another iterator may already have fetched this step's flags on our behalf: if they say the stream ends
+                # here, there is nothing to enqueue ahead)
+                parked = self._tickets[ticket]["flags"]
+                ends_here = parked is not None and bool(parked[0][0])
+                if issued < max_gen_len and can_ahead and not ends_here:
                     try:
                         nxt = begin(ahead=True)
                         issued += 1
@@ -191,11 +233,12 @@ class TTSModel:
                         if getattr(e, "code", 0) != -3:
                             raise
                         can_ahead = False
-                fin, _, _ = flags(ticket)
+                fin, _, _ = self._flags(ticket)
                 if nxt is None and not fin[0] and issued < max_gen_len:
                     nxt = begin()
                     issued += 1
-                frame = pcm(ticket).reshape(1, 1, FRAME)
+                frame = self._pcm(ticket).reshape(1, 1, FRAME)
+                mine.remove(ticket)
                 yield frame
                 if fin[0] or nxt is None:
                     break
@@ -203,12 +246,11 @@ class TTSModel:
         finally:
             # retire whatever is still in flight: the frame enqueued ahead of an EOS finish, or everything when the
             # consumer drops the iterator early (the reference's iterator simply stops being polled)
-            for t in sorted(outstanding):
-                if not outstanding[t]:
-                    eng.step_flags(t)
-                eng.step_pcm(t, want=False)
-            outstanding.clear()
-            eng.sync()
+            for t in sorted(mine):
+                if t in self._tickets:
+                    self._flags(t)
+                    self._pcm(t, want=False)
+            mine.clear()
             eng.close_stream(int(slot))
 
     def split_into_best_sentences(self, text: str) -> list[str]:
@@ -372,8 +414,17 @@ class BatchScheduler:
         self.engine, self.voice = engine, voice
         self.max_batch = max_batch or engine.max_batch
 
-    def run(self, requests: list[list[tuple]], ahead: bool = False) -> list[np.ndarray]:
-        """ahead=True keeps the device one step ahead of the host (see _run_ahead); the default is the lock-step loop."""
+    def run(self, requests: list[list[tuple]], ahead: bool = False, native: bool = False, i16: bool = False) -> list[np.ndarray]:
+        """ahead=True keeps the device one step ahead of the host (see _run_ahead); the default is the lock-step loop.
+        native=True runs the same policy inside the library (ptts_sched_*, C++): the host only submits the segment lists
+        and collects each request's PCM (f32, or i16 packed on the device with i16=True)."""
+        if native:
+            from .engine import NativeScheduler
+            ns = NativeScheduler(self.engine, self.voice, self.max_batch)
+            try:
+                return ns.run(requests, i16=i16)
+            finally:
+                ns.close()
         if ahead:
             return _run_ahead(self, requests)
         eng = self.engine

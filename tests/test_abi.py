@@ -18,20 +18,44 @@ def built_lib():
     return _lib
 
 
-def header_symbols():
-    text = (ROOT / "include" / "ptts.h").read_text()
+def header_symbols(name):
+    text = (ROOT / "include" / name).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ptts_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_exports_match_header(built_lib):
+    """Product ABI (ptts.h) and test hooks (ptts_internal.h) are separate headers; the library exports every symbol of
+    both and the ctypes binding lists exactly those."""
     L = built_lib.lib()
-    syms = header_symbols()
-    assert len(syms) >= 20
-    for s in syms:
-        assert hasattr(L, s), f"{s} declared in ptts.h but not exported"
-    assert sorted(built_lib.SYMBOLS) == syms
-    assert L.ptts_abi_version() == 1
+    product, internal = header_symbols("ptts.h"), header_symbols("ptts_internal.h")
+    assert len(product) >= 30 and not set(product) & set(internal)
+    assert not [s for s in product if "test" in s or "debug" in s or "profile" in s]
+    for s in product + internal:
+        assert hasattr(L, s), f"{s} declared in a header but not exported"
+    assert sorted(built_lib.PRODUCT_SYMBOLS) == product
+    assert sorted(built_lib.INTERNAL_SYMBOLS) == internal
+    assert L.ptts_abi_version() == 2
+
+
+def test_config_check_reads_the_reference_yaml_schema(built_lib, tmp_path):
+    """ptts_config_check (config.rs:111): a YAML in the reference's schema with the b6369a24 dimensions passes (block lists,
+    nested maps, comments), a changed dimension is named.  Needs no device."""
+    from pocket_tts_b200 import synth
+    from pocket_tts_b200.engine import config_check
+    p = tmp_path / "m.yaml"
+    p.write_text(synth.make_config_yaml())
+    config_check(p)
+    p.write_text(synth.make_config_yaml(**{"flow_lm.transformer.num_heads": 12}))
+    with pytest.raises(built_lib.PttsError) as ei:
+        config_check(p)
+    assert "flow_lm.transformer.num_heads" in str(ei.value)
+    p.write_text(synth.make_config_yaml(**{"mimi.seanet.ratios": [6, 5, 8]}))
+    with pytest.raises(built_lib.PttsError) as ei:
+        config_check(p)
+    assert "ratios" in str(ei.value)
+    with pytest.raises(built_lib.PttsError):
+        config_check(tmp_path / "missing.yaml")
 
 
 def test_sass_is_blackwell_native(built_lib):
