@@ -18,6 +18,8 @@ int main(int argc, char** argv) {
   CHECK(sizeof(ptts_engine_cfg) == 16 * sizeof(int32_t));
   CHECK(sizeof(ptts_tensor_desc) == 8 + 4 + 4 + 32 + 8);
   CHECK(sizeof(ptts_stream_params) == 32);
+  CHECK(sizeof(ptts_segment) == 56);
+  CHECK(PTTS_STEP_PCM_I16 == 4 && PTTS_SEG_TEXT == 0 && PTTS_SEG_PAUSE == 1);
   CHECK(PTTS_STEP_PCM == 1 && PTTS_STEP_AHEAD == 2 && PTTS_FRAME_OVERRUN == 2);
   printf("ok header: abi %d, cfg %zu B, tensor desc %zu B, stream params %zu B\n", ptts_abi_version(), sizeof(ptts_engine_cfg),
          sizeof(ptts_tensor_desc), sizeof(ptts_stream_params));
@@ -29,6 +31,9 @@ int main(int argc, char** argv) {
   CHECK(ptts_step(NULL, NULL, 0, NULL, NULL, NULL, NULL) == PTTS_ERR_INVALID);
   CHECK(ptts_voice_from_pcm(NULL, NULL, 0, NULL) == PTTS_ERR_INVALID);
   CHECK(ptts_step_begin(NULL, NULL, 0, PTTS_STEP_PCM) == PTTS_ERR_INVALID);
+  CHECK(ptts_voice_load(NULL, NULL, NULL) == PTTS_ERR_INVALID);
+  CHECK(ptts_sched_create(NULL, NULL, 0, NULL) == PTTS_ERR_INVALID);
+  CHECK(ptts_config_check("/nonexistent/model.yaml") == PTTS_ERR_INVALID);
   printf("ok null arguments are refused: %s\n", ptts_last_error());
 
   if (expect_no_gpu) {

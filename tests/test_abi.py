@@ -109,3 +109,4 @@ def test_plain_c_caller(built_lib, tmp_path):
     assert "ok header" in r.stdout and "FAIL" not in r.stdout
     # the same sizes the ctypes structures have
     assert C.sizeof(built_lib.EngineCfg) == 64 and C.sizeof(built_lib.TensorDesc) == 56 and C.sizeof(built_lib.StreamParams) == 32
+    assert C.sizeof(built_lib.Segment) == 56
