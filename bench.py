@@ -43,13 +43,15 @@ CONFIG = {"workload": "configs[1]: b6369a24 f16-operand batch 64 concurrent 10 s
           "l2": "no flush: per-step working set (190 MB weights + ~470 MB KV) exceeds the 126 MB L2"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures in profiles/ (bytes)
-# (profiles/r01_top_kernels_ncu_full.csv: one mid-utterance step at 64 streams, mean over the captured launches of each
-# kernel function.  Below the algorithmic bytes because the activations of a step stay in the 126 MB L2.)
-TRAFFIC_NCU: dict[str, float] = {
-    "gemm_tc_kernel": 5.42e6, "flowlm_attn_decode_kernel": 13.76e6, "flow_head_kernel": 9.24e6,
-    "mimi_attn_kernel": 25.46e6, "gemm_tc_persistent_kernel": 20.17e6,
-}
+def ncu_traffic() -> tuple[dict[str, float], str | None]:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel function, read at run time from the committed
+    summary of this round's `ncu --set full` capture (profiles/ncu_traffic.json, written by tests/ncu_summary.py from the
+    raw export) -- not a constant in this file."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return {}, None
+    d = json.loads(p.read_text())
+    return {k: float(v) for k, v in d.get("bytes_per_launch", {}).items()}, d.get("source")
 
 
 def peaks():
@@ -190,7 +192,8 @@ def run_gpu(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE {world}"
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
+        # NCCL is only the timing barrier / max-over-ranks reduction here (no data-path collective); NCCL_DEBUG is left as
+        # the caller set it, the JSON line is the last thing rank 0 prints
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -271,6 +274,53 @@ def run_gpu(args):
                     "d2h_bytes_per_step": FRAMES * STREAMS * (1920 * 4 + 1 + 32 * 4 + 4), "ms_per_step": ms_e2e},
             "gpu_launches": launches, "realtime_factor_per_gpu": STREAMS * FRAMES * FRAME_SEC / (ms_dev / 1000)}
 
+    # BASELINE configs[4] slice: concurrent 60 s long-form requests (6 chunks x 125 frames, [pause:300ms] between chunks)
+    # through the library's own continuous-batching scheduler (ptts_sched_*, C++), i16 PCM packed on the device and
+    # copied to the host every frame; request-sharded like everything else (each rank runs its share)
+    if args.longform > 0:
+        from pocket_tts_b200.engine import NativeScheduler
+        lf_chunks, lf_pause = 6, 300
+        eng_lf = eng if args.longform <= STREAMS else None
+        if eng_lf is None:
+            voice.close(); eng.close()
+            wnp2 = synth.make_weights(1234)
+            eng = Engine(wnp2, device=local, max_slots=args.longform, kv_capacity=TOKENS + FRAMES + 3, int8_weights=args.int8)
+            del wnp2
+            voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
+        reqs = []
+        for r in range(args.longform):
+            segs = []
+            for c in range(lf_chunks):
+                if c:
+                    segs.append(("pause", lf_pause))
+                segs.append(("text", StreamSpec(synth.make_tokens(TOKENS, seed=(base * 8 + r) * 16 + c), FRAMES, 3, 1e30, temp=0.7, seed=r * 16 + c)))
+            reqs.append(segs)
+        ns = NativeScheduler(eng, voice, args.longform)
+        barrier()
+        t0 = time.perf_counter()
+        out = ns.run(reqs, i16=True)
+        torch.cuda.synchronize()
+        lf_s = time.perf_counter() - t0
+        ns.close()
+        want = lf_chunks * FRAMES * 1920 + (lf_chunks - 1) * lf_pause * 24
+        assert all(o.shape == (want,) for o in out)
+        if world > 1:
+            t = torch.tensor([lf_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            lf_s = float(t.item())
+        line["longform"] = {"workload": f"configs[4] slice: {args.longform} concurrent requests per GPU x {want / 24000:.1f} s (6 chunks x 125 frames, "
+                                        f"[pause:300ms]), native scheduler, i16 PCM to the host", "requests_per_gpu": args.longform,
+                            "value": world * args.longform * want / 24000.0 / lf_s, "unit": UNIT, "wall_s": lf_s}
+        del out, reqs
+        if eng_lf is None and rank == 0:
+            # back to the headline engine for the roofline pass below
+            voice.close(); eng.close()
+            wnp2 = synth.make_weights(1234)
+            wnp2.update(synth.make_encoder_weights(4321))
+            eng = Engine(wnp2, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3, int8_weights=args.int8)
+            del wnp2
+            voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
+
     if rank == 0:
         # roofline pass: per-launch CUDA events on the engine's stream for 3 mid-utterance decode steps
         job(False, profile={60, 61, 62})
@@ -301,20 +351,45 @@ def run_gpu(args):
             f["bytes"] += v["bytes"]
             f["flops"] += v["flops"]
         fn, f = max(fns.items(), key=lambda kv: kv[1]["us"])
-        gbs, tfs = f["bytes"] / f["us"] / 1e3, f["flops"] / f["us"] / 1e6
-        bound = "hbm" if f["bytes"] / (pk["hbm"] * 1e9) >= f["flops"] / (pk["tf"] * 1e12) else "tensor"
         nl = f["launches"]
-        line["roofline"] = {"kernel": fn, "bound": bound, "achieved": gbs if bound == "hbm" else tfs,
-                            "peak": pk["hbm"] if bound == "hbm" else pk["tf"], "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-                            "frac": (gbs / pk["hbm"]) if bound == "hbm" else (tfs / pk["tf"]),
-                            "traffic": TRAFFIC_NCU.get(fn), "peak_source": pk["src"],
-                            "us_per_launch": f["us"] / nl, "us_per_launch_raw": f["us_raw"] / nl,
-                            "event_pair_overhead_us": ovh_us, "share_of_step": f["us"] / tot, "launches_per_step": nl / n_prof,
-                            "algorithmic_bytes_per_launch": f["bytes"] / nl, "algorithmic_flops_per_launch": f["flops"] / nl,
-                            "TFLOP/s": tfs, "GB/s": gbs,
-                            "how": "CUDA events around every launch of 3 mid-utterance decode steps on the engine's stream "
-                                   "(graphs and stream overlap off in this pass); the time of an empty kernel bracketed the "
-                                   "same way is subtracted; all launches of the kernel function are pooled"}
+        traffic, traffic_src = ncu_traffic()
+        if fn == "gemm_tc_kernel":
+            # the dominant kernel's time WITHOUT any event-pair correction: its four decode shapes replayed as graphs of
+            # back-to-back launches over the real weights of all six layers (ptts_profile_gemm_replay), one event pair per
+            # graph; pooled over the 24 FlowLM launches of a step (the remaining gemm_tc_kernel launches -- flow head glue
+            # and the short codec GEMMs -- are listed per class below with the event-pair method)
+            rp = eng.gemm_replay(STREAMS, 20)
+            us = sum(v["us"] for v in rp.values()) / 4
+            by = sum(v["bytes"] for v in rp.values()) / 4
+            gbs = by / us / 1e3
+            line["roofline"] = {"kernel": fn, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                                "traffic": traffic.get(fn), "traffic_source": traffic_src, "peak_source": pk["src"],
+                                "us_per_launch": us, "algorithmic_bytes_per_launch": by, "launches_per_step": nl / n_prof,
+                                "share_of_step": f["us"] / tot, "per_shape": rp,
+                                "how": "the FlowLM decode GEMMs (in_proj, out_proj, linear1, linear2; 24 of the step's launches "
+                                       "of this kernel) replayed as captured graphs of 20 x 6 back-to-back launches over the "
+                                       "real weights of every layer, CUDA events around each graph; achieved = algorithmic "
+                                       "bytes (weights + operand rows + epilogue tensors) / mean launch time"}
+        else:
+            gbs, tfs = f["bytes"] / f["us"] / 1e3, f["flops"] / f["us"] / 1e6
+            bound = "hbm" if f["bytes"] / (pk["hbm"] * 1e9) >= f["flops"] / (pk["tf"] * 1e12) else "tensor"
+            line["roofline"] = {"kernel": fn, "bound": bound, "achieved": gbs if bound == "hbm" else tfs,
+                                "peak": pk["hbm"] if bound == "hbm" else pk["tf"], "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                                "frac": (gbs / pk["hbm"]) if bound == "hbm" else (tfs / pk["tf"]),
+                                "traffic": traffic.get(fn), "traffic_source": traffic_src, "peak_source": pk["src"],
+                                "us_per_launch": f["us"] / nl, "us_per_launch_raw": f["us_raw"] / nl,
+                                "event_pair_overhead_us": ovh_us, "share_of_step": f["us"] / tot, "launches_per_step": nl / n_prof,
+                                "algorithmic_bytes_per_launch": f["bytes"] / nl, "algorithmic_flops_per_launch": f["flops"] / nl,
+                                "how": "CUDA events around every launch of 3 mid-utterance decode steps on the engine's stream; the "
+                                       "time of an empty kernel bracketed the same way is subtracted"}
+        # the whole step against the HBM roofline: SURVEY 8(d) algorithmic bytes (weights once + per stream KV read / write,
+        # Mimi KV, conv tails, PCM) over the measured step time
+        l_mean = VOICE_ROWS + TOKENS + (FRAMES - 1) / 2
+        step_bytes = 189.7e6 + STREAMS * (24576.0 * l_mean + 1.02e6 + 0.09e6 + 7680 + 0.2e6)
+        step_us = 1000.0 * ms_dev / FRAMES
+        line["roofline"]["step_frac"] = step_bytes / (step_us * 1e-6) / (pk["hbm"] * 1e9)
+        line["roofline"]["step_algorithmic_bytes"] = step_bytes
+        line["roofline"]["step_us"] = step_us
         line["kernel_functions"] = [{"kernel": k, "launches_per_step": v["launches"] / n_prof, "us_per_step": v["us"] / n_prof,
                                      "share": v["us"] / tot} for k, v in sorted(fns.items(), key=lambda kv: -kv[1]["us"])]
         line["kernel_classes"] = classes
@@ -369,6 +444,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=STREAMS,
                     help="concurrent streams per GPU (default 64 = BASELINE configs[1]; 256/512 explore configs[3]/[4] shapes)")
+    ap.add_argument("--longform", type=int, default=512,
+                    help="requests per GPU of the configs[4] slice run through the native scheduler (0 = skip); reported under `longform`")
     ap.add_argument("--int8", action="store_true",
                     help="per-tensor int8 weights (reference quantize.rs scheme), one-byte codes expanded in the decode GEMMs: configs[3] with --streams 256")
     args = ap.parse_args()

@@ -65,6 +65,10 @@ int32_t ptts_test_convtr1d(int32_t device, const float* x, const float* prev_row
                            const float* bias, float* y /*[n,t*s,cout]*/, int32_t n, int32_t t, int32_t cin,
                            int32_t cout, int32_t stride);
 
+/* Kernel time of the decode GEMMs free of per-launch event cost: in_proj / out_proj / linear1 / linear2 at `rows` batch
+ * rows replayed as one graph of iters x 6 layers of back-to-back launches per kind (real weights of every layer in turn, so
+ * each launch streams its weights from HBM), one event pair around the graph.  us_out[4], bytes_out[4] (algorithmic). */
+int32_t ptts_profile_gemm_replay(ptts_engine* e, int32_t rows, int32_t iters, float* us_out, double* bytes_out);
 /* The device noise generator on its own: out[frames * 32] = the N(0, 1) draws a stream with this seed would get
  * (before the sqrt(temp) scale); tests check its distribution. */
 int32_t ptts_test_noise(int32_t device, uint64_t seed, int32_t frames, float* out);

@@ -21,7 +21,7 @@ PRODUCT_SYMBOLS = [
 INTERNAL_SYMBOLS = [
     "ptts_debug_read", "ptts_launch_count", "ptts_step_timed", "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report",
     "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
-    "ptts_test_noise", "ptts_debug_f16_overflow",
+    "ptts_test_noise", "ptts_debug_f16_overflow", "ptts_profile_gemm_replay",
 ]
 SYMBOLS = PRODUCT_SYMBOLS + INTERNAL_SYMBOLS
 
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
     L.ptts_sched_steps.argtypes = [vp]
     L.ptts_sched_steps.restype = i64
     L.ptts_test_noise.argtypes = [i32, C.c_uint64, i32, vp]
+    L.ptts_profile_gemm_replay.argtypes = [vp, i32, i32, vp, vp]
     L.ptts_debug_f16_overflow.argtypes = [vp, C.POINTER(i64)]
     for name in SYMBOLS:
         fn = getattr(L, name)

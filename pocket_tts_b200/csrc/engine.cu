@@ -2030,6 +2030,65 @@ int32_t ptts_profile_overhead(ptts_engine* h, float* ms_out) {
   PTTS_CATCH
 }
 
+// Kernel time of the decode GEMMs without any per-launch event cost: the four FlowLM Linears of a step (in_proj,
+// out_proj, linear1, linear2 at `rows` batch rows) replayed as ONE captured graph of iters x 6 layers of back-to-back
+// launches per kind -- real weights of all six layers in turn, so every launch streams its weights from HBM like in a
+// step (151 MB per round trip > L2) -- bracketed by a single event pair.  us_out[4] = mean us per launch per kind,
+// bytes_out[4] = algorithmic bytes per launch.  Launches are the production path (Engine::gemm, PDL on).
+int32_t ptts_profile_gemm_replay(ptts_engine* h, int32_t rows, int32_t iters, float* us_out, double* bytes_out) {
+  PTTS_TRY
+  PTTS_REQUIRE(h && us_out && rows >= 1 && iters >= 1, PTTS_ERR_INVALID, "ptts_profile_gemm_replay: bad arguments");
+  Engine& e = h->e;
+  PTTS_REQUIRE(rows <= e.NB, PTTS_ERR_INVALID, "rows %d beyond max_batch %d", rows, e.NB);
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  e.sync_all();
+  e.ls = e.stream;
+  const bool was = e.profiling;
+  e.profiling = false;
+  cudaEvent_t a, b;
+  PTTS_CUDA(cudaEventCreate(&a)); PTTS_CUDA(cudaEventCreate(&b));
+  for (int kind = 0; kind < 4; ++kind) {
+    auto one = [&](int l) {
+      GemmEpi ep = epi_none();
+      if (kind == 0) { ep.out32 = e.qkv32.p; ep.out32_map = plain_map(3 * D_MODEL); e.gemm_rows(e.h16.p, rows, D_MODEL, e.w_inproj[l], 3 * D_MODEL, ep); }
+      else if (kind == 1) { ep.out32 = e.x32.p; ep.out32_map = plain_map(D_MODEL); ep.res = e.x32.p; ep.res_map = plain_map(D_MODEL);
+                            e.gemm_rows(e.attn16.p, rows, D_MODEL, e.w_outproj[l], D_MODEL, ep, true); }
+      else if (kind == 2) { ep.act = ACT_GELU; ep.out16 = e.ffn16.p; ep.out16_map = plain_map(D_FFN); e.split_cap_override = e.lin1_ctas;
+                            e.gemm_rows(e.h16.p, rows, D_MODEL, e.w_lin1[l], D_FFN, ep); }
+      else { ep.out32 = e.x32.p; ep.out32_map = plain_map(D_MODEL); ep.res = e.x32.p; ep.res_map = plain_map(D_MODEL);
+             e.gemm_rows(e.ffn16.p, rows, D_FFN, e.w_lin2[l], D_MODEL, ep, true); }
+    };
+    for (int l = 0; l < N_LAYERS; ++l) one(l);  // warm (tensor maps, instruction cache)
+    PTTS_CUDA(cudaStreamSynchronize(e.stream));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    PTTS_CUDA(cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal));
+    for (int it = 0; it < iters; ++it) for (int l = 0; l < N_LAYERS; ++l) one(l);
+    PTTS_CUDA(cudaStreamEndCapture(e.stream, &g));
+    PTTS_CUDA(cudaGraphInstantiate(&ge, g, 0));
+    PTTS_CUDA(cudaGraphLaunch(ge, e.stream));  // once untimed
+    PTTS_CUDA(cudaEventRecord(a, e.stream));
+    PTTS_CUDA(cudaGraphLaunch(ge, e.stream));
+    PTTS_CUDA(cudaEventRecord(b, e.stream));
+    PTTS_CUDA(cudaStreamSynchronize(e.stream));
+    float ms = 0;
+    PTTS_CUDA(cudaEventElapsedTime(&ms, a, b));
+    us_out[kind] = 1000.f * ms / (float)(iters * N_LAYERS);
+    cudaGraphExecDestroy(ge); cudaGraphDestroy(g);
+    if (bytes_out) {
+      const double F = kind == 0 ? 3.0 * D_MODEL : kind == 2 ? (double)D_FFN : (double)D_MODEL, K = kind == 3 ? (double)D_FFN : (double)D_MODEL;
+      const double outb = kind == 0 ? 4 : kind == 2 ? 2 : 8;  // f32 out | f16 out | f32 residual in + out
+      bytes_out[kind] = F * K * 2 + (double)rows * K * 2 + (double)rows * F * outb;
+    }
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  e.launches -= 0;
+  e.profiling = was;
+  // the replay scribbled over the residual stream / operand buffers of the decode scratch; they are rebuilt by the next step
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
 int64_t ptts_profile_report(ptts_engine* h, char* buf, int64_t cap) {
   try {
     PTTS_REQUIRE(h && buf && cap > 0, PTTS_ERR_INVALID, "null argument");
@@ -2370,7 +2429,12 @@ int32_t ptts_sched_run(ptts_sched* s, int32_t pcm_i16) {
   PTTS_CUDA(cudaSetDevice(e.cfg.device));
   const int pcm_flag = pcm_i16 ? PTTS_STEP_PCM_I16 : PTTS_STEP_PCM;
   const size_t NR = s->reqs.size();
-  for (auto& r : s->reqs) { r.cursor = 0; r.out32.clear(); r.out16.clear(); }
+  for (auto& r : s->reqs) {
+    r.cursor = 0; r.out32.clear(); r.out16.clear();
+    size_t cap = 0;  // upper bound of the request's samples: no reallocation (a 60 s request is 2.9 MB of i16) in the loop
+    for (auto& g : r.segs) cap += g.kind == PTTS_SEG_PAUSE ? (size_t)g.pause_ms * 24 : (size_t)g.params.max_gen_len * FRAME;
+    if (pcm_i16) r.out16.reserve(cap); else r.out32.reserve(cap);
+  }
   s->steps = 0;
   std::vector<int> waiting(NR);
   for (size_t i = 0; i < NR; ++i) waiting[i] = (int)i;
@@ -2412,8 +2476,6 @@ int32_t ptts_sched_run(ptts_sched* s, int32_t pcm_i16) {
   struct Flight { long long ticket; std::vector<int> slots; };
   std::vector<Flight> inflight;
   std::vector<uint8_t> fin;
-  std::vector<float> pcm32;
-  std::vector<int16_t> pcm16;
   auto begin = [&](const std::vector<int>& slots, bool ahead) {
     const long long t = step_begin_impl(e, slots.data(), (int)slots.size(), pcm_flag | (ahead ? PTTS_STEP_AHEAD : 0));
     for (int sl : slots) --budget[sl];
@@ -2427,13 +2489,16 @@ int32_t ptts_sched_run(ptts_sched* s, int32_t pcm_i16) {
     const int n = (int)f.slots.size();
     fin.assign(n, 0);
     step_flags_impl(e, f.ticket, fin.data(), nullptr, nullptr);
-    if (pcm_i16) { pcm16.resize((size_t)n * FRAME); step_pcm_impl(e, f.ticket, nullptr, pcm16.data()); }
-    else { pcm32.resize((size_t)n * FRAME); step_pcm_impl(e, f.ticket, pcm32.data()); }
+    // rows go straight from the pinned landing buffer of the step to their request (no intermediate frame copy)
+    step_pcm_impl(e, f.ticket, nullptr);
+    const int par = (int)(f.ticket % Engine::NT);
+    const int16_t* src16 = e.pin_pcm16[par];
+    const float* src32 = e.pin_pcm[par];
     for (int i = 0; i < n; ++i) {
       if (fin[i] == PTTS_FRAME_OVERRUN) continue;
       ptts_sched::Req& r = s->reqs[owner[f.slots[i]]];
-      if (pcm_i16) r.out16.insert(r.out16.end(), pcm16.begin() + (size_t)i * FRAME, pcm16.begin() + (size_t)(i + 1) * FRAME);
-      else r.out32.insert(r.out32.end(), pcm32.begin() + (size_t)i * FRAME, pcm32.begin() + (size_t)(i + 1) * FRAME);
+      if (pcm_i16) r.out16.insert(r.out16.end(), src16 + (size_t)i * FRAME, src16 + (size_t)(i + 1) * FRAME);
+      else r.out32.insert(r.out32.end(), src32 + (size_t)i * FRAME, src32 + (size_t)(i + 1) * FRAME);
       if (fin[i] && std::find(done.begin(), done.end(), f.slots[i]) == done.end()) done.push_back(f.slots[i]);
     }
   };

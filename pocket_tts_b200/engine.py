@@ -236,6 +236,13 @@ class Engine:
             out[tag] = dict(fn=fn, launches=int(cnt), ms=float(ms), bytes=float(by), flops=float(fl))
         return out
 
+    def gemm_replay(self, rows: int, iters: int = 20) -> dict[str, dict]:
+        """ptts_profile_gemm_replay: {kind: {us, bytes}} for the four FlowLM decode GEMMs, graph-replayed."""
+        us = np.zeros(4, np.float32)
+        by = np.zeros(4, np.float64)
+        check(_lib.lib().ptts_profile_gemm_replay(self._h, rows, iters, _ptr(us), _ptr(by)))
+        return {k: {"us": float(u), "bytes": float(b)} for k, u, b in zip(("in_proj", "out_proj", "linear1", "linear2"), us, by)}
+
     def profile_overhead_us(self) -> float:
         v = C.c_float()
         check(_lib.lib().ptts_profile_overhead(self._h, C.byref(v)))

@@ -1,6 +1,6 @@
-"""Probe (not a test): BASELINE configs[4] per-GPU slice through the public scheduler -- `requests` concurrent long-form
-requests of 6 chunks x 125 frames (60 s of speech) with a 300 ms `[pause:..]` between chunks, continuous batching on one
-engine (tts_model.BatchScheduler), PCM of every frame copied back to the host."""
+"""Probe (not a test): BASELINE configs[4] per-GPU slice -- `requests` concurrent long-form requests of 6 chunks x 125 frames
+(60 s of speech) with a 300 ms `[pause:..]` between chunks, continuous batching on one engine, PCM of every frame copied
+back to the host.  python tests/longform_probe.py [requests] [python|ahead|native|native16]"""
 import sys
 import time
 from pathlib import Path
@@ -13,7 +13,7 @@ from pocket_tts_b200.engine import Engine, StreamSpec
 from pocket_tts_b200.tts_model import BatchScheduler
 
 requests_n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-ahead = len(sys.argv) > 2 and sys.argv[2] == "ahead"   # device kept one step ahead of the host loop
+mode = sys.argv[2] if len(sys.argv) > 2 else "native16"
 chunks, frames, tokens, pause_ms = 6, 125, 40, 300
 eng = Engine(synth.make_weights(1234), max_slots=requests_n, kv_capacity=tokens + frames + 3)
 voice = eng.voice_from_prompt(synth.make_voice_prompt(87, seed=7))
@@ -27,10 +27,10 @@ for r in range(requests_n):
     reqs.append(segs)
 sched = BatchScheduler(eng, voice)
 t0 = time.perf_counter()
-out = sched.run(reqs, ahead=ahead)
+out = sched.run(reqs, ahead=mode == "ahead", native=mode.startswith("native"), i16=mode == "native16")
 dt = time.perf_counter() - t0
 want = chunks * frames * 1920 + (chunks - 1) * pause_ms * 24
-assert all(o.shape == (want,) for o in out) and all(np.isfinite(o).all() for o in out[:4])
+assert all(o.shape == (want,) for o in out) and all(np.isfinite(o.astype(np.float32)).all() for o in out[:4])
 audio_s = requests_n * want / 24000.0
-print(f"[{'ahead' if ahead else 'lock-step'}] {requests_n} requests x {want / 24000:.1f} s = {audio_s:.0f} audio-s in {dt:.2f} s wall -> {audio_s / dt:.0f} audio-s per wall-s "
+print(f"[{mode}] {requests_n} requests x {want / 24000:.1f} s = {audio_s:.0f} audio-s in {dt:.2f} s wall -> {audio_s / dt:.0f} audio-s per wall-s "
       f"(speech only: {requests_n * chunks * frames * 0.08 / dt:.0f}), launches {eng.launch_count()}")
