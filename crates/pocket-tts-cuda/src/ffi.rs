@@ -76,6 +76,7 @@ extern "C" {
     pub fn ptts_engine_create(cfg: *const ptts_engine_cfg, weights: *const ptts_tensor_desc, n_weights: i32, out: *mut *mut ptts_engine) -> i32;
     pub fn ptts_engine_destroy(e: *mut ptts_engine);
     pub fn ptts_engine_set_lsd_steps(e: *mut ptts_engine, lsd_steps: i32) -> i32;
+    pub fn ptts_engine_set_codec_group(e: *mut ptts_engine, frames: i32) -> i32;
     pub fn ptts_config_check(yaml_path: *const c_char) -> i32;
 
     pub fn ptts_voice_from_prompt(e: *mut ptts_engine, audio_prompt: *const f32, n_rows: i32, out: *mut *mut ptts_voice) -> i32;

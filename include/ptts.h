@@ -95,6 +95,15 @@ void ptts_engine_destroy(ptts_engine* e);
  * embeddings (SimpleMLPAdaLN::compute_time_embeddings, modules/mlp.rs:296-319). */
 int32_t ptts_engine_set_lsd_steps(ptts_engine* e, int32_t lsd_steps);
 
+/* Frames per codec pass: 1 (default), 2 or 4.  The reference decodes every latent the moment it is generated
+ * (mimi.decode_from_latent inside the frame loop, tts_model.rs:1033-1047); nothing in the language model waits for that
+ * audio, and the Mimi decoder is streaming (conv.rs:90-136,219-267; attention.rs:167-264), so `frames` consecutive
+ * latents of the same batch may be decoded by one pass with bit-identical PCM.  With frames > 1 a step's PCM leaves the
+ * device when its group is complete -- or earlier, when ptts_step_pcm asks for it, the batch composition changes, a
+ * stream is opened or closed, or ptts_sync is called (a partial group is decoded then).  Re-sizes the codec scratch:
+ * call it with no step in flight. */
+int32_t ptts_engine_set_codec_group(ptts_engine* e, int32_t frames);
+
 /* Replaces TTSModel::get_voice_state_from_prompt_tensor (tts_model.rs:490-501, which runs
  * run_flow_lm_prompt :580-599): FlowLM prefill over audio_prompt [T,1024] f32 (host);
  * the resulting KV snapshot is immutable and shared by every stream opened with it. */

@@ -11,6 +11,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libptts_cuda.so"
 # checks both headers against these lists
 PRODUCT_SYMBOLS = [
     "ptts_last_error", "ptts_abi_version", "ptts_engine_create", "ptts_engine_destroy", "ptts_engine_set_lsd_steps",
+    "ptts_engine_set_codec_group",
     "ptts_voice_from_prompt", "ptts_voice_from_pcm", "ptts_audio_prompt_from_pcm", "ptts_voice_destroy", "ptts_voice_len",
     "ptts_voice_save", "ptts_voice_load", "ptts_config_check",
     "ptts_streams_open", "ptts_step", "ptts_step_begin", "ptts_step_flags", "ptts_step_pcm", "ptts_step_pcm_i16", "ptts_step_device",
@@ -65,6 +66,7 @@ def lib() -> C.CDLL:
     L.ptts_engine_destroy.argtypes = [vp]
     L.ptts_engine_destroy.restype = None
     L.ptts_engine_set_lsd_steps.argtypes = [vp, i32]
+    L.ptts_engine_set_codec_group.argtypes = [vp, i32]
     L.ptts_voice_from_prompt.argtypes = [vp, vp, i32, C.POINTER(vp)]
     L.ptts_voice_from_pcm.argtypes = [vp, vp, i32, C.POINTER(vp)]
     L.ptts_audio_prompt_from_pcm.argtypes = [vp, vp, i32, vp, i32, C.POINTER(i32)]

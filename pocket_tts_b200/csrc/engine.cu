@@ -111,6 +111,7 @@ struct Engine {
   int split_cta_cap = 48;   // a split-K decode (swap-AB) GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
   int split_cta_cap_b = 48; // the same for the activation-as-M GEMMs of the codec half (PTTS_MAX_CTAS_B)
   int split_cap_override = 0;  // one-shot cap for the next GEMM
+  int gemm_ref_f = 1;          // > 1 while the GEMMs of a codec group of that many frames are issued (see Engine::gemm)
   int lin1_ctas = 48;          // linear1 (32 feature tiles): 64 lets it split in two and keep its K slice resident (PTTS_LIN1_CTAS)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int lsd_steps = 1;
@@ -217,19 +218,33 @@ struct Engine {
   struct { float* p; } latent_out, logit_out;
   struct { unsigned char* p; } finished_dev;
   size_t step_out_bytes() const { return (size_t)NB * (LDIM * 4 + 4 + 1); }
-  ConvSegs segs{};
+  ConvSegs segs{};             // one frame per codec pass (also what stream open zeroes)
+  ConvSegs segs_by_f[5]{};     // [frames per codec pass]
+  const ConvSegs& segs_f(int f) const { return segs_by_f[f]; }
+  // ---- codec group (set_codec_group): A queues the latents of cg consecutive frames, the codec half runs once per group
+  int cg = 1;                  // frames per codec pass
+  int pend = 0, pend_n = 0;    // frames waiting in the current queue buffer, their batch rows
+  int gbuf = 0;                // queue buffer the current group fills
+  std::vector<int> pend_rows;  // batch composition of the waiting frames
+  long long pend_ticket[4] = {-1, -1, -1, -1};
+  DevBuf<float> zq;            // [2][cg][NB][32]
+  DevBuf<int> zq_pos;          // [2][cg][NB] frame index of the queued latent
+  float* cur_zq = nullptr; int* cur_zqpos = nullptr;   // queue entry step_part_a writes (null: none)
+  cudaEvent_t ev_gfront[2] = {};
+  void flush_codec();
+  void set_codec_group(int frames);
   // ---- prefill scratch
   DevBuf<float> px32, pqkv32, pqrot;
   DevBuf<__half> ph16, pattn16, pffn16;
   DevBuf<int> prow_seq, prow_pos, ptokens;
   // ---- pinned staging
-  // a ring of three tickets: with PTTS_STEP_AHEAD step n+1 is enqueued while the flags of step n and the PCM of
-  // step n-1 are still on their way to the host
-  static constexpr int NT = 3;
+  // a ring of tickets: with PTTS_STEP_AHEAD step n+1 is enqueued while the flags of step n and the PCM of step n-1 are
+  // still on their way to the host; with a codec group the PCM of a frame leaves with its group, up to cg - 1 steps later
+  static constexpr int NT = 6;
   float* pin_pcm[NT] = {}; unsigned char* pin_fin[NT] = {};
   float* pin_lat[NT] = {}; float* pin_logit[NT] = {};
   cudaEvent_t ev_flags[NT] = {}, ev_pcm[NT] = {};
-  struct Ticket { long long id = -1; int n = 0; bool flags_done = true, pcm_done = true, want_pcm = false, want_i16 = false; std::vector<int> slot_ids; };
+  struct Ticket { long long id = -1; int n = 0; bool flags_done = true, pcm_done = true, want_pcm = false, want_i16 = false, codec_pending = false; std::vector<int> slot_ids; };
   Ticket tickets[NT];
   // a ticket whose flags have not been fetched still lists its slots: closing / reopening one of them in between would make
   // step_flags_impl book the overrun row of the OLD stream onto the NEW one
@@ -240,7 +255,7 @@ struct Engine {
     return false;
   }
   long long next_ticket = 0;
-  void sync_all() { PTTS_CUDA(cudaStreamSynchronize(stream)); PTTS_CUDA(cudaStreamSynchronize(stream_b)); }
+  void sync_all() { flush_codec(); PTTS_CUDA(cudaStreamSynchronize(stream)); PTTS_CUDA(cudaStreamSynchronize(stream_b)); }
   cudaEvent_t ev[10]{};
 
   ~Engine();
@@ -264,12 +279,15 @@ struct Engine {
   void upload_rows(const int* slot_ids, int n);
   void step_kernels(int n, float* stage_ms);
   void step_part_a(int n, bool marks);
-  void step_front(int n);
-  void step_part_b(int n, bool marks);
-  cudaGraphExec_t capture(cudaStream_t st, int n, int part, long long* kernels);
-  void run_step(int n);
-  struct StepGraph { cudaGraphExec_t a, b; long long kernels_a, kernels_b; };
-  std::map<std::pair<int, int>, StepGraph> graphs;  // (batch rows, lsd steps) -> captured decode step
+  void step_front(int n, int f, int qbuf);
+  void step_part_b(int n, int f, bool marks);
+  cudaGraphExec_t capture(cudaStream_t st, int n, int part, int arg, long long* kernels);
+  void run_step(int n, long long ticket = -1);
+  struct PartGraph { cudaGraphExec_t exec; long long kernels; };
+  // (part, batch rows, lsd steps [A only], queue entry [A] | frames per row [B]) -> captured half of a decode step
+  std::map<std::tuple<int, int, int, int>, PartGraph> graphs;
+  PartGraph& graph_of(int part, int n, int arg);
+  void drop_graphs();
   void prefill(int rows);
 };
 
@@ -284,7 +302,8 @@ Engine::~Engine() {
   for (int i = 0; i < 2; ++i) { if (pin_open[i]) cudaFreeHost(pin_open[i]); if (ev_open[i]) cudaEventDestroy(ev_open[i]); }
   for (auto& e : ev) if (e) cudaEventDestroy(e);
   for (auto& e : prof_pool) cudaEventDestroy(e);
-  for (auto& g : graphs) { cudaGraphExecDestroy(g.second.a); cudaGraphExecDestroy(g.second.b); }
+  for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+  for (auto& x : ev_gfront) if (x) cudaEventDestroy(x);
   if (ev_a_done) cudaEventDestroy(ev_a_done);
   if (ev_front_done) cudaEventDestroy(ev_front_done);
   if (ev_b_done) cudaEventDestroy(ev_b_done);
@@ -743,16 +762,6 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   fx32.alloc(NBP * FLOW_DIM); y16.alloc((size_t)NB * FLOW_DIM); fh16.alloc(NBP * FLOW_DIM);
   fg16.alloc(NBP * FLOW_DIM); z32.alloc(NBP * LDIM); z16.alloc(NBP * 64);
   mimi_pos.alloc(NB);
-  const size_t MR = (size_t)NB * MIMI_T;
-  mx32.alloc(MR * MIMI_DIM); mqkv32.alloc(MR * 3 * MIMI_DIM); mh16.alloc(MR * MIMI_DIM); mattn16.alloc(MR * MIMI_DIM);
-  mffn16.alloc(MR * MIMI_FFN);
-  tr16.alloc((size_t)NB * 22 * 512); a0.alloc((size_t)NB * 17 * 512);
-  x2.alloc((size_t)NB * 96 * 256); e2.alloc((size_t)NB * 98 * 256); h3.alloc((size_t)NB * 96 * 128);
-  a3.alloc((size_t)NB * 97 * 256); x5.alloc((size_t)NB * 480 * 128); e5.alloc((size_t)NB * 482 * 128);
-  h6.alloc((size_t)NB * 480 * 64); a6.alloc((size_t)NB * 481 * 128); x8.alloc((size_t)NB * 1920 * 64);
-  e8.alloc((size_t)NB * 1922 * 64); h9.alloc((size_t)NB * 1920 * 64); a9.alloc((size_t)NB * 1922 * 64);
-  pcm.alloc((size_t)NB * FRAME);
-  pcm16.alloc((size_t)NB * FRAME);
   open_recs.alloc(NS);
   for (int i = 0; i < 2; ++i) {
     PTTS_CUDA(cudaMallocHost(&pin_open[i], (size_t)NS * sizeof(OpenRec)));
@@ -764,14 +773,12 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   latent_out.p = reinterpret_cast<float*>(step_out.p);
   logit_out.p = latent_out.p + (size_t)NB * LDIM;
   finished_dev.p = reinterpret_cast<unsigned char*>(logit_out.p + NB);
-  segs.s[0] = ConvSeg{tr16.p, st_tr.p, 6, 16, 512, 0};
-  segs.s[1] = ConvSeg{a0.p, st_a0.p, 1, 16, 512, 0};
-  segs.s[2] = ConvSeg{e2.p, st_e2.p, 2, 96, 256, 0};
-  segs.s[3] = ConvSeg{a3.p, st_a3.p, 1, 96, 256, 0};
-  segs.s[4] = ConvSeg{e5.p, st_e5.p, 2, 480, 128, 0};
-  segs.s[5] = ConvSeg{a6.p, st_a6.p, 1, 480, 128, 0};
-  segs.s[6] = ConvSeg{e8.p, st_e8.p, 2, 1920, 64, 0};
-  segs.s[7] = ConvSeg{a9.p, st_a9.p, 2, 1920, 64, 0};
+  for (auto& x : ev_gfront) PTTS_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+  {
+    int frames = 1;
+    if (const char* v = std::getenv("PTTS_CODEC_GROUP")) frames = std::atoi(v);
+    set_codec_group(frames == 2 || frames == 4 ? frames : 1);
+  }
 
   px32.alloc((size_t)PR * D_MODEL); pqkv32.alloc((size_t)PR * 3 * D_MODEL); pqrot.alloc((size_t)PR * D_MODEL);
   ph16.alloc((size_t)PR * D_MODEL); pattn16.alloc((size_t)PR * D_MODEL); pffn16.alloc((size_t)PR * D_FFN);
@@ -814,50 +821,80 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   p.act = a.ptr; p.act_stream_stride = (long long)a.Tpad * a.C; p.act_ld = a.C; p.w = w.w.p;
   const int total_kb = p.taps * p.cblocks;
   const bool plain = (taps == 1 && n_streams == 1);
-  int force = cfg.reserved[0];  // test hook: 1 = never swap, 2 = always swap when legal
-  bool swap = plain && rows <= 256 && force != 1;
-  if (plain && !swap) { R = 128; G = 1; }
-  dim3 grid;
-  bool persistent = false;
-  if (swap) {
-    p.swap = 1;
-    p.BN = std::max(16, round_up((int)rows, 16));
-    p.n_streams = 1; p.T = (int)rows; p.R = p.BN; p.G = 1;
-    grid = dim3(w.Fpad / 128, 1, 1);
-  } else {
-    p.swap = 0;
-    PTTS_REQUIRE(R > 0 && G > 0 && R * G <= 128, PTTS_ERR_INVALID, "gemm: bad tile geometry R %d G %d", R, G);
-    p.n_streams = n_streams; p.T = T; p.R = R; p.G = G;
-    const int act_tiles = ((T + R - 1) / R) * ((n_streams + G - 1) / G);
-    p.n_act_tiles = act_tiles;
+  const int force = cfg.reserved[0];  // test hook: 1 = never swap, 2 = always swap when legal
+  // tile geometry of a GEMM over `rows_g` rows (n_streams x T_g, tiles of G_g streams x R_g rows): operand placement,
+  // persistent or one CTA per tile, feature-tile width, grid
+  struct Geo { bool swap, persistent; int R, G, bn, act_tiles; dim3 grid; };
+  auto geometry = [&](long long rows_g, int T_g, int R_g, int G_g) {
+    Geo g{};
+    g.swap = plain && rows_g <= 256 && force != 1;
+    if (plain && !g.swap) { R_g = 128; G_g = 1; }
+    g.R = R_g; g.G = G_g;
+    if (g.swap) {
+      g.bn = std::max(16, round_up((int)rows_g, 16));
+      g.grid = dim3(w.Fpad / 128, 1, 1);
+      return g;
+    }
+    PTTS_REQUIRE(R_g > 0 && G_g > 0 && R_g * G_g <= 128, PTTS_ERR_INVALID, "gemm: bad tile geometry R %d G %d", R_g, G_g);
+    g.act_tiles = ((T_g + R_g - 1) / R_g) * ((n_streams + G_g - 1) / G_g);
     const int fcap = round_up(F, 16);
-    int bn;
-    if (act_tiles >= 148 && cfg.reserved[3] != 1) {
+    if (g.act_tiles >= 148 && cfg.reserved[3] != 1) {
       // enough activation tiles to give every SM several: persistent kernel, accumulator double-buffered in TMEM
-      bn = std::min(128, fcap);
-      persistent = true;
+      g.bn = std::min(128, fcap);
+      g.persistent = true;
     } else {
       // largest tile that still leaves at least ~half the SMs busy: one wave of fat tiles beats two of thin ones
-      bn = std::min(256, fcap);
-      while (bn > 64 && (long long)act_tiles * ((F + bn - 1) / bn) < 74) bn >>= 1;
-      bn = std::min(round_up(bn, 16), fcap);
+      int bn = std::min(256, fcap);
+      while (bn > 64 && (long long)g.act_tiles * ((F + bn - 1) / bn) < 74) bn >>= 1;
+      g.bn = std::min(round_up(bn, 16), fcap);
     }
-    p.BN = bn;
-    grid = dim3(act_tiles, (F + bn - 1) / bn, 1);
-    if (persistent) grid.x = std::min(act_tiles, std::max(1, persistent_ctas / (int)grid.y));
-  }
+    g.grid = dim3(g.act_tiles, (F + g.bn - 1) / g.bn, 1);
+    return g;
+  };
   // Split-K whenever the output tiles alone cannot fill the chip (decode batches: 64 rows x F features is only
   // F/128 tiles): a cluster of `splits` CTAs along z shares one output tile (gemm.cuh), at most 8 (portable size).
-  (void)allow_split;
-  int splits = 1;
-  const int tiles = grid.x * grid.y;
   // power-of-two cluster sizes only (they pack into a GPC), and the whole grid must fit one wave with slack for
   // cluster placement: 24 tiles x 4 (96 CTAs) beats 24 x 6 (144 CTAs, measured 8.5 vs 15 us)
-  if (!persistent && total_kb >= 4) {
-    int cap = swap ? split_cta_cap : split_cta_cap_b;
-    if (split_cap_override > 0) cap = split_cap_override;
-    split_cap_override = 0;
-    while (splits * 2 <= GEMM_MAX_SPLIT && tiles * splits * 2 <= cap && splits * 2 <= total_kb / 2) splits *= 2;
+  (void)allow_split;
+  int cap_override = split_cap_override;
+  split_cap_override = 0;
+  auto split_of = [&](const Geo& g) {
+    int sp = 1;
+    const int tiles = g.grid.x * g.grid.y;
+    if (!g.persistent && total_kb >= 4) {
+      int cap = g.swap ? split_cta_cap : split_cta_cap_b;
+      if (cap_override > 0) cap = cap_override;
+      while (sp * 2 <= GEMM_MAX_SPLIT && tiles * sp * 2 <= cap && sp * 2 <= total_kb / 2) sp *= 2;
+    }
+    return sp;
+  };
+  Geo geo = geometry(rows, T, R, G);
+  int splits = split_of(geo);
+  if (gemm_ref_f > 1) {
+    // Codec group of f frames: the K split decides the order in which an output element's partial sums are added, so it is
+    // taken from the geometry the SAME call has with one frame per row -- the PCM of a group is then bit-identical to
+    // that of f single-frame passes.  (A tile's own K loop is the same sequence of k-blocks whatever the tile shape.)
+    const int f = gemm_ref_f;
+    const bool whole = (T == R);   // tiles of whole streams: one frame per row has 1/f of the rows and f times the streams per tile
+    const Geo ref = geometry(rows / f, T / f, whole ? R / f : R, whole ? std::min(G * f, 128 / std::max(1, R / f)) : G);
+    splits = split_of(ref);
+    if (splits > 1) geo.persistent = false;
+    if (!geo.swap && !geo.persistent) geo.grid = dim3(geo.act_tiles, (F + geo.bn - 1) / geo.bn, 1);
+  }
+  const bool swap = geo.swap;
+  bool persistent = geo.persistent;
+  dim3 grid = geo.grid;
+  if (swap) {
+    p.swap = 1;
+    p.BN = geo.bn;
+    p.n_streams = 1; p.T = (int)rows; p.R = p.BN; p.G = 1;
+  } else {
+    p.swap = 0;
+    R = geo.R; G = geo.G;
+    p.n_streams = n_streams; p.T = T; p.R = R; p.G = G;
+    p.n_act_tiles = geo.act_tiles;
+    p.BN = geo.bn;
+    if (persistent) grid.x = std::min(geo.act_tiles, std::max(1, persistent_ctas / (int)grid.y));
   }
   const LnSpec lnreq = next_ln;
   next_ln.set = false;
@@ -981,6 +1018,7 @@ void Engine::upload_rows(const int* slot_ids, int n) {
     step_kv_bytes += (double)((sh.voice ? sh.voice->len : 0) + sh.own_len + 1) * N_HEADS * HD * 2 * 2;
   }
   if ((int)row_seq_host.size() == n && std::equal(slot_ids, slot_ids + n, row_seq_host.begin())) return;
+  flush_codec();   // frames still queued for the codec belong to the old batch map
   PTTS_CUDA(cudaStreamWaitEvent(stream, ev_b_done, 0));  // the codec stream may still be reading the previous batch map
   row_seq_host.assign(slot_ids, slot_ids + n);
   PTTS_CUDA(cudaMemcpyAsync(row_seq.p, row_seq_host.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -1130,7 +1168,7 @@ void Engine::step_part_a(int n, bool marks) {
     for (int s = 0; s < lsd_steps; ++s) flow_head_fused(n, lm_mod.p + (size_t)s * LM_ROWS * MOD_LD);
     { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
       launch_k(use_pdl, step_end_kernel, n, 32, 0, ls, 1, row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
-                                            latent_out.p, logit_out.p); }
+                                            latent_out.p, logit_out.p, cur_zq, cur_zqpos); }
     return;
   }
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
@@ -1188,27 +1226,39 @@ void Engine::step_part_a(int n, bool marks) {
   // ---- EOS bookkeeping, AR feedback, cursors (reference tts_model.rs:1055-1069)
   { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
     launch_k(use_pdl, step_end_kernel, n, 32, 0, ls, 1, row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
-                                          latent_out.p, logit_out.p); }
+                                          latent_out.p, logit_out.p, cur_zq, cur_zqpos); }
 }
 
-void Engine::step_front(int n) {
-  // ---- Mimi: de-norm + quantizer + upsample, decoder transformer (reference mimi.rs:143-157, transformer.rs:227-251)
-  const int MR = n * MIMI_T;
-  { ProfScope ps(*this, "mimi.frontend", (double)n * 16 * 512 * 12, 0);
-    launch_k(use_pdl, mimi_frontend_kernel, dim3(n, 4), 128, 0, ls, 1, z32.p, row_seq.p, ctl.p, emb_std.p, emb_mean.p, wq.p, wup.p, up_partial.p, mx32.p,
-                                               quant_dbg.p, mimi_pos.p); }
+void Engine::step_front(int n, int f, int qbuf) {
+  // ---- Mimi: de-norm + quantizer + upsample (reference mimi.rs:143-157).  f == 0: the single frame A just produced, read
+  // from z32; f >= 1: the f queued frames of codec-group buffer `qbuf`
+  const bool queued = f >= 1;
+  const int nf = queued ? f : 1;
+  const float* zsrc = queued ? zq.p + (size_t)qbuf * cg * NB * LDIM : z32.p;
+  const int* zpos = queued ? zq_pos.p + (size_t)qbuf * cg * NB : nullptr;
+  { ProfScope ps(*this, "mimi.frontend", (double)n * nf * 16 * 512 * 12, 0);
+    launch_k(use_pdl, mimi_frontend_kernel, dim3(n, 4, nf), 128, 0, ls, 1, zsrc, (long long)NB * LDIM, zpos, row_seq.p, ctl.p, emb_std.p, emb_mean.p,
+             wq.p, wup.p, up_partial.p, mx32.p, quant_dbg.p, mimi_pos.p); }
 }
 
-void Engine::step_part_b(int n, bool marks) {
-  const int MR = n * MIMI_T;
+// Codec half for f consecutive frames of every row (f = 1: one frame).  Every buffer is [row][frames of the group][...], so
+// a group is simply a longer chunk of each stream for the streaming convolutions (T = 16 f Mimi positions) -- the same
+// arithmetic per output element as f single-frame passes.
+void Engine::step_part_b(int n, int f, bool marks) {
+  const int T1 = MIMI_T * f, T2 = 96 * f, T3 = 480 * f, T4 = FRAME * f;
+  const int MR = n * T1;
+  const int R1 = std::min(T1, 128), G1 = std::max(1, 128 / T1);   // rows per stream and streams per 128-row tile at 12.5 Hz x 16
+  const ConvSegs& sg = segs_f(f);
+  struct RefF { int& v; ~RefF() { v = 1; } } ref_guard{gemm_ref_f};
+  gemm_ref_f = f;
   GemmEpi e = epi_none();
   tag("mimi.layernorm"); ln<MIMI_DIM>(mx32.p, MR, m_ln1_w[0].p, m_ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
   for (int l = 0; l < MIMI_LAYERS; ++l) {
     e = epi_none();
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
     tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
-    { ProfScope ps(*this, "mimi.attn", (double)n * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0, "mimi_attn_kernel");
-      launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), MATTN_THREADS, MATTN_SMEM, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p); }
+    { ProfScope ps(*this, "mimi.attn", (double)n * f * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0, "mimi_attn_kernel");
+      launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), MATTN_THREADS, MATTN_SMEM, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p, f); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
     ln_after_next_gemm("mimi.layernorm", mx32.p, MR, MIMI_DIM, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
@@ -1220,7 +1270,7 @@ void Engine::step_part_b(int n, bool marks) {
     e.fscale = m_ls2[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
     const bool last = (l == MIMI_LAYERS - 1);
     if (last) {  // also emit the f16 operand of SEANet's first conv behind its 6 left-context rows
-      e.out16 = tr16.p; e.out16_map = stream_map(16, 512, 22 * 512, 6 * 512);
+      e.out16 = tr16.p; e.out16_map = stream_map(T1, 512, (long long)(6 + T1) * 512, 6 * 512);
     }
     if (!last)
       ln_after_next_gemm("mimi.layernorm", mx32.p, MR, MIMI_DIM, m_ln1_w[l + 1].p, m_ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
@@ -1229,40 +1279,40 @@ void Engine::step_part_b(int n, bool marks) {
   if (marks) PTTS_CUDA(cudaEventRecord(ev[3], ls));
   // ---- SEANet decoder (reference seanet.rs:309-402) as implicit GEMMs; ELU fused into the producer's epilogue
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
-    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, segs, row_seq.p, 0); }
-  e = epi_none(); e.bias = sb_conv0.p; e.out16 = a0.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 512, 17 * 512, 512);
-  tag("seanet.conv0"); gemm(ActView{tr16.p, 512, 22, NB}, n, 16, 7, 16, 8, s_conv0, 512, e);
-  e = epi_none(); e.bias = sb_ct2.p; e.out32 = x2.p; e.out32_map = stream_map(16, 1536, 96 * 256, 0);
-  e.out16 = e2.p; e.act16 = ACT_ELU; e.out16_map = stream_map(16, 1536, 98 * 256, 2 * 256);
-  tag("seanet.convtr2"); gemm(ActView{a0.p, 512, 17, NB}, n, 16, 2, 16, 8, s_ct2, 1536, e);
+    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, sg, row_seq.p, 0); }
+  e = epi_none(); e.bias = sb_conv0.p; e.out16 = a0.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T1, 512, (long long)(1 + T1) * 512, 512);
+  tag("seanet.conv0"); gemm(ActView{tr16.p, 512, 6 + T1, NB}, n, T1, 7, R1, G1, s_conv0, 512, e);
+  e = epi_none(); e.bias = sb_ct2.p; e.out32 = x2.p; e.out32_map = stream_map(T1, 1536, (long long)T2 * 256, 0);
+  e.out16 = e2.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T1, 1536, (long long)(2 + T2) * 256, 2 * 256);
+  tag("seanet.convtr2"); gemm(ActView{a0.p, 512, 1 + T1, NB}, n, T1, 2, R1, G1, s_ct2, 1536, e);
   e = epi_none(); e.bias = sb_r3a.p; e.out16 = h3.p; e.act16 = ACT_ELU; e.out16_map = plain_map(128);
-  tag("seanet.res3a"); gemm(ActView{e2.p, 256, 98, NB}, n, 96, 3, 96, 1, s_r3a, 128, e);
+  tag("seanet.res3a"); gemm(ActView{e2.p, 256, 2 + T2, NB}, n, T2, 3, 96, 1, s_r3a, 128, e);
   e = epi_none(); e.bias = sb_r3b.p; e.res = x2.p; e.res_map = plain_map(256);
-  e.out16 = a3.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 256, 97 * 256, 256);
+  e.out16 = a3.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T2, 256, (long long)(1 + T2) * 256, 256);
   // the k1 convs run per stream (T rows each) rather than as one flat [n*T] matrix: the epilogue's affine fast path
   // needs the output map's stream structure to match the GEMM's, and the flat form silently took the row-by-row path
   // with a division per row (res9b: 52 us in the step against 23 us for the same GEMM with plain maps)
-  tag("seanet.res3b"); gemm(ActView{h3.p, 128, 96, NB}, n, 96, 1, 96, 1, s_r3b, 256, e);
-  e = epi_none(); e.bias = sb_ct5.p; e.out32 = x5.p; e.out32_map = stream_map(96, 640, 480 * 128, 0);
-  e.out16 = e5.p; e.act16 = ACT_ELU; e.out16_map = stream_map(96, 640, 482 * 128, 2 * 128);
-  tag("seanet.convtr5"); gemm(ActView{a3.p, 256, 97, NB}, n, 96, 2, 96, 1, s_ct5, 640, e);
+  tag("seanet.res3b"); gemm(ActView{h3.p, 128, T2, NB}, n, T2, 1, 96, 1, s_r3b, 256, e);
+  e = epi_none(); e.bias = sb_ct5.p; e.out32 = x5.p; e.out32_map = stream_map(T2, 640, (long long)T3 * 128, 0);
+  e.out16 = e5.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T2, 640, (long long)(2 + T3) * 128, 2 * 128);
+  tag("seanet.convtr5"); gemm(ActView{a3.p, 256, 1 + T2, NB}, n, T2, 2, 96, 1, s_ct5, 640, e);
   e = epi_none(); e.bias = sb_r6a.p; e.out16 = h6.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
-  tag("seanet.res6a"); gemm(ActView{e5.p, 128, 482, NB}, n, 480, 3, 120, 1, s_r6a, 64, e);
+  tag("seanet.res6a"); gemm(ActView{e5.p, 128, 2 + T3, NB}, n, T3, 3, 120, 1, s_r6a, 64, e);
   e = epi_none(); e.bias = sb_r6b.p; e.res = x5.p; e.res_map = plain_map(128);
-  e.out16 = a6.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 128, 481 * 128, 128);
-  tag("seanet.res6b"); gemm(ActView{h6.p, 64, 480, NB}, n, 480, 1, 120, 1, s_r6b, 128, e);
-  e = epi_none(); e.bias = sb_ct8.p; e.out32 = x8.p; e.out32_map = stream_map(480, 256, 1920 * 64, 0);
-  e.out16 = e8.p; e.act16 = ACT_ELU; e.out16_map = stream_map(480, 256, 1922 * 64, 2 * 64);
-  tag("seanet.convtr8"); gemm(ActView{a6.p, 128, 481, NB}, n, 480, 2, 120, 1, s_ct8, 256, e);
+  e.out16 = a6.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T3, 128, (long long)(1 + T3) * 128, 128);
+  tag("seanet.res6b"); gemm(ActView{h6.p, 64, T3, NB}, n, T3, 1, 120, 1, s_r6b, 128, e);
+  e = epi_none(); e.bias = sb_ct8.p; e.out32 = x8.p; e.out32_map = stream_map(T3, 256, (long long)T4 * 64, 0);
+  e.out16 = e8.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T3, 256, (long long)(2 + T4) * 64, 2 * 64);
+  tag("seanet.convtr8"); gemm(ActView{a6.p, 128, 1 + T3, NB}, n, T3, 2, 120, 1, s_ct8, 256, e);
   e = epi_none(); e.bias = sb_r9a.p; e.out16 = h9.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
-  tag("seanet.res9a"); gemm(ActView{e8.p, 64, 1922, NB}, n, 1920, 3, 128, 1, s_r9a, 64, e);
+  tag("seanet.res9a"); gemm(ActView{e8.p, 64, 2 + T4, NB}, n, T4, 3, 128, 1, s_r9a, 64, e);
   e = epi_none(); e.bias = sb_r9b.p; e.res = x8.p; e.res_map = plain_map(64);
-  e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(1920, 64, 1922 * 64, 128);
-  tag("seanet.res9b"); gemm(ActView{h9.p, 64, 1920, NB}, n, 1920, 1, 128, 1, s_r9b, 64, e);
-  { ProfScope ps(*this, "seanet.final_conv", (double)n * (1922.0 * 128 + 1920 * 4), 2.0 * n * 1920 * 192);
-    launch_k(use_pdl, seanet_final_conv_kernel, dim3((FRAME + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, pcm.p, pcm16.p); }
+  e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T4, 64, (long long)(2 + T4) * 64, 128);
+  tag("seanet.res9b"); gemm(ActView{h9.p, 64, T4, NB}, n, T4, 1, 128, 1, s_r9b, 64, e);
+  { ProfScope ps(*this, "seanet.final_conv", (double)n * ((2.0 + T4) * 128 + T4 * 4), 2.0 * n * T4 * 192);
+    launch_k(use_pdl, seanet_final_conv_kernel, dim3((T4 + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, T4, pcm.p, pcm16.p); }
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
-    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, segs, row_seq.p, 1); }
+    launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, sg, row_seq.p, 1); }
 }
 
 // Sequential form on one stream (stage timing, per-launch profiling).
@@ -1270,10 +1320,11 @@ void Engine::step_kernels(int n, float* stage_ms) {
   ls = stream;
   const bool marks = stage_ms != nullptr;
   if (marks) PTTS_CUDA(cudaEventRecord(ev[0], ls));
+  cur_zq = nullptr; cur_zqpos = nullptr;   // the sequential form decodes the frame straight from z32
   step_part_a(n, marks);
   if (marks) PTTS_CUDA(cudaEventRecord(ev[2], ls));
-  step_front(n);
-  step_part_b(n, marks);
+  step_front(n, 0, 0);
+  step_part_b(n, 1, marks);
   if (marks) PTTS_CUDA(cudaEventRecord(ev[4], ls));
   PTTS_CUDA(cudaGetLastError());
   if (stage_ms) {
@@ -1285,14 +1336,19 @@ void Engine::step_kernels(int n, float* stage_ms) {
   }
 }
 
-cudaGraphExec_t Engine::capture(cudaStream_t st, int n, int part, long long* kernels) {
+cudaGraphExec_t Engine::capture(cudaStream_t st, int n, int part, int arg, long long* kernels) {
   const long long before = launches;
   cudaGraph_t g = nullptr;
   ls = st;
   PTTS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
   try {
-    if (part == 0) step_part_a(n, false);
-    else step_part_b(n, false);
+    if (part == 0) {   // arg: queue entry (codec group) the frame's latent goes to, or -1
+      cur_zq = arg >= 0 ? zq.p + (size_t)arg * NB * LDIM : nullptr;
+      cur_zqpos = arg >= 0 ? zq_pos.p + (size_t)arg * NB : nullptr;
+      step_part_a(n, false);
+    } else {           // arg: frames per row
+      step_part_b(n, arg, false);
+    }
   } catch (...) {
     cudaStreamEndCapture(st, &g);
     if (g) cudaGraphDestroy(g);
@@ -1307,12 +1363,76 @@ cudaGraphExec_t Engine::capture(cudaStream_t st, int n, int part, long long* ker
   return exec;
 }
 
+Engine::PartGraph& Engine::graph_of(int part, int n, int arg) {
+  const auto key = std::make_tuple(part, n, lsd_steps * (part == 0), arg);
+  auto it = graphs.find(key);
+  if (it == graphs.end()) {
+    PartGraph pg{};
+    pg.exec = capture(part == 0 ? stream : stream_b, n, part, arg, &pg.kernels);
+    it = graphs.emplace(key, pg).first;
+  }
+  return it->second;
+}
+
+void Engine::drop_graphs() {
+  for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+  graphs.clear();
+}
+
+// Codec half of the frames waiting in the current group buffer (cg > 1): front end + Mimi transformer + SEANet over
+// `pend` frames per row on the codec stream, then the PCM copies the group's tickets asked for.
+void Engine::flush_codec() {
+  if (pend == 0) return;
+  const int n = pend_n, f = pend;
+  PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_a_done, 0));   // recorded behind the group's last A
+  ls = stream_b;
+  if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[2], stream_b));
+  if (diag_skip != 1) {
+    step_front(n, f, gbuf);
+    if (cfg.use_cuda_graph) {
+      PartGraph& pg = graph_of(1, n, f);
+      PTTS_CUDA(cudaGraphLaunch(pg.exec, stream_b));
+      launches += pg.kernels;
+    } else {
+      step_part_b(n, f, false);
+    }
+  }
+  if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[3], stream_b));
+  // the queue of this buffer is consumed by the front end, but the codec scratch (mx32 ... pcm) is shared by both buffers:
+  // the next group's codec is ordered behind this one by the stream itself
+  PTTS_CUDA(cudaEventRecord(ev_gfront[gbuf], stream_b));
+  for (int j = 0; j < f; ++j) {
+    const long long id = pend_ticket[j];
+    if (id < 0) continue;
+    Ticket& t = tickets[id % NT];
+    const int par = (int)(id % NT);
+    if (t.want_i16)
+      PTTS_CUDA(cudaMemcpy2DAsync(pin_pcm16[par], (size_t)FRAME * 2, pcm16.p + (size_t)j * FRAME, (size_t)f * FRAME * 2, (size_t)FRAME * 2, n,
+                                  cudaMemcpyDeviceToHost, stream_b));
+    else if (t.want_pcm)
+      PTTS_CUDA(cudaMemcpy2DAsync(pin_pcm[par], (size_t)FRAME * 4, pcm.p + (size_t)j * FRAME, (size_t)f * FRAME * 4, (size_t)FRAME * 4, n,
+                                  cudaMemcpyDeviceToHost, stream_b));
+    PTTS_CUDA(cudaEventRecord(ev_pcm[par], stream_b));
+    t.codec_pending = false;
+  }
+  PTTS_CUDA(cudaEventRecord(ev_b_done, stream_b));
+  gbuf ^= 1;
+  pend = 0;
+  ls = stream;
+  PTTS_CUDA(cudaGetLastError());
+}
+
 // Enqueue one step: A on `stream`, front + B on `stream_b`, each of A and B replayed as a CUDA graph (the step is
 // ~100 dependent launches of a few microseconds; every pointer is a fixed engine buffer and the batch composition is
-// data, so one pair of graphs per (rows, lsd_steps) serves every step of that size).
-void Engine::run_step(int n) {
+// data, so one graph per (part, rows, lsd_steps, queue entry | frames) serves every step of that shape).
+// cg > 1 (codec group): A leaves the frame's latent in a queue and the codec half runs once per cg frames of the same
+// batch composition -- the streaming convolutions and the windowed attention do not care whether a stream's next 16 cg
+// positions arrive in one call or in cg, and B feeds nothing back into A -- so the codec's ~35 launches are paid once per
+// group.  A change of composition, a PCM fetch, close / open and ptts_sync flush a partial group.
+void Engine::run_step(int n, long long ticket) {
   if (profiling) {
     // sequential form on `stream`; the codec stream (PCM copy, ev_pcm) must still order behind it
+    flush_codec();
     step_kernels(n, nullptr);
     PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
     PTTS_CUDA(cudaEventRecord(ev_front_done, stream));
@@ -1320,42 +1440,104 @@ void Engine::run_step(int n) {
     PTTS_CUDA(cudaEventRecord(ev_b_done, stream_b));
     return;
   }
+  if (cg > 1) {
+    if (pend > 0 && (pend_n != n || !std::equal(row_seq_host.begin(), row_seq_host.begin() + n, pend_rows.begin()))) flush_codec();
+    if (pend == 0) {
+      // the queue buffer is free once the front end of the group that used it last has run
+      PTTS_CUDA(cudaStreamWaitEvent(stream, ev_gfront[gbuf], 0));
+      pend_n = n;
+      pend_rows.assign(row_seq_host.begin(), row_seq_host.begin() + n);
+    }
+    const int entry = gbuf * cg + pend;
+    if (diag_times && pend == 0) PTTS_CUDA(cudaEventRecord(ev_t[0], stream));
+    if (diag_skip != 2) {
+      if (cfg.use_cuda_graph) {
+        PartGraph& pg = graph_of(0, n, entry);
+        PTTS_CUDA(cudaGraphLaunch(pg.exec, stream));
+        launches += pg.kernels;
+      } else {
+        ls = stream;
+        cur_zq = zq.p + (size_t)entry * NB * LDIM; cur_zqpos = zq_pos.p + (size_t)entry * NB;
+        step_part_a(n, false);
+      }
+    }
+    if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[1], stream));
+    PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
+    pend_ticket[pend] = ticket;
+    ++pend;
+    if (pend == cg) flush_codec();
+    ls = stream;
+    PTTS_CUDA(cudaGetLastError());
+    return;
+  }
   // A(n) may not overwrite z32 / advance the frame counters before front(n-1) has consumed them
   PTTS_CUDA(cudaStreamWaitEvent(stream, ev_front_done, 0));
   if (cfg.use_cuda_graph) {
-    const auto key = std::make_pair(n, lsd_steps);
-    auto it = graphs.find(key);
-    if (it == graphs.end()) {
-      StepGraph sg{};
-      sg.a = capture(stream, n, 0, &sg.kernels_a);
-      sg.b = capture(stream_b, n, 1, &sg.kernels_b);
-      it = graphs.emplace(key, sg).first;
-    }
+    PartGraph& ga = graph_of(0, n, -1);
+    PartGraph& gb = graph_of(1, n, 1);
     if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[0], stream));
-    if (diag_skip != 2) PTTS_CUDA(cudaGraphLaunch(it->second.a, stream));
+    if (diag_skip != 2) PTTS_CUDA(cudaGraphLaunch(ga.exec, stream));
     if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[1], stream));
     PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
     PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_a_done, 0));
     ls = stream_b;
     if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[2], stream_b));
-    if (diag_skip != 1) step_front(n);
+    if (diag_skip != 1) step_front(n, 0, 0);
     PTTS_CUDA(cudaEventRecord(ev_front_done, stream_b));
-    if (diag_skip != 1) PTTS_CUDA(cudaGraphLaunch(it->second.b, stream_b));
+    if (diag_skip != 1) PTTS_CUDA(cudaGraphLaunch(gb.exec, stream_b));
     if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[3], stream_b));
-    launches += it->second.kernels_a + it->second.kernels_b;
+    launches += ga.kernels + gb.kernels;
   } else {
     ls = stream;
+    cur_zq = nullptr; cur_zqpos = nullptr;
     step_part_a(n, false);
     PTTS_CUDA(cudaEventRecord(ev_a_done, stream));
     PTTS_CUDA(cudaStreamWaitEvent(stream_b, ev_a_done, 0));
     ls = stream_b;
-    step_front(n);
+    step_front(n, 0, 0);
     PTTS_CUDA(cudaEventRecord(ev_front_done, stream_b));
-    step_part_b(n, false);
+    step_part_b(n, 1, false);
   }
   PTTS_CUDA(cudaEventRecord(ev_b_done, stream_b));
   ls = stream;
   PTTS_CUDA(cudaGetLastError());
+}
+
+// Frames per codec pass (1, 2 or 4).  The codec scratch is sized for it, so a change re-allocates (device idle) and drops
+// the captured graphs, which bake buffer addresses.
+void Engine::set_codec_group(int frames) {
+  PTTS_REQUIRE(frames == 1 || frames == 2 || frames == 4, PTTS_ERR_INVALID, "codec group of %d frames (supported: 1, 2, 4)", frames);
+  flush_codec();
+  sync_all();
+  if (frames == cg && mx32.p) return;
+  drop_graphs();
+  cg = frames;
+  const size_t f = (size_t)cg, MR = (size_t)NB * MIMI_T * f;
+  mx32.alloc(MR * MIMI_DIM); mqkv32.alloc(MR * 3 * MIMI_DIM); mh16.alloc(MR * MIMI_DIM); mattn16.alloc(MR * MIMI_DIM);
+  mffn16.alloc(MR * MIMI_FFN);
+  tr16.alloc((size_t)NB * (6 + 16 * f) * 512); a0.alloc((size_t)NB * (1 + 16 * f) * 512);
+  x2.alloc((size_t)NB * 96 * f * 256); e2.alloc((size_t)NB * (2 + 96 * f) * 256); h3.alloc((size_t)NB * 96 * f * 128);
+  a3.alloc((size_t)NB * (1 + 96 * f) * 256); x5.alloc((size_t)NB * 480 * f * 128); e5.alloc((size_t)NB * (2 + 480 * f) * 128);
+  h6.alloc((size_t)NB * 480 * f * 64); a6.alloc((size_t)NB * (1 + 480 * f) * 128); x8.alloc((size_t)NB * FRAME * f * 64);
+  e8.alloc((size_t)NB * (2 + FRAME * f) * 64); h9.alloc((size_t)NB * FRAME * f * 64); a9.alloc((size_t)NB * (2 + FRAME * f) * 64);
+  pcm.alloc((size_t)NB * FRAME * f);
+  pcm16.alloc((size_t)NB * FRAME * f);
+  zq.alloc((size_t)2 * f * NB * LDIM);
+  zq_pos.alloc((size_t)2 * f * NB);
+  for (int g = 1; g <= cg; ++g) {
+    ConvSegs& sg = segs_by_f[g];
+    sg.s[0] = ConvSeg{tr16.p, st_tr.p, 6, 16 * g, 512, 0};
+    sg.s[1] = ConvSeg{a0.p, st_a0.p, 1, 16 * g, 512, 0};
+    sg.s[2] = ConvSeg{e2.p, st_e2.p, 2, 96 * g, 256, 0};
+    sg.s[3] = ConvSeg{a3.p, st_a3.p, 1, 96 * g, 256, 0};
+    sg.s[4] = ConvSeg{e5.p, st_e5.p, 2, 480 * g, 128, 0};
+    sg.s[5] = ConvSeg{a6.p, st_a6.p, 1, 480 * g, 128, 0};
+    sg.s[6] = ConvSeg{e8.p, st_e8.p, 2, FRAME * g, 64, 0};
+    sg.s[7] = ConvSeg{a9.p, st_a9.p, 2, FRAME * g, 64, 0};
+  }
+  segs = segs_by_f[1];
+  pend = 0; gbuf = 0;
+  PTTS_CUDA(cudaDeviceSynchronize());
 }
 
 // PCM -> audio_prompt rows (reference tts_model.rs:504-556 up to the conditioning; models/mimi.rs:113-141):
@@ -1523,6 +1705,18 @@ int32_t ptts_engine_set_lsd_steps(ptts_engine* h, int32_t lsd_steps) {
   PTTS_CATCH
 }
 
+int32_t ptts_engine_set_codec_group(ptts_engine* h, int32_t frames) {
+  PTTS_TRY
+  PTTS_REQUIRE(h, PTTS_ERR_INVALID, "null engine");
+  Engine& e = h->e;
+  PTTS_CUDA(cudaSetDevice(e.cfg.device));
+  for (const Engine::Ticket& t : e.tickets)
+    PTTS_REQUIRE(t.flags_done && t.pcm_done, PTTS_ERR_STATE, "set_codec_group: step %lld still has unfetched results", t.id);
+  e.set_codec_group(frames);
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
 int32_t ptts_voice_from_prompt(ptts_engine* h, const float* audio_prompt, int32_t n_rows, ptts_voice** out) {
   PTTS_TRY
   PTTS_REQUIRE(h && audio_prompt && out, PTTS_ERR_INVALID, "ptts_voice_from_prompt: null argument");
@@ -1609,6 +1803,7 @@ static void streams_open_impl(Engine& e, int n, ptts_voice* const* voices, const
   }
   // the records staged two opens ago must have left this pinned buffer (long done in practice), and the codec stream must
   // be done with the slots being recycled (ordered on the device)
+  e.flush_codec();
   const int ob = e.open_parity;
   e.open_parity ^= 1;
   PTTS_CUDA(cudaEventSynchronize(e.ev_open[ob]));
@@ -1702,21 +1897,24 @@ static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, int 
   const bool want_pcm = (flags & PTTS_STEP_PCM) != 0 || want_i16, ahead = (flags & PTTS_STEP_AHEAD) != 0;
   const long long id = e.next_ticket;
   Engine::Ticket& t = e.tickets[id % Engine::NT];
-  PTTS_REQUIRE(t.flags_done && t.pcm_done, PTTS_ERR_STATE, "step %lld still has unfetched results (three steps may be in flight)", t.id);
+  PTTS_REQUIRE(t.flags_done && t.pcm_done, PTTS_ERR_STATE, "step %lld still has unfetched results (%d steps may be in flight)", t.id, Engine::NT);
   const Engine::Ticket& prev = e.tickets[(id + Engine::NT - 1) % Engine::NT];
   const Engine::Ticket& prev2 = e.tickets[(id + Engine::NT - 2) % Engine::NT];
   PTTS_REQUIRE(prev.flags_done || ahead, PTTS_ERR_STATE, "fetch the flags of step %lld before beginning the next step (or pass PTTS_STEP_AHEAD)", prev.id);
   PTTS_REQUIRE(prev2.flags_done, PTTS_ERR_STATE, "only one step may be enqueued ahead of unfetched flags (step %lld)", prev2.id);
   check_slots(e, slot_ids, n, prev.flags_done ? 0 : 1);
   e.upload_rows(slot_ids, n);
-  e.run_step(n);
   const int par = (int)(id % Engine::NT);
+  t.id = id; t.n = n; t.want_pcm = want_pcm; t.want_i16 = want_i16; t.codec_pending = e.cg > 1;
+  e.run_step(n, id);   // cg > 1: the PCM copy and ev_pcm are issued when the frame's codec group is flushed
   PTTS_CUDA(cudaMemcpyAsync(e.pin_lat[par], e.step_out.p, e.step_out_bytes(), cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaEventRecord(e.ev_flags[par], e.stream));
-  if (want_i16) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm16[par], e.pcm16.p, (size_t)n * FRAME * 2, cudaMemcpyDeviceToHost, e.stream_b));
-  else if (want_pcm) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm[par], e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream_b));
-  PTTS_CUDA(cudaEventRecord(e.ev_pcm[par], e.stream_b));
-  t.id = id; t.n = n; t.flags_done = false; t.pcm_done = false; t.want_pcm = want_pcm; t.want_i16 = want_i16;
+  if (e.cg == 1) {
+    if (want_i16) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm16[par], e.pcm16.p, (size_t)n * FRAME * 2, cudaMemcpyDeviceToHost, e.stream_b));
+    else if (want_pcm) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm[par], e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream_b));
+    PTTS_CUDA(cudaEventRecord(e.ev_pcm[par], e.stream_b));
+  }
+  t.flags_done = false; t.pcm_done = false;
   t.slot_ids.assign(slot_ids, slot_ids + n);
   e.next_ticket = id + 1;
   return id;
@@ -1748,6 +1946,7 @@ static void step_pcm_impl(Engine& e, long long id, float* pcm_out, int16_t* pcm1
   Engine::Ticket& t = e.tickets[id % Engine::NT];
   PTTS_REQUIRE(id >= 0 && t.id == id && !t.pcm_done, PTTS_ERR_STATE, "ticket %lld has no pending PCM", id);
   const int par = (int)(id % Engine::NT);
+  if (t.codec_pending) e.flush_codec();   // the frame's group is not full yet: decode what is queued
   PTTS_CUDA(cudaEventSynchronize(e.ev_pcm[par]));
   if (pcm_out) {
     PTTS_REQUIRE(t.want_pcm && !t.want_i16, PTTS_ERR_STATE, "step %lld was not begun with PTTS_STEP_PCM", id);
@@ -1908,6 +2107,7 @@ int32_t ptts_stream_set_feedback(ptts_engine* h, int32_t slot, const float* late
 static void stream_close_impl(Engine& e, int slot) {
   PTTS_REQUIRE(slot >= 0 && slot < e.NS && e.slots[slot].in_use, PTTS_ERR_STATE, "slot %d is not open", slot);
   PTTS_REQUIRE(!e.slot_in_pending_ticket(slot), PTTS_ERR_STATE, "slot %d is part of a step whose flags have not been fetched (ptts_step_flags first)", slot);
+  e.flush_codec();   // its queued frames are decoded before the slot can be recycled
   e.slots[slot] = SlotHost{};
   e.row_seq_host.clear();
 }

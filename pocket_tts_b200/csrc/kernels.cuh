@@ -426,40 +426,55 @@ __global__ void enc_downsample_boundary_prep_kernel(const float* __restrict__ x 
 
 // ---------------------------------------------------------------- Mimi front end
 // latent de-norm (tts_model.rs:1033-1035) -> Quantizer 1x1 conv 32->512 (mimi.rs:32-36) -> depthwise
-// ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid (n, 4), block 128: one channel per
+// ConvTranspose1d k32 s16 with carried partial (conv.rs:314-346 -> :219-267).  grid (n, 4, f), block 128: one channel per
 // thread, weights pre-transposed to [k][512] so every access of a warp is contiguous; the 16 partial-sum reads are
 // issued before any store to the same buffer.
-__global__ void mimi_frontend_kernel(const float* __restrict__ z, const int* __restrict__ row_seq,
-                                     const StreamCtl* __restrict__ ctl, const float* __restrict__ emb_std,
-                                     const float* __restrict__ emb_mean, const float* __restrict__ wq_t /*[32,512]*/,
-                                     const float* __restrict__ wup_t /*[32,512]*/, float* __restrict__ partial /*[slots,16,512]*/,
-                                     float* __restrict__ x /*[n*16,512]*/, float* __restrict__ dbg_quant,
-                                     int* __restrict__ mimi_pos) {
+// f > 1 (codec group): the latents of f consecutive frames of every row wait in a queue (z + j * z_frame_stride, frame
+// index of frame 0 in zpos) and are decoded by one launch.  The partial a frame inherits is a function of the previous
+// frame's latent alone, so block (b, ., j > 0) recomputes it from queue entry j - 1 instead of waiting for block j - 1;
+// only the last frame writes the slot's carried partial.  Same arithmetic as f launches of one frame (bit-identical).
+__global__ void mimi_frontend_kernel(const float* __restrict__ z, long long z_frame_stride, const int* __restrict__ zpos,
+                                     const int* __restrict__ row_seq, const StreamCtl* __restrict__ ctl,
+                                     const float* __restrict__ emb_std, const float* __restrict__ emb_mean,
+                                     const float* __restrict__ wq_t /*[32,512]*/, const float* __restrict__ wup_t /*[32,512]*/,
+                                     float* __restrict__ partial /*[slots,16,512]*/, float* __restrict__ x /*[n*f*16,512]*/,
+                                     float* __restrict__ dbg_quant, int* __restrict__ mimi_pos) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float zd[LDIM];
-  const int b = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x;
+  __shared__ float zd[2][LDIM];
+  const int b = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x, j = blockIdx.z, f = gridDim.z;
   const int slot = row_seq[b];
-  if (threadIdx.x < LDIM) zd[threadIdx.x] = z[b * LDIM + threadIdx.x] * emb_std[threadIdx.x] + emb_mean[threadIdx.x];
-  // runs after step_end of the same frame: the frame counter has already advanced by one
-  if (c == 0) mimi_pos[b] = (ctl[slot].frame - 1) * 16;
+  // zd[1]: the frame whose second half this block also needs -- the previous frame (j > 0: it supplies the partial this
+  // frame inherits) or, in block j = 0, the group's last frame (it supplies the partial the slot carries to the next pass;
+  // the block that reads the carried partial is the one that replaces it, so no other block ever touches it)
+  const int j2 = j > 0 ? j - 1 : f - 1;
+  if (threadIdx.x < LDIM) {
+    zd[0][threadIdx.x] = z[j * z_frame_stride + b * LDIM + threadIdx.x] * emb_std[threadIdx.x] + emb_mean[threadIdx.x];
+    zd[1][threadIdx.x] = z[j2 * z_frame_stride + b * LDIM + threadIdx.x] * emb_std[threadIdx.x] + emb_mean[threadIdx.x];
+  }
+  // position of the group's first frame.  Without a queue this launch runs after step_end of the same frame: the frame
+  // counter has already advanced by one
+  if (c == 0 && j == 0) mimi_pos[b] = zpos ? zpos[b] * 16 : (ctl[slot].frame - 1) * 16;
   __syncthreads();
-  float qv = 0.f;
+  float qv = 0.f, q2 = 0.f;
 #pragma unroll
-  for (int k = 0; k < LDIM; ++k) qv += __ldg(wq_t + k * 512 + c) * zd[k];
-  if (dbg_quant) dbg_quant[b * 512 + c] = qv;
+  for (int k = 0; k < LDIM; ++k) qv += __ldg(wq_t + k * 512 + c) * zd[0][k];
+#pragma unroll
+  for (int k = 0; k < LDIM; ++k) q2 += __ldg(wq_t + k * 512 + c) * zd[1][k];
+  if (dbg_quant && j == 0) dbg_quant[b * 512 + c] = q2;   // the last frame of the group
   float* part = partial + static_cast<long long>(slot) * 16 * 512;
   float old[16], w0[16], w1[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    old[j] = part[j * 512 + c];
-    w0[j] = __ldg(wup_t + j * 512 + c);
-    w1[j] = __ldg(wup_t + (16 + j) * 512 + c);
+  for (int i = 0; i < 16; ++i) {
+    w0[i] = __ldg(wup_t + i * 512 + c);
+    w1[i] = __ldg(wup_t + (16 + i) * 512 + c);
+    old[i] = (j == 0) ? part[i * 512 + c] : __fmul_rn(q2, w1[i]);
   }
+  float* xo = x + (static_cast<long long>(b) * f + j) * 16 * 512 + c;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    x[(static_cast<long long>(b) * 16 + j) * 512 + c] = qv * w0[j] + old[j];
-    part[j * 512 + c] = qv * w1[j];
+  for (int i = 0; i < 16; ++i) {
+    xo[i * 512] = __fmaf_rn(qv, w0[i], old[i]);
+    if (j == 0) part[i * 512 + c] = __fmul_rn(q2, w1[i]);
   }
 }
 
@@ -494,11 +509,17 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 __global__ void __launch_bounds__(MATTN_THREADS, 3)
-mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __restrict__ row_seq,
+mimi_attn_kernel(const float* __restrict__ qkv_all /*[n*f*16, 1536]*/, const int* __restrict__ row_seq,
                  const int* __restrict__ mimi_pos, __half* ring /*[slots][layer][k|v][8][272*64]*/, int layer, int n_layers,
-                 __half* __restrict__ out16 /*[n*16, 512]*/) {
+                 __half* __restrict__ out16_all /*[n*f*16, 512]*/, int f) {
   pdl_launch_dependents();
   pdl_wait();
+  // f > 1 (codec group): the f consecutive frames of the row, one after the other -- frame j + 1 sees the ring rows frame j
+  // wrote, exactly as f launches would
+  for (int fj = 0; fj < f; ++fj) {
+  if (fj) __syncthreads();  // the merge of the previous frame has read o_s / m_s / l_s
+  const float* qkv = qkv_all + (static_cast<long long>(blockIdx.x) * (f - 1) + fj) * 16 * 1536;
+  __half* out16 = out16_all + (static_cast<long long>(blockIdx.x) * (f - 1) + fj) * 16 * 512;
   constexpr int NH = 8, DM = 512, T = 16, NW = MATTN_WARPS;
   constexpr float kScale = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) and log2(e): softmax in base 2
   extern __shared__ __align__(16) unsigned char msm_raw[];
@@ -510,7 +531,7 @@ mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __re
   const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, c = lane & 3;
   const int slot = row_seq[b];
-  const int p0 = mimi_pos[b];  // absolute position of the first new row (multiple of 16)
+  const int p0 = mimi_pos[b] + 16 * fj;  // absolute position of the first new row (multiple of 16)
   __half* kring = ring + ((static_cast<long long>(slot) * n_layers + layer) * 2 * NH + h) * MIMI_RING * HD;
   __half* vring = kring + static_cast<long long>(NH) * MIMI_RING * HD;  // [64][272]
   const int blk0 = (p0 >> 4) % MATTN_BLOCKS;                              // ring block of the new rows
@@ -660,6 +681,7 @@ mimi_attn_kernel(const float* __restrict__ qkv /*[n*16, 1536]*/, const int* __re
     const float inv = 1.f / den;
     reinterpret_cast<__half2*>(out16 + (static_cast<long long>(b) * T + t) * DM + h * HD)[i] = __floats2half2_rn(sx * inv, sy * inv);
   }
+  }  // frames of the group
 }
 
 // ---------------------------------------------------------------- flow head glue
@@ -726,7 +748,8 @@ __global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCt
                                 int* __restrict__ own_len, const float* __restrict__ eos_logit,
                                 const float* __restrict__ z32, float* __restrict__ feedback,
                                 unsigned char* __restrict__ finished_out, float* __restrict__ latent_out,
-                                float* __restrict__ logit_out) {
+                                float* __restrict__ logit_out, float* __restrict__ zq /*[n,32] or null*/,
+                                int* __restrict__ zq_pos /*[n]*/) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x, k = threadIdx.x;  // 32 threads
@@ -735,9 +758,11 @@ __global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCt
   const float zk = z32[b * LDIM + k];
   feedback[slot * LDIM + k] = zk;
   latent_out[b * LDIM + k] = zk;
+  if (zq) zq[b * LDIM + k] = zk;  // codec group: this frame's latent waits here for the Mimi front end
   if (k == 0) {
     StreamCtl c = ctl[slot];
     const int step = c.frame;
+    if (zq_pos) zq_pos[b] = step;
     const float logit = eos_logit[b];
     if (c.finished) {  // overrun frame of a step enqueued ahead: the stream's counters stay at its last real frame
       finished_out[b] = 1;
@@ -762,9 +787,9 @@ __global__ void step_end_kernel(const int* __restrict__ row_seq, int n, StreamCt
 // One thread per output sample; the 3x64 window of sample t is 384 contiguous bytes.
 // Also packs the frame as the reference's wire format (audio.rs:129-146 pcm_i16_le_bytes: clamp to [-1, 1], * 32767,
 // truncating cast), so a host that streams i16 PCM reads back half the bytes and converts nothing.
-__global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+1920][64]*/, const float* __restrict__ w /*[3][64]*/,
-                                         const float* __restrict__ bias, int n, float* __restrict__ pcm /*[n,1920]*/,
-                                         short* __restrict__ pcm16 /*[n,1920] or null*/) {
+__global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+T][64]*/, const float* __restrict__ w /*[3][64]*/,
+                                         const float* __restrict__ bias, int n, int T /*1920 x frames of the group*/,
+                                         float* __restrict__ pcm /*[n,T]*/, short* __restrict__ pcm16 /*[n,T] or null*/) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float w_s[192];
@@ -772,8 +797,8 @@ __global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+19
   __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (t >= FRAME) return;
-  const uint4* src = reinterpret_cast<const uint4*>(a + (static_cast<long long>(b) * (FRAME + 2) + t) * 64);
+  if (t >= T) return;
+  const uint4* src = reinterpret_cast<const uint4*>(a + (static_cast<long long>(b) * (T + 2) + t) * 64);
   float acc = bias[0];
 #pragma unroll
   for (int c = 0; c < 24; ++c) {
@@ -785,8 +810,8 @@ __global__ void seanet_final_conv_kernel(const __half* __restrict__ a /*[n][2+19
       acc += f.x * w_s[c * 8 + 2 * j] + f.y * w_s[c * 8 + 2 * j + 1];
     }
   }
-  pcm[static_cast<long long>(b) * FRAME + t] = acc;
-  if (pcm16) pcm16[static_cast<long long>(b) * FRAME + t] = static_cast<short>(fminf(fmaxf(acc, -1.f), 1.f) * 32767.f);
+  pcm[static_cast<long long>(b) * T + t] = acc;
+  if (pcm16) pcm16[static_cast<long long>(b) * T + t] = static_cast<short>(fminf(fmaxf(acc, -1.f), 1.f) * 32767.f);
 }
 
 // Left-context rows of every streaming conv (reference `previous`, conv.rs:125-128; and the previous input row

@@ -50,7 +50,7 @@ class Voice:
 class Engine:
     def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
                  kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True, int8_weights: bool = False,
-                 int8_storage: bool = True, lm_step_kernel: bool | None = None):
+                 int8_storage: bool = True, lm_step_kernel: bool | None = None, codec_group: int | None = None):
         L = _lib.lib()
         self._keep = []
         descs = (TensorDesc * len(weights))()
@@ -76,6 +76,8 @@ class Engine:
         self._h = h
         self._keep = []
         self.max_batch = cfg.max_batch
+        if codec_group is not None:
+            self.set_codec_group(codec_group)
 
     def close(self):
         if self._h:
@@ -90,6 +92,10 @@ class Engine:
 
     def set_lsd_steps(self, n: int):
         check(_lib.lib().ptts_engine_set_lsd_steps(self._h, n))
+
+    def set_codec_group(self, frames: int):
+        """Frames per codec pass (ptts_engine_set_codec_group): 1, 2 or 4; same PCM, the codec's launches paid once per group."""
+        check(_lib.lib().ptts_engine_set_codec_group(self._h, frames))
 
     def voice_from_prompt(self, audio_prompt: np.ndarray) -> Voice:
         a = np.ascontiguousarray(audio_prompt, dtype=np.float32).reshape(-1, 1024)

@@ -1,5 +1,6 @@
 """One mid-utterance decode step of the bench workload inside a cudaProfilerStart/Stop range, for
-`ncu --profile-from-start off` (launch list and full-set captures; see profiles/)."""
+`ncu --profile-from-start off` (launch list and full-set captures; see profiles/).
+python tests/profile_step.py [streams] [warm steps] [profiled steps] [step_kernel: 0|1]"""
 import sys
 from pathlib import Path
 
@@ -13,7 +14,8 @@ from pocket_tts_b200.engine import Engine, StreamSpec
 streams = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-eng = Engine(synth.make_weights(1234), max_slots=streams, kv_capacity=40 + 125 + 3)
+step_kernel = bool(int(sys.argv[4])) if len(sys.argv) > 4 else None
+eng = Engine(synth.make_weights(1234), max_slots=streams, kv_capacity=40 + 125 + 3, lm_step_kernel=step_kernel)
 voice = eng.voice_from_prompt(synth.make_voice_prompt(87, seed=7))
 specs = [StreamSpec(synth.make_tokens(40, seed=1000 + i), 125, 3, 1e30, temp=0.7, seed=i) for i in range(streams)]
 slots = eng.open_streams([voice] * streams, specs)
