@@ -147,7 +147,9 @@ struct Engine {
   Weight16 w_cond, w_finproj, w_ada, w_mlp0[FLOW_DEPTH], w_mlp2[FLOW_DEPTH], w_final;
   DevBuf<__half> w_flowpack;   // mlp.0 / mlp.2 of the six blocks and the final Linear, one [6272][512] operand (flow_head.cuh)
   bool fused_flow = true;      // ptts_engine_cfg.reserved[5] = 1 or debug_gemm: the per-layer launches instead
-  void flow_head_fused(int n, const float* mod);
+  static constexpr int MOD_STEPS = 4;   // Euler steps whose modulation rows fit the scratch: one Linear + one flow-head launch for all of them
+  bool mod_all_steps() const { return lsd_steps <= MOD_STEPS; }
+  void flow_head_fused(int n, const float* mod, long long mod_step_stride, int steps);
   // ---- persistent FlowLM step kernel (lm_step.cuh): tiled weight images, operand images, split-K workspace, grid barrier
   bool lm_enabled = false;     // built at init when selected (see lm_build) and the weights are f16
   int lm_ctas = 0;             // grid of the step kernel (PTTS_LM_CTAS; default: every SM)
@@ -203,7 +205,7 @@ struct Engine {
   DevBuf<__half> tr16, a0, e2, h3, a3, e5, h6, a6, e8, h9, a9;
   DevBuf<float> x2, x5, x8, pcm;
   DevBuf<short> pcm16;          // the same frame as i16 (audio.rs:129-146), written by the last SEANet conv
-  short* pin_pcm16[3] = {};
+  short* pin_pcm16[6] = {};   // [NT]
   // stream open: pinned records -> one copy -> scatter kernel; injected noise in per-slot buffers that only grow (a
   // cudaFree per close would be a device-wide synchronisation)
   DevBuf<OpenRec> open_recs;
@@ -241,6 +243,7 @@ struct Engine {
   // a ring of tickets: with PTTS_STEP_AHEAD step n+1 is enqueued while the flags of step n and the PCM of step n-1 are
   // still on their way to the host; with a codec group the PCM of a frame leaves with its group, up to cg - 1 steps later
   static constexpr int NT = 6;
+  static_assert(NT == sizeof(pin_pcm16) / sizeof(pin_pcm16[0]), "pin_pcm16 holds one buffer per ticket");
   float* pin_pcm[NT] = {}; unsigned char* pin_fin[NT] = {};
   float* pin_lat[NT] = {}; float* pin_logit[NT] = {};
   cudaEvent_t ev_flags[NT] = {}, ev_pcm[NT] = {};
@@ -758,8 +761,8 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   // the fused flow head works on whole 64-row chunks: its row-indexed buffers are padded so that rows past the
   // batch are readable and writable (never consumed), which keeps every access at a compile-time offset
   const size_t NBP = (size_t)round_up(NB, FH_ROWS);
-  lat16.alloc((size_t)NB * 64); c32.alloc((size_t)NB * FLOW_DIM); mod32.alloc(NBP * MOD_LD);
-  fx32.alloc(NBP * FLOW_DIM); y16.alloc((size_t)NB * FLOW_DIM); fh16.alloc(NBP * FLOW_DIM);
+  lat16.alloc((size_t)NB * 64); c32.alloc((size_t)NB * FLOW_DIM); mod32.alloc((size_t)MOD_STEPS * NBP * MOD_LD);
+  fx32.alloc(NBP * FLOW_DIM); y16.alloc((size_t)MOD_STEPS * NB * FLOW_DIM); fh16.alloc(NBP * FLOW_DIM);
   fg16.alloc(NBP * FLOW_DIM); z32.alloc(NBP * LDIM); z16.alloc(NBP * 64);
   mimi_pos.alloc(NB);
   open_recs.alloc(NS);
@@ -838,7 +841,9 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     PTTS_REQUIRE(R_g > 0 && G_g > 0 && R_g * G_g <= 128, PTTS_ERR_INVALID, "gemm: bad tile geometry R %d G %d", R_g, G_g);
     g.act_tiles = ((T_g + R_g - 1) / R_g) * ((n_streams + G_g - 1) / G_g);
     const int fcap = round_up(F, 16);
-    if (g.act_tiles >= 148 && cfg.reserved[3] != 1) {
+    static const bool b_all_persistent = std::getenv("PTTS_B_ALL_PERSISTENT") && std::atoi(std::getenv("PTTS_B_ALL_PERSISTENT"));  // bring-up
+    if ((g.act_tiles >= 148 || (b_all_persistent && ls == stream_b && (long long)g.act_tiles * ((F + 127) / 128) > persistent_ctas)) &&
+        cfg.reserved[3] != 1) {
       // enough activation tiles to give every SM several: persistent kernel, accumulator double-buffered in TMEM
       g.bn = std::min(128, fcap);
       g.persistent = true;
@@ -1033,7 +1038,8 @@ static RowMap stream_map(int T, int ld, long long stream_stride, long long base)
 // Frame n+1's A depends only on frame n's A, so run_step() puts A on one stream and front+B on another: the codec
 // of frame n overlaps the language model of frame n+1.
 // input_proj + six AdaLN residual blocks + final layer of one LSD step as a single cluster kernel (flow_head.cuh)
-void Engine::flow_head_fused(int n, const float* mod) {
+// All `lsd_steps` Euler steps of the flow head in one launch; step s reads its modulation rows at mod + s * mod_step_stride.
+void Engine::flow_head_fused(int n, const float* mod, long long mod_step_stride, int steps) {
   FlowHeadParams fp{};
   fp.b_in = b_finproj.p; fp.b_final = b_final.p;
   fp.ws_in = w_finproj.wscale.p; fp.ws_final = w_final.wscale.p;
@@ -1042,30 +1048,21 @@ void Engine::flow_head_fused(int n, const float* mod) {
     fp.ln_w[i] = inln_w[i].p; fp.ln_b[i] = inln_b[i].p;
     fp.ws0[i] = w_mlp0[i].wscale.p; fp.ws2[i] = w_mlp2[i].wscale.p;
   }
-  fp.mod = mod; fp.z32 = z32.p; fp.z16 = z16.p; fp.h16 = fh16.p; fp.g16 = fg16.p; fp.x_dbg = fx32.p;
-  fp.n = n; fp.alpha = 1.f / (float)lsd_steps;
+  fp.mod = mod; fp.mod_step_stride = mod_step_stride; fp.z32 = z32.p; fp.z16 = z16.p; fp.x_dbg = fx32.p;
+  fp.n = n; fp.steps = steps; fp.alpha = 1.f / (float)lsd_steps;
   fp.trace = fh_trace.p;
   const CUtensorMap& m_win = tmaps.get(w_finproj.w.p, 64, w_finproj.Fpad, 1, 64, (long long)w_finproj.Fpad * 64, 128, 1);
   // weights: (64 k, rows, k-blocks); one box = four k-block tiles [k-block][128 features][64]
   const CUtensorMap& m_wp = tmaps.get(w_flowpack.p, 64, FH_PACK_ROWS, 8, FLOW_DIM, 64, 128, 4);
-  const long long NBP = round_up(NB, FH_ROWS);
-  // operand maps: (64 k, rows, k-blocks) with the k-block as the slowest box dimension, so one box is the whole
-  // [k-block][row][64] operand of a layer
-  const CUtensorMap& m_z = tmaps.get(z16.p, 64, NBP, 1, 64, 64, FH_ROWS, 1);
-  const CUtensorMap& m_h = tmaps.get(fh16.p, 64, NBP, 8, FLOW_DIM, 64, FH_ROWS, 8);
-  const CUtensorMap& m_g = tmaps.get(fg16.p, 64, NBP, 8, FLOW_DIM, 64, FH_ROWS, 8);
   const int chunks = (n + FH_ROWS - 1) / FH_ROWS;
-  // weights once per cluster, modulation rows three times a block, the operand all-gather twice a block
-  const double bytes = (double)chunks * ((double)FH_PACK_ROWS * FLOW_DIM * 2 + 512.0 * 64 * 2) + (double)n * (MOD_LD * 4.0 + 26.0 * FLOW_DIM * 2 + 64 * 2 + 32 * 8);
-  const double flops = 2.0 * n * (12.0 * FLOW_DIM * FLOW_DIM + 64.0 * FLOW_DIM + 32.0 * FLOW_DIM);
+  // weights once per cluster and step, modulation rows once per step, z in and out
+  const double bytes = (double)steps * ((double)chunks * ((double)FH_PACK_ROWS * FLOW_DIM * 2 + 512.0 * 64 * 2) + (double)n * MOD_LD * 4.0) + (double)n * (64 * 2 + 32 * 8);
+  const double flops = 2.0 * steps * n * (12.0 * FLOW_DIM * FLOW_DIM + 64.0 * FLOW_DIM + 32.0 * FLOW_DIM);
   ProfScope ps(*this, "flow.head_fused", bytes, flops, "flow_head_kernel");
-  launch_k(use_pdl, flow_head_kernel, dim3(chunks, 1, FH_CLUSTER), FH_THREADS, FH_SMEM, ls, FH_CLUSTER, m_win, m_wp, m_z, m_h, m_g, fp);
+  launch_k(use_pdl, flow_head_kernel, dim3(chunks, 1, FH_CLUSTER), FH_THREADS, FH_SMEM, ls, FH_CLUSTER, m_win, m_wp, fp);
   PTTS_CUDA(cudaGetLastError());
 }
 
-// The language-model half through the persistent step kernel: ONE launch for the feedback gather, input_linear, six
-// transformer layers, out_norm + EOS, cond_embed and the adaLN modulations of every LSD step; then the fused flow head
-// per LSD step and the EOS bookkeeping.
 void Engine::lm_step(int n) {
   LmStepParams& q = lm_params;
   q.n = n;
@@ -1165,7 +1162,7 @@ void Engine::step_part_a(int n, bool marks) {
   if (lm_usable(n)) {
     lm_step(n);
     if (marks) PTTS_CUDA(cudaEventRecord(ev[1], ls));
-    for (int s = 0; s < lsd_steps; ++s) flow_head_fused(n, lm_mod.p + (size_t)s * LM_ROWS * MOD_LD);
+    flow_head_fused(n, lm_mod.p, (long long)LM_ROWS * MOD_LD, lsd_steps);
     { ProfScope ps(*this, "step.end", (double)n * 32 * 12, 0);
       launch_k(use_pdl, step_end_kernel, n, 32, 0, ls, 1, row_seq.p, n, ctl.p, own_len.p, eos_logit.p, z32.p, feedback.p, finished_dev.p,
                                             latent_out.p, logit_out.p, cur_zq, cur_zqpos); }
@@ -1188,14 +1185,25 @@ void Engine::step_part_a(int n, bool marks) {
   e = epi_none();
   e.bias = b_cond.p; e.out32 = c32.p; e.out32_map = plain_map(FLOW_DIM);
   tag("flow.cond_embed"); gemm_rows(h16.p, n, D_MODEL, w_cond, FLOW_DIM, e);
+  if (fused_flow && mod_all_steps()) {
+    // the modulations of ALL Euler steps by one Linear over lsd_steps x n rows (modules/mlp.rs:322-368), then one launch
+    const int rows = lsd_steps * n;
+    { ProfScope ps(*this, "flow.silu_add", (double)rows * FLOW_DIM * 6, 0);
+      launch_k(use_pdl, silu_add_kernel, (rows * FLOW_DIM + 255) / 256, 256, 0, ls, 1, c32.p, time_emb.p, n, lsd_steps, FLOW_DIM, y16.p); }
+    e = epi_none();
+    e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
+    tag("flow.adaln"); gemm_rows(y16.p, rows, FLOW_DIM, w_ada, MOD_LD, e);
+    flow_head_fused(n, mod32.p, (long long)n * MOD_LD, lsd_steps);
+  } else
   for (int s = 0; s < lsd_steps; ++s) {
     { ProfScope ps(*this, "flow.silu_add", (double)n * FLOW_DIM * 6, 0);
-      launch_k(use_pdl, silu_add_kernel, (n * FLOW_DIM + 255) / 256, 256, 0, ls, 1, c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, FLOW_DIM, y16.p); }
+      launch_k(use_pdl, silu_add_kernel, (n * FLOW_DIM + 255) / 256, 256, 0, ls, 1, c32.p, time_emb.p + (size_t)s * FLOW_DIM, n, 1, FLOW_DIM, y16.p); }
     e = epi_none();
     e.bias = b_ada.p; e.out32 = mod32.p; e.out32_map = plain_map(MOD_LD);
     tag("flow.adaln"); gemm_rows(y16.p, n, FLOW_DIM, w_ada, MOD_LD, e);
     if (fused_flow) {
-      flow_head_fused(n, mod32.p);
+      // more Euler steps than the modulation scratch holds: one launch per step, each a one-step integration of size alpha
+      flow_head_fused(n, mod32.p, 0, 1);
       continue;
     }
     e = epi_none();
@@ -1277,6 +1285,8 @@ void Engine::step_part_b(int n, int f, bool marks) {
     tag("mimi.linear2"); gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
   }
   if (marks) PTTS_CUDA(cudaEventRecord(ev[3], ls));
+  static const int diag_b_stop = std::getenv("PTTS_DIAG_B_STOP") ? std::atoi(std::getenv("PTTS_DIAG_B_STOP")) : 0;  // bring-up: cut the codec short
+  if (diag_b_stop == 1) return;
   // ---- SEANet decoder (reference seanet.rs:309-402) as implicit GEMMs; ELU fused into the producer's epilogue
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
     launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, sg, row_seq.p, 0); }
@@ -1301,6 +1311,7 @@ void Engine::step_part_b(int n, int f, bool marks) {
   e = epi_none(); e.bias = sb_r6b.p; e.res = x5.p; e.res_map = plain_map(128);
   e.out16 = a6.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T3, 128, (long long)(1 + T3) * 128, 128);
   tag("seanet.res6b"); gemm(ActView{h6.p, 64, T3, NB}, n, T3, 1, 120, 1, s_r6b, 128, e);
+  if (diag_b_stop == 2) return;
   e = epi_none(); e.bias = sb_ct8.p; e.out32 = x8.p; e.out32_map = stream_map(T3, 256, (long long)T4 * 64, 0);
   e.out16 = e8.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T3, 256, (long long)(2 + T4) * 64, 2 * 64);
   tag("seanet.convtr8"); gemm(ActView{a6.p, 128, 1 + T3, NB}, n, T3, 2, 120, 1, s_ct8, 256, e);
@@ -1484,7 +1495,14 @@ void Engine::run_step(int n, long long ticket) {
     if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[2], stream_b));
     if (diag_skip != 1) step_front(n, 0, 0);
     PTTS_CUDA(cudaEventRecord(ev_front_done, stream_b));
-    if (diag_skip != 1) PTTS_CUDA(cudaGraphLaunch(gb.exec, stream_b));
+    if (diag_skip == 4) {   // bring-up: a codec stand-in that only occupies CTAs (PTTS_DIAG_SPIN_CTAS x PTTS_DIAG_SPIN_US, PTTS_DIAG_SPIN_SMEM KB each)
+      static const int sc = std::getenv("PTTS_DIAG_SPIN_CTAS") ? std::atoi(std::getenv("PTTS_DIAG_SPIN_CTAS")) : 1;
+      static const int su = std::getenv("PTTS_DIAG_SPIN_US") ? std::atoi(std::getenv("PTTS_DIAG_SPIN_US")) : 300;
+      static const int sk = std::getenv("PTTS_DIAG_SPIN_SMEM") ? std::atoi(std::getenv("PTTS_DIAG_SPIN_SMEM")) : 0;
+      static bool once = false;
+      if (!once) { once = true; PTTS_CUDA(cudaFuncSetAttribute(spin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); }
+      launch_k(false, spin_kernel, sc, 32, (size_t)sk * 1024, stream_b, 1, (unsigned long long)su * 1000ULL);
+    } else if (diag_skip != 1 && diag_skip != 3) PTTS_CUDA(cudaGraphLaunch(gb.exec, stream_b));
     if (diag_times) PTTS_CUDA(cudaEventRecord(ev_t[3], stream_b));
     launches += ga.kernels + gb.kernels;
   } else {

@@ -686,14 +686,16 @@ mimi_attn_kernel(const float* __restrict__ qkv_all /*[n*f*16, 1536]*/, const int
 
 // ---------------------------------------------------------------- flow head glue
 // y16[r, :] = silu(c[r, :] + te[:])   (reference modules/mlp.rs:328-330)
-__global__ void silu_add_kernel(const float* __restrict__ c, const float* __restrict__ te, int rows, int C,
-                                __half* __restrict__ y16) {
+__global__ void silu_add_kernel(const float* __restrict__ c /*[n,C]*/, const float* __restrict__ te /*[steps,C]*/, int n, int steps, int C,
+                                __half* __restrict__ y16 /*[steps*n,C]: row s*n + r = silu(c[r] + te[s])*/) {
   pdl_launch_dependents();
   pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  if (i >= static_cast<long long>(rows) * C) return;
+  if (i >= static_cast<long long>(steps) * n * C) return;
   const int col = static_cast<int>(i % C);
-  y16[i] = __float2half_rn(silu(c[i] + te[col]));
+  const long long row = i / C;
+  const int s = static_cast<int>(row / n), r = static_cast<int>(row - static_cast<long long>(s) * n);
+  y16[i] = __float2half_rn(silu(c[static_cast<long long>(r) * C + col] + te[s * C + col]));
 }
 
 // ---------------------------------------------------------------- step begin / end
@@ -883,6 +885,13 @@ __global__ void slot_open_kernel(const OpenRec* __restrict__ recs, const ConvSeg
     if (threadIdx.x == 0) { seqs[slot] = r.sd; ctl[slot] = r.ctl; own_len[slot] = r.own_len; }
     if (threadIdx.x < LDIM) feedback[slot * LDIM + threadIdx.x] = bos[threadIdx.x];
   }
+}
+
+// Bring-up probe (PTTS_DIAG_SKIP=4): occupies CTAs for a fixed time without touching memory.
+__global__ void spin_kernel(unsigned long long ns) {
+  // SM-local clock (about 1.9 cycles per ns): polling %globaltimer from many warps is itself a shared-resource load
+  const long long t0 = clock64(), cycles = static_cast<long long>(ns) * 19 / 10;
+  while (clock64() - t0 < cycles) { }
 }
 
 // The device noise generator on its own (tests: distribution of counter_normal).
