@@ -667,3 +667,36 @@ def test_large_ragged_batches_match_oracle(n_streams):
         assert snr(refs[i]["pcm"], got_pcm) >= SNR_MIN
     voice.close()
     eng.close()
+
+
+@pytest.mark.parametrize("lsd", [2, 3, 6])
+def test_flow_head_euler_steps_vs_oracle(lsd):
+    """lsd_decode_steps other than the goldens' 1 and 4 (reference flow_lm.rs:7-22): 2 and 3 run as one flow-head launch with the
+    modulations of all steps from one Linear (modules/mlp.rs:322-368), 6 exceeds the modulation scratch and takes one launch
+    per step.  Teacher-forced, two streams (the second row sits in a different half of the 16-row chunk's registers)."""
+    from oracle import ptts_oracle as O
+    from pocket_tts_b200.engine import StreamSpec
+    eng, w = engine_for(1234, 1.0, max_slots=16)
+    W = O.to_torch(w)
+    prompt = synth.make_voice_prompt(9, seed=21)
+    voice = eng.voice_from_prompt(prompt)
+    ov = O.voice_state_from_prompt(W, prompt)
+    frames = 3
+    eng.set_lsd_steps(lsd)
+    try:
+        toks = [synth.make_tokens(6 + i, seed=60 + i) for i in range(9)]
+        noises = [synth.make_noise(frames, seed=80 + i) for i in range(9)]
+        refs = {i: O.generate_segment(W, ov, toks[i], noises[i], frames, 0, float("inf"), lsd_steps=lsd, decode_audio=False) for i in (0, 8)}
+        slots = eng.open_streams([voice] * 9, [StreamSpec(toks[i], frames, 0, 1e30, noise=noises[i]) for i in range(9)])
+        for f in range(frames):
+            if f:
+                for i in (0, 8):
+                    eng.set_feedback(int(slots[i]), refs[i]["latents"][f - 1])
+            _, _, lat, _ = eng.step(slots)
+            for i in (0, 8):
+                err = float(np.abs(lat[i] - refs[i]["latents"][f]).max())
+                assert err <= LAT_TOL, f"lsd {lsd} stream {i} frame {f}: latent max-abs {err:.3e}"
+        eng.close_streams(slots)
+    finally:
+        eng.set_lsd_steps(1)
+        voice.close()
