@@ -235,6 +235,10 @@ struct Engine {
   cudaEvent_t ev_gfront[2] = {};
   void flush_codec();
   void set_codec_group(int frames);
+  // SM partition between the two streams (green contexts); 0 SMs = none
+  int sms_a = 0, sms_b = 0;
+  void* green_ctx[2] = {nullptr, nullptr};
+  void green_split(int b_sms, int prio_a, int prio_b);
   // ---- prefill scratch
   DevBuf<float> px32, pqkv32, pqrot;
   DevBuf<__half> ph16, pattn16, pffn16;
@@ -294,6 +298,16 @@ struct Engine {
   void prefill(int rows);
 };
 
+template <typename Fn>
+static Fn driver_fn(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  PTTS_CUDA(cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q));
+  PTTS_REQUIRE(p && q == cudaDriverEntryPointSuccess, PTTS_ERR_CUDA, "%s not available in this driver", name);
+  return reinterpret_cast<Fn>(p);
+}
+#define PTTS_CU(expr) do { CUresult r_ = (expr); PTTS_REQUIRE(r_ == CUDA_SUCCESS, PTTS_ERR_CUDA, "%s failed (%d)", #expr, (int)r_); } while (0)
+
 Engine::~Engine() {
   for (int i = 0; i < NT; ++i) {
     if (pin_pcm[i]) cudaFreeHost(pin_pcm[i]);
@@ -313,6 +327,12 @@ Engine::~Engine() {
   if (stream_b) cudaStreamDestroy(stream_b);
   for (auto& r : prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (stream) cudaStreamDestroy(stream);
+  if (green_ctx[0]) {
+    try {
+      auto destroy = driver_fn<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
+      for (void* g : green_ctx) if (g) destroy(static_cast<CUgreenCtx>(g));
+    } catch (...) {}
+  }
 }
 
 void Engine::prof_begin(const char* t, double bytes, double flops, const char* fn) {
@@ -692,6 +712,37 @@ void Engine::compute_time_embeddings(int steps) {
 }
 
 // ------------------------------------------------------------------------------------------------ init
+void Engine::green_split(int b_sms, int prio_a, int prio_b) {
+  auto getDev = driver_fn<CUresult (*)(CUdevice*, int)>("cuDeviceGet");
+  auto getRes = driver_fn<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
+  auto split = driver_fn<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>("cuDevSmResourceSplitByCount");
+  auto genDesc = driver_fn<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
+  auto ctxCreate = driver_fn<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
+  auto streamCreate = driver_fn<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
+  CUdevice dev;
+  PTTS_CU(getDev(&dev, cfg.device));
+  CUdevResource all{}, part_b{}, part_a{};
+  PTTS_CU(getRes(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+  unsigned int groups = 1;
+  PTTS_CU(split(&part_b, &groups, &all, &part_a, 0, (unsigned int)b_sms));
+  PTTS_REQUIRE(groups == 1 && part_a.sm.smCount >= 64, PTTS_ERR_INVALID, "SM partition: %u SMs for the codec leaves %u", part_b.sm.smCount, part_a.sm.smCount);
+  CUdevResourceDesc da, db;
+  PTTS_CU(genDesc(&da, &part_a, 1));
+  PTTS_CU(genDesc(&db, &part_b, 1));
+  CUgreenCtx ga, gb;
+  PTTS_CU(ctxCreate(&ga, da, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+  PTTS_CU(ctxCreate(&gb, db, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+  CUstream sa, sb;
+  PTTS_CU(streamCreate(&sa, ga, CU_STREAM_NON_BLOCKING, prio_a));
+  PTTS_CU(streamCreate(&sb, gb, CU_STREAM_NON_BLOCKING, prio_b));
+  stream = sa; stream_b = sb;
+  green_ctx[0] = ga; green_ctx[1] = gb;
+  sms_a = (int)part_a.sm.smCount; sms_b = (int)part_b.sm.smCount;
+  persistent_ctas = std::min(persistent_ctas, sms_b);
+  split_cta_cap_b = std::min(split_cta_cap_b, sms_b);
+  if (std::getenv("PTTS_VERBOSE")) std::fprintf(stderr, "ptts: SM partition: language model %d SMs, codec %d SMs\n", sms_a, sms_b);
+}
+
 void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   cfg = c;
   int ndev = 0;
@@ -713,8 +764,17 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     int lo = 0, hi = 0;
     PTTS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     const bool prio = !(std::getenv("PTTS_PRIO") && std::atoi(std::getenv("PTTS_PRIO")) == 0);
-    PTTS_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio ? hi : lo));
-    PTTS_CUDA(cudaStreamCreateWithPriority(&stream_b, cudaStreamNonBlocking, lo));
+    int green_b = 0;
+    if (const char* v = std::getenv("PTTS_GREEN_B_SMS")) green_b = std::atoi(v);
+    if (green_b > 0) {
+      // SM partition (green contexts): the codec stream gets `green_b` SMs (rounded by the driver to whole co-scheduling
+      // groups), the language-model stream the rest.  The two halves of a step then never share an SM, and the codec's
+      // CTAs cannot scatter over the GPCs the language model's clusters need.
+      green_split(green_b, prio ? hi : lo, lo);
+    } else {
+      PTTS_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio ? hi : lo));
+      PTTS_CUDA(cudaStreamCreateWithPriority(&stream_b, cudaStreamNonBlocking, lo));
+    }
     if (const char* v = std::getenv("PTTS_B_SMS")) persistent_ctas = std::max(8, std::atoi(v));
     if (const char* v = std::getenv("PTTS_MAX_CTAS")) split_cta_cap = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_MAX_CTAS_B")) split_cta_cap_b = std::max(1, std::atoi(v));
