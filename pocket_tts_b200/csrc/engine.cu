@@ -225,6 +225,8 @@ struct Engine {
   const ConvSegs& segs_f(int f) const { return segs_by_f[f]; }
   // ---- codec group (set_codec_group): A queues the latents of cg consecutive frames, the codec half runs once per group
   int cg = 1;                  // frames per codec pass
+  bool use_queue = false;      // PTTS_QUEUE=1 (measured: no gain): cg == 1 also hands its latent over through the (double-buffered) queue: A(n+1) then waits for front(n-1), not front(n)
+  bool queued() const { return cg > 1 || use_queue; }
   int pend = 0, pend_n = 0;    // frames waiting in the current queue buffer, their batch rows
   int gbuf = 0;                // queue buffer the current group fills
   std::vector<int> pend_rows;  // batch composition of the waiting frames
@@ -840,6 +842,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
   {
     int frames = 1;
     if (const char* v = std::getenv("PTTS_CODEC_GROUP")) frames = std::atoi(v);
+    if (const char* v = std::getenv("PTTS_QUEUE")) use_queue = std::atoi(v) != 0;
     set_codec_group(frames == 2 || frames == 4 ? frames : 1);
   }
 
@@ -1511,7 +1514,7 @@ void Engine::run_step(int n, long long ticket) {
     PTTS_CUDA(cudaEventRecord(ev_b_done, stream_b));
     return;
   }
-  if (cg > 1) {
+  if (queued()) {
     if (pend > 0 && (pend_n != n || !std::equal(row_seq_host.begin(), row_seq_host.begin() + n, pend_rows.begin()))) flush_codec();
     if (pend == 0) {
       // the queue buffer is free once the front end of the group that used it last has run
@@ -1983,11 +1986,11 @@ static long long step_begin_impl(Engine& e, const int32_t* slot_ids, int n, int 
   check_slots(e, slot_ids, n, prev.flags_done ? 0 : 1);
   e.upload_rows(slot_ids, n);
   const int par = (int)(id % Engine::NT);
-  t.id = id; t.n = n; t.want_pcm = want_pcm; t.want_i16 = want_i16; t.codec_pending = e.cg > 1;
+  t.id = id; t.n = n; t.want_pcm = want_pcm; t.want_i16 = want_i16; t.codec_pending = e.queued();
   e.run_step(n, id);   // cg > 1: the PCM copy and ev_pcm are issued when the frame's codec group is flushed
   PTTS_CUDA(cudaMemcpyAsync(e.pin_lat[par], e.step_out.p, e.step_out_bytes(), cudaMemcpyDeviceToHost, e.stream));
   PTTS_CUDA(cudaEventRecord(e.ev_flags[par], e.stream));
-  if (e.cg == 1) {
+  if (!e.queued()) {
     if (want_i16) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm16[par], e.pcm16.p, (size_t)n * FRAME * 2, cudaMemcpyDeviceToHost, e.stream_b));
     else if (want_pcm) PTTS_CUDA(cudaMemcpyAsync(e.pin_pcm[par], e.pcm.p, (size_t)n * FRAME * 4, cudaMemcpyDeviceToHost, e.stream_b));
     PTTS_CUDA(cudaEventRecord(e.ev_pcm[par], e.stream_b));
