@@ -203,7 +203,9 @@ def run_gpu(args):
 
     wnp = synth.make_weights(1234)
     wnp.update(synth.make_encoder_weights(4321))  # voice-cloning side, only used by the voice_from_pcm timing below
-    eng = Engine(wnp, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3, int8_weights=args.int8)
+    eng_kw = dict(int8_weights=args.int8, codec_group=args.codec_group if args.codec_group > 1 else None,
+                  lm_step_kernel=True if args.lm_step_kernel else None)
+    eng = Engine(wnp, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3, **eng_kw)
     del wnp
     voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
     base = rank * STREAMS  # request ids of this shard
@@ -213,24 +215,26 @@ def run_gpu(args):
 
     def job(host: bool, profile=None):
         slots = eng.open_streams([voice] * STREAMS, specs)
-        prev = None
+        lag = max(1, args.codec_group)   # the PCM of frame f is fetched once frame f + lag has been enqueued (its codec group is complete)
+        tickets = []
         t = eng.step_begin(slots) if host else None
         for f in range(FRAMES):
             if host:
                 # public pipelined calls: frame f+1 is enqueued ahead of frame f's flags (PTTS_STEP_AHEAD; every stream
                 # runs to max_gen_len here, so the host knows frame f is not the last), the flags of frame f are awaited
-                # and read, then the PCM of frame f-1 is fetched while the device is already on frame f+1
+                # and read, then the PCM of frame f-lag is fetched while the device is already on frame f+1
                 nxt = eng.step_begin(slots, ahead=True) if f + 1 < FRAMES else None
                 fin, _, _ = eng.step_flags(t)
-                if prev is not None:
-                    pcm = eng.step_pcm(prev)
-                prev, t = t, nxt
+                tickets.append(t)
+                if len(tickets) > lag:
+                    pcm = eng.step_pcm(tickets.pop(0))
+                t = nxt
             elif profile is not None and f in profile:
                 eng.profile(True); eng.step_device(slots); eng.profile(False)
             else:
                 eng.step_device(slots)
-        if host:
-            pcm = eng.step_pcm(prev)
+        for tk in tickets:
+            pcm = eng.step_pcm(tk)
         eng.sync()
         if host:
             assert fin.all() and np.isfinite(pcm).all()
@@ -284,7 +288,7 @@ def run_gpu(args):
         if eng_lf is None:
             voice.close(); eng.close()
             wnp2 = synth.make_weights(1234)
-            eng = Engine(wnp2, device=local, max_slots=args.longform, kv_capacity=TOKENS + FRAMES + 3, int8_weights=args.int8)
+            eng = Engine(wnp2, device=local, max_slots=args.longform, kv_capacity=TOKENS + FRAMES + 3, **eng_kw)
             del wnp2
             voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
         reqs = []
@@ -317,7 +321,7 @@ def run_gpu(args):
             voice.close(); eng.close()
             wnp2 = synth.make_weights(1234)
             wnp2.update(synth.make_encoder_weights(4321))
-            eng = Engine(wnp2, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3, int8_weights=args.int8)
+            eng = Engine(wnp2, device=local, max_slots=STREAMS, kv_capacity=TOKENS + FRAMES + 3, **eng_kw)
             del wnp2
             voice = eng.voice_from_prompt(synth.make_voice_prompt(VOICE_ROWS, seed=7))
 
@@ -446,12 +450,20 @@ def main():
                     help="concurrent streams per GPU (default 64 = BASELINE configs[1]; 256/512 explore configs[3]/[4] shapes)")
     ap.add_argument("--longform", type=int, default=512,
                     help="requests per GPU of the configs[4] slice run through the native scheduler (0 = skip); reported under `longform`")
+    ap.add_argument("--codec-group", type=int, default=1, choices=[1, 2, 4],
+                    help="frames per codec pass (ptts_engine_set_codec_group; non-headline when > 1: same PCM, the Mimi decoder + SEANet run once per group)")
+    ap.add_argument("--lm-step-kernel", action="store_true",
+                    help="force the persistent FlowLM step kernel (csrc/lm_step.cuh) instead of the per-layer launches (non-headline)")
     ap.add_argument("--int8", action="store_true",
                     help="per-tensor int8 weights (reference quantize.rs scheme), one-byte codes expanded in the decode GEMMs: configs[3] with --streams 256")
     args = ap.parse_args()
     if args.int8:
         CONFIG["workload"] = CONFIG["workload"].replace("f16-operand", "int8-weight (non-headline)")
         CONFIG["weights"] = "int8 per-tensor codes in HBM, f16 MMA operands, scale in the epilogue"
+    if args.codec_group > 1:
+        CONFIG["codec_group"] = args.codec_group
+    if args.lm_step_kernel:
+        CONFIG["lm_step_kernel"] = True
     if args.streams != STREAMS:
         globals()["STREAMS"] = args.streams
         CONFIG["streams_per_gpu"] = args.streams
