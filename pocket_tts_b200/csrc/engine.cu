@@ -20,6 +20,7 @@
 #include "../../include/ptts_internal.h"
 #include "kernels.cuh"
 #include "lm_step.cuh"
+#include "seanet_tail.cuh"
 
 namespace ptts {
 
@@ -237,6 +238,8 @@ struct Engine {
   cudaEvent_t ev_gfront[2] = {};
   void flush_codec();
   void set_codec_group(int frames);
+  bool fused_tail = true;      // the last SEANet block + final conv as one kernel (seanet_tail.cuh); PTTS_SEANET_TAIL=0: three launches
+  void seanet_tail(int n, int T);
   // SM partition between the two streams (green contexts); 0 SMs = none
   int sms_a = 0, sms_b = 0;
   void* green_ctx[2] = {nullptr, nullptr};
@@ -843,6 +846,9 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     int frames = 1;
     if (const char* v = std::getenv("PTTS_CODEC_GROUP")) frames = std::atoi(v);
     if (const char* v = std::getenv("PTTS_QUEUE")) use_queue = std::atoi(v) != 0;
+    if (const char* v = std::getenv("PTTS_SEANET_TAIL")) fused_tail = std::atoi(v) != 0;
+    if (cfg.debug_gemm) fused_tail = false;   // the SIMT cross-check path keeps every layer a separate launch
+    PTTS_CUDA(cudaFuncSetAttribute(seanet_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
     set_codec_group(frames == 2 || frames == 4 ? frames : 1);
   }
 
@@ -1126,6 +1132,26 @@ void Engine::flow_head_fused(int n, const float* mod, long long mod_step_stride,
   PTTS_CUDA(cudaGetLastError());
 }
 
+// The last SEANet ResBlock (k3 conv, k1 conv, skip) + the final 64 -> 1 conv of every stream over T samples (seanet_tail.cuh).
+void Engine::seanet_tail(int n, int T) {
+  SeanetTailParams tp{};
+  tp.b_a = sb_r9a.p; tp.b_b = sb_r9b.p; tp.w_f = s_final_w.p; tp.b_f = s_final_b.p;
+  tp.a9buf = a9.p; tp.pcm = pcm.p; tp.pcm16 = pcm16.p;
+  tp.n = n; tp.T = T; tp.tiles_per_stream = (T + ST_STEP - 1) / ST_STEP; tp.n_tiles = n * tp.tiles_per_stream;
+  const CUtensorMap& me = tmaps.get(e8.p, 64, 2 + T, NB, 64, (long long)(2 + T) * 64, ST_ROWS, 1);
+  // the f32 skip viewed as rows of 128 halves, so that a 128-byte swizzled box is 32 floats wide
+  const CUtensorMap& mx = tmaps.get(reinterpret_cast<const __half*>(x8.p), 128, T, NB, 128, (long long)T * 128, ST_ROWS, 1);
+  const CUtensorMap& mwa = tmaps.get(s_r9a.w.p, s_r9a.K, s_r9a.Fpad, 1, s_r9a.K, (long long)s_r9a.Fpad * s_r9a.K, 64, 1);
+  const CUtensorMap& mwb = tmaps.get(s_r9b.w.p, s_r9b.K, s_r9b.Fpad, 1, s_r9b.K, (long long)s_r9b.Fpad * s_r9b.K, 64, 1);
+  const int grid = std::min(tp.n_tiles, persistent_ctas);
+  // algorithmic traffic: e8 and x8 in, PCM (+ i16) out, weights once
+  const double bytes = (double)n * ((2.0 + T) * 128 + (double)T * 256 + T * 6.0) + 64.0 * 256 * 2 + 64 * 4 * 2 + 192 * 4;
+  const double flops = 2.0 * n * T * (64.0 * 192 + 64.0 * 64 + 192);
+  ProfScope ps(*this, "seanet.tail_fused", bytes, flops, "seanet_tail_kernel");
+  launch_k(use_pdl, seanet_tail_kernel, grid, ST_THREADS, ST_SMEM, ls, 1, me, mx, mwa, mwb, tp);
+  PTTS_CUDA(cudaGetLastError());
+}
+
 void Engine::lm_step(int n) {
   LmStepParams& q = lm_params;
   q.n = n;
@@ -1378,13 +1404,17 @@ void Engine::step_part_b(int n, int f, bool marks) {
   e = epi_none(); e.bias = sb_ct8.p; e.out32 = x8.p; e.out32_map = stream_map(T3, 256, (long long)T4 * 64, 0);
   e.out16 = e8.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T3, 256, (long long)(2 + T4) * 64, 2 * 64);
   tag("seanet.convtr8"); gemm(ActView{a6.p, 128, 1 + T3, NB}, n, T3, 2, 120, 1, s_ct8, 256, e);
-  e = epi_none(); e.bias = sb_r9a.p; e.out16 = h9.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
-  tag("seanet.res9a"); gemm(ActView{e8.p, 64, 2 + T4, NB}, n, T4, 3, 128, 1, s_r9a, 64, e);
-  e = epi_none(); e.bias = sb_r9b.p; e.res = x8.p; e.res_map = plain_map(64);
-  e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T4, 64, (long long)(2 + T4) * 64, 128);
-  tag("seanet.res9b"); gemm(ActView{h9.p, 64, T4, NB}, n, T4, 1, 128, 1, s_r9b, 64, e);
-  { ProfScope ps(*this, "seanet.final_conv", (double)n * ((2.0 + T4) * 128 + T4 * 4), 2.0 * n * T4 * 192);
-    launch_k(use_pdl, seanet_final_conv_kernel, dim3((T4 + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, T4, pcm.p, pcm16.p); }
+  if (fused_tail) {
+    seanet_tail(n, T4);
+  } else {
+    e = epi_none(); e.bias = sb_r9a.p; e.out16 = h9.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
+    tag("seanet.res9a"); gemm(ActView{e8.p, 64, 2 + T4, NB}, n, T4, 3, 128, 1, s_r9a, 64, e);
+    e = epi_none(); e.bias = sb_r9b.p; e.res = x8.p; e.res_map = plain_map(64);
+    e.out16 = a9.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T4, 64, (long long)(2 + T4) * 64, 128);
+    tag("seanet.res9b"); gemm(ActView{h9.p, 64, T4, NB}, n, T4, 1, 128, 1, s_r9b, 64, e);
+    { ProfScope ps(*this, "seanet.final_conv", (double)n * ((2.0 + T4) * 128 + T4 * 4), 2.0 * n * T4 * 192);
+      launch_k(use_pdl, seanet_final_conv_kernel, dim3((T4 + 255) / 256, n), 256, 0, ls, 1, a9.p, s_final_w.p, s_final_b.p, n, T4, pcm.p, pcm16.p); }
+  }
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
     launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, sg, row_seq.p, 1); }
 }
