@@ -1258,13 +1258,20 @@ void Engine::step_part_a(int n, bool marks) {
     return;
   }
   // ---- FlowLM AR step (reference models/flow_lm.rs:98-145)
-  { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
-    launch_k(use_pdl, step_begin_kernel, n, 64, 0, ls, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p, (const SeqDesc*)seqs.p,
-             (const int*)own_len.p, row_desc.p); }
   GemmEpi e = epi_none();
-  e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
-  ln_after_next_gemm("flowlm.layernorm", x32.p, n, D_MODEL, ln1_w[0].p, ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, h16.p, D_MODEL);
-  tag("flowlm.input_linear"); gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
+  if (!cfg.debug_gemm && cfg.reserved[0] != 1) {
+    // gather + input_linear + LayerNorm 1 of layer 0 in one launch
+    ProfScope ps(*this, "flowlm.input_fused", (double)n * (32 * 12 + D_MODEL * 6) + D_MODEL * 64.0, 2.0 * n * D_MODEL * LDIM, "flowlm_input_kernel");
+    launch_k(use_pdl, flowlm_input_kernel, n, 256, 0, ls, 1, row_seq.p, ctl.p, feedback.p, (const SeqDesc*)seqs.p, (const int*)own_len.p, row_desc.p,
+             z32.p, z16.p, (const __half*)w_input.w.p, (const float*)w_input.wscale.p, (const float*)ln1_w[0].p, (const float*)ln1_b[0].p, x32.p, h16.p);
+  } else {
+    { ProfScope ps(*this, "step.begin", (double)n * 32 * 12, 0);
+      launch_k(use_pdl, step_begin_kernel, n, 64, 0, ls, 1, row_seq.p, ctl.p, feedback.p, lat16.p, z32.p, z16.p, (const SeqDesc*)seqs.p,
+               (const int*)own_len.p, row_desc.p); }
+    e.out32 = x32.p; e.out32_map = plain_map(D_MODEL);
+    ln_after_next_gemm("flowlm.layernorm", x32.p, n, D_MODEL, ln1_w[0].p, ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, h16.p, D_MODEL);
+    tag("flowlm.input_linear"); gemm_rows(lat16.p, n, 64, w_input, D_MODEL, e);
+  }
   flowlm_layers(n, x32.p, h16.p, qkv32.p, attn16.p, ffn16.p, false, nullptr, row_seq.p, nullptr);
   { ProfScope ps(*this, "flowlm.out_norm_eos", (double)n * D_MODEL * (4 + 2 + 4), 0);
     launch_k(use_pdl, ln_eos_kernel, (n + 3) / 4, 128, 0, ls, 1, x32.p, n, outnorm_w.p, outnorm_b.p, eos_w.p, eos_b.p, h16.p, h32dbg.p,

@@ -53,10 +53,20 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, int rows, const floa
                                const float* __restrict__ b, float eps, const float* __restrict__ shift,
                                const float* __restrict__ scale, int mod_ld, __half* __restrict__ out16, int out_ld) {
   pdl_launch_dependents();
-  pdl_wait();
   constexpr int PER = C / 32;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  // the affine parameters are constants: requested before the dependency on the producer of x resolves, so that the
+  // kernel is one memory round trip (x) instead of two behind griddepcontrol.wait
+  float4 w4[PER / 4], b4[PER / 4];
+  if (w) {
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) {
+      w4[i] = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
+      b4[i] = __ldg(reinterpret_cast<const float4*>(b) + i * 32 + lane);
+    }
+  }
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
   float v[PER];
@@ -76,11 +86,12 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, int rows, const floa
 #pragma unroll
   for (int i = 0; i < PER / 4; ++i) {
     const int c = (i * 32 + lane) * 4;
+    const float wv[4] = {w4[i].x, w4[i].y, w4[i].z, w4[i].w}, bv[4] = {b4[i].x, b4[i].y, b4[i].z, b4[i].w};
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float y = (v[4 * i + j] - mean) * rstd;
-      if (w) y = y * __ldg(w + c + j) + __ldg(b + c + j);
+      if (w) y = y * wv[j] + bv[j];
       if (scale) y = y * (1.f + scale[static_cast<long long>(row) * mod_ld + c + j]) +
                      shift[static_cast<long long>(row) * mod_ld + c + j];
       o[j] = y;
@@ -99,10 +110,17 @@ __global__ void ln_eos_kernel(const float* __restrict__ x, int rows, const float
                               const float* __restrict__ b, const float* __restrict__ w_eos, const float* __restrict__ b_eos,
                               __half* __restrict__ h16, float* __restrict__ h32, float* __restrict__ eos_logit) {
   pdl_launch_dependents();
-  pdl_wait();
   constexpr int C = 1024, PER = 32;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  float4 w4[PER / 4], b4[PER / 4], e4[PER / 4];   // constants, requested before the dependency resolves
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    w4[i] = __ldg(reinterpret_cast<const float4*>(w) + i * 32 + lane);
+    b4[i] = __ldg(reinterpret_cast<const float4*>(b) + i * 32 + lane);
+    e4[i] = __ldg(reinterpret_cast<const float4*>(w_eos) + i * 32 + lane);
+  }
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
   float v[PER];
@@ -123,10 +141,12 @@ __global__ void ln_eos_kernel(const float* __restrict__ x, int rows, const float
 #pragma unroll
   for (int i = 0; i < PER / 4; ++i) {
     const int c = (i * 32 + lane) * 4;
+    const float wv[4] = {w4[i].x, w4[i].y, w4[i].z, w4[i].w}, bv[4] = {b4[i].x, b4[i].y, b4[i].z, b4[i].w};
+    const float ev[4] = {e4[i].x, e4[i].y, e4[i].z, e4[i].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float y = (v[4 * i + j] - mean) * rstd * __ldg(w + c + j) + __ldg(b + c + j);
-      dot += y * __ldg(w_eos + c + j);
+      const float y = (v[4 * i + j] - mean) * rstd * wv[j] + bv[j];
+      dot += y * ev[j];
       h16[static_cast<long long>(row) * C + c + j] = __float2half_rn(y);
       if (h32) h32[static_cast<long long>(row) * C + c + j] = y;
     }
@@ -742,6 +762,94 @@ __global__ void step_begin_kernel(const int* __restrict__ row_seq, const StreamC
   }
   lat16[b * 64 + k] = __float2half_rn(lat);
   z16[b * 64 + k] = __float2half_rn(z);
+}
+
+// step_begin + input_linear + the first LayerNorm in ONE launch (reference tts_model.rs:971,1065 feedback / BOS;
+// flow_lm.rs:118 input_linear, :148-153 noise draw; modules/mlp.rs:29-58 LayerNorm).  As three launches (gather, a tcgen05
+// GEMM with K = 32 padded to 64, LayerNorm) this was 13.6 us of mostly launch latency for 2 MFLOP.  grid n, block 256:
+// thread t owns features 4t..4t+3 of the row; its 4 x 32 weights and the affine parameters are constants and are requested
+// before the dependency on the previous step resolves.  Same arithmetic as the GEMM up to the order of the 32 additions
+// (f16 weights, the latent rounded to f16, f32 accumulation).
+__global__ void __launch_bounds__(256) flowlm_input_kernel(const int* __restrict__ row_seq, const StreamCtl* __restrict__ ctl,
+                                                           const float* __restrict__ feedback, const SeqDesc* __restrict__ seqs,
+                                                           const int* __restrict__ own_len, SeqDesc* __restrict__ row_desc,
+                                                           float* __restrict__ z32, __half* __restrict__ z16,
+                                                           const __half* __restrict__ w_in /*[1024][64], k >= 32 zero*/,
+                                                           const float* __restrict__ w_scale /*[1024] int8 mode, else null*/,
+                                                           const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                           float* __restrict__ x32 /*[n,1024]*/, __half* __restrict__ h16 /*[n,1024]*/) {
+  pdl_launch_dependents();
+  constexpr int C = 1024;
+  __shared__ float lat_s[LDIM];
+  __shared__ float red_s[2][8];
+  const int b = blockIdx.x, t = threadIdx.x, f = t * 4;
+  uint4 wr[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) wr[j][c4] = __ldg(reinterpret_cast<const uint4*>(w_in + static_cast<size_t>(f + j) * 64) + c4);
+  const float4 lw = __ldg(reinterpret_cast<const float4*>(ln_w + f)), lb = __ldg(reinterpret_cast<const float4*>(ln_b + f));
+  float4 ws = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (w_scale) ws = __ldg(reinterpret_cast<const float4*>(w_scale + f));
+  pdl_wait();
+  const int slot = row_seq[b];
+  if (t == 64) {
+    SeqDesc d = seqs[slot];
+    d.pad = own_len[slot];
+    row_desc[b] = d;
+  }
+  if (t < 64) {
+    float z = 0.f;
+    if (t < LDIM) {
+      const StreamCtl c = ctl[slot];
+      // a step enqueued ahead of the host (PTTS_STEP_AHEAD) may run one frame past the end: no noise row exists there
+      if (c.noise) z = c.frame < c.max_gen_len ? c.noise[static_cast<long long>(c.frame) * LDIM + t] : 0.f;
+      else if (c.temp > 0.f) z = sqrtf(c.temp) * counter_normal(c.seed, c.frame, t);
+      z32[b * LDIM + t] = z;
+      lat_s[t] = __half2float(__float2half_rn(feedback[slot * LDIM + t]));
+    }
+    z16[b * 64 + t] = __float2half_rn(z);
+  }
+  __syncthreads();
+  float xv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      const __half2* h2 = reinterpret_cast<const __half2*>(&wr[j][c4]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 wf = __half22float2(h2[e]);
+        a += wf.x * lat_s[c4 * 8 + 2 * e] + wf.y * lat_s[c4 * 8 + 2 * e + 1];
+      }
+    }
+    xv[j] = a;
+  }
+  xv[0] *= ws.x; xv[1] *= ws.y; xv[2] *= ws.z; xv[3] *= ws.w;
+  *reinterpret_cast<float4*>(x32 + static_cast<size_t>(b) * C + f) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+  const int warp = t >> 5, lane = t & 31;
+  float s = warp_sum(xv[0] + xv[1] + xv[2] + xv[3]);
+  if (lane == 0) red_s[0][warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red_s[0][i];
+  const float mean = tot * (1.f / C);
+  const float d0 = xv[0] - mean, d1 = xv[1] - mean, d2 = xv[2] - mean, d3 = xv[3] - mean;
+  float q = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+  if (lane == 0) red_s[1][warp] = q;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) var += red_s[1][i];
+  const float rstd = 1.f / sqrtf(var * (1.f / C) + 1e-5f);
+  const __half2 h0 = __floats2half2_rn(d0 * rstd * lw.x + lb.x, d1 * rstd * lw.y + lb.y);
+  const __half2 h1 = __floats2half2_rn(d2 * rstd * lw.z + lb.z, d3 * rstd * lw.w + lb.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(h16 + static_cast<size_t>(b) * C + f) = pk;
 }
 
 // EOS bookkeeping of the frame loop (reference tts_model.rs:1055-1069, D2: the frame at
