@@ -538,6 +538,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   const int kb0 = rank * p.kb_per_split;
   const int kb1 = min(total_kb, kb0 + p.kb_per_split);
   const int nkb = kb1 - kb0;         // >= 1 by construction of the split
+  // per-feature epilogue constants (bias, LayerScale, int8 scale): requested now, not behind the accumulator -- as the
+  // first thing of the store loop they were one L2 round trip on the critical path of every launch
+  EpiHoist hoist;
+  const bool hoisted = p.vec4 && (p.epi.bias || p.epi.fscale || p.epi.wscale);
+  if (hoisted) epi_hoist_init(p, f0, threadIdx.x, hoist);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_act);
@@ -740,7 +745,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_act, const __grid_constan
   __syncthreads();
   if (nsplit > 1) cluster_sync_all();  // all partial tiles are staged and visible cluster-wide
   pdl_wait();  // residual / gate / output tensors belong to earlier kernels until they have completed
-  epi_dispatch(p, smem_u32(smem), (p.swap ? GEMM_BM : p.BN) + 4, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit);
+  epi_dispatch(p, smem_u32(smem), (p.swap ? GEMM_BM : p.BN) + 4, f0, t0, b0, threadIdx.x, GEMM_THREADS, rank, nsplit, hoisted ? &hoist : nullptr);
   if (warp == 2) PTTS_TRACE(8);
   if (nsplit > 1) cluster_sync_relaxed();  // peers may still be reading this CTA's tile
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
