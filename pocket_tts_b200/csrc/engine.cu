@@ -113,7 +113,7 @@ struct Engine {
   int split_cta_cap_b = 48; // the same for the activation-as-M GEMMs of the codec half (PTTS_MAX_CTAS_B)
   int split_cap_override = 0;  // one-shot cap for the next GEMM
   int gemm_ref_f = 1;          // > 1 while the GEMMs of a codec group of that many frames are issued (see Engine::gemm)
-  int lin1_ctas = 48;          // linear1 (32 feature tiles): 64 lets it split in two and keep its K slice resident (PTTS_LIN1_CTAS)
+  int lin1_ctas = 64;          // linear1 (32 feature tiles): 64 lets it split in two and keep its K slice resident (PTTS_LIN1_CTAS)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)

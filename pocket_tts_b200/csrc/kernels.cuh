@@ -287,35 +287,156 @@ __device__ __forceinline__ void attend_block(const SeqDesc& sd, int layer, int h
 
 // FlowLM decode attention, one new row per stream (reference modules/attention.rs:104-231 with t = 1):
 // RoPE(q,k) at the absolute position, append K,V at the cursor, causal SDPA over prefix + own rows, all fused.
-// grid (n, heads), block ATTN_THREADS.
+// grid (n, heads), block ATTN_THREADS.  The rows already in the cache do not depend on this step's projections, so every
+// warp requests its first 16 keys the moment the row descriptor is known; the q / k / v loads, RoPE and the block barrier
+// of warp 0 then run inside that memory round trip instead of in front of it.  The new key never goes through the cache:
+// it joins the merge of the warps' partial results as a fifth partial (rounded to f16 like the row later steps will read).
 __global__ void __launch_bounds__(ATTN_THREADS, 7) flowlm_attn_decode_kernel(const float* __restrict__ qkv,
                                           const SeqDesc* __restrict__ row_desc /*[n], cursor in .pad (step_begin_kernel)*/,
                                           int layer, int n_heads, __half* __restrict__ out16) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float sm[64 + 64 + 4 * 66];
-  float* q_s = sm;
-  float* red_s = sm + 64;
-  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  constexpr int NW = ATTN_THREADS / 32, U = 4;
+  __shared__ float sm[64 + 64 + 64 + 4 * 66 + 2];
+  float* q_s = sm;            // rotated q
+  float* kn_s = sm + 64;      // the new key (rotated, f16-rounded), later the merged output
+  float* vn_s = sm + 128;     // the new value (f16-rounded)
+  float* red_s = sm + 192;    // [4][66] per-warp partials
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane >> 3, part = lane & 7;
   const int d_model = n_heads * HD;
   const SeqDesc sd = row_desc[b];
-  const int pos = sd.prefix_len + sd.pad;
-  const float* row = qkv + static_cast<long long>(b) * 3 * d_model;
+  const int pos = sd.prefix_len + sd.pad;   // keys already in the cache = position of the new row
+  uint4 ku[U], vu[U];
+  int i0 = warp * 4 * U;
+  auto request = [&](int base) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * 4 + sub;
+      ku[u] = vu[u] = make_uint4(0, 0, 0, 0);
+      if (i < pos) {
+        ku[u] = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, h, n_heads, i))[part];
+        vu[u] = reinterpret_cast<const uint4*>(kv_row(sd, layer, 1, h, n_heads, i))[part];
+      }
+    }
+  };
+  request(i0);
   if (tid < 32) {
-    float qr, qi, kr, ki;
-    rope_pair(row[h * HD + 2 * tid], row[h * HD + 2 * tid + 1], pos, tid, qr, qi);
-    rope_pair(row[d_model + h * HD + 2 * tid], row[d_model + h * HD + 2 * tid + 1], pos, tid, kr, ki);
-    q_s[2 * tid] = qr;
-    q_s[2 * tid + 1] = qi;
-    __half* kd = const_cast<__half*>(kv_row(sd, layer, 0, h, n_heads, pos));
-    __half* vd = const_cast<__half*>(kv_row(sd, layer, 1, h, n_heads, pos));
-    reinterpret_cast<__half2*>(kd)[tid] = __floats2half2_rn(kr, ki);
-    reinterpret_cast<__half2*>(vd)[tid] =
-        __floats2half2_rn(row[2 * d_model + h * HD + 2 * tid], row[2 * d_model + h * HD + 2 * tid + 1]);
+    const float* row = qkv + static_cast<long long>(b) * 3 * d_model;
+    const float2 qx = *reinterpret_cast<const float2*>(row + h * HD + 2 * tid);
+    const float2 kx = *reinterpret_cast<const float2*>(row + d_model + h * HD + 2 * tid);
+    const float2 vx = *reinterpret_cast<const float2*>(row + 2 * d_model + h * HD + 2 * tid);
+    float sn, cs;
+    sincosf(static_cast<float>(pos) * c_inv_freq[tid], &sn, &cs);   // modules/rope.rs:18-60, one angle for q and k
+    q_s[2 * tid] = qx.x * cs - qx.y * sn;
+    q_s[2 * tid + 1] = qx.x * sn + qx.y * cs;
+    const __half2 kh = __floats2half2_rn(kx.x * cs - kx.y * sn, kx.x * sn + kx.y * cs), vh = __floats2half2_rn(vx.x, vx.y);
+    reinterpret_cast<__half2*>(const_cast<__half*>(kv_row(sd, layer, 0, h, n_heads, pos)))[tid] = kh;
+    reinterpret_cast<__half2*>(const_cast<__half*>(kv_row(sd, layer, 1, h, n_heads, pos)))[tid] = vh;
+    const float2 kf = __half22float2(kh), vf = __half22float2(vh);
+    kn_s[2 * tid] = kf.x; kn_s[2 * tid + 1] = kf.y;
+    vn_s[2 * tid] = vf.x; vn_s[2 * tid + 1] = vf.y;
   }
   __syncthreads();
-  attend_block(sd, layer, h, n_heads, q_s, red_s, pos + 1);
-  if (tid < 64) out16[static_cast<long long>(b) * d_model + h * HD + tid] = __float2half_rn(red_s[tid]);
+  float q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = q_s[part * 8 + j] * 0.125f;  // 1/sqrt(64) folded into q
+  float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (; i0 < pos; i0 += NW * 4 * U) {
+    float sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const __half2* kh = reinterpret_cast<const __half2*>(&ku[u]);
+      sc[u] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(kh[j]);
+        sc[u] += f.x * q[2 * j] + f.y * q[2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int x = 1; x <= 4; x <<= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], x);
+    // one rescale for the group of U keys (keys past the end score -inf and weigh 0)
+    float m_new = m;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * 4 + sub >= pos) sc[u] = -INFINITY;
+      m_new = fmaxf(m_new, sc[u]);
+    }
+    if (m_new != -INFINITY) {
+      const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first group
+      l *= corr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= corr;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float pw = expf(sc[u] - m_new);
+        l += pw;
+        const __half2* vh = reinterpret_cast<const __half2*>(&vu[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(vh[j]);
+          acc[2 * j] += pw * f.x;
+          acc[2 * j + 1] += pw * f.y;
+        }
+      }
+      m = m_new;
+    }
+    if (i0 + NW * 4 * U < pos) request(i0 + NW * 4 * U);
+  }
+  // fold the 4 key sub-groups of the warp, then the 4 warps and the new key, always in the same order
+#pragma unroll
+  for (int x = 8; x <= 16; x <<= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m, x);
+    const float l_o = __shfl_xor_sync(0xffffffffu, l, x);
+    const float m_new = fmaxf(m, m_o);
+    const float ca = (m == -INFINITY) ? 0.f : expf(m - m_new);
+    const float cb = (m_o == -INFINITY) ? 0.f : expf(m_o - m_new);
+    l = l * ca + l_o * cb;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a_o = __shfl_xor_sync(0xffffffffu, acc[j], x);
+      acc[j] = acc[j] * ca + a_o * cb;
+    }
+    m = m_new;
+  }
+  float* wsm = red_s + warp * 66;
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wsm[part * 8 + j] = acc[j];
+    if (part == 0) { wsm[64] = m; wsm[65] = l; }
+  }
+  if (warp == 0) {  // score of the new key: q . k_new / 8
+    float sn = 0.f;
+    if (sub == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sn += q[j] * kn_s[part * 8 + j];
+    }
+#pragma unroll
+    for (int x = 1; x <= 4; x <<= 1) sn += __shfl_xor_sync(0xffffffffu, sn, x);
+    if (lane == 0) sm[192 + 4 * 66] = sn;
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const float s_new = sm[192 + 4 * 66];
+    float gm = s_new;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) gm = fmaxf(gm, red_s[w * 66 + 64]);
+    float o = 0.f, lt = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float mw = red_s[w * 66 + 64];
+      const float c = (mw == -INFINITY) ? 0.f : expf(mw - gm);
+      o += red_s[w * 66 + tid] * c;
+      lt += red_s[w * 66 + 65] * c;
+    }
+    const float cn = expf(s_new - gm);
+    o += vn_s[tid] * cn;
+    lt += cn;
+    out16[static_cast<long long>(b) * d_model + h * HD + tid] = __float2half_rn(o / lt);
+  }
 }
 
 // Prefill, step 1: RoPE + KV append for every new row (rows of several sequences at once); rotated q kept in f32.
