@@ -226,7 +226,7 @@ struct Engine {
   const ConvSegs& segs_f(int f) const { return segs_by_f[f]; }
   // ---- codec group (set_codec_group): A queues the latents of cg consecutive frames, the codec half runs once per group
   int cg = 1;                  // frames per codec pass
-  bool use_queue = false;      // PTTS_QUEUE=1 (measured: no gain): cg == 1 also hands its latent over through the (double-buffered) queue: A(n+1) then waits for front(n-1), not front(n)
+  bool use_queue = true;       // (PTTS_QUEUE=0: off) cg == 1 also hands its latent over through the (double-buffered) queue: A(n+1) then waits for front(n-1), not front(n)
   bool queued() const { return cg > 1 || use_queue; }
   int pend = 0, pend_n = 0;    // frames waiting in the current queue buffer, their batch rows
   int gbuf = 0;                // queue buffer the current group fills
