@@ -581,17 +581,29 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, long long z_fr
                                      float* __restrict__ partial /*[slots,16,512]*/, float* __restrict__ x /*[n*f*16,512]*/,
                                      float* __restrict__ dbg_quant, int* __restrict__ mimi_pos) {
   pdl_launch_dependents();
-  pdl_wait();
   __shared__ float zd[2][LDIM];
   const int b = blockIdx.x, c = blockIdx.y * 128 + threadIdx.x, j = blockIdx.z, f = gridDim.z;
+  // this thread's column of the quantizer projection and of the upsampling kernel, and the de-normalisation constants:
+  // requested before the dependency on the step that produced the latent resolves
+  float wq[LDIM], w0[16], w1[16];
+#pragma unroll
+  for (int k = 0; k < LDIM; ++k) wq[k] = __ldg(wq_t + k * 512 + c);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    w0[i] = __ldg(wup_t + i * 512 + c);
+    w1[i] = __ldg(wup_t + (16 + i) * 512 + c);
+  }
+  float es = 0.f, em = 0.f;
+  if (threadIdx.x < LDIM) { es = __ldg(emb_std + threadIdx.x); em = __ldg(emb_mean + threadIdx.x); }
+  pdl_wait();
   const int slot = row_seq[b];
   // zd[1]: the frame whose second half this block also needs -- the previous frame (j > 0: it supplies the partial this
   // frame inherits) or, in block j = 0, the group's last frame (it supplies the partial the slot carries to the next pass;
   // the block that reads the carried partial is the one that replaces it, so no other block ever touches it)
   const int j2 = j > 0 ? j - 1 : f - 1;
   if (threadIdx.x < LDIM) {
-    zd[0][threadIdx.x] = z[j * z_frame_stride + b * LDIM + threadIdx.x] * emb_std[threadIdx.x] + emb_mean[threadIdx.x];
-    zd[1][threadIdx.x] = z[j2 * z_frame_stride + b * LDIM + threadIdx.x] * emb_std[threadIdx.x] + emb_mean[threadIdx.x];
+    zd[0][threadIdx.x] = z[j * z_frame_stride + b * LDIM + threadIdx.x] * es + em;
+    zd[1][threadIdx.x] = z[j2 * z_frame_stride + b * LDIM + threadIdx.x] * es + em;
   }
   // position of the group's first frame.  Without a queue this launch runs after step_end of the same frame: the frame
   // counter has already advanced by one
@@ -599,18 +611,14 @@ __global__ void mimi_frontend_kernel(const float* __restrict__ z, long long z_fr
   __syncthreads();
   float qv = 0.f, q2 = 0.f;
 #pragma unroll
-  for (int k = 0; k < LDIM; ++k) qv += __ldg(wq_t + k * 512 + c) * zd[0][k];
+  for (int k = 0; k < LDIM; ++k) qv += wq[k] * zd[0][k];
 #pragma unroll
-  for (int k = 0; k < LDIM; ++k) q2 += __ldg(wq_t + k * 512 + c) * zd[1][k];
+  for (int k = 0; k < LDIM; ++k) q2 += wq[k] * zd[1][k];
   if (dbg_quant && j == 0) dbg_quant[b * 512 + c] = q2;   // the last frame of the group
   float* part = partial + static_cast<long long>(slot) * 16 * 512;
-  float old[16], w0[16], w1[16];
+  float old[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    w0[i] = __ldg(wup_t + i * 512 + c);
-    w1[i] = __ldg(wup_t + (16 + i) * 512 + c);
-    old[i] = (j == 0) ? part[i * 512 + c] : __fmul_rn(q2, w1[i]);
-  }
+  for (int i = 0; i < 16; ++i) old[i] = (j == 0) ? part[i * 512 + c] : __fmul_rn(q2, w1[i]);
   float* xo = x + (static_cast<long long>(b) * f + j) * 16 * 512 + c;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {

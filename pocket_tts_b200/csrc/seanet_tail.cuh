@@ -156,16 +156,16 @@ seanet_tail_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
     }
   } else {
     // ===== epilogue: thread = (tile row, half of the channels) =====
-    pdl_wait();
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int i = quad * 32 + lane;                       // tile row = TMEM lane
     const int etid = threadIdx.x - 64;
-    if (etid < 192) wf_s[etid] = p.w_f[etid];
+    if (etid < 192) wf_s[etid] = p.w_f[etid];             // constants: before the dependency resolves
     const uint32_t tm = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * 32;
     float ba[32], bb[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) { ba[c] = __ldg(p.b_a + half * 32 + c); bb[c] = __ldg(p.b_b + half * 32 + c); }
     const float bf = __ldg(p.b_f);
+    pdl_wait();
     const uint32_t sw = static_cast<uint32_t>(i & 7);
     const uint32_t row_off = static_cast<uint32_t>(i) * 128u;
     asm volatile("bar.sync 1, 256;" ::: "memory");        // wf_s visible
