@@ -191,6 +191,14 @@ impl TTSModel {
         pocket_tts::tts_model::split_into_best_sentences_with(text, |s| self.conditioner.count_tokens(s)) // tts_model.rs:604-684
     }
 
+    /// Frames per Mimi-decoder pass (1, 2 or 4; `ptts_engine_set_codec_group`).  The reference decodes every latent inside the
+    /// frame loop (tts_model.rs:1033-1047); the streaming decoder gives bit-identical PCM for a group, the PCM of a frame then
+    /// leaves the device with its group.  No counterpart in the reference; call with no iterator alive.
+    pub fn set_codec_group(&self, frames: usize) -> Result<()> {
+        let e = self.engine.lock().unwrap();
+        check(unsafe { ffi::ptts_engine_set_codec_group(e.0, frames as i32) })
+    }
+
     fn sync_params(&self) -> Result<()> {
         let e = self.engine.lock().unwrap();
         check(unsafe { ffi::ptts_engine_set_lsd_steps(e.0, self.lsd_decode_steps as i32) })
