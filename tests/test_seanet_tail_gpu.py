@@ -16,11 +16,11 @@ pytestmark = pytest.mark.gpu
 def _run(weights, fused: bool, group: int, n=5, frames=7, i16=False):
     os.environ["PTTS_SEANET_TAIL"] = "1" if fused else "0"
     try:
-        eng = Engine(weights, max_slots=8, kv_capacity=64, codec_group=group)
+        eng = Engine(weights, max_slots=max(8, n), kv_capacity=64, codec_group=group)
     finally:
         del os.environ["PTTS_SEANET_TAIL"]
     voice = eng.voice_from_prompt(synth.make_voice_prompt(9, seed=3))
-    specs = [StreamSpec(synth.make_tokens(5 + i, seed=40 + i), frames, 0, 1e30, noise=synth.make_noise(frames, seed=90 + i)) for i in range(n)]
+    specs = [StreamSpec(synth.make_tokens(5 + i % 7, seed=40 + i), frames, 0, 1e30, noise=synth.make_noise(frames, seed=90 + i)) for i in range(n)]
     slots = eng.open_streams([voice] * n, specs)
     tickets = [eng.step_begin(slots, ahead=f > 0, i16=i16) for f in range(1)]
     out = []
@@ -47,3 +47,15 @@ def test_fused_tail_bit_identical_to_separate_launches():
         got = _run(w, True, group)
         assert np.array_equal(got, ref), f"group {group}: max diff {np.abs(got - ref).max()}"
     assert np.array_equal(_run(w, True, 1, i16=True), _run(w, False, 1, i16=True))
+
+
+@pytest.mark.parametrize("n", [24, 64])
+def test_fused_tail_many_tiles_per_cta(n):
+    """16 tiles per stream and frame: 24 streams = 384 tiles, 64 streams = 1024 tiles on at most 132 persistent CTAs, so every CTA
+    walks several tiles (stage reuse, barrier phases, the accumulator hand-back) -- the batch-of-5 case above never does."""
+    w = synth.make_weights(1234)
+    ref = _run(w, False, 1, n=n, frames=3)
+    got = _run(w, True, 1, n=n, frames=3)
+    assert np.array_equal(got, ref), f"max diff {np.abs(got - ref).max()}"
+    if n == 24:
+        assert np.array_equal(_run(w, True, 4, n=n, frames=5), _run(w, False, 1, n=n, frames=5))
