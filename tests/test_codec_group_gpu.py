@@ -117,3 +117,22 @@ def test_group_device_steps_and_scheduler(weights):
     eng.close_streams(slots)
     assert np.array_equal(last, pcm)
     voice.close(); eng.close()
+
+
+def test_set_codec_group_rejects_bad_values_and_steps_in_flight(weights):
+    from pocket_tts_b200._lib import PttsError
+    eng = Engine(weights, max_slots=4, kv_capacity=64)
+    voice = eng.voice_from_prompt(synth.make_voice_prompt(9, seed=3))
+    with pytest.raises(PttsError):
+        eng.set_codec_group(3)
+    slots = eng.open_streams([voice], _specs(1, 4))
+    t = eng.step_begin(slots)
+    with pytest.raises(PttsError):          # a ticket with unfetched results: the codec scratch may not be re-sized now
+        eng.set_codec_group(2)
+    eng.step_flags(t)
+    eng.step_pcm(t)
+    eng.set_codec_group(2)                  # fine between steps, with the stream still open
+    p = eng.step(slots)[0]
+    assert np.isfinite(p).all()
+    eng.close_streams(slots)
+    voice.close(); eng.close()
