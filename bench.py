@@ -357,7 +357,7 @@ def run_gpu(args):
         fn, f = max(fns.items(), key=lambda kv: kv[1]["us"])
         nl = f["launches"]
         traffic, traffic_src = ncu_traffic()
-        if fn == "gemm_tc_kernel":
+        if fn in ("gemm_tc_kernel", "gemv_rows_kernel"):
             # the dominant kernel's time WITHOUT any event-pair correction: its four decode shapes replayed as graphs of
             # back-to-back launches over the real weights of all six layers (ptts_profile_gemm_replay), one event pair per
             # graph; pooled over the 24 FlowLM launches of a step (the remaining gemm_tc_kernel launches -- flow head glue
@@ -370,8 +370,8 @@ def run_gpu(args):
                                 "traffic": traffic.get(fn), "traffic_source": traffic_src, "peak_source": pk["src"],
                                 "us_per_launch": us, "algorithmic_bytes_per_launch": by, "launches_per_step": nl / n_prof,
                                 "share_of_step": f["us"] / tot, "per_shape": rp,
-                                "how": "the FlowLM decode GEMMs (in_proj, out_proj, linear1, linear2; 24 of the step's launches "
-                                       "of this kernel) replayed as captured graphs of 20 x 6 back-to-back launches over the "
+                                "how": "the FlowLM decode Linear layers (in_proj, out_proj, linear1, linear2; 24 of the step's launches "
+                                       "of this kernel; 1-4 rows run the small-batch GEMV of csrc/gemv.cuh, more the tcgen05 GEMM) replayed as captured graphs of 20 x 6 back-to-back launches over the "
                                        "real weights of every layer, CUDA events around each graph; achieved = algorithmic "
                                        "bytes (weights + operand rows + epilogue tensors) / mean launch time"}
         else:
@@ -422,6 +422,24 @@ def run_gpu(args):
             v = eng.voice_from_pcm(pcm)
             tv.append(1000 * (time.perf_counter() - t0))
             v.close()
+        # BASELINE configs[0] shape on the same engine: ONE utterance, 125 frames, device-resident steps -- the small-batch
+        # path (Linear layers on the GEMV of csrc/gemv.cuh); non-headline, reported beside the 64-stream value
+        one = [StreamSpec(synth.make_tokens(TOKENS, seed=5), FRAMES, 3, 1e30, temp=0.7, seed=1)]
+        us1 = []
+        for _ in range(4):
+            s = eng.open_streams([voice], one)
+            eng.step_device(s)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _f in range(FRAMES - 1):
+                eng.step_device(s)
+            e1.record(stream)
+            eng.sync()
+            us1.append(1000.0 * e0.elapsed_time(e1) / (FRAMES - 1))
+            eng.close_stream(int(s[0]))
+        line["single_stream"] = {"workload": "configs[0] shape: 1 utterance x 125 frames, device-resident decode steps",
+                                 "us_per_frame": statistics.median(us1[1:]),
+                                 "realtime_factor": FRAME_SEC * 1e6 / statistics.median(us1[1:])}
         line["ttfa_ms"] = {"p50_single_stream": statistics.median(ttfa[2:]), "batch64_first_frames": t64,
                            "voice_from_pcm_87_frames": statistics.median(tv[1:])}
         if not args.no_cpu_baseline:

@@ -6,7 +6,9 @@
  * probes; they may change between builds.
  *
  * ptts_engine_cfg.reserved[] test switches (all zero in production):
- *   [0] GEMM operand placement: 1 = never weights-on-M (swap-AB), 2 = always when legal
+ *   [0] GEMM operand placement: 1 = never weights-on-M (swap-AB), 2 = always when legal (either also keeps 1-4 row Linear
+ *       layers on the tensor-core path instead of the small-batch GEMV)
+ *   [1] 1 = never use the small-batch GEMV (csrc/gemv.cuh; Linear layers of 1-4 rows)
  *   [2] force a split-K factor for every non-persistent GEMM
  *   [3] 1 = never use the persistent GEMM kernel
  *   [4] shared-memory budget of a GEMM CTA in KB (default 200)
@@ -51,9 +53,13 @@ int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const flo
 /* The int8 weight path of the decode (swap-AB) GEMM: w is quantised per tensor with the reference's scheme
  * (crates/pocket-tts/src/quantize.rs:65-94: scale = absmax / 127, codes clamp(round(w / scale), -127, 127)),
  * D = (A . codes^T) * scale.  storage 1 streams one-byte codes from HBM and expands them in shared memory
- * (production), 0 streams an f16 copy of the same codes; both must give bit-identical D.  scale_out gets the scale. */
+ * (production), 0 streams an f16 copy of the same codes; both must give bit-identical D.  storage 2 = byte codes with the
+ * library's own choice of kernel (1-4 rows: the GEMV of csrc/gemv.cuh expanding the codes in registers).  scale_out gets
+ * the scale. */
 int32_t ptts_test_gemm_int8(int32_t device, const float* a, const float* w, float* d, int32_t rows, int32_t feats,
                             int32_t k, int32_t split_k, int32_t storage, float* scale_out);
+/* Launches of the small-batch GEMV (csrc/gemv.cuh) by this process so far: tests assert the family was actually selected. */
+int64_t ptts_test_gemv_launches(void);
 /* Bring-up probe: back-to-back launches of one GEMM with per-CTA %globaltimer stamps (10 per CTA, ns). */
 int32_t ptts_test_gemm_trace(int32_t device, int32_t rows, int32_t feats, int32_t k, int32_t mode, int32_t split_k,
                              int32_t iters, float* us_per_launch, int64_t* stamps, int32_t max_ctas, int32_t* n_ctas);

@@ -21,7 +21,7 @@ PRODUCT_SYMBOLS = [
 ]
 INTERNAL_SYMBOLS = [
     "ptts_debug_read", "ptts_launch_count", "ptts_step_timed", "ptts_cuda_stream", "ptts_profile_enable", "ptts_profile_report",
-    "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
+    "ptts_profile_overhead", "ptts_test_gemm", "ptts_test_gemm_int8", "ptts_test_gemv_launches", "ptts_test_gemm_trace", "ptts_test_conv1d", "ptts_test_convtr1d",
     "ptts_test_noise", "ptts_debug_f16_overflow", "ptts_profile_gemm_replay",
 ]
 SYMBOLS = PRODUCT_SYMBOLS + INTERNAL_SYMBOLS
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
     L.ptts_profile_overhead.argtypes = [vp, vp]
     L.ptts_test_gemm.argtypes = [i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32]
     L.ptts_test_gemm_int8.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.ptts_test_gemv_launches.argtypes = []
+    L.ptts_test_gemv_launches.restype = i64
     L.ptts_test_gemm_trace.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]
     L.ptts_test_conv1d.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]
     L.ptts_test_convtr1d.argtypes = [i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32]

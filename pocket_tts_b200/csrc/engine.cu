@@ -14,8 +14,10 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <atomic>
 #include "flow_head.cuh"
 #include "gemm.cuh"
+#include "gemv.cuh"
 #include "host_util.h"
 #include "../../include/ptts_internal.h"
 #include "kernels.cuh"
@@ -115,6 +117,7 @@ struct Engine {
   int gemm_ref_f = 1;          // > 1 while the GEMMs of a codec group of that many frames are issued (see Engine::gemm)
   int lin1_ctas = 64;          // linear1 (32 feature tiles): 64 lets it split in two and keep its K slice resident (PTTS_LIN1_CTAS)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
+  int num_sms = 148;          // grid of the small-batch GEMV (gemv.cuh); PTTS_GEMV_CTAS
   int lsd_steps = 1;
   // per-launch CUDA-event profiling (bench.py roofline pass; off in the timed region)
   struct ProfRec { const char* tag; const char* fn; cudaEvent_t a, b; double bytes, flops; };
@@ -127,6 +130,8 @@ struct Engine {
   struct LnSpec { bool set = false; const float* x; int rows, C; const float* w; const float* b; float eps; const float* shift;
                   const float* scale; int mod_ld; __half* out; int out_ld; const char* tag; };
   LnSpec next_ln;
+  void ln_pending(const LnSpec& lnreq);
+  bool gemv(const __half* x, int rows, const Weight16& w, int F, const GemmEpi& epi);
   void ln_after_next_gemm(const char* tag, const float* x, int rows, int C, const float* w, const float* b, float eps,
                           const float* shift, const float* scale, int mod_ld, __half* out, int out_ld) {
     next_ln = LnSpec{true, x, rows, C, w, b, eps, shift, scale, mod_ld, out, out_ld, tag};
@@ -787,6 +792,12 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     if (const char* v = std::getenv("PTTS_TRIG_A")) trig_a = std::atoi(v);
     if (const char* v = std::getenv("PTTS_TRIG_B")) trig_b = std::atoi(v);
   }
+  {
+    cudaDeviceProp prop{};
+    PTTS_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
+    num_sms = prop.multiProcessorCount;
+    if (const char* v = std::getenv("PTTS_GEMV_CTAS")) num_sms = std::max(1, std::atoi(v));
+  }
   ls = stream;
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_a_done, cudaEventDisableTiming));
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_front_done, cudaEventDisableTiming));
@@ -885,6 +896,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   if (rows <= 0) return;
   PTTS_REQUIRE(a.C % 64 == 0 && w.K == taps * a.C, PTTS_ERR_INVALID, "gemm: K mismatch (C %d taps %d, weight K %d)", a.C, taps, w.K);
   PTTS_REQUIRE(F <= w.Fpad, PTTS_ERR_INVALID, "gemm: F %d beyond weight rows %d", F, w.Fpad);
+  if (taps == 1 && n_streams == 1 && gemv(a.ptr, (int)rows, w, F, epi)) return;
   GemmParams p{};
   p.F = F; p.K = w.K; p.taps = taps; p.cblocks = a.C / 64;
   p.epi = epi;
@@ -1032,11 +1044,71 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
     }
     PTTS_CUDA(cudaGetLastError());
   }
-  if (lnreq.set) {
-    tag(lnreq.tag);
-    if (lnreq.C == 1024) ln<1024>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);
-    else ln<512>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);
+  ln_pending(lnreq);
+}
+
+void Engine::ln_pending(const LnSpec& lnreq) {
+  if (!lnreq.set) return;
+  tag(lnreq.tag);
+  if (lnreq.C == 1024) ln<1024>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);
+  else ln<512>(lnreq.x, lnreq.rows, lnreq.w, lnreq.b, lnreq.eps, lnreq.shift, lnreq.scale, lnreq.mod_ld, lnreq.out, lnreq.out_ld);
+}
+
+// Small-batch Linear (gemv.cuh): 1-4 rows, K a multiple of 256 (512 for one-byte codes).  Returns false when the shape or a
+// test switch (ptts_engine_cfg.reserved[0] != 0 forces an operand placement of the tensor-core path, reserved[1] = 1 or
+// PTTS_GEMV=0 turns the family off) leaves the call to the tensor-core GEMM.
+template <int ROWS, bool INT8>
+static void launch_gemv(bool pdl, cudaStream_t st, int kch, int grid, size_t smem, const GemvParams& q) {
+  switch (kch) {
+    case 1:  if constexpr (INT8) launch_k(pdl, gemv_rows_kernel<ROWS, 1, true>, grid, GEMV_THREADS, smem, st, 1, q); break;
+    case 2:  launch_k(pdl, gemv_rows_kernel<ROWS, 2, INT8>, grid, GEMV_THREADS, smem, st, 1, q); break;
+    case 4:  if constexpr (!INT8) launch_k(pdl, gemv_rows_kernel<ROWS, 4, false>, grid, GEMV_THREADS, smem, st, 1, q); break;
+    case 8:  if constexpr (INT8) launch_k(pdl, gemv_rows_kernel<ROWS, 8, true>, grid, GEMV_THREADS, smem, st, 1, q); break;
+    case 16: if constexpr (!INT8) launch_k(pdl, gemv_rows_kernel<ROWS, 16, false>, grid, GEMV_THREADS, smem, st, 1, q); break;
+    default: break;
   }
+}
+
+static std::atomic<long long> g_gemv_launches{0};
+bool Engine::gemv(const __half* x, int rows, const Weight16& w, int F, const GemmEpi& epi) {
+  static const bool env_off = std::getenv("PTTS_GEMV") && std::atoi(std::getenv("PTTS_GEMV")) == 0;
+  if (rows > GEMV_MAX_ROWS || cfg.debug_gemm || cfg.reserved[0] != 0 || cfg.reserved[1] == 1 || env_off) return false;
+  const bool int8 = w.q8.p && cfg.reserved[7] == 0;
+  const int per_chunk = int8 ? 512 : 256;   // K covered by one 16-byte chunk per lane
+  if (w.K % per_chunk) return false;
+  const int kch = w.K / per_chunk;
+  if (int8 ? !(kch == 1 || kch == 2 || kch == 8) : !(kch == 2 || kch == 4 || kch == 16)) return false;
+  PTTS_REQUIRE(F <= w.Fpad, PTTS_ERR_INVALID, "gemv: F %d beyond weight rows %d", F, w.Fpad);
+  const LnSpec lnreq = next_ln;
+  next_ln.set = false;
+  split_cap_override = 0;
+  ++g_gemv_launches;
+  GemvParams q{};
+  q.w = int8 ? (const void*)w.q8.p : (const void*)w.w.p;
+  q.x = x; q.F = F; q.K = w.K; q.rows = rows;
+  q.epi = epi;
+  q.epi.wscale = w.wscale.p;
+  const int R = rows == 1 ? 1 : rows == 2 ? 2 : 4;
+  const size_t smem = (size_t)R * w.K * 2;
+  double bytes = (double)F * w.K * (int8 ? 1 : 2) + (double)rows * w.K * 2;
+  bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + (epi.res ? 4 : 0) + (epi.gate ? 4 : 0));
+  {
+    ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K, "gemv_rows_kernel");
+    // one CTA per SM (two fit): the second slot is where the next launch's CTAs wait with their weights already requested
+    const int grid = num_sms;
+    if (int8) {
+      if (R == 1) launch_gemv<1, true>(use_pdl, ls, kch, grid, smem, q);
+      else if (R == 2) launch_gemv<2, true>(use_pdl, ls, kch, grid, smem, q);
+      else launch_gemv<4, true>(use_pdl, ls, kch, grid, smem, q);
+    } else {
+      if (R == 1) launch_gemv<1, false>(use_pdl, ls, kch, grid, smem, q);
+      else if (R == 2) launch_gemv<2, false>(use_pdl, ls, kch, grid, smem, q);
+      else launch_gemv<4, false>(use_pdl, ls, kch, grid, smem, q);
+    }
+    PTTS_CUDA(cudaGetLastError());
+  }
+  ln_pending(lnreq);
+  return true;
 }
 
 static GemmEpi epi_none() {
@@ -2923,13 +2995,16 @@ int32_t ptts_test_gemm(int32_t device, const float* a, const float* w, const flo
   PTTS_CATCH
 }
 
+int64_t ptts_test_gemv_launches(void) { return g_gemv_launches.load(); }
+
 int32_t ptts_test_gemm_int8(int32_t device, const float* a, const float* w, float* d, int32_t rows, int32_t feats,
                             int32_t k, int32_t split_k, int32_t storage, float* scale_out) {
   PTTS_TRY
   PTTS_REQUIRE(a && w && d && rows > 0 && rows <= 256 && feats > 0 && k > 0 && k % 64 == 0, PTTS_ERR_INVALID, "bad test_gemm_int8 arguments");
   TestCtx t(device, 0);
   Engine& e = t.e;
-  e.cfg.reserved[0] = 2;                 // weights on MMA-M: the only placement with in-kernel int8 expansion
+  e.cfg.reserved[0] = storage == 2 ? 0 : 2;   // weights on MMA-M: the only tensor-core placement with in-kernel int8 expansion;
+                                              // storage 2 = byte codes with the library's own choice (1-4 rows: the GEMV of gemv.cuh)
   e.cfg.reserved[7] = storage ? 0 : 1;
   DevBuf<__half> a16;
   to_f16_dev(a16, a, (size_t)rows * k);

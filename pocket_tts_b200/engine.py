@@ -50,7 +50,8 @@ class Voice:
 class Engine:
     def __init__(self, weights: dict[str, np.ndarray], device: int = 0, max_slots: int = 64, max_batch: int | None = None,
                  kv_capacity: int = 1024, debug_gemm: int = 0, gemm_mode: int = 0, cuda_graph: bool = True, int8_weights: bool = False,
-                 int8_storage: bool = True, lm_step_kernel: bool | None = None, codec_group: int | None = None):
+                 int8_storage: bool = True, lm_step_kernel: bool | None = None, codec_group: int | None = None,
+                 gemv_off: bool = False):
         L = _lib.lib()
         self._keep = []
         descs = (TensorDesc * len(weights))()
@@ -68,6 +69,7 @@ class Engine:
         cfg.max_batch = max_batch or max_slots
         cfg.kv_capacity, cfg.weight_mode, cfg.use_cuda_graph, cfg.debug_gemm = kv_capacity, int(int8_weights), int(cuda_graph), debug_gemm
         cfg.reserved[0] = gemm_mode
+        cfg.reserved[1] = 1 if gemv_off else 0      # test hook: Linear layers of 1-4 rows on the tensor-core path instead of csrc/gemv.cuh
         cfg.reserved[7] = 0 if int8_storage else 1  # test hook: int8 mode streaming f16 copies of the codes instead of bytes
         # the persistent FlowLM step kernel (csrc/lm_step.cuh): None = the library's default, True / False = force
         cfg.reserved[8] = 0 if lm_step_kernel is None else (2 if lm_step_kernel else 1)
@@ -347,6 +349,11 @@ def test_gemm_int8(a, w, split_k=1, storage=1, device=0):
     check(_lib.lib().ptts_test_gemm_int8(device, _ptr(a), _ptr(w), _ptr(d), a.shape[0], w.shape[0], a.shape[1], split_k,
                                          storage, C.byref(scale)))
     return d, float(scale.value)
+
+
+def gemv_launches() -> int:
+    """Launches of the small-batch GEMV (csrc/gemv.cuh) by this process so far."""
+    return int(_lib.lib().ptts_test_gemv_launches())
 
 
 def test_conv1d(x, prev, w, bias, device=0):

@@ -1,0 +1,121 @@
+"""Small-batch Linear (csrc/gemv.cuh): 1-4 activation rows, the shapes of a single-utterance decode step (BASELINE
+configs[0]; reference Linear sites modules/attention.rs:129,280, models/transformer.rs:85, modules/mlp.rs:322-368), through
+the C ABI against a float64 product of the same f16-rounded operands, against the tensor-core GEMM on the same inputs, and
+with one-byte weight codes (reference quantize.rs:65-94).  Every test asserts that the GEMV family was really selected."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def f16r(a):
+    return np.asarray(a, np.float32).astype(np.float16).astype(np.float32)
+
+
+def ref(a, w, bias=None, act=0):
+    d = torch.from_numpy(f16r(a)).double() @ torch.from_numpy(f16r(w)).double().T
+    if bias is not None:
+        d = d + torch.from_numpy(np.asarray(bias, np.float32)).double()
+    if act == 1:
+        d = torch.nn.functional.gelu(d, approximate="tanh")
+    elif act == 2:
+        d = torch.nn.functional.silu(d)
+    return d.float().numpy()
+
+
+# rows, feats, k, act: every (row bucket, chunks-per-lane) instantiation; feature counts that leave warps without work, need
+# a second batch per warp (10240 = flow adaLN), or are not a multiple of anything (1000, 72)
+CASES = [
+    (1, 3072, 1024, 0), (1, 1024, 1024, 0), (1, 4096, 1024, 1), (1, 1024, 4096, 0), (1, 10240, 512, 0), (1, 512, 1024, 2),
+    (2, 3072, 1024, 0), (2, 1024, 4096, 0), (2, 10240, 512, 0), (2, 1000, 1024, 1),
+    (3, 4096, 1024, 1), (3, 1024, 4096, 0), (3, 512, 512, 2),
+    (4, 3072, 1024, 0), (4, 1024, 4096, 0), (4, 10240, 512, 0), (4, 72, 512, 0), (4, 32, 512, 0),
+]
+
+
+@pytest.mark.parametrize("rows,feats,k,act", CASES)
+def test_gemv_matches_reference_and_tensor_core_path(rows, feats, k, act):
+    from pocket_tts_b200.engine import test_gemm as run, gemv_launches
+    rng = np.random.default_rng(rows * 131 + feats + k)
+    a = rng.standard_normal((rows, k), dtype=np.float32)
+    w = rng.standard_normal((feats, k), dtype=np.float32) / np.sqrt(k)
+    bias = rng.standard_normal(feats, dtype=np.float32)
+    before = gemv_launches()
+    got = run(a, w, bias, mode=0, act=act)
+    assert gemv_launches() == before + 1, "the small-batch GEMV was not selected"
+    tc = run(a, w, bias, mode=2, act=act)          # the same product on tcgen05 (weights on MMA-M)
+    assert gemv_launches() == before + 1
+    want = ref(a, w, bias, act)
+    assert np.abs(got - want).max() < 2e-3
+    assert np.abs(got - tc).max() < 1e-4           # f32 accumulation on both sides: only the order differs
+
+
+@pytest.mark.parametrize("rows,feats,k", [(1, 3072, 1024), (1, 1024, 4096), (1, 10240, 512), (2, 4096, 1024), (3, 1024, 4096),
+                                          (4, 3072, 1024), (4, 1024, 4096), (4, 512, 512), (2, 1000, 1024)])
+def test_gemv_int8_codes(rows, feats, k):
+    """Byte codes expanded in registers == the tensor-core path streaming the same codes (both exact products of f16 x
+    integer, f32 accumulate) up to summation order, and == A . (codes * scale)^T of the reference's per-tensor scheme."""
+    from pocket_tts_b200.engine import test_gemm_int8 as run, gemv_launches
+    rng = np.random.default_rng(rows + feats + k)
+    a = rng.standard_normal((rows, k), dtype=np.float32)
+    w = (rng.standard_normal((feats, k), dtype=np.float32) / np.sqrt(k)).astype(np.float32)
+    w[0, :8] = [w.max(), -np.abs(w).max(), 0.0, 1e-9, -1e-9, w.min(), 0.5 * w.max(), -0.5 * w.max()]
+    before = gemv_launches()
+    got, scale = run(a, w, storage=2)
+    assert gemv_launches() == before + 1, "the small-batch GEMV was not selected"
+    tc, scale2 = run(a, w, storage=1)
+    assert scale == scale2
+    codes = np.clip(np.rint(w / np.float32(scale)), -127, 127)
+    want = (torch.from_numpy(f16r(a)).double() @ torch.from_numpy(codes).double().T * scale).float().numpy()
+    assert np.abs(got - want).max() < 2e-3
+    assert np.abs(got - tc).max() < 1e-4
+
+
+def test_gemv_not_selected_beyond_four_rows():
+    from pocket_tts_b200.engine import test_gemm as run, gemv_launches
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((5, 1024), dtype=np.float32)
+    w = rng.standard_normal((256, 1024), dtype=np.float32) / 32
+    before = gemv_launches()
+    got = run(a, w, None)
+    assert gemv_launches() == before
+    assert np.abs(got - ref(a, w)).max() < 2e-3
+
+
+@pytest.mark.parametrize("n,int8", [(1, False), (3, False), (2, True)])
+def test_small_batch_step_runs_on_gemv_and_matches_the_tensor_core_step(n, int8):
+    """1-3 utterances through the engine with the GEMV family on (default) and off (ptts_engine_cfg.reserved[1] = 1):
+    teacher-forced latents, EOS logits and PCM of both agree to accumulation-order noise."""
+    from pocket_tts_b200 import synth
+    from pocket_tts_b200.engine import Engine, StreamSpec, gemv_launches
+    weights = synth.make_weights(3)
+    voice_rows = synth.make_voice_prompt(12, seed=4)
+    frames = 6
+    rng = np.random.default_rng(9)
+    noise = (rng.standard_normal((n, frames, 32)) * np.sqrt(0.7)).astype(np.float32)
+    feed = (rng.standard_normal((n, frames, 32)) * 0.5).astype(np.float32)
+    tokens = [np.arange(5 + i, 17 + 2 * i, dtype=np.int32) for i in range(n)]
+    outs = []
+    for off in (False, True):
+        eng = Engine(weights, max_slots=4, kv_capacity=256, gemv_off=off, int8_weights=int8)
+        voice = eng.voice_from_prompt(voice_rows)
+        slots = eng.open_streams([voice] * n, [StreamSpec(tokens[i], frames, 0, 1e30, noise=noise[i]) for i in range(n)])
+        before = gemv_launches()
+        lat, pcm, logit = [], [], []
+        for f in range(frames):
+            if f > 0:
+                for i in range(n):
+                    eng.set_feedback(int(slots[i]), feed[i, f - 1])
+            p, fin, l, lg = eng.step(slots)
+            lat.append(l.copy()); pcm.append(p.copy()); logit.append(lg.copy())
+        used = gemv_launches() - before
+        assert (used > 0) == (not off), f"GEMV launches {used} with the family {'off' if off else 'on'}"
+        outs.append((np.stack(lat), np.stack(pcm), np.stack(logit)))
+        eng.close_streams(slots)
+        voice.close()
+        eng.close()
+    (l0, p0, g0), (l1, p1, g1) = outs
+    assert np.abs(l0 - l1).max() < 1e-2   # f16 roundings of the activations flip on accumulation-order noise; the parity bar itself
+    assert np.abs(g0 - g1).max() < 1e-2
+    assert np.abs(p0 - p1).max() < 1e-2

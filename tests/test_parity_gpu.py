@@ -554,16 +554,30 @@ def test_int8_weight_mode_matches_reference_quantisation():
     eng.close()
     assert np.abs(np.stack(lat) - ref["latents"]).max() <= LAT_TOL
     assert snr(ref["pcm"], np.stack(pcm)) >= SNR_MIN
-    # one-byte storage (production) vs f16 copies of the same codes: the whole path must be bit-identical
-    eng2 = Engine(wnp, max_slots=2, kv_capacity=128, int8_weights=True, int8_storage=False)
-    voice2 = eng2.voice_from_prompt(prompt)
-    s2 = eng2.open_streams([voice2], [StreamSpec(tok, frames, 0, 1e30, noise=noise)])
-    for f in range(frames):
-        if f:
-            eng2.set_feedback(int(s2[0]), ref["latents"][f - 1])
-        p, _, l, _ = eng2.step(s2)
-        np.testing.assert_array_equal(l[0], lat[f])
-        np.testing.assert_array_equal(p[0], pcm[f])
+    # one-byte storage (production) vs f16 copies of the same codes: the whole path must be bit-identical.  One utterance runs
+    # its Linear layers on the small-batch GEMV (csrc/gemv.cuh), whose byte and f16 variants deal k to the lanes differently
+    # (16 vs 8 codes per chunk: same exact products, another summation order), so bit-identity is asserted on the
+    # tensor-core path (gemv_off) and the GEMV run above is held to the oracle like everything else.
+    runs = []
+    for storage in (True, False):
+        eng2 = Engine(wnp, max_slots=2, kv_capacity=128, int8_weights=True, int8_storage=storage, gemv_off=True)
+        voice2 = eng2.voice_from_prompt(prompt)
+        s2 = eng2.open_streams([voice2], [StreamSpec(tok, frames, 0, 1e30, noise=noise)])
+        out = []
+        for f in range(frames):
+            if f:
+                eng2.set_feedback(int(s2[0]), ref["latents"][f - 1])
+            p, _, l, _ = eng2.step(s2)
+            out.append((l[0].copy(), p[0].copy()))
+        runs.append(out)
+        if storage:
+            eng2.close_stream(int(s2[0]))
+            voice2.close()
+            eng2.close()
+    for (l_a, p_a), (l_b, p_b) in zip(*runs):
+        np.testing.assert_array_equal(l_a, l_b)
+        np.testing.assert_array_equal(p_a, p_b)
+    assert np.abs(np.stack([l for l, _ in runs[0]]) - np.stack(lat)).max() < 1e-2   # GEMV vs tensor-core int8 step
     eng2.close_stream(int(s2[0]))
     voice2.close()
     eng2.close()
