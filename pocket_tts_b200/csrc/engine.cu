@@ -114,6 +114,10 @@ struct Engine {
   int split_cta_cap = 48;   // a split-K decode (swap-AB) GEMM never spans more CTAs than this (PTTS_MAX_CTAS)
   int split_cta_cap_b = 48; // the same for the activation-as-M GEMMs of the codec half (PTTS_MAX_CTAS_B)
   int split_cap_override = 0;  // one-shot cap for the next GEMM
+  int bn_override = 0;         // one-shot feature-tile width for the next (activation-as-M, non-persistent) GEMM
+  struct Tune { int bn = 0, cap = 0; };   // per-call-site (bn, split cap) of the codec GEMMs: PTTS_TUNE_<SITE>=bn,cap
+  Tune tune_conv0, tune_ct2, tune_mlin1, tune_mlin2, tune_minproj, tune_moutproj, tune_ct5;
+  void apply(const Tune& t) { if (t.bn > 0) bn_override = t.bn; if (t.cap > 0) split_cap_override = t.cap; }
   int gemm_ref_f = 1;          // > 1 while the GEMMs of a codec group of that many frames are issued (see Engine::gemm)
   int lin1_ctas = 64;          // linear1 (32 feature tiles): 64 lets it split in two and keep its K slice resident (PTTS_LIN1_CTAS)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
@@ -131,7 +135,12 @@ struct Engine {
                   const float* scale; int mod_ld; __half* out; int out_ld; const char* tag; };
   LnSpec next_ln;
   void ln_pending(const LnSpec& lnreq);
-  bool gemv(const __half* x, int rows, const Weight16& w, int F, const GemmEpi& epi);
+  // LayerNorm in FRONT of the next Linear: folded into the small-batch GEMV's prologue (gemv.cuh) when that kernel takes
+  // the call, else launched on its own first.  Only set where ln_fusable() said yes.
+  LnSpec pre_ln;
+  bool gemv_ln = true;   // PTTS_GEMV_LN=0: LayerNorm launches kept
+  bool ln_fusable(int rows, const Weight16& w) const;
+  bool gemv(const __half* x, int rows, const Weight16& w, int F, const GemmEpi& epi, const LnSpec& pre);
   void ln_after_next_gemm(const char* tag, const float* x, int rows, int C, const float* w, const float* b, float eps,
                           const float* shift, const float* scale, int mod_ld, __half* out, int out_ld) {
     next_ln = LnSpec{true, x, rows, C, w, b, eps, shift, scale, mod_ld, out, out_ld, tag};
@@ -791,12 +800,17 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     if (const char* v = std::getenv("PTTS_LIN1_CTAS")) lin1_ctas = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_TRIG_A")) trig_a = std::atoi(v);
     if (const char* v = std::getenv("PTTS_TRIG_B")) trig_b = std::atoi(v);
+    auto tune = [](const char* name, Tune& t) { if (const char* v = std::getenv(name)) std::sscanf(v, "%d,%d", &t.bn, &t.cap); };
+    tune("PTTS_TUNE_CONV0", tune_conv0); tune("PTTS_TUNE_CT2", tune_ct2); tune("PTTS_TUNE_CT5", tune_ct5);
+    tune("PTTS_TUNE_MLIN1", tune_mlin1); tune("PTTS_TUNE_MLIN2", tune_mlin2);
+    tune("PTTS_TUNE_MINPROJ", tune_minproj); tune("PTTS_TUNE_MOUTPROJ", tune_moutproj);
   }
   {
     cudaDeviceProp prop{};
     PTTS_CUDA(cudaGetDeviceProperties(&prop, cfg.device));
     num_sms = prop.multiProcessorCount;
     if (const char* v = std::getenv("PTTS_GEMV_CTAS")) num_sms = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_GEMV_LN")) gemv_ln = std::atoi(v) != 0;
   }
   ls = stream;
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_a_done, cudaEventDisableTiming));
@@ -896,7 +910,16 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   if (rows <= 0) return;
   PTTS_REQUIRE(a.C % 64 == 0 && w.K == taps * a.C, PTTS_ERR_INVALID, "gemm: K mismatch (C %d taps %d, weight K %d)", a.C, taps, w.K);
   PTTS_REQUIRE(F <= w.Fpad, PTTS_ERR_INVALID, "gemm: F %d beyond weight rows %d", F, w.Fpad);
-  if (taps == 1 && n_streams == 1 && gemv(a.ptr, (int)rows, w, F, epi)) return;
+  {
+    const LnSpec pre = pre_ln;
+    pre_ln.set = false;
+    if (taps == 1 && n_streams == 1 && gemv(a.ptr, (int)rows, w, F, epi, pre)) return;
+    if (pre.set) {     // not taken by the GEMV: the operand is materialised by the LayerNorm kernel
+      const char* t = cur_tag;
+      ln_pending(pre);
+      cur_tag = t;
+    }
+  }
   GemmParams p{};
   p.F = F; p.K = w.K; p.taps = taps; p.cblocks = a.C / 64;
   p.epi = epi;
@@ -909,6 +932,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   // tile geometry of a GEMM over `rows_g` rows (n_streams x T_g, tiles of G_g streams x R_g rows): operand placement,
   // persistent or one CTA per tile, feature-tile width, grid
   struct Geo { bool swap, persistent; int R, G, bn, act_tiles; dim3 grid; };
+  const int bn_ov = bn_override;
   auto geometry = [&](long long rows_g, int T_g, int R_g, int G_g) {
     Geo g{};
     g.swap = plain && rows_g <= 256 && force != 1;
@@ -932,6 +956,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
       // largest tile that still leaves at least ~half the SMs busy: one wave of fat tiles beats two of thin ones
       int bn = std::min(256, fcap);
       while (bn > 64 && (long long)g.act_tiles * ((F + bn - 1) / bn) < 74) bn >>= 1;
+      if (bn_ov > 0) bn = std::min(bn_ov, std::min(256, fcap));
       g.bn = std::min(round_up(bn, 16), fcap);
     }
     g.grid = dim3(g.act_tiles, (F + g.bn - 1) / g.bn, 1);
@@ -944,6 +969,7 @@ void Engine::gemm(const ActView& a, int n_streams, int T, int taps, int R, int G
   (void)allow_split;
   int cap_override = split_cap_override;
   split_cap_override = 0;
+  bn_override = 0;
   auto split_of = [&](const Geo& g) {
     int sp = 1;
     const int tiles = g.grid.x * g.grid.y;
@@ -1070,27 +1096,42 @@ static void launch_gemv(bool pdl, cudaStream_t st, int kch, int grid, size_t sme
 }
 
 static std::atomic<long long> g_gemv_launches{0};
-bool Engine::gemv(const __half* x, int rows, const Weight16& w, int F, const GemmEpi& epi) {
-  static const bool env_off = std::getenv("PTTS_GEMV") && std::atoi(std::getenv("PTTS_GEMV")) == 0;
-  if (rows > GEMV_MAX_ROWS || cfg.debug_gemm || cfg.reserved[0] != 0 || cfg.reserved[1] == 1 || env_off) return false;
-  const bool int8 = w.q8.p && cfg.reserved[7] == 0;
+static bool gemv_shape_ok(int K, bool int8) {
   const int per_chunk = int8 ? 512 : 256;   // K covered by one 16-byte chunk per lane
-  if (w.K % per_chunk) return false;
-  const int kch = w.K / per_chunk;
-  if (int8 ? !(kch == 1 || kch == 2 || kch == 8) : !(kch == 2 || kch == 4 || kch == 16)) return false;
+  if (K % per_chunk) return false;
+  const int kch = K / per_chunk;
+  return int8 ? (kch == 1 || kch == 2 || kch == 8) : (kch == 2 || kch == 4 || kch == 16);
+}
+static bool gemv_env_off() {
+  static const bool off = std::getenv("PTTS_GEMV") && std::atoi(std::getenv("PTTS_GEMV")) == 0;
+  return off;
+}
+bool Engine::ln_fusable(int rows, const Weight16& w) const {
+  return gemv_ln && rows <= GEMV_MAX_ROWS && !cfg.debug_gemm && cfg.reserved[0] == 0 && cfg.reserved[1] == 0 && !gemv_env_off() &&
+         w.K == 1024 && gemv_shape_ok(w.K, w.q8.p && cfg.reserved[7] == 0);
+}
+
+bool Engine::gemv(const __half* x, int rows, const Weight16& w, int F, const GemmEpi& epi, const LnSpec& pre) {
+  if (rows > GEMV_MAX_ROWS || cfg.debug_gemm || cfg.reserved[0] != 0 || cfg.reserved[1] == 1 || gemv_env_off()) return false;
+  const bool int8 = w.q8.p && cfg.reserved[7] == 0;
+  if (!gemv_shape_ok(w.K, int8)) return false;
+  const int kch = w.K / (int8 ? 512 : 256);
+  if (pre.set && !(w.K == 1024 && pre.C == 1024 && pre.rows == rows && pre.out == x && !pre.scale && !pre.shift && pre.w)) return false;
   PTTS_REQUIRE(F <= w.Fpad, PTTS_ERR_INVALID, "gemv: F %d beyond weight rows %d", F, w.Fpad);
   const LnSpec lnreq = next_ln;
   next_ln.set = false;
   split_cap_override = 0;
+  bn_override = 0;
   ++g_gemv_launches;
   GemvParams q{};
   q.w = int8 ? (const void*)w.q8.p : (const void*)w.w.p;
   q.x = x; q.F = F; q.K = w.K; q.rows = rows;
   q.epi = epi;
   q.epi.wscale = w.wscale.p;
+  if (pre.set) { q.ln_x = pre.x; q.ln_w = pre.w; q.ln_b = pre.b; q.ln_eps = pre.eps; }
   const int R = rows == 1 ? 1 : rows == 2 ? 2 : 4;
-  const size_t smem = (size_t)R * w.K * 2;
-  double bytes = (double)F * w.K * (int8 ? 1 : 2) + (double)rows * w.K * 2;
+  const size_t smem = (size_t)R * w.K * 2 + (pre.set ? 2 * 1024 * sizeof(float) : 0);
+  double bytes = (double)F * w.K * (int8 ? 1 : 2) + (double)rows * w.K * (pre.set ? 4 : 2) + (pre.set ? 8.0 * w.K : 0.0);
   bytes += (double)rows * F * ((epi.out32 ? 4 : 0) + (epi.out16 ? 2 : 0) + (epi.res ? 4 : 0) + (epi.gate ? 4 : 0));
   {
     ProfScope ps(*this, take_tag("gemm"), bytes, 2.0 * rows * F * w.K, "gemv_rows_kernel");
@@ -1141,17 +1182,22 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
     // x += attn W_o^T, accumulated straight into the f32 residual stream by the (cluster split-K) epilogue; h = LN2(x)
     e = epi_none();
     e.out32 = x; e.out32_map = plain_map(D_MODEL); e.res = x; e.res_map = plain_map(D_MODEL);
-    ln_after_next_gemm("flowlm.layernorm", x, rows, D_MODEL, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
+    // 1-4 rows: LN2 / the next layer's LN1 run inside the prologue of the GEMV that consumes them (no launch, h never written)
+    const bool fuse2 = ln_fusable(rows, w_lin1[l]);
+    if (!fuse2) ln_after_next_gemm("flowlm.layernorm", x, rows, D_MODEL, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     tag(is_prefill ? "prefill.out_proj" : "flowlm.out_proj"); gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = ffn; e.out16_map = plain_map(D_FFN);
     if (!is_prefill) split_cap_override = lin1_ctas;
+    if (fuse2) pre_ln = LnSpec{true, x, rows, D_MODEL, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL, "flowlm.layernorm"};
     tag(is_prefill ? "prefill.linear1" : "flowlm.linear1"); gemm_rows(h, rows, D_MODEL, w_lin1[l], D_FFN, e);
     e = epi_none();
     e.out32 = x; e.out32_map = plain_map(D_MODEL); e.res = x; e.res_map = plain_map(D_MODEL);
-    if (l + 1 < N_LAYERS)
+    const bool fuse1 = l + 1 < N_LAYERS && ln_fusable(rows, w_inproj[l + 1]);
+    if (l + 1 < N_LAYERS && !fuse1)
       ln_after_next_gemm("flowlm.layernorm", x, rows, D_MODEL, ln1_w[l + 1].p, ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
     tag(is_prefill ? "prefill.linear2" : "flowlm.linear2"); gemm_rows(ffn, rows, D_FFN, w_lin2[l], D_MODEL, e, true);
+    if (fuse1) pre_ln = LnSpec{true, x, rows, D_MODEL, ln1_w[l + 1].p, ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL, "flowlm.layernorm"};
   }
 }
 
@@ -1432,15 +1478,18 @@ void Engine::step_part_b(int n, int f, bool marks) {
   for (int l = 0; l < MIMI_LAYERS; ++l) {
     e = epi_none();
     e.out32 = mqkv32.p; e.out32_map = plain_map(3 * MIMI_DIM);
+    apply(tune_minproj);
     tag("mimi.in_proj"); gemm_rows(mh16.p, MR, MIMI_DIM, m_inproj[l], 3 * MIMI_DIM, e);
     { ProfScope ps(*this, "mimi.attn", (double)n * f * (16.0 * 1536 * 4 + 8.0 * 266 * 256 + 8.0 * 16 * 256 + 16.0 * 512 * 2), 0, "mimi_attn_kernel");
       launch_k(use_pdl, mimi_attn_kernel, dim3(n, MIMI_HEADS), MATTN_THREADS, MATTN_SMEM, ls, 1, mqkv32.p, row_seq.p, mimi_pos.p, mimi_ring.p, l, MIMI_LAYERS, mattn16.p, f); }
     e = epi_none();
     e.fscale = m_ls1[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
     ln_after_next_gemm("mimi.layernorm", mx32.p, MR, MIMI_DIM, m_ln2_w[l].p, m_ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
+    apply(tune_moutproj);
     tag("mimi.out_proj"); gemm_rows(mattn16.p, MR, MIMI_DIM, m_outproj[l], MIMI_DIM, e, true);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = mffn16.p; e.out16_map = plain_map(MIMI_FFN);
+    apply(tune_mlin1);
     tag("mimi.linear1"); gemm_rows(mh16.p, MR, MIMI_DIM, m_lin1[l], MIMI_FFN, e);
     e = epi_none();
     e.fscale = m_ls2[l].p; e.res = mx32.p; e.res_map = plain_map(MIMI_DIM); e.out32 = mx32.p; e.out32_map = plain_map(MIMI_DIM);
@@ -1450,6 +1499,7 @@ void Engine::step_part_b(int n, int f, bool marks) {
     }
     if (!last)
       ln_after_next_gemm("mimi.layernorm", mx32.p, MR, MIMI_DIM, m_ln1_w[l + 1].p, m_ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, mh16.p, MIMI_DIM);
+    apply(tune_mlin2);
     tag("mimi.linear2"); gemm_rows(mffn16.p, MR, MIMI_FFN, m_lin2[l], MIMI_DIM, e, !last);
   }
   if (marks) PTTS_CUDA(cudaEventRecord(ev[3], ls));
@@ -1459,9 +1509,11 @@ void Engine::step_part_b(int n, int f, bool marks) {
   { ProfScope ps(*this, "seanet.state_move", (double)n * 5824 * 4, 0);
     launch_k(use_pdl, conv_state_move_kernel, dim3(n, 8), 128, 0, ls, 1, sg, row_seq.p, 0); }
   e = epi_none(); e.bias = sb_conv0.p; e.out16 = a0.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T1, 512, (long long)(1 + T1) * 512, 512);
+  apply(tune_conv0);
   tag("seanet.conv0"); gemm(ActView{tr16.p, 512, 6 + T1, NB}, n, T1, 7, R1, G1, s_conv0, 512, e);
   e = epi_none(); e.bias = sb_ct2.p; e.out32 = x2.p; e.out32_map = stream_map(T1, 1536, (long long)T2 * 256, 0);
   e.out16 = e2.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T1, 1536, (long long)(2 + T2) * 256, 2 * 256);
+  apply(tune_ct2);
   tag("seanet.convtr2"); gemm(ActView{a0.p, 512, 1 + T1, NB}, n, T1, 2, R1, G1, s_ct2, 1536, e);
   e = epi_none(); e.bias = sb_r3a.p; e.out16 = h3.p; e.act16 = ACT_ELU; e.out16_map = plain_map(128);
   tag("seanet.res3a"); gemm(ActView{e2.p, 256, 2 + T2, NB}, n, T2, 3, 96, 1, s_r3a, 128, e);
@@ -1473,6 +1525,7 @@ void Engine::step_part_b(int n, int f, bool marks) {
   tag("seanet.res3b"); gemm(ActView{h3.p, 128, T2, NB}, n, T2, 1, 96, 1, s_r3b, 256, e);
   e = epi_none(); e.bias = sb_ct5.p; e.out32 = x5.p; e.out32_map = stream_map(T2, 640, (long long)T3 * 128, 0);
   e.out16 = e5.p; e.act16 = ACT_ELU; e.out16_map = stream_map(T2, 640, (long long)(2 + T3) * 128, 2 * 128);
+  apply(tune_ct5);
   tag("seanet.convtr5"); gemm(ActView{a3.p, 256, 1 + T2, NB}, n, T2, 2, 96, 1, s_ct5, 640, e);
   e = epi_none(); e.bias = sb_r6a.p; e.out16 = h6.p; e.act16 = ACT_ELU; e.out16_map = plain_map(64);
   tag("seanet.res6a"); gemm(ActView{e5.p, 128, 2 + T3, NB}, n, T3, 3, 120, 1, s_r6a, 64, e);

@@ -25,9 +25,15 @@ namespace ptts {
 
 struct GemvParams {
   const void* w;     // f16 [Fpad][K] K-major, or int8 codes [Fpad][K]
-  const __half* x;   // [rows][K] f16
+  const __half* x;   // [rows][K] f16 (unused when ln_x is set)
   int F, K, rows;
   GemmEpi epi;
+  // fused LayerNorm prologue (K = 1024 only): the operand is LN(ln_x) * ln_w + ln_b, computed per CTA exactly as
+  // ln_rows_kernel does (one warp per row, two-pass, biased variance, eps inside the sqrt) and rounded to f16 once
+  const float* ln_x;   // [rows][K] f32 residual stream, or null
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
 };
 
 static constexpr int GEMV_THREADS = 256;
@@ -113,8 +119,65 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_rows_kernel(const GemvPa
     }
   };
   load_batch(0);        // independent of the previous kernel: in flight across the dependency
+  constexpr bool LN_OK = (INT8 ? KCH * 512 : KCH * 256) == 1024;
+  const bool fused_ln = LN_OK && p.ln_x != nullptr;
+  float* lnw_s = reinterpret_cast<float*>(gemv_smem + ROWS * 1024 * 2);
+  float* lnb_s = lnw_s + 1024;
+  if (LN_OK && fused_ln) {   // the affine parameters are constants too
+    for (int i = threadIdx.x; i < 1024 / 4; i += GEMV_THREADS) {
+      reinterpret_cast<float4*>(lnw_s)[i] = __ldg(reinterpret_cast<const float4*>(p.ln_w) + i);
+      reinterpret_cast<float4*>(lnb_s)[i] = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i);
+    }
+    __syncthreads();
+  }
   pdl_wait();
 
+  if (LN_OK && fused_ln) {
+    if (warp < ROWS) {
+      constexpr int C = 1024, PER = C / 32;
+      const int r = warp;
+      float v[PER];
+      if (r < p.rows) {
+        const float4* xr = reinterpret_cast<const float4*>(p.ln_x + static_cast<long long>(r) * C);
+#pragma unroll
+        for (int i = 0; i < PER / 4; ++i) {
+          const float4 t = __ldcg(xr + i * 32 + lane);
+          v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) v[i] = 0.f;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) sum += v[i];
+      const float mean = warp_sum(sum) * (1.f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; q += d * d; }
+      const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / C) + p.ln_eps);
+#pragma unroll
+      for (int i = 0; i < PER / 4; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 w4 = *reinterpret_cast<const float4*>(lnw_s + c), b4 = *reinterpret_cast<const float4*>(lnb_s + c);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float y = (v[4 * i + j] - mean) * rstd;
+          y = y * wv[j] + bv[j];
+          o[j] = r < p.rows ? y : 0.f;
+        }
+        const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+        const int g = c >> 3;
+        const int dst = INT8 ? r * K * 2 + (g & 1) * K + (g >> 1) * 16 + (c & 7) * 2 : r * K * 2 + c * 2;
+        *reinterpret_cast<uint2*>(gemv_smem + dst) = pk;
+      }
+    }
+  } else
   // activation rows -> shared memory.  f16 weights: the row as it is.  int8: a lane's 16 codes need 16 halves of x, kept as
   // two 16-byte planes per row (even / odd 8-element groups) so that both reads of a warp are conflict-free runs.
   {

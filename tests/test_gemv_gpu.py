@@ -119,3 +119,35 @@ def test_small_batch_step_runs_on_gemv_and_matches_the_tensor_core_step(n, int8)
     assert np.abs(l0 - l1).max() < 1e-2   # f16 roundings of the activations flip on accumulation-order noise; the parity bar itself
     assert np.abs(g0 - g1).max() < 1e-2
     assert np.abs(p0 - p1).max() < 1e-2
+
+
+@pytest.mark.parametrize("n,int8", [(1, False), (4, False), (2, True)])
+def test_fused_layernorm_prologue_is_bit_identical_to_the_layernorm_launches(n, int8, monkeypatch):
+    """The LayerNorm in front of in_proj / linear1 runs inside the GEMV's prologue (same arithmetic per row as
+    ln_rows_kernel, rounded to f16 once): latents, logits and PCM must not change by a bit against PTTS_GEMV_LN=0."""
+    from pocket_tts_b200 import synth
+    from pocket_tts_b200.engine import Engine, StreamSpec
+    weights = synth.make_weights(11)
+    voice_rows = synth.make_voice_prompt(9, seed=2)
+    frames = 5
+    rng = np.random.default_rng(3)
+    noise = (rng.standard_normal((n, frames, 32)) * np.sqrt(0.7)).astype(np.float32)
+    tokens = [np.arange(3 + i, 10 + 3 * i, dtype=np.int32) for i in range(n)]
+    outs = []
+    for ln_fused in ("1", "0"):
+        monkeypatch.setenv("PTTS_GEMV_LN", ln_fused)
+        eng = Engine(weights, max_slots=4, kv_capacity=256, int8_weights=int8)
+        voice = eng.voice_from_prompt(voice_rows)
+        slots = eng.open_streams([voice] * n, [StreamSpec(tokens[i], frames, 0, 1e30, noise=noise[i]) for i in range(n)])
+        eng.launch_count(reset=True)
+        res = [eng.step(slots) for _ in range(frames)]      # free-running: any difference would compound
+        launches = eng.launch_count()
+        outs.append((np.stack([r[2] for r in res]), np.stack([r[0] for r in res]), np.stack([r[3] for r in res]), launches))
+        eng.close_streams(slots)
+        voice.close()
+        eng.close()
+    (l0, p0, g0, n0), (l1, p1, g1, n1) = outs
+    np.testing.assert_array_equal(l0, l1)
+    np.testing.assert_array_equal(g0, g1)
+    np.testing.assert_array_equal(p0, p1)
+    assert n1 - n0 == 11 * frames, (n0, n1)     # the 11 FlowLM LayerNorm launches of a step are gone
