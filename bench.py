@@ -302,20 +302,24 @@ def run_gpu(args):
         ns = NativeScheduler(eng, voice, args.longform)
         barrier()
         t0 = time.perf_counter()
-        out = ns.run(reqs, i16=True)
+        out = ns.run(reqs, i16=True, view=True)   # PCM read in place from the scheduler's host buffers (ptts_sched_result_view)
         torch.cuda.synchronize()
         lf_s = time.perf_counter() - t0
-        ns.close()
+        lf_phases = dict(ns.last_times)
         want = lf_chunks * FRAMES * 1920 + (lf_chunks - 1) * lf_pause * 24
         assert all(o.shape == (want,) for o in out)
+        assert all(int(np.abs(o[:1920 * 4].astype(np.int32)).sum()) > 0 for o in out[:: max(1, len(out) // 16)])   # real audio, host-readable
+        del out
+        ns.close()
         if world > 1:
             t = torch.tensor([lf_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             lf_s = float(t.item())
         line["longform"] = {"workload": f"configs[4] slice: {args.longform} concurrent requests per GPU x {want / 24000:.1f} s (6 chunks x 125 frames, "
                                         f"[pause:300ms]), native scheduler, i16 PCM to the host", "requests_per_gpu": args.longform,
-                            "value": world * args.longform * want / 24000.0 / lf_s, "unit": UNIT, "wall_s": lf_s}
-        del out, reqs
+                            "value": world * args.longform * want / 24000.0 / lf_s, "unit": UNIT, "wall_s": lf_s,
+                            "phases_s": lf_phases}
+        del reqs
         if eng_lf is None and rank == 0:
             # back to the headline engine for the roofline pass below
             voice.close(); eng.close()
@@ -426,6 +430,7 @@ def run_gpu(args):
         # path (Linear layers on the GEMV of csrc/gemv.cuh); non-headline, reported beside the 64-stream value
         one = [StreamSpec(synth.make_tokens(TOKENS, seed=5), FRAMES, 3, 1e30, temp=0.7, seed=1)]
         us1 = []
+        stream = torch.cuda.ExternalStream(eng.cuda_stream, device=local)   # the long-form pass may have re-created the engine
         for _ in range(4):
             s = eng.open_streams([voice], one)
             eng.step_device(s)

@@ -109,5 +109,6 @@ extern "C" {
     pub fn ptts_sched_run(s: *mut ptts_sched, pcm_i16: i32) -> i32;
     pub fn ptts_sched_result_samples(s: *const ptts_sched, request: i64) -> i64;
     pub fn ptts_sched_result(s: *const ptts_sched, request: i64, pcm_out: *mut c_void, cap_samples: i64) -> i32;
+    pub fn ptts_sched_result_view(s: *const ptts_sched, request: i64, data: *mut *const c_void, n_samples: *mut i64) -> i32;
     pub fn ptts_sched_steps(s: *const ptts_sched) -> i64;
 }

@@ -202,7 +202,7 @@ int32_t ptts_stream_frames(ptts_engine* e, int32_t slot, int32_t* frames_out, in
  * the other, each restarting from the voice state, while different requests fill the batch; whenever streams finish the
  * next chunks are opened together (one packed open, one batched prefill) and join the next step; the device is kept one
  * step ahead of the host (PTTS_STEP_AHEAD).  ptts_sched_run returns when every submitted request is complete; the PCM
- * of a request (all its segments concatenated, f32 or i16 as chosen at run) is then read with ptts_sched_result. */
+ * of a request (all its segments concatenated, f32 or i16 as chosen at run) is then read with ptts_sched_result (copy) or ptts_sched_result_view. */
 typedef struct ptts_sched ptts_sched;
 #define PTTS_SEG_TEXT 0
 #define PTTS_SEG_PAUSE 1
@@ -220,6 +220,10 @@ int64_t ptts_sched_submit(ptts_sched* s, const ptts_segment* segments, int32_t n
 int32_t ptts_sched_run(ptts_sched* s, int32_t pcm_i16);
 int64_t ptts_sched_result_samples(const ptts_sched* s, int64_t request);
 int32_t ptts_sched_result(const ptts_sched* s, int64_t request, void* pcm_out, int64_t cap_samples);
+/* The same PCM without the copy: *data points at the request's samples in the scheduler's own host memory (f32 or i16 as
+ * chosen at run), *n_samples is their count; valid until the next ptts_sched_run or ptts_sched_destroy.  A 60 s request is
+ * 2.9 MB of i16: for 512 requests the copy above costs as much wall time as 40% of the generation itself. */
+int32_t ptts_sched_result_view(const ptts_sched* s, int64_t request, const void** data, int64_t* n_samples);
 int64_t ptts_sched_steps(const ptts_sched* s); /* decode steps the last run took */
 
 #ifdef __cplusplus

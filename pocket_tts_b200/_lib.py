@@ -16,7 +16,7 @@ PRODUCT_SYMBOLS = [
     "ptts_voice_save", "ptts_voice_load", "ptts_config_check",
     "ptts_streams_open", "ptts_step", "ptts_step_begin", "ptts_step_flags", "ptts_step_pcm", "ptts_step_pcm_i16", "ptts_step_device",
     "ptts_sync", "ptts_stream_set_feedback", "ptts_stream_close", "ptts_streams_close", "ptts_stream_frames",
-    "ptts_sched_create", "ptts_sched_destroy", "ptts_sched_submit", "ptts_sched_run", "ptts_sched_result_samples", "ptts_sched_result",
+    "ptts_sched_create", "ptts_sched_destroy", "ptts_sched_submit", "ptts_sched_run", "ptts_sched_result_samples", "ptts_sched_result", "ptts_sched_result_view",
     "ptts_sched_steps",
 ]
 INTERNAL_SYMBOLS = [
@@ -116,6 +116,7 @@ def lib() -> C.CDLL:
     L.ptts_sched_result_samples.argtypes = [vp, i64]
     L.ptts_sched_result_samples.restype = i64
     L.ptts_sched_result.argtypes = [vp, i64, vp, i64]
+    L.ptts_sched_result_view.argtypes = [vp, i64, C.POINTER(vp), C.POINTER(i64)]
     L.ptts_sched_steps.argtypes = [vp]
     L.ptts_sched_steps.restype = i64
     L.ptts_test_noise.argtypes = [i32, C.c_uint64, i32, vp]

@@ -2998,6 +2998,16 @@ int32_t ptts_sched_result(const ptts_sched* s, int64_t req, void* pcm_out, int64
   PTTS_CATCH
 }
 
+int32_t ptts_sched_result_view(const ptts_sched* s, int64_t req, const void** data, int64_t* n_samples) {
+  PTTS_TRY
+  PTTS_REQUIRE(s && data && n_samples && req >= 0 && req < (int64_t)s->reqs.size(), PTTS_ERR_INVALID, "ptts_sched_result_view: bad arguments");
+  const auto& r = s->reqs[(size_t)req];
+  if (!r.out16.empty()) { *data = r.out16.data(); *n_samples = (int64_t)r.out16.size(); }
+  else { *data = r.out32.empty() ? nullptr : (const void*)r.out32.data(); *n_samples = (int64_t)r.out32.size(); }
+  return PTTS_OK;
+  PTTS_CATCH
+}
+
 int64_t ptts_sched_steps(const ptts_sched* s) { return s ? s->steps : -1; }
 
 // ------------------------------------------------------------------------------------------------ isolated kernel tests

@@ -297,17 +297,35 @@ class NativeScheduler:
         self.n_requests = r + 1
         return r
 
-    def run(self, requests: list[list[tuple]] | None = None, i16: bool = False) -> list[np.ndarray]:
+    def run(self, requests: list[list[tuple]] | None = None, i16: bool = False, view: bool = False) -> list[np.ndarray]:
+        """-> one PCM array per request.  view=True: arrays are read-only windows onto the scheduler's own host buffers
+        (ptts_sched_result_view, no copy; valid until the next run() / close()), else private copies."""
+        import time
+        t0 = time.perf_counter()
         for r in requests or []:
             self.submit(r)
+        t1 = time.perf_counter()
         check(_lib.lib().ptts_sched_run(self._h, int(i16)))
+        t2 = time.perf_counter()
         out = []
+        dt = np.int16 if i16 else np.float32
         for r in range(self.n_requests):
+            if view:
+                ptr, n = C.c_void_p(), C.c_int64()
+                check(_lib.lib().ptts_sched_result_view(self._h, r, C.byref(ptr), C.byref(n)))
+                if n.value > 0:
+                    a = np.frombuffer((C.c_char * (n.value * np.dtype(dt).itemsize)).from_address(ptr.value), dtype=dt)
+                    a.flags.writeable = False
+                else:
+                    a = np.empty(0, dt)
+                out.append(a)
+                continue
             n = int(_lib.lib().ptts_sched_result_samples(self._h, r))
-            a = np.empty(max(n, 0), np.int16 if i16 else np.float32)
+            a = np.empty(max(n, 0), dt)
             if n > 0:
                 check(_lib.lib().ptts_sched_result(self._h, r, _ptr(a), n))
             out.append(a)
+        self.last_times = {"submit_s": t1 - t0, "run_s": t2 - t1, "collect_s": time.perf_counter() - t2}
         return out
 
     @property

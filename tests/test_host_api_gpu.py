@@ -148,6 +148,13 @@ def test_native_scheduler_matches_python_scheduler(rig):
     nat = ns.run(reqs)
     steps = ns.steps
     ns.close()
+    ns2 = NativeScheduler(eng, voice, max_batch=4)
+    views = ns2.run(reqs, view=True)      # ptts_sched_result_view: the same samples read in place, no copy
+    for a, v in zip(nat, views):
+        assert not v.flags.writeable and not v.flags.owndata
+        np.testing.assert_array_equal(a, v)
+    del views
+    ns2.close()
     assert steps > 0
     for a, b, c in zip(py, py_ahead, nat):
         # the same policy (one step ahead of the host) batches the same rows at every step: bit-identical
