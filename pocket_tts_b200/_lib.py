@@ -58,6 +58,14 @@ def lib() -> C.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(f"{LIB_PATH} is missing: run `python -m pocket_tts_b200.build` (nvcc, sm_100a). "
                           "There is no CPU or PyTorch fallback for this path.")
+    from . import build as _build
+    if _build.needs_build():
+        # the binary in the tree was not built from the sources in the tree (content hash, not file times): rebuild, or
+        # refuse -- never run a stale kernel silently
+        try:
+            _build.build()
+        except Exception as ex:
+            raise ImportError(f"{LIB_PATH} is stale (source hash differs from {_build.STAMP.name}) and cannot be rebuilt here: {ex}")
     L = C.CDLL(str(LIB_PATH))
     vp, i32, i64, fp = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)
     L.ptts_last_error.restype = C.c_char_p

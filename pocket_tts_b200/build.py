@@ -17,11 +17,25 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = PKG / "libptts_cuda.so.srchash"   # what the shipped binary was built from (travels with it, untracked like it)
+
+
+def source_hash() -> str:
+    """sha256 over the compile flags and every file the library is built from: the identity of the binary, independent of
+    file times (a snapshot copied to another box keeps contents, not necessarily mtimes)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in sorted(DEPS):
+        if p.is_file():
+            h.update(p.name.encode())
+            h.update(p.read_bytes())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not LIB.exists():
+    if not LIB.exists() or not STAMP.exists():
         return True
-    t = LIB.stat().st_mtime
-    return any(p.stat().st_mtime > t for p in DEPS)
+    return STAMP.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -38,6 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if verbose:
         sys.stderr.write(r.stderr)
+    STAMP.write_text(source_hash() + "\n")
     return LIB
 
 

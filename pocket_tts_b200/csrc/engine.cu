@@ -119,6 +119,7 @@ struct Engine {
   Tune tune_conv0, tune_ct2, tune_mlin1, tune_mlin2, tune_minproj, tune_moutproj, tune_ct5;
   void apply(const Tune& t) { if (t.bn > 0) bn_override = t.bn; if (t.cap > 0) split_cap_override = t.cap; }
   int gemm_ref_f = 1;          // > 1 while the GEMMs of a codec group of that many frames are issued (see Engine::gemm)
+  int lin2_ctas = 0, outproj_ctas = 0, inproj_ctas = 0;   // the same for the other decode GEMMs (0 = the common cap; PTTS_LIN2_CTAS / PTTS_OUTPROJ_CTAS / PTTS_INPROJ_CTAS)
   int lin1_ctas = 64;          // linear1 (32 feature tiles): 64 lets it split in two and keep its K slice resident (PTTS_LIN1_CTAS)
   int persistent_ctas = 132;  // grid of the persistent (codec) GEMMs; fewer leaves SMs to the other stream
   int num_sms = 148;          // grid of the small-batch GEMV (gemv.cuh); PTTS_GEMV_CTAS
@@ -798,6 +799,9 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     if (const char* v = std::getenv("PTTS_MAX_CTAS")) split_cta_cap = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_MAX_CTAS_B")) split_cta_cap_b = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_LIN1_CTAS")) lin1_ctas = std::max(1, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_LIN2_CTAS")) lin2_ctas = std::max(0, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_OUTPROJ_CTAS")) outproj_ctas = std::max(0, std::atoi(v));
+    if (const char* v = std::getenv("PTTS_INPROJ_CTAS")) inproj_ctas = std::max(0, std::atoi(v));
     if (const char* v = std::getenv("PTTS_TRIG_A")) trig_a = std::atoi(v);
     if (const char* v = std::getenv("PTTS_TRIG_B")) trig_b = std::atoi(v);
     auto tune = [](const char* name, Tune& t) { if (const char* v = std::getenv(name)) std::sscanf(v, "%d,%d", &t.bn, &t.cap); };
@@ -1168,6 +1172,7 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
   for (int l = 0; l < N_LAYERS; ++l) {
     GemmEpi e = epi_none();
     e.out32 = qkv; e.out32_map = plain_map(3 * D_MODEL);
+    if (!is_prefill && inproj_ctas) split_cap_override = inproj_ctas;
     tag(is_prefill ? "prefill.in_proj" : "flowlm.in_proj"); gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
     if (is_prefill) {
       { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
@@ -1185,6 +1190,7 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
     // 1-4 rows: LN2 / the next layer's LN1 run inside the prologue of the GEMV that consumes them (no launch, h never written)
     const bool fuse2 = ln_fusable(rows, w_lin1[l]);
     if (!fuse2) ln_after_next_gemm("flowlm.layernorm", x, rows, D_MODEL, ln2_w[l].p, ln2_b[l].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
+    if (!is_prefill && outproj_ctas) split_cap_override = outproj_ctas;
     tag(is_prefill ? "prefill.out_proj" : "flowlm.out_proj"); gemm_rows(attn, rows, D_MODEL, w_outproj[l], D_MODEL, e, true);
     e = epi_none();
     e.act = ACT_GELU; e.out16 = ffn; e.out16_map = plain_map(D_FFN);
@@ -1196,6 +1202,7 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
     const bool fuse1 = l + 1 < N_LAYERS && ln_fusable(rows, w_inproj[l + 1]);
     if (l + 1 < N_LAYERS && !fuse1)
       ln_after_next_gemm("flowlm.layernorm", x, rows, D_MODEL, ln1_w[l + 1].p, ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL);
+    if (!is_prefill && lin2_ctas) split_cap_override = lin2_ctas;
     tag(is_prefill ? "prefill.linear2" : "flowlm.linear2"); gemm_rows(ffn, rows, D_FFN, w_lin2[l], D_MODEL, e, true);
     if (fuse1) pre_ln = LnSpec{true, x, rows, D_MODEL, ln1_w[l + 1].p, ln1_b[l + 1].p, 1e-5f, nullptr, nullptr, 0, h, D_MODEL, "flowlm.layernorm"};
   }
@@ -2493,12 +2500,14 @@ int32_t ptts_profile_gemm_replay(ptts_engine* h, int32_t rows, int32_t iters, fl
   for (int kind = 0; kind < 4; ++kind) {
     auto one = [&](int l) {
       GemmEpi ep = epi_none();
-      if (kind == 0) { ep.out32 = e.qkv32.p; ep.out32_map = plain_map(3 * D_MODEL); e.gemm_rows(e.h16.p, rows, D_MODEL, e.w_inproj[l], 3 * D_MODEL, ep); }
+      if (kind == 0) { ep.out32 = e.qkv32.p; ep.out32_map = plain_map(3 * D_MODEL); if (e.inproj_ctas) e.split_cap_override = e.inproj_ctas; e.gemm_rows(e.h16.p, rows, D_MODEL, e.w_inproj[l], 3 * D_MODEL, ep); }
       else if (kind == 1) { ep.out32 = e.x32.p; ep.out32_map = plain_map(D_MODEL); ep.res = e.x32.p; ep.res_map = plain_map(D_MODEL);
+                            if (e.outproj_ctas) e.split_cap_override = e.outproj_ctas;
                             e.gemm_rows(e.attn16.p, rows, D_MODEL, e.w_outproj[l], D_MODEL, ep, true); }
       else if (kind == 2) { ep.act = ACT_GELU; ep.out16 = e.ffn16.p; ep.out16_map = plain_map(D_FFN); e.split_cap_override = e.lin1_ctas;
                             e.gemm_rows(e.h16.p, rows, D_MODEL, e.w_lin1[l], D_FFN, ep); }
       else { ep.out32 = e.x32.p; ep.out32_map = plain_map(D_MODEL); ep.res = e.x32.p; ep.res_map = plain_map(D_MODEL);
+             if (e.lin2_ctas) e.split_cap_override = e.lin2_ctas;
              e.gemm_rows(e.ffn16.p, rows, D_FFN, e.w_lin2[l], D_MODEL, ep, true); }
     };
     for (int l = 0; l < N_LAYERS; ++l) one(l);  // warm (tensor maps, instruction cache)

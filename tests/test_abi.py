@@ -110,3 +110,12 @@ def test_plain_c_caller(built_lib, tmp_path):
     # the same sizes the ctypes structures have
     assert C.sizeof(built_lib.EngineCfg) == 64 and C.sizeof(built_lib.TensorDesc) == 56 and C.sizeof(built_lib.StreamParams) == 32
     assert C.sizeof(built_lib.Segment) == 56
+
+
+def test_library_is_built_from_the_sources_in_the_tree():
+    """The shipped binary carries the content hash of what it was compiled from (pocket_tts_b200/build.py); loading it with
+    other sources in the tree rebuilds or refuses (never a stale kernel)."""
+    from pocket_tts_b200 import build
+    build.build()
+    assert build.STAMP.exists() and build.STAMP.read_text().strip() == build.source_hash()
+    assert not build.needs_build()
