@@ -57,6 +57,7 @@ static constexpr int D_MODEL = 1024, N_HEADS = 16, N_LAYERS = 6, D_FFN = 4096;
 static constexpr int FLOW_DIM = 512, FLOW_DEPTH = 6, MOD_LD = FLOW_DEPTH * 3 * FLOW_DIM + 2 * FLOW_DIM;  // 10240
 static constexpr int MIMI_DIM = 512, MIMI_HEADS = 8, MIMI_LAYERS = 2, MIMI_FFN = 2048, MIMI_T = 16;
 static constexpr int N_BINS = 4000;
+static constexpr size_t PF_SMEM_MAX = 200 * 1024;   // K + V rows a prefill-attention tile may stage (704 keys); longer ranges use the row-per-CTA kernel
 static constexpr int MAX_LSD = 64;   // ptts_engine_set_lsd_steps cap; time_emb is sized for it once
 
 struct Weight16 {   // GEMM operand [Fpad][K] f16, K-major
@@ -263,6 +264,10 @@ struct Engine {
   DevBuf<float> px32, pqkv32, pqrot;
   DevBuf<__half> ph16, pattn16, pffn16;
   DevBuf<int> prow_seq, prow_pos, ptokens;
+  DevBuf<int2> ptiles;            // prefill attention tiles (first row, rows) of the rows in prow_seq / prow_pos
+  int pf_tiles = 0, pf_kmax = 0;  // tiles of the pending prefill and the longest key range any of them stages (0 tiles: row-per-CTA kernel)
+  bool pf_tiled = true;           // PTTS_PREFILL_TILE=0: the row-per-CTA SIMT prefill attention instead of the tensor-core tiles
+  void set_prefill_tiles(const std::vector<int>& rs, const std::vector<int>& rp);
   // ---- pinned staging
   // a ring of tickets: with PTTS_STEP_AHEAD step n+1 is enqueued while the flags of step n and the PCM of step n-1 are
   // still on their way to the host; with a codec group the PCM of a frame leaves with its group, up to cg - 1 steps later
@@ -815,6 +820,8 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     num_sms = prop.multiProcessorCount;
     if (const char* v = std::getenv("PTTS_GEMV_CTAS")) num_sms = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_GEMV_LN")) gemv_ln = std::atoi(v) != 0;
+    if (const char* v = std::getenv("PTTS_PREFILL_TILE")) pf_tiled = std::atoi(v) != 0;
+    PTTS_CUDA(cudaFuncSetAttribute(flowlm_attn_prefill_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_MAX));
   }
   ls = stream;
   PTTS_CUDA(cudaEventCreateWithFlags(&ev_a_done, cudaEventDisableTiming));
@@ -883,7 +890,7 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
 
   px32.alloc((size_t)PR * D_MODEL); pqkv32.alloc((size_t)PR * 3 * D_MODEL); pqrot.alloc((size_t)PR * D_MODEL);
   ph16.alloc((size_t)PR * D_MODEL); pattn16.alloc((size_t)PR * D_MODEL); pffn16.alloc((size_t)PR * D_FFN);
-  prow_seq.alloc(PR); prow_pos.alloc(PR); ptokens.alloc(PR);
+  prow_seq.alloc(PR); prow_pos.alloc(PR); ptokens.alloc(PR); ptiles.alloc(PR);
   for (int i = 0; i < NT; ++i) {
     PTTS_CUDA(cudaMallocHost(&pin_pcm[i], (size_t)NB * FRAME * 4));
     PTTS_CUDA(cudaMallocHost(&pin_pcm16[i], (size_t)NB * FRAME * 2));
@@ -1176,10 +1183,15 @@ void Engine::flowlm_layers(int rows, float* x, __half* h, float* qkv, __half* at
     tag(is_prefill ? "prefill.in_proj" : "flowlm.in_proj"); gemm_rows(h, rows, D_MODEL, w_inproj[l], 3 * D_MODEL, e);
     if (is_prefill) {
       { ProfScope ps(*this, "prefill.rope_append", (double)rows * D_MODEL * (12 + 4 + 4), 0);
-        launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, N_HEADS), 32, 0, ls, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
+        launch_k(use_pdl, flowlm_rope_append_kernel, dim3(rows, (N_HEADS + 3) / 4), 128, 0, ls, 1, qkv, rseq, rpos, seqs.p, l, N_HEADS, qrot); }
       if (l == N_LAYERS - 1) break;  // the prompt pass keeps only KV (reference discards the output, tts_model.rs:958-964)
       { ProfScope ps(*this, "prefill.attn");
-        launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
+        const size_t pf_smem = (size_t)round_up(pf_kmax, 16) * 2 * PF_KP * sizeof(__half);
+        if (pf_tiles > 0 && pf_smem <= PF_SMEM_MAX)
+          launch_k(use_pdl, flowlm_attn_prefill_mma_kernel, dim3(pf_tiles, N_HEADS), 128, pf_smem, ls, 1, qrot, (const int2*)ptiles.p, rseq, rpos,
+                   seqs.p, l, N_HEADS, attn);
+        else
+          launch_k(use_pdl, flowlm_attn_prefill_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qrot, rseq, rpos, seqs.p, l, N_HEADS, attn); }
     } else {
       { ProfScope ps(*this, "flowlm.attn_decode", step_kv_bytes + (double)rows * D_MODEL * (12 + 4 + 2), 0, "flowlm_attn_decode_kernel");
         launch_k(use_pdl, flowlm_attn_decode_kernel, dim3(rows, N_HEADS), ATTN_THREADS, 0, ls, 1, qkv, (const SeqDesc*)row_desc.p, l, N_HEADS, attn); }
@@ -1895,6 +1907,23 @@ void Engine::encode_prompt(const float* pcm_host, int n_samples, std::vector<flo
   *frames_out = F;
 }
 
+// Tiles for flowlm_attn_prefill_mma_kernel: runs of up to PF_QT consecutive rows of one sequence at consecutive positions.
+void Engine::set_prefill_tiles(const std::vector<int>& rs, const std::vector<int>& rp) {
+  pf_tiles = 0; pf_kmax = 0;
+  if (!pf_tiled || cfg.debug_gemm) return;
+  std::vector<int2> t;
+  const int rows = (int)rs.size();
+  for (int r = 0; r < rows;) {
+    int n = 1;
+    while (r + n < rows && n < PF_QT && rs[r + n] == rs[r] && rp[r + n] == rp[r + n - 1] + 1) ++n;
+    t.push_back(make_int2(r, n));
+    pf_kmax = std::max(pf_kmax, rp[r + n - 1] + 1);
+    r += n;
+  }
+  PTTS_CUDA(cudaMemcpyAsync(ptiles.p, t.data(), t.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
+  pf_tiles = (int)t.size();
+}
+
 void Engine::prefill(int rows) {
   ls = stream;
   tag("flowlm.layernorm"); ln<D_MODEL>(px32.p, rows, ln1_w[0].p, ln1_b[0].p, 1e-5f, nullptr, nullptr, 0, ph16.p, D_MODEL);
@@ -1983,6 +2012,7 @@ int32_t ptts_voice_from_prompt(ptts_engine* h, const float* audio_prompt, int32_
   for (int i = 0; i < n_rows; ++i) rp[i] = i;
   PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, rs.data(), n_rows * 4, cudaMemcpyHostToDevice, e.stream));
   PTTS_CUDA(cudaMemcpyAsync(e.prow_pos.p, rp.data(), n_rows * 4, cudaMemcpyHostToDevice, e.stream));
+  e.set_prefill_tiles(rs, rp);
   PTTS_CUDA(cudaMemcpyAsync(e.px32.p, audio_prompt, (size_t)n_rows * D_MODEL * 4, cudaMemcpyHostToDevice, e.stream));
   e.prefill(n_rows);
   PTTS_CUDA(cudaStreamSynchronize(e.stream));
@@ -2104,6 +2134,7 @@ static void streams_open_impl(Engine& e, int n, ptts_voice* const* voices, const
         for (int j = 0; j < token_offsets[i + 1] - token_offsets[i]; ++j, ++r) { rs[r] = free_slots[i]; rp[r] = voices[i]->v.len + j; }
       PTTS_CUDA(cudaMemcpyAsync(e.prow_seq.p, rs.data(), rows * 4, cudaMemcpyHostToDevice, e.stream));
       PTTS_CUDA(cudaMemcpyAsync(e.prow_pos.p, rp.data(), rows * 4, cudaMemcpyHostToDevice, e.stream));
+      e.set_prefill_tiles(rs, rp);
       PTTS_CUDA(cudaMemcpyAsync(e.ptokens.p, tokens + token_offsets[i0], rows * 4, cudaMemcpyHostToDevice, e.stream));
       { ProfScope ps(e, "prefill.embed", (double)rows * 1024 * 8, 0);
         launch_k(e.use_pdl, embed_rows_kernel, rows, 256, 0, e.stream, 1, e.ptokens.p, rows, e.lut.p, e.px32.p); }

@@ -440,13 +440,15 @@ __global__ void __launch_bounds__(ATTN_THREADS, 7) flowlm_attn_decode_kernel(con
 }
 
 // Prefill, step 1: RoPE + KV append for every new row (rows of several sequences at once); rotated q kept in f32.
-// grid (rows, heads), block 32.
+// grid (rows, heads / 4), block 128: one warp per head (a 32-thread CTA per (row, head) was 40 960 CTAs for a 64 x 40-token
+// open: 48 us of CTA scheduling per layer for 10 MB of traffic).
 __global__ void flowlm_rope_append_kernel(const float* __restrict__ qkv, const int* __restrict__ row_seq,
                                           const int* __restrict__ row_pos, const SeqDesc* __restrict__ seqs, int layer,
                                           int n_heads, float* __restrict__ q_rot) {
   pdl_launch_dependents();
   pdl_wait();
-  const int r = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int r = blockIdx.x, h = blockIdx.y * 4 + (threadIdx.x >> 5), tid = threadIdx.x & 31;
+  if (h >= n_heads) return;
   const int d_model = n_heads * HD;
   const SeqDesc sd = seqs[row_seq[r]];
   const int pos = row_pos[r];
@@ -481,6 +483,158 @@ __global__ void flowlm_attn_prefill_kernel(const float* __restrict__ q_rot, cons
   __syncthreads();
   attend_block(sd, layer, h, n_heads, q_s, red_s, pos + 1);
   if (tid < 64) out16[static_cast<long long>(r) * d_model + h * HD + tid] = __float2half_rn(red_s[tid]);
+}
+
+// Prefill attention on tensor cores (reference modules/sdpa.rs:36-171 at Lq > 1: softmax(Q K^T / 8 + causal mask) V).
+// grid (tiles, heads), block 128.  A tile is up to PF_QT = 64 consecutive new rows of ONE sequence (host-built list); warp w
+// owns query rows [16 w, 16 w + 16) of it.  The row-per-CTA kernel above re-reads the sequence's K / V rows for every query
+// row (a 64 x 40-token open: 40 960 CTAs x 32 KB = 1.3 GB through L2 per layer, 222 us) and spends ~2 000 SIMT instructions
+// per row; here the CTA stages keys [0, last position] of its (sequence, head) in shared memory once (rows padded to 144
+// bytes: conflict-free fragment loads) and each warp runs a flash-style pass over them with mma.sync m16n8k16:
+//   S = Q K^T   A = Q rows as f16 fragments (held in registers for the whole pass), B = K rows (32-bit shared loads)
+//   online softmax on the accumulator fragments (row g / g + 8 of a quad: two shuffles per reduction), exp2 with
+//   log2(e) / 8 folded into the scale, causal mask by absolute position, key blocks above the warp's last row skipped
+//   O += P V    A = P rounded to f16 straight from the S fragments, B = V through ldmatrix.trans
+// f32 accumulation throughout; q and P are rounded to f16 (the K, V rows and the output already are).
+static constexpr int PF_QT = 64;
+static constexpr int PF_KP = 72;   // shared-memory pitch of a K / V row in halves (144 bytes)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__global__ void __launch_bounds__(128) flowlm_attn_prefill_mma_kernel(
+    const float* __restrict__ q_rot, const int2* __restrict__ tiles, const int* __restrict__ row_seq,
+    const int* __restrict__ row_pos, const SeqDesc* __restrict__ seqs, int layer, int n_heads, __half* __restrict__ out16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t pf_smem[];
+  const int2 tl = tiles[blockIdx.x];
+  const int r0 = tl.x, nr = tl.y, h = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int d_model = n_heads * HD;
+  const SeqDesc sd = seqs[row_seq[r0]];
+  const int pos0 = row_pos[r0];                 // absolute position of the tile's first row; rows are consecutive
+  const int kmax = pos0 + nr;                   // keys [0, kmax) cover every row of the tile
+  const int kpad = (kmax + 15) & ~15;
+  __half* ks = reinterpret_cast<__half*>(pf_smem);
+  __half* vs = ks + static_cast<size_t>(kpad) * PF_KP;
+  for (int idx = tid; idx < kpad * 8; idx += 128) {
+    const int i = idx >> 3, c = idx & 7;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+    if (i < kmax) {
+      kv = reinterpret_cast<const uint4*>(kv_row(sd, layer, 0, h, n_heads, i))[c];
+      vv = reinterpret_cast<const uint4*>(kv_row(sd, layer, 1, h, n_heads, i))[c];
+    }
+    *reinterpret_cast<uint4*>(ks + i * PF_KP + c * 8) = kv;
+    *reinterpret_cast<uint4*>(vs + i * PF_KP + c * 8) = vv;
+  }
+  __syncthreads();
+  if (warp * 16 >= nr) return;
+  // Q fragments: rows g and g + 8 of the warp's 16, four k-steps of 16 dims
+  uint32_t qa[4][4];
+  {
+    const int ra = warp * 16 + g, rb = ra + 8;
+    const float* qa_p = q_rot + static_cast<long long>(r0 + (ra < nr ? ra : 0)) * d_model + h * HD;
+    const float* qb_p = q_rot + static_cast<long long>(r0 + (rb < nr ? rb : 0)) * d_model + h * HD;
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      const float2 a_lo = *reinterpret_cast<const float2*>(qa_p + 16 * s4 + 2 * t), a_hi = *reinterpret_cast<const float2*>(qa_p + 16 * s4 + 8 + 2 * t);
+      const float2 b_lo = *reinterpret_cast<const float2*>(qb_p + 16 * s4 + 2 * t), b_hi = *reinterpret_cast<const float2*>(qb_p + 16 * s4 + 8 + 2 * t);
+      qa[s4][0] = pack_h2(a_lo.x, a_lo.y);
+      qa[s4][1] = pack_h2(b_lo.x, b_lo.y);
+      qa[s4][2] = pack_h2(a_hi.x, a_hi.y);
+      qa[s4][3] = pack_h2(b_hi.x, b_hi.y);
+    }
+  }
+  const float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) and log2(e): P = exp2(S * kScale - m)
+  const int qp_a = pos0 + warp * 16 + g, qp_b = qp_a + 8;   // absolute positions of the thread's two rows
+  const int kb_end = (pos0 + min(warp * 16 + 15, nr - 1)) / 16 + 1;   // key blocks up to the warp's last real row
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  const uint32_t vs_u32 = smem_u32(vs);
+  for (int kb = 0; kb < kb_end; ++kb) {
+    float sacc[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+      const __half* krow = ks + (kb * 16 + 8 * j + g) * PF_KP + 2 * t;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + 16 * s4);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + 16 * s4 + 8);
+        mma_16816(sacc[j], qa[s4][0], qa[s4][1], qa[s4][2], qa[s4][3], b0, b1);
+      }
+    }
+    // scale, causal mask, block row maxima
+    float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kp = kb * 16 + 8 * j + 2 * t + (e & 1);
+        const int qp = (e & 2) ? qp_b : qp_a;
+        const float sv = (kp <= qp) ? sacc[j][e] * kScale : -INFINITY;
+        sacc[j][e] = sv;
+        if (e & 2) mx_b = fmaxf(mx_b, sv); else mx_a = fmaxf(mx_a, sv);
+      }
+    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+    const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+    // key 0 is visible to every row, so mn is finite from the first block on
+    const float ca = exp2f(m_a - mn_a), cb = exp2f(m_b - mn_b);   // exp2(-inf) = 0 on the first block
+    m_a = mn_a; m_b = mn_b;
+    float p[2][4];
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      p[j][0] = exp2f(sacc[j][0] - mn_a); p[j][1] = exp2f(sacc[j][1] - mn_a);
+      p[j][2] = exp2f(sacc[j][2] - mn_b); p[j][3] = exp2f(sacc[j][3] - mn_b);
+      sa += p[j][0] + p[j][1];
+      sb += p[j][2] + p[j][3];
+    }
+    l_a = l_a * ca + sa;
+    l_b = l_b * cb + sb;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= ca; o[nt][1] *= ca; o[nt][2] *= cb; o[nt][3] *= cb; }
+    const uint32_t pa0 = pack_h2(p[0][0], p[0][1]), pa1 = pack_h2(p[0][2], p[0][3]);
+    const uint32_t pa2 = pack_h2(p[1][0], p[1][1]), pa3 = pack_h2(p[1][2], p[1][3]);
+    // V fragments: ldmatrix.x4.trans over keys kb*16 .. +15, two 8-dim column blocks per instruction
+    // (lanes 0-7: keys 0-7 of block nt, 8-15: keys 8-15 of nt, 16-23: keys 0-7 of nt+1, 24-31: keys 8-15 of nt+1)
+    const uint32_t vrow = vs_u32 + static_cast<uint32_t>(((kb * 16 + (lane & 15)) * PF_KP + (lane >> 4) * 8) * 2);
+#pragma unroll
+    for (int nt = 0; nt < 8; nt += 2) {
+      uint32_t b0, b1, b2, b3;
+      ldmatrix_x4_trans(vrow + nt * 16, b0, b1, b2, b3);
+      mma_16816(o[nt], pa0, pa1, pa2, pa3, b0, b1);
+      mma_16816(o[nt + 1], pa0, pa1, pa2, pa3, b2, b3);
+    }
+  }
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+  const float ia = 1.f / l_a, ib = 1.f / l_b;
+  const int ra = warp * 16 + g, rb = ra + 8;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (ra < nr)
+      *reinterpret_cast<uint32_t*>(out16 + static_cast<long long>(r0 + ra) * d_model + h * HD + nt * 8 + 2 * t) = pack_h2(o[nt][0] * ia, o[nt][1] * ia);
+    if (rb < nr)
+      *reinterpret_cast<uint32_t*>(out16 + static_cast<long long>(r0 + rb) * d_model + h * HD + nt * 8 + 2 * t) = pack_h2(o[nt][2] * ib, o[nt][3] * ib);
+  }
 }
 
 // ---------------------------------------------------------------- Mimi encoder (voice cloning from PCM)
