@@ -361,7 +361,7 @@ def run_gpu(args):
         fn, f = max(fns.items(), key=lambda kv: kv[1]["us"])
         nl = f["launches"]
         traffic, traffic_src = ncu_traffic()
-        if fn in ("gemm_tc_kernel", "gemv_rows_kernel"):
+        if (fn == "gemm_tc_kernel" and STREAMS > 4) or fn == "gemv_rows_kernel":
             # the dominant kernel's time WITHOUT any event-pair correction: its four decode shapes replayed as graphs of
             # back-to-back launches over the real weights of all six layers (ptts_profile_gemm_replay), one event pair per
             # graph; pooled over the 24 FlowLM launches of a step (the remaining gemm_tc_kernel launches -- flow head glue
@@ -442,9 +442,16 @@ def run_gpu(args):
             eng.sync()
             us1.append(1000.0 * e0.elapsed_time(e1) / (FRAMES - 1))
             eng.close_stream(int(s[0]))
+        rp1 = eng.gemm_replay(1, 20)     # the four decode Linear shapes at ONE row: the small-batch GEMV, graph-replayed
+        by1, t1 = sum(v["bytes"] for v in rp1.values()), sum(v["us"] for v in rp1.values())
         line["single_stream"] = {"workload": "configs[0] shape: 1 utterance x 125 frames, device-resident decode steps",
                                  "us_per_frame": statistics.median(us1[1:]),
-                                 "realtime_factor": FRAME_SEC * 1e6 / statistics.median(us1[1:])}
+                                 "realtime_factor": FRAME_SEC * 1e6 / statistics.median(us1[1:]),
+                                 "linear_layers": {"kernel": "gemv_rows_kernel", "bound": "hbm", "achieved": by1 / t1 / 1e3, "unit": "GB/s",
+                                                   "peak": peaks()["hbm"], "frac": by1 / t1 / 1e3 / peaks()["hbm"], "per_shape": rp1,
+                                                   "traffic": ncu_traffic()[0].get("gemv_rows_kernel"),
+                                                   "how": "in_proj / out_proj / linear1 / linear2 at one row over the real weights of "
+                                                          "all six layers, 20 x 6 back-to-back launches per captured graph"}}
         line["ttfa_ms"] = {"p50_single_stream": statistics.median(ttfa[2:]), "batch64_first_frames": t64,
                            "voice_from_pcm_87_frames": statistics.median(tv[1:])}
         if not args.no_cpu_baseline:

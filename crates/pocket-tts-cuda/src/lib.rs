@@ -381,10 +381,11 @@ pub fn generate_many_long(model: &TTSModel, texts: &[&str], voice: &ModelState) 
         }
         check(unsafe { ffi::ptts_sched_run(sched, 1) })?;
         (0..texts.len() as i64).map(|r| {
-            let n = unsafe { ffi::ptts_sched_result_samples(sched, r) };
-            let mut pcm = vec![0i16; n.max(0) as usize];
-            check(unsafe { ffi::ptts_sched_result(sched, r, pcm.as_mut_ptr().cast(), n) })?;
-            Ok(pcm)
+            // the samples sit in the scheduler's own host buffer: one copy into the Vec the caller owns, no zero-fill first
+            let (mut data, mut n) = (std::ptr::null::<std::ffi::c_void>(), 0i64);
+            check(unsafe { ffi::ptts_sched_result_view(sched, r, &mut data, &mut n) })?;
+            if n <= 0 || data.is_null() { return Ok(Vec::new()); }
+            Ok(unsafe { std::slice::from_raw_parts(data.cast::<i16>(), n as usize) }.to_vec())
         }).collect()
     };
     let out = run();
