@@ -119,6 +119,19 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_rows_kernel(const GemvPa
     }
   };
   load_batch(0);        // independent of the previous kernel: in flight across the dependency
+  // so are the per-feature epilogue constants of the element this lane will write for batch 0 (int8 scale, bias, LayerScale):
+  // requested here they cost nothing, behind the dependency each would be one more L2 round trip at the tail of the kernel
+  const GemmEpi& e = p.epi;
+  float c_ws = 1.f, c_bias = 0.f, c_fs = 1.f;
+  {
+    const int idx0 = lane / (32 / NV), i0 = idx0 / ROWS;
+    const int f0 = i0 * W + gw;
+    if (f0 < F) {
+      if (e.wscale) c_ws = __ldg(e.wscale + f0);
+      if (e.bias) c_bias = __ldg(e.bias + f0);
+      if (e.fscale) c_fs = __ldg(e.fscale + f0);
+    }
+  }
   constexpr bool LN_OK = (INT8 ? KCH * 512 : KCH * 256) == 1024;
   const bool fused_ln = LN_OK && p.ln_x != nullptr;
   float* lnw_s = reinterpret_cast<float*>(gemv_smem + ROWS * 1024 * 2);
@@ -192,7 +205,6 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_rows_kernel(const GemvPa
   }
   __syncthreads();
   const uint32_t xs = smem_u32(gemv_smem);
-  const GemmEpi& e = p.epi;
   const int nbatch = (F + W * NF - 1) / (W * NF);
   for (int batch = 0; batch < nbatch; ++batch) {
     if (batch > 0) load_batch(batch);
@@ -250,10 +262,15 @@ __global__ void __launch_bounds__(GEMV_THREADS, 2) gemv_rows_kernel(const GemvPa
     const int f = (batch * NF + i) * W + gw;
     if ((lane % SHARE) == 0 && f < F && r < p.rows) {
       float v = acc[0];
-      if (e.wscale) v *= __ldg(e.wscale + f);
-      if (e.bias) v += __ldg(e.bias + f);
+      if (batch > 0) {
+        if (e.wscale) c_ws = __ldg(e.wscale + f);
+        if (e.bias) c_bias = __ldg(e.bias + f);
+        if (e.fscale) c_fs = __ldg(e.fscale + f);
+      }
+      if (e.wscale) v *= c_ws;
+      if (e.bias) v += c_bias;
       v = epi_act(e.act, v) * e.alpha;
-      if (e.fscale) v *= __ldg(e.fscale + f);
+      if (e.fscale) v *= c_fs;
       if (e.gate) v *= e.gate[row_off(e.gate_map, r) + f];
       if (e.res) v += e.res[row_off(e.res_map, r) + f];
       if (e.out32) e.out32[row_off(e.out32_map, r) + f] = v;
