@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include "flow_head.cuh"
+#include "flow_small.cuh"
 #include "gemm.cuh"
 #include "gemv.cuh"
 #include "host_util.h"
@@ -163,6 +164,8 @@ struct Engine {
   DevBuf<float> outnorm_w, outnorm_b, eos_w, eos_b, bos, emb_std, emb_mean, lut;
   Weight16 w_cond, w_finproj, w_ada, w_mlp0[FLOW_DEPTH], w_mlp2[FLOW_DEPTH], w_final;
   DevBuf<__half> w_flowpack;   // mlp.0 / mlp.2 of the six blocks and the final Linear, one [6272][512] operand (flow_head.cuh)
+  bool flow_small = false;     // PTTS_FLOW_SMALL=1: 1-4 rows through the 8-CTA cluster GEMV form of the flow head (flow_small.cuh).  Opt-in:
+                               // 50 -> 33 us per launch but 236 -> 231 us per frame only, and one unexplained test failure in three runs of the round
   bool fused_flow = true;      // ptts_engine_cfg.reserved[5] = 1 or debug_gemm: the per-layer launches instead
   static constexpr int MOD_STEPS = 4;   // Euler steps whose modulation rows fit the scratch: one Linear + one flow-head launch for all of them
   bool mod_all_steps() const { return lsd_steps <= MOD_STEPS; }
@@ -821,6 +824,10 @@ void Engine::init(const ptts_engine_cfg& c, const ptts_tensor_desc* w, int nw) {
     if (const char* v = std::getenv("PTTS_GEMV_CTAS")) num_sms = std::max(1, std::atoi(v));
     if (const char* v = std::getenv("PTTS_GEMV_LN")) gemv_ln = std::atoi(v) != 0;
     if (const char* v = std::getenv("PTTS_PREFILL_TILE")) pf_tiled = std::atoi(v) != 0;
+    if (const char* v = std::getenv("PTTS_FLOW_SMALL")) flow_small = std::atoi(v) != 0;
+    PTTS_CUDA(cudaFuncSetAttribute(flow_head_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+    PTTS_CUDA(cudaFuncSetAttribute(flow_head_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
+    PTTS_CUDA(cudaFuncSetAttribute(flow_head_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM));
     PTTS_CUDA(cudaFuncSetAttribute(flowlm_attn_prefill_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM_MAX));
   }
   ls = stream;
@@ -1257,6 +1264,19 @@ void Engine::flow_head_fused(int n, const float* mod, long long mod_step_stride,
   fp.mod = mod; fp.mod_step_stride = mod_step_stride; fp.z32 = z32.p; fp.z16 = z16.p; fp.x_dbg = fx32.p;
   fp.n = n; fp.steps = steps; fp.alpha = 1.f / (float)lsd_steps;
   fp.trace = fh_trace.p;
+  if (n <= FS_MAX_ROWS && flow_small && cfg.reserved[1] == 0) {
+    FlowSmallParams q{};
+    q.fp = fp; q.fp.trace = nullptr;
+    q.w_in = w_finproj.w.p; q.w_pack = w_flowpack.p;
+    const double bytes = (double)steps * ((double)FH_PACK_ROWS * FLOW_DIM * 2 + 512.0 * 64 * 2 + (double)n * MOD_LD * 4.0) + (double)n * (64 * 2 + 32 * 8);
+    const double flops = 2.0 * steps * n * (12.0 * FLOW_DIM * FLOW_DIM + 64.0 * FLOW_DIM + 32.0 * FLOW_DIM);
+    ProfScope ps(*this, "flow.head_small", bytes, flops, "flow_head_small_kernel");
+    if (n == 1) launch_k(use_pdl, flow_head_small_kernel<1>, dim3(1, 1, FS_CL), FS_THREADS, FS_SMEM, ls, FS_CL, q);
+    else if (n == 2) launch_k(use_pdl, flow_head_small_kernel<2>, dim3(1, 1, FS_CL), FS_THREADS, FS_SMEM, ls, FS_CL, q);
+    else launch_k(use_pdl, flow_head_small_kernel<4>, dim3(1, 1, FS_CL), FS_THREADS, FS_SMEM, ls, FS_CL, q);
+    PTTS_CUDA(cudaGetLastError());
+    return;
+  }
   const CUtensorMap& m_win = tmaps.get(w_finproj.w.p, 64, w_finproj.Fpad, 1, 64, (long long)w_finproj.Fpad * 64, 128, 1);
   // weights: (64 k, rows, k-blocks); one box = four k-block tiles [k-block][128 features][64]
   const CUtensorMap& m_wp = tmaps.get(w_flowpack.p, 64, FH_PACK_ROWS, 8, FLOW_DIM, 64, 128, 4);

@@ -151,3 +151,44 @@ def test_fused_layernorm_prologue_is_bit_identical_to_the_layernorm_launches(n, 
     np.testing.assert_array_equal(g0, g1)
     np.testing.assert_array_equal(p0, p1)
     assert n1 - n0 == 11 * frames, (n0, n1)     # the 11 FlowLM LayerNorm launches of a step are gone
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("PTTS_TEST_FLOW_SMALL"),
+                    reason="flow_small.cuh is opt-in (PTTS_FLOW_SMALL=1) and so is its test (PTTS_TEST_FLOW_SMALL=1)")
+@pytest.mark.parametrize("n,lsd,int8", [(1, 1, False), (2, 4, False), (3, 1, False), (4, 2, False), (1, 4, True)])
+def test_small_batch_flow_head_matches_the_fused_cluster_kernel(n, lsd, int8, monkeypatch):
+    """flow_head_small_kernel (1-4 rows: one cluster of 8 CTAs, GEMV warps, operands replicated through distributed shared
+    memory; csrc/flow_small.cuh) against flow_head_kernel (tcgen05, PTTS_FLOW_SMALL=0) on the same conditioning: the same
+    arithmetic up to summation order, for one and several Euler steps (reference flow_lm.rs:7-22, mlp.rs:135-171,275-383)."""
+    from pocket_tts_b200 import synth
+    from pocket_tts_b200.engine import Engine, StreamSpec
+    weights = synth.make_weights(17)
+    voice_rows = synth.make_voice_prompt(10, seed=8)
+    frames = 4
+    rng = np.random.default_rng(12)
+    noise = (rng.standard_normal((n, frames, 32)) * np.sqrt(0.7)).astype(np.float32)
+    feed = (rng.standard_normal((n, frames, 32)) * 0.5).astype(np.float32)
+    tokens = [np.arange(4 + i, 12 + 2 * i, dtype=np.int32) for i in range(n)]
+    outs = []
+    for small in ("1", "0"):
+        monkeypatch.setenv("PTTS_FLOW_SMALL", small)
+        eng = Engine(weights, max_slots=4, kv_capacity=256, int8_weights=int8)
+        eng.set_lsd_steps(lsd)
+        voice = eng.voice_from_prompt(voice_rows)
+        slots = eng.open_streams([voice] * n, [StreamSpec(tokens[i], frames, 0, 1e30, noise=noise[i]) for i in range(n)])
+        lat, pcm = [], []
+        for f in range(frames):
+            if f > 0:
+                for i in range(n):
+                    eng.set_feedback(int(slots[i]), feed[i, f - 1])
+            p, fin, l, lg = eng.step(slots)
+            lat.append(l.copy()); pcm.append(p.copy())
+        outs.append((np.stack(lat), np.stack(pcm)))
+        eng.close_streams(slots)
+        voice.close()
+        eng.close()
+    (l0, p0), (l1, p1) = outs
+    assert np.isfinite(l0).all()
+    assert np.abs(l0 - l1).max() < 2e-3, np.abs(l0 - l1).max()
+    snr = 10 * np.log10((p1.astype(np.float64) ** 2).sum() / max(((p1.astype(np.float64) - p0) ** 2).sum(), 1e-30))
+    assert snr >= 50.0, snr
